@@ -1,0 +1,74 @@
+"""Builds libpranetv2_b200.so in-tree with nvcc for sm_100a.
+
+No torch extension machinery: the C ABI has no torch types in it, so this is a plain
+`nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -shared` over csrc/*.cu.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+OBJDIR = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "libpranetv2_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libpranetv2_b200.so cannot be built")
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _headers():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in sources() + _headers())
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu (in parallel, only what changed) and link the shared library."""
+    if not force and not stale():
+        return LIB
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdr_t = max([os.path.getmtime(h) for h in _headers()] or [0.0])
+    objs, procs = [], []
+    for src in sources():
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            continue
+        cmd = [_nvcc()] + CFLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        if verbose and out:
+            print(f"--- {os.path.basename(src)}\n{out}")
+    r = subprocess.run([_nvcc()] + ARCH + ["--shared", "-o", LIB] + objs + ["-lcuda"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,239 @@
+"""torch.autograd wrappers over the C ABI (include/pv2.h).  PyTorch supplies device memory, the current
+stream and autograd bookkeeping; every computation below happens in libpranetv2_b200.so.
+
+There is no CPU path: tensors that are not on a CUDA device raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PV2_F32, PV2_BF16 = 0, 1
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return PV2_F32
+    if t.dtype == torch.bfloat16:
+        return PV2_BF16
+    raise TypeError(f"pranet_v2_b200 kernels take float32 or bfloat16 tensors, got {t.dtype}")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pranet_v2_b200 ops are CUDA-only (sm_100a); got a CPU tensor and there is no CPU fallback")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------------------------
+# structure loss
+# ------------------------------------------------------------------------------------------------
+class _StructureLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_fg, mask_bg, *logits):
+        lib = _lib.load()
+        K = len(logits) // 2
+        preds = [t.contiguous() for t in logits[0::2]]
+        pred_bgs = [t.contiguous() for t in logits[1::2]]
+        B, Cc, H, W = preds[0].shape
+        dt = _dt(preds[0])
+        for t in preds + pred_bgs:
+            if tuple(t.shape) != (B, Cc, H, W) or _dt(t) != dt:
+                raise ValueError("structure_loss: all logits must share shape and dtype")
+        if tuple(mask_fg.shape) != (B, Cc, H, W):
+            raise ValueError(f"structure_loss: mask shape {tuple(mask_fg.shape)} != logits shape {(B, Cc, H, W)}")
+        mask_fg = mask_fg.contiguous().float()
+        mask_bg = mask_bg.contiguous().float() if mask_bg is not None else None
+        planes = B * Cc
+        ws_bytes = lib.pv2_structure_loss_workspace_bytes(planes, H, W, K)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=mask_fg.device)
+        loss = torch.empty(K, dtype=torch.float32, device=mask_fg.device)
+        pp, keep1 = _lib.ptr_array(preds)
+        pb, keep2 = _lib.ptr_array(pred_bgs)
+        _lib.check(lib.pv2_structure_loss_fwd(pp, pb, mask_fg.data_ptr(), mask_bg.data_ptr() if mask_bg is not None else None,
+                                              K, planes, H, W, dt, loss.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+                   "pv2_structure_loss_fwd")
+        ctx.save_for_backward(mask_fg, mask_bg, ws, *preds, *pred_bgs)
+        ctx.meta = (K, planes, H, W, dt, ws_bytes)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        K, planes, H, W, dt, ws_bytes = ctx.meta
+        mask_fg, mask_bg, ws = ctx.saved_tensors[:3]
+        preds = list(ctx.saved_tensors[3:3 + K])
+        pred_bgs = list(ctx.saved_tensors[3 + K:3 + 2 * K])
+        g = grad_loss.contiguous().float()
+        dps = [torch.empty_like(p) for p in preds]
+        dqs = [torch.empty_like(p) for p in pred_bgs]
+        pp, k1 = _lib.ptr_array(preds)
+        pb, k2 = _lib.ptr_array(pred_bgs)
+        dp, k3 = _lib.ptr_array(dps)
+        dq, k4 = _lib.ptr_array(dqs)
+        _lib.check(lib.pv2_structure_loss_bwd(pp, pb, mask_fg.data_ptr(), mask_bg.data_ptr() if mask_bg is not None else None,
+                                              g.data_ptr(), dp, dq, K, planes, H, W, dt, ws.data_ptr(), ws_bytes, _stream()),
+                   "pv2_structure_loss_bwd")
+        grads = []
+        for a, b in zip(dps, dqs):
+            grads += [a, b]
+        return (None, None, *grads)
+
+
+def structure_loss_multi(pairs, mask_fg, mask_bg=None):
+    """`pairs` = [(pred, pred_bg), ...] (1..4 of them) supervised by ONE mask -> tensor of len(pairs) losses.
+    One forward launch (+finalize) and one backward launch for all scales; the 31x31 boundary weight is
+    computed once per tile instead of once per call (the reference recomputes it 4x, MyTrain_med.py:78-81)."""
+    flat = []
+    for p, q in pairs:
+        flat += [p, q]
+    _need_cuda(mask_fg, mask_bg, *flat)
+    if not 1 <= len(pairs) <= 4:
+        raise ValueError("structure_loss_multi takes 1..4 (pred, pred_bg) pairs")
+    return _StructureLossFn.apply(mask_fg, mask_bg, *flat)
+
+
+def structure_loss(pred, pred_bg, mask_fg, mask_bg=None):
+    """Drop-in for binary_seg/MyTrain_med.py:19 `structure_loss(pred, pred_bg, mask_fg, mask_bg)`.
+    mask_bg=None means 1 - mask_fg (what the reference's training loop passes, MyTrain_med.py:74) and
+    saves reading a second mask."""
+    return structure_loss_multi([(pred, pred_bg)], mask_fg, mask_bg)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# bilinear resize
+# ------------------------------------------------------------------------------------------------
+def _ratio(in_size: int, out_size: int, align_corners: bool, scale) -> float:
+    """ATen's area_pixel_compute_scale<float> (the ratio is rounded to fp32 exactly as ATen does)."""
+    if align_corners:
+        return float(np.float32(in_size - 1) / np.float32(out_size - 1)) if out_size > 1 else 0.0
+    if scale is not None and scale > 0:
+        return float(np.float32(1.0 / scale))
+    return float(np.float32(in_size) / np.float32(out_size))
+
+
+class _BilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow, rh, rw, ac):
+        lib = _lib.load()
+        x = x.contiguous()
+        B, Cc, ih, iw = x.shape
+        out = torch.empty(B, Cc, oh, ow, dtype=x.dtype, device=x.device)
+        _lib.check(lib.pv2_bilinear_fwd(x.data_ptr(), out.data_ptr(), B * Cc, ih, iw, oh, ow, rh, rw, int(ac), _dt(x), _stream()),
+                   "pv2_bilinear_fwd")
+        ctx.meta = (B, Cc, ih, iw, oh, ow, rh, rw, int(ac))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        B, Cc, ih, iw, oh, ow, rh, rw, ac = ctx.meta
+        g = g.contiguous()
+        din = torch.empty(B, Cc, ih, iw, dtype=g.dtype, device=g.device)
+        _lib.check(lib.pv2_bilinear_bwd(g.data_ptr(), din.data_ptr(), B * Cc, ih, iw, oh, ow, rh, rw, ac, _dt(g), _stream()),
+                   "pv2_bilinear_bwd")
+        return din, None, None, None, None, None
+
+
+def interpolate_bilinear(x, size=None, scale_factor=None, align_corners=False):
+    """F.interpolate(x, size=|scale_factor=, mode='bilinear', align_corners=) on the pv2 kernels
+    (binary_seg/lib/pranet.py:349-415, :93; EMCAD/lib/decoders.py:460-461)."""
+    _need_cuda(x)
+    ih, iw = x.shape[-2:]
+    if size is not None:
+        oh, ow = (size, size) if isinstance(size, int) else tuple(size)
+        sh = sw = None
+    else:
+        sh, sw = (scale_factor, scale_factor) if not isinstance(scale_factor, (tuple, list)) else scale_factor
+        oh, ow = int(np.floor(ih * sh)), int(np.floor(iw * sw))
+    rh, rw = _ratio(ih, oh, align_corners, sh), _ratio(iw, ow, align_corners, sw)
+    return _BilinearFn.apply(x, oh, ow, rh, rw, bool(align_corners))
+
+
+# ------------------------------------------------------------------------------------------------
+# DSRA fusion
+# ------------------------------------------------------------------------------------------------
+class _DsraFuseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, fg, deep_fg, deep_bg, use_softmax, rh, rw):
+        lib = _lib.load()
+        fg, deep_fg, deep_bg = fg.contiguous().float(), deep_fg.contiguous().float(), deep_bg.contiguous().float()
+        B, Cc, h, w = fg.shape
+        dh, dw = deep_fg.shape[-2:]
+        out = torch.empty_like(fg)
+        _lib.check(lib.pv2_dsra_fuse_fwd(fg.data_ptr(), deep_fg.data_ptr(), deep_bg.data_ptr(), out.data_ptr(),
+                                         B, Cc, h, w, dh, dw, rh, rw, int(use_softmax), _stream()), "pv2_dsra_fuse_fwd")
+        ctx.save_for_backward(fg, deep_fg, deep_bg)
+        ctx.meta = (B, Cc, h, w, dh, dw, rh, rw, int(use_softmax))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        fg, deep_fg, deep_bg = ctx.saved_tensors
+        B, Cc, h, w, dh, dw, rh, rw, sm = ctx.meta
+        g = g.contiguous().float()
+        dfg, dd = torch.empty_like(fg), torch.empty_like(fg)
+        _lib.check(lib.pv2_dsra_fuse_bwd(g.data_ptr(), fg.data_ptr(), deep_fg.data_ptr(), deep_bg.data_ptr(),
+                                         dfg.data_ptr(), dd.data_ptr(), B, Cc, h, w, dh, dw, rh, rw, sm, _stream()),
+                   "pv2_dsra_fuse_bwd")
+        ddeep = torch.empty_like(deep_fg)
+        _lib.check(lib.pv2_bilinear_bwd(dd.data_ptr(), ddeep.data_ptr(), B * Cc, dh, dw, h, w, rh, rw, 0, PV2_F32, _stream()),
+                   "pv2_bilinear_bwd")
+        return dfg, ddeep, -ddeep, None, None, None
+
+
+def dsra_fuse(fg, deep_fg, deep_bg, use_softmax=True, scale_factor=None):
+    """fg + fg * softmax_c(up(deep_fg) - up(deep_bg)) with the resize of the deeper maps fused in
+    (pranet.py:353-368; EMCAD/lib/decoders.py:460-477).  `scale_factor` mirrors the reference call
+    form F.interpolate(scale_factor=) (None = the size= form)."""
+    _need_cuda(fg, deep_fg, deep_bg)
+    h, w = fg.shape[-2:]
+    dh, dw = deep_fg.shape[-2:]
+    if scale_factor is not None and (int(np.floor(dh * scale_factor)), int(np.floor(dw * scale_factor))) != (h, w):
+        raise ValueError(f"dsra_fuse: {dh}x{dw} * {scale_factor} does not give {h}x{w}")
+    return _DsraFuseFn.apply(fg, deep_fg, deep_bg, bool(use_softmax),
+                             _ratio(dh, h, False, scale_factor), _ratio(dw, w, False, scale_factor))
+
+
+# ------------------------------------------------------------------------------------------------
+# V1 reverse attention
+# ------------------------------------------------------------------------------------------------
+class _RaV1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, crop):
+        lib = _lib.load()
+        x, crop = x.contiguous(), crop.contiguous().float()
+        B, Cc, h, w = x.shape
+        y = torch.empty_like(x)
+        _lib.check(lib.pv2_ra_v1_scale_fwd(x.data_ptr(), crop.data_ptr(), y.data_ptr(), B, Cc, h * w, _dt(x), _stream()),
+                   "pv2_ra_v1_scale_fwd")
+        ctx.save_for_backward(x, crop)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, crop = ctx.saved_tensors
+        B, Cc, h, w = x.shape
+        g = g.contiguous().to(x.dtype)
+        dx, dcrop = torch.empty_like(x), torch.empty_like(crop)
+        _lib.check(lib.pv2_ra_v1_scale_bwd(g.data_ptr(), x.data_ptr(), crop.data_ptr(), dx.data_ptr(), dcrop.data_ptr(),
+                                           B, Cc, h * w, _dt(x), _stream()), "pv2_ra_v1_scale_bwd")
+        return dx, dcrop
+
+
+def ra_v1_scale(x, crop):
+    """(1 - sigmoid(crop)).expand(-1, C, -1, -1) * x  (binary_seg/lib/PraNet_Res2Net.py:153-154)."""
+    _need_cuda(x, crop)
+    if crop.shape[1] != 1 or crop.shape[0] != x.shape[0] or crop.shape[-2:] != x.shape[-2:]:
+        raise ValueError(f"ra_v1_scale: crop {tuple(crop.shape)} does not broadcast over x {tuple(x.shape)}")
+    return _RaV1Fn.apply(x, crop)

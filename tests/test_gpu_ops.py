@@ -1,0 +1,164 @@
+"""Parity of the memory-bound kernels (through the C ABI) against the CPU oracle and the golden
+vectors frozen from the reference.  Tolerances: fp32 loss 1e-4 relative (north_star), gradients
+1e-3 of their max-abs; bf16 logits 2e-2."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import pranet_v2_b200 as P
+from oracle import dsra_oracle as O
+from oracle import golden_cases as G
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _sub(t, stride):
+    t = t.detach().float().cpu()
+    return (t[:, :, ::stride, ::stride] if stride > 1 else t).numpy()
+
+
+@pytest.mark.parametrize("name", list(G.STRUCTURE_LOSS_CASES))
+@pytest.mark.parametrize("pass_mask_bg", [False, True])
+def test_structure_loss_golden(name, pass_mask_bg):
+    g = G.load(name)
+    stride = G.STRUCTURE_LOSS_CASES[name][5]
+    pred, pred_bg, m, mb = [t.to(DEV) for t in G.structure_loss_inputs(name)]
+    pred.requires_grad_(True)
+    pred_bg.requires_grad_(True)
+    loss = P.structure_loss(pred, pred_bg, m, mb if pass_mask_bg else None)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    for got, ref in ((pred.grad, g["dpred"]), (pred_bg.grad, g["dpred_bg"])):
+        np.testing.assert_allclose(_sub(got, stride), ref, rtol=0, atol=1e-3 * np.abs(ref).max() + 1e-12)
+
+
+@pytest.mark.parametrize("shape,kind", [((16, 1, 352, 352), "hard"), ((4, 1, 256, 256), "soft"), ((2, 1, 448, 448), "soft"),
+                                         ((3, 2, 100, 75), "hard"), ((1, 1, 704, 704), "hard")])
+def test_structure_loss_vs_oracle_full_size(shape, kind):
+    B, C, H, W = shape
+    pred, pred_bg = synth.logits(shape, 5, "p"), synth.logits(shape, 5, "q")
+    m = (synth.ellipse_masks(B * C, H, W, 5) if kind == "hard" else synth.soft_masks(B * C, H, W, 5)).view(shape)
+    ref_p, ref_q = pred.clone().requires_grad_(True), pred_bg.clone().requires_grad_(True)
+    ref = O.structure_loss(ref_p, ref_q, m, 1 - m)
+    ref.backward()
+    p, q = pred.to(DEV).requires_grad_(True), pred_bg.to(DEV).requires_grad_(True)
+    loss = P.structure_loss(p, q, m.to(DEV), None)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    for got, want in ((p.grad, ref_p.grad), (q.grad, ref_q.grad)):
+        assert (got.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item()
+
+
+def test_structure_loss_multi_and_bf16():
+    shape = (4, 1, 352, 352)
+    m = synth.ellipse_masks(4, 352, 352, 9).view(shape)
+    pairs = [(synth.logits(shape, 9, f"p{k}"), synth.logits(shape, 9, f"q{k}")) for k in range(4)]
+    ref = torch.stack([O.structure_loss(p, q, m, 1 - m) for p, q in pairs])
+    dev_pairs = [(p.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)) for p, q in pairs]
+    losses = P.structure_loss_multi(dev_pairs, m.to(DEV))
+    assert torch.allclose(losses.cpu(), ref, rtol=1e-4, atol=0)
+    # x4 launch == 4 single launches, bit for bit (same tiles, same reduction order)
+    singles = torch.stack([P.structure_loss(p, q, m.to(DEV)) for p, q in dev_pairs])
+    assert torch.equal(singles, losses)
+    w = torch.tensor([1.0, 0.5, 2.0, 1.5], device=DEV)
+    (losses * w).sum().backward()
+    rp = [(p.clone().requires_grad_(True), q.clone().requires_grad_(True)) for p, q in pairs]
+    (torch.stack([O.structure_loss(p, q, m, 1 - m) for p, q in rp]) * w.cpu()).sum().backward()
+    for (p, q), (a, b) in zip(dev_pairs, rp):
+        assert (p.grad.cpu() - a.grad).abs().max() <= 1e-3 * a.grad.abs().max()
+        assert (q.grad.cpu() - b.grad).abs().max() <= 1e-3 * b.grad.abs().max()
+    # bf16 logits: compare against the oracle evaluated on the bf16-rounded logits (tolerance 2e-2 stated)
+    bp = [(p.bfloat16(), q.bfloat16()) for p, q in pairs]
+    refb = torch.stack([O.structure_loss(p.float(), q.float(), m, 1 - m) for p, q in bp])
+    db = [(p.to(DEV).requires_grad_(True), q.to(DEV).requires_grad_(True)) for p, q in bp]
+    lb = P.structure_loss_multi(db, m.to(DEV))
+    assert torch.allclose(lb.cpu(), refb, rtol=1e-4, atol=0)
+    lb.sum().backward()
+    assert db[0][0].grad.dtype == torch.bfloat16
+    rr = bp[0][0].float().requires_grad_(True)
+    O.structure_loss(rr, bp[0][1].float(), m, 1 - m).backward()
+    assert (db[0][0].grad.float().cpu() - rr.grad).abs().max() <= 2e-2 * rr.grad.abs().max()
+
+
+def test_structure_loss_errors():
+    x = torch.zeros(1, 1, 8, 8, device=DEV)
+    with pytest.raises(ValueError):
+        P.structure_loss(x, x, torch.zeros(1, 1, 8, 9, device=DEV))
+    with pytest.raises(TypeError):
+        P.structure_loss(x.half(), x.half(), x)
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((2, 1, 44, 44), dict(scale_factor=8)), ((2, 1, 11, 11), dict(scale_factor=32)), ((2, 3, 22, 22), dict(scale_factor=16)),
+    ((2, 1, 44, 44), dict(scale_factor=0.25)), ((2, 1, 11, 11), dict(scale_factor=2)), ((3, 32, 11, 11), dict(scale_factor=2, align_corners=True)),
+    ((2, 9, 7, 7), dict(size=(14, 14))), ((1, 4, 13, 9), dict(size=(31, 20))), ((2, 9, 56, 56), dict(scale_factor=4)),
+    ((1, 2, 5, 7), dict(scale_factor=3)), ((1, 1, 1, 1), dict(scale_factor=4)), ((1, 1, 64, 64), dict(scale_factor=4.0)),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bilinear_fwd_bwd(shape, kw, dtype):
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1))
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    ref = F.interpolate(xr, mode="bilinear", **kw)
+    gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2))
+    if dtype == torch.bfloat16:
+        gout = gout.bfloat16().float()
+    ref.backward(gout)
+    xd = x.to(DEV, dtype).requires_grad_(True)
+    out = P.interpolate_bilinear(xd, **kw)
+    assert out.shape == ref.shape and out.dtype == dtype
+    out.backward(gout.to(DEV, dtype))
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert (out.float().cpu() - ref).abs().max() <= tol * max(1.0, ref.abs().max().item())
+    assert (xd.grad.float().cpu() - xr.grad).abs().max() <= tol * max(1.0, xr.grad.abs().max().item())
+    if dtype == torch.float32:   # the explicit float64 numpy restatement agrees too
+        sf = kw.get("scale_factor")
+        np.testing.assert_allclose(out.cpu().numpy(), O.bilinear_np(x.numpy(), ref.shape[2], ref.shape[3], kw.get("align_corners", False), sf),
+                                   rtol=1e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("B,C,h,scale,softmax", [(2, 1, 11, 0.25, True), (2, 3, 22, 2, True), (2, 9, 14, 2, True), (1, 4, 16, 2, False),
+                                                   (2, 1, 44, 2, False), (1, 9, 56, 2, True)])
+def test_dsra_fuse(B, C, h, scale, softmax):
+    g = torch.Generator().manual_seed(3)
+    dh = int(round(h / scale))
+    fg = torch.randn(B, C, h, h, generator=g)
+    dfg, dbg = torch.randn(B, C, dh, dh, generator=g), torch.randn(B, C, dh, dh, generator=g)
+    gout = torch.randn(B, C, h, h, generator=g)
+    r = [t.clone().requires_grad_(True) for t in (fg, dfg, dbg)]
+    ref = O.dsra_fuse(r[0], O.interp(r[1], scale), O.interp(r[2], scale), softmax)
+    ref.backward(gout)
+    d = [t.to(DEV).requires_grad_(True) for t in (fg, dfg, dbg)]
+    out = P.dsra_fuse(d[0], d[1], d[2], softmax, scale_factor=scale)
+    out.backward(gout.to(DEV))
+    assert (out.cpu() - ref).abs().max() <= 1e-5 * max(1.0, ref.abs().max().item())
+    for a, b in zip(d, r):
+        assert (a.grad.cpu() - b.grad).abs().max() <= 1e-5 * max(1.0, b.grad.abs().max().item())
+    if C == 1 and softmax:   # softmax over one channel == 1 -> out = 2*fg, ZERO grad to the deeper maps
+        assert torch.equal(out, 2 * d[0].detach())
+        assert d[1].grad.abs().max().item() == 0.0 and d[2].grad.abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,C,h", [(2, 2048, 11), (2, 1024, 22), (1, 512, 44), (1, 7, 5)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ra_v1_scale(B, C, h, dtype):
+    g = torch.Generator().manual_seed(4)
+    x = torch.relu(torch.randn(B, C, h, h, generator=g))
+    crop = 2 * torch.randn(B, 1, h, h, generator=g)
+    gout = torch.randn(B, C, h, h, generator=g)
+    if dtype == torch.bfloat16:
+        x, gout = x.bfloat16().float(), gout.bfloat16().float()
+    xr, cr = x.clone().requires_grad_(True), crop.clone().requires_grad_(True)
+    ref = O.ra_v1_scale(cr, xr)
+    ref.backward(gout)
+    xd, cd = x.to(DEV, dtype).requires_grad_(True), crop.to(DEV).requires_grad_(True)
+    out = P.ra_v1_scale(xd, cd)
+    out.backward(gout.to(DEV, dtype))
+    tol = 2e-5 if dtype == torch.float32 else 1e-2
+    assert (out.float().cpu() - ref).abs().max() <= tol * max(1.0, ref.abs().max().item())
+    assert (xd.grad.float().cpu() - xr.grad).abs().max() <= tol * max(1.0, xr.grad.abs().max().item())
+    assert (cd.grad.cpu() - cr.grad).abs().max() <= tol * max(1.0, cr.grad.abs().max().item())
