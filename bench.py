@@ -154,7 +154,7 @@ def main():
     import torch.distributed as dist
     import pranet_v2_b200 as P
     from pranet_v2_b200.train import TrainStep
-    from oracle import synth   # seeded synthetic inputs only (no oracle compute on this arm)
+    from pranet_v2_b200 import synthetic as synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -256,7 +256,7 @@ def roofline_structure_loss(P, dev, B, S, iters=24):
     """structure_loss x4 backward: the largest-traffic pv2 launch of the step, timed live with CUDA events
     around back-to-back C-ABI launches on torch's current stream (inputs rotate over sets larger than L2).
     Algorithmic bytes / launch = P * (4 [mask] + 4 scales * (8 read + 8 written)) fp32, P = B*S*S."""
-    from oracle import synth
+    from pranet_v2_b200 import synthetic as synth
     lib = P._lib.load()
     st = torch.cuda.current_stream().cuda_stream
     shape = (B, 1, S, S)

@@ -13,7 +13,7 @@
  *   - `stream` is a cudaStream_t passed as void*; every launch goes to that stream, nothing
  *     synchronises, allocates or frees: the caller owns all memory including workspaces;
  *   - return value 0 = ok, anything else = error; pv2_last_error() gives the message (thread local);
- *   - dtype codes: PV2_F32 = 0, PV2_BF16 = 1.
+ *   - dtype codes: PV2_F32 = 0, PV2_BF16 = 1, PV2_TF32 = 2 (operand kind only).
  */
 #ifndef PV2_H_
 #define PV2_H_
@@ -27,6 +27,7 @@ extern "C" {
 
 #define PV2_F32 0
 #define PV2_BF16 1
+#define PV2_TF32 2   /* fp32 storage read by the tensor cores as tf32; optionally split into hi + lo planes */
 
 #define PV2_MAX_SCALES 4
 
@@ -99,6 +100,75 @@ int pv2_dsra_fuse_bwd(const float* dout, const float* fg, const float* deep_fg, 
 int pv2_ra_v1_scale_fwd(const void* x, const float* crop, void* y, int B, int C, int hw, int dtype, void* stream);
 int pv2_ra_v1_scale_bwd(const void* dy, const void* x, const float* crop, void* dx, float* dcrop,
                         int B, int C, int hw, int dtype, void* stream);
+
+/* =============================================================================================
+ * Conv engine (tcgen05 / TMEM / TMA) -- nn.Conv2d + nn.BatchNorm2d + F.relu of BasicConv2d
+ * (binary_seg/lib/pranet.py:31-43 and its callers :75-82, :109-123, :357-363, :378-383, :400-405;
+ * multiclass heads EMCAD/lib/decoders.py:434-444, MERIT/lib/decoders.py:298-322, MIST/lib/MIST.py:403-412).
+ *
+ * "Operand format": NHWC, channels padded to a multiple of 8 (bf16) / 4 (tf32); `kind` = PV2_BF16 (one plane) or
+ * PV2_TF32 (fp32 storage; with nterms = 3 two planes hi, lo `*_plane_stride` ELEMENTS apart and the GEMM runs
+ * hi*hi + lo*hi + hi*lo).  Weights in operand format are [Cout][tap][Cin_p] (pv2_weight_pack).
+ * "Raw": fp32 rows [pixel][ld].  All convolutions are stride 1 with same padding (pad = dil*(k-1)/2).
+ * ============================================================================================= */
+
+/* out_mode 0: raw fp32 out[split][N*H*W][ldo] (split-K partial slabs, summed by pv2_bn_stats / the consumers);
+ * out_mode 1: fp32 NCHW out[N][Cout][H][W] + bias (bias may be NULL), splits must be 1.
+ * Also computes dgrad when given the mode-1 packed weights (Cin_p := padded Cout, Cout := Cin). */
+int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms);
+int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,
+                 int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int dil_h, int dil_w,
+                 int out_mode, float* out, int ldo, int splits, const float* bias, void* stream);
+/* dW partials out[split][Cout][KH*KW][Cin_p] = sum over the split's pixels of dY[p][co] * X[p + tap shift][ci] */
+int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind);
+int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const void* x, long long x_plane_stride, int kind, int nterms,
+                   int N, int H, int W, int Cin_p, int Cout_p, int Cout, int KH, int KW, int dil_h, int dil_w,
+                   float* out, int splits, void* stream);
+/* OIHW fp32 -> operand weights.  mode 0 (fprop): out[o_off+co][tap][i_off+ci]; mode 1 (dgrad): out[o_off+ci][flipped tap][i_off+co];
+ * i_ld = padded inner channel count of the (possibly horizontally fused) destination. */
+int pv2_weight_pack(const float* w, void* out, long long plane_stride, int nplanes, int kind, int Cout, int Cin, int KH, int KW,
+                    int mode, int i_ld, int i_off, int o_off, void* stream);
+int pv2_wgrad_unpack(const float* part, long long split_stride, int splits, float* dw, int Cout, int Cin, int KH, int KW,
+                     int Cin_p, int co_off, void* stream);
+/* NCHW (x_dtype PV2_F32 | PV2_BF16) -> operand NHWC slice [N*HW][ld] at channel c_off; and summed raw slabs -> NCHW */
+int pv2_pack_nchw(const void* x, int x_dtype, void* out, long long plane_stride, int nplanes, int kind, int N, int C, int HW,
+                  int ld, int c_off, void* stream);
+/* channels_last = 1: dx is stored NHWC (a torch channels_last tensor), no transpose */
+int pv2_unpack_to_nchw(const float* const* slabs, const int* lds, const int* offs, int nslabs, void* dx, int dx_dtype,
+                       int N, int C, int HW, int channels_last, void* stream);
+/* BatchNorm batch statistics of raw conv output (sums the split-K slabs into slab 0 first); saves mean / invstd,
+ * emits scale = gamma*invstd and shift = beta - mean*scale, updates running stats like nn.BatchNorm2d. */
+size_t pv2_bn_workspace_floats(long long M, int C);
+int pv2_bn_stats(float* y, long long slab_stride, int nslabs, long long M, int C, int ld, const float* gamma, const float* beta,
+                 float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                 float* mean_out, float* invstd_out, float* scale, float* shift, float* workspace, void* stream);
+int pv2_bn_eval_affine(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                       float* scale, float* shift, void* stream);
+/* a1 = y1*s1+b1; [a2 = y2*s2+b2; v = a1 (+|*) a2 (combine 1|2)]; [v *= mult (operand format)]; [relu]
+ * y_i may still be ns_i split-K slabs ss_i elements apart (summed on load).
+ * -> operand NHWC slice (out_nchw = 0) or fp32 NCHW (out_nchw = 1).  Covers BN(+ReLU) (pranet.py:41-42,358),
+ * relu(x_cat + conv_res) (pranet.py:82), the partial decoder's products (pranet.py:111-113) and biased heads. */
+int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long long ss1, const float* s1, const float* b1,
+                  const float* y2, int ld2, int off2, int ns2, long long ss2,
+                  const float* s2, const float* b2, int combine, const void* mult, long long mult_plane, int mult_planes,
+                  int mult_ld, int mult_off, int relu, long long M, int C, int HW, void* out, long long out_plane,
+                  int out_planes, int out_ld, int out_off, int out_nchw, int kind, void* stream);
+/* backward of pv2_act_apply (+ training-mode BN when bn_train = 1): dz comes as <= 8 summed raw slabs or one NCHW
+ * tensor; writes dy1 (dy2) in operand format for the dgrad/wgrad GEMMs, d(mult) raw, dgamma/dbeta. */
+int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long long ss1, const float* s1, const float* b1,
+                   const float* y2, int ld2, int off2, int ns2, long long ss2,
+                   const float* s2, const float* b2, int combine, const void* mult, long long mult_plane, int mult_planes,
+                   int mult_ld, int mult_off, int relu, long long M, int C, int HW,
+                   const float* const* dz_slabs, const int* dz_lds, const int* dz_offs, int dz_n, const float* dz_nchw,
+                   const float* mean1, const float* inv1, const float* mean2, const float* inv2, int bn_train,
+                   float* dmult, int dmult_ld, void* dy1, long long dy1_plane, int dy1_planes, int dy1_ld,
+                   void* dy2, long long dy2_plane, int dy2_planes, int dy2_ld,
+                   float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace, int kind, void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (pranet.py:93) on operand tensors; backward raw -> raw */
+int pv2_up2_nhwc_fwd(const void* in, long long in_plane, int in_planes, int in_ld, int in_off, void* out, long long out_plane,
+                     int out_planes, int out_ld, int out_off, int N, int H, int W, int C, int kind, void* stream);
+int pv2_up2_nhwc_bwd(const float* const* slabs, const int* lds, const int* offs, int nslabs, float* din, int din_ld,
+                     int N, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

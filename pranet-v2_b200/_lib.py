@@ -13,7 +13,10 @@ from . import build as _build
 _lib = None
 
 c_void_pp = C.POINTER(C.c_void_p)
-_i, _f, _p, _sz = C.c_int, C.c_float, C.c_void_p, C.c_size_t
+_i, _f, _p, _sz, _ll = C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_longlong
+_ip = C.POINTER(C.c_int)
+# the 24 leading arguments shared by pv2_act_apply / pv2_bn_act_bwd (the forward description)
+_APPLY = [_p, _i, _i, _i, _ll, _p, _p, _p, _i, _i, _i, _ll, _p, _p, _i, _p, _ll, _i, _i, _i, _i, _ll, _i, _i]
 
 # name -> (restype, argtypes); mirrors include/pv2.h one to one
 _SIGS = {
@@ -29,6 +32,22 @@ _SIGS = {
     "pv2_dsra_fuse_bwd": (_i, [_p] * 6 + [_i] * 6 + [_f, _f, _i, _p]),
     "pv2_ra_v1_scale_fwd": (_i, [_p] * 3 + [_i] * 4 + [_p]),
     "pv2_ra_v1_scale_bwd": (_i, [_p] * 5 + [_i] * 4 + [_p]),
+    # conv engine
+    "pv2_conv_splits_hint": (_i, [_i] * 9),
+    "pv2_conv_fwd": (_i, [_p, _ll, _p, _ll, _i, _i] + [_i] * 9 + [_i, _p, _i, _i, _p, _p]),
+    "pv2_conv_wgrad_splits_hint": (_i, [_i] * 8),
+    "pv2_conv_wgrad": (_i, [_p, _ll, _p, _ll, _i, _i] + [_i] * 10 + [_p, _i, _p]),
+    "pv2_weight_pack": (_i, [_p, _p, _ll, _i, _i] + [_i] * 8 + [_p]),
+    "pv2_wgrad_unpack": (_i, [_p, _ll, _i, _p] + [_i] * 6 + [_p]),
+    "pv2_pack_nchw": (_i, [_p, _i, _p, _ll, _i, _i] + [_i] * 5 + [_p]),
+    "pv2_unpack_to_nchw": (_i, [c_void_pp, _ip, _ip, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "pv2_bn_workspace_floats": (_sz, [_ll, _i]),
+    "pv2_bn_stats": (_i, [_p, _ll, _i, _ll, _i, _i, _p, _p, _f, _f] + [_p] * 8 + [_p]),
+    "pv2_bn_eval_affine": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _p]),
+    "pv2_act_apply": (_i, _APPLY + [_p, _ll, _i, _i, _i, _i, _i, _p]),
+    "pv2_bn_act_bwd": (_i, _APPLY + [c_void_pp, _ip, _ip, _i, _p] + [_p] * 4 + [_i, _p, _i] + [_p, _ll, _i, _i] * 2 + [_p] * 5 + [_i, _p]),
+    "pv2_up2_nhwc_fwd": (_i, [_p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i] + [_i] * 5 + [_p]),
+    "pv2_up2_nhwc_bwd": (_i, [c_void_pp, _ip, _ip, _i, _p, _i] + [_i] * 4 + [_p]),
 }
 
 
@@ -76,6 +95,11 @@ def check(status: int, what: str):
 
 def launch_count() -> int:
     return int(load().pv2_launch_count())
+
+
+def int_array(vals):
+    arr = (C.c_int * len(vals))(*[int(v) for v in vals])
+    return C.cast(arr, _ip), arr
 
 
 def ptr_array(tensors):

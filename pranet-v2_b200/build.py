@@ -62,7 +62,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out:
             print(f"--- {os.path.basename(src)}\n{out}")
-    r = subprocess.run([_nvcc()] + ARCH + ["--shared", "-o", LIB] + objs + ["-lcuda"],
+    r = subprocess.run([_nvcc()] + ARCH + ["--shared", "-o", LIB] + objs,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -1,0 +1,484 @@
+// Implicit-GEMM convolutions of the DSRA head on the 5th-gen tensor cores (tcgen05 + TMEM), fed by TMA.
+//
+// Replaces every nn.Conv2d of the head (binary_seg/lib/pranet.py:34-36 via BasicConv2d, and the biased 1x1
+// heads pranet.py:103-104): 1x1, 3x3, 5x5, 1xk, kx1 and dilated 3x3, all stride 1 with "same" padding.
+//
+// Data layout ("operand format"): activations NHWC with the channel count padded to a multiple of 8 (bf16) / 4
+// (tf32), weights [Cout][tap][Cin_p].  GEMM view: M = pixels, N = Cout, K = taps x Cin.
+//   * an M tile is a TWb x THb patch (TWb*THb = 128) of one image; for filter tap (kh, kw) the A operand is the
+//     SAME patch shifted by (kh*dil - pad, kw*dil - pad): one 4-D TMA box load per (tap, 64-channel chunk),
+//     with out-of-image elements zero-filled by the TMA unit -- the convolution's zero padding costs nothing
+//     and no im2col buffer exists anywhere;
+//   * B (weights) is a 3-D TMA box [BN rows][64 ch] of tap `tap`;
+//   * both land in 128-byte-swizzled shared memory, which is exactly the K-major UMMA canonical layout;
+//   * one elected thread issues tcgen05.mma (M = 128, N = BN <= 256, K = 16 bf16 / 8 tf32), the fp32 accumulator
+//     lives in TMEM; a 4-stage mbarrier ring overlaps TMA with MMA; 4 epilogue warps drain TMEM with tcgen05.ld.
+//   * fp32 parity mode ("tf32x3"): every fp32 operand is stored as hi + lo tf32 planes and the K loop runs the
+//     three products hi*hi + lo*hi + hi*lo into the same accumulator, which restores ~fp32 accuracy on the
+//     tensor cores (single-pass TF32 misses the 1e-3 logit tolerance through ~25 stacked conv+BN layers).
+//   * split-K over grid.z when M*N tiles cannot fill 148 SMs (the 11x11 5x5 256->256 layers: K = 6400).
+//
+// The same kernel computes dgrad (weights repacked flipped/transposed by pv2_weight_pack).  wgrad is the second
+// kernel below: D[co][ci] = sum_pixels dY[p][co] * X[p + shift][ci] with both operands MN-major straight out of
+// the same NHWC boxes.
+#include <cudaTypedefs.h>
+
+#include "pv2_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace pv2 {
+namespace {
+
+using namespace ptx;
+
+constexpr int BM = 128;                 // pixel rows per tile = UMMA M
+constexpr int ROW_BYTES = 128;          // one swizzle row: 64 bf16 or 32 tf32 channels
+constexpr int A_BYTES = BM * ROW_BYTES; // 16 KB
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+struct ConvArgs {
+    int H, W, Cout;
+    int KW, taps, dil_h, dil_w, pad_h, pad_w;
+    int TWb, THb, tiles_x, tiles_y;
+    int kc_per_tap, iters_total, iters_per_split;
+    int BN;                 // N tile (multiple of 16, <= 256)
+    uint32_t tmem_cols;     // power of two >= max(32, BN)
+    int out_mode;           // 0: raw fp32 [split][pixel][ldo]   1: NCHW fp32 + bias
+    float* out;
+    long long split_stride; // elements between split slabs (mode 0)
+    int ldo;
+    const float* bias;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs a) {
+    constexpr int KC = (KIND == 0) ? 64 : 32;   // channels per 128-byte row
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.BN * ROW_BYTES;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int n_img = blockIdx.x / tiles_per_img, trem = blockIdx.x % tiles_per_img;
+    const int y0 = (trem / a.tiles_x) * a.THb, x0 = (trem % a.tiles_x) * a.TWb;
+    const int n0 = blockIdx.y * a.BN;
+    const int it0 = blockIdx.z * a.iters_per_split;
+    const int it1 = min(a.iters_total, it0 + a.iters_per_split);
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA0); prefetch_tmap(&tmB0);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        const int per_term = a.taps * a.kc_per_tap;
+        for (int it = it0; it < it1; ++it) {
+            const int s = (it - it0) % STAGES;
+            const uint32_t ph = ((it - it0) / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int term = it / per_term, rem = it - term * per_term;
+            const int tap = rem / a.kc_per_tap, kc = rem - tap * a.kc_per_tap;
+            const int kh = tap / a.KW, kw = tap - kh * a.KW;
+            mbar_expect_tx(&full_bar[s], (uint32_t)(A_BYTES + b_bytes));
+            // tf32x3 terms: (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
+            tma_load_4d(sA + s * A_BYTES, term == 1 ? &tmA1 : &tmA0, &full_bar[s], kc * KC,
+                        x0 + kw * a.dil_w - a.pad_w, y0 + kh * a.dil_h - a.pad_h, n_img);
+            tma_load_3d(sB + (size_t)s * b_bytes, term == 2 ? &tmB1 : &tmB0, &full_bar[s], kc * KC, tap, n0);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = instr_desc(KIND == 0 ? 1 : 2, 0, 0, BM, a.BN);
+        for (int it = it0; it < it1; ++it) {
+            const int s = (it - it0) % STAGES;
+            const uint32_t ph = ((it - it0) / STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + (size_t)s * b_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // 4 x (UMMA_K = 32 bytes of K) per 128-byte row
+                umma<KIND>(tmem_base, smem_desc_sw128(a_addr + k * 32, 16, 1024), smem_desc_sw128(b_addr + k * 32, 16, 1024),
+                           idesc, (it > it0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&acc_bar);            // accumulator complete
+    } else if (warp >= 2) {
+        // ---------------- epilogue: TMEM -> registers -> global ----------------
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;                  // tile row = pixel within the patch
+        const int ty = r / a.TWb, tx = r - ty * a.TWb;
+        const int y = y0 + ty, x = x0 + tx;
+        const bool valid = (y < a.H) && (x < a.W);
+        const long long pix = ((long long)n_img * a.H + y) * a.W + x;
+        for (int c0 = 0; c0 < a.BN; c0 += 32) {
+            uint32_t v[32];
+            if (a.BN - c0 >= 32) {
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {   // BN is a multiple of 16: a 16-column tail
+                uint32_t t[16];
+                tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, t);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { v[j] = t[j]; v[16 + j] = 0u; }
+            }
+            tmem_ld_wait();
+            if (!valid) continue;
+            if (a.out_mode == 0) {
+                float* dst = a.out + (long long)blockIdx.z * a.split_stride + pix * a.ldo + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n0 + c0 + j + 3 < a.ldo)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = n0 + c0 + j;
+                    if (co < a.Cout)
+                        a.out[(((long long)n_img * a.Cout + co) * a.H + y) * a.W + x] = __uint_as_float(v[j]) + (a.bias ? a.bias[co] : 0.0f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// wgrad: per filter tap, dW[co][ci] = sum over pixels dY[p][co] * X[p + shift(tap)][ci].
+// CTA = (tap, (co tile, ci tile), pixel split).  A = dY patch, B = shifted X patch, both [128 pixels][128 B of
+// channels] boxes -> MN-major UMMA operands (K = pixels).  M = 128 output channels (rows beyond Cout are TMA
+// zero fill), N = BNW input channels.
+// ------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+    int H, W, Cout, Cin_p;
+    int KW, taps, dil_h, dil_w, pad_h, pad_w;
+    int TWb, THb, tiles_x, tiles_y, tiles_total, tiles_per_split;
+    int nterms;
+    int BN;                 // ci tile (multiple of KC, <= 256)
+    int ci_tiles;
+    uint32_t tmem_cols;
+    float* out;             // [split][Cout][taps][Cin_p]
+    long long split_stride;
+};
+
+// stage = (dY boxes + X boxes) x 16 KB: bf16 (2 + 2) x 16 KB x 3 stages, tf32 (4 + 2) x 16 KB x 2 stages = 192 KB
+template <int KIND> struct WgradCfg { static constexpr int STAGES_ = KIND == 0 ? 3 : 2; static constexpr int BN_MAX = KIND == 0 ? 128 : 64; };
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
+                  const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1, const WgradArgs a) {
+    constexpr int KC = (KIND == 0) ? 64 : 32;
+    constexpr int KSTEP_ROWS = (KIND == 0) ? 16 : 8;      // pixels per MMA (UMMA_K)
+    constexpr int A_BOXES = BM / KC;                       // dY boxes per stage (128 output channels)
+    constexpr int WSTAGES = WgradCfg<KIND>::STAGES_;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_boxes = a.BN / KC;
+    const int stage_bytes = (A_BOXES + b_boxes) * A_BYTES;
+    __shared__ __align__(8) uint64_t full_bar[WSTAGES], empty_bar[WSTAGES], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tap = blockIdx.x, kh = tap / a.KW, kw = tap - kh * a.KW;
+    const int co0 = (blockIdx.y / a.ci_tiles) * BM, ci0 = (blockIdx.y % a.ci_tiles) * a.BN;
+    const int t0 = blockIdx.z * a.tiles_per_split, t1 = min(a.tiles_total, t0 + a.tiles_per_split);
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+    const int n_iters = (t1 - t0) * a.nterms;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmG0); prefetch_tmap(&tmX0);
+        for (int s = 0; s < WSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < n_iters; ++i) {
+            const int s = i % WSTAGES;
+            const uint32_t ph = (i / WSTAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            const int t = t0 + i / a.nterms, term = i % a.nterms;
+            const int n_img = t / tiles_per_img, trem = t % tiles_per_img;
+            const int y0 = (trem / a.tiles_x) * a.THb, x0 = (trem % a.tiles_x) * a.TWb;
+            uint8_t* base = smem + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+            const CUtensorMap* mg = (term == 1) ? &tmG1 : &tmG0;   // (G_hi,X_hi) (G_lo,X_hi) (G_hi,X_lo)
+            const CUtensorMap* mx = (term == 2) ? &tmX1 : &tmX0;
+            for (int j = 0; j < A_BOXES; ++j) tma_load_4d(base + j * A_BYTES, mg, &full_bar[s], co0 + j * KC, x0, y0, n_img);
+            for (int j = 0; j < b_boxes; ++j)
+                tma_load_4d(base + (A_BOXES + j) * A_BYTES, mx, &full_bar[s], ci0 + j * KC,
+                            x0 + kw * a.dil_w - a.pad_w, y0 + kh * a.dil_h - a.pad_h, n_img);
+        }
+    } else if (warp == 1 && lane == 0) {
+        const uint32_t idesc = instr_desc(KIND == 0 ? 1 : 2, 1, 1, BM, a.BN);
+        for (int i = 0; i < n_iters; ++i) {
+            const int s = i % WSTAGES;
+            const uint32_t ph = (i / WSTAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + A_BOXES * A_BYTES;
+#pragma unroll 4
+            for (int k = 0; k < BM / KSTEP_ROWS; ++k) {
+                const uint32_t off = (uint32_t)k * KSTEP_ROWS * ROW_BYTES;
+                if constexpr (KIND == 0)
+                    umma<KIND>(tmem_base, smem_desc_sw128(a_addr + off, A_BYTES, 1024), smem_desc_sw128(b_addr + off, A_BYTES, 1024),
+                               idesc, (i > 0 || k > 0) ? 1u : 0u);
+                else   // 32-bit MN-major: 32-byte-atom swizzle, 4-row core groups
+                    umma<KIND>(tmem_base, smem_desc_sw128_base32(a_addr + off, A_BYTES, 512), smem_desc_sw128_base32(b_addr + off, A_BYTES, 512),
+                               idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_bar);
+    } else if (warp >= 2) {
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        for (int c0 = 0; c0 < a.BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (co >= a.Cout) continue;
+            float* dst = a.out + (long long)blockIdx.z * a.split_stride + ((long long)co * a.taps + tap) * a.Cin_p + ci0 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (ci0 + c0 + j + 3 < a.Cin_p)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }
+    return fn;
+}
+
+// NHWC activation map: dims (C, W, H, N), box (KC, TWb, THb, 1), 128B swizzle, zero OOB fill
+int make_act_map(CUtensorMap* m, const void* base, int kind, int Cp, int W, int H, int N, int TWb, int THb, bool atom32 = false) {
+    auto enc = get_encode();
+    PV2_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    const size_t es = kind == 0 ? 2 : 4;
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cp * es, (cuuint64_t)W * Cp * es, (cuuint64_t)H * W * Cp * es};
+    cuuint32_t box[4] = {(cuuint32_t)(kind == 0 ? 64 : 32), (cuuint32_t)TWb, (cuuint32_t)THb, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PV2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation C=%d W=%d H=%d N=%d box %dx%d) failed: %d", Cp, W, H, N, TWb, THb, (int)r);
+    return 0;
+}
+
+// weight map: dims (Cin_p, taps, Cout), box (KC, 1, BN)
+int make_w_map(CUtensorMap* m, const void* base, int kind, int Cin_p, int taps, int Cout, int BN) {
+    auto enc = get_encode();
+    PV2_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    const size_t es = kind == 0 ? 2 : 4;
+    cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)taps, (cuuint64_t)Cout};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin_p * es, (cuuint64_t)taps * Cin_p * es};
+    cuuint32_t box[3] = {(cuuint32_t)(kind == 0 ? 64 : 32), 1, (cuuint32_t)BN};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PV2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights Cin=%d taps=%d Cout=%d BN=%d) failed: %d", Cin_p, taps, Cout, BN, (int)r);
+    return 0;
+}
+
+void pick_patch(int W, int* TWb, int* THb) {
+    int tw = 8;
+    while (tw < W && tw < 128) tw <<= 1;
+    *TWb = tw;
+    *THb = BM / tw;
+}
+
+uint32_t pow2_cols(int n) {
+    uint32_t c = 32;
+    while ((int)c < n) c <<= 1;
+    return c;
+}
+
+int common_checks(const char* who, int kind, int nterms, int N, int H, int W, int Cin_p, int Cout, int KH, int KW) {
+    PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "%s: operand kind must be PV2_BF16 or PV2_TF32 (got %d)", who, kind);
+    PV2_CHECK(nterms == 1 || (kind == PV2_TF32 && nterms == 3), "%s: nterms must be 1, or 3 with tf32 operands", who);
+    PV2_CHECK(N > 0 && H > 0 && W > 0 && Cin_p > 0 && Cout > 0 && KH > 0 && KW > 0, "%s: empty shape", who);
+    PV2_CHECK((KH & 1) && (KW & 1), "%s: only odd kernel sizes with same padding are supported (%dx%d)", who, KH, KW);
+    PV2_CHECK(Cin_p % (kind == PV2_BF16 ? 8 : 4) == 0, "%s: padded input channels %d break the 16-byte TMA stride rule", who, Cin_p);
+    return 0;
+}
+
+}  // namespace
+}  // namespace pv2
+
+using namespace pv2;
+
+extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
+    int TWb, THb;
+    pick_patch(W, &TWb, &THb);
+    const int KC = kind == PV2_BF16 ? 64 : 32;
+    const int m_tiles = N * ((W + TWb - 1) / TWb) * ((H + THb - 1) / THb);
+    const int BN = Cout >= 256 ? 256 : ((Cout + 15) / 16) * 16;
+    const int n_tiles = (Cout + BN - 1) / BN;
+    const int iters = nterms * KH * KW * ((Cin_p + KC - 1) / KC);
+    int splits = 1;
+    // fill the 148 SMs when the output tiling alone cannot, keeping >= 8 K iterations per split
+    while (splits < 8 && m_tiles * n_tiles * splits * 2 <= kNumSMs && iters / (splits * 2) >= 8) splits *= 2;   // <= 8: consumers sum at most 8 slabs
+    return splits;
+}
+
+extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,
+                            int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int dil_h, int dil_w,
+                            int out_mode, float* out, int ldo, int splits, const float* bias, void* stream) {
+    if (int e = common_checks("conv_fwd", kind, nterms, N, H, W, Cin_p, Cout, KH, KW)) return e;
+    PV2_CHECK(x && w_op && out, "conv_fwd: null pointer");
+    PV2_CHECK(out_mode == 0 || out_mode == 1, "conv_fwd: bad out_mode %d", out_mode);
+    PV2_CHECK(out_mode == 1 || (ldo % 4 == 0 && ldo >= Cout), "conv_fwd: ldo=%d must be a multiple of 4 and >= Cout=%d", ldo, Cout);
+    PV2_CHECK(out_mode == 0 || splits == 1, "conv_fwd: split-K needs the raw output mode");
+    const int k = kind == PV2_BF16 ? 0 : 1, KC = k == 0 ? 64 : 32;
+    const size_t es = k == 0 ? 2 : 4;
+    ConvArgs a = {};
+    a.H = H; a.W = W; a.Cout = Cout;
+    a.KW = KW; a.taps = KH * KW; a.dil_h = dil_h; a.dil_w = dil_w;
+    a.pad_h = dil_h * (KH - 1) / 2; a.pad_w = dil_w * (KW - 1) / 2;
+    pick_patch(W, &a.TWb, &a.THb);
+    a.tiles_x = (W + a.TWb - 1) / a.TWb; a.tiles_y = (H + a.THb - 1) / a.THb;
+    a.kc_per_tap = (Cin_p + KC - 1) / KC;
+    a.iters_total = nterms * a.taps * a.kc_per_tap;
+    PV2_CHECK(splits >= 1 && splits <= a.iters_total, "conv_fwd: splits=%d out of range (K iterations %d)", splits, a.iters_total);
+    a.iters_per_split = (a.iters_total + splits - 1) / splits;
+    PV2_CHECK((long long)a.iters_per_split * (splits - 1) < a.iters_total, "conv_fwd: splits=%d leaves an empty split", splits);
+    a.BN = Cout >= 256 ? 256 : ((Cout + 15) / 16) * 16;
+    a.tmem_cols = pow2_cols(a.BN);
+    a.out_mode = out_mode; a.out = out; a.ldo = ldo; a.bias = bias;
+    a.split_stride = (long long)N * H * W * ldo;
+    CUtensorMap mA0, mA1, mB0, mB1;
+    if (int e = make_act_map(&mA0, x, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
+    if (int e = make_w_map(&mB0, w_op, k, Cin_p, a.taps, Cout, a.BN)) return e;
+    mA1 = mA0; mB1 = mB0;
+    if (nterms == 3) {
+        if (int e = make_act_map(&mA1, (const uint8_t*)x + x_plane_stride * es, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
+        if (int e = make_w_map(&mB1, (const uint8_t*)w_op + w_plane_stride * es, k, Cin_p, a.taps, Cout, a.BN)) return e;
+    }
+    const size_t smem = (size_t)STAGES * (A_BYTES + (size_t)a.BN * ROW_BYTES) + 1024;
+    dim3 grid(N * a.tiles_x * a.tiles_y, (Cout + a.BN - 1) / a.BN, splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce;
+    if (k == 0) {
+        ce = cudaFuncSetAttribute(conv_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
+        conv_fwd_kernel<0><<<grid, THREADS, smem, st>>>(mA0, mA1, mB0, mB1, a);
+    } else {
+        ce = cudaFuncSetAttribute(conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
+        conv_fwd_kernel<1><<<grid, THREADS, smem, st>>>(mA0, mA1, mB0, mB1, a);
+    }
+    PV2_LAUNCH_CHECK("conv_fwd");
+    return 0;
+}
+
+extern "C" int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind) {
+    int TWb, THb;
+    pick_patch(W, &TWb, &THb);
+    const int KC = kind == PV2_BF16 ? 64 : 32;
+    const int tiles = N * ((W + TWb - 1) / TWb) * ((H + THb - 1) / THb);
+    const int cin_r = ((Cin_p + KC - 1) / KC) * KC;
+    const int bn_max = kind == PV2_BF16 ? 128 : 64;
+    const int BN = cin_r >= bn_max ? bn_max : cin_r;
+    const int ctas = KH * KW * ((Cout + BM - 1) / BM) * ((cin_r + BN - 1) / BN);
+    int splits = 1;
+    while (ctas * splits * 2 <= 2 * kNumSMs && tiles / (splits * 2) >= 2) splits *= 2;
+    return splits;
+}
+
+extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const void* x, long long x_plane_stride, int kind, int nterms,
+                              int N, int H, int W, int Cin_p, int Cout_p, int Cout, int KH, int KW, int dil_h, int dil_w,
+                              float* out, int splits, void* stream) {
+    if (int e = common_checks("conv_wgrad", kind, nterms, N, H, W, Cin_p, Cout, KH, KW)) return e;
+    PV2_CHECK(dy && x && out, "conv_wgrad: null pointer");
+    PV2_CHECK(Cout_p % (kind == PV2_BF16 ? 8 : 4) == 0 && Cout_p >= Cout, "conv_wgrad: bad padded Cout %d", Cout_p);
+    const int k = kind == PV2_BF16 ? 0 : 1, KC = k == 0 ? 64 : 32;
+    const size_t es = k == 0 ? 2 : 4;
+    WgradArgs a = {};
+    a.H = H; a.W = W; a.Cout = Cout; a.Cin_p = Cin_p;
+    a.KW = KW; a.taps = KH * KW; a.dil_h = dil_h; a.dil_w = dil_w;
+    a.pad_h = dil_h * (KH - 1) / 2; a.pad_w = dil_w * (KW - 1) / 2;
+    pick_patch(W, &a.TWb, &a.THb);
+    a.tiles_x = (W + a.TWb - 1) / a.TWb; a.tiles_y = (H + a.THb - 1) / a.THb;
+    a.tiles_total = N * a.tiles_x * a.tiles_y;
+    PV2_CHECK(splits >= 1 && splits <= a.tiles_total, "conv_wgrad: splits=%d out of range (pixel tiles %d)", splits, a.tiles_total);
+    a.tiles_per_split = (a.tiles_total + splits - 1) / splits;
+    PV2_CHECK((long long)a.tiles_per_split * (splits - 1) < a.tiles_total, "conv_wgrad: splits=%d leaves an empty split", splits);
+    a.nterms = nterms;
+    const int cin_r = ((Cin_p + KC - 1) / KC) * KC;
+    const int bn_max = k == 0 ? WgradCfg<0>::BN_MAX : WgradCfg<1>::BN_MAX;
+    a.BN = cin_r >= bn_max ? bn_max : cin_r;
+    a.ci_tiles = (cin_r + a.BN - 1) / a.BN;
+    a.tmem_cols = pow2_cols(a.BN);
+    a.out = out;
+    a.split_stride = (long long)Cout * a.taps * Cin_p;
+    CUtensorMap mG0, mG1, mX0, mX1;
+    const bool a32 = (k == 1);   // tf32 MN-major operands: 32-byte-atom swizzle
+    if (int e = make_act_map(&mG0, dy, k, Cout_p, W, H, N, a.TWb, a.THb, a32)) return e;
+    if (int e = make_act_map(&mX0, x, k, Cin_p, W, H, N, a.TWb, a.THb, a32)) return e;
+    mG1 = mG0; mX1 = mX0;
+    if (nterms == 3) {
+        if (int e = make_act_map(&mG1, (const uint8_t*)dy + dy_plane_stride * es, k, Cout_p, W, H, N, a.TWb, a.THb, a32)) return e;
+        if (int e = make_act_map(&mX1, (const uint8_t*)x + x_plane_stride * es, k, Cin_p, W, H, N, a.TWb, a.THb, a32)) return e;
+    }
+    const size_t smem = (size_t)(k == 0 ? WgradCfg<0>::STAGES_ : WgradCfg<1>::STAGES_) * ((BM / KC) + (a.BN / KC)) * A_BYTES + 1024;
+    PV2_CHECK(smem <= 227 * 1024, "conv_wgrad: stage too large (%zu B)", smem);
+    dim3 grid(a.taps, ((Cout + BM - 1) / BM) * a.ci_tiles, splits);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce;
+    if (k == 0) {
+        ce = cudaFuncSetAttribute(conv_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        PV2_CHECK(ce == cudaSuccess, "conv_wgrad: smem attribute: %s", cudaGetErrorString(ce));
+        conv_wgrad_kernel<0><<<grid, THREADS, smem, st>>>(mG0, mG1, mX0, mX1, a);
+    } else {
+        ce = cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        PV2_CHECK(ce == cudaSuccess, "conv_wgrad: smem attribute: %s", cudaGetErrorString(ce));
+        conv_wgrad_kernel<1><<<grid, THREADS, smem, st>>>(mG0, mG1, mX0, mX1, a);
+    }
+    PV2_LAUNCH_CHECK("conv_wgrad");
+    return 0;
+}

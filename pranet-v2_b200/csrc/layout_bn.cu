@@ -1,0 +1,675 @@
+// Memory-bound companions of the tcgen05 conv kernels: operand packing, weight packing, BatchNorm statistics,
+// the fused BN-affine / activation / product / residual "apply" pass and its backward, and the x2 align-corners
+// upsample of the partial decoder in NHWC.
+//
+// Reference ops replaced: nn.BatchNorm2d inside BasicConv2d (binary_seg/lib/pranet.py:37,41-42), the callers'
+// F.relu (pranet.py:358-360), RFB_modified's relu(x_cat + conv_res(x)) (pranet.py:82), aggregation's element-wise
+// products and concats (pranet.py:111-119) and its nn.Upsample(scale_factor=2, align_corners=True) (pranet.py:93).
+//
+// "Operand format" = NHWC, channels padded, element bf16 (1 plane) or tf32 hi/lo (2 fp32 planes `plane_stride`
+// elements apart) -- what the conv kernels' TMA maps read.  "Raw" = fp32 NHWC rows [pixel][ld] as the conv epilogue
+// writes them, possibly as several slabs (split-K partials / several gradient contributions) that are summed on load.
+#include "pv2_common.cuh"
+
+namespace pv2 {
+namespace {
+
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// KIND 0: bf16, 1 plane.  KIND 1: tf32, nplanes = 1 (hi) or 2 (hi, lo)
+template <int KIND>
+__device__ __forceinline__ void store_op(void* base, long long plane_stride, int nplanes, long long idx, float v) {
+    if constexpr (KIND == 0) {
+        reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+    } else {
+        float* p = reinterpret_cast<float*>(base);
+        const float hi = tf32_rna(v);
+        p[idx] = hi;
+        if (nplanes > 1) p[idx + plane_stride] = tf32_rna(v - hi);
+    }
+}
+template <int KIND>
+__device__ __forceinline__ float load_op(const void* base, long long plane_stride, int nplanes, long long idx) {
+    if constexpr (KIND == 0) {
+        return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+    } else {
+        const float* p = reinterpret_cast<const float*>(base);
+        float v = p[idx];
+        if (nplanes > 1) v += p[idx + plane_stride];
+        return v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weights: OIHW fp32 -> operand [o][tap][i_ld] (+ i_off).  mode 0 (fprop): o = co, i = ci, tap = kh*KW+kw.
+// mode 1 (dgrad): o = ci, i = co, tap flipped.  Padding channels are zeroed by the caller (memset) once.
+// ------------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void weight_pack_kernel(const float* __restrict__ w, void* out, long long plane_stride, int nplanes,
+                                   int Cout, int Cin, int KH, int KW, int mode, int i_ld, int i_off, int o_off) {
+    const long long total = (long long)Cout * Cin * KH * KW;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int kw = (int)(e % KW);
+        const int kh = (int)((e / KW) % KH);
+        const int ci = (int)((e / ((long long)KW * KH)) % Cin);
+        const int co = (int)(e / ((long long)KW * KH * Cin));
+        const int taps = KH * KW;
+        long long idx;
+        if (mode == 0) idx = ((long long)(co + o_off) * taps + kh * KW + kw) * i_ld + i_off + ci;
+        else idx = ((long long)(ci + o_off) * taps + (KH - 1 - kh) * KW + (KW - 1 - kw)) * i_ld + i_off + co;
+        store_op<KIND>(out, plane_stride, nplanes, idx, w[e]);
+    }
+}
+
+// wgrad partials [split][Cout_total][taps][Cin_p] -> OIHW fp32 gradient of one conv (rows co_off .. co_off+Cout)
+__global__ void wgrad_unpack_kernel(const float* __restrict__ part, long long split_stride, int splits, float* __restrict__ dw,
+                                    int Cout, int Cin, int KH, int KW, int Cin_p, int co_off) {
+    const long long total = (long long)Cout * Cin * KH * KW;
+    const int taps = KH * KW;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int kw = (int)(e % KW);
+        const int kh = (int)((e / KW) % KH);
+        const int ci = (int)((e / ((long long)KW * KH)) % Cin);
+        const int co = (int)(e / ((long long)KW * KH * Cin));
+        const long long idx = ((long long)(co + co_off) * taps + kh * KW + kw) * Cin_p + ci;
+        float acc = 0.0f;
+        for (int s = 0; s < splits; ++s) acc += part[s * split_stride + idx];
+        dw[e] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// NCHW (fp32 | bf16) -> operand NHWC, tiled transpose through shared memory; and the reverse for gradients
+// ------------------------------------------------------------------------------------------------------
+template <typename TIN, int KIND>
+__global__ void __launch_bounds__(256)
+pack_nchw_kernel(const TIN* __restrict__ x, void* out, long long plane_stride, int nplanes, int C, int HW, int ld, int c_off) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + tx;
+        tile[j][tx] = (c < C && p < HW) ? to_f(x[((long long)n * C + c) * HW + p]) : 0.0f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + tx;
+        if (p < HW && c < C) store_op<KIND>(out, plane_stride, nplanes, ((long long)n * HW + p) * ld + c_off + c, tile[tx][j]);
+    }
+}
+
+struct Slabs {               // up to 8 fp32 row-major [M][ld] gradient / partial slabs that are summed on load
+    const float* p[8];
+    int ld[8];
+    int off[8];
+    int n;
+};
+__device__ __forceinline__ float slab_sum(const Slabs& s, long long row, int c) {
+    float v = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < s.n) v += s.p[i][row * s.ld[i] + s.off[i] + c];
+    return v;
+}
+
+template <typename TOUT>
+__global__ void __launch_bounds__(256)
+unpack_to_nchw_kernel(const Slabs g, TOUT* __restrict__ dx, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const int p = p0 + j, c = c0 + tx;
+        tile[j][tx] = (p < HW && c < C) ? slab_sum(g, (long long)n * HW + p, c) : 0.0f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j, p = p0 + tx;
+        if (c < C && p < HW) dx[((long long)n * C + c) * HW + p] = from_f<TOUT>(tile[tx][j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// BatchNorm batch statistics over raw conv output (sums split-K slabs first and writes the total back to slab 0)
+//   partial kernel: grid (row_blocks, ceil(C/32)); block (32 channels x 8 row lanes); shifted sums -> (n, mean, M2)
+//   finalize: Chan-combine the row blocks; mean/invstd saved for backward; scale/shift for the apply pass;
+//             running stats updated like nn.BatchNorm2d (momentum, unbiased variance), num_batches_tracked += 1
+// ------------------------------------------------------------------------------------------------------
+constexpr int ST_ROWS = 256;   // rows per partial block
+
+__global__ void __launch_bounds__(256)
+bn_stats_partial_kernel(float* __restrict__ y, long long slab_stride, int nslabs, long long M, int C, int ld,
+                        float* __restrict__ part /* [row_blocks][C][3] */) {
+    __shared__ float sh[8][32][3];
+    const int c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+    const long long r0 = (long long)blockIdx.x * ST_ROWS, r1 = min(M, r0 + ST_ROWS);
+    float cnt = 0.0f, mean = 0.0f, m2 = 0.0f;
+    if (c < C) {
+        float shift = 0.0f, s1 = 0.0f, s2 = 0.0f;
+        bool first = true;
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            float v = y[r * ld + c];
+            if (nslabs > 1) {
+                for (int s = 1; s < nslabs; ++s) v += y[s * slab_stride + r * ld + c];
+                y[r * ld + c] = v;
+            }
+            if (first) { shift = v; first = false; }
+            const float d = v - shift;
+            s1 += d; s2 += d * d; cnt += 1.0f;
+        }
+        if (cnt > 0.0f) { mean = shift + s1 / cnt; m2 = fmaxf(s2 - s1 * s1 / cnt, 0.0f); }
+    }
+    sh[ty][threadIdx.x & 31][0] = cnt; sh[ty][threadIdx.x & 31][1] = mean; sh[ty][threadIdx.x & 31][2] = m2;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float nb = sh[k][threadIdx.x][0];
+            if (nb > 0.0f) {
+                const float d = sh[k][threadIdx.x][1] - mu, nt = n + nb;
+                mu += d * nb / nt;
+                M2 += sh[k][threadIdx.x][2] + d * d * n * nb / nt;
+                n = nt;
+            }
+        }
+        float* o = part + ((long long)blockIdx.x * C + c) * 3;
+        o[0] = n; o[1] = mu; o[2] = M2;
+    }
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                         float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
+                                         float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ scale,
+                                         float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    if (c >= C) return;
+    float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+    for (int b = 0; b < row_blocks; ++b) {
+        const float* p = part + ((long long)b * C + c) * 3;
+        const float nb = p[0];
+        if (nb > 0.0f) {
+            const float d = p[1] - mu, nt = n + nb;
+            mu += d * nb / nt;
+            M2 += p[2] + d * d * n * nb / nt;
+            n = nt;
+        }
+    }
+    const float var = M2 / n;
+    const float inv = rsqrtf(var + eps);
+    mean_out[c] = mu;
+    invstd_out[c] = inv;
+    const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    scale[c] = g * inv;
+    shift[c] = b - mu * g * inv;
+    if (running_mean) {
+        running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mu;
+        running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (n > 1.0f ? M2 / (n - 1.0f) : var);
+    }
+}
+
+// eval-mode BN / plain bias as an affine: scale = gamma / sqrt(rv + eps), shift = beta - rm * scale
+__global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float s = (gamma ? gamma[c] : 1.0f) * rsqrtf(rv[c] + eps);
+    scale[c] = s;
+    shift[c] = (beta ? beta[c] : 0.0f) - rm[c] * s;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// apply:  a1 = y1*s1+b1 ; [a2 = y2*s2+b2 ; v = a1 (+|*) a2] ; [v *= mult] ; [relu] -> operand NHWC slice or NCHW fp32
+// ------------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+    const float* y1; int ld1, off1; const float* s1; const float* b1;
+    const float* y2; int ld2, off2; const float* s2; const float* b2;
+    int ns1, ns2; long long ss1, ss2;   // split-K slabs of y1 / y2 still to be summed on load (eval path), stride in elements
+    int combine;                 // 0 none, 1 add, 2 mul
+    const void* mult; long long mult_plane; int mult_planes, mult_ld, mult_off;   // operand-format multiplier (or null)
+    int relu;
+    long long M; int C, HW;
+    void* out; long long out_plane; int out_planes, out_ld, out_off;
+    int out_nchw;                // 1: out is fp32 NCHW [N][C][HW]
+};
+
+__device__ __forceinline__ float raw_load(const float* y, int ld, int off, int ns, long long ss, long long r, int c) {
+    float v = y[r * ld + off + c];
+    for (int s = 1; s < ns; ++s) v += y[s * ss + r * ld + off + c];
+    return v;
+}
+
+template <int KIND>
+__device__ __forceinline__ float apply_value(const ApplyArgs& a, long long r, int c, float* a1o, float* a2o, float* mo) {
+    const float a1 = raw_load(a.y1, a.ld1, a.off1, a.ns1, a.ss1, r, c) * a.s1[c] + a.b1[c];
+    float a2 = 0.0f, v = a1;
+    if (a.combine) {
+        a2 = raw_load(a.y2, a.ld2, a.off2, a.ns2, a.ss2, r, c) * a.s2[c] + a.b2[c];
+        v = a.combine == 1 ? a1 + a2 : a1 * a2;
+    }
+    float m = 1.0f;
+    if (a.mult) { m = load_op<KIND>(a.mult, a.mult_plane, a.mult_planes, r * a.mult_ld + a.mult_off + c); v *= m; }
+    *a1o = a1; *a2o = a2; *mo = m;
+    return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+act_apply_kernel(const ApplyArgs a) {
+    const long long total = a.M * a.C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / a.C;
+        const int c = (int)(e - r * a.C);
+        float a1, a2, m;
+        float v = apply_value<KIND>(a, r, c, &a1, &a2, &m);
+        if (a.relu) v = fmaxf(v, 0.0f);
+        if (a.out_nchw) {
+            const long long n = r / a.HW, p = r - n * a.HW;
+            reinterpret_cast<float*>(a.out)[(n * a.C + c) * a.HW + p] = v;
+        } else {
+            store_op<KIND>(a.out, a.out_plane, a.out_planes, r * a.out_ld + a.out_off + c, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// backward of apply + BN.  dz arrives as summed slabs (raw NHWC) or as one fp32 NCHW tensor.
+//   reduce pass : per channel S1_i = sum da_i, S2_i = sum da_i * yhat_i  (i = 1,2) as row-block partials;
+//                 also writes d(mult) raw fp32 [M][C] when a multiplier is present
+//   finalize    : fold partials -> sums[4][C]; dgamma_i = S2_i, dbeta_i = S1_i
+//   dx pass     : dy_i = gamma_i*invstd_i * (da_i - S1_i/n - yhat_i*S2_i/n)  (bn_train) or scale_i*da_i (affine)
+//                 written in operand format for the dgrad / wgrad GEMMs
+// ------------------------------------------------------------------------------------------------------
+struct BwdArgs {
+    ApplyArgs f;                  // the forward description (out fields unused)
+    Slabs dz; const float* dz_nchw;
+    const float* mean1; const float* inv1; const float* mean2; const float* inv2;
+    float* dmult; int dmult_ld;   // raw fp32 gradient of the multiplier (or null)
+    float* part;                  // [row_blocks][4][C]
+    const float* sums;            // [4][C] (dx pass)
+    int bn_train;                 // 1: batch-stat BN backward, 0: plain affine
+    void* dy1; long long dy1_plane; int dy1_planes, dy1_ld;
+    void* dy2; long long dy2_plane; int dy2_planes, dy2_ld;
+};
+
+template <int KIND>
+__device__ __forceinline__ void bwd_da(const BwdArgs& b, long long r, int c, float* da1, float* da2, float* yh1, float* yh2, float* dm) {
+    const ApplyArgs& a = b.f;
+    float a1, a2, m;
+    const float v = apply_value<KIND>(a, r, c, &a1, &a2, &m);
+    float g;
+    if (b.dz_nchw) {
+        const long long n = r / a.HW, p = r - n * a.HW;
+        g = b.dz_nchw[(n * a.C + c) * a.HW + p];
+    } else {
+        g = slab_sum(b.dz, r, c);
+    }
+    if (a.relu && !(v > 0.0f)) g = 0.0f;
+    float comb = a1;
+    if (a.combine == 1) comb = a1 + a2; else if (a.combine == 2) comb = a1 * a2;
+    *dm = g * comb;
+    const float dc = a.mult ? g * m : g;
+    *da1 = a.combine == 2 ? dc * a2 : dc;
+    *da2 = a.combine == 0 ? 0.0f : (a.combine == 2 ? dc * a1 : dc);
+    const float y1v = raw_load(a.y1, a.ld1, a.off1, a.ns1, a.ss1, r, c);
+    *yh1 = b.mean1 ? (y1v - b.mean1[c]) * b.inv1[c] : y1v;
+    const float y2v = a.combine ? raw_load(a.y2, a.ld2, a.off2, a.ns2, a.ss2, r, c) : 0.0f;
+    *yh2 = (a.combine && b.mean2) ? (y2v - b.mean2[c]) * b.inv2[c] : y2v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const BwdArgs b) {
+    __shared__ float sh[8][32][4];
+    const int C = b.f.C;
+    const int c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
+    const long long r0 = (long long)blockIdx.x * ST_ROWS, r1 = min(b.f.M, r0 + ST_ROWS);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            float da1, da2, yh1, yh2, dm;
+            bwd_da<KIND>(b, r, c, &da1, &da2, &yh1, &yh2, &dm);
+            s[0] += da1; s[1] += da1 * yh1; s[2] += da2; s[3] += da2 * yh2;
+            if (b.dmult) b.dmult[r * b.dmult_ld + c] = dm;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sh[ty][threadIdx.x & 31][k] = s[k];
+    __syncthreads();
+    if (ty == 0 && c < C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float t = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += sh[j][threadIdx.x][k];
+            b.part[((long long)blockIdx.x * 4 + k) * C + c] = t;
+        }
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, float* __restrict__ sums,
+                                       float* __restrict__ dgamma1, float* __restrict__ dbeta1, float* __restrict__ dgamma2,
+                                       float* __restrict__ dbeta2) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < row_blocks; ++b)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s[k] += part[((long long)b * 4 + k) * C + c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sums[k * C + c] = s[k];
+    if (dbeta1) dbeta1[c] = s[0];
+    if (dgamma1) dgamma1[c] = s[1];
+    if (dbeta2) dbeta2[c] = s[2];
+    if (dgamma2) dgamma2[c] = s[3];
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_kernel(const BwdArgs b) {
+    const ApplyArgs& a = b.f;
+    const long long total = a.M * a.C;
+    const float invn = 1.0f / (float)a.M;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / a.C;
+        const int c = (int)(e - r * a.C);
+        float da1, da2, yh1, yh2, dm;
+        bwd_da<KIND>(b, r, c, &da1, &da2, &yh1, &yh2, &dm);
+        float d1, d2 = 0.0f;
+        if (b.bn_train) {
+            d1 = a.s1[c] * (da1 - b.sums[c] * invn - yh1 * b.sums[a.C + c] * invn);          // s1 = gamma*invstd
+            if (a.combine) d2 = a.s2[c] * (da2 - b.sums[2 * a.C + c] * invn - yh2 * b.sums[3 * a.C + c] * invn);
+        } else {
+            d1 = a.s1[c] * da1;
+            if (a.combine) d2 = a.s2[c] * da2;
+        }
+        store_op<KIND>(b.dy1, b.dy1_plane, b.dy1_planes, r * b.dy1_ld + c, d1);
+        if (a.combine) store_op<KIND>(b.dy2, b.dy2_plane, b.dy2_planes, r * b.dy2_ld + c, d2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// x2 bilinear upsample, align_corners=True, NHWC operand -> NHWC operand slice; backward raw -> raw
+// ------------------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256)
+up2_nhwc_fwd_kernel(const void* in, long long in_plane, int in_planes, int in_ld, int in_off, void* out, long long out_plane,
+                    int out_planes, int out_ld, int out_off, int N, int H, int W, int C, float rh, float rw) {
+    const int OH = 2 * H, OW = 2 * W;
+    const long long total = (long long)N * OH * OW * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        long long t = e / C;
+        const int ox = (int)(t % OW); t /= OW;
+        const int oy = (int)(t % OH);
+        const long long n = t / OH;
+        const Tap ty = bilinear_tap(oy, H, rh, true), tx = bilinear_tap(ox, W, rw, true);
+        const long long b0 = (n * H + ty.i0) * W, b1 = (n * H + ty.i1) * W;
+        const float v00 = load_op<KIND>(in, in_plane, in_planes, (b0 + tx.i0) * in_ld + in_off + c);
+        const float v01 = load_op<KIND>(in, in_plane, in_planes, (b0 + tx.i1) * in_ld + in_off + c);
+        const float v10 = load_op<KIND>(in, in_plane, in_planes, (b1 + tx.i0) * in_ld + in_off + c);
+        const float v11 = load_op<KIND>(in, in_plane, in_planes, (b1 + tx.i1) * in_ld + in_off + c);
+        const float v = ty.w0 * (tx.w0 * v00 + tx.w1 * v01) + ty.w1 * (tx.w0 * v10 + tx.w1 * v11);
+        store_op<KIND>(out, out_plane, out_planes, ((n * OH + oy) * OW + ox) * out_ld + out_off + c, v);
+    }
+}
+
+__device__ __forceinline__ float ac_weight(int o, int i, int in_size, float ratio) {
+    const Tap t = bilinear_tap(o, in_size, ratio, true);
+    return (t.i0 == i ? t.w0 : 0.0f) + (t.i1 == i ? t.w1 : 0.0f);
+}
+
+__global__ void __launch_bounds__(256)
+up2_nhwc_bwd_kernel(const Slabs g, float* __restrict__ din, int din_ld, int N, int H, int W, int C, float rh, float rw) {
+    const int OH = 2 * H, OW = 2 * W;
+    const long long total = (long long)N * H * W * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        long long t = e / C;
+        const int ix = (int)(t % W); t /= W;
+        const int iy = (int)(t % H);
+        const long long n = t / H;
+        // outputs whose taps can touch (iy, ix): src = ratio*o in (i-1, i+1)
+        const int ylo = max(0, rh > 0.f ? (int)floorf((iy - 1) / rh) : 0), yhi = min(OH - 1, rh > 0.f ? (int)ceilf((iy + 1) / rh) : OH - 1);
+        const int xlo = max(0, rw > 0.f ? (int)floorf((ix - 1) / rw) : 0), xhi = min(OW - 1, rw > 0.f ? (int)ceilf((ix + 1) / rw) : OW - 1);
+        float acc = 0.0f;
+        for (int oy = ylo; oy <= yhi; ++oy) {
+            const float wy = ac_weight(oy, iy, H, rh);
+            if (wy == 0.0f) continue;
+            for (int ox = xlo; ox <= xhi; ++ox) {
+                const float wx = ac_weight(ox, ix, W, rw);
+                if (wx != 0.0f) acc += wy * wx * slab_sum(g, (n * OH + oy) * OW + ox, c);
+            }
+        }
+        din[((n * H + iy) * W + ix) * din_ld + c] = acc;
+    }
+}
+
+inline int grid_for(long long total, int threads = 256) {
+    long long b = (total + threads - 1) / threads;
+    const long long cap = (long long)kNumSMs * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int fill_slabs(Slabs* s, const float* const* ptrs, const int* lds, const int* offs, int n, const char* who) {
+    PV2_CHECK(n >= 1 && n <= 8, "%s: between 1 and 8 gradient slabs expected, got %d", who, n);
+    s->n = n;
+    for (int i = 0; i < 8; ++i) { s->p[i] = nullptr; s->ld[i] = 0; s->off[i] = 0; }
+    for (int i = 0; i < n; ++i) {
+        PV2_CHECK(ptrs[i] != nullptr, "%s: null slab %d", who, i);
+        s->p[i] = ptrs[i]; s->ld[i] = lds[i]; s->off[i] = offs[i];
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace pv2
+
+using namespace pv2;
+
+#define KIND_CHECK(who)                                                                                              \
+    PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, who ": operand kind must be PV2_BF16 or PV2_TF32 (got %d)", kind); \
+    PV2_CHECK(nplanes == 1 || (kind == PV2_TF32 && nplanes == 2), who ": nplanes must be 1 (or 2 with tf32)")
+
+extern "C" int pv2_weight_pack(const float* w, void* out, long long plane_stride, int nplanes, int kind, int Cout, int Cin, int KH, int KW,
+                               int mode, int i_ld, int i_off, int o_off, void* stream) {
+    KIND_CHECK("weight_pack");
+    PV2_CHECK(w && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "weight_pack: bad arguments");
+    const long long total = (long long)Cout * Cin * KH * KW;
+    if (kind == PV2_BF16) weight_pack_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(w, out, plane_stride, nplanes, Cout, Cin, KH, KW, mode, i_ld, i_off, o_off);
+    else weight_pack_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(w, out, plane_stride, nplanes, Cout, Cin, KH, KW, mode, i_ld, i_off, o_off);
+    PV2_LAUNCH_CHECK("weight_pack");
+    return 0;
+}
+
+extern "C" int pv2_wgrad_unpack(const float* part, long long split_stride, int splits, float* dw, int Cout, int Cin, int KH, int KW,
+                                int Cin_p, int co_off, void* stream) {
+    PV2_CHECK(part && dw && splits >= 1, "wgrad_unpack: bad arguments");
+    const long long total = (long long)Cout * Cin * KH * KW;
+    wgrad_unpack_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(part, split_stride, splits, dw, Cout, Cin, KH, KW, Cin_p, co_off);
+    PV2_LAUNCH_CHECK("wgrad_unpack");
+    return 0;
+}
+
+extern "C" int pv2_pack_nchw(const void* x, int x_dtype, void* out, long long plane_stride, int nplanes, int kind, int N, int C, int HW,
+                             int ld, int c_off, void* stream) {
+    KIND_CHECK("pack_nchw");
+    PV2_CHECK(x && out && N > 0 && C > 0 && HW > 0 && N <= 65535, "pack_nchw: bad arguments");
+    PV2_CHECK(x_dtype == PV2_F32 || x_dtype == PV2_BF16, "pack_nchw: bad input dtype %d", x_dtype);
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == PV2_F32 && kind == PV2_BF16) pack_nchw_kernel<float, 0><<<grid, 256, 0, st>>>((const float*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    else if (x_dtype == PV2_F32) pack_nchw_kernel<float, 1><<<grid, 256, 0, st>>>((const float*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    else if (kind == PV2_BF16) pack_nchw_kernel<__nv_bfloat16, 0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    else pack_nchw_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    PV2_LAUNCH_CHECK("pack_nchw");
+    return 0;
+}
+
+template <typename TOUT>
+__global__ void __launch_bounds__(256)
+slabs_to_nhwc_kernel(const pv2::Slabs g, TOUT* __restrict__ dx, long long M, int C) {
+    const long long total = M * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / C;
+        dx[e] = pv2::from_f<TOUT>(pv2::slab_sum(g, r, (int)(e - r * C)));
+    }
+}
+
+extern "C" int pv2_unpack_to_nchw(const float* const* slabs, const int* lds, const int* offs, int nslabs, void* dx, int dx_dtype,
+                                  int N, int C, int HW, int channels_last, void* stream) {
+    if (channels_last) {
+        Slabs s2;
+        if (int e = fill_slabs(&s2, slabs, lds, offs, nslabs, "unpack_to_nchw")) return e;
+        PV2_CHECK(dx && N > 0 && C > 0 && HW > 0, "unpack_to_nchw: bad arguments");
+        const long long M = (long long)N * HW;
+        if (dx_dtype == PV2_F32) slabs_to_nhwc_kernel<float><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>(s2, (float*)dx, M, C);
+        else if (dx_dtype == PV2_BF16) slabs_to_nhwc_kernel<__nv_bfloat16><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>(s2, (__nv_bfloat16*)dx, M, C);
+        else PV2_CHECK(false, "unpack_to_nchw: bad dtype %d", dx_dtype);
+        PV2_LAUNCH_CHECK("slabs_to_nhwc");
+        return 0;
+    }
+    Slabs s;
+    if (int e = fill_slabs(&s, slabs, lds, offs, nslabs, "unpack_to_nchw")) return e;
+    PV2_CHECK(dx && N > 0 && C > 0 && HW > 0 && N <= 65535, "unpack_to_nchw: bad arguments");
+    PV2_CHECK(dx_dtype == PV2_F32 || dx_dtype == PV2_BF16, "unpack_to_nchw: bad dtype %d", dx_dtype);
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
+    if (dx_dtype == PV2_F32) unpack_to_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(s, (float*)dx, C, HW);
+    else unpack_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, (__nv_bfloat16*)dx, C, HW);
+    PV2_LAUNCH_CHECK("unpack_to_nchw");
+    return 0;
+}
+
+extern "C" size_t pv2_bn_workspace_floats(long long M, int C) {
+    const long long rb = (M + ST_ROWS - 1) / ST_ROWS;
+    return (size_t)(rb * C * 4 + 4 * (long long)C);
+}
+
+extern "C" int pv2_bn_stats(float* y, long long slab_stride, int nslabs, long long M, int C, int ld, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                            float* mean_out, float* invstd_out, float* scale, float* shift, float* workspace, void* stream) {
+    PV2_CHECK(y && mean_out && invstd_out && scale && shift && workspace, "bn_stats: null pointer");
+    PV2_CHECK(M > 0 && C > 0 && ld >= C && nslabs >= 1, "bn_stats: bad shape");
+    const int rb = (int)((M + ST_ROWS - 1) / ST_ROWS);
+    PV2_CHECK((C + 31) / 32 <= 65535, "bn_stats: too many channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    bn_stats_partial_kernel<<<dim3(rb, (C + 31) / 32), 256, 0, st>>>(y, slab_stride, nslabs, M, C, ld, workspace);
+    PV2_LAUNCH_CHECK("bn_stats_partial");
+    bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, rb, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                                               num_batches_tracked, mean_out, invstd_out, scale, shift);
+    PV2_LAUNCH_CHECK("bn_stats_finalize");
+    return 0;
+}
+
+extern "C" int pv2_bn_eval_affine(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                  float* scale, float* shift, void* stream) {
+    PV2_CHECK(C > 0 && rm && rv && scale && shift, "bn_eval_affine: bad arguments");
+    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, rm, rv, eps, scale, shift);
+    PV2_LAUNCH_CHECK("bn_eval_affine");
+    return 0;
+}
+
+// flat argument list -> ApplyArgs (ctypes-friendly)
+static int fill_apply(ApplyArgs* a, const float* y1, int ld1, int off1, int ns1, long long ss1, const float* s1, const float* b1,
+                      const float* y2, int ld2, int off2, int ns2, long long ss2, const float* s2, const float* b2, int combine, const void* mult, long long mult_plane, int mult_planes, int mult_ld,
+                      int mult_off, int relu, long long M, int C, int HW) {
+    PV2_CHECK(y1 && s1 && b1 && M > 0 && C > 0 && HW > 0, "apply: bad arguments");
+    PV2_CHECK(combine >= 0 && combine <= 2 && (combine == 0 || (y2 && s2 && b2)), "apply: bad combine arguments");
+    a->y1 = y1; a->ld1 = ld1; a->off1 = off1; a->s1 = s1; a->b1 = b1;
+    a->y2 = y2; a->ld2 = ld2; a->off2 = off2; a->s2 = s2; a->b2 = b2;
+    a->ns1 = ns1 < 1 ? 1 : ns1; a->ss1 = ss1; a->ns2 = ns2 < 1 ? 1 : ns2; a->ss2 = ss2;
+    a->combine = combine;
+    a->mult = mult; a->mult_plane = mult_plane; a->mult_planes = mult_planes; a->mult_ld = mult_ld; a->mult_off = mult_off;
+    a->relu = relu; a->M = M; a->C = C; a->HW = HW;
+    a->out = nullptr; a->out_plane = 0; a->out_planes = 1; a->out_ld = 0; a->out_off = 0; a->out_nchw = 0;
+    return 0;
+}
+
+extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long long ss1, const float* s1, const float* b1,
+                             const float* y2, int ld2, int off2, int ns2, long long ss2,
+                             const float* s2, const float* b2, int combine, const void* mult, long long mult_plane, int mult_planes,
+                             int mult_ld, int mult_off, int relu, long long M, int C, int HW, void* out, long long out_plane,
+                             int out_planes, int out_ld, int out_off, int out_nchw, int kind, void* stream) {
+    PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "act_apply: bad operand kind %d", kind);
+    ApplyArgs a;
+    if (int e = fill_apply(&a, y1, ld1, off1, ns1, ss1, s1, b1, y2, ld2, off2, ns2, ss2, s2, b2, combine, mult, mult_plane, mult_planes, mult_ld, mult_off, relu, M, C, HW)) return e;
+    PV2_CHECK(out != nullptr, "act_apply: null output");
+    a.out = out; a.out_plane = out_plane; a.out_planes = out_planes; a.out_ld = out_ld; a.out_off = out_off; a.out_nchw = out_nchw;
+    const long long total = M * C;
+    if (kind == PV2_BF16) act_apply_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(a);
+    else act_apply_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(a);
+    PV2_LAUNCH_CHECK("act_apply");
+    return 0;
+}
+
+extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long long ss1, const float* s1, const float* b1,
+                              const float* y2, int ld2, int off2, int ns2, long long ss2,
+                              const float* s2, const float* b2, int combine, const void* mult, long long mult_plane, int mult_planes,
+                              int mult_ld, int mult_off, int relu, long long M, int C, int HW,
+                              const float* const* dz_slabs, const int* dz_lds, const int* dz_offs, int dz_n, const float* dz_nchw,
+                              const float* mean1, const float* inv1, const float* mean2, const float* inv2, int bn_train,
+                              float* dmult, int dmult_ld, void* dy1, long long dy1_plane, int dy1_planes, int dy1_ld,
+                              void* dy2, long long dy2_plane, int dy2_planes, int dy2_ld,
+                              float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace, int kind, void* stream) {
+    PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "bn_act_bwd: bad operand kind %d", kind);
+    BwdArgs b = {};
+    if (int e = fill_apply(&b.f, y1, ld1, off1, ns1, ss1, s1, b1, y2, ld2, off2, ns2, ss2, s2, b2, combine, mult, mult_plane, mult_planes, mult_ld, mult_off, relu, M, C, HW)) return e;
+    if (dz_nchw == nullptr) {
+        if (int e = fill_slabs(&b.dz, dz_slabs, dz_lds, dz_offs, dz_n, "bn_act_bwd")) return e;
+    } else {
+        b.dz.n = 0;
+    }
+    b.dz_nchw = dz_nchw;
+    PV2_CHECK(dy1 && workspace, "bn_act_bwd: null pointer");
+    PV2_CHECK(combine == 0 || dy2, "bn_act_bwd: dy2 missing for a combined op");
+    PV2_CHECK(!bn_train || (mean1 && inv1 && (combine == 0 || (mean2 && inv2))), "bn_act_bwd: saved batch statistics missing");
+    b.mean1 = mean1; b.inv1 = inv1; b.mean2 = mean2; b.inv2 = inv2;
+    b.dmult = mult ? dmult : nullptr; b.dmult_ld = dmult_ld;
+    b.bn_train = bn_train;
+    b.dy1 = dy1; b.dy1_plane = dy1_plane; b.dy1_planes = dy1_planes; b.dy1_ld = dy1_ld;
+    b.dy2 = dy2; b.dy2_plane = dy2_plane; b.dy2_planes = dy2_planes; b.dy2_ld = dy2_ld;
+    const int rb = (int)((M + ST_ROWS - 1) / ST_ROWS);
+    float* part = workspace;
+    float* sums = workspace + (size_t)rb * 4 * C;
+    b.part = part; b.sums = sums;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 rgrid(rb, (C + 31) / 32);
+    if (kind == PV2_BF16) bn_bwd_reduce_kernel<0><<<rgrid, 256, 0, st>>>(b); else bn_bwd_reduce_kernel<1><<<rgrid, 256, 0, st>>>(b);
+    PV2_LAUNCH_CHECK("bn_bwd_reduce");
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, rb, C, sums, dgamma1, dbeta1, dgamma2, dbeta2);
+    PV2_LAUNCH_CHECK("bn_bwd_finalize");
+    const long long total = M * C;
+    if (kind == PV2_BF16) bn_bwd_dx_kernel<0><<<grid_for(total), 256, 0, st>>>(b); else bn_bwd_dx_kernel<1><<<grid_for(total), 256, 0, st>>>(b);
+    PV2_LAUNCH_CHECK("bn_bwd_dx");
+    return 0;
+}
+
+extern "C" int pv2_up2_nhwc_fwd(const void* in, long long in_plane, int in_planes, int in_ld, int in_off, void* out, long long out_plane,
+                                int out_planes, int out_ld, int out_off, int N, int H, int W, int C, int kind, void* stream) {
+    PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "up2_nhwc_fwd: bad operand kind %d", kind);
+    PV2_CHECK(in && out && N > 0 && H > 0 && W > 0 && C > 0, "up2_nhwc_fwd: bad arguments");
+    const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
+    const long long total = (long long)N * 4 * H * W * C;
+    if (kind == PV2_BF16) up2_nhwc_fwd_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, in_plane, in_planes, in_ld, in_off, out, out_plane, out_planes, out_ld, out_off, N, H, W, C, rh, rw);
+    else up2_nhwc_fwd_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, in_plane, in_planes, in_ld, in_off, out, out_plane, out_planes, out_ld, out_off, N, H, W, C, rh, rw);
+    PV2_LAUNCH_CHECK("up2_nhwc_fwd");
+    return 0;
+}
+
+extern "C" int pv2_up2_nhwc_bwd(const float* const* slabs, const int* lds, const int* offs, int nslabs, float* din, int din_ld,
+                                int N, int H, int W, int C, void* stream) {
+    Slabs s;
+    if (int e = fill_slabs(&s, slabs, lds, offs, nslabs, "up2_nhwc_bwd")) return e;
+    PV2_CHECK(din && N > 0 && H > 0 && W > 0 && C > 0, "up2_nhwc_bwd: bad arguments");
+    const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
+    up2_nhwc_bwd_kernel<<<grid_for((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(s, din, din_ld, N, H, W, C, rh, rw);
+    PV2_LAUNCH_CHECK("up2_nhwc_bwd");
+    return 0;
+}

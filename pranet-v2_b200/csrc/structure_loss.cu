@@ -76,15 +76,33 @@ __device__ __forceinline__ void tile_weit(const float* __restrict__ mask, int H,
     }
 }
 
+// MUFU-only transcendental pieces: e = exp(-|x|) via ex2.approx, log1p(e) via lg2.approx(1+e).
+// Absolute error of log1p(e) <= ~6e-8 (when e underflows against 1), far inside the 1e-4 loss tolerance.
+__device__ __forceinline__ float fast_ex2(float v) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float fast_lg2(float v) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float fast_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+// softplus(x) - x*t  and sigmoid(x)
 __device__ __forceinline__ void bce_sig(float x, float t, float& bce, float& sig) {
-    float e = __expf(-fabsf(x));
-    float inv = __fdividef(1.0f, 1.0f + e);
+    const float e = fast_ex2(-fabsf(x) * LOG2E);
+    const float d = 1.0f + e;
+    const float inv = fast_rcp(d);
     sig = x >= 0.0f ? inv : e * inv;
-    bce = fmaxf(x, 0.0f) - x * t + log1pf(e);
+    bce = fmaf(-x, t, fmaxf(x, 0.0f)) + fast_lg2(d) * LN2;
+}
+__device__ __forceinline__ float bce_only(float x, float t) {
+    const float e = fast_ex2(-fabsf(x) * LOG2E);
+    return fmaf(-x, t, fmaxf(x, 0.0f)) + fast_lg2(1.0f + e) * LN2;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    const float e = fast_ex2(-fabsf(x) * LOG2E);
+    const float inv = fast_rcp(1.0f + e);
+    return x >= 0.0f ? inv : e * inv;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
                           int nscales, int H, int W, int tiles_x, int tiles_per_plane, float* __restrict__ partials) {
     __shared__ float sm[SH * SPITCH];
@@ -129,9 +147,9 @@ structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
         float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
 #pragma unroll
         for (int j = 0; j < ROWS_PER_THREAD; ++j) {
-            float bce, sig, bce2, sig2;
+            float bce, sig;
             bce_sig(pv[j], m[j], bce, sig);
-            bce_sig(qv[j], mb[j], bce2, sig2);
+            const float bce2 = bce_only(qv[j], mb[j]);
             a += w[j] * bce;
             b += w[j] * bce2;
             c += sig * m[j] * w[j];
@@ -160,42 +178,74 @@ structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
     }
 }
 
-// one block; plane_sums[plane][NSUM_MAX] <- fixed-order sum over tiles; loss[k] <- mean over planes
-__global__ void structure_loss_finalize_kernel(const float* __restrict__ partials, float* __restrict__ plane_sums,
-                                               float* __restrict__ loss, int planes, int tiles_per_plane, int nscales) {
-    __shared__ float red[32][PV2_MAX_SCALES];
-    const int nsum = 1 + 4 * nscales;
-    float acc[PV2_MAX_SCALES] = {0.f, 0.f, 0.f, 0.f};
-    // warp per plane: lanes take the sums, tiles are walked in order
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int p = warp; p < planes; p += nwarps) {
+// grid = planes; one CTA folds the per-tile partials of its plane in a FIXED order (thread t takes tiles
+// t, t+128, ...; then a fixed shuffle/shared tree), writes plane_sums[plane][*] and this plane's loss terms.
+constexpr int FIN_THREADS = 128;
+__global__ void __launch_bounds__(FIN_THREADS)
+structure_loss_plane_kernel(const float* __restrict__ partials, float* __restrict__ plane_sums,
+                            float* __restrict__ plane_loss, int tiles_per_plane, int nscales) {
+    __shared__ float red[FIN_THREADS / 32][NSUM_MAX];
+    const int p = blockIdx.x, nsum = 1 + 4 * nscales;
+    float acc[NSUM_MAX];
+#pragma unroll
+    for (int i = 0; i < NSUM_MAX; ++i) acc[i] = 0.0f;
+    for (int t = threadIdx.x; t < tiles_per_plane; t += FIN_THREADS) {
+        const float* src = partials + ((size_t)p * tiles_per_plane + t) * NSUM_MAX;
+#pragma unroll
+        for (int i = 0; i < NSUM_MAX; ++i)
+            if (i < nsum) acc[i] += src[i];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < NSUM_MAX; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
         float v = 0.0f;
         if (lane < nsum) {
-            const float* src = partials + (size_t)p * tiles_per_plane * NSUM_MAX + lane;
-            for (int t = 0; t < tiles_per_plane; ++t) v += src[(size_t)t * NSUM_MAX];
+#pragma unroll
+            for (int wi = 0; wi < FIN_THREADS / 32; ++wi) v += red[wi][lane];
             plane_sums[(size_t)p * NSUM_MAX + lane] = v;
         }
-        float Wsum = __shfl_sync(0xffffffffu, v, 0);
-        for (int k = 0; k < nscales; ++k) {
-            float sb = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 0);
-            float sb2 = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 1);
-            float inter = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 2);
-            float uni = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 3);
-            acc[k] += sb / Wsum + 1.0f - (inter + 1.0f) / (uni - inter + 1.0f) + 0.8f * sb2 / Wsum;
+        const float Wsum = __shfl_sync(0xffffffffu, v, 0);
+#pragma unroll
+        for (int k = 0; k < PV2_MAX_SCALES; ++k) {
+            const float sb = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 0);
+            const float sb2 = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 1);
+            const float inter = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 2);
+            const float uni = __shfl_sync(0xffffffffu, v, 1 + 4 * k + 3);
+            if (lane == 0 && k < nscales)
+                plane_loss[(size_t)p * PV2_MAX_SCALES + k] = sb / Wsum + 1.0f - (inter + 1.0f) / (uni - inter + 1.0f) + 0.8f * sb2 / Wsum;
         }
     }
-    if (lane == 0)
-        for (int k = 0; k < PV2_MAX_SCALES; ++k) red[warp][k] = acc[k];
+}
+
+// one small CTA: loss[k] = mean over planes (fixed order)
+__global__ void structure_loss_mean_kernel(const float* __restrict__ plane_loss, float* __restrict__ loss, int planes, int nscales) {
+    __shared__ float red[8][PV2_MAX_SCALES];
+    float acc[PV2_MAX_SCALES] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = threadIdx.x; p < planes; p += blockDim.x)
+#pragma unroll
+        for (int k = 0; k < PV2_MAX_SCALES; ++k)
+            if (k < nscales) acc[k] += plane_loss[(size_t)p * PV2_MAX_SCALES + k];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < PV2_MAX_SCALES; ++k) {
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
     __syncthreads();
     if (threadIdx.x < nscales) {
         float v = 0.0f;
-        for (int wi = 0; wi < nwarps; ++wi) v += red[wi][threadIdx.x];
+        for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) v += red[wi][threadIdx.x];
         loss[threadIdx.x] = v / (float)planes;
     }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 structure_loss_bwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
                           const float* __restrict__ grad_loss, const float* __restrict__ plane_sums,
                           int nscales, int planes, int H, int W, int tiles_x) {
@@ -221,7 +271,9 @@ structure_loss_bwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
     const float* ps = plane_sums + (size_t)plane * NSUM_MAX;
     const float invW = 1.0f / ps[0];
     const float invn = 1.0f / (float)planes;
-    for (int k = 0; k < nscales; ++k) {
+#pragma unroll
+    for (int k = 0; k < PV2_MAX_SCALES; ++k) {
+        if (k >= nscales) break;
         const T* p = reinterpret_cast<const T*>(pp.pred[k]) + poff;
         const T* q = reinterpret_cast<const T*>(pp.pred_bg[k]) + poff;
         T* dp = reinterpret_cast<T*>(pp.dpred[k]) + poff;
@@ -239,12 +291,7 @@ structure_loss_bwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
 #pragma unroll
         for (int j = 0; j < ROWS_PER_THREAD; ++j) {
             if (!ok[j]) continue;
-            float e = __expf(-fabsf(pv[j]));
-            float inv = __fdividef(1.0f, 1.0f + e);
-            float s = pv[j] >= 0.0f ? inv : e * inv;
-            float e2 = __expf(-fabsf(qv[j]));
-            float inv2 = __fdividef(1.0f, 1.0f + e2);
-            float s2 = qv[j] >= 0.0f ? inv2 : e2 * inv2;
+            const float s = sigmoid_fast(pv[j]), s2 = sigmoid_fast(qv[j]);
             float mw = m[j] * w[j];
             // d wiou / d sigma = -[ m w den - (inter+1)(w - m w) ] / den^2
             float dwiou = -(mw * den - ip1 * (w[j] - mw)) * inv_den2;
@@ -271,7 +318,7 @@ extern "C" size_t pv2_structure_loss_workspace_bytes(int planes, int H, int W, i
     (void)nscales;
     int tx;
     int tiles = tiles_of(H, W, &tx);
-    return sizeof(float) * (size_t)NSUM_MAX * ((size_t)planes + (size_t)planes * tiles);
+    return sizeof(float) * ((size_t)NSUM_MAX * ((size_t)planes + (size_t)planes * tiles) + (size_t)PV2_MAX_SCALES * planes);
 }
 
 static int check_common(const void* const* pred, const void* const* pred_bg, const float* mask_fg, int nscales,
@@ -299,14 +346,17 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
     for (int k = 0; k < nscales; ++k) { pp.pred[k] = pred[k]; pp.pred_bg[k] = pred_bg[k]; }
     float* plane_sums = (float*)workspace;
     float* partials = plane_sums + (size_t)planes * NSUM_MAX;
+    float* plane_loss = partials + (size_t)planes * tiles * NSUM_MAX;
     dim3 grid(tiles, planes);
     if (logit_dtype == PV2_F32)
         structure_loss_fwd_kernel<float><<<grid, THREADS, 0, st>>>(pp, mask_fg, mask_bg, nscales, H, W, tx, tiles, partials);
     else
         structure_loss_fwd_kernel<__nv_bfloat16><<<grid, THREADS, 0, st>>>(pp, mask_fg, mask_bg, nscales, H, W, tx, tiles, partials);
     PV2_LAUNCH_CHECK("structure_loss_fwd");
-    structure_loss_finalize_kernel<<<1, 1024, 0, st>>>(partials, plane_sums, loss, planes, tiles, nscales);
-    PV2_LAUNCH_CHECK("structure_loss_finalize");
+    structure_loss_plane_kernel<<<planes, FIN_THREADS, 0, st>>>(partials, plane_sums, plane_loss, tiles, nscales);
+    PV2_LAUNCH_CHECK("structure_loss_plane");
+    structure_loss_mean_kernel<<<1, 256, 0, st>>>(plane_loss, loss, planes, nscales);
+    PV2_LAUNCH_CHECK("structure_loss_mean");
     return 0;
 }
 

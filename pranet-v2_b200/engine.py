@@ -1,42 +1,563 @@
-"""Dispatch layer between the drop-in modules (heads.py / models.py) and the kernels.
+"""The head engine: runs the DSRA head's layers on the pv2 kernels and records its own backward tape.
 
-Every dense contraction, BN, activation and glue op of the head goes through one of the functions
-below, so the choice of implementation is made in exactly one place.
+Why not torch.autograd per layer?  The kernels work on data formats autograd cannot describe (NHWC operand
+tensors in bf16 or split tf32 hi/lo planes, raw split-K slabs, gradients that arrive as several slabs to be
+summed on load), so the whole head is ONE torch.autograd.Function (`run_head`): its forward executes engine ops
+that append backward closures to a tape, its backward replays the tape in reverse.  PyTorch is used for device
+memory (caching allocator), the current stream and parameter storage only.
+
+Precision: `bf16` (tensor cores, kind::f16, bf16 operands / fp32 accumulate) or `fp32` (tensor cores, kind::tf32
+with every operand split into hi + lo tf32 planes and three products per K step ~ fp32 accuracy).
 """
 from __future__ import annotations
 
+import ctypes as C
+import math
+
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
-from . import ops
+from . import _lib
+from .ops import PV2_BF16, PV2_F32, _ratio, _stream
 
-
-def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool):
-    """BasicConv2d body: BN(conv(x)) [+ ReLU] (binary_seg/lib/pranet.py:40-43 + the callers' F.relu)."""
-    y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation)
-    y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.training, bn.momentum, bn.eps)
-    if bn.training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
-    return F.relu(y) if relu else y
+PV2_TF32 = 2
+_PRECISION = "auto"
 
 
-def conv_bias(x, conv: nn.Conv2d):
-    return F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)
+def set_precision(p: str):
+    """'bf16' | 'fp32' | 'auto' (bf16 when the backbone features are bf16 / autocast is on, else fp32)."""
+    global _PRECISION
+    if p not in ("bf16", "fp32", "auto"):
+        raise ValueError(p)
+    _PRECISION = p
 
 
-def concat(xs):
-    return torch.cat(xs, 1)
+def get_precision() -> str:
+    return _PRECISION
 
 
-def mul(a, b):
-    return a * b
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
 
 
-def add_relu(a, b):
-    return F.relu(a + b)
+class Act:
+    """Operand-format activation: NHWC, `ld` stored channels (padded), bf16 [N,H,W,ld] or fp32 [planes,N,H,W,ld].
+    May be a channel slice [off, off+C) of a wider (concat) buffer."""
+    __slots__ = ("t", "N", "H", "W", "C", "ld", "off", "gslabs", "want_grad")
+
+    def __init__(self, t, N, H, W, C, ld, off=0, want_grad=False):
+        self.t, self.N, self.H, self.W, self.C, self.ld, self.off = t, N, H, W, C, ld, off
+        self.gslabs = []          # gradient contributions: (fp32 tensor [M, ld_g], ld_g, off_g)
+        self.want_grad = want_grad
+
+    @property
+    def M(self):
+        return self.N * self.H * self.W
 
 
-def up2_align_corners(x):
-    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (pranet.py:93)."""
-    return ops.interpolate_bilinear(x, scale_factor=2, align_corners=True)
+
+class Raw:
+    """Raw conv output: fp32 [splits, M, ld]; after bn_stats slab 0 holds the split sum."""
+    __slots__ = ("t", "splits", "M", "ld", "C", "dy", "N", "H", "W")
+
+    def __init__(self, t, splits, N, H, W, ld, C):
+        self.t, self.splits, self.N, self.H, self.W, self.ld, self.C = t, splits, N, H, W, ld, C
+        self.M = N * H * W
+        self.dy = None            # operand-format gradient w.r.t. this raw output (set by the apply backward)
+
+
+class Map:
+    """Small fp32 NCHW map (head logits at feature resolution) with gradient accumulation."""
+    __slots__ = ("t", "grads")
+
+    def __init__(self, t):
+        self.t, self.grads = t, []
+
+    def grad(self):
+        if not self.grads:
+            return None
+        g = self.grads[0]
+        for h in self.grads[1:]:
+            g = g + h
+        return g
+
+
+class Engine:
+    def __init__(self, device, precision: str, training: bool, need_grad: bool):
+        self.lib = _lib.load()
+        self.dev = device
+        self.kind = PV2_BF16 if precision == "bf16" else PV2_TF32
+        self.nterms = 1 if precision == "bf16" else 3
+        self.planes = 1 if precision == "bf16" else 2
+        self.cpad = 8 if precision == "bf16" else 4
+        self.op_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.training = training
+        self.need_grad = need_grad
+        self.tape = []
+        self.param_grads = {}     # id(param) -> grad tensor
+
+    # ---- allocation ---------------------------------------------------------------------------------
+    def pad(self, c):
+        return (c + self.cpad - 1) // self.cpad * self.cpad
+
+    def new_act(self, N, H, W, C, ld=None, zero_pad=True):
+        ld = ld or self.pad(C)
+        shape = (N, H, W, ld) if self.planes == 1 else (self.planes, N, H, W, ld)
+        t = torch.zeros(shape, dtype=self.op_dtype, device=self.dev) if (zero_pad and ld != C) else torch.empty(shape, dtype=self.op_dtype, device=self.dev)
+        return Act(t, N, H, W, C, ld, 0, self.need_grad)
+
+    def plane_stride(self, a: Act):
+        return a.N * a.H * a.W * a.ld
+
+    def _es(self):
+        return 2 if self.kind == PV2_BF16 else 4
+
+    def _act_ptr(self, a: Act):
+        return a.t.data_ptr() + a.off * self._es()
+
+    def f32(self, *shape, zero=False):
+        return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.dev)
+
+    def add_param_grad(self, p, g):
+        k = id(p)
+        self.param_grads[k] = g if k not in self.param_grads else self.param_grads[k] + g
+
+    # ---- inputs ---------------------------------------------------------------------------------------
+    def from_nchw(self, x: torch.Tensor, grad_sink=None):
+        """Backbone feature (NCHW fp32 / bf16, any memory format) -> operand tensor.  A bf16 channels_last tensor with
+        C % 8 == 0 is used in place (it already IS the operand layout).  grad_sink(dx) receives the input gradient."""
+        N, Cc, H, W = x.shape
+        if (self.kind == PV2_BF16 and x.dtype == torch.bfloat16 and Cc % 8 == 0
+                and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0):
+            a = Act(x.permute(0, 2, 3, 1), N, H, W, Cc, Cc, 0, self.need_grad)
+        else:
+            xc = x.contiguous()
+            a = self.new_act(N, H, W, Cc)
+            _lib.check(self.lib.pv2_pack_nchw(xc.data_ptr(), PV2_F32 if xc.dtype == torch.float32 else PV2_BF16, a.t.data_ptr(),
+                                              self.plane_stride(a), self.planes, self.kind, N, Cc, H * W, a.ld, 0, _stream()), "pv2_pack_nchw")
+        if self.need_grad and grad_sink is not None:
+            cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+
+            def bwd():
+                if not a.gslabs:
+                    return
+                dx = torch.empty((N, Cc, H, W), dtype=x.dtype, device=self.dev,
+                                 memory_format=torch.channels_last if cl else torch.contiguous_format)
+                self._unpack_slabs(a.gslabs, dx, N, Cc, H * W, cl)
+                grad_sink(dx)
+            self.tape.append(bwd)
+        return a
+
+    def _slab_arrays(self, slabs):
+        pp, k1 = _lib.ptr_array([s[0] for s in slabs])
+        lds, k2 = _lib.int_array([s[1] for s in slabs])
+        offs, k3 = _lib.int_array([s[2] for s in slabs])
+        return pp, lds, offs, (k1, k2, k3)
+
+    def _unpack_slabs(self, slabs, dx, N, Cc, HW, channels_last=False):
+        pp, lds, offs, keep = self._slab_arrays(slabs)
+        _lib.check(self.lib.pv2_unpack_to_nchw(pp, lds, offs, len(slabs), dx.data_ptr(), PV2_F32 if dx.dtype == torch.float32 else PV2_BF16,
+                                               N, Cc, HW, int(channels_last), _stream()), "pv2_unpack_to_nchw")
+
+    # ---- convolution (optionally several convs of identical geometry fused along Cout) ---------------------
+    def conv(self, x: Act, convs, out_nchw_bias=False):
+        """x -> Raw [splits, M, ld] (or, with out_nchw_bias, a biased fp32 NCHW Map straight from the epilogue)."""
+        convs = list(convs)
+        c0 = convs[0]
+        KH, KW = c0.kernel_size
+        dh, dw = c0.dilation
+        for cv in convs:
+            if (cv.kernel_size, cv.dilation, cv.in_channels) != (c0.kernel_size, c0.dilation, c0.in_channels) or cv.stride != (1, 1) or cv.groups != 1:
+                raise ValueError("pv2 conv engine: fused convs must share geometry; stride 1, groups 1 only")
+            if tuple(cv.padding) != (dh * (KH - 1) // 2, dw * (KW - 1) // 2):
+                raise ValueError(f"pv2 conv engine: only 'same' padding is supported (got kernel {cv.kernel_size} dil {cv.dilation} pad {cv.padding})")
+        if x.off != 0 or x.ld != self.pad(x.C) or x.C != c0.in_channels:
+            raise ValueError("pv2 conv engine: conv input must be a whole operand tensor with matching channels")
+        Cin, Cin_p = x.C, x.ld
+        Cout = sum(cv.out_channels for cv in convs)
+        taps = KH * KW
+        lib, st = self.lib, _stream()
+        # forward weights [Cout][tap][Cin_p]
+        wshape = (Cout, taps, Cin_p) if self.planes == 1 else (self.planes, Cout, taps, Cin_p)
+        w_op = (torch.zeros if Cin_p != Cin else torch.empty)(wshape, dtype=self.op_dtype, device=self.dev)
+        o = 0
+        for cv in convs:
+            _lib.check(lib.pv2_weight_pack(cv.weight.data_ptr(), w_op.data_ptr(), Cout * taps * Cin_p, self.planes, self.kind,
+                                           cv.out_channels, Cin, KH, KW, 0, Cin_p, 0, o, st), "pv2_weight_pack")
+            o += cv.out_channels
+        N, H, W = x.N, x.H, x.W
+        if out_nchw_bias:
+            assert len(convs) == 1
+            out = self.f32(N, Cout, H, W)
+            _lib.check(lib.pv2_conv_fwd(self._act_ptr(x), self.plane_stride(x), w_op.data_ptr(), Cout * taps * Cin_p, self.kind, self.nterms,
+                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 1, out.data_ptr(), 0, 1, _ptr(c0.bias), st), "pv2_conv_fwd")
+            res = Map(out)
+        else:
+            ld = (Cout + 3) // 4 * 4
+            splits = lib.pv2_conv_splits_hint(N, H, W, Cin_p, Cout, KH, KW, self.kind, self.nterms)
+            raw_t = self.f32(splits, N * H * W, ld)
+            _lib.check(lib.pv2_conv_fwd(self._act_ptr(x), self.plane_stride(x), w_op.data_ptr(), Cout * taps * Cin_p, self.kind, self.nterms,
+                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 0, raw_t.data_ptr(), ld, splits, None, st), "pv2_conv_fwd")
+            res = Raw(raw_t, splits, N, H, W, ld, Cout)
+        if self.need_grad:
+            self.tape.append(lambda: self._conv_bwd(x, convs, res, KH, KW, dh, dw, Cin, Cin_p, Cout))
+        return res
+
+    def _conv_bwd(self, x: Act, convs, res, KH, KW, dh, dw, Cin, Cin_p, Cout):
+        lib, st = self.lib, _stream()
+        N, H, W, taps = x.N, x.H, x.W, KH * KW
+        if isinstance(res, Map):     # biased NCHW head: gradient arrives as an NCHW map
+            g = res.grad()
+            if g is None:
+                return
+            cv = convs[0]
+            if cv.bias is not None and cv.bias.requires_grad:
+                self.add_param_grad(cv.bias, g.sum((0, 2, 3)))
+            dy = self.new_act(N, H, W, Cout)
+            _lib.check(lib.pv2_pack_nchw(g.contiguous().data_ptr(), PV2_F32, dy.t.data_ptr(), self.plane_stride(dy), self.planes, self.kind,
+                                         N, Cout, H * W, dy.ld, 0, st), "pv2_pack_nchw")
+        else:
+            dy = res.dy
+            if dy is None:
+                return
+        Cout_p = dy.ld
+        # wgrad -> parameter gradients
+        if any(cv.weight.requires_grad for cv in convs):
+            splits = lib.pv2_conv_wgrad_splits_hint(N, H, W, Cin_p, Cout, KH, KW, self.kind)
+            part = self.f32(splits, Cout, taps, Cin_p)
+            _lib.check(lib.pv2_conv_wgrad(self._act_ptr(dy), self.plane_stride(dy), self._act_ptr(x), self.plane_stride(x), self.kind, self.nterms,
+                                          N, H, W, Cin_p, Cout_p, Cout, KH, KW, dh, dw, part.data_ptr(), splits, st), "pv2_conv_wgrad")
+            o = 0
+            for cv in convs:
+                if cv.weight.requires_grad:
+                    dw_ = torch.empty_like(cv.weight, memory_format=torch.contiguous_format)
+                    _lib.check(lib.pv2_wgrad_unpack(part.data_ptr(), Cout * taps * Cin_p, splits, dw_.data_ptr(), cv.out_channels, Cin, KH, KW,
+                                                    Cin_p, o, st), "pv2_wgrad_unpack")
+                    self.add_param_grad(cv.weight, dw_)
+                o += cv.out_channels
+        # dgrad -> raw slabs appended to the input's gradient list
+        if x.want_grad and x.gslabs is not None:
+            wshape = (Cin, taps, Cout_p) if self.planes == 1 else (self.planes, Cin, taps, Cout_p)
+            wt = (torch.zeros if Cout_p != Cout else torch.empty)(wshape, dtype=self.op_dtype, device=self.dev)
+            o = 0
+            for cv in convs:
+                _lib.check(lib.pv2_weight_pack(cv.weight.data_ptr(), wt.data_ptr(), Cin * taps * Cout_p, self.planes, self.kind,
+                                               cv.out_channels, Cin, KH, KW, 1, Cout_p, o, 0, st), "pv2_weight_pack")
+                o += cv.out_channels
+            ld = (Cin + 3) // 4 * 4
+            splits = lib.pv2_conv_splits_hint(N, H, W, Cout_p, Cin, KH, KW, self.kind, self.nterms)
+            dx = self.f32(splits, N * H * W, ld)
+            _lib.check(lib.pv2_conv_fwd(self._act_ptr(dy), self.plane_stride(dy), wt.data_ptr(), Cin * taps * Cout_p, self.kind, self.nterms,
+                                        N, H, W, Cout_p, Cin, KH, KW, dh, dw, 0, dx.data_ptr(), ld, splits, None, st), "pv2_conv_fwd(dgrad)")
+            for s in range(splits):
+                x.gslabs.append((dx[s], ld, 0))
+
+    # ---- BN (+ combine, multiplier, relu) -> operand slice or NCHW map -------------------------------------------
+    def _affine(self, raw: Raw, off, C, bn, bias):
+        """(scale, shift, mean, invstd) for raw[:, off:off+C]; training BN computes batch stats and updates running stats."""
+        lib, st = self.lib, _stream()
+        scale, shift = self.f32(C), self.f32(C)
+        if bn is None:     # plain bias
+            scale.fill_(1.0)
+            if bias is not None:
+                shift.copy_(bias.detach())
+            else:
+                shift.zero_()
+            return scale, shift, None, None
+        if self.training:
+            raise RuntimeError("internal: training-mode BN statistics are computed per Raw, see bn_apply")
+        _lib.check(lib.pv2_bn_eval_affine(C, _ptr(bn.weight), _ptr(bn.bias), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                          float(bn.eps), scale.data_ptr(), shift.data_ptr(), st), "pv2_bn_eval_affine")
+        return scale, shift, None, None
+
+    def _bn_train_stats(self, raw: Raw, off, C, bn):
+        lib, st = self.lib, _stream()
+        scale, shift, mean, inv = self.f32(C), self.f32(C), self.f32(C), self.f32(C)
+        ws = self.f32(lib.pv2_bn_workspace_floats(raw.M, C))
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        track = bn.track_running_stats and bn.running_mean is not None
+        _lib.check(lib.pv2_bn_stats(raw.t.data_ptr() + off * 4, raw.M * raw.ld, raw.splits, raw.M, C, raw.ld, _ptr(bn.weight), _ptr(bn.bias),
+                                    float(bn.eps), mom, _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
+                                    _ptr(bn.num_batches_tracked) if track else None, mean.data_ptr(), inv.data_ptr(), scale.data_ptr(),
+                                    shift.data_ptr(), ws.data_ptr(), st), "pv2_bn_stats")
+        return scale, shift, mean, inv
+
+    def bn_apply(self, src1, src2=None, combine=0, mult: Act = None, relu=False, out: Act = None, out_map=False):
+        """src = (raw, channel offset, C, bn module or None, bias or None).  Writes into `out` (an Act or Act slice) or
+        returns a Map when out_map.  Covers BasicConv2d's BN (+ caller's ReLU), RFB's relu(a + b), the partial
+        decoder's products, and biased / BN'd DSRA heads."""
+        lib, st = self.lib, _stream()
+        raw1, off1, Cc, bn1, bias1 = src1
+        stats = []
+        for (raw, off, c, bn, bias) in ([src1] + ([src2] if src2 else [])):
+            if bn is not None and self.training:
+                stats.append(self._bn_train_stats(raw, off, c, bn))      # also folds the split-K slabs into slab 0
+            else:
+                stats.append(self._affine(raw, off, c, bn, bias))
+        (s1, b1, m1, i1) = stats[0]
+        (s2, b2, m2, i2) = stats[1] if src2 else (None, None, None, None)
+        raw2, off2 = (src2[0], src2[1]) if src2 else (None, 0)
+        M, HW = raw1.M, raw1.H * raw1.W
+        if out_map:
+            out_t = self.f32(raw1.N, Cc, raw1.H, raw1.W)
+            res = Map(out_t)
+            o_ptr, o_plane, o_planes, o_ld, o_off, o_nchw = out_t.data_ptr(), 0, 1, 0, 0, 1
+        else:
+            if out is None:
+                out = self.new_act(raw1.N, raw1.H, raw1.W, Cc)
+            res = out
+            o_ptr, o_plane, o_planes, o_ld, o_off, o_nchw = out.t.data_ptr(), self.plane_stride(out), self.planes, out.ld, out.off, 0
+        # slab 0 already holds the split-K sum when training-mode BN statistics ran over this raw output
+        ns1 = 1 if (bn1 is not None and self.training) else raw1.splits
+        ns2 = (1 if (src2[3] is not None and self.training) else raw2.splits) if src2 else 1
+        fwd_args = (raw1.t.data_ptr(), raw1.ld, off1, ns1, raw1.M * raw1.ld, s1.data_ptr(), b1.data_ptr(),
+                    _ptr(raw2.t) if raw2 else None, raw2.ld if raw2 else 0, off2, ns2, (raw2.M * raw2.ld) if raw2 else 0,
+                    _ptr(s2), _ptr(b2), combine,
+                    (mult.t.data_ptr() if mult is not None else None), self.plane_stride(mult) if mult is not None else 0,
+                    self.planes, mult.ld if mult is not None else 0, mult.off if mult is not None else 0, int(relu), M, Cc, HW)
+        _lib.check(lib.pv2_act_apply(*fwd_args, o_ptr, o_plane, o_planes, o_ld, o_off, o_nchw, self.kind, st), "pv2_act_apply")
+        if self.need_grad:
+            keep = (s1, b1, s2, b2, m1, i1, m2, i2)
+
+            def bwd():
+                _alive = keep     # fwd_args holds raw device pointers into these tensors: keep them referenced
+                if out_map:
+                    g = res.grad()
+                    if g is None:
+                        return
+                    g = g.contiguous()
+                    dz = (None, None, None, 0, g.data_ptr())
+                    hold = g
+                else:
+                    slabs = res.gslabs if res.gslabs is not None else None
+                    if not slabs:
+                        return
+                    pp, lds, offs, hold = self._slab_arrays(slabs)
+                    dz = (pp, lds, offs, len(slabs), None)
+                bn_train = 1 if (bn1 is not None and self.training) else 0
+                dy1, dy1_ptr = self._dy_slice(raw1, off1)
+                dy2, dy2_ptr = self._dy_slice(raw2, off2) if src2 else (None, None)
+                dmult = self.f32(M, Cc) if (mult is not None and mult.want_grad) else None
+                dg1, db1 = self.f32(Cc), self.f32(Cc)
+                dg2, db2 = (self.f32(Cc), self.f32(Cc)) if src2 else (None, None)
+                ws = self.f32(lib.pv2_bn_workspace_floats(M, Cc))
+                _lib.check(lib.pv2_bn_act_bwd(*fwd_args, *dz, _ptr(m1), _ptr(i1), _ptr(m2), _ptr(i2), bn_train,
+                                              _ptr(dmult), Cc, dy1_ptr, self.plane_stride(dy1), self.planes, dy1.ld,
+                                              dy2_ptr, self.plane_stride(dy2) if dy2 else 0, self.planes, dy2.ld if dy2 else 0,
+                                              dg1.data_ptr(), db1.data_ptr(), _ptr(dg2), _ptr(db2), ws.data_ptr(), self.kind, _stream()),
+                           "pv2_bn_act_bwd")
+                self._route_bn_grads(src1, dg1, db1, bn_train)
+                if src2:
+                    self._route_bn_grads(src2, dg2, db2, bn_train)
+                if dmult is not None:
+                    self._add_grad(mult, dmult, Cc, 0)
+            self.tape.append(bwd)
+        return res
+
+    def _dy_slice(self, raw: Raw, off):
+        """Operand-format gradient buffer of a raw conv output (allocated once; horizontally fused convs fill slices)."""
+        if raw.dy is None:
+            raw.dy = self.new_act(raw.N, raw.H, raw.W, raw.C)
+        return raw.dy, raw.dy.t.data_ptr() + off * self._es()
+
+    def _route_bn_grads(self, src, dgamma, dbeta, bn_train):
+        raw, off, Cc, bn, bias = src
+        if bn is not None:
+            if bn.weight is not None and bn.weight.requires_grad:
+                # training BN: the kernel's sum(da*yhat) IS dgamma.  eval BN (affine): z = y*s + b with s = gamma*r, b = beta - rm*s,
+                # r = rsqrt(rv+eps), so dgamma = r * (sum(da*y) - rm*sum(da))
+                self.add_param_grad(bn.weight, dgamma if bn_train else (dgamma - dbeta * bn.running_mean) * torch.rsqrt(bn.running_var + bn.eps))
+            if bn.bias is not None and bn.bias.requires_grad:
+                self.add_param_grad(bn.bias, dbeta)
+        elif bias is not None and bias.requires_grad:
+            self.add_param_grad(bias, dbeta)
+
+    def _add_grad(self, a: Act, g, ld, off):
+        if a.gslabs is not None:
+            a.gslabs.append((g, ld, off))
+        else:
+            raise RuntimeError("internal: gradient routed to an operand slice without an owner")
+
+    # ---- concat: allocate the wide buffer first, producers write slices ---------------------------------------------
+    def concat_buffer(self, N, H, W, parts):
+        """parts = list of channel counts -> (whole Act, [slice Acts]).  Gradients w.r.t. the whole buffer are seen by
+        the slices as (slab, ld, off + slice offset)."""
+        total = sum(parts)
+        whole = self.new_act(N, H, W, total)
+        slices, o = [], 0
+        for c in parts:
+            s = Act(whole.t, N, H, W, c, whole.ld, o, self.need_grad)
+            s.gslabs = _SliceGrads(whole, o)
+            slices.append(s)
+            o += c
+        return whole, slices
+
+    # ---- x2 align-corners upsample (partial decoder) ---------------------------------------------------------------------
+    def up2(self, a: Act):
+        lib = self.lib
+        out = self.new_act(a.N, 2 * a.H, 2 * a.W, a.C)
+        _lib.check(lib.pv2_up2_nhwc_fwd(a.t.data_ptr(), self.plane_stride(a), self.planes, a.ld, a.off, out.t.data_ptr(), self.plane_stride(out),
+                                        self.planes, out.ld, 0, a.N, a.H, a.W, a.C, self.kind, _stream()), "pv2_up2_nhwc_fwd")
+        if self.need_grad:
+            def bwd():
+                if not out.gslabs:
+                    return
+                pp, lds, offs, hold = self._slab_arrays(list(out.gslabs))
+                din = self.f32(a.M, a.C)
+                _lib.check(lib.pv2_up2_nhwc_bwd(pp, lds, offs, len(out.gslabs), din.data_ptr(), a.C, a.N, a.H, a.W, a.C, _stream()), "pv2_up2_nhwc_bwd")
+                self._add_grad(a, din, a.C, 0)
+            self.tape.append(bwd)
+        return out
+
+    # ---- small NCHW maps: bilinear resize, DSRA fusion, V1 residual ---------------------------------------------------------
+    def resize(self, m: Map, scale_factor=None, size=None, final=False):
+        t = m.t
+        B, Cc, ih, iw = t.shape
+        if size is None:
+            oh, ow = int(math.floor(ih * scale_factor)), int(math.floor(iw * scale_factor))
+        else:
+            oh, ow = size
+        rh, rw = _ratio(ih, oh, False, scale_factor), _ratio(iw, ow, False, scale_factor)
+        out = self.f32(B, Cc, oh, ow)
+        _lib.check(self.lib.pv2_bilinear_fwd(t.data_ptr(), out.data_ptr(), B * Cc, ih, iw, oh, ow, rh, rw, 0, PV2_F32, _stream()), "pv2_bilinear_fwd")
+        res = Map(out)
+        if self.need_grad:
+            def bwd():
+                g = res.grad()
+                if g is None:
+                    return
+                g = g.contiguous().float()
+                din = self.f32(B, Cc, ih, iw)
+                _lib.check(self.lib.pv2_bilinear_bwd(g.data_ptr(), din.data_ptr(), B * Cc, ih, iw, oh, ow, rh, rw, 0, PV2_F32, _stream()), "pv2_bilinear_bwd")
+                m.grads.append(din)
+            self.tape.append(bwd)
+        return res
+
+    def fuse(self, fg: Map, deep_fg: Map, deep_bg: Map, use_softmax=True, scale_factor=None):
+        B, Cc, h, w = fg.t.shape
+        dh, dw = deep_fg.t.shape[-2:]
+        rh, rw = _ratio(dh, h, False, scale_factor), _ratio(dw, w, False, scale_factor)
+        out = self.f32(B, Cc, h, w)
+        lib = self.lib
+        _lib.check(lib.pv2_dsra_fuse_fwd(fg.t.data_ptr(), deep_fg.t.data_ptr(), deep_bg.t.data_ptr(), out.data_ptr(), B, Cc, h, w, dh, dw, rh, rw,
+                                         int(use_softmax), _stream()), "pv2_dsra_fuse_fwd")
+        res = Map(out)
+        if self.need_grad:
+            def bwd():
+                g = res.grad()
+                if g is None:
+                    return
+                g = g.contiguous()
+                dfg, dd = self.f32(B, Cc, h, w), self.f32(B, Cc, h, w)
+                _lib.check(lib.pv2_dsra_fuse_bwd(g.data_ptr(), fg.t.data_ptr(), deep_fg.t.data_ptr(), deep_bg.t.data_ptr(), dfg.data_ptr(), dd.data_ptr(),
+                                                 B, Cc, h, w, dh, dw, rh, rw, int(use_softmax), _stream()), "pv2_dsra_fuse_bwd")
+                fg.grads.append(dfg)
+                if not (Cc == 1 and use_softmax):     # softmax over one channel is constant: exactly zero gradient
+                    ddeep = self.f32(B, Cc, dh, dw)
+                    _lib.check(lib.pv2_bilinear_bwd(dd.data_ptr(), ddeep.data_ptr(), B * Cc, dh, dw, h, w, rh, rw, 0, PV2_F32, _stream()), "pv2_bilinear_bwd")
+                    deep_fg.grads.append(ddeep)
+                    deep_bg.grads.append(-ddeep)
+            self.tape.append(bwd)
+        return res
+
+    def add_maps(self, a: Map, b: Map):
+        res = Map(a.t + b.t)
+        if self.need_grad:
+            def bwd():
+                g = res.grad()
+                if g is not None:
+                    a.grads.append(g)
+                    b.grads.append(g)
+            self.tape.append(bwd)
+        return res
+
+    def ra_v1(self, x: torch.Tensor, crop: Map, grad_sink):
+        """V1 reverse attention on an NCHW backbone feature: (1 - sigmoid(crop)) * x -> NCHW tensor (then packed by from_nchw)."""
+        lib = self.lib
+        xc = x.contiguous()
+        B, Cc, h, w = xc.shape
+        y = torch.empty_like(xc)
+        dt = PV2_F32 if xc.dtype == torch.float32 else PV2_BF16
+        _lib.check(lib.pv2_ra_v1_scale_fwd(xc.data_ptr(), crop.t.data_ptr(), y.data_ptr(), B, Cc, h * w, dt, _stream()), "pv2_ra_v1_scale_fwd")
+
+        def sink(dy):
+            dy = dy.contiguous()
+            dx, dcrop = torch.empty_like(xc), self.f32(B, 1, h, w)
+            _lib.check(lib.pv2_ra_v1_scale_bwd(dy.data_ptr(), xc.data_ptr(), crop.t.data_ptr(), dx.data_ptr(), dcrop.data_ptr(), B, Cc, h * w, dt, _stream()),
+                       "pv2_ra_v1_scale_bwd")
+            crop.grads.append(dcrop)
+            grad_sink(dx)
+        return y, sink
+
+    def backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []
+
+
+class _SliceGrads:
+    """gslabs proxy of a concat slice: gradients of the WHOLE buffer, seen at this slice's channel offset."""
+
+    def __init__(self, whole: Act, off: int):
+        self.whole, self.off = whole, off
+
+    def __bool__(self):
+        return bool(self.whole.gslabs)
+
+    def __len__(self):
+        return len(self.whole.gslabs)
+
+    def __iter__(self):
+        return iter([(g, ld, o + self.off) for (g, ld, o) in self.whole.gslabs])
+
+    def __getitem__(self, i):
+        g, ld, o = self.whole.gslabs[i]
+        return (g, ld, o + self.off)
+
+    def append(self, item):
+        raise RuntimeError("internal: a concat slice has exactly one consumer (the conv over the whole buffer)")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autograd boundary
+# ------------------------------------------------------------------------------------------------------------
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, runner, n_inputs, precision, training, *tensors):
+        inputs, params = tensors[:n_inputs], tensors[n_inputs:]
+        need_grad = any(ctx.needs_input_grad[4:])
+        eng = Engine(inputs[0].device, precision, training, need_grad)
+        in_grads = [None] * n_inputs
+        outs = runner(eng, inputs, in_grads)
+        ctx.eng, ctx.in_grads, ctx.params, ctx.outs = eng, in_grads, params, outs
+        ctx.n_inputs = n_inputs
+        return tuple(o.t for o in outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        eng = ctx.eng
+        for o, g in zip(ctx.outs, gouts):
+            if g is not None:
+                o.grads.append(g)
+        eng.backward()
+        grads = []
+        for i in range(ctx.n_inputs):
+            grads.append(ctx.in_grads[i] if ctx.needs_input_grad[4 + i] else None)
+        for j, p in enumerate(ctx.params):
+            g = eng.param_grads.get(id(p)) if ctx.needs_input_grad[4 + ctx.n_inputs + j] else None
+            grads.append(g)
+        ctx.eng = ctx.outs = None
+        return (None, None, None, None, *grads)
+
+
+def run_head(runner, inputs, params, training):
+    """runner(engine, inputs, in_grads) -> list of Map.  `inputs` are NCHW feature tensors, `params` the list of
+    parameters the runner touches (so autograd can hand their gradients back)."""
+    for t in inputs:
+        if not t.is_cuda:
+            raise RuntimeError("pranet_v2_b200 head is CUDA-only (sm_100a); got a CPU tensor and there is no CPU fallback")
+    prec = _PRECISION
+    if prec == "auto":
+        prec = "bf16" if (inputs[0].dtype == torch.bfloat16 or torch.is_autocast_enabled()) else "fp32"
+    with torch.autocast("cuda", enabled=False):
+        return _HeadFn.apply(runner, len(inputs), prec, training, *inputs, *params)

@@ -3,19 +3,30 @@
 Parameter containers (and therefore state_dict keys) are exactly the reference's -- `X.conv.weight`,
 `X.bn.{weight,bias,running_mean,running_var,num_batches_tracked}` for every BasicConv2d, `branch{b}.{i}`
 inside RFB_modified, `conv_upsample{1..5} / conv_concat{2,3} / conv4 / conv5_fg / conv5_bg` inside
-aggregation (binary_seg/lib/pranet.py:31-125) -- so `RES-V2.pth` / `PVT-V2.pth` load unchanged.  What the
-forward passes *do* is dispatched to the pv2 kernels through `engine` / `ops`.
+aggregation (binary_seg/lib/pranet.py:31-125) -- so `RES-V2.pth` / `PVT-V2.pth` load unchanged.  The modules own
+no computation of their own: `forward` hands a *runner* to `engine.run_head`, and the `*_run` functions below
+describe each block in terms of engine ops (tcgen05 convs, BN statistics / apply kernels, NHWC upsample ...).
+Every block is also callable on its own with NCHW tensors, like the reference modules.
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
-from . import engine, ops
+from . import engine as E
 
 
-def _pair(v):
-    return (v, v) if isinstance(v, int) else tuple(v)
+def _params(*mods):
+    out = []
+    for m in mods:
+        out += [p for p in m.parameters()]
+    return out
+
+
+def _sink(in_grads, i):
+    def f(g):
+        in_grads[i] = g if in_grads[i] is None else in_grads[i] + g
+    return f
 
 
 class BasicConv2d(nn.Module):
@@ -28,12 +39,39 @@ class BasicConv2d(nn.Module):
                               padding=padding, dilation=dilation, bias=False)
         self.bn = nn.BatchNorm2d(out_planes)
 
+    def run(self, eng, x: E.Act, relu=False, out=None, out_map=False):
+        raw = eng.conv(x, [self.conv])
+        return eng.bn_apply((raw, 0, self.conv.out_channels, self.bn, None), relu=relu, out=out, out_map=out_map)
+
     def forward(self, x, relu: bool = False):
-        return engine.conv_bn_act(x, self.conv, self.bn, relu)
+        def runner(eng, inputs, in_grads):
+            return [self.run(eng, eng.from_nchw(inputs[0], _sink(in_grads, 0)), relu=relu, out_map=True)]
+        return E.run_head(runner, [x], _params(self), self.training)[0]
+
+
+def rfb_run(eng, rfb: "RFB_modified", raw1x1: E.Raw, off: int, out_map=False):
+    """RFB_modified.forward (pranet.py:75-83) given the raw output of the horizontally fused 1x1 convs
+    [branch0.0 | branch1.0 | branch2.0 | branch3.0 | conv_res] starting at channel `off` of `raw1x1`."""
+    c = rfb.conv_res.conv.out_channels
+    whole, sl = eng.concat_buffer(raw1x1.N, raw1x1.H, raw1x1.W, [c] * 4)
+    eng.bn_apply((raw1x1, off, c, rfb.branch0[0].bn, None), out=sl[0])
+    for b in (1, 2, 3):
+        br = getattr(rfb, f"branch{b}")
+        t = eng.bn_apply((raw1x1, off + b * c, c, br[0].bn, None))
+        t = br[1].run(eng, t)
+        t = br[2].run(eng, t)
+        br[3].run(eng, t, out=sl[b])
+    raw_cat = eng.conv(whole, [rfb.conv_cat.conv])
+    return eng.bn_apply((raw_cat, 0, c, rfb.conv_cat.bn, None), src2=(raw1x1, off + 4 * c, c, rfb.conv_res.bn, None), combine=1, relu=True,
+                        out_map=out_map)
+
+
+def rfb_convs(rfb: "RFB_modified"):
+    return [rfb.branch0[0].conv, rfb.branch1[0].conv, rfb.branch2[0].conv, rfb.branch3[0].conv, rfb.conv_res.conv]
 
 
 class RFB_modified(nn.Module):
-    """Receptive-field block (pranet.py:46-83): five 1x1 reductions of the same input, three
+    """Receptive-field block (pranet.py:46-83): five 1x1 reductions of the same input (ONE fused GEMM here), three
     (1xk, kx1, 3x3 dil k) chains, 3x3 over the concat, residual add, ReLU."""
 
     def __init__(self, in_channel, out_channel):
@@ -49,8 +87,40 @@ class RFB_modified(nn.Module):
         self.conv_res = BasicConv2d(in_channel, out_channel, 1)
 
     def forward(self, x):
-        outs = [self.branch0(x), self.branch1(x), self.branch2(x), self.branch3(x)]
-        return engine.add_relu(self.conv_cat(engine.concat(outs)), self.conv_res(x))
+        def runner(eng, inputs, in_grads):
+            a = eng.from_nchw(inputs[0], _sink(in_grads, 0))
+            return [rfb_run(eng, self, eng.conv(a, rfb_convs(self)), 0, out_map=True)]
+        return E.run_head(runner, [x], _params(self), self.training)[0]
+
+
+def aggregation_run(eng, agg: "aggregation", x1: E.Act, x2: E.Act, x3: E.Act):
+    """aggregation.forward (pranet.py:109-125): x1 deepest (H/32), x2 (H/16), x3 (H/8).  Returns the list of
+    head Maps ([fg, bg] for V2, [single] for V1)."""
+    c = x1.C
+    up_x1 = eng.up2(x1)
+    upup_x1 = eng.up2(up_x1)
+    up_x2 = eng.up2(x2)
+    # conv_upsample1 and conv_upsample4 read the same tensor: one GEMM
+    raw_a = eng.conv(up_x1, [agg.conv_upsample1.conv, agg.conv_upsample4.conv])
+    cat2, s2 = eng.concat_buffer(x2.N, x2.H, x2.W, [c, c])
+    eng.bn_apply((raw_a, 0, c, agg.conv_upsample1.bn, None), mult=x2, out=s2[0])                       # x2_1
+    eng.bn_apply((raw_a, c, c, agg.conv_upsample4.bn, None), out=s2[1])
+    x2_2 = agg.conv_concat2.run(eng, cat2)
+    raw_b = eng.conv(upup_x1, [agg.conv_upsample2.conv])
+    raw_c = eng.conv(up_x2, [agg.conv_upsample3.conv])
+    cat3, s3 = eng.concat_buffer(x3.N, x3.H, x3.W, [c, 2 * c])
+    eng.bn_apply((raw_b, 0, c, agg.conv_upsample2.bn, None), src2=(raw_c, 0, c, agg.conv_upsample3.bn, None),
+                 combine=2, mult=x3, out=s3[0])                                                         # x3_1
+    agg.conv_upsample5.run(eng, eng.up2(x2_2), out=s3[1])
+    x3_2 = agg.conv_concat3.run(eng, cat3)
+    x = agg.conv4.run(eng, x3_2)
+    heads = [agg.conv5] if hasattr(agg, "conv5") else [agg.conv5_fg, agg.conv5_bg]
+    raw_h = eng.conv(x, heads)                                                                         # biased 1x1 heads, fused
+    outs, o = [], 0
+    for h in heads:
+        outs.append(eng.bn_apply((raw_h, o, h.out_channels, None, h.bias), out_map=True))
+        o += h.out_channels
+    return outs
 
 
 class aggregation(nn.Module):
@@ -74,68 +144,64 @@ class aggregation(nn.Module):
             self.conv5_fg = nn.Conv2d(3 * c, num_class, 1)
             self.conv5_bg = nn.Conv2d(3 * c, num_class, 1)
 
-    def trunk(self, x1, x2, x3):
-        up = engine.up2_align_corners
-        x2_1 = engine.mul(self.conv_upsample1(up(x1)), x2)
-        x3_1 = engine.mul(engine.mul(self.conv_upsample2(up(up(x1))), self.conv_upsample3(up(x2))), x3)
-        x2_2 = self.conv_concat2(engine.concat([x2_1, self.conv_upsample4(up(x1))]))
-        x3_2 = self.conv_concat3(engine.concat([x3_1, self.conv_upsample5(up(x2_2))]))
-        return self.conv4(x3_2)
-
     def forward(self, x1, x2, x3):
-        x = self.trunk(x1, x2, x3)
-        if hasattr(self, "conv5"):
-            return engine.conv_bias(x, self.conv5)
-        return engine.conv_bias(x, self.conv5_fg), engine.conv_bias(x, self.conv5_bg)
+        def runner(eng, inputs, in_grads):
+            acts = [eng.from_nchw(t, _sink(in_grads, i)) for i, t in enumerate(inputs)]
+            return aggregation_run(eng, self, *acts)
+        outs = E.run_head(runner, [x1, x2, x3], _params(self), self.training)
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
 
-class DualHeadStage(nn.Module):
-    """One DSRA stage of a multiclass host decoder: fg / bg heads on the same decoder feature, then
-    fg <- fg + fg * softmax_c(resize(deeper_fg) - resize(deeper_bg)).
+# ----------------------------------------------------------------------------------------------------------
+# DSRA stages of the multiclass host decoders
+# ----------------------------------------------------------------------------------------------------------
+def dual_heads_run(eng, fg_mod, bg_mod, feat: E.Act):
+    """fg / bg heads on the same decoder feature as ONE GEMM (N = 2*num_class).  BasicConv2d heads (conv + BN:
+    EMCAD/lib/decoders.py:434-444, MERIT/lib/decoders.py:298-322) or biased 1x1 nn.Conv2d (MIST/lib/MIST.py:403-412)."""
+    if isinstance(fg_mod, BasicConv2d):
+        raw = eng.conv(feat, [fg_mod.conv, bg_mod.conv])
+        c = fg_mod.conv.out_channels
+        return (eng.bn_apply((raw, 0, c, fg_mod.bn, None), out_map=True), eng.bn_apply((raw, c, c, bg_mod.bn, None), out_map=True))
+    raw = eng.conv(feat, [fg_mod, bg_mod])
+    c = fg_mod.out_channels
+    return (eng.bn_apply((raw, 0, c, None, fg_mod.bias), out_map=True), eng.bn_apply((raw, c, c, None, bg_mod.bias), out_map=True))
 
-    Mirrors `ConvBlock{k}_fg/_bg` + the fusion lines of EMCAD_dual (EMCAD/lib/decoders.py:434-444,
-    454-523) and CASCADE_Add_dual (MERIT/lib/decoders.py:298-322, 342-428); with bn=False the heads are
-    the biased 1x1 convs of MIST's CAM (MIST/lib/MIST.py:403-449).  The two head modules are registered
-    on the *parent* under the reference's attribute names by `attach_dual_heads`."""
 
-    def __init__(self, fg: nn.Module, bg: nn.Module, use_softmax=True):
+class DSRAStages(nn.Module):
+    """The DSRA part of EMCAD_dual / CASCADE_Add_dual / CAM as one plug-in: owns `<name>_fg` / `<name>_bg` for
+    the four stages (registered on the PARENT under the reference's attribute names by `attach`) and runs
+        fg_k, bg_k = heads(d_k);  fg_k <- fg_k + fg_k * softmax_c(resize(fg_{k+1}) - resize(bg_{k+1}))
+    deep -> shallow, returning [d4_fg, d3_fg, d2_fg, d1_fg, d4_bg, d3_bg, d2_bg, d1_bg]
+    (EMCAD/lib/decoders.py:454-526; MERIT/lib/decoders.py:342-431; MIST/lib/MIST.py:418-451)."""
+
+    def __init__(self, parent: nn.Module, channels, num_class, names=("ConvBlock4", "ConvBlock3", "ConvBlock2", "ConvBlock1"),
+                 kernel_sizes=(1, 3, 3, 3), bn=True, use_softmax=True):
         super().__init__()
-        object.__setattr__(self, "_fg", fg)   # not registered here: owned by the parent
-        object.__setattr__(self, "_bg", bg)
         self.use_softmax = use_softmax
+        mods = []
+        for c, n, k in zip(channels, names, kernel_sizes):
+            if bn:
+                fg, bg = BasicConv2d(c, num_class, k, padding=k // 2), BasicConv2d(c, num_class, k, padding=k // 2)
+            else:
+                fg, bg = nn.Conv2d(c, num_class, 1), nn.Conv2d(c, num_class, 1)
+            setattr(parent, n + "_fg", fg)
+            setattr(parent, n + "_bg", bg)
+            mods.append((fg, bg))
+        object.__setattr__(self, "_mods", mods)      # owned (registered) by the parent, not by this helper
 
-    def forward(self, feat, deeper_fg=None, deeper_bg=None):
-        if isinstance(self._fg, BasicConv2d):
-            fg, bg = self._fg(feat), self._bg(feat)
-        else:
-            fg, bg = engine.conv_bias(feat, self._fg), engine.conv_bias(feat, self._bg)
-        if deeper_fg is not None:
-            fg = ops.dsra_fuse(fg, deeper_fg, deeper_bg, self.use_softmax)
-        return fg, bg
+    def forward(self, feats):
+        mods = self._mods
 
-
-def attach_dual_heads(parent: nn.Module, channels, num_class, names=("ConvBlock4", "ConvBlock3", "ConvBlock2", "ConvBlock1"),
-                      kernel_sizes=(1, 3, 3, 3), bn=True, use_softmax=True):
-    """Registers `<name>_fg` / `<name>_bg` on `parent` (same keys as the reference decoders) and returns
-    the list of DualHeadStage callables, deep -> shallow."""
-    stages = []
-    for c, n, k in zip(channels, names, kernel_sizes):
-        if bn:
-            fg, bg = BasicConv2d(c, num_class, k, padding=k // 2), BasicConv2d(c, num_class, k, padding=k // 2)
-        else:
-            fg, bg = nn.Conv2d(c, num_class, 1), nn.Conv2d(c, num_class, 1)
-        setattr(parent, n + "_fg", fg)
-        setattr(parent, n + "_bg", bg)
-        stages.append(DualHeadStage(fg, bg, use_softmax))
-    return stages
-
-
-def dsra_cascade(stages, feats):
-    """Runs the DSRA stages over decoder features d4..d1 (deep -> shallow) and returns
-    [d4_fg, d3_fg, d2_fg, d1_fg, d4_bg, d3_bg, d2_bg, d1_bg] like EMCAD_dual.forward (decoders.py:526)."""
-    fgs, bgs = [], []
-    for st, d in zip(stages, feats):
-        fg, bg = st(d, fgs[-1] if fgs else None, bgs[-1] if bgs else None)
-        fgs.append(fg)
-        bgs.append(bg)
-    return fgs + bgs
+        def runner(eng, inputs, in_grads):
+            fgs, bgs = [], []
+            for i, (x, (fg_m, bg_m)) in enumerate(zip(inputs, mods)):
+                fg, bg = dual_heads_run(eng, fg_m, bg_m, eng.from_nchw(x, _sink(in_grads, i)))
+                if fgs:
+                    fg = eng.fuse(fg, fgs[-1], bgs[-1], self.use_softmax, None)
+                fgs.append(fg)
+                bgs.append(bg)
+            return fgs + bgs
+        params = []
+        for fg_m, bg_m in mods:
+            params += _params(fg_m, bg_m)
+        return list(E.run_head(runner, list(feats), params, mods[0][0].training))

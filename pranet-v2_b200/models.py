@@ -15,9 +15,9 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from . import engine, ops
+from . import engine as E
 from .backbones import PvtV2B2, Res2Net50
-from .heads import BasicConv2d, RFB_modified, aggregation
+from .heads import BasicConv2d, RFB_modified, _sink, aggregation, aggregation_run, rfb_convs, rfb_run
 
 RES2NET_CH = (512, 1024, 2048)
 PVT_CH = (128, 320, 512)
@@ -50,13 +50,15 @@ class _PraNetBase(nn.Module):
                 setattr(self, f"ra3_conv4_{t}", BasicConv2d(64, num_class, kernel_size=3, padding=1))
                 setattr(self, f"ra2_conv4_{t}", BasicConv2d(64, num_class, kernel_size=3, padding=1))
 
-    def _stack(self, stage, x, n):
-        """ra{stage}_conv1 without ReLU, then ra{stage}_conv2..n each followed by ReLU
-        (pranet.py:357-360, 378-380, 400-402)."""
-        x = getattr(self, f"ra{stage}_conv1")(x)
+    def _stack(self, eng, stage, t, n):
+        """ra{stage}_conv2..n, each followed by ReLU (pranet.py:358-360, 379-380, 401-402); `t` is the BN'd (no ReLU)
+        output of ra{stage}_conv1."""
         for i in range(2, n + 1):
-            x = getattr(self, f"ra{stage}_conv{i}")(x, relu=True)
-        return x
+            t = getattr(self, f"ra{stage}_conv{i}").run(eng, t, relu=True)
+        return t
+
+    def head_parameters(self):
+        return [p for n, p in self.named_parameters() if not n.startswith(("backbone.", "resnet.", "conv."))]
 
     def load_backbone(self, state_dict):
         """Key-filtered merge, like pranet.py:148-152."""
@@ -78,27 +80,40 @@ class _V2Mixin(_PraNetBase):
 
     def forward_head(self, x2, x3, x4):
         """pranet.py:343-417 -> (l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg)."""
-        up = ops.interpolate_bilinear
         sd = self.sem_downsample
-        x2_rfb, x3_rfb, x4_rfb = self.rfb2_1(x2), self.rfb3_1(x3), self.rfb4_1(x4)
-        ra5_fg, ra5_bg = self.agg1(x4_rfb, x3_rfb, x2_rfb)
-        l5_fg, l5_bg = up(ra5_fg, scale_factor=8 / sd), up(ra5_bg, scale_factor=8 / sd)
-        # DSRA3: deeper maps are the x0.25-resized coarse maps (resize fused into the fusion kernel)
-        t = self._stack(4, x4, 4)
-        fg, bg = self.ra4_conv5_fg(t), self.ra4_conv5_bg(t)
-        fg = ops.dsra_fuse(fg, ra5_fg, ra5_bg, self.use_softmax, scale_factor=0.25)
-        l4_fg, l4_bg = up(fg, scale_factor=32 / sd), up(bg, scale_factor=32 / sd)
-        # DSRA2
-        t = self._stack(3, x3, 3)
-        fg3, bg3 = self.ra3_conv4_fg(t), self.ra3_conv4_bg(t)
-        fg3 = ops.dsra_fuse(fg3, fg, bg, self.use_softmax, scale_factor=2)
-        l3_fg, l3_bg = up(fg3, scale_factor=16 / sd), up(bg3, scale_factor=16 / sd)
-        # DSRA1
-        t = self._stack(2, x2, 3)
-        fg2, bg2 = self.ra2_conv4_fg(t), self.ra2_conv4_bg(t)
-        fg2 = ops.dsra_fuse(fg2, fg3, bg3, self.use_softmax, scale_factor=2)
-        l2_fg, l2_bg = up(fg2, scale_factor=8 / sd), up(bg2, scale_factor=8 / sd)
-        return l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg
+
+        def runner(eng, inputs, in_grads):
+            feats = [eng.from_nchw(t, _sink(in_grads, i)) for i, t in enumerate(inputs)]
+            rfbs, stacks = [], []
+            # per pyramid level ONE GEMM for the six 1x1 convs that read the backbone feature:
+            # [rfb.branch0..3 first convs | rfb.conv_res | ra_conv1]
+            for a, rfb, stage in zip(feats, (self.rfb2_1, self.rfb3_1, self.rfb4_1), (2, 3, 4)):
+                ra1 = getattr(self, f"ra{stage}_conv1")
+                raw = eng.conv(a, rfb_convs(rfb) + [ra1.conv])
+                c = rfb.conv_res.conv.out_channels
+                rfbs.append(rfb_run(eng, rfb, raw, 0))
+                stacks.append(eng.bn_apply((raw, 5 * c, ra1.conv.out_channels, ra1.bn, None)))       # no ReLU after conv1
+            ra5_fg, ra5_bg = aggregation_run(eng, self.agg1, rfbs[2], rfbs[1], rfbs[0])
+            l5_fg, l5_bg = eng.resize(ra5_fg, 8 / sd), eng.resize(ra5_bg, 8 / sd)
+            # DSRA3: the x0.25 resize of the coarse maps is fused into the fusion kernel
+            t = self._stack(eng, 4, stacks[2], 4)
+            fg4, bg4 = dual(eng, self.ra4_conv5_fg, self.ra4_conv5_bg, t)
+            fg4 = eng.fuse(fg4, ra5_fg, ra5_bg, self.use_softmax, 0.25)
+            l4_fg, l4_bg = eng.resize(fg4, 32 / sd), eng.resize(bg4, 32 / sd)
+            # DSRA2
+            t = self._stack(eng, 3, stacks[1], 3)
+            fg3, bg3 = dual(eng, self.ra3_conv4_fg, self.ra3_conv4_bg, t)
+            fg3 = eng.fuse(fg3, fg4, bg4, self.use_softmax, 2)
+            l3_fg, l3_bg = eng.resize(fg3, 16 / sd), eng.resize(bg3, 16 / sd)
+            # DSRA1
+            t = self._stack(eng, 2, stacks[0], 3)
+            fg2, bg2 = dual(eng, self.ra2_conv4_fg, self.ra2_conv4_bg, t)
+            fg2 = eng.fuse(fg2, fg3, bg3, self.use_softmax, 2)
+            l2_fg, l2_bg = eng.resize(fg2, 8 / sd), eng.resize(bg2, 8 / sd)
+            return [l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg]
+
+        from .heads import dual_heads_run as dual
+        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training)
 
 
 class PraNet_V2(_V2Mixin):
@@ -132,20 +147,22 @@ class PVT_PraNet_V2(_V2Mixin):
 class _V1Mixin(_PraNetBase):
     def forward_head(self, x2, x3, x4):
         """PraNet_Res2Net.py:143-186 -> (l5, l4, l3, l2)."""
-        up = ops.interpolate_bilinear
-        x2_rfb, x3_rfb, x4_rfb = self.rfb2_1(x2), self.rfb3_1(x3), self.rfb4_1(x4)
-        ra5 = self.agg1(x4_rfb, x3_rfb, x2_rfb)
-        l5 = up(ra5, scale_factor=8)
-        crop = up(ra5, scale_factor=0.25)
-        x = self.ra4_conv5(self._stack(4, ops.ra_v1_scale(x4, crop), 4)) + crop
-        l4 = up(x, scale_factor=32)
-        crop = up(x, scale_factor=2)
-        x = self.ra3_conv4(self._stack(3, ops.ra_v1_scale(x3, crop), 3)) + crop
-        l3 = up(x, scale_factor=16)
-        crop = up(x, scale_factor=2)
-        x = self.ra2_conv4(self._stack(2, ops.ra_v1_scale(x2, crop), 3)) + crop
-        l2 = up(x, scale_factor=8)
-        return l5, l4, l3, l2
+        def runner(eng, inputs, in_grads):
+            feats = [eng.from_nchw(t, _sink(in_grads, i)) for i, t in enumerate(inputs)]
+            rfbs = [rfb_run(eng, rfb, eng.conv(a, rfb_convs(rfb)), 0) for a, rfb in zip(feats, (self.rfb2_1, self.rfb3_1, self.rfb4_1))]
+            ra5 = aggregation_run(eng, self.agg1, rfbs[2], rfbs[1], rfbs[0])[0]
+            outs = [eng.resize(ra5, 8)]
+            x = ra5
+            for stage, i, n, head, s_in, s_out in ((4, 2, 4, self.ra4_conv5, 0.25, 32), (3, 1, 3, self.ra3_conv4, 2, 16), (2, 0, 3, self.ra2_conv4, 2, 8)):
+                crop = eng.resize(x, s_in)
+                # reverse attention: (1 - sigmoid(crop)) * x_k  (PraNet_Res2Net.py:153-154), then the conv stack
+                scaled, sink = eng.ra_v1(inputs[i], crop, _sink(in_grads, i))
+                t = getattr(self, f"ra{stage}_conv1").run(eng, eng.from_nchw(scaled, sink))
+                t = self._stack(eng, stage, t, n)
+                x = eng.add_maps(head.run(eng, t, out_map=True), crop)                                  # ra_feat + crop
+                outs.append(eng.resize(x, s_out))
+            return outs
+        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training)
 
 
 class PraNet(_V1Mixin):
