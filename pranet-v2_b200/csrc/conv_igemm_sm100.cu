@@ -363,7 +363,8 @@ extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, in
     int splits = 1;
     // fill the 148 SMs when the output tiling alone cannot, keeping >= 8 K iterations per split
     while (splits < 8 && m_tiles * n_tiles * splits * 2 <= kNumSMs && iters / (splits * 2) >= 8) splits *= 2;   // <= 8: consumers sum at most 8 slabs
-    return splits;
+    const int per = (iters + splits - 1) / splits;
+    return (iters + per - 1) / per;   // no empty split
 }
 
 extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,
@@ -426,8 +427,9 @@ extern "C" int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Co
     const int BN = cin_r >= bn_max ? bn_max : cin_r;
     const int ctas = KH * KW * ((Cout + BM - 1) / BM) * ((cin_r + BN - 1) / BN);
     int splits = 1;
-    while (ctas * splits * 2 <= 2 * kNumSMs && tiles / (splits * 2) >= 2) splits *= 2;
-    return splits;
+    while (splits < 64 && ctas * splits * 2 <= 2 * kNumSMs && tiles / (splits * 2) >= 2) splits *= 2;
+    const int per = (tiles + splits - 1) / splits;
+    return (tiles + per - 1) / per;   // no empty split
 }
 
 extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const void* x, long long x_plane_stride, int kind, int nterms,

@@ -87,13 +87,19 @@ __global__ void dsra_fuse_bwd_kernel(const float* __restrict__ dout, const float
         }
         return;
     }
+    if (C == 1) {   // softmax over a single channel is the constant 1: out = 2*fg, no gradient reaches the deeper maps
+        const float g = dout[base];
+        dfg[base] = g + g;
+        dd[base] = 0.0f;
+        return;
+    }
     float mx = -INFINITY;
     for (int c = 0; c < C; ++c) mx = fmaxf(mx, s(pf + c * dh * dw) - s(pb + c * dh * dw));
     float den = 0.0f, dot = 0.0f;
     for (int c = 0; c < C; ++c) {
         float e = expf(s(pf + c * dh * dw) - s(pb + c * dh * dw) - mx);
         den += e;
-        dot += e * dout[base + (size_t)c * hw] * fg[base + (size_t)c * hw];
+        dot += e * __fmul_rn(dout[base + (size_t)c * hw], fg[base + (size_t)c * hw]);
     }
     const float inv = 1.0f / den;
     dot *= inv;  // sum_j p_j t_j
@@ -101,7 +107,7 @@ __global__ void dsra_fuse_bwd_kernel(const float* __restrict__ dout, const float
         float p = expf(s(pf + c * dh * dw) - s(pb + c * dh * dw) - mx) * inv;
         float g = dout[base + (size_t)c * hw], v = fg[base + (size_t)c * hw];
         dfg[base + (size_t)c * hw] = g + g * p;
-        dd[base + (size_t)c * hw] = p * (g * v - dot);
+        dd[base + (size_t)c * hw] = p * (__fmul_rn(g, v) - dot);
     }
 }
 

@@ -117,7 +117,7 @@ def test_bilinear_fwd_bwd(shape, kw, dtype):
     assert (xd.grad.float().cpu() - xr.grad).abs().max() <= tol * max(1.0, xr.grad.abs().max().item())
     if dtype == torch.float32:   # the explicit float64 numpy restatement agrees too
         sf = kw.get("scale_factor")
-        np.testing.assert_allclose(out.cpu().numpy(), O.bilinear_np(x.numpy(), ref.shape[2], ref.shape[3], kw.get("align_corners", False), sf),
+        np.testing.assert_allclose(out.detach().cpu().numpy(), O.bilinear_np(x.numpy(), ref.shape[2], ref.shape[3], kw.get("align_corners", False), sf),
                                    rtol=1e-4, atol=5e-5)
 
 
