@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=4, help="batch of one CPU-baseline step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     return ap.parse_args()
 
 
@@ -170,7 +171,7 @@ def main():
     B, S = args.batch, args.size
     torch.manual_seed(0)
     model = P.PraNet_V2(num_class=1)
-    ts = TrainStep(model, lr=1e-4, clip=0.5, autocast_backbone=(args.precision == "bf16"), device=dev)
+    ts = TrainStep(model, lr=1e-4, clip=0.5, autocast_backbone=(args.precision == "bf16"), device=dev, use_graph=not args.no_graph)
     g = torch.Generator().manual_seed(1000 + rank)
     # a few distinct batches (> L2 together with the activations; inputs change step to step)
     nbuf = 4
@@ -191,7 +192,6 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    n0 = P._lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -200,7 +200,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = P._lib.launch_count() - n0
+    launches = ts.pv2_launches_per_step * args.steps   # pv2 kernel nodes replayed inside the CUDA graphs of the timed steps
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end timing: pinned host inputs -> H2D -> step -> loss D2H every step ----
@@ -238,7 +238,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"PraNet-V2 Res2Net-50 train step (fwd + 4x structure_loss + bwd + clamp + Adam), per-GPU batch {B} @ {S}^2, random init",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "l2": "inputs rotate over 4 batches; per-step working set (activations+grads) >> 126 MB L2"},
+                       "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "l2": "inputs rotate over 4 batches; per-step working set (activations+grads) >> 126 MB L2"},
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": imgs_h[0].numel() * 4 + gts_h[0].numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

@@ -1,9 +1,15 @@
 """Training / inference step drivers: the public API bench.py and users call.
 
 `TrainStep` reproduces one optimizer step of binary_seg/MyTrain_med.py:59-86 at rate 1: forward, the four
-structure losses (fused into one x4 launch), backward, element-wise gradient clamp (utils/utils.py:7-17),
-Adam.  One process per GPU; when torch.distributed is initialised the model is wrapped in DDP (NCCL
-all-reduce of gradients over NVLink, bucketed and overlapped with backward -- the only collective).
+structure losses (one fused x4 launch), backward, element-wise gradient clamp (utils/utils.py:7-17), Adam.
+
+Execution model (B200-first, no tracing compiler):
+  * the step is launch-bound in eager mode (~4800 kernel launches, mostly the stock backbone), so it is captured
+    once into two CUDA graphs and replayed: graph A = forward + losses + backward + gather of all gradients into ONE
+    flat fp32 bucket; graph B = clamp + fused Adam on views of that bucket;
+  * one process per GPU; between the two graphs the flat bucket is all-reduced with NCCL over NVLink (the only
+    collective of the path: a single ~130 MB message, ~0.3 ms at NVSwitch bandwidth, so bucketing/overlap machinery
+    would buy nothing here); BatchNorm statistics stay per replica, as in the reference.
 """
 from __future__ import annotations
 
@@ -11,51 +17,113 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
+
+_UNUSED_PREFIXES = ("conv.", "backbone.fc.", "resnet.fc.")   # defined by the reference nets but never used in forward
 
 
 class TrainStep:
     def __init__(self, model: nn.Module, lr: float = 1e-4, clip: float = 0.5, autocast_backbone: bool = True,
-                 device=None, channels_last: bool = True):
+                 device=None, channels_last: bool = True, use_graph: bool = True):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.raw = model.to(self.device).train()
+        self.model = model.to(self.device).train()
         if channels_last:
-            self.raw = self.raw.to(memory_format=torch.channels_last)
-        self.model = self.raw
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            self.model = nn.parallel.DistributedDataParallel(self.raw, device_ids=[self.device.index], gradient_as_bucket_view=True,
-                                                             bucket_cap_mb=32, broadcast_buffers=False)
-        self.params = [p for p in self.raw.parameters() if p.requires_grad]
-        self.opt = torch.optim.Adam(self.params, lr, fused=True)   # MyTrain_med.py:148-149
-        self.clip = clip
-        self.autocast = autocast_backbone
-        self.channels_last = channels_last
-        self._img = self._gt = None
+            self.model = self.model.to(memory_format=torch.channels_last)
+        for n, p in self.model.named_parameters():
+            if n.startswith(_UNUSED_PREFIXES):
+                p.requires_grad_(False)
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        if self.world > 1:   # identical replicas to start from
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, 0)
+        # one flat gradient bucket; p.grad for the optimizer are views into it
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=self.device)
+        self.views, o = [], 0
+        for p in self.params:
+            # same strides as the parameter (conv weights are channels_last): the fused optimizer wants matching layouts
+            self.views.append(torch.as_strided(self.flat, p.shape, p.stride(), storage_offset=o))
+            o += p.numel()
+        self.opt = torch.optim.Adam(self.params, lr, fused=True, capturable=True)   # MyTrain_med.py:148-149
+        self.clip, self.autocast, self.channels_last, self.use_graph = clip, autocast_backbone, channels_last, use_graph
+        self._static = None
+        self._loss = None
+        self.pv2_launches_per_step = 0
 
-    # -- device-resident step -------------------------------------------------------------------
-    def step_device(self, images: torch.Tensor, gts: torch.Tensor) -> torch.Tensor:
-        self.opt.zero_grad(set_to_none=True)
-        if self.channels_last:
-            images = images.contiguous(memory_format=torch.channels_last)
+    # -- the two halves of a step ------------------------------------------------------------------------
+    def _fwd_bwd(self, images, gts):
+        for p in self.params:
+            p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
             outs = self.model(images)
         pairs = [(outs[i].float(), outs[i + 4].float()) for i in range(4)]
         loss = ops.structure_loss_multi(pairs, gts).sum()            # MyTrain_med.py:78-82
         loss.backward()
-        grads = [p.grad for p in self.params if p.grad is not None]
-        torch._foreach_clamp_min_(grads, -self.clip)                 # clip_gradient: clamp_(-clip, clip)
-        torch._foreach_clamp_max_(grads, self.clip)
-        self.opt.step()
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        torch._foreach_copy_(self.views, grads)
         return loss.detach()
 
-    # -- end-to-end step: pinned host buffers in, host scalar out ----------------------------------
+    def _update(self):
+        if self.world > 1:
+            self.flat.div_(self.world)
+        self.flat.clamp_(-self.clip, self.clip)                      # clip_gradient: grad.clamp_(-clip, clip)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        self.opt.step()
+
+    # -- graph capture ------------------------------------------------------------------------------------------
+    def _capture(self, images, gts):
+        self._img = torch.empty(images.shape, dtype=images.dtype, device=self.device,
+                                memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+        self._gt = torch.empty(gts.shape, dtype=gts.dtype, device=self.device)
+        self._img.copy_(images)
+        self._gt.copy_(gts)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                                       # warm-up: cuDNN autotune, allocator, lazy inits
+                self._fwd_bwd(self._img, self._gt)
+                if self.world > 1:
+                    dist.all_reduce(self.flat)
+                self._update()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph_a):
+            self._loss = self._fwd_bwd(self._img, self._gt)
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+            self._update()
+        self.pv2_launches_per_step = _lib.launch_count() - n0     # pv2 kernel nodes inside the two graphs
+        self._static = (tuple(images.shape), tuple(gts.shape))
+
+    # -- public steps -------------------------------------------------------------------------------------------
+    def step_device(self, images: torch.Tensor, gts: torch.Tensor) -> torch.Tensor:
+        """One optimizer step on device-resident inputs; returns the (device) loss."""
+        if not self.use_graph:
+            images, gts = images.to(self.device, non_blocking=True), gts.to(self.device, non_blocking=True)
+            if self.channels_last:
+                images = images.contiguous(memory_format=torch.channels_last)
+            n0 = _lib.launch_count()
+            loss = self._fwd_bwd(images, gts)
+            self.pv2_launches_per_step = _lib.launch_count() - n0
+            if self.world > 1:
+                dist.all_reduce(self.flat)
+            self._update()
+            return loss
+        if self._static != (tuple(images.shape), tuple(gts.shape)):
+            self._capture(images, gts)
+        self._img.copy_(images, non_blocking=True)
+        self._gt.copy_(gts, non_blocking=True)
+        self.graph_a.replay()
+        if self.world > 1:
+            dist.all_reduce(self.flat)                               # NCCL over NVLink: the path's only collective
+        self.graph_b.replay()
+        return self._loss
+
     def step_host(self, images_pinned: torch.Tensor, gts_pinned: torch.Tensor) -> float:
-        if self._img is None or self._img.shape != images_pinned.shape:
-            self._img = torch.empty(images_pinned.shape, dtype=images_pinned.dtype, device=self.device)
-            self._gt = torch.empty(gts_pinned.shape, dtype=gts_pinned.dtype, device=self.device)
-        self._img.copy_(images_pinned, non_blocking=True)
-        self._gt.copy_(gts_pinned, non_blocking=True)
-        return float(self.step_device(self._img, self._gt).item())
+        """End-to-end step: pinned host inputs -> H2D -> step -> loss read back to the host."""
+        return float(self.step_device(images_pinned, gts_pinned).item())
 
 
 @torch.no_grad()

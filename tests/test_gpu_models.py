@@ -107,3 +107,54 @@ def test_head_vs_oracle_352():
             assert (o.cpu() - r).abs().max().item() <= LOGIT_ATOL
         agree = ((sum(o.cpu() for o in outs[:4]) > 0) == (sum(ref[:4]) > 0)).float().mean().item()
         assert agree >= 0.999
+
+
+def test_train_step_graph_matches_eager():
+    """A CUDA-graph replay of the training step (train.TrainStep) computes what eager launches compute from the
+    same parameters and inputs, and the replayed optimizer step trains."""
+    from pranet_v2_b200.train import TrainStep
+    from pranet_v2_b200 import synthetic
+    torch.manual_seed(0)
+    m = P.PraNet_V2(num_class=1)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=3))
+    ts = TrainStep(m, lr=1e-4, clip=0.5, autocast_backbone=False, device="cuda:0", use_graph=True)
+    x = synthetic.images(2, 128, 0).to(DEV)
+    gt = synthetic.ellipse_masks(2, 128, 128, 0).to(DEV)
+    l1 = float(ts.step_device(x, gt))                      # captures (3 warm-up steps) and replays once
+    assert ts.pv2_launches_per_step > 100
+    # BN running stats are the only state _fwd_bwd mutates besides gradients; snapshot the model to undo its side effects
+    state = {k: v.clone() for k, v in ts.model.state_dict().items()}
+    eager = float(ts._fwd_bwd(x.contiguous(memory_format=torch.channels_last), gt))
+    ts.model.load_state_dict(state)
+    l2 = float(ts.step_device(x, gt))                      # replay from the same parameters
+    assert abs(l2 - eager) <= 1e-5 * abs(eager), (l2, eager)
+    assert l2 < l1                                         # and it trains
+
+
+@pytest.mark.parametrize("name", list(G.MC_CASES))
+def test_multiclass_dsra_stages_golden(name):
+    """DSRAStages (the plug-in for EMCAD_dual / CASCADE_Add_dual / CAM) on the decoder features captured from the
+    reference decoders, against the reference's own outputs; then the x32/x16/x8/x4 final upsample of EMCADNet."""
+    case = G.MC_CASES[name]
+    g = G.load(name)
+    bn = case["kind"] != "mist"
+    names = ("ConvBlock4", "ConvBlock3", "ConvBlock2", "ConvBlock1") if bn else ("out_head1", "out_head2", "out_head3", "out_head4")
+    ks = (1, 3, 3, 3) if bn else (1, 1, 1, 1)
+    host = torch.nn.Module()
+    stages = P.DSRAStages(host, case["channels"], case["num_class"], names, ks, bn, case.get("use_softmax", True))
+    from oracle import templates
+    sd = synth.synth_state_dict(templates.dual_heads(case["channels"], case["num_class"], names, ks, bn), seed=2)
+    host.load_state_dict(sd)
+    host.to(DEV).train(case["training"])
+    feats = [torch.from_numpy(g[f"d{i}"]).to(DEV) for i in range(4)]
+    with torch.no_grad():
+        outs = stages(feats)
+        ups = [P.interpolate_bilinear(o, scale_factor=(32, 16, 8, 4)[i % 4]) for i, o in enumerate(outs)]
+    for i, o in enumerate(outs):
+        assert np.abs(o.cpu().numpy() - g[f"out{i}"]).max() <= LOGIT_ATOL, f"{name} out{i}"
+    for i, o in enumerate(ups):
+        assert np.abs(_sub(o, 2) - g[f"up{i}"]).max() <= LOGIT_ATOL, f"{name} up{i}"
+    # multiclass prediction rule: argmax_c sum_i (fg_i - bg_i)   (EMCAD/utils/utils.py:266-273)
+    ours = sum(_sub(ups[i], 2) - _sub(ups[i + 4], 2) for i in range(4)).argmax(1)
+    theirs = sum(g[f"up{i}"] - g[f"up{i + 4}"] for i in range(4)).argmax(1)
+    assert (ours == theirs).mean() >= 0.999
