@@ -130,6 +130,22 @@ int pv2_weight_pack(const float* w, void* out, long long plane_stride, int nplan
                     int mode, int i_ld, int i_off, int o_off, void* stream);
 int pv2_wgrad_unpack(const float* part, long long split_stride, int splits, float* dw, int Cout, int Cin, int KH, int KW,
                      int Cin_p, int co_off, void* stream);
+/* Multi-tensor forms: a handful of launches for every conv of the head.  `descs` is a HOST array of n descriptors in
+ * increasing `start` order (start = running element offset of each OIHW tensor in the concatenated index space); the
+ * descriptors are passed to the kernels by value, 40 (56) per launch, so the calls are CUDA-graph capturable.
+ * pack: writes the fprop layout to out_f and, when out_d != NULL, the dgrad layout to out_d (fields as in pv2_weight_pack). */
+typedef struct pv2_pack_desc {
+    const float* w; void* out_f; void* out_d;
+    long long f_plane, d_plane, start;
+    int Cout, Cin, KH, KW, f_ild, f_ioff, f_ooff, d_ild, d_ioff, d_ooff;
+} pv2_pack_desc;
+typedef struct pv2_unpack_desc {
+    const float* part; float* dw;
+    long long split_stride, start;
+    int splits, Cout, Cin, KH, KW, Cin_p, co_off, pad_;
+} pv2_unpack_desc;
+int pv2_weight_pack_multi(const pv2_pack_desc* descs, int n, int nplanes, int kind, void* stream);
+int pv2_wgrad_unpack_multi(const pv2_unpack_desc* descs, int n, void* stream);
 /* NCHW (x_dtype PV2_F32 | PV2_BF16) -> operand NHWC slice [N*HW][ld] at channel c_off; and summed raw slabs -> NCHW */
 int pv2_pack_nchw(const void* x, int x_dtype, void* out, long long plane_stride, int nplanes, int kind, int N, int C, int HW,
                   int ld, int c_off, void* stream);

@@ -39,6 +39,8 @@ _SIGS = {
     "pv2_conv_wgrad": (_i, [_p, _ll, _p, _ll, _i, _i] + [_i] * 10 + [_p, _i, _p]),
     "pv2_weight_pack": (_i, [_p, _p, _ll, _i, _i] + [_i] * 8 + [_p]),
     "pv2_wgrad_unpack": (_i, [_p, _ll, _i, _p] + [_i] * 6 + [_p]),
+    "pv2_weight_pack_multi": (_i, [_p, _i, _i, _i, _p]),
+    "pv2_wgrad_unpack_multi": (_i, [_p, _i, _p]),
     "pv2_pack_nchw": (_i, [_p, _i, _p, _ll, _i, _i] + [_i] * 5 + [_p]),
     "pv2_unpack_to_nchw": (_i, [c_void_pp, _ip, _ip, _i, _p, _i, _i, _i, _i, _i, _p]),
     "pv2_bn_workspace_floats": (_sz, [_ll, _i]),

@@ -82,6 +82,54 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ part, long long sp
     }
 }
 
+// multi-tensor variants: a handful of launches pack every conv weight of the head (both layouts) / unpack every weight
+// gradient.  The descriptors travel BY VALUE in the kernel parameters (<= 4 KB per launch), so nothing has to be staged
+// in device memory and the launches are CUDA-graph capturable as they are.  Each thread owns one OIHW element of the
+// batch's concatenated index space and finds its tensor by binary search on `start`.
+constexpr int PACK_BATCH = 40;     // 40 * 88 B  = 3520 B of kernel parameters
+constexpr int UNPACK_BATCH = 56;   // 56 * 64 B  = 3584 B
+struct PackBatch { pv2_pack_desc d[PACK_BATCH]; };
+struct UnpackBatch { pv2_unpack_desc d[UNPACK_BATCH]; };
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+weight_pack_multi_kernel(const __grid_constant__ PackBatch b, int n, long long base, long long total, int nplanes) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.d[mid].start - base <= e) lo = mid; else hi = mid - 1; }
+        const pv2_pack_desc& t = b.d[lo];
+        const long long l = e - (t.start - base);
+        const int kw = (int)(l % t.KW);
+        const int kh = (int)((l / t.KW) % t.KH);
+        const int ci = (int)((l / ((long long)t.KW * t.KH)) % t.Cin);
+        const int co = (int)(l / ((long long)t.KW * t.KH * t.Cin));
+        const int taps = t.KH * t.KW;
+        const float v = t.w[l];
+        store_op<KIND>(t.out_f, t.f_plane, nplanes, ((long long)(co + t.f_ooff) * taps + kh * t.KW + kw) * t.f_ild + t.f_ioff + ci, v);
+        if (t.out_d)
+            store_op<KIND>(t.out_d, t.d_plane, nplanes,
+                           ((long long)(ci + t.d_ooff) * taps + (t.KH - 1 - kh) * t.KW + (t.KW - 1 - kw)) * t.d_ild + t.d_ioff + co, v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_unpack_multi_kernel(const __grid_constant__ UnpackBatch b, int n, long long base, long long total) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.d[mid].start - base <= e) lo = mid; else hi = mid - 1; }
+        const pv2_unpack_desc& t = b.d[lo];
+        const long long l = e - (t.start - base);
+        const int kw = (int)(l % t.KW);
+        const int kh = (int)((l / t.KW) % t.KH);
+        const int ci = (int)((l / ((long long)t.KW * t.KH)) % t.Cin);
+        const int co = (int)(l / ((long long)t.KW * t.KH * t.Cin));
+        const long long idx = ((long long)(co + t.co_off) * (t.KH * t.KW) + kh * t.KW + kw) * t.Cin_p + ci;
+        float acc = 0.0f;
+        for (int sp = 0; sp < t.splits; ++sp) acc += t.part[sp * t.split_stride + idx];
+        t.dw[l] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // NCHW (fp32 | bf16) -> operand NHWC, tiled transpose through shared memory; and the reverse for gradients
 // ------------------------------------------------------------------------------------------------------
@@ -139,14 +187,35 @@ unpack_to_nchw_kernel(const Slabs g, TOUT* __restrict__ dx, int C, int HW) {
 //   finalize: Chan-combine the row blocks; mean/invstd saved for backward; scale/shift for the apply pass;
 //             running stats updated like nn.BatchNorm2d (momentum, unbiased variance), num_batches_tracked += 1
 // ------------------------------------------------------------------------------------------------------
-constexpr int ST_ROWS = 256;   // rows per partial block
+constexpr int ST_ROWS_MIN = 32, ST_ROWS_MAX = 256;   // rows per partial block (chosen per call so that ~2 waves of CTAs exist)
+
+inline int pick_rows(long long M, int C) {
+    const int cg = (C + 31) / 32;
+    long long rb_target = (2LL * kNumSMs + cg - 1) / cg;
+    if (rb_target < 1) rb_target = 1;
+    long long rows = (M + rb_target - 1) / rb_target;
+    rows = (rows + 7) / 8 * 8;
+    if (rows < ST_ROWS_MIN) rows = ST_ROWS_MIN;
+    if (rows > ST_ROWS_MAX) rows = ST_ROWS_MAX;
+    return (int)rows;
+}
+
+// Chan's parallel combination of (count, mean, M2)
+__device__ __forceinline__ void chan_combine(float& n, float& mu, float& M2, float nb, float mub, float M2b) {
+    if (nb > 0.0f) {
+        const float d = mub - mu, nt = n + nb;
+        mu += d * nb / nt;
+        M2 += M2b + d * d * n * nb / nt;
+        n = nt;
+    }
+}
 
 __global__ void __launch_bounds__(256)
-bn_stats_partial_kernel(float* __restrict__ y, long long slab_stride, int nslabs, long long M, int C, int ld,
+bn_stats_partial_kernel(float* __restrict__ y, long long slab_stride, int nslabs, long long M, int C, int ld, int rows_pb,
                         float* __restrict__ part /* [row_blocks][C][3] */) {
     __shared__ float sh[8][32][3];
     const int c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
-    const long long r0 = (long long)blockIdx.x * ST_ROWS, r1 = min(M, r0 + ST_ROWS);
+    const long long r0 = (long long)blockIdx.x * rows_pb, r1 = min(M, r0 + rows_pb);
     float cnt = 0.0f, mean = 0.0f, m2 = 0.0f;
     if (c < C) {
         float shift = 0.0f, s1 = 0.0f, s2 = 0.0f;
@@ -168,39 +237,41 @@ bn_stats_partial_kernel(float* __restrict__ y, long long slab_stride, int nslabs
     if (ty == 0 && c < C) {
         float n = 0.0f, mu = 0.0f, M2 = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float nb = sh[k][threadIdx.x][0];
-            if (nb > 0.0f) {
-                const float d = sh[k][threadIdx.x][1] - mu, nt = n + nb;
-                mu += d * nb / nt;
-                M2 += sh[k][threadIdx.x][2] + d * d * n * nb / nt;
-                n = nt;
-            }
-        }
+        for (int k = 0; k < 8; ++k) chan_combine(n, mu, M2, sh[k][threadIdx.x][0], sh[k][threadIdx.x][1], sh[k][threadIdx.x][2]);
         float* o = part + ((long long)blockIdx.x * C + c) * 3;
         o[0] = n; o[1] = mu; o[2] = M2;
     }
 }
 
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-                                         float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
-                                         float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ scale,
-                                         float* __restrict__ shift) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+// one warp per channel: lanes take row blocks b = lane, lane+32, ... (fixed order), then a fixed shuffle tree
+__global__ void __launch_bounds__(128)
+bn_stats_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                         float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
+                         float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ scale,
+                         float* __restrict__ shift) {
+    const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c == 0 && lane == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
     float n = 0.0f, mu = 0.0f, M2 = 0.0f;
-    for (int b = 0; b < row_blocks; ++b) {
+    for (int b = lane; b < row_blocks; b += 32) {
         const float* p = part + ((long long)b * C + c) * 3;
-        const float nb = p[0];
-        if (nb > 0.0f) {
-            const float d = p[1] - mu, nt = n + nb;
-            mu += d * nb / nt;
-            M2 += p[2] + d * d * n * nb / nt;
-            n = nt;
-        }
+        chan_combine(n, mu, M2, p[0], p[1], p[2]);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, n, o), mub = __shfl_xor_sync(0xffffffffu, mu, o), M2b = __shfl_xor_sync(0xffffffffu, M2, o);
+        // combine in a lane-symmetric way so every lane ends with the same value
+        const float nt = n + nb;
+        if (nt > 0.0f) {
+            const float d = mub - mu;
+            const float mu_new = (n * mu + nb * mub) / nt;
+            M2 = M2 + M2b + d * d * n * nb / nt;
+            mu = mu_new;
+        }
+        n = nt;
+    }
+    if (lane != 0) return;
     const float var = M2 / n;
     const float inv = rsqrtf(var + eps);
     mean_out[c] = mu;
@@ -295,6 +366,7 @@ struct BwdArgs {
     float* part;                  // [row_blocks][4][C]
     const float* sums;            // [4][C] (dx pass)
     int bn_train;                 // 1: batch-stat BN backward, 0: plain affine
+    int rows_pb;                  // rows per reduce block
     void* dy1; long long dy1_plane; int dy1_planes, dy1_ld;
     void* dy2; long long dy2_plane; int dy2_planes, dy2_ld;
 };
@@ -330,7 +402,7 @@ bn_bwd_reduce_kernel(const BwdArgs b) {
     __shared__ float sh[8][32][4];
     const int C = b.f.C;
     const int c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
-    const long long r0 = (long long)blockIdx.x * ST_ROWS, r1 = min(b.f.M, r0 + ST_ROWS);
+    const long long r0 = (long long)blockIdx.x * b.rows_pb, r1 = min(b.f.M, r0 + b.rows_pb);
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < C) {
         for (long long r = r0 + ty; r < r1; r += 8) {
@@ -354,15 +426,20 @@ bn_bwd_reduce_kernel(const BwdArgs b) {
     }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, float* __restrict__ sums,
-                                       float* __restrict__ dgamma1, float* __restrict__ dbeta1, float* __restrict__ dgamma2,
-                                       float* __restrict__ dbeta2) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per channel, lanes over row blocks (fixed order) + shuffle tree
+__global__ void __launch_bounds__(128)
+bn_bwd_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, float* __restrict__ sums,
+                       float* __restrict__ dgamma1, float* __restrict__ dbeta1, float* __restrict__ dgamma2,
+                       float* __restrict__ dbeta2) {
+    const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < row_blocks; ++b)
+    for (int b = lane; b < row_blocks; b += 32)
 #pragma unroll
         for (int k = 0; k < 4; ++k) s[k] += part[((long long)b * 4 + k) * C + c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = warp_sum(s[k]);
+    if (lane != 0) return;
 #pragma unroll
     for (int k = 0; k < 4; ++k) sums[k * C + c] = s[k];
     if (dbeta1) dbeta1[c] = s[0];
@@ -498,6 +575,43 @@ extern "C" int pv2_wgrad_unpack(const float* part, long long split_stride, int s
     return 0;
 }
 
+extern "C" int pv2_weight_pack_multi(const pv2_pack_desc* descs, int n, int nplanes, int kind, void* stream) {
+    KIND_CHECK("weight_pack_multi");
+    PV2_CHECK(descs && n > 0, "weight_pack_multi: bad arguments");
+    for (int i0 = 0; i0 < n; i0 += PACK_BATCH) {
+        const int nb = n - i0 < PACK_BATCH ? n - i0 : PACK_BATCH;
+        PackBatch b;
+        long long total = 0;
+        for (int i = 0; i < nb; ++i) {
+            b.d[i] = descs[i0 + i];
+            PV2_CHECK(b.d[i].w && b.d[i].out_f, "weight_pack_multi: null pointer in descriptor %d", i0 + i);
+            total += (long long)b.d[i].Cout * b.d[i].Cin * b.d[i].KH * b.d[i].KW;
+        }
+        const long long base = b.d[0].start;
+        if (kind == PV2_BF16) weight_pack_multi_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(b, nb, base, total, nplanes);
+        else weight_pack_multi_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(b, nb, base, total, nplanes);
+        PV2_LAUNCH_CHECK("weight_pack_multi");
+    }
+    return 0;
+}
+
+extern "C" int pv2_wgrad_unpack_multi(const pv2_unpack_desc* descs, int n, void* stream) {
+    PV2_CHECK(descs && n > 0, "wgrad_unpack_multi: bad arguments");
+    for (int i0 = 0; i0 < n; i0 += UNPACK_BATCH) {
+        const int nb = n - i0 < UNPACK_BATCH ? n - i0 : UNPACK_BATCH;
+        UnpackBatch b;
+        long long total = 0;
+        for (int i = 0; i < nb; ++i) {
+            b.d[i] = descs[i0 + i];
+            PV2_CHECK(b.d[i].part && b.d[i].dw, "wgrad_unpack_multi: null pointer in descriptor %d", i0 + i);
+            total += (long long)b.d[i].Cout * b.d[i].Cin * b.d[i].KH * b.d[i].KW;
+        }
+        wgrad_unpack_multi_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(b, nb, b.d[0].start, total);
+        PV2_LAUNCH_CHECK("wgrad_unpack_multi");
+    }
+    return 0;
+}
+
 extern "C" int pv2_pack_nchw(const void* x, int x_dtype, void* out, long long plane_stride, int nplanes, int kind, int N, int C, int HW,
                              int ld, int c_off, void* stream) {
     KIND_CHECK("pack_nchw");
@@ -548,7 +662,8 @@ extern "C" int pv2_unpack_to_nchw(const float* const* slabs, const int* lds, con
 }
 
 extern "C" size_t pv2_bn_workspace_floats(long long M, int C) {
-    const long long rb = (M + ST_ROWS - 1) / ST_ROWS;
+    const int rows = pick_rows(M, C);
+    const long long rb = (M + rows - 1) / rows;
     return (size_t)(rb * C * 4 + 4 * (long long)C);
 }
 
@@ -557,12 +672,13 @@ extern "C" int pv2_bn_stats(float* y, long long slab_stride, int nslabs, long lo
                             float* mean_out, float* invstd_out, float* scale, float* shift, float* workspace, void* stream) {
     PV2_CHECK(y && mean_out && invstd_out && scale && shift && workspace, "bn_stats: null pointer");
     PV2_CHECK(M > 0 && C > 0 && ld >= C && nslabs >= 1, "bn_stats: bad shape");
-    const int rb = (int)((M + ST_ROWS - 1) / ST_ROWS);
+    const int rows = pick_rows(M, C);
+    const int rb = (int)((M + rows - 1) / rows);
     PV2_CHECK((C + 31) / 32 <= 65535, "bn_stats: too many channels");
     cudaStream_t st = (cudaStream_t)stream;
-    bn_stats_partial_kernel<<<dim3(rb, (C + 31) / 32), 256, 0, st>>>(y, slab_stride, nslabs, M, C, ld, workspace);
+    bn_stats_partial_kernel<<<dim3(rb, (C + 31) / 32), 256, 0, st>>>(y, slab_stride, nslabs, M, C, ld, rows, workspace);
     PV2_LAUNCH_CHECK("bn_stats_partial");
-    bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(workspace, rb, C, gamma, beta, eps, momentum, running_mean, running_var,
+    bn_stats_finalize_kernel<<<(C + 3) / 4, 128, 0, st>>>(workspace, rb, C, gamma, beta, eps, momentum, running_mean, running_var,
                                                                num_batches_tracked, mean_out, invstd_out, scale, shift);
     PV2_LAUNCH_CHECK("bn_stats_finalize");
     return 0;
@@ -635,7 +751,9 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
     b.bn_train = bn_train;
     b.dy1 = dy1; b.dy1_plane = dy1_plane; b.dy1_planes = dy1_planes; b.dy1_ld = dy1_ld;
     b.dy2 = dy2; b.dy2_plane = dy2_plane; b.dy2_planes = dy2_planes; b.dy2_ld = dy2_ld;
-    const int rb = (int)((M + ST_ROWS - 1) / ST_ROWS);
+    const int rows = pick_rows(M, C);
+    const int rb = (int)((M + rows - 1) / rows);
+    b.rows_pb = rows;
     float* part = workspace;
     float* sums = workspace + (size_t)rb * 4 * C;
     b.part = part; b.sums = sums;
@@ -643,7 +761,7 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
     const dim3 rgrid(rb, (C + 31) / 32);
     if (kind == PV2_BF16) bn_bwd_reduce_kernel<0><<<rgrid, 256, 0, st>>>(b); else bn_bwd_reduce_kernel<1><<<rgrid, 256, 0, st>>>(b);
     PV2_LAUNCH_CHECK("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, rb, C, sums, dgamma1, dbeta1, dgamma2, dbeta2);
+    bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, st>>>(part, rb, C, sums, dgamma1, dbeta1, dgamma2, dbeta2);
     PV2_LAUNCH_CHECK("bn_bwd_finalize");
     const long long total = M * C;
     if (kind == PV2_BF16) bn_bwd_dx_kernel<0><<<grid_for(total), 256, 0, st>>>(b); else bn_bwd_dx_kernel<1><<<grid_for(total), 256, 0, st>>>(b);

@@ -47,10 +47,16 @@ boundary_weight_kernel(const float* __restrict__ mask, uint16_t* __restrict__ wm
     if (plane == 0 && tile == 0 && tid == 0) *ticket = 0u;   // the forward kernel that follows counts on this
     const int y0 = (tile / tiles_x) * TH, x0 = (tile % tiles_x) * TW;
     const float* mp = mask + (size_t)plane * H * W;
-    for (int i = tid; i < SH * SW; i += WT_THREADS) {
-        const int r = i / SW, c = i - r * SW;
-        const int gy = y0 + r - HALO, gx = x0 + c - HALO;
-        sm[r * SPITCH + c] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(mp + (size_t)gy * W + gx) : 0.0f;
+    // stage tile + halo: warp = staged row (stride 8), lane = staged column (stride 32): coalesced, no integer division
+    for (int r = tid >> 5; r < SH; r += WT_THREADS / 32) {
+        const int gy = y0 + r - HALO;
+        const bool row_ok = (gy >= 0) && (gy < H);
+        const float* src = mp + (size_t)(row_ok ? gy : 0) * W;
+#pragma unroll
+        for (int c = tid & 31; c < SW; c += 32) {
+            const int gx = x0 + c - HALO;
+            sm[r * SPITCH + c] = (row_ok && gx >= 0 && gx < W) ? __ldg(src + gx) : 0.0f;
+        }
     }
     __syncthreads();
     // horizontal running sums: item = (row, segment of 8 outputs); rows vary fastest across lanes

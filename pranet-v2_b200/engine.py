@@ -23,6 +23,15 @@ from .ops import PV2_BF16, PV2_F32, _ratio, _stream
 PV2_TF32 = 2
 _PRECISION = "auto"
 
+import numpy as np  # noqa: E402
+
+_PACK_DT = np.dtype([("w", "u8"), ("out_f", "u8"), ("out_d", "u8"), ("f_plane", "i8"), ("d_plane", "i8"), ("start", "i8"),
+                     ("Cout", "i4"), ("Cin", "i4"), ("KH", "i4"), ("KW", "i4"), ("f_ild", "i4"), ("f_ioff", "i4"), ("f_ooff", "i4"),
+                     ("d_ild", "i4"), ("d_ioff", "i4"), ("d_ooff", "i4")], align=True)       # == pv2_pack_desc (88 B)
+_UNPACK_DT = np.dtype([("part", "u8"), ("dw", "u8"), ("split_stride", "i8"), ("start", "i8"), ("splits", "i4"), ("Cout", "i4"),
+                       ("Cin", "i4"), ("KH", "i4"), ("KW", "i4"), ("Cin_p", "i4"), ("co_off", "i4"), ("pad_", "i4")], align=True)   # == pv2_unpack_desc (64 B)
+assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64
+
 
 def set_precision(p: str):
     """'bf16' | 'fp32' | 'auto' (bf16 when the backbone features are bf16 / autocast is on, else fp32)."""
@@ -83,8 +92,12 @@ class Map:
 
 
 class Engine:
-    def __init__(self, device, precision: str, training: bool, need_grad: bool):
+    def __init__(self, device, precision: str, training: bool, need_grad: bool, cache: dict = None):
         self.lib = _lib.load()
+        self.cache = cache if cache is not None else {}
+        self.groups_seen = []      # conv groups in call order (recorded on the first run, prepacked in one launch afterwards)
+        self.packed = {}           # group key -> (w_op fprop layout, w_op dgrad layout or None)
+        self.unpack_jobs = []
         self.dev = device
         self.kind = PV2_BF16 if precision == "bf16" else PV2_TF32
         self.nterms = 1 if precision == "bf16" else 3
@@ -159,6 +172,54 @@ class Engine:
         _lib.check(self.lib.pv2_unpack_to_nchw(pp, lds, offs, len(slabs), dx.data_ptr(), PV2_F32 if dx.dtype == torch.float32 else PV2_BF16,
                                                N, Cc, HW, int(channels_last), _stream()), "pv2_unpack_to_nchw")
 
+    # ---- weights: every conv group of the head packed by ONE multi-tensor launch ------------------------------------------
+    @staticmethod
+    def _gkey(convs):
+        return tuple(id(c) for c in convs)
+
+    def _alloc_packed(self, convs):
+        c0 = convs[0]
+        KH, KW = c0.kernel_size
+        taps, Cin, Cout = KH * KW, c0.in_channels, sum(c.out_channels for c in convs)
+        Cin_p, Cout_p = self.pad(Cin), self.pad(Cout)
+        fshape = (Cout, taps, Cin_p) if self.planes == 1 else (self.planes, Cout, taps, Cin_p)
+        w_f = (torch.zeros if Cin_p != Cin else torch.empty)(fshape, dtype=self.op_dtype, device=self.dev)
+        w_d = None
+        if self.need_grad:
+            dshape = (Cin, taps, Cout_p) if self.planes == 1 else (self.planes, Cin, taps, Cout_p)
+            w_d = (torch.zeros if Cout_p != Cout else torch.empty)(dshape, dtype=self.op_dtype, device=self.dev)
+        return w_f, w_d, (KH, KW, taps, Cin, Cout, Cin_p, Cout_p)
+
+    def prepack(self, groups):
+        """Pack the weights of all `groups` (lists of nn.Conv2d fused along Cout) in both layouts with one launch per
+        40 tensors; called at the start of a run once the group list of this head is known."""
+        descs, start = [], 0
+        for convs in groups:
+            w_f, w_d, (KH, KW, taps, Cin, Cout, Cin_p, Cout_p) = self._alloc_packed(convs)
+            self.packed[self._gkey(convs)] = (w_f, w_d)
+            o = 0
+            for cv in convs:
+                descs.append((cv.weight.data_ptr(), w_f.data_ptr(), w_d.data_ptr() if w_d is not None else 0,
+                              Cout * taps * Cin_p, Cin * taps * Cout_p, start,
+                              cv.out_channels, Cin, KH, KW, Cin_p, 0, o, Cout_p, o, 0))
+                start += cv.weight.numel()
+                o += cv.out_channels
+        if descs:
+            arr = np.array(descs, dtype=_PACK_DT)
+            _lib.check(self.lib.pv2_weight_pack_multi(arr.ctypes.data, len(descs), self.planes, self.kind, _stream()), "pv2_weight_pack_multi")
+
+    def flush_unpack(self):
+        """All weight gradients of this backward pass: [split][Cout][tap][Cin_p] partials -> OIHW, one launch per 56 tensors."""
+        if not self.unpack_jobs:
+            return
+        descs, start = [], 0
+        for (part, split_stride, splits, dw_, Cout, Cin, KH, KW, Cin_p, co_off) in self.unpack_jobs:
+            descs.append((part.data_ptr(), dw_.data_ptr(), split_stride, start, splits, Cout, Cin, KH, KW, Cin_p, co_off, 0))
+            start += dw_.numel()
+        arr = np.array(descs, dtype=_UNPACK_DT)
+        _lib.check(self.lib.pv2_wgrad_unpack_multi(arr.ctypes.data, len(descs), _stream()), "pv2_wgrad_unpack_multi")
+        self.unpack_jobs = []
+
     # ---- convolution (optionally several convs of identical geometry fused along Cout) ---------------------
     def conv(self, x: Act, convs, out_nchw_bias=False):
         """x -> Raw [splits, M, ld] (or, with out_nchw_bias, a biased fp32 NCHW Map straight from the epilogue)."""
@@ -177,14 +238,11 @@ class Engine:
         Cout = sum(cv.out_channels for cv in convs)
         taps = KH * KW
         lib, st = self.lib, _stream()
-        # forward weights [Cout][tap][Cin_p]
-        wshape = (Cout, taps, Cin_p) if self.planes == 1 else (self.planes, Cout, taps, Cin_p)
-        w_op = (torch.zeros if Cin_p != Cin else torch.empty)(wshape, dtype=self.op_dtype, device=self.dev)
-        o = 0
-        for cv in convs:
-            _lib.check(lib.pv2_weight_pack(cv.weight.data_ptr(), w_op.data_ptr(), Cout * taps * Cin_p, self.planes, self.kind,
-                                           cv.out_channels, Cin, KH, KW, 0, Cin_p, 0, o, st), "pv2_weight_pack")
-            o += cv.out_channels
+        self.groups_seen.append(convs)
+        key = self._gkey(convs)
+        if key not in self.packed:      # first run of this head (group list not cached yet): pack this group on its own
+            self.prepack([convs])
+        w_op = self.packed[key][0]
         N, H, W = x.N, x.H, x.W
         if out_nchw_bias:
             assert len(convs) == 1
@@ -230,20 +288,13 @@ class Engine:
             o = 0
             for cv in convs:
                 if cv.weight.requires_grad:
-                    dw_ = torch.empty_like(cv.weight, memory_format=torch.contiguous_format)
-                    _lib.check(lib.pv2_wgrad_unpack(part.data_ptr(), Cout * taps * Cin_p, splits, dw_.data_ptr(), cv.out_channels, Cin, KH, KW,
-                                                    Cin_p, o, st), "pv2_wgrad_unpack")
-                    self.add_param_grad(cv.weight, dw_)
+                    dw_ = torch.empty(cv.weight.shape, dtype=torch.float32, device=self.dev)
+                    self.unpack_jobs.append((part, Cout * taps * Cin_p, splits, dw_, cv.out_channels, Cin, KH, KW, Cin_p, o))
+                    self.add_param_grad(cv.weight, dw_)      # filled by flush_unpack() before backward() returns
                 o += cv.out_channels
         # dgrad -> raw slabs appended to the input's gradient list
         if x.want_grad and x.gslabs is not None:
-            wshape = (Cin, taps, Cout_p) if self.planes == 1 else (self.planes, Cin, taps, Cout_p)
-            wt = (torch.zeros if Cout_p != Cout else torch.empty)(wshape, dtype=self.op_dtype, device=self.dev)
-            o = 0
-            for cv in convs:
-                _lib.check(lib.pv2_weight_pack(cv.weight.data_ptr(), wt.data_ptr(), Cin * taps * Cout_p, self.planes, self.kind,
-                                               cv.out_channels, Cin, KH, KW, 1, Cout_p, o, 0, st), "pv2_weight_pack")
-                o += cv.out_channels
+            wt = self.packed[self._gkey(convs)][1]           # dgrad layout, packed together with the fprop layout
             ld = (Cin + 3) // 4 * 4
             splits = lib.pv2_conv_splits_hint(N, H, W, Cout_p, Cin, KH, KW, self.kind, self.nterms)
             dx = self.f32(splits, N * H * W, ld)
@@ -492,6 +543,7 @@ class Engine:
     def backward(self):
         for fn in reversed(self.tape):
             fn()
+        self.flush_unpack()
         self.tape = []
 
 
@@ -523,12 +575,16 @@ class _SliceGrads:
 # ------------------------------------------------------------------------------------------------------------
 class _HeadFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, n_inputs, precision, training, *tensors):
+    def forward(ctx, runner, n_inputs, precision, training, cache, *tensors):
         inputs, params = tensors[:n_inputs], tensors[n_inputs:]
-        need_grad = any(ctx.needs_input_grad[4:])
-        eng = Engine(inputs[0].device, precision, training, need_grad)
+        need_grad = any(ctx.needs_input_grad[5:])
+        eng = Engine(inputs[0].device, precision, training, need_grad, cache)
         in_grads = [None] * n_inputs
+        if cache is not None and "groups" in cache:
+            eng.prepack(cache["groups"])           # every conv weight of this head, both layouts, one launch per 40 tensors
         outs = runner(eng, inputs, in_grads)
+        if cache is not None and "groups" not in cache:
+            cache["groups"] = eng.groups_seen
         ctx.eng, ctx.in_grads, ctx.params, ctx.outs = eng, in_grads, params, outs
         ctx.n_inputs = n_inputs
         return tuple(o.t for o in outs)
@@ -542,15 +598,15 @@ class _HeadFn(torch.autograd.Function):
         eng.backward()
         grads = []
         for i in range(ctx.n_inputs):
-            grads.append(ctx.in_grads[i] if ctx.needs_input_grad[4 + i] else None)
+            grads.append(ctx.in_grads[i] if ctx.needs_input_grad[5 + i] else None)
         for j, p in enumerate(ctx.params):
-            g = eng.param_grads.get(id(p)) if ctx.needs_input_grad[4 + ctx.n_inputs + j] else None
+            g = eng.param_grads.get(id(p)) if ctx.needs_input_grad[5 + ctx.n_inputs + j] else None
             grads.append(g)
         ctx.eng = ctx.outs = None
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
-def run_head(runner, inputs, params, training):
+def run_head(runner, inputs, params, training, cache=None):
     """runner(engine, inputs, in_grads) -> list of Map.  `inputs` are NCHW feature tensors, `params` the list of
     parameters the runner touches (so autograd can hand their gradients back)."""
     for t in inputs:
@@ -560,4 +616,4 @@ def run_head(runner, inputs, params, training):
     if prec == "auto":
         prec = "bf16" if (inputs[0].dtype == torch.bfloat16 or torch.is_autocast_enabled()) else "fp32"
     with torch.autocast("cuda", enabled=False):
-        return _HeadFn.apply(runner, len(inputs), prec, training, *inputs, *params)
+        return _HeadFn.apply(runner, len(inputs), prec, training, cache, *inputs, *params)

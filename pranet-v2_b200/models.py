@@ -113,7 +113,7 @@ class _V2Mixin(_PraNetBase):
             return [l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg]
 
         from .heads import dual_heads_run as dual
-        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training)
+        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training, self.__dict__.setdefault("_pv2_cache", {}))
 
 
 class PraNet_V2(_V2Mixin):
@@ -162,7 +162,7 @@ class _V1Mixin(_PraNetBase):
                 x = eng.add_maps(head.run(eng, t, out_map=True), crop)                                  # ra_feat + crop
                 outs.append(eng.resize(x, s_out))
             return outs
-        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training)
+        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training, self.__dict__.setdefault("_pv2_cache", {}))
 
 
 class PraNet(_V1Mixin):

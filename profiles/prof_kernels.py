@@ -1,0 +1,39 @@
+"""Small driver for ncu captures of the pv2 kernels (not a benchmark: numbers printed under a profiler are never
+bench values).  Usage (on the GPU box, one GPU):
+    ncu --set full --clock-control none --import-source on -k regex:structure_loss -c 6 -o gpurun_out/prof_loss  python profiles/prof_kernels.py loss
+    ncu --set full --clock-control none --import-source on -k regex:conv_ -c 120 -o gpurun_out/prof_conv         python profiles/prof_kernels.py head
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import pranet_v2_b200 as P
+from pranet_v2_b200 import synthetic
+
+what = sys.argv[1] if len(sys.argv) > 1 else "loss"
+B, S = 16, 352
+dev = "cuda"
+torch.manual_seed(0)
+if what == "step":     # two eager training steps of the bench workload (launch list of the pv2 kernels)
+    from pranet_v2_b200.train import TrainStep
+    ts = TrainStep(P.PraNet_V2(num_class=1), device="cuda:0", use_graph=False)
+    x, gt = synthetic.images(B, S, 1).to(dev), synthetic.ellipse_masks(B, S, S, 1).to(dev)
+    for it in range(2):
+        ts.step_device(x, gt)
+elif what == "loss":
+    m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
+    for it in range(2):
+        pairs = [(torch.randn(B, 1, S, S, device=dev).requires_grad_(True), torch.randn(B, 1, S, S, device=dev).requires_grad_(True)) for _ in range(4)]
+        P.structure_loss_multi(pairs, m).sum().backward()
+else:
+    model = P.PraNet_V2(num_class=1).to(dev).train()
+    feats = [torch.relu(torch.randn(B, c, S // s, S // s, device=dev)).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+             for c, s in ((512, 8), (1024, 16), (2048, 32))]
+    gt = synthetic.ellipse_masks(B, S, S, 3).to(dev)
+    for it in range(2):
+        outs = model.forward_head(*feats)
+        P.structure_loss_multi([(outs[i], outs[i + 4]) for i in range(4)], gt).sum().backward()
+torch.cuda.synchronize()
+print("done", what)
