@@ -101,6 +101,23 @@ int pv2_ra_v1_scale_fwd(const void* x, const float* crop, void* y, int B, int C,
 int pv2_ra_v1_scale_bwd(const void* dy, const void* x, const float* crop, void* dx, float* dcrop,
                         int B, int C, int hw, int dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Multiclass dual-supervision loss -- EMCAD/trainer.py:123-140 (== MERIT/train_ACDC.py:259-284 == MIST/trainer.py:112-129)
+ * with its pieces powerset (EMCAD/utils/utils.py:20-30), DiceLoss (utils.py:102-138) and the inverted one-hot mask
+ * (trainer.py:22-29, built on the fly from the int64 labels, never materialised).
+ *   loss = sum_s lc_ce*CE(sum_{i in s} P_fg[i], y) + lc_dice*Dice(softmax(.), y) + lc_bce*mean BCEWithLogits(sum_{i in s} P_bg[i], 1-onehot(y))
+ * mode 0: s runs over all non-empty subsets of the nscales (<= 4) maps ('mutation'); mode 1: singletons ('deep_supervision').
+ * P_fg / P_bg: HOST arrays of nscales device pointers to fp32 [B][C][H][W]; labels int64 [B][H][W]; 2 <= C <= 12.
+ * fwd writes the scalar loss and leaves the Dice sums in the workspace for bwd; bwd writes all 2*nscales gradients.
+ * ------------------------------------------------------------------------------------------- */
+size_t pv2_mc_dual_loss_workspace_bytes(int B, int C, int H, int W);
+int pv2_mc_dual_loss_fwd(const float* const* P_fg, const float* const* P_bg, const long long* labels, int nscales, int mode,
+                         int B, int C, int H, int W, float lc_ce, float lc_dice, float lc_bce, float* loss,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int pv2_mc_dual_loss_bwd(const float* const* P_fg, const float* const* P_bg, const long long* labels, const float* grad_loss,
+                         float* const* dP_fg, float* const* dP_bg, int nscales, int mode, int B, int C, int H, int W,
+                         float lc_ce, float lc_dice, float lc_bce, const void* workspace, size_t workspace_bytes, void* stream);
+
 /* =============================================================================================
  * Conv engine (tcgen05 / TMEM / TMA) -- nn.Conv2d + nn.BatchNorm2d + F.relu of BasicConv2d
  * (binary_seg/lib/pranet.py:31-43 and its callers :75-82, :109-123, :357-363, :378-383, :400-405;

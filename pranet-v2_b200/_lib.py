@@ -32,6 +32,9 @@ _SIGS = {
     "pv2_dsra_fuse_bwd": (_i, [_p] * 6 + [_i] * 6 + [_f, _f, _i, _p]),
     "pv2_ra_v1_scale_fwd": (_i, [_p] * 3 + [_i] * 4 + [_p]),
     "pv2_ra_v1_scale_bwd": (_i, [_p] * 5 + [_i] * 4 + [_p]),
+    "pv2_mc_dual_loss_workspace_bytes": (_sz, [_i] * 4),
+    "pv2_mc_dual_loss_fwd": (_i, [c_void_pp, c_void_pp, _p, _i, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _sz, _p]),
+    "pv2_mc_dual_loss_bwd": (_i, [c_void_pp, c_void_pp, _p, _p, c_void_pp, c_void_pp, _i, _i, _i, _i, _i, _i, _f, _f, _f, _p, _sz, _p]),
     # conv engine
     "pv2_conv_splits_hint": (_i, [_i] * 9),
     "pv2_conv_fwd": (_i, [_p, _ll, _p, _ll, _i, _i] + [_i] * 9 + [_i, _p, _i, _i, _p, _p]),

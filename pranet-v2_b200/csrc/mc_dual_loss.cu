@@ -1,0 +1,333 @@
+// Multiclass dual-supervision loss (EMCAD/trainer.py:123-140 == MERIT/train_ACDC.py:259-284 == MIST/trainer.py:112-129):
+//
+//   loss = sum over the non-empty subsets s of the n (= 4) scales of
+//          lc_ce * CE(sum_{i in s} P_fg[i], y) + lc_dice * Dice(softmax(sum P_fg[i]), onehot(y)) + lc_bce * mean BCEWithLogits(sum P_bg[i], 1 - onehot(y))
+//   Dice = mean_c [ 1 - (2*sum p_c t_c + 1e-5) / (sum p_c^2 + sum t_c^2 + 1e-5) ]   over the WHOLE batch (EMCAD/utils/utils.py:102-138)
+//
+// The reference evaluates this as 15 x (CrossEntropyLoss + softmax + a 9-iteration python Dice loop with .item() syncs +
+// BCEWithLogitsLoss) on tensors it first sums in separate kernels, and builds the inverted one-hot mask on the CPU
+// (trainer.py:22-29, 99-103).  Here: ONE forward launch (+ a tiny fold) and ONE backward launch.
+//   * one thread = one pixel; the 8*C logits of the pixel are read once (coalesced per class plane) into registers;
+//   * the 2^n - 1 subsets are walked in Gray-code order, so every step adds or removes ONE scale from the running sums;
+//   * the inverted one-hot target is derived from the label on the fly (no mask tensor, no H2D copy);
+//   * per subset the 2 + 2C partial sums are reduced warp-shuffle -> per-warp shared slots -> one partial row per CTA;
+//     the fold kernel adds the CTA rows in a fixed order (bit-reproducible) and leaves the Dice sums for the backward.
+// Bound: MUFU (C exp + C softplus per subset and pixel), not HBM: 15*(2C) ex2 + 15*C lg2 per pixel.
+#include "pv2_common.cuh"
+
+namespace pv2 {
+namespace {
+
+constexpr int MAXN = 4;               // scales
+constexpr int MAXS = (1 << MAXN) - 1; // subsets
+constexpr int MC_THREADS = 128;
+constexpr float DICE_EPS = 1e-5f;
+
+struct McPtrs {
+    const float* fg[MAXN];
+    const float* bg[MAXN];
+    float* dfg[MAXN];
+    float* dbg[MAXN];
+};
+
+__device__ __forceinline__ int subset_of(int k, int mode) {   // k = 1 .. nsub
+    return mode == 0 ? (k ^ (k >> 1)) : (1 << (k - 1));         // Gray code over all non-empty subsets | singletons
+}
+
+// row layout of the partial / total sums for subset index j (0-based): [ce, bce, I_0..I_{C-1}, Z_0..Z_{C-1}]
+template <int C> struct Row { static constexpr int N = 2 + 2 * C; };
+
+template <int C>
+__global__ void __launch_bounds__(MC_THREADS)
+mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mode, long long npix, int HW,
+                   float* __restrict__ partials /* [grid][nsub*Row + C] */) {
+    constexpr int R = Row<C>::N;
+    const int nsub = mode == 0 ? (1 << n) - 1 : n;
+    extern __shared__ float sacc[];                     // [warps][nsub*R + C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = MC_THREADS / 32;
+    const int width = nsub * R + C;
+    for (int i = threadIdx.x; i < nw * width; i += MC_THREADS) sacc[i] = 0.0f;
+    __syncthreads();
+    float* my = sacc + warp * width;
+    for (long long pix0 = (long long)blockIdx.x * MC_THREADS; pix0 < npix; pix0 += (long long)gridDim.x * MC_THREADS) {
+        const long long pix = pix0 + threadIdx.x;
+        const bool ok = pix < npix;
+        const long long b = ok ? pix / HW : 0, hw = ok ? pix - b * HW : 0;
+        const int y = ok ? (int)labels[pix] : -1;
+        float f[MAXN][C], g[MAXN][C];
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const long long off = (b * C + c) * HW + hw;
+                f[i][c] = (ok && i < n) ? __ldg(p.fg[i] + off) : 0.0f;
+                g[i][c] = (ok && i < n) ? __ldg(p.bg[i] + off) : 0.0f;
+            }
+        // class counts (sum t_c^2 = sum t_c), once per pixel
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float v = warp_sum((ok && y == c) ? 1.0f : 0.0f);
+            if (lane == 0) my[nsub * R + c] += v;
+        }
+        float so[C], sb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) { so[c] = 0.0f; sb[c] = 0.0f; }
+        int prev = 0;
+        for (int k = 1; k <= nsub; ++k) {
+            const int s = subset_of(k, mode), diff = s ^ prev;
+            prev = s;
+#pragma unroll
+            for (int i = 0; i < MAXN; ++i) {
+                if (diff & (1 << i)) {
+                    const float sg = (s & (1 << i)) ? 1.0f : -1.0f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) { so[c] = fmaf(sg, f[i][c], so[c]); sb[c] = fmaf(sg, g[i][c], sb[c]); }
+                }
+            }
+            float mx = so[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) mx = fmaxf(mx, so[c]);
+            float e[C], den = 0.0f, sy = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { e[c] = __expf(so[c] - mx); den += e[c]; if (c == y) sy = so[c]; }
+            const float inv = 1.0f / den;
+            float ce = ok ? (__logf(den) + mx - sy) : 0.0f, bce = 0.0f;
+            float* row = my + (k - 1) * R;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float pc = ok ? e[c] * inv : 0.0f;
+                const float t = (c == y) ? 1.0f : 0.0f;
+                const float x = sb[c];
+                bce += ok ? (fmaxf(x, 0.0f) - x * (1.0f - t) + __logf(1.0f + __expf(-fabsf(x)))) : 0.0f;
+                const float I = warp_sum(pc * t), Z = warp_sum(pc * pc);
+                if (lane == 0) { row[2 + c] += I; row[2 + C + c] += Z; }
+            }
+            ce = warp_sum(ce); bce = warp_sum(bce);
+            if (lane == 0) { row[0] += ce; row[1] += bce; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < width; i += MC_THREADS) {
+        float v = 0.0f;
+        for (int w = 0; w < nw; ++w) v += sacc[w * width + i];
+        partials[(size_t)blockIdx.x * width + i] = v;
+    }
+}
+
+// one CTA: totals[i] = sum over CTA rows (fixed order); loss from the totals
+template <int C>
+__global__ void mc_loss_fold_kernel(const float* __restrict__ partials, int nrows, int nsub, long long npix,
+                                    float lc_ce, float lc_dice, float lc_bce, float* __restrict__ totals, float* __restrict__ loss) {
+    constexpr int R = Row<C>::N;
+    const int width = nsub * R + C;
+    for (int i = threadIdx.x; i < width; i += blockDim.x) {
+        float v = 0.0f;
+        for (int r = 0; r < nrows; ++r) v += partials[(size_t)r * width + i];
+        totals[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float L = 0.0f;
+        for (int j = 0; j < nsub; ++j) {
+            const float* row = totals + j * R;
+            float dice = 0.0f;
+            for (int c = 0; c < C; ++c) {
+                const float Y = totals[nsub * R + c];
+                dice += 1.0f - (2.0f * row[2 + c] + DICE_EPS) / (row[2 + C + c] + Y + DICE_EPS);
+            }
+            L += lc_ce * row[0] / (float)npix + lc_dice * dice / (float)C + lc_bce * row[1] / ((float)npix * (float)C);
+        }
+        *loss = L;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(MC_THREADS)
+mc_loss_bwd_kernel(McPtrs p, const long long* __restrict__ labels, const float* __restrict__ grad_loss,
+                   const float* __restrict__ totals, int n, int mode, long long npix, int HW,
+                   float lc_ce, float lc_dice, float lc_bce) {
+    constexpr int R = Row<C>::N;
+    const int nsub = mode == 0 ? (1 << n) - 1 : n;
+    const long long pix = (long long)blockIdx.x * MC_THREADS + threadIdx.x;
+    if (pix >= npix) return;
+    const long long b = pix / HW, hw = pix - b * HW;
+    const int y = (int)labels[pix];
+    const float gl = *grad_loss;
+    const float w_ce = gl * lc_ce / (float)npix, w_bce = gl * lc_bce / ((float)npix * (float)C), w_dice = gl * lc_dice / (float)C;
+    // ---- foreground: CE + Dice through the softmax ----
+    {
+        float f[MAXN][C], d[MAXN][C], so[C];
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) { f[i][c] = i < n ? __ldg(p.fg[i] + (b * C + c) * HW + hw) : 0.0f; d[i][c] = 0.0f; }
+#pragma unroll
+        for (int c = 0; c < C; ++c) so[c] = 0.0f;
+        int prev = 0;
+        for (int k = 1; k <= nsub; ++k) {
+            const int s = subset_of(k, mode), diff = s ^ prev;
+            prev = s;
+#pragma unroll
+            for (int i = 0; i < MAXN; ++i)
+                if (diff & (1 << i)) {
+                    const float sg = (s & (1 << i)) ? 1.0f : -1.0f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) so[c] = fmaf(sg, f[i][c], so[c]);
+                }
+            float mx = so[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) mx = fmaxf(mx, so[c]);
+            float pr[C], den = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { pr[c] = __expf(so[c] - mx); den += pr[c]; }
+            const float inv = 1.0f / den;
+            const float* row = totals + (k - 1) * R;
+            float dp[C], dot = 0.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                pr[c] *= inv;
+                const float t = (c == y) ? 1.0f : 0.0f;
+                const float num = 2.0f * row[2 + c] + DICE_EPS, D = row[2 + C + c] + totals[nsub * R + c] + DICE_EPS;
+                // d/dp_c of -(num/D): -(2 t D - num * 2 p) / D^2
+                dp[c] = -w_dice * (2.0f * t * D - num * 2.0f * pr[c]) / (D * D);
+                dot += pr[c] * dp[c];
+            }
+            float gs[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) gs[c] = pr[c] * (dp[c] - dot) + w_ce * (pr[c] - ((c == y) ? 1.0f : 0.0f));
+#pragma unroll
+            for (int i = 0; i < MAXN; ++i)
+                if (s & (1 << i)) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) d[i][c] += gs[c];
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+            if (i < n) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) p.dfg[i][(b * C + c) * HW + hw] = d[i][c];
+            }
+    }
+    // ---- background: BCE against the inverted one-hot ----
+    {
+        float g[MAXN][C], d[MAXN][C], sb[C];
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+#pragma unroll
+            for (int c = 0; c < C; ++c) { g[i][c] = i < n ? __ldg(p.bg[i] + (b * C + c) * HW + hw) : 0.0f; d[i][c] = 0.0f; }
+#pragma unroll
+        for (int c = 0; c < C; ++c) sb[c] = 0.0f;
+        int prev = 0;
+        for (int k = 1; k <= nsub; ++k) {
+            const int s = subset_of(k, mode), diff = s ^ prev;
+            prev = s;
+#pragma unroll
+            for (int i = 0; i < MAXN; ++i)
+                if (diff & (1 << i)) {
+                    const float sg = (s & (1 << i)) ? 1.0f : -1.0f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) sb[c] = fmaf(sg, g[i][c], sb[c]);
+                }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float sig = 1.0f / (1.0f + __expf(-sb[c]));
+                const float gq = w_bce * (sig - ((c == y) ? 0.0f : 1.0f));
+#pragma unroll
+                for (int i = 0; i < MAXN; ++i)
+                    if (s & (1 << i)) d[i][c] += gq;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXN; ++i)
+            if (i < n) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) p.dbg[i][(b * C + c) * HW + hw] = d[i][c];
+            }
+    }
+}
+
+inline int fwd_grid(long long npix) {
+    long long g = (npix + MC_THREADS - 1) / MC_THREADS;
+    const long long cap = (long long)kNumSMs * 8;
+    return (int)(g > cap ? cap : g);
+}
+
+template <int C>
+int launch_all(bool backward, const McPtrs& p, const long long* labels, const float* grad_loss, int n, int mode, int B, int H, int W,
+               float lc_ce, float lc_dice, float lc_bce, float* loss, float* ws, cudaStream_t st) {
+    const long long npix = (long long)B * H * W;
+    const int nsub = mode == 0 ? (1 << n) - 1 : n, width = nsub * Row<C>::N + C, grid = fwd_grid(npix);
+    float* totals = ws;
+    float* partials = ws + ((width + 63) / 64) * 64;
+    if (!backward) {
+        const size_t smem = sizeof(float) * (MC_THREADS / 32) * width;
+        mc_loss_fwd_kernel<C><<<grid, MC_THREADS, smem, st>>>(p, labels, n, mode, npix, H * W, partials);
+        PV2_LAUNCH_CHECK("mc_loss_fwd");
+        mc_loss_fold_kernel<C><<<1, 256, 0, st>>>(partials, grid, nsub, npix, lc_ce, lc_dice, lc_bce, totals, loss);
+        PV2_LAUNCH_CHECK("mc_loss_fold");
+    } else {
+        mc_loss_bwd_kernel<C><<<(unsigned)((npix + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st>>>(p, labels, grad_loss, totals, n, mode, npix, H * W,
+                                                                                                        lc_ce, lc_dice, lc_bce);
+        PV2_LAUNCH_CHECK("mc_loss_bwd");
+    }
+    return 0;
+}
+
+int dispatch(bool backward, int C, const McPtrs& p, const long long* labels, const float* grad_loss, int n, int mode, int B, int H, int W,
+             float a, float b2, float c2, float* loss, float* ws, cudaStream_t st) {
+#define PV2_MC(CV) case CV: return launch_all<CV>(backward, p, labels, grad_loss, n, mode, B, H, W, a, b2, c2, loss, ws, st)
+    switch (C) {
+        PV2_MC(2); PV2_MC(3); PV2_MC(4); PV2_MC(5); PV2_MC(6); PV2_MC(7); PV2_MC(8); PV2_MC(9); PV2_MC(10); PV2_MC(11); PV2_MC(12);
+        default: break;
+    }
+#undef PV2_MC
+    set_error("mc_dual_loss: num_classes=%d not in the compiled range [2,12]", C);
+    return 1;
+}
+
+int mc_check(const float* const* fg, const float* const* bg, const long long* labels, int n, int mode, int B, int C, int H, int W,
+             const void* ws, size_t ws_bytes) {
+    PV2_CHECK(fg && bg && labels && ws, "mc_dual_loss: null pointer");
+    PV2_CHECK(n >= 1 && n <= MAXN, "mc_dual_loss: number of scales %d out of range [1,%d]", n, MAXN);
+    PV2_CHECK(mode == 0 || mode == 1, "mc_dual_loss: mode must be 0 (all non-empty subsets) or 1 (deep supervision)");
+    PV2_CHECK(B > 0 && C >= 2 && H > 0 && W > 0, "mc_dual_loss: bad shape");
+    for (int i = 0; i < n; ++i) PV2_CHECK(fg[i] && bg[i], "mc_dual_loss: null logits pointer at scale %d", i);
+    PV2_CHECK(ws_bytes >= pv2_mc_dual_loss_workspace_bytes(B, C, H, W), "mc_dual_loss: workspace too small");
+    return 0;
+}
+
+}  // namespace
+}  // namespace pv2
+
+using namespace pv2;
+
+extern "C" size_t pv2_mc_dual_loss_workspace_bytes(int B, int C, int H, int W) {
+    const int width = MAXS * (2 + 2 * C) + C;
+    const long long npix = (long long)B * H * W;
+    return sizeof(float) * ((size_t)((width + 63) / 64) * 64 + (size_t)fwd_grid(npix) * width);
+}
+
+extern "C" int pv2_mc_dual_loss_fwd(const float* const* P_fg, const float* const* P_bg, const long long* labels, int nscales, int mode,
+                                    int B, int C, int H, int W, float lc_ce, float lc_dice, float lc_bce, float* loss,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (int e = mc_check(P_fg, P_bg, labels, nscales, mode, B, C, H, W, workspace, workspace_bytes)) return e;
+    PV2_CHECK(loss != nullptr, "mc_dual_loss_fwd: null loss pointer");
+    McPtrs p = {};
+    for (int i = 0; i < nscales; ++i) { p.fg[i] = P_fg[i]; p.bg[i] = P_bg[i]; }
+    return dispatch(false, C, p, labels, nullptr, nscales, mode, B, H, W, lc_ce, lc_dice, lc_bce, loss, (float*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" int pv2_mc_dual_loss_bwd(const float* const* P_fg, const float* const* P_bg, const long long* labels, const float* grad_loss,
+                                    float* const* dP_fg, float* const* dP_bg, int nscales, int mode, int B, int C, int H, int W,
+                                    float lc_ce, float lc_dice, float lc_bce, const void* workspace, size_t workspace_bytes, void* stream) {
+    if (int e = mc_check(P_fg, P_bg, labels, nscales, mode, B, C, H, W, workspace, workspace_bytes)) return e;
+    PV2_CHECK(grad_loss && dP_fg && dP_bg, "mc_dual_loss_bwd: null pointer");
+    McPtrs p = {};
+    for (int i = 0; i < nscales; ++i) {
+        PV2_CHECK(dP_fg[i] && dP_bg[i], "mc_dual_loss_bwd: null gradient pointer at scale %d", i);
+        p.fg[i] = P_fg[i]; p.bg[i] = P_bg[i]; p.dfg[i] = dP_fg[i]; p.dbg[i] = dP_bg[i];
+    }
+    return dispatch(true, C, p, labels, grad_loss, nscales, mode, B, H, W, lc_ce, lc_dice, lc_bce, nullptr, (float*)const_cast<void*>(workspace),
+                    (cudaStream_t)stream);
+}

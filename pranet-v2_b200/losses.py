@@ -5,8 +5,4 @@ loss is the block at EMCAD/trainer.py:123-140 (== MERIT/train_ACDC.py:259-284 ==
 """
 from __future__ import annotations
 
-from .ops import structure_loss, structure_loss_multi  # noqa: F401
-
-
-def mc_dual_loss(P_fg, P_bg, labels, num_classes, lc=(0.5, 0.7, 0.3)):
-    raise NotImplementedError("mc_dual_loss kernel not built yet")
+from .ops import mc_dual_loss, structure_loss, structure_loss_multi  # noqa: F401

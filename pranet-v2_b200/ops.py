@@ -237,3 +237,64 @@ def ra_v1_scale(x, crop):
     if crop.shape[1] != 1 or crop.shape[0] != x.shape[0] or crop.shape[-2:] != x.shape[-2:]:
         raise ValueError(f"ra_v1_scale: crop {tuple(crop.shape)} does not broadcast over x {tuple(x.shape)}")
     return _RaV1Fn.apply(x, crop)
+
+
+# ------------------------------------------------------------------------------------------------
+# multiclass dual-supervision loss
+# ------------------------------------------------------------------------------------------------
+class _McDualLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels, num_classes, mode, lc, *logits):
+        lib = _lib.load()
+        n = len(logits) // 2
+        fgs = [t.contiguous().float() for t in logits[:n]]
+        bgs = [t.contiguous().float() for t in logits[n:]]
+        B, Cc, H, W = fgs[0].shape
+        if Cc != num_classes:
+            raise ValueError(f"mc_dual_loss: logits have {Cc} channels, num_classes={num_classes}")
+        for t in fgs + bgs:
+            if tuple(t.shape) != (B, Cc, H, W):
+                raise ValueError("mc_dual_loss: all logits must share one shape")
+        if tuple(labels.shape) != (B, H, W):
+            raise ValueError(f"mc_dual_loss: labels shape {tuple(labels.shape)} != {(B, H, W)}")
+        labels = labels.contiguous().long()
+        ws_bytes = lib.pv2_mc_dual_loss_workspace_bytes(B, Cc, H, W)
+        ws = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=labels.device)
+        loss = torch.empty((), dtype=torch.float32, device=labels.device)
+        pf, k1 = _lib.ptr_array(fgs)
+        pb, k2 = _lib.ptr_array(bgs)
+        _lib.check(lib.pv2_mc_dual_loss_fwd(pf, pb, labels.data_ptr(), n, mode, B, Cc, H, W, lc[0], lc[1], lc[2], loss.data_ptr(),
+                                            ws.data_ptr(), ws_bytes, _stream()), "pv2_mc_dual_loss_fwd")
+        ctx.save_for_backward(labels, ws, *fgs, *bgs)
+        ctx.meta = (n, mode, B, Cc, H, W, lc, ws_bytes)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        n, mode, B, Cc, H, W, lc, ws_bytes = ctx.meta
+        labels, ws = ctx.saved_tensors[:2]
+        fgs, bgs = list(ctx.saved_tensors[2:2 + n]), list(ctx.saved_tensors[2 + n:2 + 2 * n])
+        g = g.contiguous().float()
+        dfg = [torch.empty_like(t) for t in fgs]
+        dbg = [torch.empty_like(t) for t in bgs]
+        pf, k1 = _lib.ptr_array(fgs)
+        pb, k2 = _lib.ptr_array(bgs)
+        df, k3 = _lib.ptr_array(dfg)
+        db, k4 = _lib.ptr_array(dbg)
+        _lib.check(lib.pv2_mc_dual_loss_bwd(pf, pb, labels.data_ptr(), g.data_ptr(), df, db, n, mode, B, Cc, H, W, lc[0], lc[1], lc[2],
+                                            ws.data_ptr(), ws_bytes, _stream()), "pv2_mc_dual_loss_bwd")
+        return (None, None, None, None, *dfg, *dbg)
+
+
+def mc_dual_loss(P_fg, P_bg, labels, num_classes, lc=(0.5, 0.7, 0.3), supervision="mutation"):
+    """The multiclass dual loss block of EMCAD/trainer.py:123-140: P_fg / P_bg are the lists of (up to 4) foreground /
+    background logits (B, C, H, W), labels the (B, H, W) class map; `supervision` = 'mutation' (all non-empty subsets,
+    the reference default) or 'deep_supervision' (each scale alone).  The inverted one-hot mask of trainer.py:22-29 is
+    derived on the device from `labels`."""
+    P_fg, P_bg = list(P_fg), list(P_bg)
+    _need_cuda(labels, *P_fg, *P_bg)
+    if len(P_fg) != len(P_bg) or not 1 <= len(P_fg) <= 4:
+        raise ValueError("mc_dual_loss takes 1..4 foreground maps and as many background maps")
+    mode = {"mutation": 0, "deep_supervision": 1}[supervision]
+    return _McDualLossFn.apply(labels, int(num_classes), mode, tuple(float(v) for v in lc), *P_fg, *P_bg)

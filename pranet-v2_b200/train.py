@@ -22,6 +22,42 @@ from . import _lib, ops
 _UNUSED_PREFIXES = ("conv.", "backbone.fc.", "resnet.fc.")   # defined by the reference nets but never used in forward
 
 
+class FlatGradBucket:
+    """All gradients of a replica in ONE flat fp32 buffer: gathered with a multi-tensor copy, all-reduced as a single
+    message (NCCL over NVLink on the GPU box, gloo in the CPU tests), clamped element-wise, and handed to the optimizer as
+    per-parameter views (same strides as the parameters, so fused optimizers accept them)."""
+
+    def __init__(self, params, device):
+        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=device)
+        self.views, o = [], 0
+        for p in params:
+            self.views.append(torch.as_strided(self.flat, p.shape, p.stride(), storage_offset=o))
+            o += p.numel()
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def gather(self, grads):
+        torch._foreach_copy_(self.views, [g if g is not None else torch.zeros_like(v) for g, v in zip(grads, self.views)])
+
+    def all_reduce_sum(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat)
+
+    def all_reduce_mean(self):
+        self.all_reduce_sum()
+        self.scale_for_mean()
+
+    def scale_for_mean(self):
+        if self.world > 1:
+            self.flat.div_(self.world)
+
+    def clamp_(self, clip):
+        self.flat.clamp_(-clip, clip)                  # clip_gradient of binary_seg/utils/utils.py:7-17
+
+    def install(self, params):
+        for p, v in zip(params, self.views):
+            p.grad = v
+
+
 class TrainStep:
     def __init__(self, model: nn.Module, lr: float = 1e-4, clip: float = 0.5, autocast_backbone: bool = True,
                  device=None, channels_last: bool = True, use_graph: bool = True):
@@ -37,13 +73,8 @@ class TrainStep:
         if self.world > 1:   # identical replicas to start from
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, 0)
-        # one flat gradient bucket; p.grad for the optimizer are views into it
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=self.device)
-        self.views, o = [], 0
-        for p in self.params:
-            # same strides as the parameter (conv weights are channels_last): the fused optimizer wants matching layouts
-            self.views.append(torch.as_strided(self.flat, p.shape, p.stride(), storage_offset=o))
-            o += p.numel()
+        self.bucket = FlatGradBucket(self.params, self.device)
+        self.flat = self.bucket.flat
         self.opt = torch.optim.Adam(self.params, lr, fused=True, capturable=True)   # MyTrain_med.py:148-149
         self.clip, self.autocast, self.channels_last, self.use_graph = clip, autocast_backbone, channels_last, use_graph
         self._static = None
@@ -59,16 +90,13 @@ class TrainStep:
         pairs = [(outs[i].float(), outs[i + 4].float()) for i in range(4)]
         loss = ops.structure_loss_multi(pairs, gts).sum()            # MyTrain_med.py:78-82
         loss.backward()
-        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
-        torch._foreach_copy_(self.views, grads)
+        self.bucket.gather([p.grad for p in self.params])
         return loss.detach()
 
     def _update(self):
-        if self.world > 1:
-            self.flat.div_(self.world)
-        self.flat.clamp_(-self.clip, self.clip)                      # clip_gradient: grad.clamp_(-clip, clip)
-        for p, v in zip(self.params, self.views):
-            p.grad = v
+        self.bucket.scale_for_mean()
+        self.bucket.clamp_(self.clip)
+        self.bucket.install(self.params)
         self.opt.step()
 
     # -- graph capture ------------------------------------------------------------------------------------------

@@ -162,3 +162,38 @@ def test_ra_v1_scale(B, C, h, dtype):
     assert (out.float().cpu() - ref).abs().max() <= tol * max(1.0, ref.abs().max().item())
     assert (xd.grad.float().cpu() - xr.grad).abs().max() <= tol * max(1.0, xr.grad.abs().max().item())
     assert (cd.grad.cpu() - cr.grad).abs().max() <= tol * max(1.0, cr.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("name", list(G.MC_LOSS_CASES))
+def test_mc_dual_loss_golden(name):
+    case = G.MC_LOSS_CASES[name]
+    g = G.load(name)
+    P_fg, P_bg, labels = G.mc_loss_inputs(name)
+    fg = [t.to(DEV).requires_grad_(True) for t in P_fg]
+    bg = [t.to(DEV).requires_grad_(True) for t in P_bg]
+    loss = P.mc_dual_loss(fg, bg, labels.to(DEV), case["num_class"])
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    for i in range(4):
+        for got, ref in ((fg[i].grad, g[f"dfg{i}"]), (bg[i].grad, g[f"dbg{i}"])):
+            assert np.abs(got.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("B,C,H,W,supervision,nmaps", [(4, 9, 224, 224, "mutation", 4), (2, 4, 100, 75, "mutation", 4),
+                                                        (2, 9, 64, 64, "deep_supervision", 4), (2, 5, 40, 40, "mutation", 3)])
+def test_mc_dual_loss_vs_oracle(B, C, H, W, supervision, nmaps):
+    fg = [synth.logits((B, C, H, W), 3, f"f{i}", 1.5) for i in range(nmaps)]
+    bg = [synth.logits((B, C, H, W), 3, f"b{i}", 1.5) for i in range(nmaps)]
+    labels = synth.class_labels(B, H, W, C, 3)
+    rf = [t.clone().requires_grad_(True) for t in fg]
+    rb = [t.clone().requires_grad_(True) for t in bg]
+    subsets = O.powerset_subsets(nmaps) if supervision == "mutation" else [[i] for i in range(nmaps)]
+    ref = O.mc_dual_loss(rf, rb, labels, C, subsets)
+    ref.backward()
+    df = [t.to(DEV).requires_grad_(True) for t in fg]
+    db = [t.to(DEV).requires_grad_(True) for t in bg]
+    loss = P.mc_dual_loss(df, db, labels.to(DEV), C, supervision=supervision)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    for a, b in zip(df + db, rf + rb):
+        assert (a.grad.cpu() - b.grad).abs().max() <= 1e-3 * b.grad.abs().max()
