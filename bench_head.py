@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench_head.py -- BASELINE.json config 5: DSRA head + structure_loss microbenchmark sweep with a roofline report.
+
+    python bench_head.py [--batches 1,4,16,64] [--sizes 256,352,704] [--iters 50] [--precision bf16|fp32]
+                         [--backbone res2net|pvt] [--out gpurun_out/head_sweep.jsonl] [--kernels]
+
+For every (batch B, input size S) the head is fed synthetic backbone features relu(randn) of shapes
+(B,512,S/8,S/8), (B,1024,S/16,S/16), (B,2048,S/32,S/32) [PVT: 128/320/512] and timed as ONE
+CUDA graph: head forward -> 4x structure loss (one fused launch) -> backward through loss and head (feature gradients and
+all weight gradients).  Timing: CUDA events around `iters` replays after warm-up; features, activations and gradients
+of a replay exceed the 126 MB L2 only at the large end of the sweep -- the small end is launch/latency bound and says so.
+
+`--kernels` adds the per-kernel roofline table: the memory-bound kernels (structure loss fwd/bwd, boundary weight, final
+upsample fwd/bwd, V1 reverse-attention scale) in GB/s of ALGORITHMIC bytes against the measured HBM peak, and the conv
+GEMMs (fprop of the head's distinct shapes) in TFLOP/s of un-padded 2*M*N*K against the measured bf16 peak.
+With torchrun every rank runs the same sweep on its own GPU (independent replicas) and rank 0 reports min/median.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md: 6650 GB/s, 1590 TFLOP/s)"
+
+
+def timed(fn, iters, warm=5):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters   # ms
+
+
+def head_flops(model, B, S):
+    """Un-padded conv FLOPs of one head forward (2*M*N*K summed over every nn.Conv2d outside the backbone)."""
+    import torch.nn as nn
+    res = {"backbone.": None}
+    total = 0
+    # spatial size per conv: derived from the module name (x4-level convs run at S/32, x3 at S/16, x2 at S/8)
+    for name, m in model.named_modules():
+        if not isinstance(m, nn.Conv2d) or name.startswith(("backbone.", "resnet.", "conv.")):
+            continue
+        if name.startswith(("rfb4_1", "ra4_")):
+            hw = S // 32
+        elif name.startswith(("rfb3_1", "ra3_")):
+            hw = S // 16
+        elif name.startswith(("rfb2_1", "ra2_")):
+            hw = S // 8
+        elif name.startswith("agg1.conv_upsample1") or name.startswith("agg1.conv_upsample4") or name.startswith("agg1.conv_concat2"):
+            hw = S // 16
+        else:
+            hw = S // 8
+        kh, kw = m.kernel_size
+        total += 2 * B * hw * hw * m.out_channels * m.in_channels * kh * kw
+    return total
+
+
+def sweep_point(P, model, B, S, iters, chans, dev):
+    from pranet_v2_b200 import synthetic
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + S)
+    feats = [torch.relu(torch.randn(B, c, S // s, S // s, generator=g)).to(dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+             for c, s in zip(chans, (8, 16, 32))]
+    if P.get_precision() == "fp32":
+        feats = [f.detach().float().contiguous().requires_grad_(True) for f in feats]
+    gt = synthetic.ellipse_masks(B, S, S, 3).to(dev)
+    params = model.head_parameters()
+
+    def step():
+        for p in params:
+            p.grad = None
+        for f in feats:
+            f.grad = None
+        outs = model.forward_head(*feats)
+        loss = P.structure_loss_multi([(outs[i], outs[i + 4]) for i in range(4)], gt).sum()
+        loss.backward()
+        return loss
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    n0 = P._lib.launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        loss = step()
+    launches = P._lib.launch_count() - n0
+    ms = timed(graph.replay, iters)
+    ms_eager = timed(step, max(3, iters // 10), warm=1)
+    px = B * S * S
+    # algorithmic HBM bytes of the full-resolution part of the step (fp32 maps): 8 final maps written (fwd) and their
+    # gradients read (bwd) by the upsample kernels, the loss reading 8 maps + mask (fwd) and reading 8 + mask / writing 8 (bwd)
+    full_res_bytes = px * 4 * (8 + 8 + (8 + 1) + (8 + 1 + 8))
+    return {"B": B, "S": S, "ms_graph": ms, "ms_eager": ms_eager, "images_per_s": B / ms * 1e3, "pv2_launches": launches,
+            "loss": float(loss), "head_conv_gflop_fwd": head_flops(model, B, S) / 1e9,
+            "conv_tflops_fwd_bwd": 3 * head_flops(model, B, S) / (ms * 1e-3) / 1e12,
+            "full_res_bytes": full_res_bytes, "full_res_gbs_if_alone": full_res_bytes / (ms * 1e-3) / 1e9}
+
+
+def kernel_table(P, dev, B, S, hbm, tflops):
+    """Per-kernel rooflines at one (B, S): each kernel launched back to back over rotating buffers (> L2), CUDA events."""
+    from pranet_v2_b200 import synthetic
+    from pranet_v2_b200.ops import PV2_F32, _ratio
+    lib = P._lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+    px = B * S * S
+    nset = max(2, int(400e6 // (px * 4 * 16)) + 1)
+    m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
+    shape = (B, 1, S, S)
+    logits = [[torch.randn(shape, device=dev) for _ in range(8)] for _ in range(nset)]
+    grads = [[torch.empty(shape, device=dev) for _ in range(8)] for _ in range(nset)]
+    ws_bytes = lib.pv2_structure_loss_workspace_bytes(B, S, S, 4)
+    ws = torch.empty(ws_bytes // 4, device=dev)
+    loss, gl = torch.empty(4, device=dev), torch.ones(4, device=dev)
+    packs = [(P._lib.ptr_array(logits[j][:4]), P._lib.ptr_array(logits[j][4:]), P._lib.ptr_array(grads[j][:4]), P._lib.ptr_array(grads[j][4:])) for j in range(nset)]
+    cnt = [0]
+
+    def rot():
+        cnt[0] += 1
+        return cnt[0] % nset
+
+    def sl_fwd():
+        (pp, _), (pb, _), _, _ = packs[rot()]
+        P._lib.check(lib.pv2_structure_loss_fwd(pp, pb, m.data_ptr(), None, 4, B, S, S, 0, loss.data_ptr(), ws.data_ptr(), ws_bytes, st), "fwd")
+
+    def sl_bwd():
+        (pp, _), (pb, _), (dp, _), (dq, _) = packs[rot()]
+        P._lib.check(lib.pv2_structure_loss_bwd(pp, pb, m.data_ptr(), None, gl.data_ptr(), dp, dq, 4, B, S, S, 0, ws.data_ptr(), ws_bytes, st), "bwd")
+
+    sl_fwd()
+    t = timed(sl_fwd, 30)
+    rows.append(("structure_loss fwd x4 (+ boundary weight + finalize)", "hbm", px * (4 + 4 * 8), t))
+    t = timed(sl_bwd, 30)
+    rows.append(("structure_loss bwd x4", "hbm", px * (4 + 4 * 16), t))
+    # final upsamples: x8 of a 44^2 map (two of the 8 maps are x32 / x16; x8 dominates), fp32
+    for s in (8, 16, 32):
+        h = S // s
+        lo = [torch.randn(B, 1, h, h, device=dev) for _ in range(nset * 8)]
+        hi = [torch.empty(B, 1, S, S, device=dev) for _ in range(nset * 8)]
+        r = _ratio(h, S, False, float(s))
+
+        def up_f():
+            j = rot() * 8 % len(lo)
+            P._lib.check(lib.pv2_bilinear_fwd(lo[j].data_ptr(), hi[j].data_ptr(), B, h, h, S, S, r, r, 0, PV2_F32, st), "bil")
+
+        def up_b():
+            j = rot() * 8 % len(lo)
+            P._lib.check(lib.pv2_bilinear_bwd(hi[j].data_ptr(), lo[j].data_ptr(), B, h, h, S, S, r, r, 0, PV2_F32, st), "bilb")
+        rows.append((f"bilinear x{s} fwd (one map)", "hbm", (px + B * h * h) * 4, timed(up_f, 50)))
+        rows.append((f"bilinear x{s} bwd (one map)", "hbm", (px + B * h * h) * 4, timed(up_b, 50)))
+        del lo, hi
+    # V1 reverse attention scale on the three backbone features (bf16)
+    for c, s in ((512, 8), (1024, 16), (2048, 32)):
+        h = S // s
+        n = max(2, int(300e6 // (B * c * h * h * 4)) + 1)
+        xs = [torch.randn(B, c, h, h, device=dev).bfloat16() for _ in range(n)]
+        ys = [torch.empty_like(x) for x in xs]
+        crop = torch.randn(B, 1, h, h, device=dev)
+
+        def ra():
+            j = rot() % n
+            P._lib.check(lib.pv2_ra_v1_scale_fwd(xs[j].data_ptr(), crop.data_ptr(), ys[j].data_ptr(), B, c, h * h, 1, st), "ra")
+        rows.append((f"ra_v1_scale fwd C={c} {h}^2 bf16", "hbm", 2 * B * c * h * h * 2 + B * h * h * 4, timed(ra, 50)))
+        del xs, ys
+    out = []
+    for name, bound, work, ms in rows:
+        ach = work / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "bound": bound, "bytes": work, "us": ms * 1e3, "achieved_gbs": ach, "frac_of_hbm_peak": ach / hbm})
+    # conv GEMMs (fprop) of the head's distinct big shapes, bf16
+    eng = P.engine.Engine(torch.device(dev), "bf16", True, False)
+    import torch.nn as nn
+    for (cin, cout, k, hw, label) in ((512, 224, 1, S // 8, "x2: 6 fused 1x1 (RFB x5 + ra2_conv1)"), (1024, 224, 1, S // 16, "x3: 6 fused 1x1"),
+                                      (2048, 416, 1, S // 32, "x4: 6 fused 1x1 (RFB x5 + ra4_conv1)"), (256, 256, 5, S // 32, "ra4_conv2-4 5x5 256->256"),
+                                      (96, 96, 3, S // 8, "agg1.conv_concat3 / conv4 3x3 96->96"), (64, 64, 3, S // 8, "ra2_conv2-3 3x3 64->64"),
+                                      (32, 32, 3, S // 8, "RFB branch 3x3 32->32 (dil 3)")):
+        conv = nn.Conv2d(cin, cout, k, padding=k // 2, bias=False).to(dev)
+        n = max(2, int(300e6 // (B * cin * hw * hw * 2)) + 1)
+        acts = [eng.new_act(B, hw, hw, cin) for _ in range(n)]
+        for a in acts:
+            a.t.normal_()
+
+        def cv():
+            eng.conv(acts[rot() % n], [conv])
+        cv()
+        ms = timed(cv, 50)
+        fl = 2.0 * B * hw * hw * cout * cin * k * k
+        out.append({"kernel": f"conv_fwd {label} M={B * hw * hw} N={cout} K={cin * k * k}", "bound": "tensor", "flops": fl, "us": ms * 1e3,
+                    "achieved_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tflops})
+        del acts
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batches", default="1,4,16,64")
+    ap.add_argument("--sizes", default="256,352,704")
+    ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--backbone", default="res2net", choices=["res2net", "pvt"])
+    ap.add_argument("--kernels", action="store_true")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_head.py needs a CUDA device (there is no CPU path)")
+    import pranet_v2_b200 as P
+    import torch.distributed as dist
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    P.set_precision(args.precision)
+    hbm, tfl, src = peaks()
+    torch.manual_seed(0)
+    model = (P.PraNet_V2 if args.backbone == "res2net" else P.PVT_PraNet_V2)(num_class=1).to(dev).train()
+    chans = (512, 1024, 2048) if args.backbone == "res2net" else (128, 320, 512)
+    lines = []
+    for S in [int(s) for s in args.sizes.split(",")]:
+        for B in [int(b) for b in args.batches.split(",")]:
+            if B * S * S > 64 * 704 * 704:
+                continue
+            r = sweep_point(P, model, B, S, args.iters, chans, dev)
+            if world > 1:
+                t = torch.tensor([r["ms_graph"]], device=dev, dtype=torch.float64)
+                allt = [torch.zeros_like(t) for _ in range(world)]
+                dist.all_gather(allt, t)
+                v = sorted(float(x) for x in allt)
+                r["ms_graph_min_over_gpus"], r["ms_graph_median_over_gpus"], r["n_gpus"] = v[0], v[len(v) // 2], world
+            r.update({"precision": args.precision, "backbone": args.backbone, "peaks": src})
+            lines.append(r)
+            if rank == 0:
+                print(json.dumps(r), flush=True)
+            torch.cuda.empty_cache()
+    if args.kernels and rank == 0:
+        for r in kernel_table(P, dev, 16, 352, hbm, tfl):
+            r["peaks"] = src
+            lines.append(r)
+            print(json.dumps(r), flush=True)
+    if args.out and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        with open(args.out, "w") as f:
+            for r in lines:
+                f.write(json.dumps(r) + "\n")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

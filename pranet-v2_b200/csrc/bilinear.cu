@@ -23,6 +23,7 @@ template <typename T>
 __global__ void __launch_bounds__(FWD_THREADS)
 bilinear_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int ih, int iw, int oh, int ow,
                     float rh, float rw, int ac, int max_src_rows) {
+    pv2::pdl_prologue();
     extern __shared__ float srows[];  // [nrows][iw]
     const int plane = blockIdx.y;
     const int oy0 = blockIdx.x * BAND, oy1 = min(oy0 + BAND, oh);
@@ -92,6 +93,7 @@ template <typename T>
 __global__ void __launch_bounds__(BWD_THREADS)
 bilinear_bwd_kernel(const T* __restrict__ dout, T* __restrict__ din, int ih, int iw, int oh, int ow,
                     float rh, float rw, int ac) {
+    pv2::pdl_prologue();
     extern __shared__ float colsum[];  // [ow]
     const int plane = blockIdx.y, iy = blockIdx.x;
     const T* g = dout + (size_t)plane * oh * ow;
@@ -141,9 +143,9 @@ extern "C" int pv2_bilinear_fwd(const void* in, void* out, int planes, int ih, i
     size_t smem = (size_t)max_rows * iw * 4;
     dim3 grid((oh + BAND - 1) / BAND, planes);
     if (dtype == PV2_F32)
-        bilinear_fwd_kernel<float><<<grid, FWD_THREADS, smem, st>>>((const float*)in, (float*)out, ih, iw, oh, ow, rh, rw, align_corners, max_rows);
+        pv2::launch(bilinear_fwd_kernel<float>, grid, FWD_THREADS, smem, st, (const float*)in, (float*)out, ih, iw, oh, ow, rh, rw, align_corners, max_rows);
     else
-        bilinear_fwd_kernel<__nv_bfloat16><<<grid, FWD_THREADS, smem, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, ih, iw, oh, ow, rh, rw, align_corners, max_rows);
+        pv2::launch(bilinear_fwd_kernel<__nv_bfloat16>, grid, FWD_THREADS, smem, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ih, iw, oh, ow, rh, rw, align_corners, max_rows);
     PV2_LAUNCH_CHECK("bilinear_fwd");
     return 0;
 }
@@ -157,9 +159,9 @@ extern "C" int pv2_bilinear_bwd(const void* dout, void* din, int planes, int ih,
     dim3 grid(ih, planes);
     size_t smem = (size_t)ow * 4;
     if (dtype == PV2_F32)
-        bilinear_bwd_kernel<float><<<grid, BWD_THREADS, smem, st>>>((const float*)dout, (float*)din, ih, iw, oh, ow, rh, rw, align_corners);
+        pv2::launch(bilinear_bwd_kernel<float>, grid, BWD_THREADS, smem, st, (const float*)dout, (float*)din, ih, iw, oh, ow, rh, rw, align_corners);
     else
-        bilinear_bwd_kernel<__nv_bfloat16><<<grid, BWD_THREADS, smem, st>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)din, ih, iw, oh, ow, rh, rw, align_corners);
+        pv2::launch(bilinear_bwd_kernel<__nv_bfloat16>, grid, BWD_THREADS, smem, st, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, ih, iw, oh, ow, rh, rw, align_corners);
     PV2_LAUNCH_CHECK("bilinear_bwd");
     return 0;
 }

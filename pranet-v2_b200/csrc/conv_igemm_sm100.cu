@@ -5,10 +5,12 @@
 //
 // Data layout ("operand format"): activations NHWC with the channel count padded to a multiple of 8 (bf16) / 4
 // (tf32), weights [Cout][tap][Cin_p].  GEMM view: M = pixels, N = Cout, K = taps x Cin.
-//   * an M tile is a TWb x THb patch (TWb*THb = 128) of one image; for filter tap (kh, kw) the A operand is the
-//     SAME patch shifted by (kh*dil - pad, kw*dil - pad): one 4-D TMA box load per (tap, 64-channel chunk),
-//     with out-of-image elements zero-filled by the TMA unit -- the convolution's zero padding costs nothing
-//     and no im2col buffer exists anywhere;
+//   * an M tile is 128 CONSECUTIVE output pixels of the flattened (n, y, x) axis; for filter tap (kh, kw) the A operand is
+//     those pixels displaced by (kh*dil - pad, kw*dil - pad): ONE im2col-mode TMA load per (tap, 64-channel chunk) --
+//     the TMA unit walks rows / images inside the bounding box and zero-fills out-of-image elements, so the
+//     convolution's zero padding costs nothing, every MMA row is a real pixel (M = 30976 / 7744 / 1936 at B=16 are
+//     242 / 60.5 / 15.1 tiles) and no im2col buffer exists anywhere.  (PV2_CONV_PATCH=1 selects the older tiling:
+//     TWb x THb patches of one image loaded with 4-D tiled boxes.);
 //   * B (weights) is a 3-D TMA box [BN rows][64 ch] of tap `tap`;
 //   * both land in 128-byte-swizzled shared memory, which is exactly the K-major UMMA canonical layout;
 //   * one elected thread issues tcgen05.mma (M = 128, N = BN <= 256, K = 16 bf16 / 8 tf32), the fp32 accumulator
@@ -41,6 +43,8 @@ struct ConvArgs {
     int H, W, Cout;
     int KW, taps, dil_h, dil_w, pad_h, pad_w;
     int TWb, THb, tiles_x, tiles_y;
+    int im2col;             // 1: flat 128-pixel tiles loaded in TMA im2col mode; 0: TWb x THb patches (tiled mode)
+    long long M;            // N*H*W
     int kc_per_tap, iters_total, iters_per_split;
     int BN;                 // N tile (multiple of 16, <= 256)
     uint32_t tmem_cols;     // power of two >= max(32, BN)
@@ -55,6 +59,7 @@ template <int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs a) {
+    pdl_trigger();
     constexpr int KC = (KIND == 0) ? 64 : 32;   // channels per 128-byte row
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -65,9 +70,19 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_img = a.tiles_x * a.tiles_y;
-    const int n_img = blockIdx.x / tiles_per_img, trem = blockIdx.x % tiles_per_img;
-    const int y0 = (trem / a.tiles_x) * a.THb, x0 = (trem % a.tiles_x) * a.TWb;
+    int n_img, y0, x0;
+    const long long m0 = (long long)blockIdx.x * BM;
+    if (a.im2col) {
+        const int hw = a.H * a.W;
+        n_img = (int)(m0 / hw);
+        const int rem = (int)(m0 - (long long)n_img * hw);
+        y0 = rem / a.W; x0 = rem - y0 * a.W;
+    } else {
+        const int tiles_per_img = a.tiles_x * a.tiles_y;
+        n_img = blockIdx.x / tiles_per_img;
+        const int trem = blockIdx.x % tiles_per_img;
+        y0 = (trem / a.tiles_x) * a.THb; x0 = (trem % a.tiles_x) * a.TWb;
+    }
     const int n0 = blockIdx.y * a.BN;
     const int it0 = blockIdx.z * a.iters_per_split;
     const int it1 = min(a.iters_total, it0 + a.iters_per_split);
@@ -83,6 +98,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer ----------------
@@ -96,8 +112,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int kh = tap / a.KW, kw = tap - kh * a.KW;
             mbar_expect_tx(&full_bar[s], (uint32_t)(A_BYTES + b_bytes));
             // tf32x3 terms: (A_hi,B_hi) (A_lo,B_hi) (A_hi,B_lo)
-            tma_load_4d(sA + s * A_BYTES, term == 1 ? &tmA1 : &tmA0, &full_bar[s], kc * KC,
-                        x0 + kw * a.dil_w - a.pad_w, y0 + kh * a.dil_h - a.pad_h, n_img);
+            if (a.im2col)
+                tma_load_im2col_4d(sA + s * A_BYTES, term == 1 ? &tmA1 : &tmA0, &full_bar[s], kc * KC, x0 - a.pad_w, y0 - a.pad_h, n_img,
+                                   (uint16_t)(kw * a.dil_w), (uint16_t)(kh * a.dil_h));
+            else
+                tma_load_4d(sA + s * A_BYTES, term == 1 ? &tmA1 : &tmA0, &full_bar[s], kc * KC,
+                            x0 + kw * a.dil_w - a.pad_w, y0 + kh * a.dil_h - a.pad_h, n_img);
             tma_load_3d(sB + (size_t)s * b_bytes, term == 2 ? &tmB1 : &tmB0, &full_bar[s], kc * KC, tap, n0);
         }
     } else if (warp == 1 && lane == 0) {
@@ -122,11 +142,23 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         mbar_wait(&acc_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;                  // tile row = pixel within the patch
-        const int ty = r / a.TWb, tx = r - ty * a.TWb;
-        const int y = y0 + ty, x = x0 + tx;
-        const bool valid = (y < a.H) && (x < a.W);
-        const long long pix = ((long long)n_img * a.H + y) * a.W + x;
+        const int r = q * 32 + lane;                  // tile row = pixel within the tile
+        bool valid;
+        long long pix;
+        int y, x, n_pix = n_img;
+        if (a.im2col) {
+            pix = m0 + r;
+            valid = pix < a.M;
+            const int hw = a.H * a.W;
+            n_pix = (int)(pix / hw);
+            const int rem = (int)(pix - (long long)n_pix * hw);
+            y = rem / a.W; x = rem - y * a.W;
+        } else {
+            const int ty = r / a.TWb, tx = r - ty * a.TWb;
+            y = y0 + ty; x = x0 + tx;
+            valid = (y < a.H) && (x < a.W);
+            pix = ((long long)n_img * a.H + y) * a.W + x;
+        }
         for (int c0 = 0; c0 < a.BN; c0 += 32) {
             uint32_t v[32];
             if (a.BN - c0 >= 32) {
@@ -152,7 +184,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 for (int j = 0; j < 32; ++j) {
                     const int co = n0 + c0 + j;
                     if (co < a.Cout)
-                        a.out[(((long long)n_img * a.Cout + co) * a.H + y) * a.W + x] = __uint_as_float(v[j]) + (a.bias ? a.bias[co] : 0.0f);
+                        a.out[(((long long)n_pix * a.Cout + co) * a.H + y) * a.W + x] = __uint_as_float(v[j]) + (a.bias ? a.bias[co] : 0.0f);
                 }
             }
         }
@@ -172,6 +204,7 @@ struct WgradArgs {
     int H, W, Cout, Cin_p;
     int KW, taps, dil_h, dil_w, pad_h, pad_w;
     int TWb, THb, tiles_x, tiles_y, tiles_total, tiles_per_split;
+    int im2col;             // 1: flat 128-pixel K tiles (dY: 2-D flat boxes, X: im2col-mode loads); 0: patches
     int nterms;
     int BN;                 // ci tile (multiple of KC, <= 256)
     int ci_tiles;
@@ -187,6 +220,7 @@ template <int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
                   const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1, const WgradArgs a) {
+    pdl_trigger();
     constexpr int KC = (KIND == 0) ? 64 : 32;
     constexpr int KSTEP_ROWS = (KIND == 0) ? 16 : 8;      // pixels per MMA (UMMA_K)
     constexpr int A_BOXES = BM / KC;                       // dY boxes per stage (128 output channels)
@@ -216,6 +250,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < n_iters; ++i) {
@@ -223,16 +258,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constan
             const uint32_t ph = (i / WSTAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             const int t = t0 + i / a.nterms, term = i % a.nterms;
-            const int n_img = t / tiles_per_img, trem = t % tiles_per_img;
-            const int y0 = (trem / a.tiles_x) * a.THb, x0 = (trem % a.tiles_x) * a.TWb;
             uint8_t* base = smem + (size_t)s * stage_bytes;
             mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
             const CUtensorMap* mg = (term == 1) ? &tmG1 : &tmG0;   // (G_hi,X_hi) (G_lo,X_hi) (G_hi,X_lo)
             const CUtensorMap* mx = (term == 2) ? &tmX1 : &tmX0;
-            for (int j = 0; j < A_BOXES; ++j) tma_load_4d(base + j * A_BYTES, mg, &full_bar[s], co0 + j * KC, x0, y0, n_img);
-            for (int j = 0; j < b_boxes; ++j)
-                tma_load_4d(base + (A_BOXES + j) * A_BYTES, mx, &full_bar[s], ci0 + j * KC,
-                            x0 + kw * a.dil_w - a.pad_w, y0 + kh * a.dil_h - a.pad_h, n_img);
+            if (a.im2col) {
+                const long long m0 = (long long)t * BM;
+                const int hw = a.H * a.W;
+                const int n_img = (int)(m0 / hw), rem = (int)(m0 - (long long)n_img * hw);
+                const int y0 = rem / a.W, x0 = rem - y0 * a.W;
+                for (int j = 0; j < A_BOXES; ++j) tma_load_2d(base + j * A_BYTES, mg, &full_bar[s], co0 + j * KC, (int)m0);
+                for (int j = 0; j < b_boxes; ++j)
+                    tma_load_im2col_4d(base + (A_BOXES + j) * A_BYTES, mx, &full_bar[s], ci0 + j * KC, x0 - a.pad_w, y0 - a.pad_h, n_img,
+                                       (uint16_t)(kw * a.dil_w), (uint16_t)(kh * a.dil_h));
+            } else {
+                const int n_img = t / tiles_per_img, trem = t % tiles_per_img;
+                const int y0 = (trem / a.tiles_x) * a.THb, x0 = (trem % a.tiles_x) * a.TWb;
+                for (int j = 0; j < A_BOXES; ++j) tma_load_4d(base + j * A_BYTES, mg, &full_bar[s], co0 + j * KC, x0, y0, n_img);
+                for (int j = 0; j < b_boxes; ++j)
+                    tma_load_4d(base + (A_BOXES + j) * A_BYTES, mx, &full_bar[s], ci0 + j * KC,
+                                x0 + kw * a.dil_w - a.pad_w, y0 + kh * a.dil_h - a.pad_h, n_img);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         const uint32_t idesc = instr_desc(KIND == 0 ? 1 : 2, 1, 1, BM, a.BN);
@@ -309,6 +355,58 @@ int make_act_map(CUtensorMap* m, const void* base, int kind, int Cp, int W, int 
     return 0;
 }
 
+PFN_cuTensorMapEncodeIm2col_v12000 get_encode_im2col() {
+    static PFN_cuTensorMapEncodeIm2col_v12000 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_cuTensorMapEncodeIm2col_v12000)p;
+    }
+    return fn;
+}
+
+bool use_im2col() {
+    static const bool on = [] { const char* e = getenv("PV2_CONV_PATCH"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+// NHWC activation map in im2col mode: dims (C, W, H, N); the base pixel walks the W x H bounding box whose lower corner is
+// (-pad_w, -pad_h) and whose upper corner is pulled in by (K-1)*dil - pad = pad ("same" convolution), KC channels per pixel,
+// 128 pixels per load; the per-tap displacement (kw*dil_w, kh*dil_h) is given to each load instruction.
+int make_im2col_map(CUtensorMap* m, const void* base, int kind, int Cp, int W, int H, int N, int pad_w, int pad_h, bool atom32 = false) {
+    auto enc = get_encode_im2col();
+    PV2_CHECK(enc != nullptr, "cuTensorMapEncodeIm2col not available from the driver");
+    PV2_CHECK(pad_w <= 127 && pad_h <= 127, "im2col map: padding %dx%d exceeds the 8-bit corner range", pad_h, pad_w);
+    const size_t es = kind == 0 ? 2 : 4;
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cp * es, (cuuint64_t)W * Cp * es, (cuuint64_t)H * W * Cp * es};
+    int lower[2] = {-pad_w, -pad_h}, upper[2] = {-pad_w, -pad_h};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims,
+                     strides, lower, upper, (cuuint32_t)(kind == 0 ? 64 : 32), (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PV2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col(C=%d W=%d H=%d N=%d pad %dx%d) failed: %d", Cp, W, H, N, pad_h, pad_w, (int)r);
+    return 0;
+}
+
+// flat [M][Cp] map (wgrad's dY operand with flat pixel tiles): dims (Cp, M), box (KC, 128)
+int make_flat_map(CUtensorMap* m, const void* base, int kind, int Cp, long long M, bool atom32 = false) {
+    auto enc = get_encode();
+    PV2_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    const size_t es = kind == 0 ? 2 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)Cp, (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)Cp * es};
+    cuuint32_t box[2] = {(cuuint32_t)(kind == 0 ? 64 : 32), (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PV2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(flat C=%d M=%lld) failed: %d", Cp, M, (int)r);
+    return 0;
+}
+
 // weight map: dims (Cin_p, taps, Cout), box (KC, 1, BN)
 int make_w_map(CUtensorMap* m, const void* base, int kind, int Cin_p, int taps, int Cout, int BN) {
     auto enc = get_encode();
@@ -332,6 +430,20 @@ void pick_patch(int W, int* TWb, int* THb) {
     *THb = BM / tw;
 }
 
+// A 1x1 convolution has no spatial structure: its pixels are one flat GEMM M dimension, so the 128-row tiles are taken
+// from the flattened [N*H*W] axis (every MMA row is a real pixel) instead of per-image TWb x THb patches.
+void flatten_1x1(int KH, int KW, int* N, int* H, int* W) {
+    if (KH == 1 && KW == 1) { *W = *N * *H * *W; *H = 1; *N = 1; }
+}
+
+int m_tiles_of(int N, int H, int W, int KH, int KW, bool flatten_ok) {
+    if (use_im2col()) return (int)(((long long)N * H * W + BM - 1) / BM);
+    if (flatten_ok) flatten_1x1(KH, KW, &N, &H, &W);
+    int TWb, THb;
+    pick_patch(W, &TWb, &THb);
+    return N * ((W + TWb - 1) / TWb) * ((H + THb - 1) / THb);
+}
+
 uint32_t pow2_cols(int n) {
     uint32_t c = 32;
     while ((int)c < n) c <<= 1;
@@ -353,10 +465,8 @@ int common_checks(const char* who, int kind, int nterms, int N, int H, int W, in
 using namespace pv2;
 
 extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
-    int TWb, THb;
-    pick_patch(W, &TWb, &THb);
     const int KC = kind == PV2_BF16 ? 64 : 32;
-    const int m_tiles = N * ((W + TWb - 1) / TWb) * ((H + THb - 1) / THb);
+    const int m_tiles = m_tiles_of(N, H, W, KH, KW, true);
     const int BN = Cout >= 256 ? 256 : ((Cout + 15) / 16) * 16;
     const int n_tiles = (Cout + BN - 1) / BN;
     const int iters = nterms * KH * KW * ((Cin_p + KC - 1) / KC);
@@ -375,6 +485,8 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     PV2_CHECK(out_mode == 0 || out_mode == 1, "conv_fwd: bad out_mode %d", out_mode);
     PV2_CHECK(out_mode == 1 || (ldo % 4 == 0 && ldo >= Cout), "conv_fwd: ldo=%d must be a multiple of 4 and >= Cout=%d", ldo, Cout);
     PV2_CHECK(out_mode == 0 || splits == 1, "conv_fwd: split-K needs the raw output mode");
+    const bool im2col = use_im2col();
+    if (out_mode == 0 && !im2col) flatten_1x1(KH, KW, &N, &H, &W);
     const int k = kind == PV2_BF16 ? 0 : 1, KC = k == 0 ? 64 : 32;
     const size_t es = k == 0 ? 2 : 4;
     ConvArgs a = {};
@@ -383,6 +495,8 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     a.pad_h = dil_h * (KH - 1) / 2; a.pad_w = dil_w * (KW - 1) / 2;
     pick_patch(W, &a.TWb, &a.THb);
     a.tiles_x = (W + a.TWb - 1) / a.TWb; a.tiles_y = (H + a.THb - 1) / a.THb;
+    a.im2col = im2col ? 1 : 0;
+    a.M = (long long)N * H * W;
     a.kc_per_tap = (Cin_p + KC - 1) / KC;
     a.iters_total = nterms * a.taps * a.kc_per_tap;
     PV2_CHECK(splits >= 1 && splits <= a.iters_total, "conv_fwd: splits=%d out of range (K iterations %d)", splits, a.iters_total);
@@ -393,35 +507,34 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     a.out_mode = out_mode; a.out = out; a.ldo = ldo; a.bias = bias;
     a.split_stride = (long long)N * H * W * ldo;
     CUtensorMap mA0, mA1, mB0, mB1;
-    if (int e = make_act_map(&mA0, x, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
+    if (int e = im2col ? make_im2col_map(&mA0, x, k, Cin_p, W, H, N, a.pad_w, a.pad_h) : make_act_map(&mA0, x, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
     if (int e = make_w_map(&mB0, w_op, k, Cin_p, a.taps, Cout, a.BN)) return e;
     mA1 = mA0; mB1 = mB0;
     if (nterms == 3) {
-        if (int e = make_act_map(&mA1, (const uint8_t*)x + x_plane_stride * es, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
+        const void* x1 = (const uint8_t*)x + x_plane_stride * es;
+        if (int e = im2col ? make_im2col_map(&mA1, x1, k, Cin_p, W, H, N, a.pad_w, a.pad_h) : make_act_map(&mA1, x1, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
         if (int e = make_w_map(&mB1, (const uint8_t*)w_op + w_plane_stride * es, k, Cin_p, a.taps, Cout, a.BN)) return e;
     }
     const size_t smem = (size_t)STAGES * (A_BYTES + (size_t)a.BN * ROW_BYTES) + 1024;
-    dim3 grid(N * a.tiles_x * a.tiles_y, (Cout + a.BN - 1) / a.BN, splits);
+    dim3 grid(im2col ? (unsigned)((a.M + BM - 1) / BM) : (unsigned)(N * a.tiles_x * a.tiles_y), (Cout + a.BN - 1) / a.BN, splits);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce;
     if (k == 0) {
         ce = cudaFuncSetAttribute(conv_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
-        conv_fwd_kernel<0><<<grid, THREADS, smem, st>>>(mA0, mA1, mB0, mB1, a);
+        pv2::launch(conv_fwd_kernel<0>, grid, THREADS, smem, st, mA0, mA1, mB0, mB1, a);
     } else {
         ce = cudaFuncSetAttribute(conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
-        conv_fwd_kernel<1><<<grid, THREADS, smem, st>>>(mA0, mA1, mB0, mB1, a);
+        pv2::launch(conv_fwd_kernel<1>, grid, THREADS, smem, st, mA0, mA1, mB0, mB1, a);
     }
     PV2_LAUNCH_CHECK("conv_fwd");
     return 0;
 }
 
 extern "C" int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind) {
-    int TWb, THb;
-    pick_patch(W, &TWb, &THb);
     const int KC = kind == PV2_BF16 ? 64 : 32;
-    const int tiles = N * ((W + TWb - 1) / TWb) * ((H + THb - 1) / THb);
+    const int tiles = m_tiles_of(N, H, W, KH, KW, true);
     const int cin_r = ((Cin_p + KC - 1) / KC) * KC;
     const int bn_max = kind == PV2_BF16 ? 128 : 64;
     const int BN = cin_r >= bn_max ? bn_max : cin_r;
@@ -438,15 +551,19 @@ extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const v
     if (int e = common_checks("conv_wgrad", kind, nterms, N, H, W, Cin_p, Cout, KH, KW)) return e;
     PV2_CHECK(dy && x && out, "conv_wgrad: null pointer");
     PV2_CHECK(Cout_p % (kind == PV2_BF16 ? 8 : 4) == 0 && Cout_p >= Cout, "conv_wgrad: bad padded Cout %d", Cout_p);
+    const bool im2col = use_im2col();
+    if (!im2col) flatten_1x1(KH, KW, &N, &H, &W);
     const int k = kind == PV2_BF16 ? 0 : 1, KC = k == 0 ? 64 : 32;
     const size_t es = k == 0 ? 2 : 4;
     WgradArgs a = {};
+    a.im2col = im2col ? 1 : 0;
     a.H = H; a.W = W; a.Cout = Cout; a.Cin_p = Cin_p;
     a.KW = KW; a.taps = KH * KW; a.dil_h = dil_h; a.dil_w = dil_w;
     a.pad_h = dil_h * (KH - 1) / 2; a.pad_w = dil_w * (KW - 1) / 2;
     pick_patch(W, &a.TWb, &a.THb);
     a.tiles_x = (W + a.TWb - 1) / a.TWb; a.tiles_y = (H + a.THb - 1) / a.THb;
-    a.tiles_total = N * a.tiles_x * a.tiles_y;
+    const long long Mtot = (long long)N * H * W;
+    a.tiles_total = im2col ? (int)((Mtot + BM - 1) / BM) : N * a.tiles_x * a.tiles_y;
     PV2_CHECK(splits >= 1 && splits <= a.tiles_total, "conv_wgrad: splits=%d out of range (pixel tiles %d)", splits, a.tiles_total);
     a.tiles_per_split = (a.tiles_total + splits - 1) / splits;
     PV2_CHECK((long long)a.tiles_per_split * (splits - 1) < a.tiles_total, "conv_wgrad: splits=%d leaves an empty split", splits);
@@ -460,12 +577,14 @@ extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const v
     a.split_stride = (long long)Cout * a.taps * Cin_p;
     CUtensorMap mG0, mG1, mX0, mX1;
     const bool a32 = (k == 1);   // tf32 MN-major operands: 32-byte-atom swizzle
-    if (int e = make_act_map(&mG0, dy, k, Cout_p, W, H, N, a.TWb, a.THb, a32)) return e;
-    if (int e = make_act_map(&mX0, x, k, Cin_p, W, H, N, a.TWb, a.THb, a32)) return e;
+    if (int e = im2col ? make_flat_map(&mG0, dy, k, Cout_p, Mtot, a32) : make_act_map(&mG0, dy, k, Cout_p, W, H, N, a.TWb, a.THb, a32)) return e;
+    if (int e = im2col ? make_im2col_map(&mX0, x, k, Cin_p, W, H, N, a.pad_w, a.pad_h, a32) : make_act_map(&mX0, x, k, Cin_p, W, H, N, a.TWb, a.THb, a32)) return e;
     mG1 = mG0; mX1 = mX0;
     if (nterms == 3) {
-        if (int e = make_act_map(&mG1, (const uint8_t*)dy + dy_plane_stride * es, k, Cout_p, W, H, N, a.TWb, a.THb, a32)) return e;
-        if (int e = make_act_map(&mX1, (const uint8_t*)x + x_plane_stride * es, k, Cin_p, W, H, N, a.TWb, a.THb, a32)) return e;
+        const void* dy1 = (const uint8_t*)dy + dy_plane_stride * es;
+        const void* x1 = (const uint8_t*)x + x_plane_stride * es;
+        if (int e = im2col ? make_flat_map(&mG1, dy1, k, Cout_p, Mtot, a32) : make_act_map(&mG1, dy1, k, Cout_p, W, H, N, a.TWb, a.THb, a32)) return e;
+        if (int e = im2col ? make_im2col_map(&mX1, x1, k, Cin_p, W, H, N, a.pad_w, a.pad_h, a32) : make_act_map(&mX1, x1, k, Cin_p, W, H, N, a.TWb, a.THb, a32)) return e;
     }
     const size_t smem = (size_t)(k == 0 ? WgradCfg<0>::STAGES_ : WgradCfg<1>::STAGES_) * ((BM / KC) + (a.BN / KC)) * A_BYTES + 1024;
     PV2_CHECK(smem <= 227 * 1024, "conv_wgrad: stage too large (%zu B)", smem);
@@ -475,11 +594,11 @@ extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const v
     if (k == 0) {
         ce = cudaFuncSetAttribute(conv_wgrad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         PV2_CHECK(ce == cudaSuccess, "conv_wgrad: smem attribute: %s", cudaGetErrorString(ce));
-        conv_wgrad_kernel<0><<<grid, THREADS, smem, st>>>(mG0, mG1, mX0, mX1, a);
+        pv2::launch(conv_wgrad_kernel<0>, grid, THREADS, smem, st, mG0, mG1, mX0, mX1, a);
     } else {
         ce = cudaFuncSetAttribute(conv_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         PV2_CHECK(ce == cudaSuccess, "conv_wgrad: smem attribute: %s", cudaGetErrorString(ce));
-        conv_wgrad_kernel<1><<<grid, THREADS, smem, st>>>(mG0, mG1, mX0, mX1, a);
+        pv2::launch(conv_wgrad_kernel<1>, grid, THREADS, smem, st, mG0, mG1, mX0, mX1, a);
     }
     PV2_LAUNCH_CHECK("conv_wgrad");
     return 0;

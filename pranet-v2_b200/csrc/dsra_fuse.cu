@@ -39,6 +39,7 @@ __device__ __forceinline__ Sampler make_sampler(int y, int x, int dh, int dw, fl
 __global__ void dsra_fuse_fwd_kernel(const float* __restrict__ fg, const float* __restrict__ dfg_map,
                                      const float* __restrict__ dbg_map, float* __restrict__ out, int B, int C,
                                      int h, int w, int dh, int dw, float rh, float rw, int use_softmax) {
+    pv2::pdl_prologue();
     const int hw = h * w, idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * hw) return;
     const int b = idx / hw, pix = idx - b * hw, y = pix / w, x = pix - y * w;
@@ -71,6 +72,7 @@ __global__ void dsra_fuse_bwd_kernel(const float* __restrict__ dout, const float
                                      const float* __restrict__ dfg_map, const float* __restrict__ dbg_map,
                                      float* __restrict__ dfg, float* __restrict__ dd, int B, int C, int h, int w,
                                      int dh, int dw, float rh, float rw, int use_softmax) {
+    pv2::pdl_prologue();
     const int hw = h * w, idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * hw) return;
     const int b = idx / hw, pix = idx - b * hw, y = pix / w, x = pix - y * w;
@@ -115,6 +117,7 @@ __global__ void dsra_fuse_bwd_kernel(const float* __restrict__ dout, const float
 template <typename T>
 __global__ void ra_v1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ crop, T* __restrict__ y,
                                  int C, int hw, size_t total_vec) {
+    pv2::pdl_prologue();
     // hw % 4 == 0: one thread = 4 consecutive pixels of one (b,c) plane
     const int vec_per_plane = hw >> 2;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
@@ -134,6 +137,7 @@ __global__ void ra_v1_fwd_kernel(const T* __restrict__ x, const float* __restric
 template <typename T>
 __global__ void ra_v1_fwd_scalar_kernel(const T* __restrict__ x, const float* __restrict__ crop, T* __restrict__ y,
                                         int C, int hw, size_t total) {
+    pv2::pdl_prologue();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t plane = i / hw;
         const int p = (int)(i - plane * hw);
@@ -147,6 +151,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 ra_v1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ crop,
                  T* __restrict__ dx, float* __restrict__ dcrop, int C, int hw) {
+    pv2::pdl_prologue();
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5, b = blockIdx.y;
     const int p = blockIdx.x * 32 + lane;
@@ -188,7 +193,7 @@ extern "C" int pv2_dsra_fuse_fwd(const float* fg, const float* deep_fg, const fl
     if (int e = fuse_check(B, C, h, w, dh, dw, "dsra_fuse_fwd")) return e;
     PV2_CHECK(fg && deep_fg && deep_bg && out, "dsra_fuse_fwd: null pointer");
     const int n = B * h * w, threads = 128;
-    dsra_fuse_fwd_kernel<<<(n + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+    pv2::launch(dsra_fuse_fwd_kernel, (n + threads - 1) / threads, threads, 0, (cudaStream_t)stream, 
         fg, deep_fg, deep_bg, out, B, C, h, w, dh, dw, rh, rw, use_softmax);
     PV2_LAUNCH_CHECK("dsra_fuse_fwd");
     return 0;
@@ -200,7 +205,7 @@ extern "C" int pv2_dsra_fuse_bwd(const float* dout, const float* fg, const float
     if (int e = fuse_check(B, C, h, w, dh, dw, "dsra_fuse_bwd")) return e;
     PV2_CHECK(dout && fg && deep_fg && deep_bg && dfg && dd, "dsra_fuse_bwd: null pointer");
     const int n = B * h * w, threads = 128;
-    dsra_fuse_bwd_kernel<<<(n + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(
+    pv2::launch(dsra_fuse_bwd_kernel, (n + threads - 1) / threads, threads, 0, (cudaStream_t)stream, 
         dout, fg, deep_fg, deep_bg, dfg, dd, B, C, h, w, dh, dw, rh, rw, use_softmax);
     PV2_LAUNCH_CHECK("dsra_fuse_bwd");
     return 0;
@@ -217,13 +222,13 @@ extern "C" int pv2_ra_v1_scale_fwd(const void* x, const float* crop, void* y, in
         const size_t nv = total / 4;
         int blocks = (int)((nv + threads - 1) / threads);
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-        if (dtype == PV2_F32) ra_v1_fwd_kernel<float><<<blocks, threads, 0, st>>>((const float*)x, crop, (float*)y, C, hw, nv);
-        else ra_v1_fwd_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, nv);
+        if (dtype == PV2_F32) pv2::launch(ra_v1_fwd_kernel<float>, blocks, threads, 0, st, (const float*)x, crop, (float*)y, C, hw, nv);
+        else pv2::launch(ra_v1_fwd_kernel<__nv_bfloat16>, blocks, threads, 0, st, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, nv);
     } else {
         int blocks = (int)((total + threads - 1) / threads);
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-        if (dtype == PV2_F32) ra_v1_fwd_scalar_kernel<float><<<blocks, threads, 0, st>>>((const float*)x, crop, (float*)y, C, hw, total);
-        else ra_v1_fwd_scalar_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, total);
+        if (dtype == PV2_F32) pv2::launch(ra_v1_fwd_scalar_kernel<float>, blocks, threads, 0, st, (const float*)x, crop, (float*)y, C, hw, total);
+        else pv2::launch(ra_v1_fwd_scalar_kernel<__nv_bfloat16>, blocks, threads, 0, st, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, total);
     }
     PV2_LAUNCH_CHECK("ra_v1_scale_fwd");
     return 0;
@@ -236,8 +241,8 @@ extern "C" int pv2_ra_v1_scale_bwd(const void* dy, const void* x, const float* c
     PV2_CHECK(dtype == PV2_F32 || dtype == PV2_BF16, "ra_v1_scale_bwd: bad dtype %d", dtype);
     dim3 grid((hw + 31) / 32, B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == PV2_F32) ra_v1_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)x, crop, (float*)dx, dcrop, C, hw);
-    else ra_v1_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)dx, dcrop, C, hw);
+    if (dtype == PV2_F32) pv2::launch(ra_v1_bwd_kernel<float>, grid, 256, 0, st, (const float*)dy, (const float*)x, crop, (float*)dx, dcrop, C, hw);
+    else pv2::launch(ra_v1_bwd_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)dx, dcrop, C, hw);
     PV2_LAUNCH_CHECK("ra_v1_scale_bwd");
     return 0;
 }

@@ -51,6 +51,7 @@ __device__ __forceinline__ float load_op(const void* base, long long plane_strid
 template <int KIND>
 __global__ void weight_pack_kernel(const float* __restrict__ w, void* out, long long plane_stride, int nplanes,
                                    int Cout, int Cin, int KH, int KW, int mode, int i_ld, int i_off, int o_off) {
+    pv2::pdl_prologue();
     const long long total = (long long)Cout * Cin * KH * KW;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int kw = (int)(e % KW);
@@ -68,6 +69,7 @@ __global__ void weight_pack_kernel(const float* __restrict__ w, void* out, long 
 // wgrad partials [split][Cout_total][taps][Cin_p] -> OIHW fp32 gradient of one conv (rows co_off .. co_off+Cout)
 __global__ void wgrad_unpack_kernel(const float* __restrict__ part, long long split_stride, int splits, float* __restrict__ dw,
                                     int Cout, int Cin, int KH, int KW, int Cin_p, int co_off) {
+    pv2::pdl_prologue();
     const long long total = (long long)Cout * Cin * KH * KW;
     const int taps = KH * KW;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -94,6 +96,7 @@ struct UnpackBatch { pv2_unpack_desc d[UNPACK_BATCH]; };
 template <int KIND>
 __global__ void __launch_bounds__(256)
 weight_pack_multi_kernel(const __grid_constant__ PackBatch b, int n, long long base, long long total, int nplanes) {
+    pv2::pdl_prologue();
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = n - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.d[mid].start - base <= e) lo = mid; else hi = mid - 1; }
@@ -114,6 +117,7 @@ weight_pack_multi_kernel(const __grid_constant__ PackBatch b, int n, long long b
 
 __global__ void __launch_bounds__(256)
 wgrad_unpack_multi_kernel(const __grid_constant__ UnpackBatch b, int n, long long base, long long total) {
+    pv2::pdl_prologue();
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = n - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.d[mid].start - base <= e) lo = mid; else hi = mid - 1; }
@@ -136,6 +140,7 @@ wgrad_unpack_multi_kernel(const __grid_constant__ UnpackBatch b, int n, long lon
 template <typename TIN, int KIND>
 __global__ void __launch_bounds__(256)
 pack_nchw_kernel(const TIN* __restrict__ x, void* out, long long plane_stride, int nplanes, int C, int HW, int ld, int c_off) {
+    pv2::pdl_prologue();
     __shared__ float tile[32][33];
     const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -167,6 +172,7 @@ __device__ __forceinline__ float slab_sum(const Slabs& s, long long row, int c) 
 template <typename TOUT>
 __global__ void __launch_bounds__(256)
 unpack_to_nchw_kernel(const Slabs g, TOUT* __restrict__ dx, int C, int HW) {
+    pv2::pdl_prologue();
     __shared__ float tile[32][33];
     const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -213,6 +219,7 @@ __device__ __forceinline__ void chan_combine(float& n, float& mu, float& M2, flo
 __global__ void __launch_bounds__(256)
 bn_stats_partial_kernel(float* __restrict__ y, long long slab_stride, int nslabs, long long M, int C, int ld, int rows_pb,
                         float* __restrict__ part /* [row_blocks][C][3] */) {
+    pv2::pdl_prologue();
     __shared__ float sh[8][32][3];
     const int c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
     const long long r0 = (long long)blockIdx.x * rows_pb, r1 = min(M, r0 + rows_pb);
@@ -250,6 +257,7 @@ bn_stats_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, 
                          float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
                          float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ scale,
                          float* __restrict__ shift) {
+    pv2::pdl_prologue();
     const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c == 0 && lane == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
@@ -289,6 +297,7 @@ bn_stats_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, 
 __global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+    pv2::pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float s = (gamma ? gamma[c] : 1.0f) * rsqrtf(rv[c] + eps);
@@ -334,6 +343,7 @@ __device__ __forceinline__ float apply_value(const ApplyArgs& a, long long r, in
 template <int KIND>
 __global__ void __launch_bounds__(256)
 act_apply_kernel(const ApplyArgs a) {
+    pv2::pdl_prologue();
     const long long total = a.M * a.C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long r = e / a.C;
@@ -399,6 +409,7 @@ __device__ __forceinline__ void bwd_da(const BwdArgs& b, long long r, int c, flo
 template <int KIND>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const BwdArgs b) {
+    pv2::pdl_prologue();
     __shared__ float sh[8][32][4];
     const int C = b.f.C;
     const int c = blockIdx.y * 32 + (threadIdx.x & 31), ty = threadIdx.x >> 5;
@@ -431,6 +442,7 @@ __global__ void __launch_bounds__(128)
 bn_bwd_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, float* __restrict__ sums,
                        float* __restrict__ dgamma1, float* __restrict__ dbeta1, float* __restrict__ dgamma2,
                        float* __restrict__ dbeta2) {
+    pv2::pdl_prologue();
     const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= C) return;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
@@ -451,6 +463,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, fl
 template <int KIND>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(const BwdArgs b) {
+    pv2::pdl_prologue();
     const ApplyArgs& a = b.f;
     const long long total = a.M * a.C;
     const float invn = 1.0f / (float)a.M;
@@ -479,6 +492,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256)
 up2_nhwc_fwd_kernel(const void* in, long long in_plane, int in_planes, int in_ld, int in_off, void* out, long long out_plane,
                     int out_planes, int out_ld, int out_off, int N, int H, int W, int C, float rh, float rw) {
+    pv2::pdl_prologue();
     const int OH = 2 * H, OW = 2 * W;
     const long long total = (long long)N * OH * OW * C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -505,6 +519,7 @@ __device__ __forceinline__ float ac_weight(int o, int i, int in_size, float rati
 
 __global__ void __launch_bounds__(256)
 up2_nhwc_bwd_kernel(const Slabs g, float* __restrict__ din, int din_ld, int N, int H, int W, int C, float rh, float rw) {
+    pv2::pdl_prologue();
     const int OH = 2 * H, OW = 2 * W;
     const long long total = (long long)N * H * W * C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -560,8 +575,8 @@ extern "C" int pv2_weight_pack(const float* w, void* out, long long plane_stride
     KIND_CHECK("weight_pack");
     PV2_CHECK(w && out && Cout > 0 && Cin > 0 && KH > 0 && KW > 0, "weight_pack: bad arguments");
     const long long total = (long long)Cout * Cin * KH * KW;
-    if (kind == PV2_BF16) weight_pack_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(w, out, plane_stride, nplanes, Cout, Cin, KH, KW, mode, i_ld, i_off, o_off);
-    else weight_pack_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(w, out, plane_stride, nplanes, Cout, Cin, KH, KW, mode, i_ld, i_off, o_off);
+    if (kind == PV2_BF16) pv2::launch(weight_pack_kernel<0>, grid_for(total), 256, 0, (cudaStream_t)stream, w, out, plane_stride, nplanes, Cout, Cin, KH, KW, mode, i_ld, i_off, o_off);
+    else pv2::launch(weight_pack_kernel<1>, grid_for(total), 256, 0, (cudaStream_t)stream, w, out, plane_stride, nplanes, Cout, Cin, KH, KW, mode, i_ld, i_off, o_off);
     PV2_LAUNCH_CHECK("weight_pack");
     return 0;
 }
@@ -570,7 +585,7 @@ extern "C" int pv2_wgrad_unpack(const float* part, long long split_stride, int s
                                 int Cin_p, int co_off, void* stream) {
     PV2_CHECK(part && dw && splits >= 1, "wgrad_unpack: bad arguments");
     const long long total = (long long)Cout * Cin * KH * KW;
-    wgrad_unpack_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(part, split_stride, splits, dw, Cout, Cin, KH, KW, Cin_p, co_off);
+    pv2::launch(wgrad_unpack_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, part, split_stride, splits, dw, Cout, Cin, KH, KW, Cin_p, co_off);
     PV2_LAUNCH_CHECK("wgrad_unpack");
     return 0;
 }
@@ -588,8 +603,8 @@ extern "C" int pv2_weight_pack_multi(const pv2_pack_desc* descs, int n, int npla
             total += (long long)b.d[i].Cout * b.d[i].Cin * b.d[i].KH * b.d[i].KW;
         }
         const long long base = b.d[0].start;
-        if (kind == PV2_BF16) weight_pack_multi_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(b, nb, base, total, nplanes);
-        else weight_pack_multi_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(b, nb, base, total, nplanes);
+        if (kind == PV2_BF16) pv2::launch(weight_pack_multi_kernel<0>, grid_for(total), 256, 0, (cudaStream_t)stream, b, nb, base, total, nplanes);
+        else pv2::launch(weight_pack_multi_kernel<1>, grid_for(total), 256, 0, (cudaStream_t)stream, b, nb, base, total, nplanes);
         PV2_LAUNCH_CHECK("weight_pack_multi");
     }
     return 0;
@@ -606,7 +621,7 @@ extern "C" int pv2_wgrad_unpack_multi(const pv2_unpack_desc* descs, int n, void*
             PV2_CHECK(b.d[i].part && b.d[i].dw, "wgrad_unpack_multi: null pointer in descriptor %d", i0 + i);
             total += (long long)b.d[i].Cout * b.d[i].Cin * b.d[i].KH * b.d[i].KW;
         }
-        wgrad_unpack_multi_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(b, nb, b.d[0].start, total);
+        pv2::launch(wgrad_unpack_multi_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, b, nb, b.d[0].start, total);
         PV2_LAUNCH_CHECK("wgrad_unpack_multi");
     }
     return 0;
@@ -619,10 +634,10 @@ extern "C" int pv2_pack_nchw(const void* x, int x_dtype, void* out, long long pl
     PV2_CHECK(x_dtype == PV2_F32 || x_dtype == PV2_BF16, "pack_nchw: bad input dtype %d", x_dtype);
     dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_dtype == PV2_F32 && kind == PV2_BF16) pack_nchw_kernel<float, 0><<<grid, 256, 0, st>>>((const float*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
-    else if (x_dtype == PV2_F32) pack_nchw_kernel<float, 1><<<grid, 256, 0, st>>>((const float*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
-    else if (kind == PV2_BF16) pack_nchw_kernel<__nv_bfloat16, 0><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
-    else pack_nchw_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    if (x_dtype == PV2_F32 && kind == PV2_BF16) pv2::launch(pack_nchw_kernel<float, 0>, grid, 256, 0, st, (const float*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    else if (x_dtype == PV2_F32) pv2::launch(pack_nchw_kernel<float, 1>, grid, 256, 0, st, (const float*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    else if (kind == PV2_BF16) pv2::launch(pack_nchw_kernel<__nv_bfloat16, 0>, grid, 256, 0, st, (const __nv_bfloat16*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
+    else pv2::launch(pack_nchw_kernel<__nv_bfloat16, 1>, grid, 256, 0, st, (const __nv_bfloat16*)x, out, plane_stride, nplanes, C, HW, ld, c_off);
     PV2_LAUNCH_CHECK("pack_nchw");
     return 0;
 }
@@ -630,6 +645,7 @@ extern "C" int pv2_pack_nchw(const void* x, int x_dtype, void* out, long long pl
 template <typename TOUT>
 __global__ void __launch_bounds__(256)
 slabs_to_nhwc_kernel(const pv2::Slabs g, TOUT* __restrict__ dx, long long M, int C) {
+    pv2::pdl_prologue();
     const long long total = M * C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long r = e / C;
@@ -644,8 +660,8 @@ extern "C" int pv2_unpack_to_nchw(const float* const* slabs, const int* lds, con
         if (int e = fill_slabs(&s2, slabs, lds, offs, nslabs, "unpack_to_nchw")) return e;
         PV2_CHECK(dx && N > 0 && C > 0 && HW > 0, "unpack_to_nchw: bad arguments");
         const long long M = (long long)N * HW;
-        if (dx_dtype == PV2_F32) slabs_to_nhwc_kernel<float><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>(s2, (float*)dx, M, C);
-        else if (dx_dtype == PV2_BF16) slabs_to_nhwc_kernel<__nv_bfloat16><<<grid_for(M * C), 256, 0, (cudaStream_t)stream>>>(s2, (__nv_bfloat16*)dx, M, C);
+        if (dx_dtype == PV2_F32) pv2::launch(slabs_to_nhwc_kernel<float>, grid_for(M * C), 256, 0, (cudaStream_t)stream, s2, (float*)dx, M, C);
+        else if (dx_dtype == PV2_BF16) pv2::launch(slabs_to_nhwc_kernel<__nv_bfloat16>, grid_for(M * C), 256, 0, (cudaStream_t)stream, s2, (__nv_bfloat16*)dx, M, C);
         else PV2_CHECK(false, "unpack_to_nchw: bad dtype %d", dx_dtype);
         PV2_LAUNCH_CHECK("slabs_to_nhwc");
         return 0;
@@ -655,8 +671,8 @@ extern "C" int pv2_unpack_to_nchw(const float* const* slabs, const int* lds, con
     PV2_CHECK(dx && N > 0 && C > 0 && HW > 0 && N <= 65535, "unpack_to_nchw: bad arguments");
     PV2_CHECK(dx_dtype == PV2_F32 || dx_dtype == PV2_BF16, "unpack_to_nchw: bad dtype %d", dx_dtype);
     dim3 grid((HW + 31) / 32, (C + 31) / 32, N);
-    if (dx_dtype == PV2_F32) unpack_to_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(s, (float*)dx, C, HW);
-    else unpack_to_nchw_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, (__nv_bfloat16*)dx, C, HW);
+    if (dx_dtype == PV2_F32) pv2::launch(unpack_to_nchw_kernel<float>, grid, 256, 0, (cudaStream_t)stream, s, (float*)dx, C, HW);
+    else pv2::launch(unpack_to_nchw_kernel<__nv_bfloat16>, grid, 256, 0, (cudaStream_t)stream, s, (__nv_bfloat16*)dx, C, HW);
     PV2_LAUNCH_CHECK("unpack_to_nchw");
     return 0;
 }
@@ -676,9 +692,9 @@ extern "C" int pv2_bn_stats(float* y, long long slab_stride, int nslabs, long lo
     const int rb = (int)((M + rows - 1) / rows);
     PV2_CHECK((C + 31) / 32 <= 65535, "bn_stats: too many channels");
     cudaStream_t st = (cudaStream_t)stream;
-    bn_stats_partial_kernel<<<dim3(rb, (C + 31) / 32), 256, 0, st>>>(y, slab_stride, nslabs, M, C, ld, rows, workspace);
+    pv2::launch(bn_stats_partial_kernel, dim3(rb, (C + 31) / 32), 256, 0, st, y, slab_stride, nslabs, M, C, ld, rows, workspace);
     PV2_LAUNCH_CHECK("bn_stats_partial");
-    bn_stats_finalize_kernel<<<(C + 3) / 4, 128, 0, st>>>(workspace, rb, C, gamma, beta, eps, momentum, running_mean, running_var,
+    pv2::launch(bn_stats_finalize_kernel, (C + 3) / 4, 128, 0, st, workspace, rb, C, gamma, beta, eps, momentum, running_mean, running_var,
                                                                num_batches_tracked, mean_out, invstd_out, scale, shift);
     PV2_LAUNCH_CHECK("bn_stats_finalize");
     return 0;
@@ -687,7 +703,7 @@ extern "C" int pv2_bn_stats(float* y, long long slab_stride, int nslabs, long lo
 extern "C" int pv2_bn_eval_affine(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                   float* scale, float* shift, void* stream) {
     PV2_CHECK(C > 0 && rm && rv && scale && shift, "bn_eval_affine: bad arguments");
-    bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, rm, rv, eps, scale, shift);
+    pv2::launch(bn_eval_affine_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, C, gamma, beta, rm, rv, eps, scale, shift);
     PV2_LAUNCH_CHECK("bn_eval_affine");
     return 0;
 }
@@ -719,8 +735,8 @@ extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long l
     PV2_CHECK(out != nullptr, "act_apply: null output");
     a.out = out; a.out_plane = out_plane; a.out_planes = out_planes; a.out_ld = out_ld; a.out_off = out_off; a.out_nchw = out_nchw;
     const long long total = M * C;
-    if (kind == PV2_BF16) act_apply_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(a);
-    else act_apply_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(a);
+    if (kind == PV2_BF16) pv2::launch(act_apply_kernel<0>, grid_for(total), 256, 0, (cudaStream_t)stream, a);
+    else pv2::launch(act_apply_kernel<1>, grid_for(total), 256, 0, (cudaStream_t)stream, a);
     PV2_LAUNCH_CHECK("act_apply");
     return 0;
 }
@@ -759,12 +775,12 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
     b.part = part; b.sums = sums;
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 rgrid(rb, (C + 31) / 32);
-    if (kind == PV2_BF16) bn_bwd_reduce_kernel<0><<<rgrid, 256, 0, st>>>(b); else bn_bwd_reduce_kernel<1><<<rgrid, 256, 0, st>>>(b);
+    if (kind == PV2_BF16) pv2::launch(bn_bwd_reduce_kernel<0>, rgrid, 256, 0, st, b); else pv2::launch(bn_bwd_reduce_kernel<1>, rgrid, 256, 0, st, b);
     PV2_LAUNCH_CHECK("bn_bwd_reduce");
-    bn_bwd_finalize_kernel<<<(C + 3) / 4, 128, 0, st>>>(part, rb, C, sums, dgamma1, dbeta1, dgamma2, dbeta2);
+    pv2::launch(bn_bwd_finalize_kernel, (C + 3) / 4, 128, 0, st, part, rb, C, sums, dgamma1, dbeta1, dgamma2, dbeta2);
     PV2_LAUNCH_CHECK("bn_bwd_finalize");
     const long long total = M * C;
-    if (kind == PV2_BF16) bn_bwd_dx_kernel<0><<<grid_for(total), 256, 0, st>>>(b); else bn_bwd_dx_kernel<1><<<grid_for(total), 256, 0, st>>>(b);
+    if (kind == PV2_BF16) pv2::launch(bn_bwd_dx_kernel<0>, grid_for(total), 256, 0, st, b); else pv2::launch(bn_bwd_dx_kernel<1>, grid_for(total), 256, 0, st, b);
     PV2_LAUNCH_CHECK("bn_bwd_dx");
     return 0;
 }
@@ -775,8 +791,8 @@ extern "C" int pv2_up2_nhwc_fwd(const void* in, long long in_plane, int in_plane
     PV2_CHECK(in && out && N > 0 && H > 0 && W > 0 && C > 0, "up2_nhwc_fwd: bad arguments");
     const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
     const long long total = (long long)N * 4 * H * W * C;
-    if (kind == PV2_BF16) up2_nhwc_fwd_kernel<0><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, in_plane, in_planes, in_ld, in_off, out, out_plane, out_planes, out_ld, out_off, N, H, W, C, rh, rw);
-    else up2_nhwc_fwd_kernel<1><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(in, in_plane, in_planes, in_ld, in_off, out, out_plane, out_planes, out_ld, out_off, N, H, W, C, rh, rw);
+    if (kind == PV2_BF16) pv2::launch(up2_nhwc_fwd_kernel<0>, grid_for(total), 256, 0, (cudaStream_t)stream, in, in_plane, in_planes, in_ld, in_off, out, out_plane, out_planes, out_ld, out_off, N, H, W, C, rh, rw);
+    else pv2::launch(up2_nhwc_fwd_kernel<1>, grid_for(total), 256, 0, (cudaStream_t)stream, in, in_plane, in_planes, in_ld, in_off, out, out_plane, out_planes, out_ld, out_off, N, H, W, C, rh, rw);
     PV2_LAUNCH_CHECK("up2_nhwc_fwd");
     return 0;
 }
@@ -787,7 +803,7 @@ extern "C" int pv2_up2_nhwc_bwd(const float* const* slabs, const int* lds, const
     if (int e = fill_slabs(&s, slabs, lds, offs, nslabs, "up2_nhwc_bwd")) return e;
     PV2_CHECK(din && N > 0 && H > 0 && W > 0 && C > 0, "up2_nhwc_bwd: bad arguments");
     const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
-    up2_nhwc_bwd_kernel<<<grid_for((long long)N * H * W * C), 256, 0, (cudaStream_t)stream>>>(s, din, din_ld, N, H, W, C, rh, rw);
+    pv2::launch(up2_nhwc_bwd_kernel, grid_for((long long)N * H * W * C), 256, 0, (cudaStream_t)stream, s, din, din_ld, N, H, W, C, rh, rw);
     PV2_LAUNCH_CHECK("up2_nhwc_bwd");
     return 0;
 }

@@ -41,6 +41,7 @@ template <int C>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mode, long long npix, int HW,
                    float* __restrict__ partials /* [grid][nsub*Row + C] */) {
+    pv2::pdl_prologue();
     constexpr int R = Row<C>::N;
     const int nsub = mode == 0 ? (1 << n) - 1 : n;
     extern __shared__ float sacc[];                     // [warps][nsub*R + C]
@@ -118,6 +119,7 @@ mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mo
 template <int C>
 __global__ void mc_loss_fold_kernel(const float* __restrict__ partials, int nrows, int nsub, long long npix,
                                     float lc_ce, float lc_dice, float lc_bce, float* __restrict__ totals, float* __restrict__ loss) {
+    pv2::pdl_prologue();
     constexpr int R = Row<C>::N;
     const int width = nsub * R + C;
     for (int i = threadIdx.x; i < width; i += blockDim.x) {
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(MC_THREADS)
 mc_loss_bwd_kernel(McPtrs p, const long long* __restrict__ labels, const float* __restrict__ grad_loss,
                    const float* __restrict__ totals, int n, int mode, long long npix, int HW,
                    float lc_ce, float lc_dice, float lc_bce) {
+    pv2::pdl_prologue();
     constexpr int R = Row<C>::N;
     const int nsub = mode == 0 ? (1 << n) - 1 : n;
     const long long pix = (long long)blockIdx.x * MC_THREADS + threadIdx.x;
@@ -262,12 +265,12 @@ int launch_all(bool backward, const McPtrs& p, const long long* labels, const fl
     float* partials = ws + ((width + 63) / 64) * 64;
     if (!backward) {
         const size_t smem = sizeof(float) * (MC_THREADS / 32) * width;
-        mc_loss_fwd_kernel<C><<<grid, MC_THREADS, smem, st>>>(p, labels, n, mode, npix, H * W, partials);
+        pv2::launch(mc_loss_fwd_kernel<C>, grid, MC_THREADS, smem, st, p, labels, n, mode, npix, H * W, partials);
         PV2_LAUNCH_CHECK("mc_loss_fwd");
-        mc_loss_fold_kernel<C><<<1, 256, 0, st>>>(partials, grid, nsub, npix, lc_ce, lc_dice, lc_bce, totals, loss);
+        pv2::launch(mc_loss_fold_kernel<C>, 1, 256, 0, st, partials, grid, nsub, npix, lc_ce, lc_dice, lc_bce, totals, loss);
         PV2_LAUNCH_CHECK("mc_loss_fold");
     } else {
-        mc_loss_bwd_kernel<C><<<(unsigned)((npix + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st>>>(p, labels, grad_loss, totals, n, mode, npix, H * W,
+        pv2::launch(mc_loss_bwd_kernel<C>, (unsigned)((npix + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st, p, labels, grad_loss, totals, n, mode, npix, H * W,
                                                                                                         lc_ce, lc_dice, lc_bce);
         PV2_LAUNCH_CHECK("mc_loss_bwd");
     }

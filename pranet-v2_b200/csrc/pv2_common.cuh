@@ -36,6 +36,28 @@ void count_launch(int n = 1);
         pv2::count_launch();                                                     \
     } while (0)
 
+// Programmatic dependent launch (PDL): every pv2 kernel is launched with programmatic stream serialization, lets its
+// successor start launching immediately (launch_dependents) and waits for its predecessor's memory (wait) before it
+// touches global memory.  Inside a CUDA graph this removes most of the inter-kernel gap of the ~600 small launches a
+// head step consists of.  PV2_PDL=0 in the environment falls back to plain stream-ordered launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through PV2_LAUNCH_CHECK
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -40,6 +40,7 @@ __device__ __forceinline__ float weit_from_q(uint32_t q) { return fmaf((float)q,
 __global__ void __launch_bounds__(WT_THREADS)
 boundary_weight_kernel(const float* __restrict__ mask, uint16_t* __restrict__ wmap, float* __restrict__ wsum_part,
                        unsigned int* __restrict__ ticket, int H, int W, int tiles_x, int tiles_per_plane) {
+    pv2::pdl_prologue();
     __shared__ float sm[SH * SPITCH];
     __shared__ float hs[SH * TW];
     __shared__ float red[WT_THREADS / 32];
@@ -179,6 +180,7 @@ structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
                           const uint16_t* __restrict__ wmap, int HW, int planes, int chunks, int wt_tiles,
                           float* __restrict__ partials, const float* __restrict__ wsum_part, float* __restrict__ plane_sums,
                           float* __restrict__ plane_loss, float* __restrict__ loss, unsigned int* __restrict__ ticket) {
+    pv2::pdl_prologue();
     __shared__ float red[LS_THREADS / 32][4 * NS];
     __shared__ bool is_last;
     const int plane = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(LS_THREADS)
 structure_loss_bwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
                           const uint16_t* __restrict__ wmap, const float* __restrict__ grad_loss,
                           const float* __restrict__ plane_sums, int HW, int planes) {
+    pv2::pdl_prologue();
     const int plane = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const size_t pbase = (size_t)plane * HW;
     const int p0 = chunk * CHUNK, p1 = min(HW, p0 + CHUNK);
@@ -342,14 +345,14 @@ structure_loss_bwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
 
 template <typename T, int VEC>
 void launch_fwd(int ns, dim3 grid, cudaStream_t st, const PtrPack& pp, const float* mf, const float* mb, const Layout& L, int HW, int planes, float* loss) {
-#define PV2_FWD(NSV) structure_loss_fwd_kernel<T, NSV, VEC><<<grid, LS_THREADS, 0, st>>>(pp, mf, mb, L.wmap, HW, planes, L.chunks, L.wt_tiles, \
+#define PV2_FWD(NSV) pv2::launch(structure_loss_fwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, HW, planes, L.chunks, L.wt_tiles, \
                          L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
     switch (ns) { case 1: PV2_FWD(1); break; case 2: PV2_FWD(2); break; case 3: PV2_FWD(3); break; default: PV2_FWD(4); break; }
 #undef PV2_FWD
 }
 template <typename T, int VEC>
 void launch_bwd(int ns, dim3 grid, cudaStream_t st, const PtrPack& pp, const float* mf, const float* mb, const Layout& L, const float* gl, int HW, int planes) {
-#define PV2_BWD(NSV) structure_loss_bwd_kernel<T, NSV, VEC><<<grid, LS_THREADS, 0, st>>>(pp, mf, mb, L.wmap, gl, L.plane_sums, HW, planes)
+#define PV2_BWD(NSV) pv2::launch(structure_loss_bwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, gl, L.plane_sums, HW, planes)
     switch (ns) { case 1: PV2_BWD(1); break; case 2: PV2_BWD(2); break; case 3: PV2_BWD(3); break; default: PV2_BWD(4); break; }
 #undef PV2_BWD
 }
@@ -400,7 +403,7 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
     const Layout L = make_layout(workspace, planes, H, W);
     PtrPack pp = {};
     for (int k = 0; k < nscales; ++k) { pp.pred[k] = pred[k]; pp.pred_bg[k] = pred_bg[k]; }
-    boundary_weight_kernel<<<dim3(L.wt_tiles, planes), WT_THREADS, 0, st>>>(mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
+    pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, st, mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
     PV2_LAUNCH_CHECK("boundary_weight");
     const int HW = H * W;
     const dim3 grid(L.chunks, planes);
