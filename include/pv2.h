@@ -129,13 +129,41 @@ int pv2_mc_dual_loss_bwd(const float* const* P_fg, const float* const* P_bg, con
  * "Raw": fp32 rows [pixel][ld].  All convolutions are stride 1 with same padding (pad = dil*(k-1)/2).
  * ============================================================================================= */
 
+/* Training-mode BatchNorm statistics fused into the conv epilogue (nn.BatchNorm2d of BasicConv2d, pranet.py:37,41-42).
+ * A conv group (several convs fused along Cout) carries up to PV2_MAX_BN_SEGS BatchNorm modules, each owning the channel
+ * range [c_begin, c_end) of the group's Cout.  With splits == 1 the epilogue reduces every 128-pixel tile of the fp32
+ * accumulator to per-channel (mean, M2) before the tile leaves the SM, and the last CTA to finish (two-level ticket,
+ * fixed combination order: bit-reproducible) folds the tiles with Chan's formula, writes mean / invstd / scale = gamma*invstd
+ * / shift = beta - mean*scale for all Cout channels and updates running_mean / running_var / num_batches_tracked exactly
+ * like nn.BatchNorm2d (momentum, unbiased running variance).  With split-K the same descriptor is given to
+ * pv2_bn_stats_group after the conv.  `counters` must be zero-initialised once; every launch leaves it zeroed. */
+#define PV2_MAX_BN_SEGS 8
+#define PV2_BN_COUNTERS 4096
+typedef struct pv2_bn_seg {
+    const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches_tracked;
+    float eps, momentum;
+    int c_begin, c_end;
+} pv2_bn_seg;
+typedef struct pv2_bn_fuse {
+    pv2_bn_seg seg[PV2_MAX_BN_SEGS];
+    float* mean; float* invstd; float* scale; float* shift;   /* [Cout] each */
+    float* part;                                              /* pv2_bn_fuse_workspace_floats(M, Cout) floats */
+    unsigned int* counters;                                   /* PV2_BN_COUNTERS uints */
+    int nsegs, pad_;
+} pv2_bn_fuse;
+size_t pv2_bn_fuse_workspace_floats(long long M, int Cout);
+/* 1 when pv2_conv_fwd with these arguments computes the statistics in its epilogue (else call pv2_bn_stats_group) */
+int pv2_conv_fuses_bn_stats(int splits, int out_mode);
+/* statistics of raw[slab][M][ld] (slabs summed into slab 0 first) for every segment of `bn`: two launches per GROUP */
+int pv2_bn_stats_group(float* y, long long slab_stride, int nslabs, long long M, int Cout, int ld, const pv2_bn_fuse* bn, void* stream);
+
 /* out_mode 0: raw fp32 out[split][N*H*W][ldo] (split-K partial slabs, summed by pv2_bn_stats / the consumers);
  * out_mode 1: fp32 NCHW out[N][Cout][H][W] + bias (bias may be NULL), splits must be 1.
  * Also computes dgrad when given the mode-1 packed weights (Cin_p := padded Cout, Cout := Cin). */
 int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms);
 int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,
                  int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int dil_h, int dil_w,
-                 int out_mode, float* out, int ldo, int splits, const float* bias, void* stream);
+                 int out_mode, float* out, int ldo, int splits, const float* bias, const pv2_bn_fuse* bn /* or NULL */, void* stream);
 /* dW partials out[split][Cout][KH*KW][Cin_p] = sum over the split's pixels of dY[p][co] * X[p + tap shift][ci] */
 int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind);
 int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const void* x, long long x_plane_stride, int kind, int nterms,
@@ -196,7 +224,8 @@ int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long long ss1, c
                    const float* mean1, const float* inv1, const float* mean2, const float* inv2, int bn_train,
                    float* dmult, int dmult_ld, void* dy1, long long dy1_plane, int dy1_planes, int dy1_ld,
                    void* dy2, long long dy2_plane, int dy2_planes, int dy2_ld,
-                   float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace, int kind, void* stream);
+                   float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace,
+                   unsigned int* counters /* PV2_BN_COUNTERS zero-initialised uints (or NULL: three-launch scalar path) */, int kind, void* stream);
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (pranet.py:93) on operand tensors; backward raw -> raw */
 int pv2_up2_nhwc_fwd(const void* in, long long in_plane, int in_planes, int in_ld, int in_off, void* out, long long out_plane,
                      int out_planes, int out_ld, int out_off, int N, int H, int W, int C, int kind, void* stream);

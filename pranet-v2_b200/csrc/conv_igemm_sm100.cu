@@ -27,6 +27,7 @@
 
 #include "pv2_common.cuh"
 #include "sm100_ptx.cuh"
+#include "ticket.cuh"
 
 namespace pv2 {
 namespace {
@@ -46,6 +47,8 @@ struct ConvArgs {
     int im2col;             // 1: flat 128-pixel tiles loaded in TMA im2col mode; 0: TWb x THb patches (tiled mode)
     long long M;            // N*H*W
     int kc_per_tap, iters_total, iters_per_split;
+    int stats;              // 1: the epilogue also produces the BatchNorm batch statistics (im2col tiles, no split-K)
+    int m_tiles, G, ngroups;   // two-level fold of the per-tile statistics
     int BN;                 // N tile (multiple of 16, <= 256)
     uint32_t tmem_cols;     // power of two >= max(32, BN)
     int out_mode;           // 0: raw fp32 [split][pixel][ldo]   1: NCHW fp32 + bias
@@ -58,7 +61,8 @@ struct ConvArgs {
 template <int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs a) {
+                const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs a,
+                const __grid_constant__ BnFuseDev bn) {
     pdl_trigger();
     constexpr int KC = (KIND == 0) ? 64 : 32;   // channels per 128-byte row
     extern __shared__ uint8_t smem_raw[];
@@ -68,6 +72,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     uint8_t* sB = smem + STAGES * A_BYTES;
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ int s_flag;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int n_img, y0, x0;
@@ -159,6 +164,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             valid = (y < a.H) && (x < a.W);
             pix = ((long long)n_img * a.H + y) * a.W + x;
         }
+        // fused BatchNorm statistics: the pipeline's shared memory is idle now (every MMA has completed) and serves as scratch
+        float* scratch = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);   // this warp's 32 rows x 32 columns, transposed read
+        float* wstat = reinterpret_cast<float*>(smem) + 4 * 32 * 33;                // [4 row quarters][BN][mean, M2]
+        int nvalid_w = 0;                                                           // valid rows of this warp: a prefix (flat tiles)
+        if (a.stats) {
+            const long long rem = a.M - m0 - q * 32;
+            nvalid_w = rem < 0 ? 0 : (rem > 32 ? 32 : (int)rem);
+        }
         for (int c0 = 0; c0 < a.BN; c0 += 32) {
             uint32_t v[32];
             if (a.BN - c0 >= 32) {
@@ -170,6 +183,20 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 for (int j = 0; j < 16; ++j) { v[j] = t[j]; v[16 + j] = 0u; }
             }
             tmem_ld_wait();
+            if (a.stats) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                float sum = 0.0f;
+#pragma unroll 8
+                for (int r2 = 0; r2 < nvalid_w; ++r2) sum += scratch[r2 * 33 + lane];
+                const float mean = nvalid_w > 0 ? sum / (float)nvalid_w : 0.0f;
+                float m2 = 0.0f;
+#pragma unroll 8
+                for (int r2 = 0; r2 < nvalid_w; ++r2) { const float d = scratch[r2 * 33 + lane] - mean; m2 = fmaf(d, d, m2); }
+                __syncwarp();
+                if (c0 + lane < a.BN) { wstat[(q * a.BN + c0 + lane) * 2] = mean; wstat[(q * a.BN + c0 + lane) * 2 + 1] = m2; }
+            }
             if (!valid) continue;
             if (a.out_mode == 0) {
                 float* dst = a.out + (long long)blockIdx.z * a.split_stride + pix * a.ldo + n0 + c0;
@@ -185,6 +212,55 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     const int co = n0 + c0 + j;
                     if (co < a.Cout)
                         a.out[(((long long)n_pix * a.Cout + co) * a.H + y) * a.W + x] = __uint_as_float(v[j]) + (a.bias ? a.bias[co] : 0.0f);
+                }
+            }
+        }
+        if (a.stats) {
+            const int et = threadIdx.x - 64;                 // 0..127 over the four epilogue warps
+            const int tile_m = blockIdx.x;
+            bar_sync(1, 128);
+            // tile statistics: the four row quarters combined in row order
+            for (int c = et; c < a.BN; c += 128) {
+                const int cg = n0 + c;
+                if (cg >= a.Cout) continue;
+                float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const long long rem = a.M - m0 - qq * 32;
+                    const float nv = rem < 0 ? 0.0f : (rem > 32 ? 32.0f : (float)rem);
+                    chan_combine(n, mu, M2, nv, wstat[(qq * a.BN + c) * 2], wstat[(qq * a.BN + c) * 2 + 1]);
+                }
+                float* p = bn.f.part + ((size_t)tile_m * a.Cout + cg) * 2;
+                p[0] = mu; p[1] = M2;
+            }
+            unsigned int* cnt = bn.f.counters + (size_t)blockIdx.y * (a.ngroups + 1);
+            const int g = tile_m / a.G;
+            const int t0 = g * a.G, t1 = min(t0 + a.G, a.m_tiles);
+            if (ticket_last(cnt + g, (unsigned)(t1 - t0), et == 0, &s_flag, 1, 128)) {
+                float* gpart = bn.f.part + (size_t)a.m_tiles * a.Cout * 2;
+                for (int c = et; c < a.BN; c += 128) {
+                    const int cg = n0 + c;
+                    if (cg >= a.Cout) continue;
+                    float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+                    for (int t = t0; t < t1; ++t) {
+                        const long long rem = a.M - (long long)t * BM;
+                        const float* p = bn.f.part + ((size_t)t * a.Cout + cg) * 2;
+                        chan_combine(n, mu, M2, rem > BM ? (float)BM : (float)rem, __ldcg(p), __ldcg(p + 1));
+                    }
+                    float* gp = gpart + ((size_t)g * a.Cout + cg) * 3;
+                    gp[0] = n; gp[1] = mu; gp[2] = M2;
+                }
+                if (ticket_last(cnt + a.ngroups, (unsigned)a.ngroups, et == 0, &s_flag, 1, 128)) {
+                    for (int c = et; c < a.BN; c += 128) {
+                        const int cg = n0 + c;
+                        if (cg >= a.Cout) continue;
+                        float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+                        for (int gg = 0; gg < a.ngroups; ++gg) {
+                            const float* gp = gpart + ((size_t)gg * a.Cout + cg) * 3;
+                            chan_combine(n, mu, M2, __ldcg(gp), __ldcg(gp + 1), __ldcg(gp + 2));
+                        }
+                        bn_write_channel(bn.f, cg, n, mu, M2);
+                    }
                 }
             }
         }
@@ -464,6 +540,8 @@ int common_checks(const char* who, int kind, int nterms, int N, int H, int W, in
 
 using namespace pv2;
 
+extern "C" int pv2_conv_fuses_bn_stats(int splits, int out_mode) { return (use_im2col() && splits == 1 && out_mode == 0) ? 1 : 0; }
+
 extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
     const int KC = kind == PV2_BF16 ? 64 : 32;
     const int m_tiles = m_tiles_of(N, H, W, KH, KW, true);
@@ -479,7 +557,7 @@ extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, in
 
 extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,
                             int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int dil_h, int dil_w,
-                            int out_mode, float* out, int ldo, int splits, const float* bias, void* stream) {
+                            int out_mode, float* out, int ldo, int splits, const float* bias, const pv2_bn_fuse* bn, void* stream) {
     if (int e = common_checks("conv_fwd", kind, nterms, N, H, W, Cin_p, Cout, KH, KW)) return e;
     PV2_CHECK(x && w_op && out, "conv_fwd: null pointer");
     PV2_CHECK(out_mode == 0 || out_mode == 1, "conv_fwd: bad out_mode %d", out_mode);
@@ -506,6 +584,16 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     a.tmem_cols = pow2_cols(a.BN);
     a.out_mode = out_mode; a.out = out; a.ldo = ldo; a.bias = bias;
     a.split_stride = (long long)N * H * W * ldo;
+    BnFuseDev bnd = {};
+    a.m_tiles = (int)((a.M + BM - 1) / BM);
+    if (bn != nullptr && bn->nsegs > 0 && pv2_conv_fuses_bn_stats(splits, out_mode)) {
+        PV2_CHECK(bn->nsegs <= PV2_MAX_BN_SEGS && bn->mean && bn->invstd && bn->scale && bn->shift && bn->part && bn->counters,
+                  "conv_fwd: incomplete pv2_bn_fuse descriptor");
+        const FoldPlan fp = make_fold_plan(a.m_tiles);
+        a.stats = 1; a.G = fp.G; a.ngroups = fp.ngroups;
+        PV2_CHECK((long long)((Cout + a.BN - 1) / a.BN) * (fp.ngroups + 1) <= PV2_BN_COUNTERS, "conv_fwd: ticket counters too small for %d tiles", a.m_tiles);
+        bnd.f = *bn;
+    }
     CUtensorMap mA0, mA1, mB0, mB1;
     if (int e = im2col ? make_im2col_map(&mA0, x, k, Cin_p, W, H, N, a.pad_w, a.pad_h) : make_act_map(&mA0, x, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
     if (int e = make_w_map(&mB0, w_op, k, Cin_p, a.taps, Cout, a.BN)) return e;
@@ -522,11 +610,11 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     if (k == 0) {
         ce = cudaFuncSetAttribute(conv_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
-        pv2::launch(conv_fwd_kernel<0>, grid, THREADS, smem, st, mA0, mA1, mB0, mB1, a);
+        pv2::launch(conv_fwd_kernel<0>, grid, THREADS, smem, st, mA0, mA1, mB0, mB1, a, bnd);
     } else {
         ce = cudaFuncSetAttribute(conv_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
-        pv2::launch(conv_fwd_kernel<1>, grid, THREADS, smem, st, mA0, mA1, mB0, mB1, a);
+        pv2::launch(conv_fwd_kernel<1>, grid, THREADS, smem, st, mA0, mA1, mB0, mB1, a, bnd);
     }
     PV2_LAUNCH_CHECK("conv_fwd");
     return 0;

@@ -10,6 +10,7 @@
 // elements apart) -- what the conv kernels' TMA maps read.  "Raw" = fp32 NHWC rows [pixel][ld] as the conv epilogue
 // writes them, possibly as several slabs (split-K partials / several gradient contributions) that are summed on load.
 #include "pv2_common.cuh"
+#include "ticket.cuh"
 
 namespace pv2 {
 namespace {
@@ -206,16 +207,6 @@ inline int pick_rows(long long M, int C) {
     return (int)rows;
 }
 
-// Chan's parallel combination of (count, mean, M2)
-__device__ __forceinline__ void chan_combine(float& n, float& mu, float& M2, float nb, float mub, float M2b) {
-    if (nb > 0.0f) {
-        const float d = mub - mu, nt = n + nb;
-        mu += d * nb / nt;
-        M2 += M2b + d * d * n * nb / nt;
-        n = nt;
-    }
-}
-
 __global__ void __launch_bounds__(256)
 bn_stats_partial_kernel(float* __restrict__ y, long long slab_stride, int nslabs, long long M, int C, int ld, int rows_pb,
                         float* __restrict__ part /* [row_blocks][C][3] */) {
@@ -291,6 +282,32 @@ bn_stats_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, 
         running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * mu;
         running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (n > 1.0f ? M2 / (n - 1.0f) : var);
     }
+}
+
+// the same fold for a whole conv group: one warp per channel of the group, BatchNorm module found through the segment table
+__global__ void __launch_bounds__(128)
+bn_group_finalize_kernel(const float* __restrict__ part, int row_blocks, int C, const __grid_constant__ BnFuseDev bn) {
+    pv2::pdl_prologue();
+    const int lane = threadIdx.x & 31, c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+    for (int b = lane; b < row_blocks; b += 32) {
+        const float* p = part + ((long long)b * C + c) * 3;
+        chan_combine(n, mu, M2, p[0], p[1], p[2]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, n, o), mub = __shfl_xor_sync(0xffffffffu, mu, o), M2b = __shfl_xor_sync(0xffffffffu, M2, o);
+        const float nt = n + nb;
+        if (nt > 0.0f) {
+            const float d = mub - mu;
+            const float mu_new = (n * mu + nb * mub) / nt;
+            M2 = M2 + M2b + d * d * n * nb / nt;
+            mu = mu_new;
+        }
+        n = nt;
+    }
+    if (lane == 0) bn_write_channel(bn.f, c, n, mu, M2);
 }
 
 // eval-mode BN / plain bias as an affine: scale = gamma / sqrt(rv + eps), shift = beta - rm * scale
@@ -482,6 +499,207 @@ bn_bwd_dx_kernel(const BwdArgs b) {
         }
         store_op<KIND>(b.dy1, b.dy1_plane, b.dy1_planes, r * b.dy1_ld + c, d1);
         if (a.combine) store_op<KIND>(b.dy2, b.dy2_plane, b.dy2_planes, r * b.dy2_ld + c, d2);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 4-channel vector forms of apply / backward (every BasicConv2d of the head qualifies: C % 4 == 0, slices at channel
+// offsets that are multiples of 4).  One thread = one pixel x 4 channels: 16-byte loads of the raw fp32 rows, 8-byte
+// bf16 stores.  The scalar kernels above remain for C = 1 / 9 head maps and NCHW outputs.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 f4_ld(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) { return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w)); }
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float4 f4_set(float v) { return make_float4(v, v, v, v); }
+
+template <int KIND>
+__device__ __forceinline__ void store_op4(void* base, long long plane_stride, int nplanes, long long idx, float4 v) {
+    if constexpr (KIND == 0) {
+        store4<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(base) + idx, v);
+    } else {
+        float* p = reinterpret_cast<float*>(base);
+        const float4 hi = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        *reinterpret_cast<float4*>(p + idx) = hi;
+        if (nplanes > 1)
+            *reinterpret_cast<float4*>(p + idx + plane_stride) =
+                make_float4(tf32_rna(v.x - hi.x), tf32_rna(v.y - hi.y), tf32_rna(v.z - hi.z), tf32_rna(v.w - hi.w));
+    }
+}
+template <int KIND>
+__device__ __forceinline__ float4 load_op4(const void* base, long long plane_stride, int nplanes, long long idx) {
+    if constexpr (KIND == 0) {
+        return load4<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    } else {
+        const float* p = reinterpret_cast<const float*>(base);
+        float4 v = f4_ld(p + idx);
+        if (nplanes > 1) v = f4_add(v, f4_ld(p + idx + plane_stride));
+        return v;
+    }
+}
+__device__ __forceinline__ float4 raw_load4(const float* y, int ld, int off, int ns, long long ss, long long r, int c) {
+    float4 v = f4_ld(y + r * ld + off + c);
+    for (int s = 1; s < ns; ++s) v = f4_add(v, f4_ld(y + s * ss + r * ld + off + c));
+    return v;
+}
+__device__ __forceinline__ float4 slab_sum4(const Slabs& s, long long row, int c) {
+    float4 v = f4_set(0.0f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < s.n) v = f4_add(v, f4_ld(s.p[i] + row * s.ld[i] + s.off[i] + c));
+    return v;
+}
+
+template <int KIND>
+__device__ __forceinline__ float4 apply_value4(const ApplyArgs& a, long long r, int c, float4* a1o, float4* a2o, float4* mo) {
+    const float4 a1 = f4_fma(raw_load4(a.y1, a.ld1, a.off1, a.ns1, a.ss1, r, c), f4_ld(a.s1 + c), f4_ld(a.b1 + c));
+    float4 a2 = f4_set(0.0f), v = a1;
+    if (a.combine) {
+        a2 = f4_fma(raw_load4(a.y2, a.ld2, a.off2, a.ns2, a.ss2, r, c), f4_ld(a.s2 + c), f4_ld(a.b2 + c));
+        v = a.combine == 1 ? f4_add(a1, a2) : f4_mul(a1, a2);
+    }
+    float4 m = f4_set(1.0f);
+    if (a.mult) { m = load_op4<KIND>(a.mult, a.mult_plane, a.mult_planes, r * a.mult_ld + a.mult_off + c); v = f4_mul(v, m); }
+    *a1o = a1; *a2o = a2; *mo = m;
+    return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+act_apply4_kernel(const ApplyArgs a) {
+    pv2::pdl_prologue();
+    const unsigned C4 = (unsigned)a.C >> 2;
+    const unsigned total = (unsigned)a.M * C4;
+    for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += gridDim.x * 256u) {
+        const unsigned r = e / C4;
+        const int c = (int)(e - r * C4) << 2;
+        float4 a1, a2, m;
+        float4 v = apply_value4<KIND>(a, r, c, &a1, &a2, &m);
+        if (a.relu) v = make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
+        store_op4<KIND>(a.out, a.out_plane, a.out_planes, (long long)r * a.out_ld + a.out_off + c, v);
+    }
+}
+
+struct Da4 { float4 da1, da2, yh1, yh2, dm; };
+
+template <int KIND>
+__device__ __forceinline__ Da4 bwd_da4(const BwdArgs& b, long long r, int c) {
+    const ApplyArgs& a = b.f;
+    float4 a1, a2, m;
+    const float4 v = apply_value4<KIND>(a, r, c, &a1, &a2, &m);
+    float4 g = slab_sum4(b.dz, r, c);
+    if (a.relu) {
+        if (!(v.x > 0.0f)) g.x = 0.0f;
+        if (!(v.y > 0.0f)) g.y = 0.0f;
+        if (!(v.z > 0.0f)) g.z = 0.0f;
+        if (!(v.w > 0.0f)) g.w = 0.0f;
+    }
+    float4 comb = a1;
+    if (a.combine == 1) comb = f4_add(a1, a2); else if (a.combine == 2) comb = f4_mul(a1, a2);
+    Da4 o;
+    o.dm = f4_mul(g, comb);
+    const float4 dc = a.mult ? f4_mul(g, m) : g;
+    o.da1 = a.combine == 2 ? f4_mul(dc, a2) : dc;
+    o.da2 = a.combine == 0 ? f4_set(0.0f) : (a.combine == 2 ? f4_mul(dc, a1) : dc);
+    const float4 y1v = raw_load4(a.y1, a.ld1, a.off1, a.ns1, a.ss1, r, c);
+    o.yh1 = b.mean1 ? f4_mul(f4_sub(y1v, f4_ld(b.mean1 + c)), f4_ld(b.inv1 + c)) : y1v;
+    const float4 y2v = a.combine ? raw_load4(a.y2, a.ld2, a.off2, a.ns2, a.ss2, r, c) : f4_set(0.0f);
+    o.yh2 = (a.combine && b.mean2) ? f4_mul(f4_sub(y2v, f4_ld(b.mean2 + c)), f4_ld(b.inv2 + c)) : y2v;
+    return o;
+}
+
+// reduce pass, vector form.  block = RP rows x C4 channel quads; the row-block partials are folded by the CTA that draws the
+// last ticket (two levels, fixed order) into sums[4][C] = (sum da1, sum da1*yhat1, sum da2, sum da2*yhat2) -- which are also
+// dbeta / dgamma -- so no finalize launch follows.
+struct Reduce4Plan { int nblk, rows_pb, RP, G, ngroups; unsigned int* counters; float* gpart; float* dg1; float* db1; float* dg2; float* db2; float* sums_out; };
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce4_kernel(const BwdArgs b, const Reduce4Plan pl) {
+    pv2::pdl_prologue();
+    __shared__ float sh[256 * 16];
+    __shared__ int s_flag;
+    const int C = b.f.C, C4 = C >> 2;
+    const int tid = threadIdx.x;
+    const int quad = tid % C4, rp = tid / C4;
+    const long long r0 = (long long)blockIdx.x * pl.rows_pb, r1 = min(b.f.M, r0 + pl.rows_pb);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+    if (rp < pl.RP) {
+        const int c = quad << 2;
+        for (long long r = r0 + rp; r < r1; r += pl.RP) {
+            const Da4 d = bwd_da4<KIND>(b, r, c);
+            acc[0] += d.da1.x; acc[1] += d.da1.y; acc[2] += d.da1.z; acc[3] += d.da1.w;
+            acc[4] = fmaf(d.da1.x, d.yh1.x, acc[4]); acc[5] = fmaf(d.da1.y, d.yh1.y, acc[5]);
+            acc[6] = fmaf(d.da1.z, d.yh1.z, acc[6]); acc[7] = fmaf(d.da1.w, d.yh1.w, acc[7]);
+            acc[8] += d.da2.x; acc[9] += d.da2.y; acc[10] += d.da2.z; acc[11] += d.da2.w;
+            acc[12] = fmaf(d.da2.x, d.yh2.x, acc[12]); acc[13] = fmaf(d.da2.y, d.yh2.y, acc[13]);
+            acc[14] = fmaf(d.da2.z, d.yh2.z, acc[14]); acc[15] = fmaf(d.da2.w, d.yh2.w, acc[15]);
+            if (b.dmult) *reinterpret_cast<float4*>(b.dmult + r * b.dmult_ld + c) = d.dm;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sh[tid * 16 + i] = acc[i];
+    __syncthreads();
+    // (quad, k) -> sum over the RP row lanes in order; k = 4*which_sum + channel
+    for (int idx = tid; idx < C4 * 16; idx += 256) {
+        const int qd = idx >> 4, k = idx & 15;
+        float t = 0.0f;
+        for (int j = 0; j < pl.RP; ++j) t += sh[(j * C4 + qd) * 16 + k];
+        b.part[((long long)blockIdx.x * 4 + (k >> 2)) * C + (qd << 2) + (k & 3)] = t;
+    }
+    const int g = blockIdx.x / pl.G;
+    const int b0 = g * pl.G, b1 = min(b0 + pl.G, pl.nblk);
+    if (!ticket_last(pl.counters + g, (unsigned)(b1 - b0), tid == 0, &s_flag, 1, 256)) return;
+    for (int i = tid; i < 4 * C; i += 256) {
+        float t = 0.0f;
+        for (int bb = b0; bb < b1; ++bb) t += __ldcg(b.part + (long long)bb * 4 * C + i);
+        pl.gpart[(long long)g * 4 * C + i] = t;
+    }
+    if (!ticket_last(pl.counters + pl.ngroups, (unsigned)pl.ngroups, tid == 0, &s_flag, 1, 256)) return;
+    for (int i = tid; i < 4 * C; i += 256) {
+        float t = 0.0f;
+        for (int gg = 0; gg < pl.ngroups; ++gg) t += __ldcg(pl.gpart + (long long)gg * 4 * C + i);
+        pl.sums_out[i] = t;
+        const int k = i / C, c = i - k * C;
+        if (k == 0 && pl.db1) pl.db1[c] = t;
+        if (k == 1 && pl.dg1) pl.dg1[c] = t;
+        if (k == 2 && pl.db2) pl.db2[c] = t;
+        if (k == 3 && pl.dg2) pl.dg2[c] = t;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+bn_bwd_dx4_kernel(const BwdArgs b) {
+    pv2::pdl_prologue();
+    const ApplyArgs& a = b.f;
+    const unsigned C4 = (unsigned)a.C >> 2;
+    const unsigned total = (unsigned)a.M * C4;
+    const float invn = 1.0f / (float)a.M;
+    for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += gridDim.x * 256u) {
+        const unsigned r = e / C4;
+        const int c = (int)(e - r * C4) << 2;
+        const Da4 d = bwd_da4<KIND>(b, r, c);
+        float4 d1, d2 = f4_set(0.0f);
+        const float4 s1 = f4_ld(a.s1 + c);
+        if (b.bn_train) {
+            const float4 S1 = f4_ld(b.sums + c), S2 = f4_ld(b.sums + a.C + c);
+            d1 = make_float4(s1.x * (d.da1.x - S1.x * invn - d.yh1.x * S2.x * invn), s1.y * (d.da1.y - S1.y * invn - d.yh1.y * S2.y * invn),
+                             s1.z * (d.da1.z - S1.z * invn - d.yh1.z * S2.z * invn), s1.w * (d.da1.w - S1.w * invn - d.yh1.w * S2.w * invn));
+            if (a.combine) {
+                const float4 s2 = f4_ld(a.s2 + c), T1 = f4_ld(b.sums + 2 * a.C + c), T2 = f4_ld(b.sums + 3 * a.C + c);
+                d2 = make_float4(s2.x * (d.da2.x - T1.x * invn - d.yh2.x * T2.x * invn), s2.y * (d.da2.y - T1.y * invn - d.yh2.y * T2.y * invn),
+                                 s2.z * (d.da2.z - T1.z * invn - d.yh2.z * T2.z * invn), s2.w * (d.da2.w - T1.w * invn - d.yh2.w * T2.w * invn));
+            }
+        } else {
+            d1 = f4_mul(s1, d.da1);
+            if (a.combine) d2 = f4_mul(f4_ld(a.s2 + c), d.da2);
+        }
+        store_op4<KIND>(b.dy1, b.dy1_plane, b.dy1_planes, (long long)r * b.dy1_ld + c, d1);
+        if (a.combine) store_op4<KIND>(b.dy2, b.dy2_plane, b.dy2_planes, (long long)r * b.dy2_ld + c, d2);
     }
 }
 
@@ -680,7 +898,11 @@ extern "C" int pv2_unpack_to_nchw(const float* const* slabs, const int* lds, con
 extern "C" size_t pv2_bn_workspace_floats(long long M, int C) {
     const int rows = pick_rows(M, C);
     const long long rb = (M + rows - 1) / rows;
-    return (size_t)(rb * C * 4 + 4 * (long long)C);
+    const long long scalar = rb * C * 4 + 4 * (long long)C;
+    // vector backward: <= 2*148 row blocks + their sqrt-sized groups + the folded sums
+    const long long nblk = 2 * kNumSMs;
+    const long long vec = (nblk + make_fold_plan((int)nblk).ngroups + 1) * 4 * (long long)C;
+    return (size_t)(scalar > vec ? scalar : vec);
 }
 
 extern "C" int pv2_bn_stats(float* y, long long slab_stride, int nslabs, long long M, int C, int ld, const float* gamma, const float* beta,
@@ -700,12 +922,47 @@ extern "C" int pv2_bn_stats(float* y, long long slab_stride, int nslabs, long lo
     return 0;
 }
 
+extern "C" size_t pv2_bn_fuse_workspace_floats(long long M, int Cout) {
+    const long long m_tiles = (M + 127) / 128;
+    const FoldPlan fp = make_fold_plan((int)m_tiles);
+    const long long fused = m_tiles * Cout * 2 + (long long)fp.ngroups * Cout * 3;       // conv epilogue: tile + group partials
+    const int rows = pick_rows(M, Cout);
+    const long long standalone = ((M + rows - 1) / rows) * Cout * 3;                       // pv2_bn_stats_group row-block partials
+    return (size_t)(fused > standalone ? fused : standalone);
+}
+
+extern "C" int pv2_bn_stats_group(float* y, long long slab_stride, int nslabs, long long M, int Cout, int ld, const pv2_bn_fuse* bn, void* stream) {
+    PV2_CHECK(y && bn && bn->nsegs > 0 && bn->nsegs <= PV2_MAX_BN_SEGS, "bn_stats_group: bad arguments");
+    PV2_CHECK(bn->mean && bn->invstd && bn->scale && bn->shift && bn->part, "bn_stats_group: incomplete pv2_bn_fuse descriptor");
+    PV2_CHECK(M > 0 && Cout > 0 && ld >= Cout && nslabs >= 1, "bn_stats_group: bad shape");
+    const int rows = pick_rows(M, Cout);
+    const int rb = (int)((M + rows - 1) / rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    pv2::launch(bn_stats_partial_kernel, dim3(rb, (Cout + 31) / 32), 256, 0, st, y, slab_stride, nslabs, M, Cout, ld, rows, bn->part);
+    PV2_LAUNCH_CHECK("bn_stats_partial");
+    BnFuseDev d;
+    d.f = *bn;
+    pv2::launch(bn_group_finalize_kernel, (Cout + 3) / 4, 128, 0, st, (const float*)bn->part, rb, Cout, d);
+    PV2_LAUNCH_CHECK("bn_group_finalize");
+    return 0;
+}
+
 extern "C" int pv2_bn_eval_affine(int C, const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                   float* scale, float* shift, void* stream) {
     PV2_CHECK(C > 0 && rm && rv && scale && shift, "bn_eval_affine: bad arguments");
     pv2::launch(bn_eval_affine_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, C, gamma, beta, rm, rv, eps, scale, shift);
     PV2_LAUNCH_CHECK("bn_eval_affine");
     return 0;
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// the 4-channel vector kernels need every per-channel array and every row start on a 16-byte (bf16 operand: 8-byte) boundary
+static bool apply_vec_ok(const pv2::ApplyArgs& a) {
+    if (a.C % 4 != 0 || a.M * (long long)a.C >= (1LL << 31)) return false;
+    if (a.ld1 % 4 != 0 || a.off1 % 4 != 0 || a.ss1 % 4 != 0 || !al16(a.y1) || !al16(a.s1) || !al16(a.b1)) return false;
+    if (a.combine && (a.ld2 % 4 != 0 || a.off2 % 4 != 0 || a.ss2 % 4 != 0 || !al16(a.y2) || !al16(a.s2) || !al16(a.b2))) return false;
+    if (a.mult && (a.mult_ld % 4 != 0 || a.mult_off % 4 != 0 || a.mult_plane % 4 != 0 || !al16(a.mult))) return false;
+    return true;
 }
 
 // flat argument list -> ApplyArgs (ctypes-friendly)
@@ -735,6 +992,12 @@ extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long l
     PV2_CHECK(out != nullptr, "act_apply: null output");
     a.out = out; a.out_plane = out_plane; a.out_planes = out_planes; a.out_ld = out_ld; a.out_off = out_off; a.out_nchw = out_nchw;
     const long long total = M * C;
+    if (!out_nchw && apply_vec_ok(a) && out_ld % 4 == 0 && out_off % 4 == 0 && al16(out)) {
+        if (kind == PV2_BF16) pv2::launch(act_apply4_kernel<0>, grid_for(total / 4), 256, 0, (cudaStream_t)stream, a);
+        else pv2::launch(act_apply4_kernel<1>, grid_for(total / 4), 256, 0, (cudaStream_t)stream, a);
+        PV2_LAUNCH_CHECK("act_apply4");
+        return 0;
+    }
     if (kind == PV2_BF16) pv2::launch(act_apply_kernel<0>, grid_for(total), 256, 0, (cudaStream_t)stream, a);
     else pv2::launch(act_apply_kernel<1>, grid_for(total), 256, 0, (cudaStream_t)stream, a);
     PV2_LAUNCH_CHECK("act_apply");
@@ -749,7 +1012,8 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
                               const float* mean1, const float* inv1, const float* mean2, const float* inv2, int bn_train,
                               float* dmult, int dmult_ld, void* dy1, long long dy1_plane, int dy1_planes, int dy1_ld,
                               void* dy2, long long dy2_plane, int dy2_planes, int dy2_ld,
-                              float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace, int kind, void* stream) {
+                              float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace, unsigned int* counters,
+                              int kind, void* stream) {
     PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "bn_act_bwd: bad operand kind %d", kind);
     BwdArgs b = {};
     if (int e = fill_apply(&b.f, y1, ld1, off1, ns1, ss1, s1, b1, y2, ld2, off2, ns2, ss2, s2, b2, combine, mult, mult_plane, mult_planes, mult_ld, mult_off, relu, M, C, HW)) return e;
@@ -767,6 +1031,46 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
     b.bn_train = bn_train;
     b.dy1 = dy1; b.dy1_plane = dy1_plane; b.dy1_planes = dy1_planes; b.dy1_ld = dy1_ld;
     b.dy2 = dy2; b.dy2_plane = dy2_plane; b.dy2_planes = dy2_planes; b.dy2_ld = dy2_ld;
+    {   // vector path: reduce (+ ticket fold) and dx, two launches
+        bool ok = dz_nchw == nullptr && apply_vec_ok(b.f) && dy1_ld % 4 == 0 && al16(dy1) && dy1_plane % 4 == 0 && counters != nullptr;
+        if (ok && combine) ok = dy2_ld % 4 == 0 && al16(dy2) && dy2_plane % 4 == 0;
+        if (ok && bn_train) ok = al16(mean1) && al16(inv1) && (!combine || (al16(mean2) && al16(inv2)));
+        if (ok && b.dmult) ok = dmult_ld % 4 == 0 && al16(dmult);
+        for (int i = 0; ok && i < b.dz.n; ++i) ok = b.dz.ld[i] % 4 == 0 && b.dz.off[i] % 4 == 0 && al16(b.dz.p[i]);
+        if (ok) {
+            const int C4 = C / 4;
+            ok = C4 <= 256;
+            if (ok) {
+                Reduce4Plan pl;
+                pl.RP = 256 / C4;
+                long long nblk = (M + pl.RP - 1) / pl.RP;                 // at least one pass of rows per block
+                const long long cap = 2 * kNumSMs;
+                if (nblk > cap) nblk = cap;
+                long long rows = (M + nblk - 1) / nblk;
+                rows = (rows + pl.RP - 1) / pl.RP * pl.RP;
+                nblk = (M + rows - 1) / rows;
+                pl.nblk = (int)nblk; pl.rows_pb = (int)rows;
+                const FoldPlan fp = make_fold_plan(pl.nblk);
+                pl.G = fp.G; pl.ngroups = fp.ngroups;
+                PV2_CHECK(fp.ngroups + 1 <= PV2_BN_COUNTERS, "bn_act_bwd: ticket counters too small");
+                pl.counters = counters;
+                // workspace: part [nblk][4][C] | gpart [ngroups][4][C] | sums [4][C]   (pv2_bn_workspace_floats covers it)
+                b.part = workspace;
+                pl.gpart = workspace + (size_t)pl.nblk * 4 * C;
+                float* sums4 = pl.gpart + (size_t)pl.ngroups * 4 * C;
+                pl.sums_out = sums4; b.sums = sums4;
+                pl.dg1 = dgamma1; pl.db1 = dbeta1; pl.dg2 = dgamma2; pl.db2 = dbeta2;
+                b.rows_pb = pl.rows_pb;
+                cudaStream_t st4 = (cudaStream_t)stream;
+                if (kind == PV2_BF16) pv2::launch(bn_bwd_reduce4_kernel<0>, pl.nblk, 256, 0, st4, b, pl); else pv2::launch(bn_bwd_reduce4_kernel<1>, pl.nblk, 256, 0, st4, b, pl);
+                PV2_LAUNCH_CHECK("bn_bwd_reduce4");
+                const long long total4 = M * C4;
+                if (kind == PV2_BF16) pv2::launch(bn_bwd_dx4_kernel<0>, grid_for(total4), 256, 0, st4, b); else pv2::launch(bn_bwd_dx4_kernel<1>, grid_for(total4), 256, 0, st4, b);
+                PV2_LAUNCH_CHECK("bn_bwd_dx4");
+                return 0;
+            }
+        }
+    }
     const int rows = pick_rows(M, C);
     const int rb = (int)((M + rows - 1) / rows);
     b.rows_pb = rows;

@@ -30,7 +30,22 @@ _PACK_DT = np.dtype([("w", "u8"), ("out_f", "u8"), ("out_d", "u8"), ("f_plane", 
                      ("d_ild", "i4"), ("d_ioff", "i4"), ("d_ooff", "i4")], align=True)       # == pv2_pack_desc (88 B)
 _UNPACK_DT = np.dtype([("part", "u8"), ("dw", "u8"), ("split_stride", "i8"), ("start", "i8"), ("splits", "i4"), ("Cout", "i4"),
                        ("Cin", "i4"), ("KH", "i4"), ("KW", "i4"), ("Cin_p", "i4"), ("co_off", "i4"), ("pad_", "i4")], align=True)   # == pv2_unpack_desc (64 B)
-assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64
+_BNSEG_DT = np.dtype([("gamma", "u8"), ("beta", "u8"), ("rm", "u8"), ("rv", "u8"), ("nbt", "u8"), ("eps", "f4"), ("momentum", "f4"),
+                      ("c_begin", "i4"), ("c_end", "i4")], align=True)                                  # == pv2_bn_seg (56 B)
+_BNFUSE_DT = np.dtype([("seg", _BNSEG_DT, (8,)), ("mean", "u8"), ("invstd", "u8"), ("scale", "u8"), ("shift", "u8"), ("part", "u8"),
+                       ("counters", "u8"), ("nsegs", "i4"), ("pad_", "i4")], align=True)                 # == pv2_bn_fuse (504 B)
+assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.itemsize == 56 and _BNFUSE_DT.itemsize == 504
+_COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
+
+
+def _ticket_counters(device):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    t = _COUNTERS.get(key)
+    if t is None:
+        t = torch.zeros(4096, dtype=torch.int32, device=device)
+        if not torch.cuda.is_current_stream_capturing():     # a buffer born inside a graph capture belongs to that graph's pool
+            _COUNTERS[key] = t
+    return t
 
 
 def set_precision(p: str):
@@ -67,12 +82,14 @@ class Act:
 
 class Raw:
     """Raw conv output: fp32 [splits, M, ld]; after bn_stats slab 0 holds the split sum."""
-    __slots__ = ("t", "splits", "M", "ld", "C", "dy", "N", "H", "W")
+    __slots__ = ("t", "splits", "M", "ld", "C", "dy", "N", "H", "W", "stats", "stat_bns")
 
     def __init__(self, t, splits, N, H, W, ld, C):
         self.t, self.splits, self.N, self.H, self.W, self.ld, self.C = t, splits, N, H, W, ld, C
         self.M = N * H * W
         self.dy = None            # operand-format gradient w.r.t. this raw output (set by the apply backward)
+        self.stats = None         # fp32 [4][C]: batch mean, invstd, scale, shift of every channel (training BN, produced with the conv)
+        self.stat_bns = {}        # channel offset -> BatchNorm module whose statistics `stats` holds there
 
 
 class Map:
@@ -221,8 +238,33 @@ class Engine:
         self.unpack_jobs = []
 
     # ---- convolution (optionally several convs of identical geometry fused along Cout) ---------------------
-    def conv(self, x: Act, convs, out_nchw_bias=False):
-        """x -> Raw [splits, M, ld] (or, with out_nchw_bias, a biased fp32 NCHW Map straight from the epilogue)."""
+    def _bn_fuse(self, convs, bns, M, Cout):
+        """pv2_bn_fuse descriptor (host struct, passed by value into the kernels) for the BatchNorms that follow `convs`."""
+        stats = self.f32(4, Cout)
+        ws = self.f32(self.lib.pv2_bn_fuse_workspace_floats(M, Cout))
+        cnt = _ticket_counters(self.dev)
+        d = np.zeros(1, dtype=_BNFUSE_DT)
+        o, n, seg_of = 0, 0, {}
+        for cv, bn in zip(convs, bns):
+            if bn is not None:
+                track = bn.track_running_stats and bn.running_mean is not None
+                d["seg"][0, n] = (_ptr(bn.weight) or 0, _ptr(bn.bias) or 0, bn.running_mean.data_ptr() if track else 0,
+                                  bn.running_var.data_ptr() if track else 0, bn.num_batches_tracked.data_ptr() if track else 0,
+                                  float(bn.eps), 0.1 if bn.momentum is None else float(bn.momentum), o, o + cv.out_channels)
+                seg_of[o] = bn
+                n += 1
+            o += cv.out_channels
+        if n > 8:
+            raise ValueError("pv2 conv engine: at most 8 BatchNorm modules per fused conv group")
+        base = stats.data_ptr()
+        d["mean"], d["invstd"], d["scale"], d["shift"] = base, base + 4 * Cout, base + 8 * Cout, base + 12 * Cout
+        d["part"], d["counters"], d["nsegs"] = ws.data_ptr(), cnt.data_ptr(), n
+        return d, stats, seg_of, (ws, cnt)
+
+    def conv(self, x: Act, convs, bns=None, out_nchw_bias=False):
+        """x -> Raw [splits, M, ld] (or, with out_nchw_bias, a biased fp32 NCHW Map straight from the epilogue).
+        `bns` (one BatchNorm2d or None per conv): in training mode their batch statistics are produced by the conv
+        launch itself (epilogue reduction + ticket fold) or, under split-K, by one grouped statistics pass."""
         convs = list(convs)
         c0 = convs[0]
         KH, KW = c0.kernel_size
@@ -248,15 +290,24 @@ class Engine:
             assert len(convs) == 1
             out = self.f32(N, Cout, H, W)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(x), self.plane_stride(x), w_op.data_ptr(), Cout * taps * Cin_p, self.kind, self.nterms,
-                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 1, out.data_ptr(), 0, 1, _ptr(c0.bias), st), "pv2_conv_fwd")
+                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 1, out.data_ptr(), 0, 1, _ptr(c0.bias), None, st), "pv2_conv_fwd")
             res = Map(out)
         else:
             ld = (Cout + 3) // 4 * 4
             splits = lib.pv2_conv_splits_hint(N, H, W, Cin_p, Cout, KH, KW, self.kind, self.nterms)
             raw_t = self.f32(splits, N * H * W, ld)
+            fuse = None
+            if self.training and bns is not None and any(b is not None for b in bns):
+                fuse, stats, seg_of, hold = self._bn_fuse(convs, list(bns), N * H * W, Cout)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(x), self.plane_stride(x), w_op.data_ptr(), Cout * taps * Cin_p, self.kind, self.nterms,
-                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 0, raw_t.data_ptr(), ld, splits, None, st), "pv2_conv_fwd")
+                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 0, raw_t.data_ptr(), ld, splits, None,
+                                        fuse.ctypes.data if fuse is not None else None, st), "pv2_conv_fwd")
             res = Raw(raw_t, splits, N, H, W, ld, Cout)
+            if fuse is not None:
+                if not lib.pv2_conv_fuses_bn_stats(splits, 0):      # split-K (or patch tiles): one grouped pass, sums the slabs into slab 0
+                    _lib.check(lib.pv2_bn_stats_group(raw_t.data_ptr(), N * H * W * ld, splits, N * H * W, Cout, ld, fuse.ctypes.data, st),
+                               "pv2_bn_stats_group")
+                res.stats, res.stat_bns = stats, seg_of
         if self.need_grad:
             self.tape.append(lambda: self._conv_bwd(x, convs, res, KH, KW, dh, dw, Cin, Cin_p, Cout))
         return res
@@ -299,7 +350,7 @@ class Engine:
             splits = lib.pv2_conv_splits_hint(N, H, W, Cout_p, Cin, KH, KW, self.kind, self.nterms)
             dx = self.f32(splits, N * H * W, ld)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(dy), self.plane_stride(dy), wt.data_ptr(), Cin * taps * Cout_p, self.kind, self.nterms,
-                                        N, H, W, Cout_p, Cin, KH, KW, dh, dw, 0, dx.data_ptr(), ld, splits, None, st), "pv2_conv_fwd(dgrad)")
+                                        N, H, W, Cout_p, Cin, KH, KW, dh, dw, 0, dx.data_ptr(), ld, splits, None, None, st), "pv2_conv_fwd(dgrad)")
             for s in range(splits):
                 x.gslabs.append((dx[s], ld, 0))
 
@@ -322,6 +373,9 @@ class Engine:
         return scale, shift, None, None
 
     def _bn_train_stats(self, raw: Raw, off, C, bn):
+        if raw.stats is not None and raw.stat_bns.get(off) is bn:      # produced together with the conv
+            st4 = raw.stats
+            return st4[2, off:off + C], st4[3, off:off + C], st4[0, off:off + C], st4[1, off:off + C]
         lib, st = self.lib, _stream()
         scale, shift, mean, inv = self.f32(C), self.f32(C), self.f32(C), self.f32(C)
         ws = self.f32(lib.pv2_bn_workspace_floats(raw.M, C))
@@ -395,7 +449,8 @@ class Engine:
                 _lib.check(lib.pv2_bn_act_bwd(*fwd_args, *dz, _ptr(m1), _ptr(i1), _ptr(m2), _ptr(i2), bn_train,
                                               _ptr(dmult), Cc, dy1_ptr, self.plane_stride(dy1), self.planes, dy1.ld,
                                               dy2_ptr, self.plane_stride(dy2) if dy2 else 0, self.planes, dy2.ld if dy2 else 0,
-                                              dg1.data_ptr(), db1.data_ptr(), _ptr(dg2), _ptr(db2), ws.data_ptr(), self.kind, _stream()),
+                                              dg1.data_ptr(), db1.data_ptr(), _ptr(dg2), _ptr(db2), ws.data_ptr(), _ticket_counters(self.dev).data_ptr(),
+                                              self.kind, _stream()),
                            "pv2_bn_act_bwd")
                 self._route_bn_grads(src1, dg1, db1, bn_train)
                 if src2:

@@ -40,7 +40,7 @@ class BasicConv2d(nn.Module):
         self.bn = nn.BatchNorm2d(out_planes)
 
     def run(self, eng, x: E.Act, relu=False, out=None, out_map=False):
-        raw = eng.conv(x, [self.conv])
+        raw = eng.conv(x, [self.conv], [self.bn])
         return eng.bn_apply((raw, 0, self.conv.out_channels, self.bn, None), relu=relu, out=out, out_map=out_map)
 
     def forward(self, x, relu: bool = False):
@@ -61,13 +61,17 @@ def rfb_run(eng, rfb: "RFB_modified", raw1x1: E.Raw, off: int, out_map=False):
         t = br[1].run(eng, t)
         t = br[2].run(eng, t)
         br[3].run(eng, t, out=sl[b])
-    raw_cat = eng.conv(whole, [rfb.conv_cat.conv])
+    raw_cat = eng.conv(whole, [rfb.conv_cat.conv], [rfb.conv_cat.bn])
     return eng.bn_apply((raw_cat, 0, c, rfb.conv_cat.bn, None), src2=(raw1x1, off + 4 * c, c, rfb.conv_res.bn, None), combine=1, relu=True,
                         out_map=out_map)
 
 
 def rfb_convs(rfb: "RFB_modified"):
     return [rfb.branch0[0].conv, rfb.branch1[0].conv, rfb.branch2[0].conv, rfb.branch3[0].conv, rfb.conv_res.conv]
+
+
+def rfb_bns(rfb: "RFB_modified"):
+    return [rfb.branch0[0].bn, rfb.branch1[0].bn, rfb.branch2[0].bn, rfb.branch3[0].bn, rfb.conv_res.bn]
 
 
 class RFB_modified(nn.Module):
@@ -89,7 +93,7 @@ class RFB_modified(nn.Module):
     def forward(self, x):
         def runner(eng, inputs, in_grads):
             a = eng.from_nchw(inputs[0], _sink(in_grads, 0))
-            return [rfb_run(eng, self, eng.conv(a, rfb_convs(self)), 0, out_map=True)]
+            return [rfb_run(eng, self, eng.conv(a, rfb_convs(self), rfb_bns(self)), 0, out_map=True)]
         return E.run_head(runner, [x], _params(self), self.training)[0]
 
 
@@ -101,13 +105,13 @@ def aggregation_run(eng, agg: "aggregation", x1: E.Act, x2: E.Act, x3: E.Act):
     upup_x1 = eng.up2(up_x1)
     up_x2 = eng.up2(x2)
     # conv_upsample1 and conv_upsample4 read the same tensor: one GEMM
-    raw_a = eng.conv(up_x1, [agg.conv_upsample1.conv, agg.conv_upsample4.conv])
+    raw_a = eng.conv(up_x1, [agg.conv_upsample1.conv, agg.conv_upsample4.conv], [agg.conv_upsample1.bn, agg.conv_upsample4.bn])
     cat2, s2 = eng.concat_buffer(x2.N, x2.H, x2.W, [c, c])
     eng.bn_apply((raw_a, 0, c, agg.conv_upsample1.bn, None), mult=x2, out=s2[0])                       # x2_1
     eng.bn_apply((raw_a, c, c, agg.conv_upsample4.bn, None), out=s2[1])
     x2_2 = agg.conv_concat2.run(eng, cat2)
-    raw_b = eng.conv(upup_x1, [agg.conv_upsample2.conv])
-    raw_c = eng.conv(up_x2, [agg.conv_upsample3.conv])
+    raw_b = eng.conv(upup_x1, [agg.conv_upsample2.conv], [agg.conv_upsample2.bn])
+    raw_c = eng.conv(up_x2, [agg.conv_upsample3.conv], [agg.conv_upsample3.bn])
     cat3, s3 = eng.concat_buffer(x3.N, x3.H, x3.W, [c, 2 * c])
     eng.bn_apply((raw_b, 0, c, agg.conv_upsample2.bn, None), src2=(raw_c, 0, c, agg.conv_upsample3.bn, None),
                  combine=2, mult=x3, out=s3[0])                                                         # x3_1
@@ -159,7 +163,7 @@ def dual_heads_run(eng, fg_mod, bg_mod, feat: E.Act):
     """fg / bg heads on the same decoder feature as ONE GEMM (N = 2*num_class).  BasicConv2d heads (conv + BN:
     EMCAD/lib/decoders.py:434-444, MERIT/lib/decoders.py:298-322) or biased 1x1 nn.Conv2d (MIST/lib/MIST.py:403-412)."""
     if isinstance(fg_mod, BasicConv2d):
-        raw = eng.conv(feat, [fg_mod.conv, bg_mod.conv])
+        raw = eng.conv(feat, [fg_mod.conv, bg_mod.conv], [fg_mod.bn, bg_mod.bn])
         c = fg_mod.conv.out_channels
         return (eng.bn_apply((raw, 0, c, fg_mod.bn, None), out_map=True), eng.bn_apply((raw, c, c, bg_mod.bn, None), out_map=True))
     raw = eng.conv(feat, [fg_mod, bg_mod])

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import engine as E
 from .backbones import PvtV2B2, Res2Net50
-from .heads import BasicConv2d, RFB_modified, _sink, aggregation, aggregation_run, rfb_convs, rfb_run
+from .heads import BasicConv2d, RFB_modified, _sink, aggregation, aggregation_run, rfb_bns, rfb_convs, rfb_run
 
 RES2NET_CH = (512, 1024, 2048)
 PVT_CH = (128, 320, 512)
@@ -89,7 +89,7 @@ class _V2Mixin(_PraNetBase):
             # [rfb.branch0..3 first convs | rfb.conv_res | ra_conv1]
             for a, rfb, stage in zip(feats, (self.rfb2_1, self.rfb3_1, self.rfb4_1), (2, 3, 4)):
                 ra1 = getattr(self, f"ra{stage}_conv1")
-                raw = eng.conv(a, rfb_convs(rfb) + [ra1.conv])
+                raw = eng.conv(a, rfb_convs(rfb) + [ra1.conv], rfb_bns(rfb) + [ra1.bn])
                 c = rfb.conv_res.conv.out_channels
                 rfbs.append(rfb_run(eng, rfb, raw, 0))
                 stacks.append(eng.bn_apply((raw, 5 * c, ra1.conv.out_channels, ra1.bn, None)))       # no ReLU after conv1
@@ -149,7 +149,7 @@ class _V1Mixin(_PraNetBase):
         """PraNet_Res2Net.py:143-186 -> (l5, l4, l3, l2)."""
         def runner(eng, inputs, in_grads):
             feats = [eng.from_nchw(t, _sink(in_grads, i)) for i, t in enumerate(inputs)]
-            rfbs = [rfb_run(eng, rfb, eng.conv(a, rfb_convs(rfb)), 0) for a, rfb in zip(feats, (self.rfb2_1, self.rfb3_1, self.rfb4_1))]
+            rfbs = [rfb_run(eng, rfb, eng.conv(a, rfb_convs(rfb), rfb_bns(rfb)), 0) for a, rfb in zip(feats, (self.rfb2_1, self.rfb3_1, self.rfb4_1))]
             ra5 = aggregation_run(eng, self.agg1, rfbs[2], rfbs[1], rfbs[0])[0]
             outs = [eng.resize(ra5, 8)]
             x = ra5
