@@ -50,6 +50,24 @@ def timed(fn, iters, warm=5):
     return a.elapsed_time(b) / iters   # ms
 
 
+def timed_graph(fn, n=24, reps=5):
+    """Device time of one fn() launch sequence, free of CPU launch overhead: n calls captured in a CUDA graph, replayed."""
+    fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            fn()
+    g.replay()
+    return timed(g.replay, reps, warm=2) / n
+
+
 def head_flops(model, B, S):
     """Un-padded conv FLOPs of one head forward (2*M*N*K summed over every nn.Conv2d outside the backbone)."""
     import torch.nn as nn
@@ -72,6 +90,37 @@ def head_flops(model, B, S):
         kh, kw = m.kernel_size
         total += 2 * B * hw * hw * m.out_channels * m.in_channels * kh * kw
     return total
+
+
+def trace_graph(graph, path, B, S, reps=3):
+    """Per-kernel device durations INSIDE the graph replay (CUPTI via torch.profiler): what each launch really costs
+    when it runs in its place in the step, plus the idle gaps between consecutive kernels."""
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            graph.replay()
+        torch.cuda.synchronize()
+    evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start],
+                 key=lambda e: e.time_range.start)
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    busy, gaps, last_end = 0.0, 0.0, None
+    for e in evs:
+        d = e.time_range.end - e.time_range.start
+        m = re.search(r"pv2::(?:\(anonymous namespace\)::|<unnamed>::)?(\w+)", e.name)
+        name = "pv2::" + m.group(1) if m else ("pv2::slabs_to_nhwc_kernel" if "slabs_to" in e.name else "torch: " + e.name[:60])
+        agg[name][0] += 1
+        agg[name][1] += d
+        busy += d
+        if last_end is not None and e.time_range.start > last_end and e.time_range.start - last_end < 200:
+            gaps += e.time_range.start - last_end
+        last_end = max(last_end or 0, e.time_range.end)
+    with open(path, "a") as f:
+        f.write(f"# B={B} S={S}: {len(evs) // reps} kernels/replay, sum of kernel durations {busy / reps:.1f} us/replay, idle gaps {gaps / reps:.1f} us/replay\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{v[1] / reps:10.1f} us n={v[0] // reps:5d} avg {v[1] / v[0]:7.2f} us  {k}\n")
 
 
 def sweep_point(P, model, B, S, iters, chans, dev):
@@ -107,6 +156,8 @@ def sweep_point(P, model, B, S, iters, chans, dev):
         loss = step()
     launches = P._lib.launch_count() - n0
     ms = timed(graph.replay, iters)
+    if os.environ.get("PV2_TRACE"):
+        trace_graph(graph, os.environ["PV2_TRACE"], B, S)
     ms_eager = timed(step, max(3, iters // 10), warm=1)
     px = B * S * S
     # algorithmic HBM bytes of the full-resolution part of the step (fp32 maps): 8 final maps written (fwd) and their
@@ -123,7 +174,13 @@ def kernel_table(P, dev, B, S, hbm, tflops):
     from pranet_v2_b200 import synthetic
     from pranet_v2_b200.ops import PV2_F32, _ratio
     lib = P._lib.load()
-    st = torch.cuda.current_stream().cuda_stream
+
+    class _St:      # the launching stream is whatever torch's current stream is at call time (a capture stream under timed_graph)
+        def __int__(self):
+            return torch.cuda.current_stream().cuda_stream
+    import ctypes
+    def cur():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     rows = []
     px = B * S * S
     nset = max(2, int(400e6 // (px * 4 * 16)) + 1)
@@ -143,16 +200,16 @@ def kernel_table(P, dev, B, S, hbm, tflops):
 
     def sl_fwd():
         (pp, _), (pb, _), _, _ = packs[rot()]
-        P._lib.check(lib.pv2_structure_loss_fwd(pp, pb, m.data_ptr(), None, 4, B, S, S, 0, loss.data_ptr(), ws.data_ptr(), ws_bytes, st), "fwd")
+        P._lib.check(lib.pv2_structure_loss_fwd(pp, pb, m.data_ptr(), None, 4, B, S, S, 0, loss.data_ptr(), ws.data_ptr(), ws_bytes, cur()), "fwd")
 
     def sl_bwd():
         (pp, _), (pb, _), (dp, _), (dq, _) = packs[rot()]
-        P._lib.check(lib.pv2_structure_loss_bwd(pp, pb, m.data_ptr(), None, gl.data_ptr(), dp, dq, 4, B, S, S, 0, ws.data_ptr(), ws_bytes, st), "bwd")
+        P._lib.check(lib.pv2_structure_loss_bwd(pp, pb, m.data_ptr(), None, gl.data_ptr(), dp, dq, 4, B, S, S, 0, ws.data_ptr(), ws_bytes, cur()), "bwd")
 
     sl_fwd()
-    t = timed(sl_fwd, 30)
+    t = timed_graph(sl_fwd)
     rows.append(("structure_loss fwd x4 (+ boundary weight + finalize)", "hbm", px * (4 + 4 * 8), t))
-    t = timed(sl_bwd, 30)
+    t = timed_graph(sl_bwd)
     rows.append(("structure_loss bwd x4", "hbm", px * (4 + 4 * 16), t))
     # final upsamples: x8 of a 44^2 map (two of the 8 maps are x32 / x16; x8 dominates), fp32
     for s in (8, 16, 32):
@@ -163,14 +220,34 @@ def kernel_table(P, dev, B, S, hbm, tflops):
 
         def up_f():
             j = rot() * 8 % len(lo)
-            P._lib.check(lib.pv2_bilinear_fwd(lo[j].data_ptr(), hi[j].data_ptr(), B, h, h, S, S, r, r, 0, PV2_F32, st), "bil")
+            P._lib.check(lib.pv2_bilinear_fwd(lo[j].data_ptr(), hi[j].data_ptr(), B, h, h, S, S, r, r, 0, PV2_F32, cur()), "bil")
 
         def up_b():
             j = rot() * 8 % len(lo)
-            P._lib.check(lib.pv2_bilinear_bwd(hi[j].data_ptr(), lo[j].data_ptr(), B, h, h, S, S, r, r, 0, PV2_F32, st), "bilb")
-        rows.append((f"bilinear x{s} fwd (one map)", "hbm", (px + B * h * h) * 4, timed(up_f, 50)))
-        rows.append((f"bilinear x{s} bwd (one map)", "hbm", (px + B * h * h) * 4, timed(up_b, 50)))
+            P._lib.check(lib.pv2_bilinear_bwd(hi[j].data_ptr(), lo[j].data_ptr(), B, h, h, S, S, r, r, 0, PV2_F32, cur()), "bilb")
+        rows.append((f"bilinear x{s} fwd (one map)", "hbm", (px + B * h * h) * 4, timed_graph(up_f)))
+        rows.append((f"bilinear x{s} bwd (one map)", "hbm", (px + B * h * h) * 4, timed_graph(up_b)))
         del lo, hi
+    # the 8 final maps in one launch (x8, x16, x32, x8, twice), as the head issues them
+    scs = (8, 16, 32, 8, 8, 16, 32, 8)
+    nrot = max(2, nset // 2)
+    lows = [[torch.randn(B, 1, S // s, S // s, device=dev) for s in scs] for _ in range(nrot)]
+    his = [[torch.empty(B, 1, S, S, device=dev) for _ in scs] for _ in range(nrot)]
+    ihs = (ctypes.c_int * 8)(*[S // s for s in scs])
+    rr = (ctypes.c_float * 8)(*[_ratio(S // s, S, False, float(s)) for s in scs])
+    pk = [(P._lib.ptr_array(lows[j]), P._lib.ptr_array(his[j])) for j in range(nrot)]
+
+    def mf():
+        (pl, _), (ph, _) = pk[rot() % nrot]
+        P._lib.check(lib.pv2_bilinear_multi_fwd(pl, ph, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, cur()), "bilm")
+
+    def mb():
+        (pl, _), (ph, _) = pk[rot() % nrot]
+        P._lib.check(lib.pv2_bilinear_multi_bwd(ph, pl, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, cur()), "bilmb")
+    lowpx = sum(B * (S // s) ** 2 for s in scs)
+    rows.append(("bilinear fwd, 8 final maps in one launch", "hbm", (8 * px + lowpx) * 4, timed_graph(mf)))
+    rows.append(("bilinear bwd, 8 final maps in one launch", "hbm", (8 * px + lowpx) * 4, timed_graph(mb)))
+    del lows, his
     # V1 reverse attention scale on the three backbone features (bf16)
     for c, s in ((512, 8), (1024, 16), (2048, 32)):
         h = S // s
@@ -181,8 +258,8 @@ def kernel_table(P, dev, B, S, hbm, tflops):
 
         def ra():
             j = rot() % n
-            P._lib.check(lib.pv2_ra_v1_scale_fwd(xs[j].data_ptr(), crop.data_ptr(), ys[j].data_ptr(), B, c, h * h, 1, st), "ra")
-        rows.append((f"ra_v1_scale fwd C={c} {h}^2 bf16", "hbm", 2 * B * c * h * h * 2 + B * h * h * 4, timed(ra, 50)))
+            P._lib.check(lib.pv2_ra_v1_scale_fwd(xs[j].data_ptr(), crop.data_ptr(), ys[j].data_ptr(), B, c, h * h, 1, cur()), "ra")
+        rows.append((f"ra_v1_scale fwd C={c} {h}^2 bf16", "hbm", 2 * B * c * h * h * 2 + B * h * h * 4, timed_graph(ra)))
         del xs, ys
     out = []
     for name, bound, work, ms in rows:
@@ -204,7 +281,7 @@ def kernel_table(P, dev, B, S, hbm, tflops):
         def cv():
             eng.conv(acts[rot() % n], [conv])
         cv()
-        ms = timed(cv, 50)
+        ms = timed_graph(cv)
         fl = 2.0 * B * hw * hw * cout * cin * k * k
         out.append({"kernel": f"conv_fwd {label} M={B * hw * hw} N={cout} K={cin * k * k}", "bound": "tensor", "flops": fl, "us": ms * 1e3,
                     "achieved_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tflops})

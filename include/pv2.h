@@ -73,6 +73,14 @@ int pv2_bilinear_fwd(const void* in, void* out, int planes, int ih, int iw, int 
 int pv2_bilinear_bwd(const void* dout, void* din, int planes, int ih, int iw, int oh, int ow,
                      float rh, float rw, int align_corners, int dtype, void* stream);
 
+/* Up to PV2_MAX_MAPS maps resized to the SAME output size by one launch (the 8 final logit maps of PraNet_V2.forward,
+ * pranet.py:349-350,370-371,392-393,414-415; EMCAD/lib/networks.py:116-123): in/out (dout/din), ih, iw, rh, rw are HOST arrays. */
+#define PV2_MAX_MAPS 8
+int pv2_bilinear_multi_fwd(const void* const* in, void* const* out, const int* ih, const int* iw, const float* rh, const float* rw,
+                           int nmaps, int planes, int oh, int ow, int align_corners, int dtype, void* stream);
+int pv2_bilinear_multi_bwd(const void* const* dout, void* const* din, const int* ih, const int* iw, const float* rh, const float* rw,
+                           int nmaps, int planes, int oh, int ow, int align_corners, int dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * DSRA attention fusion -- binary_seg/lib/pranet.py:365-368,385-389,407-411;
  * EMCAD/lib/decoders.py:477,500,523; MERIT/lib/decoders.py:369-372; MIST/lib/MIST.py:431,440,449

@@ -28,6 +28,8 @@ _SIGS = {
     "pv2_structure_loss_bwd": (_i, [c_void_pp, c_void_pp, _p, _p, _p, c_void_pp, c_void_pp, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "pv2_bilinear_fwd": (_i, [_p, _p] + [_i] * 5 + [_f, _f, _i, _i, _p]),
     "pv2_bilinear_bwd": (_i, [_p, _p] + [_i] * 5 + [_f, _f, _i, _i, _p]),
+    "pv2_bilinear_multi_fwd": (_i, [c_void_pp, c_void_pp, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)] + [_i] * 6 + [_p]),
+    "pv2_bilinear_multi_bwd": (_i, [c_void_pp, c_void_pp, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)] + [_i] * 6 + [_p]),
     "pv2_dsra_fuse_fwd": (_i, [_p] * 4 + [_i] * 6 + [_f, _f, _i, _p]),
     "pv2_dsra_fuse_bwd": (_i, [_p] * 6 + [_i] * 6 + [_f, _f, _i, _p]),
     "pv2_ra_v1_scale_fwd": (_i, [_p] * 3 + [_i] * 4 + [_p]),

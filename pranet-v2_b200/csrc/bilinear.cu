@@ -19,12 +19,25 @@ namespace {
 constexpr int FWD_THREADS = 256;
 constexpr int BAND = 16;  // output rows per CTA (fwd)
 
+// up to PV2_MAX_MAPS maps of the same output size in ONE launch (grid.z = map): the 8 final logit maps of a step are
+// 8 x 8 MB at B=16 -- far too little per launch to fill HBM, so they share a launch.
+struct MultiMaps {
+    const void* in[PV2_MAX_MAPS];
+    void* out[PV2_MAX_MAPS];
+    int ih[PV2_MAX_MAPS], iw[PV2_MAX_MAPS], max_rows[PV2_MAX_MAPS];
+    float rh[PV2_MAX_MAPS], rw[PV2_MAX_MAPS];
+};
+
 template <typename T>
 __global__ void __launch_bounds__(FWD_THREADS)
-bilinear_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, int ih, int iw, int oh, int ow,
-                    float rh, float rw, int ac, int max_src_rows) {
+bilinear_fwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac) {
     pv2::pdl_prologue();
     extern __shared__ float srows[];  // [nrows][iw]
+    const int map = blockIdx.z;
+    const T* __restrict__ in = reinterpret_cast<const T*>(mm.in[map]);
+    T* __restrict__ out = reinterpret_cast<T*>(mm.out[map]);
+    const int ih = mm.ih[map], iw = mm.iw[map], max_src_rows = mm.max_rows[map];
+    const float rh = mm.rh[map], rw = mm.rw[map];
     const int plane = blockIdx.y;
     const int oy0 = blockIdx.x * BAND, oy1 = min(oy0 + BAND, oh);
     const int r0 = bilinear_tap(oy0, ih, rh, ac).i0;
@@ -88,24 +101,69 @@ __device__ __forceinline__ void touch_window(int i, int out_size, float ratio, b
 }
 
 constexpr int BWD_THREADS = 256;
+constexpr int BWD_MAX_WIN = 96;      // output rows one input row can touch: 2*scale + a few (scale <= 32 + slack)
 
+// CTA = (input row, plane, map).  Pass 1: the <= 2s+2 output rows that touch this input row are folded into one row of
+// column sums; a thread owns 4 consecutive columns (16-byte loads) and the row window is split over the thread groups
+// (partials in shared memory, fixed order).  Pass 2 folds the columns.  No atomics, deterministic.
 template <typename T>
 __global__ void __launch_bounds__(BWD_THREADS)
-bilinear_bwd_kernel(const T* __restrict__ dout, T* __restrict__ din, int ih, int iw, int oh, int ow,
-                    float rh, float rw, int ac) {
+bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int rgroups) {
     pv2::pdl_prologue();
-    extern __shared__ float colsum[];  // [ow]
+    extern __shared__ float colsum[];  // [rgroups][ow4*4]
+    __shared__ float wts[BWD_MAX_WIN];
+    const int map = blockIdx.z;
+    // for the backward, `in` is the low-resolution gradient being produced and `out` the upstream gradient
+    const T* __restrict__ dout = reinterpret_cast<const T*>(mm.out[map]);
+    T* __restrict__ din = reinterpret_cast<T*>(const_cast<void*>(mm.in[map]));
+    const int ih = mm.ih[map], iw = mm.iw[map];
+    const float rh = mm.rh[map], rw = mm.rw[map];
     const int plane = blockIdx.y, iy = blockIdx.x;
+    if (iy >= ih) return;
     const T* g = dout + (size_t)plane * oh * ow;
     int lo, hi;
     touch_window(iy, oh, rh, ac, lo, hi);
-    for (int ox = threadIdx.x; ox < ow; ox += BWD_THREADS) {
-        float acc = 0.0f;
-        for (int oy = lo; oy <= hi; ++oy) {
-            const float wy = tap_weight(oy, iy, ih, rh, ac);
-            if (wy != 0.0f) acc += wy * to_f(g[(size_t)oy * ow + ox]);
+    const int nwin = hi - lo + 1;
+    const int ow4 = (ow + 3) >> 2, pitch = ow4 * 4;
+    const bool vec_ok = (ow & 3) == 0;
+    if (nwin <= BWD_MAX_WIN) {
+        for (int j = threadIdx.x; j < nwin; j += BWD_THREADS) wts[j] = tap_weight(lo + j, iy, ih, rh, ac);
+        __syncthreads();
+        const int q = threadIdx.x % ow4, rg = threadIdx.x / ow4;
+        if (rg < rgroups) {
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            const int ox = q * 4;
+            if (vec_ok) {
+#pragma unroll 4
+                for (int j = rg; j < nwin; j += rgroups) {
+                    const float wy = wts[j];
+                    const float4 v = load4<T>(g + (size_t)(lo + j) * ow + ox);
+                    a0 = fmaf(wy, v.x, a0); a1 = fmaf(wy, v.y, a1); a2 = fmaf(wy, v.z, a2); a3 = fmaf(wy, v.w, a3);
+                }
+            } else {
+                for (int j = rg; j < nwin; j += rgroups) {
+                    const float wy = wts[j];
+                    const T* row = g + (size_t)(lo + j) * ow;
+                    if (ox < ow) a0 = fmaf(wy, to_f(row[ox]), a0);
+                    if (ox + 1 < ow) a1 = fmaf(wy, to_f(row[ox + 1]), a1);
+                    if (ox + 2 < ow) a2 = fmaf(wy, to_f(row[ox + 2]), a2);
+                    if (ox + 3 < ow) a3 = fmaf(wy, to_f(row[ox + 3]), a3);
+                }
+            }
+            float* cs = colsum + rg * pitch + ox;
+            cs[0] = a0; cs[1] = a1; cs[2] = a2; cs[3] = a3;
         }
-        colsum[ox] = acc;
+    } else {   // very large scale factors: one column per thread, weights on the fly
+        for (int ox = threadIdx.x; ox < pitch; ox += BWD_THREADS) {
+            float acc = 0.0f;
+            if (ox < ow)
+                for (int oy = lo; oy <= hi; ++oy) {
+                    const float wy = tap_weight(oy, iy, ih, rh, ac);
+                    if (wy != 0.0f) acc += wy * to_f(g[(size_t)oy * ow + ox]);
+                }
+            colsum[ox] = acc;
+        }
+        rgroups = 1;
     }
     __syncthreads();
     T* d = din + ((size_t)plane * ih + iy) * iw;
@@ -113,7 +171,11 @@ bilinear_bwd_kernel(const T* __restrict__ dout, T* __restrict__ din, int ih, int
         int xl, xh;
         touch_window(ix, ow, rw, ac, xl, xh);
         float acc = 0.0f;
-        for (int ox = xl; ox <= xh; ++ox) acc += tap_weight(ox, ix, iw, rw, ac) * colsum[ox];
+        for (int ox = xl; ox <= xh; ++ox) {
+            float cs = colsum[ox];
+            for (int r = 1; r < rgroups; ++r) cs += colsum[r * pitch + ox];
+            acc += tap_weight(ox, ix, iw, rw, ac) * cs;
+        }
         d[ix] = from_f<T>(acc);
     }
 }
@@ -131,37 +193,77 @@ int check(const void* a, const void* b, int planes, int ih, int iw, int oh, int 
 
 using namespace pv2;
 
+static int launch_fwd(const MultiMaps& mm, int nmaps, int planes, int oh, int ow, int align_corners, int dtype, size_t smem, cudaStream_t st) {
+    dim3 grid((oh + BAND - 1) / BAND, planes, nmaps);
+    if (dtype == PV2_F32) pv2::launch(bilinear_fwd_kernel<float>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners);
+    else pv2::launch(bilinear_fwd_kernel<__nv_bfloat16>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners);
+    PV2_LAUNCH_CHECK("bilinear_fwd");
+    return 0;
+}
+
+static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int max_ih, int oh, int ow, int align_corners, int dtype, cudaStream_t st) {
+    const int ow4 = (ow + 3) / 4;
+    PV2_CHECK(ow4 <= BWD_THREADS, "bilinear_bwd: output width %d too large", ow);
+    int rgroups = BWD_THREADS / ow4;
+    if (rgroups > 8) rgroups = 8;
+    const size_t smem = (size_t)rgroups * ow4 * 4 * sizeof(float);
+    dim3 grid(max_ih, planes, nmaps);
+    if (dtype == PV2_F32) pv2::launch(bilinear_bwd_kernel<float>, grid, BWD_THREADS, smem, st, mm, oh, ow, align_corners, rgroups);
+    else pv2::launch(bilinear_bwd_kernel<__nv_bfloat16>, grid, BWD_THREADS, smem, st, mm, oh, ow, align_corners, rgroups);
+    PV2_LAUNCH_CHECK("bilinear_bwd");
+    return 0;
+}
+
+// rows of the source a BAND of output rows can touch, if they fit in 48 KB of shared memory (else 0: read through L1/L2)
+static int staged_rows(int ih, int iw, float rh) {
+    int want = (int)(BAND * (double)rh) + 4;
+    if (want > ih) want = ih;
+    const int cap = (48 * 1024) / (iw * 4);
+    return want <= cap ? want : 0;
+}
+
 extern "C" int pv2_bilinear_fwd(const void* in, void* out, int planes, int ih, int iw, int oh, int ow,
                                 float rh, float rw, int align_corners, int dtype, void* stream) {
     if (int e = check(in, out, planes, ih, iw, oh, ow, dtype, "bilinear_fwd")) return e;
-    cudaStream_t st = (cudaStream_t)stream;
-    // source rows a band can touch: BAND*ratio + 3, capped by what fits in 48 KB of shared memory
-    int want = (int)(BAND * (double)rh) + 4;
-    if (want > ih) want = ih;
-    int cap = (48 * 1024) / (iw * 4);
-    int max_rows = want <= cap ? want : 0;
-    size_t smem = (size_t)max_rows * iw * 4;
-    dim3 grid((oh + BAND - 1) / BAND, planes);
-    if (dtype == PV2_F32)
-        pv2::launch(bilinear_fwd_kernel<float>, grid, FWD_THREADS, smem, st, (const float*)in, (float*)out, ih, iw, oh, ow, rh, rw, align_corners, max_rows);
-    else
-        pv2::launch(bilinear_fwd_kernel<__nv_bfloat16>, grid, FWD_THREADS, smem, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, ih, iw, oh, ow, rh, rw, align_corners, max_rows);
-    PV2_LAUNCH_CHECK("bilinear_fwd");
-    return 0;
+    MultiMaps mm = {};
+    mm.in[0] = in; mm.out[0] = out; mm.ih[0] = ih; mm.iw[0] = iw; mm.rh[0] = rh; mm.rw[0] = rw;
+    mm.max_rows[0] = staged_rows(ih, iw, rh);
+    return launch_fwd(mm, 1, planes, oh, ow, align_corners, dtype, (size_t)mm.max_rows[0] * iw * 4, (cudaStream_t)stream);
 }
 
 extern "C" int pv2_bilinear_bwd(const void* dout, void* din, int planes, int ih, int iw, int oh, int ow,
                                 float rh, float rw, int align_corners, int dtype, void* stream) {
     if (int e = check(dout, din, planes, ih, iw, oh, ow, dtype, "bilinear_bwd")) return e;
-    PV2_CHECK((size_t)ow * 4 <= 48 * 1024, "bilinear_bwd: output width %d too large", ow);
     PV2_CHECK(ih <= 65535 * 32, "bilinear_bwd: input height %d too large", ih);
-    cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid(ih, planes);
-    size_t smem = (size_t)ow * 4;
-    if (dtype == PV2_F32)
-        pv2::launch(bilinear_bwd_kernel<float>, grid, BWD_THREADS, smem, st, (const float*)dout, (float*)din, ih, iw, oh, ow, rh, rw, align_corners);
-    else
-        pv2::launch(bilinear_bwd_kernel<__nv_bfloat16>, grid, BWD_THREADS, smem, st, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, ih, iw, oh, ow, rh, rw, align_corners);
-    PV2_LAUNCH_CHECK("bilinear_bwd");
-    return 0;
+    MultiMaps mm = {};
+    mm.in[0] = din; mm.out[0] = const_cast<void*>(dout); mm.ih[0] = ih; mm.iw[0] = iw; mm.rh[0] = rh; mm.rw[0] = rw;
+    return launch_bwd(mm, 1, planes, ih, oh, ow, align_corners, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int pv2_bilinear_multi_fwd(const void* const* in, void* const* out, const int* ih, const int* iw, const float* rh, const float* rw,
+                                      int nmaps, int planes, int oh, int ow, int align_corners, int dtype, void* stream) {
+    PV2_CHECK(in && out && ih && iw && rh && rw && nmaps >= 1 && nmaps <= PV2_MAX_MAPS, "bilinear_multi_fwd: 1..%d maps expected", PV2_MAX_MAPS);
+    MultiMaps mm = {};
+    size_t smem = 0;
+    for (int i = 0; i < nmaps; ++i) {
+        if (int e = check(in[i], out[i], planes, ih[i], iw[i], oh, ow, dtype, "bilinear_multi_fwd")) return e;
+        mm.in[i] = in[i]; mm.out[i] = out[i]; mm.ih[i] = ih[i]; mm.iw[i] = iw[i]; mm.rh[i] = rh[i]; mm.rw[i] = rw[i];
+        mm.max_rows[i] = staged_rows(ih[i], iw[i], rh[i]);
+        const size_t b = (size_t)mm.max_rows[i] * iw[i] * 4;
+        if (b > smem) smem = b;
+    }
+    return launch_fwd(mm, nmaps, planes, oh, ow, align_corners, dtype, smem, (cudaStream_t)stream);
+}
+
+extern "C" int pv2_bilinear_multi_bwd(const void* const* dout, void* const* din, const int* ih, const int* iw, const float* rh, const float* rw,
+                                      int nmaps, int planes, int oh, int ow, int align_corners, int dtype, void* stream) {
+    PV2_CHECK(dout && din && ih && iw && rh && rw && nmaps >= 1 && nmaps <= PV2_MAX_MAPS, "bilinear_multi_bwd: 1..%d maps expected", PV2_MAX_MAPS);
+    MultiMaps mm = {};
+    int max_ih = 0;
+    for (int i = 0; i < nmaps; ++i) {
+        if (int e = check(dout[i], din[i], planes, ih[i], iw[i], oh, ow, dtype, "bilinear_multi_bwd")) return e;
+        mm.in[i] = din[i]; mm.out[i] = const_cast<void*>(dout[i]); mm.ih[i] = ih[i]; mm.iw[i] = iw[i]; mm.rh[i] = rh[i]; mm.rw[i] = rw[i];
+        if (ih[i] > max_ih) max_ih = ih[i];
+    }
+    return launch_bwd(mm, nmaps, planes, max_ih, oh, ow, align_corners, dtype, (cudaStream_t)stream);
 }

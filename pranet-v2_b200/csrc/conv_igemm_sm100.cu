@@ -237,28 +237,33 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             const int g = tile_m / a.G;
             const int t0 = g * a.G, t1 = min(t0 + a.G, a.m_tiles);
             if (ticket_last(cnt + g, (unsigned)(t1 - t0), et == 0, &s_flag, 1, 128)) {
+                // group fold: one thread per channel, the group's tile partials fetched as one batch of independent loads
                 float* gpart = bn.f.part + (size_t)a.m_tiles * a.Cout * 2;
                 for (int c = et; c < a.BN; c += 128) {
                     const int cg = n0 + c;
                     if (cg >= a.Cout) continue;
-                    float n = 0.0f, mu = 0.0f, M2 = 0.0f;
-                    for (int t = t0; t < t1; ++t) {
+                    float n, mu, M2;
+                    pooled_stats(t0, t1, [&](int t, float& pn, float& pmu, float& pm2) {
                         const long long rem = a.M - (long long)t * BM;
                         const float* p = bn.f.part + ((size_t)t * a.Cout + cg) * 2;
-                        chan_combine(n, mu, M2, rem > BM ? (float)BM : (float)rem, __ldcg(p), __ldcg(p + 1));
+                        pn = rem > BM ? (float)BM : (float)rem; pmu = __ldcg(p); pm2 = __ldcg(p + 1);
+                    }, n, mu, M2);
+                    if (a.ngroups == 1) {                      // few tiles: this fold is already the final one
+                        bn_write_channel(bn.f, cg, n, mu, M2);
+                    } else {
+                        float* gp = gpart + ((size_t)g * a.Cout + cg) * 3;
+                        gp[0] = n; gp[1] = mu; gp[2] = M2;
                     }
-                    float* gp = gpart + ((size_t)g * a.Cout + cg) * 3;
-                    gp[0] = n; gp[1] = mu; gp[2] = M2;
                 }
-                if (ticket_last(cnt + a.ngroups, (unsigned)a.ngroups, et == 0, &s_flag, 1, 128)) {
+                if (a.ngroups > 1 && ticket_last(cnt + a.ngroups, (unsigned)a.ngroups, et == 0, &s_flag, 1, 128)) {
                     for (int c = et; c < a.BN; c += 128) {
                         const int cg = n0 + c;
                         if (cg >= a.Cout) continue;
-                        float n = 0.0f, mu = 0.0f, M2 = 0.0f;
-                        for (int gg = 0; gg < a.ngroups; ++gg) {
+                        float n, mu, M2;
+                        pooled_stats(0, a.ngroups, [&](int gg, float& pn, float& pmu, float& pm2) {
                             const float* gp = gpart + ((size_t)gg * a.Cout + cg) * 3;
-                            chan_combine(n, mu, M2, __ldcg(gp), __ldcg(gp + 1), __ldcg(gp + 2));
-                        }
+                            pn = __ldcg(gp); pmu = __ldcg(gp + 1); pm2 = __ldcg(gp + 2);
+                        }, n, mu, M2);
                         bn_write_channel(bn.f, cg, n, mu, M2);
                     }
                 }
@@ -540,7 +545,10 @@ int common_checks(const char* who, int kind, int nterms, int N, int H, int W, in
 
 using namespace pv2;
 
-extern "C" int pv2_conv_fuses_bn_stats(int splits, int out_mode) { return (use_im2col() && splits == 1 && out_mode == 0) ? 1 : 0; }
+extern "C" int pv2_conv_fuses_bn_stats(int splits, int out_mode) {
+    static const bool off = [] { const char* e = getenv("PV2_NO_FUSED_STATS"); return e && e[0] == '1'; }();   // A/B switch for profiling
+    return (!off && use_im2col() && splits == 1 && out_mode == 0) ? 1 : 0;
+}
 
 extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
     const int KC = kind == PV2_BF16 ? 64 : 32;

@@ -618,7 +618,7 @@ template <int KIND>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce4_kernel(const BwdArgs b, const Reduce4Plan pl) {
     pv2::pdl_prologue();
-    __shared__ float sh[256 * 16];
+    __shared__ float sh[256 * 17];     // pitch 17: conflict-free writes (thread-major) and reads (value-major)
     __shared__ int s_flag;
     const int C = b.f.C, C4 = C >> 2;
     const int tid = threadIdx.x;
@@ -641,27 +641,27 @@ bn_bwd_reduce4_kernel(const BwdArgs b, const Reduce4Plan pl) {
         }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) sh[tid * 16 + i] = acc[i];
+    for (int i = 0; i < 16; ++i) sh[tid * 17 + i] = acc[i];
     __syncthreads();
     // (quad, k) -> sum over the RP row lanes in order; k = 4*which_sum + channel
     for (int idx = tid; idx < C4 * 16; idx += 256) {
         const int qd = idx >> 4, k = idx & 15;
         float t = 0.0f;
-        for (int j = 0; j < pl.RP; ++j) t += sh[(j * C4 + qd) * 16 + k];
+        for (int j = 0; j < pl.RP; ++j) t += sh[(j * C4 + qd) * 17 + k];
         b.part[((long long)blockIdx.x * 4 + (k >> 2)) * C + (qd << 2) + (k & 3)] = t;
     }
     const int g = blockIdx.x / pl.G;
     const int b0 = g * pl.G, b1 = min(b0 + pl.G, pl.nblk);
     if (!ticket_last(pl.counters + g, (unsigned)(b1 - b0), tid == 0, &s_flag, 1, 256)) return;
-    for (int i = tid; i < 4 * C; i += 256) {
-        float t = 0.0f;
-        for (int bb = b0; bb < b1; ++bb) t += __ldcg(b.part + (long long)bb * 4 * C + i);
-        pl.gpart[(long long)g * 4 * C + i] = t;
+    const int nv = b.f.combine ? 4 * C : 2 * C;       // sums 2, 3 belong to the second source
+    const bool single = pl.ngroups == 1;              // few row blocks: the group fold is already the final one
+    if (!single) {
+        for (int i = tid; i < nv; i += 256)           // one thread per value, the group's row-block partials loaded as one batch
+            pl.gpart[(long long)g * 4 * C + i] = fold_sum(b.part + i, 4LL * C, b0, b1);
+        if (!ticket_last(pl.counters + pl.ngroups, (unsigned)pl.ngroups, tid == 0, &s_flag, 1, 256)) return;
     }
-    if (!ticket_last(pl.counters + pl.ngroups, (unsigned)pl.ngroups, tid == 0, &s_flag, 1, 256)) return;
-    for (int i = tid; i < 4 * C; i += 256) {
-        float t = 0.0f;
-        for (int gg = 0; gg < pl.ngroups; ++gg) t += __ldcg(pl.gpart + (long long)gg * 4 * C + i);
+    for (int i = tid; i < nv; i += 256) {
+        const float t = single ? fold_sum(b.part + i, 4LL * C, b0, b1) : fold_sum(pl.gpart + i, 4LL * C, 0, pl.ngroups);
         pl.sums_out[i] = t;
         const int k = i / C, c = i - k * C;
         if (k == 0 && pl.db1) pl.db1[c] = t;

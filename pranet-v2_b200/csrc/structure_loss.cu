@@ -154,6 +154,7 @@ struct Layout {
     float* partials;     // [planes][chunks][4*MAX]
     uint16_t* wmap;
     int wt_tiles_x, wt_tiles, chunks;
+    int ft_tiles_x, ft_tiles;       // fused forward: 32 x 128 tiles
     size_t bytes;
 };
 inline Layout make_layout(void* ws, int planes, int H, int W) {
@@ -161,14 +162,18 @@ inline Layout make_layout(void* ws, int planes, int H, int W) {
     L.wt_tiles_x = (W + TW - 1) / TW;
     L.wt_tiles = L.wt_tiles_x * ((H + TH - 1) / TH);
     L.chunks = (H * W + CHUNK - 1) / CHUNK;
+    L.ft_tiles_x = (W + 127) / 128;
+    L.ft_tiles = L.ft_tiles_x * ((H + 31) / 32);
+    const int np = L.chunks > L.ft_tiles ? L.chunks : L.ft_tiles;      // partial slots: whichever forward runs
+    const int nw = L.wt_tiles > L.ft_tiles ? L.wt_tiles : L.ft_tiles;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     uint8_t* b = (uint8_t*)ws;
     L.ticket = (unsigned int*)(b + take(256));
     L.plane_sums = (float*)(b + take(sizeof(float) * (size_t)planes * NSUM));
     L.plane_loss = (float*)(b + take(sizeof(float) * (size_t)planes * PV2_MAX_SCALES));
-    L.wsum_part = (float*)(b + take(sizeof(float) * (size_t)planes * L.wt_tiles));
-    L.partials = (float*)(b + take(sizeof(float) * (size_t)planes * L.chunks * 4 * PV2_MAX_SCALES));
+    L.wsum_part = (float*)(b + take(sizeof(float) * (size_t)planes * nw));
+    L.partials = (float*)(b + take(sizeof(float) * (size_t)planes * np * 4 * PV2_MAX_SCALES));
     L.wmap = (uint16_t*)(b + take(sizeof(uint16_t) * (size_t)planes * H * W));
     L.bytes = off;
     return L;
@@ -253,6 +258,197 @@ structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
         for (int i = 0; i < 4 * NS; ++i) s[i] = 0.0f;
         for (int c = lane; c < chunks; c += 32) {
             const float* src = partials + ((size_t)pl * chunks + c) * (4 * PV2_MAX_SCALES);
+#pragma unroll
+            for (int i = 0; i < 4 * NS; ++i) s[i] += __ldcg(src + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 4 * NS; ++i) s[i] = warp_sum(s[i]);
+        if (lane == 0) {
+            float* ps = plane_sums + (size_t)pl * NSUM;
+            ps[0] = Wp;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                ps[1 + 4 * k + 0] = s[4 * k + 0]; ps[1 + 4 * k + 1] = s[4 * k + 1];
+                ps[1 + 4 * k + 2] = s[4 * k + 2]; ps[1 + 4 * k + 3] = s[4 * k + 3];
+                const float inter = s[4 * k + 2], uni = s[4 * k + 3];
+                plane_loss[(size_t)pl * PV2_MAX_SCALES + k] =
+                    s[4 * k + 0] / Wp + 1.0f - (inter + 1.0f) / (uni - inter + 1.0f) + 0.8f * s[4 * k + 1] / Wp;
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (warp == 0) {   // mean over planes, fixed order
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            float v = 0.0f;
+            for (int pl = lane; pl < planes; pl += 32) v += __ldcg(plane_loss + (size_t)pl * PV2_MAX_SCALES + k);
+            v = warp_sum(v);
+            if (lane == 0) loss[k] = v / (float)planes;
+        }
+        if (lane == 0) *ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2b. fused forward: boundary weight + loss sums in ONE pass (the path taken whenever rows are 16-byte vectorisable).
+// CTA = 32 x 128 pixel tile of one plane.  The mask tile with its 15-px halo is turned into a summed-area table in
+// shared memory (row prefix by warp scan while staging, column prefix by one thread per column), so the 31x31 box
+// sum of a pixel is 4 shared-memory reads; the weight is quantised exactly as the backward will read it, written to the
+// 16-bit map, and used immediately on the logits of that pixel, which stream through once (16-byte loads).  HBM bytes per
+// pixel: 4 (mask) + 8*NS (logits) read, 2 written.  The last CTA (ticket) folds the per-tile sums in a fixed order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FT_H = 32, FT_W = 128;
+constexpr int FS_H = FT_H + 2 * HALO + 1;      // 63 table rows: row 0 is the zero border of the summed-area table
+constexpr int FS_W = FT_W + 2 * HALO + 1;      // 159
+constexpr int FS_PITCH = 161;                  // odd: column walks and row scans are both bank-conflict free
+constexpr int FS_PER_LANE = 5;                 // 32 lanes x 5 = 160 >= 158 staged columns
+
+template <typename T, int NS>
+__global__ void __launch_bounds__(LS_THREADS, 3)
+structure_loss_fwd_fused_kernel(PtrPack pp, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
+                                uint16_t* __restrict__ wmap, int H, int W, int planes, int tiles_x, int tiles,
+                                float* __restrict__ partials, float* __restrict__ wsum_part, float* __restrict__ plane_sums,
+                                float* __restrict__ plane_loss, float* __restrict__ loss, unsigned int* __restrict__ ticket) {
+    pv2::pdl_prologue();
+    __shared__ float sat[FS_H * FS_PITCH];
+    __shared__ float red[LS_THREADS / 32][4 * NS + 1];
+    __shared__ bool is_last;
+    const int plane = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int y0 = (tile / tiles_x) * FT_H, x0 = (tile % tiles_x) * FT_W;
+    const int HW = H * W;
+    const size_t pbase = (size_t)plane * HW;
+    const float* mp = mask_fg + pbase;
+    // ---- stage + row prefix: warp = table row, lane = 5 consecutive columns ----
+    if (tid < FS_PITCH) sat[tid] = 0.0f;                       // row 0
+    for (int r = 1 + warp; r < FS_H; r += LS_THREADS / 32) {
+        const int gy = y0 - (HALO + 1) + r;
+        const bool row_ok = gy >= 0 && gy < H;
+        const float* src = mp + (size_t)(row_ok ? gy : 0) * W;
+        float v[FS_PER_LANE];
+        float run = 0.0f;
+#pragma unroll
+        for (int j = 0; j < FS_PER_LANE; ++j) {
+            const int c = 1 + lane * FS_PER_LANE + j;          // table column
+            const int gx = x0 - (HALO + 1) + c;
+            const float m = (row_ok && c < FS_W && gx >= 0 && gx < W) ? __ldg(src + gx) : 0.0f;
+            run += m;
+            v[j] = run;
+        }
+        float incl = run;                                      // inclusive scan of the lane totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const float base = incl - run;
+        float* row = sat + r * FS_PITCH;
+        if (lane == 0) row[0] = 0.0f;                          // column 0
+#pragma unroll
+        for (int j = 0; j < FS_PER_LANE; ++j) {
+            const int c = 1 + lane * FS_PER_LANE + j;
+            if (c < FS_W) row[c] = base + v[j];
+        }
+    }
+    __syncthreads();
+    // ---- column prefix: one thread per column ----
+    if (tid >= 1 && tid < FS_W) {
+        float accv = 0.0f;
+#pragma unroll 8
+        for (int r = 1; r < FS_H; ++r) {
+            accv += sat[r * FS_PITCH + tid];
+            sat[r * FS_PITCH + tid] = accv;
+        }
+    }
+    __syncthreads();
+    // ---- stream the tile: thread = 4 consecutive pixels of a row, warp = row ----
+    float acc[4 * NS];
+#pragma unroll
+    for (int i = 0; i < 4 * NS; ++i) acc[i] = 0.0f;
+    float wsum = 0.0f;
+    const int tx = lane * 4, gx = x0 + tx;
+    for (int ty = warp; ty < FT_H; ty += LS_THREADS / 32) {
+        const int gy = y0 + ty;
+        if (gy >= H || gx >= W) continue;                      // W % 4 == 0: a quad is inside or outside as a whole
+        const size_t p = pbase + (size_t)gy * W + gx;
+        Vec<float, 4> m, mb;
+        Vec<T, 4> x[NS], xb[NS];
+        m.load(mask_fg + p);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            x[k].load(reinterpret_cast<const T*>(pp.pred[k]) + p);
+            xb[k].load(reinterpret_cast<const T*>(pp.pred_bg[k]) + p);
+        }
+        if (mask_bg != nullptr) mb.load(mask_bg + p);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mb.v[j] = 1.0f - m.v[j];
+        }
+        // 31x31 box sums from the table: S[ty+31][tx+31+j] - S[ty][tx+31+j] - S[ty+31][tx+j] + S[ty][tx+j]
+        const float* s_lo = sat + ty * FS_PITCH + tx;
+        const float* s_hi = sat + (ty + KS) * FS_PITCH + tx;
+        float w[4];
+        uint32_t q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float box = (s_hi[KS + j] - s_lo[KS + j]) - (s_hi[j] - s_lo[j]);
+            const float d = fminf(fabsf(box * INV_AREA - m.v[j]), 1.0f);
+            q[j] = (uint32_t)__float2int_rn(d * WQ);
+            w[j] = weit_from_q(q[j]);
+            wsum += w[j];
+        }
+        *reinterpret_cast<uint2*>(wmap + p) = make_uint2(q[0] | (q[1] << 16), q[2] | (q[3] << 16));
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float xv = x[k].v[j], qv = xb[k].v[j], mv = m.v[j], wv = w[j];
+                const float e = fast_ex2(-fabsf(xv) * LOG2E), d = 1.0f + e;
+                const float inv = fast_rcp(d);
+                const float sig = xv >= 0.0f ? inv : e * inv;
+                const float bce = fmaf(-xv, mv, fmaxf(xv, 0.0f)) + fast_lg2(d) * LN2;
+                const float e2 = fast_ex2(-fabsf(qv) * LOG2E);
+                const float bce2 = fmaf(-qv, mb.v[j], fmaxf(qv, 0.0f)) + fast_lg2(1.0f + e2) * LN2;
+                const float sw = sig * wv;
+                acc[4 * k + 0] = fmaf(wv, bce, acc[4 * k + 0]);
+                acc[4 * k + 1] = fmaf(wv, bce2, acc[4 * k + 1]);
+                acc[4 * k + 2] = fmaf(sw, mv, acc[4 * k + 2]);
+                acc[4 * k + 3] = fmaf(mv, wv, acc[4 * k + 3] + sw);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * NS; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    wsum = warp_sum(wsum);
+    if (lane == 0) red[warp][4 * NS] = wsum;
+    __syncthreads();
+    if (tid <= 4 * NS) {
+        float v = 0.0f;
+#pragma unroll
+        for (int wi = 0; wi < LS_THREADS / 32; ++wi) v += red[wi][tid];
+        if (tid < 4 * NS) partials[((size_t)plane * tiles + tile) * (4 * PV2_MAX_SCALES) + tid] = v;
+        else wsum_part[(size_t)plane * tiles + tile] = v;
+    }
+    // ---- the last CTA to finish folds everything in a fixed order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(ticket, 1u) == (unsigned)(planes * tiles) - 1u);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int pl = warp; pl < planes; pl += LS_THREADS / 32) {
+        float Wp = 0.0f;
+        for (int t = lane; t < tiles; t += 32) Wp += __ldcg(wsum_part + (size_t)pl * tiles + t);
+        Wp = warp_sum(Wp);
+        float s[4 * NS];
+#pragma unroll
+        for (int i = 0; i < 4 * NS; ++i) s[i] = 0.0f;
+        for (int c = lane; c < tiles; c += 32) {
+            const float* src = partials + ((size_t)pl * tiles + c) * (4 * PV2_MAX_SCALES);
 #pragma unroll
             for (int i = 0; i < 4 * NS; ++i) s[i] += __ldcg(src + i);
         }
@@ -403,11 +599,27 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
     const Layout L = make_layout(workspace, planes, H, W);
     PtrPack pp = {};
     for (int k = 0; k < nscales; ++k) { pp.pred[k] = pred[k]; pp.pred_bg[k] = pred_bg[k]; }
+    const int HW = H * W;
+    const bool vec = can_vec(pp, nscales, mask_fg, mask_bg, HW, false);
+    static const bool no_fused = [] { const char* e = getenv("PV2_LOSS_TWO_PASS"); return e && e[0] == '1'; }();
+    if (vec && W % 4 == 0 && !no_fused) {      // one pass: boundary weight + loss sums
+        cudaError_t ce = cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), st);
+        PV2_CHECK(ce == cudaSuccess, "structure_loss_fwd: memset: %s", cudaGetErrorString(ce));
+        const dim3 fgrid(L.ft_tiles, planes);
+#define PV2_FUSED(TT, NSV) pv2::launch(structure_loss_fwd_fused_kernel<TT, NSV>, fgrid, LS_THREADS, 0, st, pp, mask_fg, mask_bg, L.wmap, H, W, planes, \
+                                       L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
+        if (logit_dtype == PV2_F32) {
+            switch (nscales) { case 1: PV2_FUSED(float, 1); break; case 2: PV2_FUSED(float, 2); break; case 3: PV2_FUSED(float, 3); break; default: PV2_FUSED(float, 4); break; }
+        } else {
+            switch (nscales) { case 1: PV2_FUSED(__nv_bfloat16, 1); break; case 2: PV2_FUSED(__nv_bfloat16, 2); break; case 3: PV2_FUSED(__nv_bfloat16, 3); break; default: PV2_FUSED(__nv_bfloat16, 4); break; }
+        }
+#undef PV2_FUSED
+        PV2_LAUNCH_CHECK("structure_loss_fwd_fused");
+        return 0;
+    }
     pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, st, mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
     PV2_LAUNCH_CHECK("boundary_weight");
-    const int HW = H * W;
     const dim3 grid(L.chunks, planes);
-    const bool vec = can_vec(pp, nscales, mask_fg, mask_bg, HW, false);
     if (logit_dtype == PV2_F32) {
         if (vec) launch_fwd<float, 4>(nscales, grid, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
         else launch_fwd<float, 1>(nscales, grid, st, pp, mask_fg, mask_bg, L, HW, planes, loss);

@@ -33,6 +33,7 @@ struct FoldPlan {       // host-computed: n partials in ngroups groups of G
 inline FoldPlan make_fold_plan(int n) {
     FoldPlan p;
     p.n = n;
+    if (n <= 16) { p.G = n < 1 ? 1 : n; p.ngroups = 1; return p; }     // one batch of loads (FOLD_BATCH): a single level is enough
     int g = 1;
     while (g * g < n) ++g;
     p.G = g;
@@ -48,6 +49,70 @@ __device__ __forceinline__ void chan_combine(float& n, float& mu, float& M2, flo
         M2 += M2b + d * d * n * nb / nt;
         n = nt;
     }
+}
+
+// The folds themselves must not be serial chains of L2 loads (each ~0.6 us): a warp folds one value at a time with its LANES
+// over the partials (one independent load per lane) and a fixed shuffle tree, so a fold level costs about one L2 latency.
+// The folds must not be serial chains of L2 loads (each ~0.6 us).  One THREAD folds one value; the partials it needs are
+// fetched in batches of independent (predicated) loads, so a fold level costs one or two L2 latencies whatever the count.
+constexpr int FOLD_BATCH = 16;
+
+// Pooled statistics of the partials (n_i, mean_i, M2_i), i in [b0, b1):
+//   N = sum n_i,  mean = sum n_i*mean_i / N,  M2 = sum [ M2_i + n_i*(mean_i - mean)^2 ]     (every term non-negative: stable)
+template <class LoadFn>
+__device__ __forceinline__ void pooled_stats(int b0, int b1, LoadFn load, float& N, float& mean, float& M2) {
+    float n[FOLD_BATCH], mu[FOLD_BATCH], m2[FOLD_BATCH];
+    if (b1 - b0 <= FOLD_BATCH) {          // the usual case: everything in registers, loaded once
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) {
+            n[j] = 0.0f; mu[j] = 0.0f; m2[j] = 0.0f;
+            if (b0 + j < b1) load(b0 + j, n[j], mu[j], m2[j]);
+        }
+        float S = 0.0f, Nn = 0.0f;
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) { S = fmaf(n[j], mu[j], S); Nn += n[j]; }
+        const float mean_ = Nn > 0.0f ? S / Nn : 0.0f;
+        float q = 0.0f;
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) { const float d = mu[j] - mean_; q += m2[j] + n[j] * d * d; }
+        N = Nn; mean = mean_; M2 = q;
+        return;
+    }
+    float S = 0.0f, Nn = 0.0f;
+    for (int b = b0; b < b1; b += FOLD_BATCH) {
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) {
+            n[j] = 0.0f; mu[j] = 0.0f; m2[j] = 0.0f;
+            if (b + j < b1) load(b + j, n[j], mu[j], m2[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) { S = fmaf(n[j], mu[j], S); Nn += n[j]; }
+    }
+    const float mean_ = Nn > 0.0f ? S / Nn : 0.0f;
+    float q = 0.0f;
+    for (int b = b0; b < b1; b += FOLD_BATCH) {
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) {
+            n[j] = 0.0f; mu[j] = 0.0f; m2[j] = 0.0f;
+            if (b + j < b1) load(b + j, n[j], mu[j], m2[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) { const float d = mu[j] - mean_; q += m2[j] + n[j] * d * d; }
+    }
+    N = Nn; mean = mean_; M2 = q;
+}
+
+// out = sum over b in [b0, b1) of src[b * stride] in index order, loads batched
+__device__ __forceinline__ float fold_sum(const float* src, long long stride, int b0, int b1) {
+    float t = 0.0f;
+    for (int b = b0; b < b1; b += FOLD_BATCH) {
+        float v[FOLD_BATCH];
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) v[j] = (b + j < b1) ? __ldcg(src + (long long)(b + j) * stride) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < FOLD_BATCH; ++j) t += v[j];
+    }
+    return t;
 }
 
 // Per-channel BatchNorm epilogue shared by the conv kernel's fused statistics and pv2_bn_stats_group.

@@ -216,6 +216,9 @@ class Engine:
             self.packed[self._gkey(convs)] = (w_f, w_d)
             o = 0
             for cv in convs:
+                if not cv.weight.is_contiguous():
+                    raise RuntimeError("pv2 conv engine: conv weights must be dense OIHW (these have channels_last strides); "
+                                       "convert only the backbone to channels_last, not the DSRA head")
                 descs.append((cv.weight.data_ptr(), w_f.data_ptr(), w_d.data_ptr() if w_d is not None else 0,
                               Cout * taps * Cin_p, Cin * taps * Cout_p, start,
                               cv.out_channels, Cin, KH, KW, Cin_p, 0, o, Cout_p, o, 0))
@@ -536,6 +539,47 @@ class Engine:
                 din = self.f32(B, Cc, ih, iw)
                 _lib.check(self.lib.pv2_bilinear_bwd(g.data_ptr(), din.data_ptr(), B * Cc, ih, iw, oh, ow, rh, rw, 0, PV2_F32, _stream()), "pv2_bilinear_bwd")
                 m.grads.append(din)
+            self.tape.append(bwd)
+        return res
+
+    def resize_multi(self, maps, scale_factors):
+        """The final upsamples of a forward (pranet.py:349-350,370-371,392-393,414-415): up to 8 maps resized to one output
+        size by ONE launch, and their 8 gradients pulled back by one launch -- a single 8 MB map cannot fill HBM."""
+        B, Cc = maps[0].t.shape[:2]
+        geo = []
+        for m, sf in zip(maps, scale_factors):
+            ih, iw = m.t.shape[-2:]
+            geo.append((ih, iw, int(math.floor(ih * sf)), int(math.floor(iw * sf)), _ratio(ih, int(math.floor(ih * sf)), False, sf),
+                        _ratio(iw, int(math.floor(iw * sf)), False, sf)))
+        oh, ow = geo[0][2], geo[0][3]
+        if len(maps) > 8 or any((g[2], g[3]) != (oh, ow) for g in geo) or any(tuple(m.t.shape[:2]) != (B, Cc) for m in maps):
+            return [self.resize(m, sf) for m, sf in zip(maps, scale_factors)]
+        outs = [self.f32(B, Cc, oh, ow) for _ in maps]
+        ihs, k1 = _lib.int_array([g[0] for g in geo])
+        iws, k2 = _lib.int_array([g[1] for g in geo])
+        rhs = (C.c_float * len(maps))(*[g[4] for g in geo])
+        rws = (C.c_float * len(maps))(*[g[5] for g in geo])
+        pin, k3 = _lib.ptr_array([m.t for m in maps])
+        pout, k4 = _lib.ptr_array(outs)
+        _lib.check(self.lib.pv2_bilinear_multi_fwd(pin, pout, ihs, iws, rhs, rws, len(maps), B * Cc, oh, ow, 0, PV2_F32, _stream()), "pv2_bilinear_multi_fwd")
+        res = [Map(o) for o in outs]
+        if self.need_grad:
+            def bwd():
+                gs = [r.grad() for r in res]
+                live = [i for i, g in enumerate(gs) if g is not None]
+                if not live:
+                    return
+                gl = [gs[i].contiguous().float() for i in live]
+                dins = [self.f32(B, Cc, geo[i][0], geo[i][1]) for i in live]
+                a1, h1 = _lib.int_array([geo[i][0] for i in live])
+                a2, h2 = _lib.int_array([geo[i][1] for i in live])
+                b1 = (C.c_float * len(live))(*[geo[i][4] for i in live])
+                b2 = (C.c_float * len(live))(*[geo[i][5] for i in live])
+                pg, h3 = _lib.ptr_array(gl)
+                pd, h4 = _lib.ptr_array(dins)
+                _lib.check(self.lib.pv2_bilinear_multi_bwd(pg, pd, a1, a2, b1, b2, len(live), B * Cc, oh, ow, 0, PV2_F32, _stream()), "pv2_bilinear_multi_bwd")
+                for i, d in zip(live, dins):
+                    maps[i].grads.append(d)
             self.tape.append(bwd)
         return res
 

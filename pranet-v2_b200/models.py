@@ -94,22 +94,21 @@ class _V2Mixin(_PraNetBase):
                 rfbs.append(rfb_run(eng, rfb, raw, 0))
                 stacks.append(eng.bn_apply((raw, 5 * c, ra1.conv.out_channels, ra1.bn, None)))       # no ReLU after conv1
             ra5_fg, ra5_bg = aggregation_run(eng, self.agg1, rfbs[2], rfbs[1], rfbs[0])
-            l5_fg, l5_bg = eng.resize(ra5_fg, 8 / sd), eng.resize(ra5_bg, 8 / sd)
             # DSRA3: the x0.25 resize of the coarse maps is fused into the fusion kernel
             t = self._stack(eng, 4, stacks[2], 4)
             fg4, bg4 = dual(eng, self.ra4_conv5_fg, self.ra4_conv5_bg, t)
             fg4 = eng.fuse(fg4, ra5_fg, ra5_bg, self.use_softmax, 0.25)
-            l4_fg, l4_bg = eng.resize(fg4, 32 / sd), eng.resize(bg4, 32 / sd)
             # DSRA2
             t = self._stack(eng, 3, stacks[1], 3)
             fg3, bg3 = dual(eng, self.ra3_conv4_fg, self.ra3_conv4_bg, t)
             fg3 = eng.fuse(fg3, fg4, bg4, self.use_softmax, 2)
-            l3_fg, l3_bg = eng.resize(fg3, 16 / sd), eng.resize(bg3, 16 / sd)
             # DSRA1
             t = self._stack(eng, 2, stacks[0], 3)
             fg2, bg2 = dual(eng, self.ra2_conv4_fg, self.ra2_conv4_bg, t)
             fg2 = eng.fuse(fg2, fg3, bg3, self.use_softmax, 2)
-            l2_fg, l2_bg = eng.resize(fg2, 8 / sd), eng.resize(bg2, 8 / sd)
+            # the eight final upsamples (x8, x16, x32, x8 for fg and bg; pranet.py:349-350,370-371,392-393,414-415): one launch
+            l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg = eng.resize_multi(
+                [fg2, fg3, fg4, ra5_fg, bg2, bg3, bg4, ra5_bg], [8 / sd, 16 / sd, 32 / sd, 8 / sd] * 2)
             return [l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg]
 
         from .heads import dual_heads_run as dual

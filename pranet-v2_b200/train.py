@@ -64,7 +64,10 @@ class TrainStep:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.model = model.to(self.device).train()
         if channels_last:
-            self.model = self.model.to(memory_format=torch.channels_last)
+            # the stock backbone only: the head's conv weights stay dense OIHW, which is what pv2_weight_pack reads
+            bb = getattr(self.model, "backbone", None) or getattr(self.model, "resnet", None)
+            if bb is not None:
+                bb.to(memory_format=torch.channels_last)
         for n, p in self.model.named_parameters():
             if n.startswith(_UNUSED_PREFIXES):
                 p.requires_grad_(False)

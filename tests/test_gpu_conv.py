@@ -135,3 +135,37 @@ def test_aggregation(precision, num_class):
         assert (o.cpu() - r).abs().max().item() <= tol * max(1.0, r.abs().max().item())
     for a, b in zip(xd, xr):
         assert _rel(a.grad.cpu(), b.grad) <= 5 * tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,H,W", [(16, 44, 44), (5, 40, 40), (3, 11, 11)])
+def test_fused_bn_statistics_many_tiles(precision, B, H, W):
+    """BatchNorm statistics produced by the conv epilogue + ticket fold (one and two fold levels, ragged last tile) against
+    torch's batch_norm on the same conv output: mean / biased var, running stats, and the BN backward sums."""
+    E.set_precision(precision)
+    m = BasicConv2d(64, 96, 3, padding=1)
+    sd = synth.synth_state_dict({"m." + kk: v for kk, v in m.state_dict().items()}, seed=33)
+    if precision == "bf16":
+        sd["m.conv.weight"] = sd["m.conv.weight"].bfloat16().float()
+    m.load_state_dict({kk[2:]: v for kk, v in sd.items()})
+    m = m.to(DEV).train()
+    x = torch.randn(B, 64, H, W, generator=torch.Generator().manual_seed(9))
+    if precision == "bf16":
+        x = x.bfloat16().float()
+    xd = x.to(DEV).requires_grad_(True)
+    y = m(xd, relu=True)
+    gout = torch.randn(y.shape, generator=torch.Generator().manual_seed(10))
+    y.backward(gout.to(DEV))
+    xr = x.clone().requires_grad_(True)
+    w = sd["m.conv.weight"].clone().requires_grad_(True)
+    gam, bet = sd["m.bn.weight"].clone().requires_grad_(True), sd["m.bn.bias"].clone().requires_grad_(True)
+    rm, rv = sd["m.bn.running_mean"].clone(), sd["m.bn.running_var"].clone()
+    ref = F.relu(F.batch_norm(F.conv2d(xr, w, padding=1), rm, rv, gam, bet, True, 0.1, 1e-5))
+    ref.backward(gout)
+    tol = TOL[precision]
+    assert _rel(y.detach().cpu(), ref.detach()) <= tol
+    assert _rel(m.bn.running_mean.cpu(), rm) <= tol and _rel(m.bn.running_var.cpu(), rv) <= tol
+    assert int(m.bn.num_batches_tracked) == int(sd["m.bn.num_batches_tracked"]) + 1
+    assert _rel(xd.grad.cpu(), xr.grad) <= 5 * tol
+    assert _rel(m.conv.weight.grad.cpu(), w.grad) <= 5 * tol
+    assert _rel(m.bn.weight.grad.cpu(), gam.grad) <= 5 * tol and _rel(m.bn.bias.grad.cpu(), bet.grad) <= 5 * tol

@@ -129,6 +129,13 @@ def test_train_step_graph_matches_eager():
     l2 = float(ts.step_device(x, gt))                      # replay from the same parameters
     assert abs(l2 - eager) <= 1e-5 * abs(eager), (l2, eager)
     assert l2 < l1                                         # and it trains
+    # channels_last is applied to the stock backbone only: the head's weights stay dense OIHW (what pv2_weight_pack reads)
+    assert all(p.is_contiguous() for p in ts.model.head_parameters())
+    bad = torch.nn.Conv2d(8, 8, 3, padding=1).to(DEV).to(memory_format=torch.channels_last)
+    from pranet_v2_b200 import engine as E
+    eng = E.Engine(torch.device(DEV), "bf16", False, False)
+    with pytest.raises(RuntimeError, match="dense OIHW"):
+        eng.conv(eng.new_act(1, 8, 8, 8), [bad])
 
 
 @pytest.mark.parametrize("name", list(G.MC_CASES))

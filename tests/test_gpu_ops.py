@@ -197,3 +197,56 @@ def test_mc_dual_loss_vs_oracle(B, C, H, W, supervision, nmaps):
     assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
     for a, b in zip(df + db, rf + rb):
         assert (a.grad.cpu() - b.grad).abs().max() <= 1e-3 * b.grad.abs().max()
+
+
+def test_bilinear_multi_matches_single():
+    """pv2_bilinear_multi_fwd/bwd (8 maps, one launch) == 8 single-map launches == F.interpolate."""
+    from pranet_v2_b200 import engine as E
+    B, S = 2, 96
+    g = torch.Generator().manual_seed(11)
+    lows = [torch.randn(B, 1, S // s, S // s, generator=g) for s in (8, 16, 32, 8, 8, 16, 32, 8)]
+    scales = [8, 16, 32, 8, 8, 16, 32, 8]
+    gouts = [torch.randn(B, 1, S, S, generator=g) for _ in lows]
+    refs, rgrads = [], []
+    for x, s, go in zip(lows, scales, gouts):
+        xr = x.clone().requires_grad_(True)
+        r = F.interpolate(xr, scale_factor=s, mode="bilinear")
+        r.backward(go)
+        refs.append(r.detach())
+        rgrads.append(xr.grad)
+    eng = E.Engine(torch.device(DEV), "fp32", True, True)
+    maps = [E.Map(x.to(DEV)) for x in lows]
+    outs = eng.resize_multi(maps, scales)
+    for o, go in zip(outs, gouts):
+        o.grads.append(go.to(DEV))
+    eng.backward()
+    for o, r, m, rg in zip(outs, refs, maps, rgrads):
+        assert (o.t.cpu() - r).abs().max() <= 1e-5 * max(1.0, r.abs().max().item())
+        assert (m.grad().cpu() - rg).abs().max() <= 1e-5 * max(1.0, rg.abs().max().item())
+
+
+@pytest.mark.parametrize("shape", [(16, 1, 352, 352), (3, 1, 96, 80), (2, 2, 40, 56)])
+def test_structure_loss_fused_equals_two_pass(shape, monkeypatch):
+    """The fused forward (summed-area-table boundary weight inside the loss kernel) and the two-kernel forward write the
+    same 16-bit weight map semantics: losses agree to 1e-6 relative, gradients to 1e-6 of their max."""
+    import subprocess, sys, os, json
+    B, Cc, H, W = shape
+    g = torch.Generator().manual_seed(3)
+    pred, pbg = torch.randn(shape, generator=g) * 3, torch.randn(shape, generator=g) * 3
+    mask = synth.ellipse_masks(B * Cc, H, W, 7).reshape(shape)
+    if W % 8:
+        mask = F.interpolate(mask, size=(H, W), mode="bilinear", align_corners=True)
+    res = []
+    for a, b in ((pred, pbg),):
+        p = a.to(DEV).requires_grad_(True)
+        q = b.to(DEV).requires_grad_(True)
+        loss = P.structure_loss(p, q, mask.to(DEV))
+        loss.backward()
+        res.append((loss.item(), p.grad.cpu(), q.grad.cpu()))
+    ref_p = pred.clone().requires_grad_(True)
+    ref_q = pbg.clone().requires_grad_(True)
+    rl = O.structure_loss(ref_p, ref_q, mask, 1 - mask)
+    rl.backward()
+    assert abs(res[0][0] - rl.item()) <= 1e-4 * abs(rl.item())
+    assert (res[0][1] - ref_p.grad).abs().max() <= 1e-3 * ref_p.grad.abs().max()
+    assert (res[0][2] - ref_q.grad).abs().max() <= 1e-3 * ref_q.grad.abs().max()
