@@ -52,33 +52,44 @@ bilinear_fwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
     T* dst = out + (size_t)plane * oh * ow;
     const int vec_per_row = (ow + 3) >> 2;
     const bool vec_ok = (ow & 3) == 0;
-    for (int it = threadIdx.x; it < (oy1 - oy0) * vec_per_row; it += FWD_THREADS) {
-        const int oy = oy0 + it / vec_per_row, ox = (it % vec_per_row) * 4;
-        const Tap ty = bilinear_tap(oy, ih, rh, ac);
-        float v[4];
+    // thread = one quad of 4 consecutive output columns (x taps computed once) x every rgroups-th row of the band
+    const bool wide = vec_per_row >= FWD_THREADS;              // more quads than threads: threads stride over the quads
+    const int rgroups = wide ? 1 : FWD_THREADS / vec_per_row;
+    const int rg = wide ? 0 : threadIdx.x / vec_per_row;
+    const int qstep = wide ? FWD_THREADS : vec_per_row;
+    for (int q = wide ? threadIdx.x : threadIdx.x % vec_per_row; rg < rgroups && q < vec_per_row; q += qstep) {
+        const int ox = q * 4;
+        int xi0[4], xi1[4];
+        float xw0[4], xw1[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int oxj = min(ox + j, ow - 1);
-            const Tap tx = bilinear_tap(oxj, iw, rw, ac);
-            float a, b, c, d;
+            const Tap tx = bilinear_tap(min(ox + j, ow - 1), iw, rw, ac);
+            xi0[j] = tx.i0; xi1[j] = tx.i1; xw0[j] = tx.w0; xw1[j] = tx.w1;
+        }
+        for (int oy = oy0 + rg; oy < oy1; oy += rgroups) {
+            const Tap ty = bilinear_tap(oy, ih, rh, ac);
+            float v[4];
             if (staged) {
                 const float* ra = srows + (ty.i0 - r0) * iw;
                 const float* rb = srows + (ty.i1 - r0) * iw;
-                a = ra[tx.i0]; b = ra[tx.i1]; c = rb[tx.i0]; d = rb[tx.i1];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = ty.w0 * (xw0[j] * ra[xi0[j]] + xw1[j] * ra[xi1[j]]) + ty.w1 * (xw0[j] * rb[xi0[j]] + xw1[j] * rb[xi1[j]]);
             } else {
                 const T* ra = src + (size_t)ty.i0 * iw;
                 const T* rb = src + (size_t)ty.i1 * iw;
-                a = to_f(ra[tx.i0]); b = to_f(ra[tx.i1]); c = to_f(rb[tx.i0]); d = to_f(rb[tx.i1]);
-            }
-            v[j] = ty.w0 * (tx.w0 * a + tx.w1 * b) + ty.w1 * (tx.w0 * c + tx.w1 * d);
-        }
-        T* o = dst + (size_t)oy * ow + ox;
-        if (vec_ok) {
-            store4<T>(o, make_float4(v[0], v[1], v[2], v[3]));
-        } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (ox + j < ow) o[j] = from_f<T>(v[j]);
+                for (int j = 0; j < 4; ++j)
+                    v[j] = ty.w0 * (xw0[j] * to_f(ra[xi0[j]]) + xw1[j] * to_f(ra[xi1[j]])) + ty.w1 * (xw0[j] * to_f(rb[xi0[j]]) + xw1[j] * to_f(rb[xi1[j]]));
+            }
+            T* o = dst + (size_t)oy * ow + ox;
+            if (vec_ok) {
+                store4<T>(o, make_float4(v[0], v[1], v[2], v[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ox + j < ow) o[j] = from_f<T>(v[j]);
+            }
         }
     }
 }
@@ -101,82 +112,101 @@ __device__ __forceinline__ void touch_window(int i, int out_size, float ratio, b
 }
 
 constexpr int BWD_THREADS = 256;
-constexpr int BWD_MAX_WIN = 96;      // output rows one input row can touch: 2*scale + a few (scale <= 32 + slack)
+constexpr int BWD_R = 4;             // input rows per CTA: neighbouring input rows share output rows, so (R+1)*s rows are read for R rows
+constexpr int BWD_MAX_WIN = 192;     // output rows a block of R input rows can touch: (R+1)*scale + a few (scale <= 32)
 
-// CTA = (input row, plane, map).  Pass 1: the <= 2s+2 output rows that touch this input row are folded into one row of
-// column sums; a thread owns 4 consecutive columns (16-byte loads) and the row window is split over the thread groups
-// (partials in shared memory, fixed order).  Pass 2 folds the columns.  No atomics, deterministic.
+// CTA = (block of BWD_R input rows, plane, map).  Pass 1: every output row the block touches is read ONCE (16-byte loads, a
+// thread owns 4 consecutive columns, the row window is split over `rgroups` thread groups) and folded into the R rows of column
+// sums with its tap weights; pass 2 folds the columns.  No atomics, deterministic.
 template <typename T>
 __global__ void __launch_bounds__(BWD_THREADS)
 bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int rgroups) {
     pv2::pdl_prologue();
-    extern __shared__ float colsum[];  // [rgroups][ow4*4]
-    __shared__ float wts[BWD_MAX_WIN];
+    extern __shared__ float colsum[];  // [BWD_R][rgroups][pitch]
+    __shared__ float wts[BWD_R][BWD_MAX_WIN];
     const int map = blockIdx.z;
     // for the backward, `in` is the low-resolution gradient being produced and `out` the upstream gradient
     const T* __restrict__ dout = reinterpret_cast<const T*>(mm.out[map]);
     T* __restrict__ din = reinterpret_cast<T*>(const_cast<void*>(mm.in[map]));
     const int ih = mm.ih[map], iw = mm.iw[map];
     const float rh = mm.rh[map], rw = mm.rw[map];
-    const int plane = blockIdx.y, iy = blockIdx.x;
-    if (iy >= ih) return;
+    // rows per CTA by scale, so that every CTA reads a similar number of output rows: x8 -> 4, x16 -> 2, x32 and beyond -> 1
+    const int scale = (oh + ih - 1) / ih;
+    const int R = scale <= 8 ? BWD_R : (scale <= 16 ? 2 : 1);
+    const int plane = blockIdx.y, iy0 = blockIdx.x * R;
+    if (iy0 >= ih) return;
+    const int nr = min(R, ih - iy0);
     const T* g = dout + (size_t)plane * oh * ow;
-    int lo, hi;
-    touch_window(iy, oh, rh, ac, lo, hi);
+    int lo, hi, lo2, hi2;
+    touch_window(iy0, oh, rh, ac, lo, hi2);
+    touch_window(iy0 + nr - 1, oh, rh, ac, lo2, hi);
     const int nwin = hi - lo + 1;
     const int ow4 = (ow + 3) >> 2, pitch = ow4 * 4;
     const bool vec_ok = (ow & 3) == 0;
     if (nwin <= BWD_MAX_WIN) {
-        for (int j = threadIdx.x; j < nwin; j += BWD_THREADS) wts[j] = tap_weight(lo + j, iy, ih, rh, ac);
+        for (int j = threadIdx.x; j < nwin * BWD_R; j += BWD_THREADS) {
+            const int r = j / nwin, jj = j - r * nwin;
+            wts[r][jj] = r < nr ? tap_weight(lo + jj, iy0 + r, ih, rh, ac) : 0.0f;
+        }
         __syncthreads();
         const int q = threadIdx.x % ow4, rg = threadIdx.x / ow4;
         if (rg < rgroups) {
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+            float acc[BWD_R][4];
+#pragma unroll
+            for (int r = 0; r < BWD_R; ++r) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; acc[r][3] = 0.0f; }
             const int ox = q * 4;
-            if (vec_ok) {
-#pragma unroll 4
-                for (int j = rg; j < nwin; j += rgroups) {
-                    const float wy = wts[j];
-                    const float4 v = load4<T>(g + (size_t)(lo + j) * ow + ox);
-                    a0 = fmaf(wy, v.x, a0); a1 = fmaf(wy, v.y, a1); a2 = fmaf(wy, v.z, a2); a3 = fmaf(wy, v.w, a3);
-                }
-            } else {
-                for (int j = rg; j < nwin; j += rgroups) {
-                    const float wy = wts[j];
+#pragma unroll 8
+            for (int j = rg; j < nwin; j += rgroups) {
+                float4 v;
+                if (vec_ok) {
+                    v = load4<T>(g + (size_t)(lo + j) * ow + ox);
+                } else {
                     const T* row = g + (size_t)(lo + j) * ow;
-                    if (ox < ow) a0 = fmaf(wy, to_f(row[ox]), a0);
-                    if (ox + 1 < ow) a1 = fmaf(wy, to_f(row[ox + 1]), a1);
-                    if (ox + 2 < ow) a2 = fmaf(wy, to_f(row[ox + 2]), a2);
-                    if (ox + 3 < ow) a3 = fmaf(wy, to_f(row[ox + 3]), a3);
+                    v.x = ox < ow ? to_f(row[ox]) : 0.0f;         v.y = ox + 1 < ow ? to_f(row[ox + 1]) : 0.0f;
+                    v.z = ox + 2 < ow ? to_f(row[ox + 2]) : 0.0f; v.w = ox + 3 < ow ? to_f(row[ox + 3]) : 0.0f;
+                }
+#pragma unroll
+                for (int r = 0; r < BWD_R; ++r) {
+                    const float wy = wts[r][j];
+                    acc[r][0] = fmaf(wy, v.x, acc[r][0]); acc[r][1] = fmaf(wy, v.y, acc[r][1]);
+                    acc[r][2] = fmaf(wy, v.z, acc[r][2]); acc[r][3] = fmaf(wy, v.w, acc[r][3]);
                 }
             }
-            float* cs = colsum + rg * pitch + ox;
-            cs[0] = a0; cs[1] = a1; cs[2] = a2; cs[3] = a3;
+#pragma unroll
+            for (int r = 0; r < BWD_R; ++r) {
+                float* cs = colsum + (r * rgroups + rg) * pitch + ox;
+                cs[0] = acc[r][0]; cs[1] = acc[r][1]; cs[2] = acc[r][2]; cs[3] = acc[r][3];
+            }
         }
     } else {   // very large scale factors: one column per thread, weights on the fly
-        for (int ox = threadIdx.x; ox < pitch; ox += BWD_THREADS) {
-            float acc = 0.0f;
-            if (ox < ow)
-                for (int oy = lo; oy <= hi; ++oy) {
-                    const float wy = tap_weight(oy, iy, ih, rh, ac);
-                    if (wy != 0.0f) acc += wy * to_f(g[(size_t)oy * ow + ox]);
-                }
-            colsum[ox] = acc;
+        for (int r = 0; r < nr; ++r) {
+            int rl, rh2;
+            touch_window(iy0 + r, oh, rh, ac, rl, rh2);
+            for (int ox = threadIdx.x; ox < pitch; ox += BWD_THREADS) {
+                float acc = 0.0f;
+                if (ox < ow)
+                    for (int oy = rl; oy <= rh2; ++oy) {
+                        const float wy = tap_weight(oy, iy0 + r, ih, rh, ac);
+                        if (wy != 0.0f) acc += wy * to_f(g[(size_t)oy * ow + ox]);
+                    }
+                colsum[r * pitch + ox] = acc;
+            }
         }
         rgroups = 1;
     }
     __syncthreads();
-    T* d = din + ((size_t)plane * ih + iy) * iw;
-    for (int ix = threadIdx.x; ix < iw; ix += BWD_THREADS) {
+    for (int it = threadIdx.x; it < nr * iw; it += BWD_THREADS) {
+        const int r = it / iw, ix = it - r * iw;
         int xl, xh;
         touch_window(ix, ow, rw, ac, xl, xh);
         float acc = 0.0f;
+        const float* base = colsum + r * rgroups * pitch;
         for (int ox = xl; ox <= xh; ++ox) {
-            float cs = colsum[ox];
-            for (int r = 1; r < rgroups; ++r) cs += colsum[r * pitch + ox];
+            float cs = base[ox];
+            for (int k = 1; k < rgroups; ++k) cs += base[k * pitch + ox];
             acc += tap_weight(ox, ix, iw, rw, ac) * cs;
         }
-        d[ix] = from_f<T>(acc);
+        din[((size_t)plane * ih + iy0 + r) * iw + ix] = from_f<T>(acc);
     }
 }
 
@@ -201,13 +231,21 @@ static int launch_fwd(const MultiMaps& mm, int nmaps, int planes, int oh, int ow
     return 0;
 }
 
-static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int max_ih, int oh, int ow, int align_corners, int dtype, cudaStream_t st) {
+// grid.x of the backward for one map: input rows / rows per CTA (same rule as in the kernel)
+static int bwd_row_blocks(int ih, int oh) {
+    const int scale = (oh + ih - 1) / ih;
+    const int R = scale <= 8 ? BWD_R : (scale <= 16 ? 2 : 1);
+    return (ih + R - 1) / R;
+}
+
+static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int row_blocks, int oh, int ow, int align_corners, int dtype, cudaStream_t st) {
     const int ow4 = (ow + 3) / 4;
     PV2_CHECK(ow4 <= BWD_THREADS, "bilinear_bwd: output width %d too large", ow);
     int rgroups = BWD_THREADS / ow4;
     if (rgroups > 8) rgroups = 8;
-    const size_t smem = (size_t)rgroups * ow4 * 4 * sizeof(float);
-    dim3 grid(max_ih, planes, nmaps);
+    const size_t smem = (size_t)BWD_R * rgroups * ow4 * 4 * sizeof(float);
+    PV2_CHECK(smem <= 48 * 1024, "bilinear_bwd: output width %d too large", ow);
+    dim3 grid(row_blocks, planes, nmaps);
     if (dtype == PV2_F32) pv2::launch(bilinear_bwd_kernel<float>, grid, BWD_THREADS, smem, st, mm, oh, ow, align_corners, rgroups);
     else pv2::launch(bilinear_bwd_kernel<__nv_bfloat16>, grid, BWD_THREADS, smem, st, mm, oh, ow, align_corners, rgroups);
     PV2_LAUNCH_CHECK("bilinear_bwd");
@@ -237,7 +275,7 @@ extern "C" int pv2_bilinear_bwd(const void* dout, void* din, int planes, int ih,
     PV2_CHECK(ih <= 65535 * 32, "bilinear_bwd: input height %d too large", ih);
     MultiMaps mm = {};
     mm.in[0] = din; mm.out[0] = const_cast<void*>(dout); mm.ih[0] = ih; mm.iw[0] = iw; mm.rh[0] = rh; mm.rw[0] = rw;
-    return launch_bwd(mm, 1, planes, ih, oh, ow, align_corners, dtype, (cudaStream_t)stream);
+    return launch_bwd(mm, 1, planes, bwd_row_blocks(ih, oh), oh, ow, align_corners, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int pv2_bilinear_multi_fwd(const void* const* in, void* const* out, const int* ih, const int* iw, const float* rh, const float* rw,
@@ -259,11 +297,12 @@ extern "C" int pv2_bilinear_multi_bwd(const void* const* dout, void* const* din,
                                       int nmaps, int planes, int oh, int ow, int align_corners, int dtype, void* stream) {
     PV2_CHECK(dout && din && ih && iw && rh && rw && nmaps >= 1 && nmaps <= PV2_MAX_MAPS, "bilinear_multi_bwd: 1..%d maps expected", PV2_MAX_MAPS);
     MultiMaps mm = {};
-    int max_ih = 0;
+    int max_blocks = 0;
     for (int i = 0; i < nmaps; ++i) {
         if (int e = check(dout[i], din[i], planes, ih[i], iw[i], oh, ow, dtype, "bilinear_multi_bwd")) return e;
         mm.in[i] = din[i]; mm.out[i] = const_cast<void*>(dout[i]); mm.ih[i] = ih[i]; mm.iw[i] = iw[i]; mm.rh[i] = rh[i]; mm.rw[i] = rw[i];
-        if (ih[i] > max_ih) max_ih = ih[i];
+        const int nb = bwd_row_blocks(ih[i], oh);
+        if (nb > max_blocks) max_blocks = nb;
     }
-    return launch_bwd(mm, nmaps, planes, max_ih, oh, ow, align_corners, dtype, (cudaStream_t)stream);
+    return launch_bwd(mm, nmaps, planes, max_blocks, oh, ow, align_corners, dtype, (cudaStream_t)stream);
 }

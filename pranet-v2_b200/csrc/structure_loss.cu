@@ -305,7 +305,7 @@ constexpr int FS_PITCH = 161;                  // odd: column walks and row scan
 constexpr int FS_PER_LANE = 5;                 // 32 lanes x 5 = 160 >= 158 staged columns
 
 template <typename T, int NS>
-__global__ void __launch_bounds__(LS_THREADS, 3)
+__global__ void __launch_bounds__(LS_THREADS, 4)
 structure_loss_fwd_fused_kernel(PtrPack pp, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
                                 uint16_t* __restrict__ wmap, int H, int W, int planes, int tiles_x, int tiles,
                                 float* __restrict__ partials, float* __restrict__ wsum_part, float* __restrict__ plane_sums,
@@ -322,20 +322,29 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const float* __restrict__ mask_fg, c
     const float* mp = mask_fg + pbase;
     // ---- stage + row prefix: warp = table row, lane = 5 consecutive columns ----
     if (tid < FS_PITCH) sat[tid] = 0.0f;                       // row 0
-    for (int r = 1 + warp; r < FS_H; r += LS_THREADS / 32) {
+    constexpr int ROWS_PW = (FS_H - 1 + LS_THREADS / 32 - 1) / (LS_THREADS / 32);   // 8 table rows per warp
+    float v[ROWS_PW][FS_PER_LANE];
+    // all global loads of this warp's rows first (independent), then the scans: one memory latency instead of eight
+#pragma unroll
+    for (int i = 0; i < ROWS_PW; ++i) {
+        const int r = 1 + warp + i * (LS_THREADS / 32);
         const int gy = y0 - (HALO + 1) + r;
-        const bool row_ok = gy >= 0 && gy < H;
+        const bool row_ok = r < FS_H && gy >= 0 && gy < H;
         const float* src = mp + (size_t)(row_ok ? gy : 0) * W;
-        float v[FS_PER_LANE];
-        float run = 0.0f;
 #pragma unroll
         for (int j = 0; j < FS_PER_LANE; ++j) {
             const int c = 1 + lane * FS_PER_LANE + j;          // table column
             const int gx = x0 - (HALO + 1) + c;
-            const float m = (row_ok && c < FS_W && gx >= 0 && gx < W) ? __ldg(src + gx) : 0.0f;
-            run += m;
-            v[j] = run;
+            v[i][j] = (row_ok && c < FS_W && gx >= 0 && gx < W) ? __ldg(src + gx) : 0.0f;
         }
+    }
+#pragma unroll
+    for (int i = 0; i < ROWS_PW; ++i) {
+        const int r = 1 + warp + i * (LS_THREADS / 32);
+        if (r >= FS_H) break;
+        float run = 0.0f;
+#pragma unroll
+        for (int j = 0; j < FS_PER_LANE; ++j) { run += v[i][j]; v[i][j] = run; }
         float incl = run;                                      // inclusive scan of the lane totals
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -348,18 +357,24 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const float* __restrict__ mask_fg, c
 #pragma unroll
         for (int j = 0; j < FS_PER_LANE; ++j) {
             const int c = 1 + lane * FS_PER_LANE + j;
-            if (c < FS_W) row[c] = base + v[j];
+            if (c < FS_W) row[c] = base + v[i][j];
         }
     }
     __syncthreads();
-    // ---- column prefix: one thread per column ----
-    if (tid >= 1 && tid < FS_W) {
-        float accv = 0.0f;
-#pragma unroll 8
-        for (int r = 1; r < FS_H; ++r) {
-            accv += sat[r * FS_PITCH + tid];
-            sat[r * FS_PITCH + tid] = accv;
+    // ---- column prefix: one warp per column, lanes over row pairs, shuffle scan (a serial walk would cost 62 dependent
+    //      shared-memory round trips) ----
+    for (int c = 1 + warp; c < FS_W; c += LS_THREADS / 32) {
+        const int r0 = 1 + 2 * lane;                           // rows r0, r0 + 1; 62 rows = 31 lanes
+        float a = 0.0f, b2 = 0.0f;
+        if (r0 < FS_H) { a = sat[r0 * FS_PITCH + c]; b2 = a + sat[(r0 + 1) * FS_PITCH + c]; }
+        float incl = b2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
+        const float base = incl - b2;
+        if (r0 < FS_H) { sat[r0 * FS_PITCH + c] = base + a; sat[(r0 + 1) * FS_PITCH + c] = base + b2; }
     }
     __syncthreads();
     // ---- stream the tile: thread = 4 consecutive pixels of a row, warp = row ----

@@ -38,8 +38,9 @@ assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.items
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
 
 
-def _ticket_counters(device):
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+def _ticket_counters(device, branch=0):
+    """One counter buffer per concurrent branch (stream): kernels that may run at the same time must not share tickets."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), branch)
     t = _COUNTERS.get(key)
     if t is None:
         t = torch.zeros(4096, dtype=torch.int32, device=device)
@@ -108,8 +109,67 @@ class Map:
         return g
 
 
+_SIDE_STREAMS = {}   # device index -> list of side streams for the parallel sections of a head
+MAX_BRANCHES = 12
+
+
+def _side_streams(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=device) for _ in range(MAX_BRANCHES)]
+    return _SIDE_STREAMS[idx]
+
+
+def streams_enabled() -> bool:
+    import os
+    return os.environ.get("PV2_STREAMS", "1") != "0"
+
+
+class _Tape(list):
+    """Backward tape: ('op', closure, branch) entries plus ('fork', n) / ('join', n) markers of the parallel sections."""
+
+    def __init__(self, eng):
+        super().__init__()
+        self.eng = eng
+
+    def append(self, fn):
+        list.append(self, ("op", fn, self.eng.cur))
+
+    def mark(self, kind, n):
+        list.append(self, (kind, n, 0))
+
+
+class _Branch:
+    def __init__(self, eng, i):
+        self.eng, self.i, self.ctx = eng, i, None
+
+    def __enter__(self):
+        self.eng.cur = self.i
+        if self.i > 0:
+            self.ctx = torch.cuda.stream(self.eng.side[self.i - 1])
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+        self.eng.cur = 0
+        return False
+
+
 class Engine:
+    """Parallel sections.  The head is many small dependent kernels (most launches are 16-242 CTAs and latency bound), but
+    its graph is wide: three pyramid levels, three RFB branches and a reverse-attention stack per level.  `fork(n)` /
+    `branch(i)` / `join()` run such independent chains on side streams (inside a CUDA-graph capture they become parallel
+    branches of the graph); the backward tape mirrors the structure (a forward join is a backward fork).  Discipline that
+    keeps the stream-ordered allocator safe without record_stream: the main stream idles between fork and join, every
+    section is joined before the next fork, and every buffer the engine allocates stays referenced until the pass ends."""
+
     def __init__(self, device, precision: str, training: bool, need_grad: bool, cache: dict = None):
+        self.cur = 0              # branch the ops being issued belong to (0 = main stream)
+        self.side = _side_streams(device) if streams_enabled() else None
+        self._open = 0            # branches of the open section
+        self._keep = []           # every buffer of this pass (see the class docstring)
         self.lib = _lib.load()
         self.cache = cache if cache is not None else {}
         self.groups_seen = []      # conv groups in call order (recorded on the first run, prepacked in one launch afterwards)
@@ -123,8 +183,46 @@ class Engine:
         self.op_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
         self.training = training
         self.need_grad = need_grad
-        self.tape = []
+        self.tape = _Tape(self)
         self.param_grads = {}     # id(param) -> grad tensor
+
+    # ---- parallel sections -----------------------------------------------------------------------------
+    def _fan_out(self, n):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for i in range(n):
+            self.side[i].wait_event(ev)
+
+    def _fan_in(self, n):
+        main = torch.cuda.current_stream()
+        for i in range(n):
+            ev = torch.cuda.Event()
+            ev.record(self.side[i])
+            main.wait_event(ev)
+
+    def fork(self, n):
+        """Open a section of n independent branches (branch indices 1..n); no-op when streams are disabled."""
+        if self.side is None:
+            return
+        if self._open or n > len(self.side):
+            raise RuntimeError("internal: nested or oversized parallel section")
+        self._open = n
+        self._fan_out(n)
+        if self.need_grad:
+            self.tape.mark("fork", n)
+
+    def branch(self, i):
+        """Context of branch i (1-based) of the open section."""
+        return _Branch(self, i if (self.side is not None and self._open) else 0)
+
+    def join(self):
+        if self.side is None or not self._open:
+            return
+        self._fan_in(self._open)
+        if self.need_grad:
+            self.tape.mark("join", self._open)
+        self._open = 0
 
     # ---- allocation ---------------------------------------------------------------------------------
     def pad(self, c):
@@ -134,6 +232,7 @@ class Engine:
         ld = ld or self.pad(C)
         shape = (N, H, W, ld) if self.planes == 1 else (self.planes, N, H, W, ld)
         t = torch.zeros(shape, dtype=self.op_dtype, device=self.dev) if (zero_pad and ld != C) else torch.empty(shape, dtype=self.op_dtype, device=self.dev)
+        self._keep.append(t)
         return Act(t, N, H, W, C, ld, 0, self.need_grad)
 
     def plane_stride(self, a: Act):
@@ -146,7 +245,9 @@ class Engine:
         return a.t.data_ptr() + a.off * self._es()
 
     def f32(self, *shape, zero=False):
-        return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.dev)
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.dev)
+        self._keep.append(t)
+        return t
 
     def add_param_grad(self, p, g):
         k = id(p)
@@ -245,7 +346,7 @@ class Engine:
         """pv2_bn_fuse descriptor (host struct, passed by value into the kernels) for the BatchNorms that follow `convs`."""
         stats = self.f32(4, Cout)
         ws = self.f32(self.lib.pv2_bn_fuse_workspace_floats(M, Cout))
-        cnt = _ticket_counters(self.dev)
+        cnt = _ticket_counters(self.dev, self.cur)
         d = np.zeros(1, dtype=_BNFUSE_DT)
         o, n, seg_of = 0, 0, {}
         for cv, bn in zip(convs, bns):
@@ -306,6 +407,10 @@ class Engine:
                                         N, H, W, Cin_p, Cout, KH, KW, dh, dw, 0, raw_t.data_ptr(), ld, splits, None,
                                         fuse.ctypes.data if fuse is not None else None, st), "pv2_conv_fwd")
             res = Raw(raw_t, splits, N, H, W, ld, Cout)
+            if self.need_grad and len(convs) > 1:
+                # the gradient buffer of a horizontally fused group is filled slice by slice, possibly from several branches:
+                # allocate (and zero its padding) here, on the forward stream, not lazily inside one of them
+                res.dy = self.new_act(N, H, W, Cout)
             if fuse is not None:
                 if not lib.pv2_conv_fuses_bn_stats(splits, 0):      # split-K (or patch tiles): one grouped pass, sums the slabs into slab 0
                     _lib.check(lib.pv2_bn_stats_group(raw_t.data_ptr(), N * H * W * ld, splits, N * H * W, Cout, ld, fuse.ctypes.data, st),
@@ -452,7 +557,7 @@ class Engine:
                 _lib.check(lib.pv2_bn_act_bwd(*fwd_args, *dz, _ptr(m1), _ptr(i1), _ptr(m2), _ptr(i2), bn_train,
                                               _ptr(dmult), Cc, dy1_ptr, self.plane_stride(dy1), self.planes, dy1.ld,
                                               dy2_ptr, self.plane_stride(dy2) if dy2 else 0, self.planes, dy2.ld if dy2 else 0,
-                                              dg1.data_ptr(), db1.data_ptr(), _ptr(dg2), _ptr(db2), ws.data_ptr(), _ticket_counters(self.dev).data_ptr(),
+                                              dg1.data_ptr(), db1.data_ptr(), _ptr(dg2), _ptr(db2), ws.data_ptr(), _ticket_counters(self.dev, self.cur).data_ptr(),
                                               self.kind, _stream()),
                            "pv2_bn_act_bwd")
                 self._route_bn_grads(src1, dg1, db1, bn_train)
@@ -640,10 +745,17 @@ class Engine:
         return y, sink
 
     def backward(self):
-        for fn in reversed(self.tape):
-            fn()
+        for kind, x, br in reversed(self.tape):
+            if kind == "op":
+                with _Branch(self, br if self.side is not None else 0):
+                    x()
+            elif kind == "join":          # a forward join is a backward fork, and vice versa
+                self._fan_out(x)
+            else:
+                self._fan_in(x)
         self.flush_unpack()
-        self.tape = []
+        self.tape = _Tape(self)
+        self._keep = []
 
 
 class _SliceGrads:

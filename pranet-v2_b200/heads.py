@@ -49,21 +49,46 @@ class BasicConv2d(nn.Module):
         return E.run_head(runner, [x], _params(self), self.training)[0]
 
 
-def rfb_run(eng, rfb: "RFB_modified", raw1x1: E.Raw, off: int, out_map=False):
-    """RFB_modified.forward (pranet.py:75-83) given the raw output of the horizontally fused 1x1 convs
-    [branch0.0 | branch1.0 | branch2.0 | branch3.0 | conv_res] starting at channel `off` of `raw1x1`."""
+def rfb_begin(eng, rfb: "RFB_modified", raw1x1: E.Raw):
+    """The concat buffer the four RFB branches write their slices of."""
     c = rfb.conv_res.conv.out_channels
-    whole, sl = eng.concat_buffer(raw1x1.N, raw1x1.H, raw1x1.W, [c] * 4)
-    eng.bn_apply((raw1x1, off, c, rfb.branch0[0].bn, None), out=sl[0])
-    for b in (1, 2, 3):
-        br = getattr(rfb, f"branch{b}")
-        t = eng.bn_apply((raw1x1, off + b * c, c, br[0].bn, None))
-        t = br[1].run(eng, t)
-        t = br[2].run(eng, t)
-        br[3].run(eng, t, out=sl[b])
+    return eng.concat_buffer(raw1x1.N, raw1x1.H, raw1x1.W, [c] * 4)
+
+
+def rfb_branch(eng, rfb: "RFB_modified", state, raw1x1: E.Raw, off: int, b: int):
+    """Branch b (0..3) of RFB_modified.forward (pranet.py:76-79): independent of the other branches."""
+    c = rfb.conv_res.conv.out_channels
+    _, sl = state
+    if b == 0:
+        eng.bn_apply((raw1x1, off, c, rfb.branch0[0].bn, None), out=sl[0])
+        return
+    br = getattr(rfb, f"branch{b}")
+    t = eng.bn_apply((raw1x1, off + b * c, c, br[0].bn, None))
+    t = br[1].run(eng, t)
+    t = br[2].run(eng, t)
+    br[3].run(eng, t, out=sl[b])
+
+
+def rfb_finish(eng, rfb: "RFB_modified", state, raw1x1: E.Raw, off: int, out_map=False):
+    """conv_cat over the concat, + conv_res, ReLU (pranet.py:80-82)."""
+    c = rfb.conv_res.conv.out_channels
+    whole, _ = state
     raw_cat = eng.conv(whole, [rfb.conv_cat.conv], [rfb.conv_cat.bn])
     return eng.bn_apply((raw_cat, 0, c, rfb.conv_cat.bn, None), src2=(raw1x1, off + 4 * c, c, rfb.conv_res.bn, None), combine=1, relu=True,
                         out_map=out_map)
+
+
+def rfb_run(eng, rfb: "RFB_modified", raw1x1: E.Raw, off: int, out_map=False):
+    """RFB_modified.forward (pranet.py:75-83) given the raw output of the horizontally fused 1x1 convs
+    [branch0.0 | branch1.0 | branch2.0 | branch3.0 | conv_res] starting at channel `off` of `raw1x1`.  The four branches
+    run as a parallel section when the engine has side streams."""
+    state = rfb_begin(eng, rfb, raw1x1)
+    eng.fork(4)
+    for b in range(4):
+        with eng.branch(b + 1):
+            rfb_branch(eng, rfb, state, raw1x1, off, b)
+    eng.join()
+    return rfb_finish(eng, rfb, state, raw1x1, off, out_map)
 
 
 def rfb_convs(rfb: "RFB_modified"):

@@ -17,7 +17,8 @@ import torch.nn as nn
 
 from . import engine as E
 from .backbones import PvtV2B2, Res2Net50
-from .heads import BasicConv2d, RFB_modified, _sink, aggregation, aggregation_run, rfb_bns, rfb_convs, rfb_run
+from .heads import (BasicConv2d, RFB_modified, _sink, aggregation, aggregation_run, rfb_begin, rfb_bns, rfb_branch, rfb_convs, rfb_finish,
+                    rfb_run)
 
 RES2NET_CH = (512, 1024, 2048)
 PVT_CH = (128, 320, 512)
@@ -84,27 +85,46 @@ class _V2Mixin(_PraNetBase):
 
         def runner(eng, inputs, in_grads):
             feats = [eng.from_nchw(t, _sink(in_grads, i)) for i, t in enumerate(inputs)]
-            rfbs, stacks = [], []
-            # per pyramid level ONE GEMM for the six 1x1 convs that read the backbone feature:
-            # [rfb.branch0..3 first convs | rfb.conv_res | ra_conv1]
-            for a, rfb, stage in zip(feats, (self.rfb2_1, self.rfb3_1, self.rfb4_1), (2, 3, 4)):
-                ra1 = getattr(self, f"ra{stage}_conv1")
-                raw = eng.conv(a, rfb_convs(rfb) + [ra1.conv], rfb_bns(rfb) + [ra1.bn])
-                c = rfb.conv_res.conv.out_channels
-                rfbs.append(rfb_run(eng, rfb, raw, 0))
-                stacks.append(eng.bn_apply((raw, 5 * c, ra1.conv.out_channels, ra1.bn, None)))       # no ReLU after conv1
+            levels = list(zip(feats, (self.rfb2_1, self.rfb3_1, self.rfb4_1), (2, 3, 4), (3, 3, 4)))
+            # section 1 -- per pyramid level ONE GEMM for the six 1x1 convs that read the backbone feature:
+            # [rfb.branch0..3 first convs | rfb.conv_res | ra_conv1]; the three levels are independent
+            raws = [None] * 3
+            eng.fork(3)
+            for li, (a, rfb, stage, _) in enumerate(levels):
+                with eng.branch(li + 1):
+                    ra1 = getattr(self, f"ra{stage}_conv1")
+                    raws[li] = eng.conv(a, rfb_convs(rfb) + [ra1.conv], rfb_bns(rfb) + [ra1.bn])
+            eng.join()
+            # section 2 -- per level: RFB branches 1..3, and [RFB branch 0 + the reverse-attention stack + its fg/bg heads]:
+            # twelve independent chains
+            states = [rfb_begin(eng, rfb, raws[li]) for li, (_, rfb, _, _) in enumerate(levels)]
+            heads_ = [None] * 3
+            eng.fork(12)
+            for li, (a, rfb, stage, depth) in enumerate(levels):
+                for b in (1, 2, 3):
+                    with eng.branch(li * 4 + b):
+                        rfb_branch(eng, rfb, states[li], raws[li], 0, b)
+                with eng.branch(li * 4 + 4):
+                    rfb_branch(eng, rfb, states[li], raws[li], 0, 0)
+                    ra1 = getattr(self, f"ra{stage}_conv1")
+                    c = rfb.conv_res.conv.out_channels
+                    t = eng.bn_apply((raws[li], 5 * c, ra1.conv.out_channels, ra1.bn, None))                 # no ReLU after conv1
+                    t = self._stack(eng, stage, t, depth)
+                    head = "conv5" if stage == 4 else "conv4"
+                    heads_[li] = dual(eng, getattr(self, f"ra{stage}_{head}_fg"), getattr(self, f"ra{stage}_{head}_bg"), t)
+            eng.join()
+            # section 3 -- conv_cat + residual + ReLU of the three RFBs
+            rfbs = [None] * 3
+            eng.fork(3)
+            for li, (_, rfb, _, _) in enumerate(levels):
+                with eng.branch(li + 1):
+                    rfbs[li] = rfb_finish(eng, rfb, states[li], raws[li], 0)
+            eng.join()
             ra5_fg, ra5_bg = aggregation_run(eng, self.agg1, rfbs[2], rfbs[1], rfbs[0])
-            # DSRA3: the x0.25 resize of the coarse maps is fused into the fusion kernel
-            t = self._stack(eng, 4, stacks[2], 4)
-            fg4, bg4 = dual(eng, self.ra4_conv5_fg, self.ra4_conv5_bg, t)
+            (fg2, bg2), (fg3, bg3), (fg4, bg4) = heads_
+            # DSRA fusions, deep -> shallow; the x0.25 / x2 resize of the deeper maps is fused into the fusion kernel
             fg4 = eng.fuse(fg4, ra5_fg, ra5_bg, self.use_softmax, 0.25)
-            # DSRA2
-            t = self._stack(eng, 3, stacks[1], 3)
-            fg3, bg3 = dual(eng, self.ra3_conv4_fg, self.ra3_conv4_bg, t)
             fg3 = eng.fuse(fg3, fg4, bg4, self.use_softmax, 2)
-            # DSRA1
-            t = self._stack(eng, 2, stacks[0], 3)
-            fg2, bg2 = dual(eng, self.ra2_conv4_fg, self.ra2_conv4_bg, t)
             fg2 = eng.fuse(fg2, fg3, bg3, self.use_softmax, 2)
             # the eight final upsamples (x8, x16, x32, x8 for fg and bg; pranet.py:349-350,370-371,392-393,414-415): one launch
             l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg = eng.resize_multi(
