@@ -240,6 +240,45 @@ int pv2_up2_nhwc_fwd(const void* in, long long in_plane, int in_planes, int in_l
 int pv2_up2_nhwc_bwd(const float* const* slabs, const int* lds, const int* offs, int nslabs, float* din, int din_ld,
                      int N, int H, int W, int C, void* stream);
 
+/* =============================================================================================
+ * Optimizer tail -- binary_seg/utils/utils.py:7-17 clip_gradient (param.grad.data.clamp_(-clip, clip)) followed by
+ * optimizer.step() of torch.optim.Adam(params, lr) (binary_seg/MyTrain_med.py:85-86,148-149) or optim.AdamW(..., lr,
+ * weight_decay=1e-4) (EMCAD/trainer.py:86,155-157; MERIT/train_ACDC.py; MIST/trainer.py), as ONE flat stream.
+ * params / grads / exp_avg / exp_avg_sq are four fp32 buffers of n elements sharing one layout (n % 4 == 0, 16-byte aligned;
+ * padding elements carry zero gradients and stay zero).  Per element:
+ *   g = clamp(g * grad_scale, -clip, clip)          grad_scale = 1/world after the all-reduce (sum)
+ *   decoupled = 0 (Adam):  g += weight_decay * p     decoupled = 1 (AdamW): p *= 1 - lr*weight_decay
+ *   m = m + (g - m)(1 - beta1);  v = beta2*v + (1 - beta2) g*g
+ *   p -= lr/(1 - beta1^t) * m / (sqrt(v)/sqrt(1 - beta2^t) + eps),   t = *step + 1
+ * `step` (device int64, starts at 0) is advanced by the kernel, so a captured CUDA graph replays correctly; `ticket` is one
+ * zero-initialised device uint the launch leaves zeroed.  Algorithmic HBM bytes: 28 per element.
+ * ============================================================================================= */
+int pv2_adam_clamp_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                        long long* step, unsigned int* ticket, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int decoupled, float clip, float grad_scale, void* stream);
+
+/* =============================================================================================
+ * Inference tails from the LOW-RESOLUTION head maps (the 8 full-resolution fp32 maps are never written).
+ *
+ * Binary -- binary_seg/MyTest_med.py:35-42 and :104-111 (V2: res2+res3+res4+res5; V1 :98-102: a single map):
+ *     z   = F.interpolate( sum_k F.interpolate(map_k, scale_factor=s_k, bilinear), size=(GH, GW), bilinear )   align_corners=False
+ *     out = uint8( (sigmoid(z) - min) / (max - min + 1e-8) * 255 )      min / max per image (the reference runs batch 1)
+ * maps: HOST array of nmaps (<= 4) device pointers to fp32 [B][1][mh_k][mw_k]; rh_k / rw_k = 1/s_k; (SH, SW) = the size the
+ * model's own final upsample produces (pranet.py:349-415); rgh = SH/GH, rgw = SW/GW (the size= form of F.interpolate).
+ * out: uint8 [B][GH][GW].  workspace: pv2_infer_tail_workspace_bytes(B) bytes.
+ *
+ * Multiclass -- EMCAD/utils/utils.py:261-273,286-296 (val_single_volume, use_dual):
+ *     label = argmax_c softmax( sum_k (P[k] - P_bg[k]) ),  P[k] = F.interpolate(map_k, scale_factor=s_k, bilinear)  (EMCAD/lib/networks.py:116-123)
+ * P_fg / P_bg: HOST arrays of nmaps device pointers to fp32 [B][C][mh_k][mw_k], 1 <= C <= 16.  out: uint8 [B][H][W].
+ * Algorithmic HBM bytes: 1 per output pixel (+ the KB-sized maps).
+ * ============================================================================================= */
+size_t pv2_infer_tail_workspace_bytes(int B);
+int pv2_infer_tail_binary(const float* const* maps, const int* mh, const int* mw, const float* rh, const float* rw, int nmaps,
+                          int B, int SH, int SW, int GH, int GW, float rgh, float rgw, uint8_t* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int pv2_infer_tail_argmax(const float* const* P_fg, const float* const* P_bg, const int* mh, const int* mw, const float* rh,
+                          const float* rw, int nmaps, int B, int C, int H, int W, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

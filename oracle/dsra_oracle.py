@@ -214,6 +214,57 @@ def final_upsample(maps, scales=(32, 16, 8, 4)):
 
 
 # --------------------------------------------------------------------------------------
+# inference tails
+# --------------------------------------------------------------------------------------
+def infer_tail_binary(lowres_maps, scale_factors, size=None):
+    """Test-time post-processing of binary_seg/MyTest_med.py:35-42 (:104-111; V1 :98-102 with one map), starting from the
+    low-res foreground maps: final upsamples of the model (pranet.py:349-415), p2+p3+p4+p5, resize to the ground-truth
+    size, sigmoid, min-max normalisation, uint8.  Per image (the reference runs batch 1).  Returns uint8 (B, H, W)."""
+    ups = [interp(m, s) for m, s in zip(lowres_maps, scale_factors)]
+    out = ups[0]
+    for u in ups[1:]:
+        out = out + u
+    if size is None:
+        size = tuple(out.shape[-2:])
+    res = []
+    for b in range(out.shape[0]):
+        o = F.interpolate(out[b:b + 1], size=tuple(size), mode="bilinear", align_corners=False)
+        o = o.sigmoid().data.cpu().numpy().squeeze()
+        o = (o - o.min()) / (o.max() - o.min() + 1e-8)
+        res.append((o * 255).astype(np.uint8))
+    return np.stack(res)
+
+
+def infer_tail_binary_float(lowres_maps, scale_factors, size=None):
+    """Same as infer_tail_binary but returning the float value before the uint8 truncation (to tell +-1 truncation flips
+    from real errors)."""
+    ups = [interp(m, s) for m, s in zip(lowres_maps, scale_factors)]
+    out = ups[0]
+    for u in ups[1:]:
+        out = out + u
+    if size is None:
+        size = tuple(out.shape[-2:])
+    res = []
+    for b in range(out.shape[0]):
+        o = F.interpolate(out[b:b + 1], size=tuple(size), mode="bilinear", align_corners=False)
+        o = o.sigmoid().data.cpu().numpy().squeeze()
+        res.append((o - o.min()) / (o.max() - o.min() + 1e-8) * 255)
+    return np.stack(res)
+
+
+def infer_tail_argmax(P_fg_low, P_bg_low, scales=(32, 16, 8, 4)):
+    """Dual-branch prediction rule of EMCAD/utils/utils.py:261-273,285-296 from the low-res stage maps: final upsamples of
+    EMCAD/lib/networks.py:116-123, outputs = sum_k (P[k] - P_bg[k]), argmax_c softmax.  Returns (labels uint8 (B,H,W),
+    margin (B,H,W) = top-1 minus top-2 of the summed logits, so near-ties can be excluded from exact comparisons)."""
+    outputs = 0.0
+    for fg, bg, s in zip(P_fg_low, P_bg_low, scales):
+        outputs += (interp(fg, s) - interp(bg, s))
+    out = torch.argmax(torch.softmax(outputs, dim=1), dim=1)
+    top2 = torch.topk(outputs, 2, dim=1).values if outputs.shape[1] > 1 else torch.cat([outputs, outputs - 1], 1)
+    return out.numpy().astype(np.uint8), (top2[:, 0] - top2[:, 1]).numpy()
+
+
+# --------------------------------------------------------------------------------------
 # losses
 # --------------------------------------------------------------------------------------
 def structure_loss(pred, pred_bg, mask_fg, mask_bg):

@@ -104,6 +104,37 @@ def mc_loss_inputs(name):
     return P_fg, P_bg, labels
 
 
+# ---- inference tails from the low-res maps (binary_seg/MyTest_med.py:35-42; EMCAD/utils/utils.py:285-296) ----
+# binary: input size S (maps at S/8, S/16, S/32, S/8), ground-truth size the reference resizes to; nmaps=1 is the V1 rule
+TAIL_BINARY_CASES = {
+    "tail_bin_352_same": dict(B=2, S=352, gt=(352, 352), nmaps=4),
+    "tail_bin_352_to_288x384": dict(B=1, S=352, gt=(288, 384), nmaps=4),
+    "tail_bin_64_to_531x473": dict(B=2, S=64, gt=(531, 473), nmaps=4),     # odd, non-multiple-of-4 ground-truth size
+    "tail_bin_v1_96_to_100x120": dict(B=1, S=96, gt=(100, 120), nmaps=1),
+}
+TAIL_MC_CASES = {
+    "tail_mc_c9_224": dict(B=2, C=9, S=224),
+    "tail_mc_c4_96": dict(B=1, C=4, S=96),
+}
+TAIL_BIN_SCALES = (8, 16, 32, 8)
+TAIL_MC_SCALES = (32, 16, 8, 4)
+
+
+def tail_binary_inputs(name):
+    c = TAIL_BINARY_CASES[name]
+    seed = hash_name(name)
+    scales = TAIL_BIN_SCALES[:c["nmaps"]]
+    return [synth.logits((c["B"], 1, c["S"] // s, c["S"] // s), seed, f"m{k}", 2.0) for k, s in enumerate(scales)], list(scales)
+
+
+def tail_mc_inputs(name):
+    c = TAIL_MC_CASES[name]
+    seed = hash_name(name)
+    fg = [synth.logits((c["B"], c["C"], c["S"] // s, c["S"] // s), seed, f"fg{k}", 2.0) for k, s in enumerate(TAIL_MC_SCALES)]
+    bg = [synth.logits((c["B"], c["C"], c["S"] // s, c["S"] // s), seed, f"bg{k}", 2.0) for k, s in enumerate(TAIL_MC_SCALES)]
+    return fg, bg
+
+
 # ---- full models (stock backbone + head) ---------------------------------------------
 FULL_CASES = {
     "full_v2_res_352": dict(model="PraNet_V2", kw=dict(num_class=1), B=1, size=352, training=True, stride=4),

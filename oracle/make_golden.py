@@ -216,7 +216,30 @@ def gen_full():
         _save(name, **arrays)
 
 
-GROUPS = {"sl": gen_structure_loss, "head": gen_heads, "mc": gen_multiclass, "mcl": gen_mc_loss, "full": gen_full}
+def gen_tail():
+    """Inference tails: the reference's own statements (MyTest_med.py:35-42, EMCAD/utils/utils.py:285-296) run on the final
+    upsamples (pranet.py:349-415 / EMCAD networks.py:116-123) of seeded low-res maps."""
+    import torch.nn.functional as F
+    bin_tail, mc_tail = R.binary_test_tail(), R.multiclass_val_tail()
+    for name, case in G.TAIL_BINARY_CASES.items():
+        maps, scales = G.tail_binary_inputs(name)
+        outs = []
+        for b in range(case["B"]):                     # the reference's test loader is batch 1
+            ups = [F.interpolate(m[b:b + 1], scale_factor=s, mode="bilinear") for m, s in zip(maps, scales)]
+            if case["nmaps"] == 1:                     # V1 rule (MyTest_med.py:98-102): res = res2 only; same statements with zeros added
+                ups = ups + [torch.zeros_like(ups[0])] * 3
+            outs.append(bin_tail(lambda image: tuple(ups) + (None,) * 4, None, np.zeros(case["gt"], np.float32)))
+        _save(name, out=np.stack(outs))
+    for name, case in G.TAIL_MC_CASES.items():
+        fg, bg = G.tail_mc_inputs(name)
+        labels = []
+        for b in range(case["B"]):
+            P = [F.interpolate(m[b:b + 1], scale_factor=s, mode="bilinear") for m, s in zip(fg + bg, G.TAIL_MC_SCALES * 2)]
+            labels.append(mc_tail(lambda inp: P, None).numpy().astype(np.uint8))
+        _save(name, labels=np.stack(labels))
+
+
+GROUPS = {"tail": gen_tail, "sl": gen_structure_loss, "head": gen_heads, "mc": gen_multiclass, "mcl": gen_mc_loss, "full": gen_full}
 
 if __name__ == "__main__":
     assert R.available(), "reference not mounted; golden vectors can only be generated in the builder container"

@@ -223,3 +223,49 @@ def emcad_loss_pieces():
     exec(compile(ast.Module(body=keep, type_ignores=[]), "trainer.py", "exec"), ns)
     _cache["mcl"] = (ns["powerset"], ns["DiceLoss"], ns["convert_labels_to_one_hot_masks"])
     return _cache["mcl"]
+
+
+def _stmts_between(path: str, first: int, last: int):
+    """The innermost statement list of `path` that covers source lines [first, last], restricted to that range."""
+    tree = ast.parse(open(path).read())
+    best = None
+    for node in ast.walk(tree):
+        for field in ("body", "orelse", "finalbody"):
+            stmts = getattr(node, field, None)
+            if not isinstance(stmts, list) or not stmts or not isinstance(stmts[0], ast.stmt):
+                continue
+            inside = [s for s in stmts if s.lineno >= first and s.end_lineno <= last]
+            if inside and inside[0].lineno == first and inside[-1].end_lineno == last:
+                best = inside
+    if best is None:
+        raise RuntimeError(f"{path}: no statement list spans lines {first}-{last}")
+    return best
+
+
+def binary_test_tail():
+    """The reference's binary test-time post-processing, run from its own source: the statements of
+    binary_seg/MyTest_med.py:35-42 (forward, p2+p3+p4+p5, resize to gt.shape, sigmoid, min-max, uint8) compiled as they
+    stand.  Returns f(model, image, gt) -> output_uint8 (numpy)."""
+    stmts = _stmts_between(os.path.join(REF, "binary_seg", "MyTest_med.py"), 35, 42)
+    code = compile(ast.Module(body=stmts, type_ignores=[]), "MyTest_med.py", "exec")
+
+    def run(model, image, gt):
+        import numpy as np
+        ns = {"torch": torch, "F": F, "np": np, "model": model, "image": image, "gt": gt}
+        exec(code, ns)
+        return ns["output_uint8"]
+    return run
+
+
+def multiclass_val_tail():
+    """The dual-branch prediction rule of EMCAD/utils/utils.py:285-296 (val_single_volume, 2-D branch: P = net(input)[:4],
+    P_bg = net(input)[-4:], outputs = sum (P - P_bg), argmax softmax), compiled from the reference source as it stands.
+    Returns f(net, input) -> label map tensor (H, W)."""
+    stmts = _stmts_between(os.path.join(REF, "multiclass_seg/EMCAD/utils/utils.py"), 285, 296)
+    code = compile(ast.Module(body=stmts, type_ignores=[]), "utils.py", "exec")
+
+    def run(net, inp):
+        ns = {"torch": torch, "net": net, "input": inp, "use_dual": True}
+        exec(code, ns)
+        return ns["out"]
+    return run

@@ -15,6 +15,7 @@ _lib = None
 c_void_pp = C.POINTER(C.c_void_p)
 _i, _f, _p, _sz, _ll = C.c_int, C.c_float, C.c_void_p, C.c_size_t, C.c_longlong
 _ip = C.POINTER(C.c_int)
+_fp = C.POINTER(C.c_float)
 # the 24 leading arguments shared by pv2_act_apply / pv2_bn_act_bwd (the forward description)
 _APPLY = [_p, _i, _i, _i, _ll, _p, _p, _p, _i, _i, _i, _ll, _p, _p, _i, _p, _ll, _i, _i, _i, _i, _ll, _i, _i]
 
@@ -58,6 +59,12 @@ _SIGS = {
     "pv2_bn_act_bwd": (_i, _APPLY + [c_void_pp, _ip, _ip, _i, _p] + [_p] * 4 + [_i, _p, _i] + [_p, _ll, _i, _i] * 2 + [_p] * 6 + [_i, _p]),
     "pv2_up2_nhwc_fwd": (_i, [_p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i] + [_i] * 5 + [_p]),
     "pv2_up2_nhwc_bwd": (_i, [c_void_pp, _ip, _ip, _i, _p, _i] + [_i] * 4 + [_p]),
+    # inference tails
+    "pv2_infer_tail_workspace_bytes": (_sz, [_i]),
+    "pv2_infer_tail_binary": (_i, [c_void_pp, _ip, _ip, _fp, _fp] + [_i] * 6 + [_f, _f, _p, _p, _sz, _p]),
+    "pv2_infer_tail_argmax": (_i, [c_void_pp, c_void_pp, _ip, _ip, _fp, _fp] + [_i] * 5 + [_p, _p]),
+    # optimizer tail
+    "pv2_adam_clamp_flat": (_i, [_p] * 4 + [_ll, _p, _p] + [_f] * 5 + [_i, _f, _f, _p]),
 }
 
 
@@ -110,6 +117,11 @@ def launch_count() -> int:
 def int_array(vals):
     arr = (C.c_int * len(vals))(*[int(v) for v in vals])
     return C.cast(arr, _ip), arr
+
+
+def float_array(vals):
+    arr = (C.c_float * len(vals))(*[float(v) for v in vals])
+    return C.cast(arr, _fp), arr
 
 
 def ptr_array(tensors):

@@ -37,7 +37,7 @@ using namespace ptx;
 constexpr int BM = 128;                 // pixel rows per tile = UMMA M
 constexpr int ROW_BYTES = 128;          // one swizzle row: 64 bf16 or 32 tf32 channels
 constexpr int A_BYTES = BM * ROW_BYTES; // 16 KB
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 6;           // mbarrier ring capacity; the launch picks 2..6 stages so that several CTAs share an SM
 constexpr int THREADS = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
 struct ConvArgs {
@@ -50,6 +50,7 @@ struct ConvArgs {
     int stats;              // 1: the epilogue also produces the BatchNorm batch statistics (im2col tiles, no split-K)
     int m_tiles, G, ngroups;   // two-level fold of the per-tile statistics
     int BN;                 // N tile (multiple of 16, <= 256)
+    int stages;             // depth of the TMA -> MMA ring (2..MAX_STAGES)
     uint32_t tmem_cols;     // power of two >= max(32, BN)
     int out_mode;           // 0: raw fp32 [split][pixel][ldo]   1: NCHW fp32 + bias
     float* out;
@@ -59,18 +60,18 @@ struct ConvArgs {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 3)   // up to 3 co-resident CTAs (plan_stages)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs a,
                 const __grid_constant__ BnFuseDev bn) {
-    pdl_trigger();
     constexpr int KC = (KIND == 0) ? 64 : 32;   // channels per 128-byte row
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_bytes = a.BN * ROW_BYTES;
+    const int STAGES = a.stages;
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_flag;
 
@@ -103,6 +104,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    // Dependents may be scheduled only now that this CTA owns its TMEM columns: CTAs of a dependent grid co-reside with ours
+    // (shallow rings leave shared memory free) and would otherwise be able to take the columns we still need while they
+    // sit in griddepcontrol.wait for us -- a circular wait.
+    pdl_trigger();
     pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
 
     if (warp == 0 && lane == 0) {
@@ -288,6 +293,7 @@ struct WgradArgs {
     int im2col;             // 1: flat 128-pixel K tiles (dY: 2-D flat boxes, X: im2col-mode loads); 0: patches
     int nterms;
     int BN;                 // ci tile (multiple of KC, <= 256)
+    int stages;             // ring depth (2..WgradCfg::STAGES_)
     int ci_tiles;
     uint32_t tmem_cols;
     float* out;             // [split][Cout][taps][Cin_p]
@@ -295,22 +301,21 @@ struct WgradArgs {
 };
 
 // stage = (dY boxes + X boxes) x 16 KB: bf16 (2 + 2) x 16 KB x 3 stages, tf32 (4 + 2) x 16 KB x 2 stages = 192 KB
-template <int KIND> struct WgradCfg { static constexpr int STAGES_ = KIND == 0 ? 3 : 2; static constexpr int BN_MAX = KIND == 0 ? 128 : 64; };
+template <int KIND> struct WgradCfg { static constexpr int STAGES_ = KIND == 0 ? 3 : 2; static constexpr int BN_MAX = KIND == 0 ? 128 : 64; };   // STAGES_: upper bound
 
 template <int KIND>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, 3)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
                   const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1, const WgradArgs a) {
-    pdl_trigger();
     constexpr int KC = (KIND == 0) ? 64 : 32;
     constexpr int KSTEP_ROWS = (KIND == 0) ? 16 : 8;      // pixels per MMA (UMMA_K)
     constexpr int A_BOXES = BM / KC;                       // dY boxes per stage (128 output channels)
-    constexpr int WSTAGES = WgradCfg<KIND>::STAGES_;
+    const int WSTAGES = a.stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int b_boxes = a.BN / KC;
     const int stage_bytes = (A_BOXES + b_boxes) * A_BYTES;
-    __shared__ __align__(8) uint64_t full_bar[WSTAGES], empty_bar[WSTAGES], acc_bar;
+    __shared__ __align__(8) uint64_t full_bar[WgradCfg<KIND>::STAGES_], empty_bar[WgradCfg<KIND>::STAGES_], acc_bar;
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,6 +336,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    // Dependents may be scheduled only now that this CTA owns its TMEM columns: CTAs of a dependent grid co-reside with ours
+    // (shallow rings leave shared memory free) and would otherwise be able to take the columns we still need while they
+    // sit in griddepcontrol.wait for us -- a circular wait.
+    pdl_trigger();
     pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
 
     if (warp == 0 && lane == 0) {
@@ -531,6 +540,35 @@ uint32_t pow2_cols(int n) {
     return c;
 }
 
+// How many pipeline stages a CTA gets.  The head's GEMMs are short (8..100 K iterations per CTA) and their epilogue (TMEM ->
+// registers -> global, plus the fused BatchNorm statistics) is as long as the main loop, so instead of one CTA owning the
+// whole SM with a deep ring, several CTAs with a shallow ring share it: one CTA's epilogue / prologue overlaps another's
+// MMAs, and grids of 150..300 tiles run as ONE wave.  Bounded by shared memory (227 KB), by TMEM (512 columns) and by the
+// scratch the statistics epilogue needs.  PV2_CONV_STAGES / PV2_CONV_CTAS override (profiling sweeps).
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+int plan_stages(long long ctas, int iters, size_t stage_bytes, uint32_t tmem_cols, size_t min_bytes, int max_stages) {
+    static const int force_stages = env_int("PV2_CONV_STAGES", 0), force_ctas = env_int("PV2_CONV_CTAS", 0);
+    int target = force_ctas > 0 ? force_ctas : (int)((ctas + kNumSMs - 1) / kNumSMs);
+    if (target > 3) target = 3;
+    if (target < 1) target = 1;
+    while (target > 1 && (uint32_t)target * tmem_cols > 512u) --target;
+    int stages = max_stages;
+    for (;; --target) {
+        const size_t budget = (size_t)(227 * 1024) / target - 2048;     // 1 KB reserved per CTA + 1 KB alignment slack
+        stages = (int)(budget / stage_bytes);
+        if (stages > max_stages) stages = max_stages;
+        if ((stages >= 2 && (size_t)stages * stage_bytes >= min_bytes) || target == 1) break;
+    }
+    if (stages < 2) stages = 2;
+    if (force_stages > 0) stages = force_stages < 2 ? 2 : (force_stages > max_stages ? max_stages : force_stages);
+    if (stages > iters && iters >= 2) stages = iters;
+    while ((size_t)stages * stage_bytes < min_bytes && stages < max_stages) ++stages;
+    return stages;
+}
+
 int common_checks(const char* who, int kind, int nterms, int N, int H, int W, int Cin_p, int Cout, int KH, int KW) {
     PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "%s: operand kind must be PV2_BF16 or PV2_TF32 (got %d)", who, kind);
     PV2_CHECK(nterms == 1 || (kind == PV2_TF32 && nterms == 3), "%s: nterms must be 1, or 3 with tf32 operands", who);
@@ -611,8 +649,12 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
         if (int e = im2col ? make_im2col_map(&mA1, x1, k, Cin_p, W, H, N, a.pad_w, a.pad_h) : make_act_map(&mA1, x1, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
         if (int e = make_w_map(&mB1, (const uint8_t*)w_op + w_plane_stride * es, k, Cin_p, a.taps, Cout, a.BN)) return e;
     }
-    const size_t smem = (size_t)STAGES * (A_BYTES + (size_t)a.BN * ROW_BYTES) + 1024;
     dim3 grid(im2col ? (unsigned)((a.M + BM - 1) / BM) : (unsigned)(N * a.tiles_x * a.tiles_y), (Cout + a.BN - 1) / a.BN, splits);
+    const size_t stage_bytes = A_BYTES + (size_t)a.BN * ROW_BYTES;
+    const size_t stats_scratch = a.stats ? (size_t)(4 * 32 * 33 + 4 * a.BN * 2) * sizeof(float) : 0;   // epilogue reuses the ring
+    a.stages = plan_stages((long long)grid.x * grid.y * grid.z, a.iters_per_split, stage_bytes, a.tmem_cols, stats_scratch, MAX_STAGES);
+    const size_t smem = (size_t)a.stages * stage_bytes + 1024;
+    PV2_CHECK(smem <= 227 * 1024 && smem - 1024 >= stats_scratch, "conv_fwd: bad stage plan (%d stages of %zu B)", a.stages, stage_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce;
     if (k == 0) {
@@ -682,9 +724,12 @@ extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const v
         if (int e = im2col ? make_flat_map(&mG1, dy1, k, Cout_p, Mtot, a32) : make_act_map(&mG1, dy1, k, Cout_p, W, H, N, a.TWb, a.THb, a32)) return e;
         if (int e = im2col ? make_im2col_map(&mX1, x1, k, Cin_p, W, H, N, a.pad_w, a.pad_h, a32) : make_act_map(&mX1, x1, k, Cin_p, W, H, N, a.TWb, a.THb, a32)) return e;
     }
-    const size_t smem = (size_t)(k == 0 ? WgradCfg<0>::STAGES_ : WgradCfg<1>::STAGES_) * ((BM / KC) + (a.BN / KC)) * A_BYTES + 1024;
-    PV2_CHECK(smem <= 227 * 1024, "conv_wgrad: stage too large (%zu B)", smem);
     dim3 grid(a.taps, ((Cout + BM - 1) / BM) * a.ci_tiles, splits);
+    const size_t wstage_bytes = (size_t)((BM / KC) + (a.BN / KC)) * A_BYTES;
+    a.stages = plan_stages((long long)grid.x * grid.y * grid.z, a.tiles_per_split * nterms, wstage_bytes, a.tmem_cols, 0,
+                           k == 0 ? WgradCfg<0>::STAGES_ : WgradCfg<1>::STAGES_);
+    const size_t smem = (size_t)a.stages * wstage_bytes + 1024;
+    PV2_CHECK(smem <= 227 * 1024, "conv_wgrad: stage too large (%zu B)", smem);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce;
     if (k == 0) {

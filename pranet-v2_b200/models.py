@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import engine as E
+from . import ops
 from .backbones import PvtV2B2, Res2Net50
 from .heads import (BasicConv2d, RFB_modified, _sink, aggregation, aggregation_run, rfb_begin, rfb_bns, rfb_branch, rfb_convs, rfb_finish,
                     rfb_run)
@@ -79,8 +80,15 @@ class _V2Mixin(_PraNetBase):
         self.conv = nn.Sequential(nn.Conv2d(1, 3, kernel_size=1), nn.BatchNorm2d(3), nn.ReLU(inplace=True))
         self._build_head(channels, channel, num_class, v1=False)
 
-    def forward_head(self, x2, x3, x4):
-        """pranet.py:343-417 -> (l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg)."""
+    def final_scale_factors(self):
+        """scale_factor of the four final F.interpolate calls (pranet.py:349-350,370-371,392-393,414-415), in output order."""
+        sd = self.sem_downsample
+        return [8 / sd, 16 / sd, 32 / sd, 8 / sd]
+
+    def forward_head(self, x2, x3, x4, lowres=False):
+        """pranet.py:343-417 -> (l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg).
+        lowres=True returns the same eight maps BEFORE their final upsample (44^2, 22^2, 11^2, 44^2 at 352^2 input): what the
+        fused inference tail (ops.infer_tail_binary) and loss-from-low-res paths consume."""
         sd = self.sem_downsample
 
         def runner(eng, inputs, in_grads):
@@ -126,6 +134,8 @@ class _V2Mixin(_PraNetBase):
             fg4 = eng.fuse(fg4, ra5_fg, ra5_bg, self.use_softmax, 0.25)
             fg3 = eng.fuse(fg3, fg4, bg4, self.use_softmax, 2)
             fg2 = eng.fuse(fg2, fg3, bg3, self.use_softmax, 2)
+            if lowres:
+                return [fg2, fg3, fg4, ra5_fg, bg2, bg3, bg4, ra5_bg]
             # the eight final upsamples (x8, x16, x32, x8 for fg and bg; pranet.py:349-350,370-371,392-393,414-415): one launch
             l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg = eng.resize_multi(
                 [fg2, fg3, fg4, ra5_fg, bg2, bg3, bg4, ra5_bg], [8 / sd, 16 / sd, 32 / sd, 8 / sd] * 2)
@@ -133,6 +143,17 @@ class _V2Mixin(_PraNetBase):
 
         from .heads import dual_heads_run as dual
         return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training, self.__dict__.setdefault("_pv2_cache", {}))
+
+
+    @torch.no_grad()
+    def predict_uint8(self, x, size=None):
+        """The whole test-time path of binary_seg/MyTest_med.py:35-42 (:104-111) for a batch: forward, p2+p3+p4+p5, resize to
+        `size` (the ground-truth H x W; None = input size), sigmoid, per-image min-max, uint8 -- the post-processing is ONE
+        fused tail on the low-res maps (num_class must be 1, as in the reference's polyp models)."""
+        if self.num_class != 1:
+            raise ValueError("predict_uint8 is the binary test path (num_class=1); use ops.infer_tail_argmax for multiclass maps")
+        maps = self.forward_features_lowres(x)[:4]
+        return ops.infer_tail_binary(maps, self.final_scale_factors(), size)
 
 
 class PraNet_V2(_V2Mixin):
@@ -146,6 +167,10 @@ class PraNet_V2(_V2Mixin):
     def forward(self, x, segSize=None):
         _, x2, x3, x4 = self.backbone.pyramid(x)
         return self.forward_head(x2, x3, x4)
+
+    def forward_features_lowres(self, x):
+        _, x2, x3, x4 = self.backbone.pyramid(x)
+        return self.forward_head(x2, x3, x4, lowres=True)
 
 
 class PVT_PraNet_V2(_V2Mixin):
@@ -161,6 +186,12 @@ class PVT_PraNet_V2(_V2Mixin):
             x = self.conv(x)
         _, x2, x3, x4 = self.backbone(x)
         return self.forward_head(x2, x3, x4)
+
+    def forward_features_lowres(self, x):
+        if x.size(1) == 1:
+            x = self.conv(x)
+        _, x2, x3, x4 = self.backbone(x)
+        return self.forward_head(x2, x3, x4, lowres=True)
 
 
 class _V1Mixin(_PraNetBase):

@@ -298,3 +298,71 @@ def mc_dual_loss(P_fg, P_bg, labels, num_classes, lc=(0.5, 0.7, 0.3), supervisio
         raise ValueError("mc_dual_loss takes 1..4 foreground maps and as many background maps")
     mode = {"mutation": 0, "deep_supervision": 1}[supervision]
     return _McDualLossFn.apply(labels, int(num_classes), mode, tuple(float(v) for v in lc), *P_fg, *P_bg)
+
+
+# ------------------------------------------------------------------------------------------------
+# inference tails from the low-resolution head maps
+# ------------------------------------------------------------------------------------------------
+def _tail_geometry(maps, scale_factors):
+    hs, ws, rhs, rws = [], [], [], []
+    size = None
+    for t, s in zip(maps, scale_factors):
+        h, w = t.shape[-2:]
+        out = (int(np.floor(h * s)), int(np.floor(w * s)))
+        if size is not None and out != size:
+            raise ValueError(f"inference tail: maps upsample to different sizes ({size} vs {out})")
+        size = out
+        hs.append(h); ws.append(w)
+        rhs.append(_ratio(h, out[0], False, s)); rws.append(_ratio(w, out[1], False, s))
+    return hs, ws, rhs, rws, size
+
+
+@torch.no_grad()
+def infer_tail_binary(maps, scale_factors, size=None):
+    """uint8 saliency maps of binary_seg/MyTest_med.py:35-42 / :104-111 from the LOW-RES foreground maps.
+
+    maps: 1..4 tensors (B, 1, h_k, w_k); scale_factors: the factors the model's final F.interpolate calls use
+    (pranet.py:349-415: 8, 16, 32, 8 over sem_downsample); size: the ground-truth (H, W) the reference resizes to
+    (None = the model output size).  Returns uint8 (B, H, W); min-max normalisation is per image."""
+    maps = [m.contiguous().float() for m in maps]
+    _need_cuda(*maps)
+    lib = _lib.load()
+    B = maps[0].shape[0]
+    if any(m.dim() != 4 or m.shape[0] != B or m.shape[1] != 1 for m in maps):
+        raise ValueError("infer_tail_binary takes (B, 1, h, w) maps")
+    hs, ws, rhs, rws, (SH, SW) = _tail_geometry(maps, scale_factors)
+    GH, GW = (SH, SW) if size is None else tuple(int(v) for v in size)
+    out = torch.empty(B, GH, GW, dtype=torch.uint8, device=maps[0].device)
+    ws_bytes = lib.pv2_infer_tail_workspace_bytes(B)
+    wsp = torch.empty((ws_bytes + 3) // 4, dtype=torch.int32, device=maps[0].device)
+    pm, k0 = _lib.ptr_array(maps)
+    ph, k1 = _lib.int_array(hs)
+    pw, k2 = _lib.int_array(ws)
+    prh, k3 = _lib.float_array(rhs)
+    prw, k4 = _lib.float_array(rws)
+    _lib.check(lib.pv2_infer_tail_binary(pm, ph, pw, prh, prw, len(maps), B, SH, SW, GH, GW, _ratio(SH, GH, False, None), _ratio(SW, GW, False, None),
+                                         out.data_ptr(), wsp.data_ptr(), ws_bytes, _stream()), "pv2_infer_tail_binary")
+    return out
+
+
+@torch.no_grad()
+def infer_tail_argmax(P_fg, P_bg, scale_factors):
+    """Label maps of EMCAD/utils/utils.py:261-273 (use_dual): argmax_c sum_k (up(P_fg_k) - up(P_bg_k)) from the LOW-RES
+    (B, C, h_k, w_k) stage maps; scale_factors as in EMCAD/lib/networks.py:116-123 (32, 16, 8, 4).  Returns uint8 (B, H, W)."""
+    P_fg = [m.contiguous().float() for m in P_fg]
+    P_bg = [m.contiguous().float() for m in P_bg]
+    _need_cuda(*P_fg, *P_bg)
+    lib = _lib.load()
+    B, Cc = P_fg[0].shape[:2]
+    if len(P_fg) != len(P_bg) or any(a.shape != b.shape or a.shape[:2] != (B, Cc) for a, b in zip(P_fg, P_bg)):
+        raise ValueError("infer_tail_argmax: foreground / background maps must pair up and share (B, C)")
+    hs, ws, rhs, rws, (H, W) = _tail_geometry(P_fg, scale_factors)
+    out = torch.empty(B, H, W, dtype=torch.uint8, device=P_fg[0].device)
+    pf, k0 = _lib.ptr_array(P_fg)
+    pb, k5 = _lib.ptr_array(P_bg)
+    ph, k1 = _lib.int_array(hs)
+    pw, k2 = _lib.int_array(ws)
+    prh, k3 = _lib.float_array(rhs)
+    prw, k4 = _lib.float_array(rws)
+    _lib.check(lib.pv2_infer_tail_argmax(pf, pb, ph, pw, prh, prw, len(P_fg), B, Cc, H, W, out.data_ptr(), _stream()), "pv2_infer_tail_argmax")
+    return out

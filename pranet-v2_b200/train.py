@@ -58,9 +58,70 @@ class FlatGradBucket:
             p.grad = v
 
 
+def _is_dense(t: torch.Tensor) -> bool:
+    """True when the tensor's elements tile numel() consecutive storage slots (contiguous in some dimension order)."""
+    expect = 1
+    for size, stride in sorted(((sz, st) for sz, st in zip(t.shape, t.stride()) if sz > 1), key=lambda x: x[1]):
+        if stride != expect:
+            return False
+        expect *= size
+    return True
+
+
+class FlatParams:
+    """Every trainable parameter, its gradient and both Adam moments in FOUR flat fp32 buffers sharing ONE layout (each
+    tensor's offset padded to 4 elements = 16 bytes), so the optimizer tail -- all-reduce mean, clip_gradient
+    (binary_seg/utils/utils.py:7-17) and Adam / AdamW (MyTrain_med.py:148-149, EMCAD/trainer.py:86) -- is a single
+    streaming launch (pv2_adam_clamp_flat) over 28 bytes per element instead of ~950 tensors walked twice.
+    The parameters are re-pointed at views of the flat buffer (same shapes and strides, values preserved), the gradient
+    buffer doubles as the all-reduce message."""
+
+    def __init__(self, params, device, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, clip=0.5):
+        self.params = list(params)
+        self.offsets, o = [], 0
+        for p in self.params:
+            self.offsets.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.n = max(o, 4)
+        self.p = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.g = torch.zeros_like(self.p)
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=device)
+        self.views = []
+        for p, off in zip(self.params, self.offsets):
+            if p.dtype != torch.float32:
+                raise TypeError("FlatParams holds fp32 master parameters")
+            src = p.data if _is_dense(p.data) else p.data.contiguous()
+            pv = torch.as_strided(self.p, src.shape, src.stride(), storage_offset=off)
+            pv.copy_(src)
+            p.data = pv                                                                # the module now trains the flat storage
+            self.views.append(torch.as_strided(self.g, src.shape, src.stride(), storage_offset=off))
+        self.flat = self.g                                                             # the all-reduce message
+        self.lr, self.betas, self.eps, self.weight_decay, self.decoupled, self.clip = lr, betas, eps, weight_decay, decoupled, clip
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+    def gather(self, grads):
+        torch._foreach_copy_(self.views, [g if g is not None else torch.zeros_like(v) for g, v in zip(grads, self.views)])
+
+    def all_reduce_sum(self):
+        if self.world > 1:
+            dist.all_reduce(self.g)
+
+    def update(self):
+        """mean over ranks + clamp + Adam(W) + step counter: ONE launch on the current stream."""
+        lib = _lib.load()
+        _lib.check(lib.pv2_adam_clamp_flat(self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.n,
+                                           self.step.data_ptr(), self.ticket.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                           self.weight_decay, int(self.decoupled), self.clip if self.clip else float("inf"),
+                                           1.0 / self.world, torch.cuda.current_stream().cuda_stream), "pv2_adam_clamp_flat")
+
+
 class TrainStep:
     def __init__(self, model: nn.Module, lr: float = 1e-4, clip: float = 0.5, autocast_backbone: bool = True,
-                 device=None, channels_last: bool = True, use_graph: bool = True):
+                 device=None, channels_last: bool = True, use_graph: bool = True, optimizer: str = "pv2",
+                 weight_decay: float = 0.0, decoupled: bool = False):
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.model = model.to(self.device).train()
         if channels_last:
@@ -76,12 +137,19 @@ class TrainStep:
         if self.world > 1:   # identical replicas to start from
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, 0)
-        self.bucket = FlatGradBucket(self.params, self.device)
+        if optimizer == "pv2":      # flat parameters + the fused clamp/Adam stream (pv2_adam_clamp_flat)
+            self.bucket = FlatParams(self.params, self.device, lr=lr, weight_decay=weight_decay, decoupled=decoupled, clip=clip)
+            self.opt = None
+        elif optimizer == "torch":  # stock torch.optim on a flat gradient bucket (kept for A/B measurements and the parity tests)
+            self.bucket = FlatGradBucket(self.params, self.device)
+            cls = torch.optim.AdamW if decoupled else torch.optim.Adam
+            self.opt = cls(self.params, lr, weight_decay=weight_decay, fused=True, capturable=True)   # MyTrain_med.py:148-149
+        else:
+            raise ValueError(f"optimizer must be 'pv2' or 'torch', got {optimizer!r}")
         self.flat = self.bucket.flat
-        self.opt = torch.optim.Adam(self.params, lr, fused=True, capturable=True)   # MyTrain_med.py:148-149
         self.clip, self.autocast, self.channels_last, self.use_graph = clip, autocast_backbone, channels_last, use_graph
-        self._static = None
-        self._loss = None
+        self._graphs = {}      # (image shape, mask shape) -> (graph_a, graph_b, static image, static mask, loss)
+        self._pool = None
         self.pv2_launches_per_step = 0
 
     # -- the two halves of a step ------------------------------------------------------------------------
@@ -97,6 +165,8 @@ class TrainStep:
         return loss.detach()
 
     def _update(self):
+        if self.opt is None:
+            return self.bucket.update()
         self.bucket.scale_for_mean()
         self.bucket.clamp_(self.clip)
         self.bucket.install(self.params)
@@ -104,29 +174,48 @@ class TrainStep:
 
     # -- graph capture ------------------------------------------------------------------------------------------
     def _capture(self, images, gts):
-        self._img = torch.empty(images.shape, dtype=images.dtype, device=self.device,
-                                memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
-        self._gt = torch.empty(gts.shape, dtype=gts.dtype, device=self.device)
-        self._img.copy_(images)
-        self._gt.copy_(gts)
+        """Capture the step for one input shape.  Every shape (the multi-scale loop of MyTrain_med.py:59-74 uses three) gets its
+        own pair of graphs and static input buffers; all of them share one memory pool (they never run concurrently) and, of
+        course, the parameters / optimizer state."""
+        img = torch.empty(images.shape, dtype=images.dtype, device=self.device,
+                          memory_format=torch.channels_last if self.channels_last else torch.contiguous_format)
+        gt = torch.empty(gts.shape, dtype=gts.dtype, device=self.device)
+        img.copy_(images)
+        gt.copy_(gts)
+        # warm-up (cuDNN autotune, allocator, lazy inits) must not train: with the flat layout the whole training state is
+        # four buffers + the BatchNorm statistics, snapshotted here and put back before the capture
+        snap = None
+        if self.opt is None:
+            b = self.bucket
+            snap = ([b.p.clone(), b.m.clone(), b.v.clone(), b.step.clone()], [t.clone() for t in self.model.buffers()])
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):                                       # warm-up: cuDNN autotune, allocator, lazy inits
-                self._fwd_bwd(self._img, self._gt)
+            for _ in range(3):
+                self._fwd_bwd(img, gt)
                 if self.world > 1:
                     dist.all_reduce(self.flat)
                 self._update()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        if snap is not None:
+            for dst, src in zip([b.p, b.m, b.v, b.step], snap[0]):
+                dst.copy_(src)
+            for dst, src in zip(self.model.buffers(), snap[1]):
+                dst.copy_(src)
+            del snap
+            torch.cuda.synchronize()
+        graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = self._pool
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph_a):
-            self._loss = self._fwd_bwd(self._img, self._gt)
-        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+        with torch.cuda.graph(graph_a, pool=pool):
+            loss = self._fwd_bwd(img, gt)
+        if pool is None:
+            pool = self._pool = graph_a.pool()
+        with torch.cuda.graph(graph_b, pool=pool):
             self._update()
         self.pv2_launches_per_step = _lib.launch_count() - n0     # pv2 kernel nodes inside the two graphs
-        self._static = (tuple(images.shape), tuple(gts.shape))
+        return graph_a, graph_b, img, gt, loss
 
     # -- public steps -------------------------------------------------------------------------------------------
     def step_device(self, images: torch.Tensor, gts: torch.Tensor) -> torch.Tensor:
@@ -137,20 +226,39 @@ class TrainStep:
                 images = images.contiguous(memory_format=torch.channels_last)
             n0 = _lib.launch_count()
             loss = self._fwd_bwd(images, gts)
-            self.pv2_launches_per_step = _lib.launch_count() - n0
             if self.world > 1:
                 dist.all_reduce(self.flat)
             self._update()
+            self.pv2_launches_per_step = _lib.launch_count() - n0
             return loss
-        if self._static != (tuple(images.shape), tuple(gts.shape)):
-            self._capture(images, gts)
-        self._img.copy_(images, non_blocking=True)
-        self._gt.copy_(gts, non_blocking=True)
-        self.graph_a.replay()
+        key = (tuple(images.shape), tuple(gts.shape))
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(images, gts)
+        graph_a, graph_b, img, gt, loss = self._graphs[key]
+        img.copy_(images, non_blocking=True)
+        gt.copy_(gts, non_blocking=True)
+        graph_a.replay()
         if self.world > 1:
             dist.all_reduce(self.flat)                               # NCCL over NVLink: the path's only collective
-        self.graph_b.replay()
-        return self._loss
+        graph_b.replay()
+        return loss
+
+    def step_multiscale(self, images: torch.Tensor, gts: torch.Tensor, trainsize: int = 352, rates=(0.75, 1, 1.25)):
+        """The inner loop of binary_seg/MyTrain_med.py:59-86: one optimizer step per size rate, images and masks rescaled
+        with bilinear align_corners=True (:70-73) ON THE DEVICE by the pv2 resize kernel (the soft mask values this produces at
+        rates != 1 are what structure_loss then sees), bg_mask = 1 - gts derived inside the loss kernel (:74).
+        Returns the list of per-rate losses (device tensors)."""
+        images, gts = images.to(self.device, non_blocking=True), gts.to(self.device, non_blocking=True)
+        losses = []
+        for rate in rates:
+            size = int(round(trainsize * rate / 32) * 32)
+            if rate != 1:
+                im = ops.interpolate_bilinear(images.float().contiguous(), size=(size, size), align_corners=True)
+                gt = ops.interpolate_bilinear(gts.float().contiguous(), size=(size, size), align_corners=True)
+            else:
+                im, gt = images, gts
+            losses.append(self.step_device(im, gt).clone())
+        return losses
 
     def step_host(self, images_pinned: torch.Tensor, gts_pinned: torch.Tensor) -> float:
         """End-to-end step: pinned host inputs -> H2D -> step -> loss read back to the host."""

@@ -165,3 +165,55 @@ def test_multiclass_dsra_stages_golden(name):
     ours = sum(_sub(ups[i], 2) - _sub(ups[i + 4], 2) for i in range(4)).argmax(1)
     theirs = sum(g[f"up{i}"] - g[f"up{i + 4}"] for i in range(4)).argmax(1)
     assert (ours == theirs).mean() >= 0.999
+
+
+def test_train_step_flat_adam_matches_torch_optimizer():
+    """The same three eager training steps with the fused optimizer tail (flat parameters + pv2_adam_clamp_flat) and with
+    clamp_ + torch.optim.Adam on a gradient bucket end at the same parameters."""
+    from pranet_v2_b200.train import TrainStep
+    from pranet_v2_b200 import synthetic
+    det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        finals = []
+        for optimizer in ("pv2", "torch"):
+            torch.manual_seed(0)
+            m = P.PraNet_V2(num_class=1)
+            m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=3))
+            ts = TrainStep(m, lr=1e-4, clip=0.5, autocast_backbone=False, device="cuda:0", use_graph=False, optimizer=optimizer)
+            for i in range(3):
+                x = synthetic.images(2, 96, i).to(DEV)
+                gt = synthetic.ellipse_masks(2, 96, 96, i).to(DEV)
+                loss = float(ts.step_device(x, gt))
+                assert np.isfinite(loss)
+            finals.append(torch.cat([p.detach().flatten().cpu() for p in ts.params]))
+            if optimizer == "pv2":
+                assert int(ts.bucket.step.item()) == 3
+        d = (finals[0] - finals[1]).abs()
+        # Adam moves every element by ~lr per step whatever the gradient's size, so an element whose gradient is at rounding
+        # level may legitimately differ by a few lr; the bulk must agree to fp32 rounding
+        assert d.mean().item() <= 1e-6 and (d <= 2e-6).float().mean().item() >= 0.99 and d.max().item() <= 7e-4
+    finally:
+        torch.backends.cudnn.deterministic = det
+
+
+def test_train_step_multiscale_graphs():
+    """MyTrain_med.py:59-86: three size rates per batch, resized on the device; one captured graph pair per shape, all sharing
+    the parameters; capture warm-ups leave the training state untouched."""
+    from pranet_v2_b200.train import TrainStep
+    from pranet_v2_b200 import synthetic
+    torch.manual_seed(0)
+    m = P.PraNet_V2(num_class=1)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=3))
+    ts = TrainStep(m, lr=1e-4, clip=0.5, autocast_backbone=False, device="cuda:0", use_graph=True)
+    x = synthetic.images(2, 128, 0).to(DEV)
+    gt = synthetic.ellipse_masks(2, 128, 128, 0).to(DEV)
+    p0 = ts.bucket.p.clone()
+    losses = [float(v) for v in ts.step_multiscale(x, gt, trainsize=128)]
+    assert len(losses) == 3 and all(np.isfinite(v) for v in losses)
+    assert len(ts._graphs) == 3 and {k[0][-1] for k in ts._graphs} == {96, 128, 160}
+    assert int(ts.bucket.step.item()) == 3                        # exactly three optimizer steps: the 9 warm-up steps were undone
+    moved = (ts.bucket.p - p0).abs().max().item()
+    assert 0 < moved <= 3.5e-4                                     # at most 3 x lr (bias-corrected Adam step <= lr per step ... first steps)
+    again = [float(v) for v in ts.step_multiscale(x, gt, trainsize=128)]
+    assert len(ts._graphs) == 3 and sum(again) < sum(losses)        # replays only, and it trains
