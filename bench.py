@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--profile-only", action="store_true",
+                    help="run the warm-up + timed steps only (no e2e / roofline / CPU legs) and exit: the command ncu wraps for the launch list")
     return ap.parse_args()
 
 
@@ -202,6 +204,13 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ts.pv2_launches_per_step * args.steps   # pv2 kernel nodes replayed inside the CUDA graphs of the timed steps
     clocks = sampler.stop() if rank == 0 else None
+
+    if args.profile_only:
+        if rank == 0:
+            print(json.dumps({"profile_only": True, "ms_per_step": ms / args.steps, "gpu_launches": int(launches), "steps": args.steps}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- end-to-end timing: pinned host inputs -> H2D -> step -> loss D2H every step ----
     for i in range(2):

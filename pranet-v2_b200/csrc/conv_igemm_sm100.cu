@@ -60,7 +60,7 @@ struct ConvArgs {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(THREADS, 3)   // up to 3 co-resident CTAs (plan_stages)
+__global__ void __launch_bounds__(THREADS, 4)   // up to MAX_CTAS_PER_SM co-resident CTAs (plan_stages)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs a,
                 const __grid_constant__ BnFuseDev bn) {
@@ -304,7 +304,7 @@ struct WgradArgs {
 template <int KIND> struct WgradCfg { static constexpr int STAGES_ = KIND == 0 ? 3 : 2; static constexpr int BN_MAX = KIND == 0 ? 128 : 64; };   // STAGES_: upper bound
 
 template <int KIND>
-__global__ void __launch_bounds__(THREADS, 3)
+__global__ void __launch_bounds__(THREADS, 4)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constant__ CUtensorMap tmG1,
                   const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1, const WgradArgs a) {
     constexpr int KC = (KIND == 0) ? 64 : 32;
@@ -540,20 +540,23 @@ uint32_t pow2_cols(int n) {
     return c;
 }
 
-// How many pipeline stages a CTA gets.  The head's GEMMs are short (8..100 K iterations per CTA) and their epilogue (TMEM ->
-// registers -> global, plus the fused BatchNorm statistics) is as long as the main loop, so instead of one CTA owning the
-// whole SM with a deep ring, several CTAs with a shallow ring share it: one CTA's epilogue / prologue overlaps another's
-// MMAs, and grids of 150..300 tiles run as ONE wave.  Bounded by shared memory (227 KB), by TMEM (512 columns) and by the
-// scratch the statistics epilogue needs.  PV2_CONV_STAGES / PV2_CONV_CTAS override (profiling sweeps).
+// How many pipeline stages a CTA gets.  The head's GEMMs are short (8..100 K iterations per CTA), their epilogue (TMEM ->
+// registers -> global, plus the fused BatchNorm statistics) is as long as the main loop, and up to twelve independent chains
+// of the head run concurrently on side streams.  So instead of one CTA owning an SM with a deep ring, a CTA takes the
+// SMALLEST footprint that still pipelines (>= 2 stages) and up to MAX_CTAS_PER_SM CTAs -- of this grid or of a sibling
+// chain's kernel -- share the SM: one CTA's epilogue / prologue overlaps another's MMAs, and grids of 150..600 tiles run as
+// one wave.  Measured on the B=16 x 352^2 head step (fwd + loss + bwd, CUDA graph): 1 CTA/SM 3.15 ms, 2: 2.84 ms, 3: 2.73 ms.
+// Bounded by shared memory (227 KB), TMEM (512 columns) and the scratch the statistics epilogue needs.
+// PV2_CONV_CTAS / PV2_CONV_STAGES override (profiling sweeps).
+constexpr int MAX_CTAS_PER_SM = 4;      // == the kernels' __launch_bounds__ minimum-blocks argument
 int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && e[0]) ? atoi(e) : dflt;
 }
-int plan_stages(long long ctas, int iters, size_t stage_bytes, uint32_t tmem_cols, size_t min_bytes, int max_stages) {
+int plan_stages(int iters, size_t stage_bytes, uint32_t tmem_cols, size_t min_bytes, int max_stages) {
     static const int force_stages = env_int("PV2_CONV_STAGES", 0), force_ctas = env_int("PV2_CONV_CTAS", 0);
-    int target = force_ctas > 0 ? force_ctas : (int)((ctas + kNumSMs - 1) / kNumSMs);
-    if (target > 3) target = 3;
-    if (target < 1) target = 1;
+    int target = force_ctas > 0 ? force_ctas : 3;
+    if (target > MAX_CTAS_PER_SM) target = MAX_CTAS_PER_SM;
     while (target > 1 && (uint32_t)target * tmem_cols > 512u) --target;
     int stages = max_stages;
     for (;; --target) {
@@ -652,7 +655,7 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     dim3 grid(im2col ? (unsigned)((a.M + BM - 1) / BM) : (unsigned)(N * a.tiles_x * a.tiles_y), (Cout + a.BN - 1) / a.BN, splits);
     const size_t stage_bytes = A_BYTES + (size_t)a.BN * ROW_BYTES;
     const size_t stats_scratch = a.stats ? (size_t)(4 * 32 * 33 + 4 * a.BN * 2) * sizeof(float) : 0;   // epilogue reuses the ring
-    a.stages = plan_stages((long long)grid.x * grid.y * grid.z, a.iters_per_split, stage_bytes, a.tmem_cols, stats_scratch, MAX_STAGES);
+    a.stages = plan_stages(a.iters_per_split, stage_bytes, a.tmem_cols, stats_scratch, MAX_STAGES);
     const size_t smem = (size_t)a.stages * stage_bytes + 1024;
     PV2_CHECK(smem <= 227 * 1024 && smem - 1024 >= stats_scratch, "conv_fwd: bad stage plan (%d stages of %zu B)", a.stages, stage_bytes);
     cudaStream_t st = (cudaStream_t)stream;
@@ -726,7 +729,7 @@ extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const v
     }
     dim3 grid(a.taps, ((Cout + BM - 1) / BM) * a.ci_tiles, splits);
     const size_t wstage_bytes = (size_t)((BM / KC) + (a.BN / KC)) * A_BYTES;
-    a.stages = plan_stages((long long)grid.x * grid.y * grid.z, a.tiles_per_split * nterms, wstage_bytes, a.tmem_cols, 0,
+    a.stages = plan_stages(a.tiles_per_split * nterms, wstage_bytes, a.tmem_cols, 0,
                            k == 0 ? WgradCfg<0>::STAGES_ : WgradCfg<1>::STAGES_);
     const size_t smem = (size_t)a.stages * wstage_bytes + 1024;
     PV2_CHECK(smem <= 227 * 1024, "conv_wgrad: stage too large (%zu B)", smem);

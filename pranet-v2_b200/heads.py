@@ -126,21 +126,27 @@ def aggregation_run(eng, agg: "aggregation", x1: E.Act, x2: E.Act, x3: E.Act):
     """aggregation.forward (pranet.py:109-125): x1 deepest (H/32), x2 (H/16), x3 (H/8).  Returns the list of
     head Maps ([fg, bg] for V2, [single] for V1)."""
     c = x1.C
-    up_x1 = eng.up2(x1)
-    upup_x1 = eng.up2(up_x1)
-    up_x2 = eng.up2(x2)
-    # conv_upsample1 and conv_upsample4 read the same tensor: one GEMM
-    raw_a = eng.conv(up_x1, [agg.conv_upsample1.conv, agg.conv_upsample4.conv], [agg.conv_upsample1.bn, agg.conv_upsample4.bn])
     cat2, s2 = eng.concat_buffer(x2.N, x2.H, x2.W, [c, c])
-    eng.bn_apply((raw_a, 0, c, agg.conv_upsample1.bn, None), mult=x2, out=s2[0])                       # x2_1
-    eng.bn_apply((raw_a, c, c, agg.conv_upsample4.bn, None), out=s2[1])
-    x2_2 = agg.conv_concat2.run(eng, cat2)
-    raw_b = eng.conv(upup_x1, [agg.conv_upsample2.conv], [agg.conv_upsample2.bn])
-    raw_c = eng.conv(up_x2, [agg.conv_upsample3.conv], [agg.conv_upsample3.bn])
     cat3, s3 = eng.concat_buffer(x3.N, x3.H, x3.W, [c, 2 * c])
-    eng.bn_apply((raw_b, 0, c, agg.conv_upsample2.bn, None), src2=(raw_c, 0, c, agg.conv_upsample3.bn, None),
+    # three independent chains (pranet.py:109-118): [up(x1) -> conv_upsample1|4 -> x2_1, cat2 -> conv_concat2 -> up -> conv_upsample5],
+    # [up(up(x1)) -> conv_upsample2] and [up(x2) -> conv_upsample3]; they meet in x3_1 = conv_upsample2(.) * conv_upsample3(.) * x3
+    res = {}
+    eng.fork(3)
+    with eng.branch(1):
+        up_x1 = eng.up2(x1)
+        # conv_upsample1 and conv_upsample4 read the same tensor: one GEMM
+        raw_a = eng.conv(up_x1, [agg.conv_upsample1.conv, agg.conv_upsample4.conv], [agg.conv_upsample1.bn, agg.conv_upsample4.bn])
+        eng.bn_apply((raw_a, 0, c, agg.conv_upsample1.bn, None), mult=x2, out=s2[0])                   # x2_1
+        eng.bn_apply((raw_a, c, c, agg.conv_upsample4.bn, None), out=s2[1])
+        x2_2 = agg.conv_concat2.run(eng, cat2)
+        agg.conv_upsample5.run(eng, eng.up2(x2_2), out=s3[1])
+    with eng.branch(2):
+        res["b"] = eng.conv(eng.up2(eng.up2(x1)), [agg.conv_upsample2.conv], [agg.conv_upsample2.bn])
+    with eng.branch(3):
+        res["c"] = eng.conv(eng.up2(x2), [agg.conv_upsample3.conv], [agg.conv_upsample3.bn])
+    eng.join()
+    eng.bn_apply((res["b"], 0, c, agg.conv_upsample2.bn, None), src2=(res["c"], 0, c, agg.conv_upsample3.bn, None),
                  combine=2, mult=x3, out=s3[0])                                                         # x3_1
-    agg.conv_upsample5.run(eng, eng.up2(x2_2), out=s3[1])
     x3_2 = agg.conv_concat3.run(eng, cat3)
     x = agg.conv4.run(eng, x3_2)
     heads = [agg.conv5] if hasattr(agg, "conv5") else [agg.conv5_fg, agg.conv5_bg]
