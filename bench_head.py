@@ -103,6 +103,10 @@ def trace_graph(graph, path, B, S, reps=3):
         for _ in range(reps):
             graph.replay()
         torch.cuda.synchronize()
+    try:
+        prof.export_chrome_trace(path + ".chrome.json")      # per-kernel (stream, start, end): the step's timeline for offline analysis
+    except Exception as exc:                                  # noqa: BLE001 -- the aggregate below does not depend on it
+        print("chrome trace export failed:", exc)
     evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start],
                  key=lambda e: e.time_range.start)
     agg = collections.defaultdict(lambda: [0, 0.0])

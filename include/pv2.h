@@ -166,7 +166,9 @@ int pv2_conv_fuses_bn_stats(int splits, int out_mode);
 int pv2_bn_stats_group(float* y, long long slab_stride, int nslabs, long long M, int Cout, int ld, const pv2_bn_fuse* bn, void* stream);
 
 /* out_mode 0: raw fp32 out[split][N*H*W][ldo] (split-K partial slabs, summed by pv2_bn_stats / the consumers);
- * out_mode 1: fp32 NCHW out[N][Cout][H][W] + bias (bias may be NULL), splits must be 1.
+ * out_mode 1: fp32 NCHW out[N][Cout][H][W] + bias (bias may be NULL), splits must be 1;
+ * out_mode 2: bf16 rows out[N*H*W][ldo] (ldo % 8 == 0; `out` is really a bf16 pointer) = a torch channels_last bf16 tensor, splits
+ *             must be 1 -- the dgrad of the GEMM that reads a backbone feature writes the feature gradient in its final form.
  * Also computes dgrad when given the mode-1 packed weights (Cin_p := padded Cout, Cout := Cin). */
 int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms);
 int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,

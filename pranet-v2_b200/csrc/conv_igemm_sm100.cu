@@ -40,6 +40,11 @@ constexpr int A_BYTES = BM * ROW_BYTES; // 16 KB
 constexpr int MAX_STAGES = 6;           // mbarrier ring capacity; the launch picks 2..6 stages so that several CTAs share an SM
 constexpr int THREADS = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 struct ConvArgs {
     int H, W, Cout;
     int KW, taps, dil_h, dil_w, pad_h, pad_w;
@@ -52,7 +57,7 @@ struct ConvArgs {
     int BN;                 // N tile (multiple of 16, <= 256)
     int stages;             // depth of the TMA -> MMA ring (2..MAX_STAGES)
     uint32_t tmem_cols;     // power of two >= max(32, BN)
-    int out_mode;           // 0: raw fp32 [split][pixel][ldo]   1: NCHW fp32 + bias
+    int out_mode;           // 0: raw fp32 [split][pixel][ldo]   1: NCHW fp32 + bias   2: bf16 [pixel][ldo] (channels_last tensor)
     float* out;
     long long split_stride; // elements between split slabs (mode 0)
     int ldo;
@@ -210,6 +215,19 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                     if (n0 + c0 + j + 3 < a.ldo)
                         *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                }
+            } else if (a.out_mode == 2) {   // bf16 rows [pixel][ldo]: a channels_last bf16 tensor (the gradient of a backbone feature), final
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ldo + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (n0 + c0 + j + 7 < a.ldo) {
+                        uint4 u;
+                        u.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                        u.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        u.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                        u.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                        *reinterpret_cast<uint4*>(dst + j) = u;
+                    }
                 }
             } else {
 #pragma unroll
@@ -553,9 +571,11 @@ int env_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return (e && e[0]) ? atoi(e) : dflt;
 }
-int plan_stages(int iters, size_t stage_bytes, uint32_t tmem_cols, size_t min_bytes, int max_stages) {
+int plan_stages(long long ctas, int iters, size_t stage_bytes, uint32_t tmem_cols, size_t min_bytes, int max_stages) {
     static const int force_stages = env_int("PV2_CONV_STAGES", 0), force_ctas = env_int("PV2_CONV_CTAS", 0);
+    static const int small_grid = env_int("PV2_CONV_SMALL", 0);   // grids up to this many CTAs take the deepest ring (latency mode)
     int target = force_ctas > 0 ? force_ctas : 3;
+    if (ctas <= small_grid) target = 1;
     if (target > MAX_CTAS_PER_SM) target = MAX_CTAS_PER_SM;
     while (target > 1 && (uint32_t)target * tmem_cols > 512u) --target;
     int stages = max_stages;
@@ -609,8 +629,9 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
                             int out_mode, float* out, int ldo, int splits, const float* bias, const pv2_bn_fuse* bn, void* stream) {
     if (int e = common_checks("conv_fwd", kind, nterms, N, H, W, Cin_p, Cout, KH, KW)) return e;
     PV2_CHECK(x && w_op && out, "conv_fwd: null pointer");
-    PV2_CHECK(out_mode == 0 || out_mode == 1, "conv_fwd: bad out_mode %d", out_mode);
+    PV2_CHECK(out_mode >= 0 && out_mode <= 2, "conv_fwd: bad out_mode %d", out_mode);
     PV2_CHECK(out_mode == 1 || (ldo % 4 == 0 && ldo >= Cout), "conv_fwd: ldo=%d must be a multiple of 4 and >= Cout=%d", ldo, Cout);
+    PV2_CHECK(out_mode != 2 || (ldo % 8 == 0 && ((uintptr_t)out & 15) == 0), "conv_fwd: bf16 row output needs ldo %% 8 == 0 and a 16-byte aligned base");
     PV2_CHECK(out_mode == 0 || splits == 1, "conv_fwd: split-K needs the raw output mode");
     const bool im2col = use_im2col();
     if (out_mode == 0 && !im2col) flatten_1x1(KH, KW, &N, &H, &W);
@@ -655,7 +676,7 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     dim3 grid(im2col ? (unsigned)((a.M + BM - 1) / BM) : (unsigned)(N * a.tiles_x * a.tiles_y), (Cout + a.BN - 1) / a.BN, splits);
     const size_t stage_bytes = A_BYTES + (size_t)a.BN * ROW_BYTES;
     const size_t stats_scratch = a.stats ? (size_t)(4 * 32 * 33 + 4 * a.BN * 2) * sizeof(float) : 0;   // epilogue reuses the ring
-    a.stages = plan_stages(a.iters_per_split, stage_bytes, a.tmem_cols, stats_scratch, MAX_STAGES);
+    a.stages = plan_stages((long long)grid.x * grid.y * grid.z, a.iters_per_split, stage_bytes, a.tmem_cols, stats_scratch, MAX_STAGES);
     const size_t smem = (size_t)a.stages * stage_bytes + 1024;
     PV2_CHECK(smem <= 227 * 1024 && smem - 1024 >= stats_scratch, "conv_fwd: bad stage plan (%d stages of %zu B)", a.stages, stage_bytes);
     cudaStream_t st = (cudaStream_t)stream;
@@ -729,7 +750,7 @@ extern "C" int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const v
     }
     dim3 grid(a.taps, ((Cout + BM - 1) / BM) * a.ci_tiles, splits);
     const size_t wstage_bytes = (size_t)((BM / KC) + (a.BN / KC)) * A_BYTES;
-    a.stages = plan_stages(a.tiles_per_split * nterms, wstage_bytes, a.tmem_cols, 0,
+    a.stages = plan_stages((long long)grid.x * grid.y * grid.z, a.tiles_per_split * nterms, wstage_bytes, a.tmem_cols, 0,
                            k == 0 ? WgradCfg<0>::STAGES_ : WgradCfg<1>::STAGES_);
     const size_t smem = (size_t)a.stages * wstage_bytes + 1024;
     PV2_CHECK(smem <= 227 * 1024, "conv_wgrad: stage too large (%zu B)", smem);

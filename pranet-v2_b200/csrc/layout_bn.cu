@@ -87,51 +87,125 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ part, long long sp
 
 // multi-tensor variants: a handful of launches pack every conv weight of the head (both layouts) / unpack every weight
 // gradient.  The descriptors travel BY VALUE in the kernel parameters (<= 4 KB per launch), so nothing has to be staged
-// in device memory and the launches are CUDA-graph capturable as they are.  Each thread owns one OIHW element of the
-// batch's concatenated index space and finds its tensor by binary search on `start`.
-constexpr int PACK_BATCH = 40;     // 40 * 88 B  = 3520 B of kernel parameters
-constexpr int UNPACK_BATCH = 56;   // 56 * 64 B  = 3584 B
-struct PackBatch { pv2_pack_desc d[PACK_BATCH]; };
-struct UnpackBatch { pv2_unpack_desc d[UNPACK_BATCH]; };
+// in device memory and the launches are CUDA-graph capturable as they are.
+// Work unit = one TILE of one tensor: (co tile, ci tile, all taps), staged in shared memory so that the OIHW side AND the
+// operand side are both accessed in contiguous runs (the three layouts [co][ci][tap], [co][tap][ci] and [ci][tap'][co] are
+// permutations of each other: an element-per-thread walk is coalesced on one side only and pays one 32-byte sector per 2-byte
+// element on the other).  A CTA finds its tensor once (binary search over the per-tensor tile prefix), not once per element,
+// and all in-tensor index arithmetic is 32-bit.
+constexpr int PACK_BATCH = 40;     // 40 * 88 B + 41 * 4 B = 3684 B of kernel parameters
+constexpr int UNPACK_BATCH = 56;   // 56 * 64 B + 57 * 4 B = 3812 B
+constexpr int PK_TCI = 32, UP_TCI = 32;    // input channels per tile
+// output channels per tile: ~12800 (pack) / ~2048 (unpack) elements whatever the filter size, so a 1x1 tile is not 25x
+// smaller than a 5x5 one.  pack keeps >= 16 so that the dgrad layout's co runs stay >= one 32-byte sector.
+__host__ __device__ inline int pk_tco(int taps) { const int t = 12800 / (PK_TCI * taps); return t < 16 ? 16 : (t > 128 ? 128 : t); }
+constexpr int UP_EPT = 8, UP_SPU = 8;       // elements per thread of an unpack tile (2048 / 256); splits fetched per round trip
+__host__ __device__ inline int up_tco(int taps) { const int t = 2048 / (UP_TCI * taps); return t < 1 ? 1 : (t > 64 ? 64 : t); }
+struct PackBatch { pv2_pack_desc d[PACK_BATCH]; int tile_start[PACK_BATCH + 1]; };
+struct UnpackBatch { pv2_unpack_desc d[UNPACK_BATCH]; int tile_start[UNPACK_BATCH + 1]; };
+
+template <int NB>
+__device__ __forceinline__ int find_tensor(const int* tile_start, int n, int tile) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_start[mid] <= tile) lo = mid; else hi = mid - 1; }
+    return lo;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(256)
-weight_pack_multi_kernel(const __grid_constant__ PackBatch b, int n, long long base, long long total, int nplanes) {
+weight_pack_multi_kernel(const __grid_constant__ PackBatch b, int n, int nplanes) {
     pv2::pdl_prologue();
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = n - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.d[mid].start - base <= e) lo = mid; else hi = mid - 1; }
-        const pv2_pack_desc& t = b.d[lo];
-        const long long l = e - (t.start - base);
-        const int kw = (int)(l % t.KW);
-        const int kh = (int)((l / t.KW) % t.KH);
-        const int ci = (int)((l / ((long long)t.KW * t.KH)) % t.Cin);
-        const int co = (int)(l / ((long long)t.KW * t.KH * t.Cin));
-        const int taps = t.KH * t.KW;
-        const float v = t.w[l];
-        store_op<KIND>(t.out_f, t.f_plane, nplanes, ((long long)(co + t.f_ooff) * taps + kh * t.KW + kw) * t.f_ild + t.f_ioff + ci, v);
-        if (t.out_d)
-            store_op<KIND>(t.out_d, t.d_plane, nplanes,
-                           ((long long)(ci + t.d_ooff) * taps + (t.KH - 1 - kh) * t.KW + (t.KW - 1 - kw)) * t.d_ild + t.d_ioff + co, v);
+    extern __shared__ float pk_tile[];           // [pk_tco(taps)][PK_TCI * taps + 1]
+    __shared__ int s_t;
+    if (threadIdx.x == 0) s_t = find_tensor<PACK_BATCH>(b.tile_start, n, (int)blockIdx.x);
+    __syncthreads();
+    const pv2_pack_desc& t = b.d[s_t];
+    const int taps = t.KH * t.KW;
+    const int ci_tiles = (t.Cin + PK_TCI - 1) / PK_TCI;
+    const int lt = (int)blockIdx.x - b.tile_start[s_t];
+    const int TCO = pk_tco(taps);
+    const int co0 = (lt / ci_tiles) * TCO, ci0 = (lt % ci_tiles) * PK_TCI;
+    const int nco = min(TCO, t.Cout - co0), nci = min(PK_TCI, t.Cin - ci0);
+    const int run = nci * taps, pitch = PK_TCI * taps + 1;
+    // OIHW side: for every co of the tile the (ci, tap) run is contiguous
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+        const int col = i / run, j = i - col * run;
+        pk_tile[col * pitch + j] = __ldg(t.w + ((size_t)(co0 + col) * t.Cin + ci0) * taps + j);
+    }
+    __syncthreads();
+    // fprop layout [co][tap][ci]: ci fastest
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+        const int cil = i % nci, r = i / nci, tap = r % taps, col = r / taps;
+        store_op<KIND>(t.out_f, t.f_plane, nplanes, ((long long)(co0 + col + t.f_ooff) * taps + tap) * t.f_ild + t.f_ioff + ci0 + cil,
+                       pk_tile[col * pitch + cil * taps + tap]);
+    }
+    // dgrad layout [ci][flipped tap][co]: co fastest
+    if (t.out_d) {
+        for (int i = threadIdx.x; i < nco * run; i += 256) {
+            const int col = i % nco, r = i / nco, tap = r % taps, cil = r / taps;
+            store_op<KIND>(t.out_d, t.d_plane, nplanes, ((long long)(ci0 + cil + t.d_ooff) * taps + (taps - 1 - tap)) * t.d_ild + t.d_ioff + co0 + col,
+                           pk_tile[col * pitch + cil * taps + tap]);
+        }
     }
 }
 
 __global__ void __launch_bounds__(256)
-wgrad_unpack_multi_kernel(const __grid_constant__ UnpackBatch b, int n, long long base, long long total) {
+wgrad_unpack_multi_kernel(const __grid_constant__ UnpackBatch b, int n) {
     pv2::pdl_prologue();
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = n - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (b.d[mid].start - base <= e) lo = mid; else hi = mid - 1; }
-        const pv2_unpack_desc& t = b.d[lo];
-        const long long l = e - (t.start - base);
-        const int kw = (int)(l % t.KW);
-        const int kh = (int)((l / t.KW) % t.KH);
-        const int ci = (int)((l / ((long long)t.KW * t.KH)) % t.Cin);
-        const int co = (int)(l / ((long long)t.KW * t.KH * t.Cin));
-        const long long idx = ((long long)(co + t.co_off) * (t.KH * t.KW) + kh * t.KW + kw) * t.Cin_p + ci;
-        float acc = 0.0f;
-        for (int sp = 0; sp < t.splits; ++sp) acc += t.part[sp * t.split_stride + idx];
-        t.dw[l] = acc;
+    extern __shared__ float up_tile[];           // [up_tco(taps)][taps][UP_TCI + 1]
+    __shared__ int s_t;
+    if (threadIdx.x == 0) s_t = find_tensor<UNPACK_BATCH>(b.tile_start, n, (int)blockIdx.x);
+    __syncthreads();
+    const pv2_unpack_desc& t = b.d[s_t];
+    const int taps = t.KH * t.KW;
+    const int ci_tiles = (t.Cin + UP_TCI - 1) / UP_TCI;
+    const int lt = (int)blockIdx.x - b.tile_start[s_t];
+    const int TCO = up_tco(taps);
+    const int co0 = (lt / ci_tiles) * TCO, ci0 = (lt % ci_tiles) * UP_TCI;
+    const int nco = min(TCO, t.Cout - co0), nci = min(UP_TCI, t.Cin - ci0);
+    // partial side [split][co][tap][ci]: ci fastest.  A thread owns up to UP_EPT elements of the tile and walks the splits in
+    // the OUTER loop with one accumulator per element: UP_EPT independent loads in flight per thread (a per-element split
+    // loop is a chain of dependent L2 round trips -- 31 splits x 16 elements made a CTA live > 100 us), and every element
+    // still sums its splits in split order (deterministic).
+    const int nelem = nco * taps * nci;          // <= up_tco(taps) * taps * UP_TCI <= 2048 = 256 threads * UP_EPT
+    int soff[UP_EPT], doff[UP_EPT];
+    float acc[UP_EPT];
+#pragma unroll
+    for (int e = 0; e < UP_EPT; ++e) {
+        const int i = threadIdx.x + e * 256;
+        acc[e] = 0.0f;
+        soff[e] = -1; doff[e] = 0;
+        if (i < nelem) {
+            const int cil = i % nci, r = i / nci, tap = r % taps, col = r / taps;
+            soff[e] = ((co0 + col + t.co_off) * taps + tap) * t.Cin_p + ci0 + cil;     // < 2^31: one conv's partial slab
+            doff[e] = (col * taps + tap) * (UP_TCI + 1) + cil;
+        }
+    }
+    // UP_SPU splits x UP_EPT elements = 64 independent loads per thread per round trip (a 31-split tensor is 4 round trips)
+    for (int sp0 = 0; sp0 < t.splits; sp0 += UP_SPU) {
+        float v[UP_SPU][UP_EPT];
+#pragma unroll
+        for (int u = 0; u < UP_SPU; ++u) {
+            const float* src = t.part + (size_t)(sp0 + u) * t.split_stride;
+            const bool live = sp0 + u < t.splits;
+#pragma unroll
+            for (int e = 0; e < UP_EPT; ++e) v[u][e] = (live && soff[e] >= 0) ? __ldg(src + soff[e]) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < UP_SPU; ++u) {
+#pragma unroll
+            for (int e = 0; e < UP_EPT; ++e) acc[e] += v[u][e];      // split order preserved per element
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < UP_EPT; ++e)
+        if (soff[e] >= 0) up_tile[doff[e]] = acc[e];
+    __syncthreads();
+    // OIHW side: for every co the (ci, tap) run is contiguous
+    const int run = nci * taps;
+    for (int i = threadIdx.x; i < nco * run; i += 256) {
+        const int col = i / run, j = i - col * run, cil = j / taps, tap = j - cil * taps;
+        t.dw[((size_t)(co0 + col) * t.Cin + ci0) * taps + j] = up_tile[(col * taps + tap) * (UP_TCI + 1) + cil];
     }
 }
 
@@ -813,16 +887,27 @@ extern "C" int pv2_weight_pack_multi(const pv2_pack_desc* descs, int n, int npla
     PV2_CHECK(descs && n > 0, "weight_pack_multi: bad arguments");
     for (int i0 = 0; i0 < n; i0 += PACK_BATCH) {
         const int nb = n - i0 < PACK_BATCH ? n - i0 : PACK_BATCH;
-        PackBatch b;
-        long long total = 0;
+        PackBatch b = {};
+        int tiles = 0;
+        size_t smem = 0;
         for (int i = 0; i < nb; ++i) {
             b.d[i] = descs[i0 + i];
-            PV2_CHECK(b.d[i].w && b.d[i].out_f, "weight_pack_multi: null pointer in descriptor %d", i0 + i);
-            total += (long long)b.d[i].Cout * b.d[i].Cin * b.d[i].KH * b.d[i].KW;
+            const pv2_pack_desc& t = b.d[i];
+            PV2_CHECK(t.w && t.out_f, "weight_pack_multi: null pointer in descriptor %d", i0 + i);
+            PV2_CHECK(t.Cout > 0 && t.Cin > 0 && t.KH > 0 && t.KW > 0 && t.KH * t.KW <= 64, "weight_pack_multi: bad shape in descriptor %d", i0 + i);
+            b.tile_start[i] = tiles;
+            const int taps = t.KH * t.KW, tco = pk_tco(taps);
+            tiles += ((t.Cout + tco - 1) / tco) * ((t.Cin + PK_TCI - 1) / PK_TCI);
+            const size_t need = (size_t)tco * (PK_TCI * taps + 1) * sizeof(float);
+            if (need > smem) smem = need;
         }
-        const long long base = b.d[0].start;
-        if (kind == PV2_BF16) pv2::launch(weight_pack_multi_kernel<0>, grid_for(total), 256, 0, (cudaStream_t)stream, b, nb, base, total, nplanes);
-        else pv2::launch(weight_pack_multi_kernel<1>, grid_for(total), 256, 0, (cudaStream_t)stream, b, nb, base, total, nplanes);
+        for (int i = nb; i <= PACK_BATCH; ++i) b.tile_start[i] = tiles;
+        PV2_CHECK(smem <= 200 * 1024, "weight_pack_multi: tile needs %zu B of shared memory", smem);
+        cudaError_t ce = kind == PV2_BF16 ? cudaFuncSetAttribute(weight_pack_multi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                          : cudaFuncSetAttribute(weight_pack_multi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        PV2_CHECK(ce == cudaSuccess, "weight_pack_multi: smem attribute: %s", cudaGetErrorString(ce));
+        if (kind == PV2_BF16) pv2::launch(weight_pack_multi_kernel<0>, dim3(tiles), 256, smem, (cudaStream_t)stream, b, nb, nplanes);
+        else pv2::launch(weight_pack_multi_kernel<1>, dim3(tiles), 256, smem, (cudaStream_t)stream, b, nb, nplanes);
         PV2_LAUNCH_CHECK("weight_pack_multi");
     }
     return 0;
@@ -832,14 +917,24 @@ extern "C" int pv2_wgrad_unpack_multi(const pv2_unpack_desc* descs, int n, void*
     PV2_CHECK(descs && n > 0, "wgrad_unpack_multi: bad arguments");
     for (int i0 = 0; i0 < n; i0 += UNPACK_BATCH) {
         const int nb = n - i0 < UNPACK_BATCH ? n - i0 : UNPACK_BATCH;
-        UnpackBatch b;
-        long long total = 0;
+        UnpackBatch b = {};
+        int tiles = 0;
+        size_t smem = 0;
         for (int i = 0; i < nb; ++i) {
             b.d[i] = descs[i0 + i];
-            PV2_CHECK(b.d[i].part && b.d[i].dw, "wgrad_unpack_multi: null pointer in descriptor %d", i0 + i);
-            total += (long long)b.d[i].Cout * b.d[i].Cin * b.d[i].KH * b.d[i].KW;
+            const pv2_unpack_desc& t = b.d[i];
+            PV2_CHECK(t.part && t.dw, "wgrad_unpack_multi: null pointer in descriptor %d", i0 + i);
+            PV2_CHECK(t.Cout > 0 && t.Cin > 0 && t.KH > 0 && t.KW > 0 && t.KH * t.KW <= 64 && t.splits >= 1, "wgrad_unpack_multi: bad descriptor %d", i0 + i);
+            b.tile_start[i] = tiles;
+            const int taps = t.KH * t.KW, tco = up_tco(taps);
+            tiles += ((t.Cout + tco - 1) / tco) * ((t.Cin + UP_TCI - 1) / UP_TCI);
+            const size_t need = (size_t)tco * taps * (UP_TCI + 1) * sizeof(float);
+            if (need > smem) smem = need;
         }
-        pv2::launch(wgrad_unpack_multi_kernel, grid_for(total), 256, 0, (cudaStream_t)stream, b, nb, b.d[0].start, total);
+        for (int i = nb; i <= UNPACK_BATCH; ++i) b.tile_start[i] = tiles;
+        cudaError_t ce = cudaFuncSetAttribute(wgrad_unpack_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        PV2_CHECK(ce == cudaSuccess, "wgrad_unpack_multi: smem attribute: %s", cudaGetErrorString(ce));
+        pv2::launch(wgrad_unpack_multi_kernel, dim3(tiles), 256, smem, (cudaStream_t)stream, b, nb);
         PV2_LAUNCH_CHECK("wgrad_unpack_multi");
     }
     return 0;

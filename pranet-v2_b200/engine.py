@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -68,10 +69,11 @@ def _ptr(t):
 class Act:
     """Operand-format activation: NHWC, `ld` stored channels (padded), bf16 [N,H,W,ld] or fp32 [planes,N,H,W,ld].
     May be a channel slice [off, off+C) of a wider (concat) buffer."""
-    __slots__ = ("t", "N", "H", "W", "C", "ld", "off", "gslabs", "want_grad")
+    __slots__ = ("t", "N", "H", "W", "C", "ld", "off", "gslabs", "want_grad", "direct")
 
     def __init__(self, t, N, H, W, C, ld, off=0, want_grad=False):
         self.t, self.N, self.H, self.W, self.C, self.ld, self.off = t, N, H, W, C, ld, off
+        self.direct = None        # zero-copy bf16 channels_last input: {"consumers": n, "dx": gradient written by the dgrad epilogue}
         self.gslabs = []          # gradient contributions: (fp32 tensor [M, ld_g], ld_g, off_g)
         self.want_grad = want_grad
 
@@ -118,6 +120,16 @@ def _side_streams(device):
     if idx not in _SIDE_STREAMS:
         _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=device) for _ in range(MAX_BRANCHES)]
     return _SIDE_STREAMS[idx]
+
+
+_WGRAD_STREAMS = {}  # device index -> one weight-gradient stream per branch (index 0 = main)
+
+
+def _wgrad_streams(device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _WGRAD_STREAMS:
+        _WGRAD_STREAMS[idx] = [torch.cuda.Stream(device=device) for _ in range(MAX_BRANCHES + 1)]
+    return _WGRAD_STREAMS[idx]
 
 
 def streams_enabled() -> bool:
@@ -169,6 +181,11 @@ class Engine:
         self.cur = 0              # branch the ops being issued belong to (0 = main stream)
         self.side = _side_streams(device) if streams_enabled() else None
         self._open = 0            # branches of the open section
+        # Weight gradients are leaves of the backward graph: nothing waits for them before the optimizer.  Each branch hands its
+        # wgrad GEMMs to a companion stream, so the chain dgrad -> BN backward -> dgrad ... never queues behind them and they
+        # fill whatever SMs the chains leave idle; backward() joins the companions before the gradients are unpacked.
+        self.wside = _wgrad_streams(device) if (streams_enabled() and os.environ.get("PV2_WGRAD_STREAMS", "1") != "0") else None
+        self._wused = set()
         self._keep = []           # every buffer of this pass (see the class docstring)
         self.lib = _lib.load()
         self.cache = cache if cache is not None else {}
@@ -261,6 +278,8 @@ class Engine:
         if (self.kind == PV2_BF16 and x.dtype == torch.bfloat16 and Cc % 8 == 0
                 and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0):
             a = Act(x.permute(0, 2, 3, 1), N, H, W, Cc, Cc, 0, self.need_grad)
+            if self.need_grad and grad_sink is not None and not x.is_contiguous():
+                a.direct = {"consumers": 0, "dx": None}
         else:
             xc = x.contiguous()
             a = self.new_act(N, H, W, Cc)
@@ -270,11 +289,16 @@ class Engine:
             cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
 
             def bwd():
+                if a.direct is not None and a.direct["dx"] is not None and not a.gslabs:
+                    grad_sink(a.direct["dx"])       # the dgrad GEMM's epilogue already wrote the channels_last bf16 gradient
+                    return
                 if not a.gslabs:
                     return
                 dx = torch.empty((N, Cc, H, W), dtype=x.dtype, device=self.dev,
                                  memory_format=torch.channels_last if cl else torch.contiguous_format)
                 self._unpack_slabs(a.gslabs, dx, N, Cc, H * W, cl)
+                if a.direct is not None and a.direct["dx"] is not None:
+                    dx = dx + a.direct["dx"]
                 grad_sink(dx)
             self.tape.append(bwd)
         return a
@@ -329,16 +353,20 @@ class Engine:
             arr = np.array(descs, dtype=_PACK_DT)
             _lib.check(self.lib.pv2_weight_pack_multi(arr.ctypes.data, len(descs), self.planes, self.kind, _stream()), "pv2_weight_pack_multi")
 
-    def flush_unpack(self):
-        """All weight gradients of this backward pass: [split][Cout][tap][Cin_p] partials -> OIHW, one launch per 56 tensors."""
-        if not self.unpack_jobs:
+    def _unpack(self, jobs, stream):
+        """[split][Cout][tap][Cin_p] partials -> OIHW weight gradients, one launch per 56 tensors."""
+        if not jobs:
             return
         descs, start = [], 0
-        for (part, split_stride, splits, dw_, Cout, Cin, KH, KW, Cin_p, co_off) in self.unpack_jobs:
+        for (part, split_stride, splits, dw_, Cout, Cin, KH, KW, Cin_p, co_off) in jobs:
             descs.append((part.data_ptr(), dw_.data_ptr(), split_stride, start, splits, Cout, Cin, KH, KW, Cin_p, co_off, 0))
             start += dw_.numel()
         arr = np.array(descs, dtype=_UNPACK_DT)
-        _lib.check(self.lib.pv2_wgrad_unpack_multi(arr.ctypes.data, len(descs), _stream()), "pv2_wgrad_unpack_multi")
+        _lib.check(self.lib.pv2_wgrad_unpack_multi(arr.ctypes.data, len(descs), stream), "pv2_wgrad_unpack_multi")
+
+    def flush_unpack(self):
+        """Weight gradients still waiting for their unpack (single-stream mode): all of them in one multi-tensor launch."""
+        self._unpack(self.unpack_jobs, _stream())
         self.unpack_jobs = []
 
     # ---- convolution (optionally several convs of identical geometry fused along Cout) ---------------------
@@ -384,6 +412,8 @@ class Engine:
         Cout = sum(cv.out_channels for cv in convs)
         taps = KH * KW
         lib, st = self.lib, _stream()
+        if x.direct is not None:
+            x.direct["consumers"] += 1
         self.groups_seen.append(convs)
         key = self._gkey(convs)
         if key not in self.packed:      # first run of this head (group list not cached yet): pack this group on its own
@@ -442,20 +472,48 @@ class Engine:
         if any(cv.weight.requires_grad for cv in convs):
             splits = lib.pv2_conv_wgrad_splits_hint(N, H, W, Cin_p, Cout, KH, KW, self.kind)
             part = self.f32(splits, Cout, taps, Cin_p)
-            _lib.check(lib.pv2_conv_wgrad(self._act_ptr(dy), self.plane_stride(dy), self._act_ptr(x), self.plane_stride(x), self.kind, self.nterms,
-                                          N, H, W, Cin_p, Cout_p, Cout, KH, KW, dh, dw, part.data_ptr(), splits, st), "pv2_conv_wgrad")
-            o = 0
+            wst, wctx = st, None
+            if self.wside is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())           # dy (and `part`'s previous life, if any) are ordered before this
+                ws = self.wside[self.cur]
+                ws.wait_event(ev)
+                self._wused.add(self.cur)
+                wctx = torch.cuda.stream(ws)
+                wctx.__enter__()
+                wst = ws.cuda_stream
+            jobs, o = [], 0
             for cv in convs:
                 if cv.weight.requires_grad:
                     dw_ = torch.empty(cv.weight.shape, dtype=torch.float32, device=self.dev)
-                    self.unpack_jobs.append((part, Cout * taps * Cin_p, splits, dw_, cv.out_channels, Cin, KH, KW, Cin_p, o))
-                    self.add_param_grad(cv.weight, dw_)      # filled by flush_unpack() before backward() returns
+                    jobs.append((part, Cout * taps * Cin_p, splits, dw_, cv.out_channels, Cin, KH, KW, Cin_p, o))
+                    self.add_param_grad(cv.weight, dw_)      # filled before backward() returns
                 o += cv.out_channels
+            try:
+                _lib.check(lib.pv2_conv_wgrad(self._act_ptr(dy), self.plane_stride(dy), self._act_ptr(x), self.plane_stride(x), self.kind, self.nterms,
+                                              N, H, W, Cin_p, Cout_p, Cout, KH, KW, dh, dw, part.data_ptr(), splits, wst), "pv2_conv_wgrad")
+                if wctx is not None:
+                    # on the companion stream the split sum + OIHW transpose follows its GEMM at once: it is off the critical path
+                    # there, and the end of the backward pass is not a 200 us serial tail of one big unpack over cold partials
+                    self._unpack(jobs, wst)
+                else:
+                    self.unpack_jobs += jobs                 # single-stream mode: one multi-tensor launch in flush_unpack()
+            finally:
+                if wctx is not None:
+                    wctx.__exit__(None, None, None)
         # dgrad -> raw slabs appended to the input's gradient list
         if x.want_grad and x.gslabs is not None:
             wt = self.packed[self._gkey(convs)][1]           # dgrad layout, packed together with the fprop layout
             ld = (Cin + 3) // 4 * 4
             splits = lib.pv2_conv_splits_hint(N, H, W, Cout_p, Cin, KH, KW, self.kind, self.nterms)
+            if x.direct is not None and x.direct["consumers"] == 1 and splits == 1 and x.ld == Cin and x.off == 0:
+                # sole consumer of a zero-copy backbone feature: no fp32 slab, no unpack pass -- bf16 channels_last from the epilogue
+                dxf = torch.empty((N, Cin, H, W), dtype=torch.bfloat16, device=self.dev, memory_format=torch.channels_last)
+                self._keep.append(dxf)
+                _lib.check(lib.pv2_conv_fwd(self._act_ptr(dy), self.plane_stride(dy), wt.data_ptr(), Cin * taps * Cout_p, self.kind, self.nterms,
+                                            N, H, W, Cout_p, Cin, KH, KW, dh, dw, 2, dxf.data_ptr(), Cin, 1, None, None, st), "pv2_conv_fwd(dgrad, bf16)")
+                x.direct["dx"] = dxf
+                return
             dx = self.f32(splits, N * H * W, ld)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(dy), self.plane_stride(dy), wt.data_ptr(), Cin * taps * Cout_p, self.kind, self.nterms,
                                         N, H, W, Cout_p, Cin, KH, KW, dh, dw, 0, dx.data_ptr(), ld, splits, None, None, st), "pv2_conv_fwd(dgrad)")
@@ -753,6 +811,13 @@ class Engine:
                 self._fan_out(x)
             else:
                 self._fan_in(x)
+        if self._wused:            # join the weight-gradient streams
+            main = torch.cuda.current_stream()
+            for i in sorted(self._wused):
+                ev = torch.cuda.Event()
+                ev.record(self.wside[i])
+                main.wait_event(ev)
+            self._wused = set()
         self.flush_unpack()
         self.tape = _Tape(self)
         self._keep = []
@@ -813,7 +878,10 @@ class _HeadFn(torch.autograd.Function):
         for j, p in enumerate(ctx.params):
             g = eng.param_grads.get(id(p)) if ctx.needs_input_grad[5 + ctx.n_inputs + j] else None
             grads.append(g)
-        ctx.eng = ctx.outs = None
+        # drop every other reference to the gradient tensors: autograd's AccumulateGrad adopts a gradient it holds the only
+        # reference to and CLONES it otherwise (209 head parameters = 209 serialised 1.4 us copies at the end of the step)
+        eng.param_grads = {}
+        ctx.eng = ctx.outs = ctx.in_grads = None
         return (None, None, None, None, None, *grads)
 
 
