@@ -245,6 +245,13 @@ def main():
         roof["peak"] = hbm
         roof["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         roof["frac"] = roof["achieved"] / hbm
+        try:     # measured DRAM bytes per launch of the same kernel at the same size, from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["adam_clamp_flat_kernel"]
+            if tr["elements"] == roof["elements"]:
+                roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                roof["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         for o in roof["other_kernels"]:
             o["frac"] = o["achieved"] / hbm
             o["fwd"]["frac"] = o["fwd"]["achieved"] / hbm

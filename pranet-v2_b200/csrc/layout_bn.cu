@@ -292,15 +292,30 @@ bn_stats_partial_kernel(float* __restrict__ y, long long slab_stride, int nslabs
     if (c < C) {
         float shift = 0.0f, s1 = 0.0f, s2 = 0.0f;
         bool first = true;
-        for (long long r = r0 + ty; r < r1; r += 8) {
-            float v = y[r * ld + c];
-            if (nslabs > 1) {
-                for (int s = 1; s < nslabs; ++s) v += y[s * slab_stride + r * ld + c];
-                y[r * ld + c] = v;
+        // Two rows x up to 8 slabs = 16 independent loads per round trip; a row-by-row, slab-by-slab walk is a chain of
+        // dependent L2 latencies (7 rows x 8 slabs ~ 30 us for the 11x11 maps of the split-K 5x5 convs).  Slabs are summed in
+        // slab order, rows enter the running statistics in row order: same arithmetic as the serial walk.
+        for (long long r = r0 + ty; r < r1; r += 16) {
+            float v[2][8];
+            const bool two = r + 8 < r1;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long rr = (u == 0 || two) ? r + 8 * u : r;
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl) v[u][sl] = sl < nslabs ? y[sl * slab_stride + rr * ld + c] : 0.0f;
             }
-            if (first) { shift = v; first = false; }
-            const float d = v - shift;
-            s1 += d; s2 += d * d; cnt += 1.0f;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                float t = v[u][0];
+#pragma unroll
+                for (int sl = 1; sl < 8; ++sl) t += v[u][sl];       // slabs beyond nslabs contribute +0.0f
+                for (int sl = 8; sl < nslabs; ++sl) t += y[sl * slab_stride + (r + 8 * u) * ld + c];
+                if (nslabs > 1) y[(r + 8 * u) * ld + c] = t;
+                if (first) { shift = t; first = false; }
+                const float d = t - shift;
+                s1 += d; s2 += d * d; cnt += 1.0f;
+            }
         }
         if (cnt > 0.0f) { mean = shift + s1 / cnt; m2 = fmaxf(s2 - s1 * s1 / cnt, 0.0f); }
     }

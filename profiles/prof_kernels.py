@@ -2,6 +2,8 @@
 bench values).  Usage (on the GPU box, one GPU):
     ncu --set full --clock-control none --import-source on -k regex:structure_loss -c 6 -o gpurun_out/prof_loss  python profiles/prof_kernels.py loss
     ncu --set full --clock-control none --import-source on -k regex:conv_ -c 120 -o gpurun_out/prof_conv         python profiles/prof_kernels.py head
+    ncu --set full --clock-control none --import-source on -k regex:adam_clamp -c 3 -o gpurun_out/prof_adam       python profiles/prof_kernels.py adam
+    ncu --set full --clock-control none --import-source on -k regex:tail_ -c 4 -o gpurun_out/prof_tail            python profiles/prof_kernels.py tail
 """
 import os
 import sys
@@ -22,6 +24,22 @@ if what == "step":     # two eager training steps of the bench workload (launch 
     x, gt = synthetic.images(B, S, 1).to(dev), synthetic.ellipse_masks(B, S, S, 1).to(dev)
     for it in range(2):
         ts.step_device(x, gt)
+elif what == "adam":   # the optimizer tail over the PraNet-V2 Res2Net-50 parameter count
+    lib = P._lib.load()
+    n = 30_499_908
+    p, g = torch.randn(n, device=dev), torch.randn(n, device=dev)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step, ticket = torch.zeros(1, dtype=torch.int64, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+    for it in range(3):
+        P._lib.check(lib.pv2_adam_clamp_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, step.data_ptr(), ticket.data_ptr(),
+                                             1e-4, 0.9, 0.999, 1e-8, 0.0, 0, 0.5, 1.0, torch.cuda.current_stream().cuda_stream), "adam")
+elif what == "tail":   # fused inference tails from the low-res maps
+    maps = [torch.randn(B, 1, S // s, S // s, device=dev) for s in (8, 16, 32, 8)]
+    for it in range(2):
+        P.ops.infer_tail_binary(maps, [8, 16, 32, 8], (S, S))
+    fg = [torch.randn(B, 9, 224 // s, 224 // s, device=dev) for s in (32, 16, 8, 4)]
+    bg = [torch.randn(B, 9, 224 // s, 224 // s, device=dev) for s in (32, 16, 8, 4)]
+    P.ops.infer_tail_argmax(fg, bg, [32, 16, 8, 4])
 elif what == "loss":
     m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
     for it in range(2):
