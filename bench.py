@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train (default, the headline metric) or infer: batched test-time path, images/s of uint8 saliency maps")
     ap.add_argument("--profile-only", action="store_true",
                     help="run the warm-up + timed steps only (no e2e / roofline / CPU legs) and exit: the command ncu wraps for the launch list")
     return ap.parse_args()
@@ -51,11 +53,15 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.first = index, None, [], 0
+
+    def mark(self):
+        """Samples before this call (warm-up) are dropped from the report."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -72,7 +78,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in (self.lines[self.first:] or self.lines[-3:]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -131,6 +137,13 @@ def time_cpu(batch, size, steps, warmup):
     return batch * steps / dt, dt / steps
 
 
+def train_config(args, world):
+    """The workload both arms are quoted on (BASELINE.json configs[1])."""
+    return {"workload": f"PraNet-V2 Res2Net-50 train step (fwd + 4x structure_loss + bwd + clamp + Adam), per-GPU batch {args.batch} @ {args.size}^2, random init",
+            "global_batch": world * args.batch, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+            "l2": "inputs rotate over 4 batches; per-step working set (activations+grads) >> 126 MB L2"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -142,7 +155,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"PraNet-V2 Res2Net-50 train step, CPU oracle port, batch {args.cpu_batch} @ {args.size}^2"},
+        "config": train_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -173,6 +186,8 @@ def main():
     B, S = args.batch, args.size
     torch.manual_seed(0)
     model = P.PraNet_V2(num_class=1)
+    if args.mode == "infer":
+        return run_infer(args, P, model, dev, world, rank, local)
     ts = TrainStep(model, lr=1e-4, clip=0.5, autocast_backbone=(args.precision == "bf16"), device=dev, use_graph=not args.no_graph)
     g = torch.Generator().manual_seed(1000 + rank)
     # a few distinct batches (> L2 together with the activations; inputs change step to step)
@@ -188,12 +203,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()            # nvidia-smi needs a few hundred ms before its first sample: start it ahead of the warm-up
     for i in range(args.warmup):
         ts.step_device(imgs_d[i % nbuf], gts_d[i % nbuf])
     barrier()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()             # only samples taken from here on (the timed region) are reported
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -259,8 +276,7 @@ def main():
             "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"PraNet-V2 Res2Net-50 train step (fwd + 4x structure_loss + bwd + clamp + Adam), per-GPU batch {B} @ {S}^2, random init",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph, "l2": "inputs rotate over 4 batches; per-step working set (activations+grads) >> 126 MB L2"},
+            "config": train_config(args, world),
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": imgs_h[0].numel() * 4 + gts_h[0].numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
@@ -270,6 +286,68 @@ def main():
             out["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                    "sample": f"3 timed steps (1 warm-up) of batch {args.cpu_batch} @ {S}^2: stock Res2Net-50 on torch-CPU + oracle head/loss, fp32"}
         print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_infer(args, P, model, dev, world, rank, local):
+    """BASELINE.json's "infer images/sec @352^2": batched test-time path (binary_seg/MyTest_med.py:28-42) -- forward in eval mode +
+    fused uint8 tail -- replicas only across GPUs (no collective).  Same timing rules as the training arm."""
+    import torch.distributed as dist
+    from pranet_v2_b200.train import InferStep
+    B, S = args.batch, args.size
+    inf = InferStep(model, device=dev, autocast=(args.precision == "bf16"), use_graph=not args.no_graph)
+    g = torch.Generator().manual_seed(2000 + rank)
+    nbuf = 4
+    imgs_h = [torch.randn(B, 3, S, S, generator=g).pin_memory() for _ in range(nbuf)]
+    imgs_d = [t.to(dev) for t in imgs_h]
+    out_h = torch.empty(B, S, S, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for i in range(args.warmup):
+        inf.predict_device(imgs_d[i % nbuf])
+    barrier()
+    if rank == 0:
+        sampler.mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        inf.predict_device(imgs_d[i % nbuf])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        inf.predict_host(imgs_h[i % nbuf], out_h)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        inf.predict_host(imgs_h[i % nbuf], out_h)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "infer images/sec @352^2 (PraNet-V2 Res2Net-50 forward + fused uint8 tail)", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"PraNet-V2 Res2Net-50 batched inference (eval forward + p2+p3+p4+p5 / resize / sigmoid / min-max / uint8 tail), per-GPU batch {B} @ {S}^2",
+                       "global_batch": world * B, "parallelism": f"replicas x{world}", "cuda_graph": not args.no_graph, "l2": "inputs rotate over 4 batches"},
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": imgs_h[0].numel() * 4, "d2h_bytes_per_step": out_h.numel()},
+            "gpu_launches": int(inf.pv2_launches_per_step * args.steps), "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -90,3 +90,29 @@ def test_predict_uint8_matches_reference_rule_gpu():
         o = (o - o.min()) / (o.max() - o.min() + 1e-8)
         want.append((o * 255).astype(np.uint8))
     _check_u8(got, np.stack(want))
+
+
+@pytest.mark.gpu
+def test_infer_step_graph_matches_eager_gpu():
+    """InferStep (CUDA graph of eval forward + fused tail) reproduces the eager path and the reference rule on the model's own
+    full-resolution outputs; a second batch replays the same graph."""
+    import pranet_v2_b200 as P
+    from pranet_v2_b200.train import InferStep
+    from pranet_v2_b200 import synthetic
+    torch.manual_seed(0)
+    m = P.PraNet_V2(num_class=1)
+    inf = InferStep(m, device="cuda:0", autocast=False, use_graph=True)
+    for seed in (0, 1):
+        x = synthetic.images(2, 128, seed).cuda()
+        got = inf.predict_device(x, (100, 140)).cpu().numpy()
+        with torch.no_grad():
+            outs = inf.model(x.contiguous(memory_format=torch.channels_last))
+        out = (outs[0] + outs[1] + outs[2] + outs[3]).float().cpu()
+        want = []
+        for b in range(2):
+            o = torch.nn.functional.interpolate(out[b:b + 1], size=(100, 140), mode="bilinear", align_corners=False)
+            o = o.sigmoid().numpy().squeeze()
+            o = (o - o.min()) / (o.max() - o.min() + 1e-8)
+            want.append((o * 255).astype(np.uint8))
+        _check_u8(got, np.stack(want))
+    assert len(inf._graphs) == 1 and inf.pv2_launches_per_step > 50
