@@ -252,6 +252,19 @@ def kernel_table(P, dev, B, S, hbm, tflops):
     rows.append(("bilinear fwd, 8 final maps in one launch", "hbm", (8 * px + lowpx) * 4, timed_graph(mf)))
     rows.append(("bilinear bwd, 8 final maps in one launch", "hbm", (8 * px + lowpx) * 4, timed_graph(mb)))
     del lows, his
+    # yardsticks for the rows above: what a plain write-only / read+write stream of the same size reaches on this GPU (stock
+    # torch kernels; the "measured HBM peak" is a 2 GiB copy and a 63 MB write-only launch does not get there either)
+    big = [torch.empty(8 * px, device=dev) for _ in range(max(3, nrot + 1))]
+
+    def fill():
+        big[rot() % len(big)].fill_(1.0)
+
+    def cpy():
+        j = rot() % len(big)
+        big[j].copy_(big[(j + 1) % len(big)])
+    rows.append(("yardstick: torch fill_ of the 8 maps' bytes (write-only stream)", "hbm", 8 * px * 4, timed_graph(fill)))
+    rows.append(("yardstick: torch copy_ of the 8 maps' bytes (read + write)", "hbm", 2 * 8 * px * 4, timed_graph(cpy)))
+    del big
     # V1 reverse attention scale on the three backbone features (bf16)
     for c, s in ((512, 8), (1024, 16), (2048, 32)):
         h = S // s

@@ -66,10 +66,20 @@ bilinear_fwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
             const Tap tx = bilinear_tap(min(ox + j, ow - 1), iw, rw, ac);
             xi0[j] = tx.i0; xi1[j] = tx.i1; xw0[j] = tx.w0; xw1[j] = tx.w1;
         }
+        // integer up-scaling by a multiple of 4: the four outputs of a quad read the SAME two source columns, so a row costs 4
+        // shared-memory loads instead of 16 (the kernel was issue bound: 160 instructions per quad, 79 % issue slots busy)
+        const bool same_cols = xi0[0] == xi0[3] && xi1[0] == xi1[3] && xi0[0] == xi0[1] && xi0[0] == xi0[2] && xi1[0] == xi1[1] && xi1[0] == xi1[2];
         for (int oy = oy0 + rg; oy < oy1; oy += rgroups) {
             const Tap ty = bilinear_tap(oy, ih, rh, ac);
             float v[4];
-            if (staged) {
+            if (staged && same_cols) {
+                const float* ra = srows + (ty.i0 - r0) * iw;
+                const float* rb = srows + (ty.i1 - r0) * iw;
+                const float a0 = ra[xi0[0]], a1 = ra[xi1[0]], b0 = rb[xi0[0]], b1 = rb[xi1[0]];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)        // same expression, same order as the general path: bit-identical results
+                    v[j] = ty.w0 * (xw0[j] * a0 + xw1[j] * a1) + ty.w1 * (xw0[j] * b0 + xw1[j] * b1);
+            } else if (staged) {
                 const float* ra = srows + (ty.i0 - r0) * iw;
                 const float* rb = srows + (ty.i1 - r0) * iw;
 #pragma unroll
@@ -111,15 +121,16 @@ __device__ __forceinline__ void touch_window(int i, int out_size, float ratio, b
     if (i == 0) lo = 0;  // clamped sources (src < 0) all land on index 0
 }
 
-constexpr int BWD_THREADS = 256;
+constexpr int BWD_THREADS = 384;   // upper bound; the launch uses ow4 * rgroups threads so that every thread owns a column quad
 constexpr int BWD_R = 4;             // input rows per CTA: neighbouring input rows share output rows, so (R+1)*s rows are read for R rows
+constexpr int BWD_BATCH = 8;         // output rows a thread fetches per round trip
 constexpr int BWD_MAX_WIN = 192;     // output rows a block of R input rows can touch: (R+1)*scale + a few (scale <= 32)
 
 // CTA = (block of BWD_R input rows, plane, map).  Pass 1: every output row the block touches is read ONCE (16-byte loads, a
 // thread owns 4 consecutive columns, the row window is split over `rgroups` thread groups) and folded into the R rows of column
 // sums with its tap weights; pass 2 folds the columns.  No atomics, deterministic.
 template <typename T>
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS, 2)
 bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int rgroups) {
     pv2::pdl_prologue();
     extern __shared__ float colsum[];  // [BWD_R][rgroups][pitch]
@@ -144,7 +155,7 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
     const int ow4 = (ow + 3) >> 2, pitch = ow4 * 4;
     const bool vec_ok = (ow & 3) == 0;
     if (nwin <= BWD_MAX_WIN) {
-        for (int j = threadIdx.x; j < nwin * BWD_R; j += BWD_THREADS) {
+        for (int j = threadIdx.x; j < nwin * BWD_R; j += blockDim.x) {
             const int r = j / nwin, jj = j - r * nwin;
             wts[r][jj] = r < nr ? tap_weight(lo + jj, iy0 + r, ih, rh, ac) : 0.0f;
         }
@@ -155,21 +166,35 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
 #pragma unroll
             for (int r = 0; r < BWD_R; ++r) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; acc[r][3] = 0.0f; }
             const int ox = q * 4;
-#pragma unroll 8
-            for (int j = rg; j < nwin; j += rgroups) {
-                float4 v;
-                if (vec_ok) {
-                    v = load4<T>(g + (size_t)(lo + j) * ow + ox);
-                } else {
-                    const T* row = g + (size_t)(lo + j) * ow;
-                    v.x = ox < ow ? to_f(row[ox]) : 0.0f;         v.y = ox + 1 < ow ? to_f(row[ox + 1]) : 0.0f;
-                    v.z = ox + 2 < ow ? to_f(row[ox + 2]) : 0.0f; v.w = ox + 3 < ow ? to_f(row[ox + 3]) : 0.0f;
+            // batches of BWD_BATCH rows: every load of a batch is issued before the first FMA (the kernel was latency bound:
+            // 6.8 long-scoreboard stalls per issue, 37 % issue slots)
+            for (int j0 = rg; j0 < nwin; j0 += BWD_BATCH * rgroups) {
+                float4 v[BWD_BATCH];
+#pragma unroll
+                for (int u = 0; u < BWD_BATCH; ++u) {
+                    const int j = j0 + u * rgroups;
+                    v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (j < nwin) {
+                        if (vec_ok) {
+                            v[u] = load4<T>(g + (size_t)(lo + j) * ow + ox);
+                        } else {
+                            const T* row = g + (size_t)(lo + j) * ow;
+                            v[u].x = ox < ow ? to_f(row[ox]) : 0.0f;         v[u].y = ox + 1 < ow ? to_f(row[ox + 1]) : 0.0f;
+                            v[u].z = ox + 2 < ow ? to_f(row[ox + 2]) : 0.0f; v[u].w = ox + 3 < ow ? to_f(row[ox + 3]) : 0.0f;
+                        }
+                    }
                 }
 #pragma unroll
-                for (int r = 0; r < BWD_R; ++r) {
-                    const float wy = wts[r][j];
-                    acc[r][0] = fmaf(wy, v.x, acc[r][0]); acc[r][1] = fmaf(wy, v.y, acc[r][1]);
-                    acc[r][2] = fmaf(wy, v.z, acc[r][2]); acc[r][3] = fmaf(wy, v.w, acc[r][3]);
+                for (int u = 0; u < BWD_BATCH; ++u) {
+                    const int j = j0 + u * rgroups;
+                    if (j < nwin) {
+#pragma unroll
+                        for (int r = 0; r < BWD_R; ++r) {
+                            const float wy = wts[r][j];
+                            acc[r][0] = fmaf(wy, v[u].x, acc[r][0]); acc[r][1] = fmaf(wy, v[u].y, acc[r][1]);
+                            acc[r][2] = fmaf(wy, v[u].z, acc[r][2]); acc[r][3] = fmaf(wy, v[u].w, acc[r][3]);
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -182,7 +207,7 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
         for (int r = 0; r < nr; ++r) {
             int rl, rh2;
             touch_window(iy0 + r, oh, rh, ac, rl, rh2);
-            for (int ox = threadIdx.x; ox < pitch; ox += BWD_THREADS) {
+            for (int ox = threadIdx.x; ox < pitch; ox += blockDim.x) {
                 float acc = 0.0f;
                 if (ox < ow)
                     for (int oy = rl; oy <= rh2; ++oy) {
@@ -195,7 +220,7 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
         rgroups = 1;
     }
     __syncthreads();
-    for (int it = threadIdx.x; it < nr * iw; it += BWD_THREADS) {
+    for (int it = threadIdx.x; it < nr * iw; it += blockDim.x) {
         const int r = it / iw, ix = it - r * iw;
         int xl, xh;
         touch_window(ix, ow, rw, ac, xl, xh);
@@ -243,11 +268,13 @@ static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int row_blocks
     PV2_CHECK(ow4 <= BWD_THREADS, "bilinear_bwd: output width %d too large", ow);
     int rgroups = BWD_THREADS / ow4;
     if (rgroups > 8) rgroups = 8;
+    int threads = (ow4 * rgroups + 31) / 32 * 32;       // every thread owns a (column quad, row group): no idle lanes beyond the last warp
+    if (threads < 64) threads = 64;
     const size_t smem = (size_t)BWD_R * rgroups * ow4 * 4 * sizeof(float);
     PV2_CHECK(smem <= 48 * 1024, "bilinear_bwd: output width %d too large", ow);
     dim3 grid(row_blocks, planes, nmaps);
-    if (dtype == PV2_F32) pv2::launch(bilinear_bwd_kernel<float>, grid, BWD_THREADS, smem, st, mm, oh, ow, align_corners, rgroups);
-    else pv2::launch(bilinear_bwd_kernel<__nv_bfloat16>, grid, BWD_THREADS, smem, st, mm, oh, ow, align_corners, rgroups);
+    if (dtype == PV2_F32) pv2::launch(bilinear_bwd_kernel<float>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups);
+    else pv2::launch(bilinear_bwd_kernel<__nv_bfloat16>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups);
     PV2_LAUNCH_CHECK("bilinear_bwd");
     return 0;
 }

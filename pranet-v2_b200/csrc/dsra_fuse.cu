@@ -114,24 +114,28 @@ __global__ void dsra_fuse_bwd_kernel(const float* __restrict__ dout, const float
 }
 
 // ---- V1 reverse attention -----------------------------------------------------------------------
+// block = 64 pixel quads x 4 channel groups; a thread computes the four (1 - sigmoid) factors of its pixels ONCE and applies
+// them to RA_CPT channels whose loads are all in flight together.  (One thread per (b, c, quad) recomputed the sigmoid for
+// every channel and spent two 64-bit divisions per quad on finding its plane: 41 instructions per element, issue bound.)
+constexpr int RA_CPT = 8;
 template <typename T>
-__global__ void ra_v1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ crop, T* __restrict__ y,
-                                 int C, int hw, size_t total_vec) {
+__global__ void __launch_bounds__(256)
+ra_v1_fwd_kernel(const T* __restrict__ x, const float* __restrict__ crop, T* __restrict__ y, int C, int hw, int vec_per_plane) {
     pv2::pdl_prologue();
-    // hw % 4 == 0: one thread = 4 consecutive pixels of one (b,c) plane
-    const int vec_per_plane = hw >> 2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t plane = i / vec_per_plane;
-        const int v = (int)(i - plane * vec_per_plane);
-        const size_t b = plane / C;
-        const float4 c4 = __ldg(reinterpret_cast<const float4*>(crop + b * hw) + v);
-        float4 xv = load4<T>(x + plane * hw + (size_t)v * 4);
-        xv.x *= 1.0f - 1.0f / (1.0f + __expf(-c4.x));
-        xv.y *= 1.0f - 1.0f / (1.0f + __expf(-c4.y));
-        xv.z *= 1.0f - 1.0f / (1.0f + __expf(-c4.z));
-        xv.w *= 1.0f - 1.0f / (1.0f + __expf(-c4.w));
-        store4<T>(y + plane * hw + (size_t)v * 4, xv);
-    }
+    const int v = blockIdx.x * 64 + (threadIdx.x & 63), b = blockIdx.y;
+    const int c0 = (blockIdx.z * 4 + (threadIdx.x >> 6)) * RA_CPT;
+    if (v >= vec_per_plane || c0 >= C) return;
+    const float4 c4 = __ldg(reinterpret_cast<const float4*>(crop + (size_t)b * hw) + v);
+    const float a0 = 1.0f - 1.0f / (1.0f + __expf(-c4.x)), a1 = 1.0f - 1.0f / (1.0f + __expf(-c4.y));
+    const float a2 = 1.0f - 1.0f / (1.0f + __expf(-c4.z)), a3 = 1.0f - 1.0f / (1.0f + __expf(-c4.w));
+    const size_t base = ((size_t)b * C + c0) * hw + (size_t)v * 4;
+    float4 xv[RA_CPT];
+#pragma unroll
+    for (int k = 0; k < RA_CPT; ++k)
+        if (c0 + k < C) xv[k] = load4<T>(x + base + (size_t)k * hw);
+#pragma unroll
+    for (int k = 0; k < RA_CPT; ++k)
+        if (c0 + k < C) store4<T>(y + base + (size_t)k * hw, make_float4(xv[k].x * a0, xv[k].y * a1, xv[k].z * a2, xv[k].w * a3));
 }
 
 template <typename T>
@@ -146,7 +150,7 @@ __global__ void ra_v1_fwd_scalar_kernel(const T* __restrict__ x, const float* __
     }
 }
 
-// block = 32 pixels x 8 channel groups; grid = (ceil(hw/32), B)
+// block = 32 pixels x 8 channel groups; grid = (ceil(hw/32), B)   (scalar form: hw % 4 != 0)
 template <typename T>
 __global__ void __launch_bounds__(256)
 ra_v1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ crop,
@@ -173,6 +177,51 @@ ra_v1_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float*
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][lane];
         dcrop[(size_t)b * hw + p] = -s * a * t;
+    }
+}
+
+// vector form (hw % 4 == 0): block = 32 pixel quads x 8 channel groups, a thread owns 4 consecutive pixels and walks its
+// channels 8 at a time (16 independent 8/16-byte loads in flight); the channel groups are folded in group order through
+// shared memory (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+ra_v1_bwd4_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ crop,
+                  T* __restrict__ dx, float* __restrict__ dcrop, int C, int hw, int vec_per_plane) {
+    pv2::pdl_prologue();
+    __shared__ float4 red[8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5, b = blockIdx.y;
+    const int v = blockIdx.x * 32 + lane;
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f), a = acc, s = acc;
+    if (v < vec_per_plane) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(crop + (size_t)b * hw) + v);
+        s = make_float4(1.0f / (1.0f + __expf(-c4.x)), 1.0f / (1.0f + __expf(-c4.y)), 1.0f / (1.0f + __expf(-c4.z)), 1.0f / (1.0f + __expf(-c4.w)));
+        a = make_float4(1.0f - s.x, 1.0f - s.y, 1.0f - s.z, 1.0f - s.w);
+        const size_t base = (size_t)b * C * hw + (size_t)v * 4;
+        for (int c = grp; c < C; c += 64) {
+            float4 g[8], xv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int cc = c + 8 * k;
+                if (cc < C) { g[k] = load4<T>(dy + base + (size_t)cc * hw); xv[k] = load4<T>(x + base + (size_t)cc * hw); }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int cc = c + 8 * k;
+                if (cc < C) {
+                    acc.x = fmaf(g[k].x, xv[k].x, acc.x); acc.y = fmaf(g[k].y, xv[k].y, acc.y);
+                    acc.z = fmaf(g[k].z, xv[k].z, acc.z); acc.w = fmaf(g[k].w, xv[k].w, acc.w);
+                    store4<T>(dx + base + (size_t)cc * hw, make_float4(a.x * g[k].x, a.y * g[k].y, a.z * g[k].z, a.w * g[k].w));
+                }
+            }
+        }
+    }
+    red[grp][lane] = acc;
+    __syncthreads();
+    if (grp == 0 && v < vec_per_plane) {
+        float4 t = red[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { t.x += red[k][lane].x; t.y += red[k][lane].y; t.z += red[k][lane].z; t.w += red[k][lane].w; }
+        reinterpret_cast<float4*>(dcrop + (size_t)b * hw)[v] = make_float4(-s.x * a.x * t.x, -s.y * a.y * t.y, -s.z * a.z * t.z, -s.w * a.w * t.w);
     }
 }
 
@@ -218,12 +267,11 @@ extern "C" int pv2_ra_v1_scale_fwd(const void* x, const float* crop, void* y, in
     cudaStream_t st = (cudaStream_t)stream;
     const size_t total = (size_t)B * C * hw;
     const int threads = 256;
-    if ((hw & 3) == 0) {
-        const size_t nv = total / 4;
-        int blocks = (int)((nv + threads - 1) / threads);
-        if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-        if (dtype == PV2_F32) pv2::launch(ra_v1_fwd_kernel<float>, blocks, threads, 0, st, (const float*)x, crop, (float*)y, C, hw, nv);
-        else pv2::launch(ra_v1_fwd_kernel<__nv_bfloat16>, blocks, threads, 0, st, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, nv);
+    if ((hw & 3) == 0 && B <= 65535 && (C + 4 * RA_CPT - 1) / (4 * RA_CPT) <= 65535) {
+        const int vpp = hw >> 2;
+        dim3 grid((vpp + 63) / 64, B, (C + 4 * RA_CPT - 1) / (4 * RA_CPT));
+        if (dtype == PV2_F32) pv2::launch(ra_v1_fwd_kernel<float>, grid, threads, 0, st, (const float*)x, crop, (float*)y, C, hw, vpp);
+        else pv2::launch(ra_v1_fwd_kernel<__nv_bfloat16>, grid, threads, 0, st, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, vpp);
     } else {
         int blocks = (int)((total + threads - 1) / threads);
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
@@ -239,8 +287,16 @@ extern "C" int pv2_ra_v1_scale_bwd(const void* dy, const void* x, const float* c
     PV2_CHECK(dy && x && crop && dx && dcrop, "ra_v1_scale_bwd: null pointer");
     PV2_CHECK(B > 0 && C > 0 && hw > 0 && B <= 65535, "ra_v1_scale_bwd: bad shape");
     PV2_CHECK(dtype == PV2_F32 || dtype == PV2_BF16, "ra_v1_scale_bwd: bad dtype %d", dtype);
-    dim3 grid((hw + 31) / 32, B);
     cudaStream_t st = (cudaStream_t)stream;
+    if ((hw & 3) == 0) {
+        const int vpp = hw >> 2;
+        dim3 grid4((vpp + 31) / 32, B);
+        if (dtype == PV2_F32) pv2::launch(ra_v1_bwd4_kernel<float>, grid4, 256, 0, st, (const float*)dy, (const float*)x, crop, (float*)dx, dcrop, C, hw, vpp);
+        else pv2::launch(ra_v1_bwd4_kernel<__nv_bfloat16>, grid4, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)dx, dcrop, C, hw, vpp);
+        PV2_LAUNCH_CHECK("ra_v1_scale_bwd");
+        return 0;
+    }
+    dim3 grid((hw + 31) / 32, B);
     if (dtype == PV2_F32) pv2::launch(ra_v1_bwd_kernel<float>, grid, 256, 0, st, (const float*)dy, (const float*)x, crop, (float*)dx, dcrop, C, hw);
     else pv2::launch(ra_v1_bwd_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)dx, dcrop, C, hw);
     PV2_LAUNCH_CHECK("ra_v1_scale_bwd");

@@ -186,6 +186,7 @@ class Engine:
         # fill whatever SMs the chains leave idle; backward() joins the companions before the gradients are unpacked.
         self.wside = _wgrad_streams(device) if (streams_enabled() and os.environ.get("PV2_WGRAD_STREAMS", "1") != "0") else None
         self._wused = set()
+        self._pack_ev, self._late_keys, self._pack_waited = None, set(), set()
         self._keep = []           # every buffer of this pass (see the class docstring)
         self.lib = _lib.load()
         self.cache = cache if cache is not None else {}
@@ -332,9 +333,7 @@ class Engine:
             w_d = (torch.zeros if Cout_p != Cout else torch.empty)(dshape, dtype=self.op_dtype, device=self.dev)
         return w_f, w_d, (KH, KW, taps, Cin, Cout, Cin_p, Cout_p)
 
-    def prepack(self, groups):
-        """Pack the weights of all `groups` (lists of nn.Conv2d fused along Cout) in both layouts with one launch per
-        40 tensors; called at the start of a run once the group list of this head is known."""
+    def _pack_groups(self, groups, stream):
         descs, start = [], 0
         for convs in groups:
             w_f, w_d, (KH, KW, taps, Cin, Cout, Cin_p, Cout_p) = self._alloc_packed(convs)
@@ -351,7 +350,38 @@ class Engine:
                 o += cv.out_channels
         if descs:
             arr = np.array(descs, dtype=_PACK_DT)
-            _lib.check(self.lib.pv2_weight_pack_multi(arr.ctypes.data, len(descs), self.planes, self.kind, _stream()), "pv2_weight_pack_multi")
+            _lib.check(self.lib.pv2_weight_pack_multi(arr.ctypes.data, len(descs), self.planes, self.kind, stream), "pv2_weight_pack_multi")
+
+    def prepack(self, groups, early=0):
+        """Pack the weights of all `groups` (lists of nn.Conv2d fused along Cout) in both layouts with one launch per
+        40 tensors; called at the start of a run once the group list of this head is known.  The first `early` groups (the
+        level GEMMs that open the head) are packed on the current stream; the rest -- most of the bytes: the 5x5 stacks -- on a
+        companion stream while those GEMMs already run, and every stream waits for them before its first other conv."""
+        groups = list(groups)
+        if self.wside is None or early <= 0 or early >= len(groups):
+            return self._pack_groups(groups, _stream())
+        # buffers of the late groups are allocated here (current stream) and filled on the companion stream
+        self._pack_groups(groups[:early], _stream())
+        cur = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        ws = self.wside[0]
+        ws.wait_event(ev)
+        with torch.cuda.stream(ws):
+            self._pack_groups(groups[early:], ws.cuda_stream)
+            self._pack_ev = torch.cuda.Event()
+            self._pack_ev.record(ws)
+        self._late_keys = {self._gkey(g) for g in groups[early:]}
+        self._pack_waited = set()
+
+    def _await_pack(self, key):
+        """Order the current stream after the companion-stream pack if `key`'s weights were packed there."""
+        if self._pack_ev is None or key not in self._late_keys:
+            return
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream not in self._pack_waited:
+            cur.wait_event(self._pack_ev)
+            self._pack_waited.add(cur.cuda_stream)
 
     def _unpack(self, jobs, stream):
         """[split][Cout][tap][Cin_p] partials -> OIHW weight gradients, one launch per 56 tensors."""
@@ -418,6 +448,7 @@ class Engine:
         key = self._gkey(convs)
         if key not in self.packed:      # first run of this head (group list not cached yet): pack this group on its own
             self.prepack([convs])
+        self._await_pack(key)
         w_op = self.packed[key][0]
         N, H, W = x.N, x.H, x.W
         if out_nchw_bias:
@@ -857,7 +888,7 @@ class _HeadFn(torch.autograd.Function):
         eng = Engine(inputs[0].device, precision, training, need_grad, cache)
         in_grads = [None] * n_inputs
         if cache is not None and "groups" in cache:
-            eng.prepack(cache["groups"])           # every conv weight of this head, both layouts, one launch per 40 tensors
+            eng.prepack(cache["groups"], cache.get("early_groups", 0))   # every conv weight of this head, both layouts
         outs = runner(eng, inputs, in_grads)
         if cache is not None and "groups" not in cache:
             cache["groups"] = eng.groups_seen

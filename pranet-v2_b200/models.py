@@ -142,7 +142,9 @@ class _V2Mixin(_PraNetBase):
             return [l2_fg, l3_fg, l4_fg, l5_fg, l2_bg, l3_bg, l4_bg, l5_bg]
 
         from .heads import dual_heads_run as dual
-        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training, self.__dict__.setdefault("_pv2_cache", {}))
+        cache = self.__dict__.setdefault("_pv2_cache", {})
+        cache["early_groups"] = 3          # the three level GEMMs open the head: their weights are packed first, the rest meanwhile
+        return E.run_head(runner, [x2, x3, x4], self.head_parameters(), self.training, cache)
 
 
     @torch.no_grad()

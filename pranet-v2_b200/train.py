@@ -150,6 +150,7 @@ class TrainStep:
         self.clip, self.autocast, self.channels_last, self.use_graph = clip, autocast_backbone, channels_last, use_graph
         self._graphs = {}      # (image shape, mask shape) -> (graph_a, graph_b, static image, static mask, loss)
         self._pool = None
+        self._staged, self._copy_stream, self._stage_bufs, self._stage_slot = None, None, {}, 0
         self.pv2_launches_per_step = 0
 
     # -- the two halves of a step ------------------------------------------------------------------------
@@ -260,9 +261,42 @@ class TrainStep:
             losses.append(self.step_device(im, gt).clone())
         return losses
 
-    def step_host(self, images_pinned: torch.Tensor, gts_pinned: torch.Tensor) -> float:
-        """End-to-end step: pinned host inputs -> H2D -> step -> loss read back to the host."""
-        return float(self.step_device(images_pinned, gts_pinned).item())
+    def step_host(self, images_pinned: torch.Tensor, gts_pinned: torch.Tensor, next_batch=None) -> float:
+        """End-to-end step: pinned host inputs -> H2D -> step -> loss read back to the host.
+
+        `next_batch=(images_pinned, gts_pinned)` is the batch the NEXT call will be given: its host-to-device copy is started on a
+        copy stream as soon as this step's kernels are queued, so it crosses PCIe while the GPU computes (what a prefetching
+        data loader does; the reference's loop copies synchronously, MyTrain_med.py:63-68).  Every step still moves its own
+        inputs host -> device and its loss device -> host."""
+        ev_top = torch.cuda.Event()
+        ev_top.record(torch.cuda.current_stream())                   # everything queued by earlier calls (incl. their reads of the staging slots)
+        staged = self._staged
+        if staged is not None and staged[0] is images_pinned and staged[1] is gts_pinned:
+            torch.cuda.current_stream().wait_event(staged[4])
+            images, gts = staged[2], staged[3]                       # already on the device (prefetched during the last step)
+        else:
+            images, gts = images_pinned, gts_pinned
+        self._staged = None
+        loss = self.step_device(images, gts)
+        if next_batch is not None:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cs = self._copy_stream
+            self._stage_slot = 1 - self._stage_slot                  # two slots: the one being read now is never the one being filled
+            key = (tuple(next_batch[0].shape), tuple(next_batch[1].shape), self._stage_slot)
+            if key not in self._stage_bufs:
+                self._stage_bufs[key] = (torch.empty(next_batch[0].shape, dtype=next_batch[0].dtype, device=self.device),
+                                         torch.empty(next_batch[1].shape, dtype=next_batch[1].dtype, device=self.device))
+            di, dg = self._stage_bufs[key]
+            cs.wait_event(ev_top)
+            with torch.cuda.stream(cs):
+                di.copy_(next_batch[0], non_blocking=True)
+                dg.copy_(next_batch[1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            self._staged = (next_batch[0], next_batch[1], di, dg, ev)
+        out = float(loss.item())
+        return out
 
 
 @torch.no_grad()

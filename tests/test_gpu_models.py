@@ -216,3 +216,28 @@ def test_train_step_multiscale_graphs():
     assert 0 < moved <= 3.5e-4                                     # at most 3 x lr (bias-corrected Adam step <= lr per step ... first steps)
     again = [float(v) for v in ts.step_multiscale(x, gt, trainsize=128)]
     assert len(ts._graphs) == 3 and sum(again) < sum(losses)        # replays only, and it trains
+
+
+def test_step_host_prefetch_equals_plain():
+    """step_host with next_batch= (H2D of the next batch overlapped with this step's compute) trains exactly like step_host
+    without it: same batches in the same order reach the same losses."""
+    from pranet_v2_b200.train import TrainStep
+    from pranet_v2_b200 import synthetic
+    batches = [(synthetic.images(2, 96, i).pin_memory(), synthetic.ellipse_masks(2, 96, 96, i).pin_memory()) for i in range(4)]
+    losses = []
+    for prefetch in (False, True):
+        torch.manual_seed(0)
+        m = P.PraNet_V2(num_class=1)
+        m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=3))
+        ts = TrainStep(m, lr=1e-4, clip=0.5, autocast_backbone=False, device="cuda:0", use_graph=True)
+        out = []
+        for i in range(6):
+            x, g = batches[i % 4]
+            nxt = batches[(i + 1) % 4] if prefetch else None
+            out.append(ts.step_host(x, g, next_batch=nxt))
+        losses.append(out)
+    # two independent training runs agree to ~1e-4 (cuDNN's backbone gradients are not bit-reproducible and Adam amplifies that);
+    # a batch consumed out of order would move the loss by far more: the batches' own losses differ by > 2e-2 relative
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 2e-3 * abs(a), (losses[0], losses[1])
+    assert abs(losses[0][0] - losses[0][1]) > 2e-2 * abs(losses[0][0]), losses[0]
