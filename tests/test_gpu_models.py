@@ -235,6 +235,8 @@ def test_step_host_prefetch_equals_plain():
             x, g = batches[i % 4]
             nxt = batches[(i + 1) % 4] if prefetch else None
             out.append(ts.step_host(x, g, next_batch=nxt))
+            (_, _, img_static, gt_static, _), = ts._graphs.values()
+            assert torch.equal(img_static.cpu(), x) and torch.equal(gt_static.cpu(), g), f"step {i}: the graph consumed another batch"
         losses.append(out)
     # two independent training runs agree to ~1e-4 (cuDNN's backbone gradients are not bit-reproducible and Adam amplifies that)
     for a, b in zip(*losses):
