@@ -278,7 +278,7 @@ def main():
             "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": train_config(args, world),
+            "config": dict(train_config(args, world), loss_from_lowres=bool(ts.loss_from_lowres)),
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": imgs_h[0].numel() * 4 + gts_h[0].numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,

@@ -127,7 +127,7 @@ def trace_graph(graph, path, B, S, reps=3):
             f.write(f"{v[1] / reps:10.1f} us n={v[0] // reps:5d} avg {v[1] / v[0]:7.2f} us  {k}\n")
 
 
-def sweep_point(P, model, B, S, iters, chans, dev):
+def sweep_point(P, model, B, S, iters, chans, dev, lowres=False):
     from pranet_v2_b200 import synthetic
     g = torch.Generator(device="cpu").manual_seed(B * 1000 + S)
     feats = [torch.relu(torch.randn(B, c, S // s, S // s, generator=g)).to(dev).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
@@ -142,8 +142,12 @@ def sweep_point(P, model, B, S, iters, chans, dev):
             p.grad = None
         for f in feats:
             f.grad = None
-        outs = model.forward_head(*feats)
-        loss = P.structure_loss_multi([(outs[i], outs[i + 4]) for i in range(4)], gt).sum()
+        if lowres:      # head stopped at the low-res maps, final upsamples inside the loss kernels
+            outs = model.forward_head(*feats, lowres=True)
+            loss = P.structure_loss_lowres([(outs[i], outs[i + 4]) for i in range(4)], model.final_scale_factors(), gt).sum()
+        else:
+            outs = model.forward_head(*feats)
+            loss = P.structure_loss_multi([(outs[i], outs[i + 4]) for i in range(4)], gt).sum()
         loss.backward()
         return loss
 
@@ -167,7 +171,7 @@ def sweep_point(P, model, B, S, iters, chans, dev):
     # algorithmic HBM bytes of the full-resolution part of the step (fp32 maps): 8 final maps written (fwd) and their
     # gradients read (bwd) by the upsample kernels, the loss reading 8 maps + mask (fwd) and reading 8 + mask / writing 8 (bwd)
     full_res_bytes = px * 4 * (8 + 8 + (8 + 1) + (8 + 1 + 8))
-    return {"B": B, "S": S, "ms_graph": ms, "ms_eager": ms_eager, "images_per_s": B / ms * 1e3, "pv2_launches": launches,
+    return {"B": B, "S": S, "loss_from_lowres": bool(lowres), "ms_graph": ms, "ms_eager": ms_eager, "images_per_s": B / ms * 1e3, "pv2_launches": launches,
             "loss": float(loss), "head_conv_gflop_fwd": head_flops(model, B, S) / 1e9,
             "conv_tflops_fwd_bwd": 3 * head_flops(model, B, S) / (ms * 1e-3) / 1e12,
             "full_res_bytes": full_res_bytes, "full_res_gbs_if_alone": full_res_bytes / (ms * 1e-3) / 1e9}
@@ -215,6 +219,34 @@ def kernel_table(P, dev, B, S, hbm, tflops):
     rows.append(("structure_loss fwd x4 (+ boundary weight + finalize)", "hbm", px * (4 + 4 * 8), t))
     t = timed_graph(sl_bwd)
     rows.append(("structure_loss bwd x4", "hbm", px * (4 + 4 * 16), t))
+    # the same four losses from the LOW-RES maps (8 f2): final upsamples inside the loss kernels, no full-resolution maps / gradients.
+    # Algorithmic bytes: mask read + 16-bit weight map written (fwd) / both read (bwd); these launches are issue bound, the number to
+    # compare is their time against [bilinear x8 fwd + loss fwd] and [loss bwd + bilinear x8 bwd] below.
+    lscs = (8, 16, 32, 8)
+    lfg = [[torch.randn(B, 1, S // s, S // s, device=dev) * 3 for s in lscs] for _ in range(2)]
+    dlow = [[torch.empty(B, 1, S // s, S // s, device=dev) for s in lscs] for _ in range(2)]
+    lws_bytes = lib.pv2_structure_loss_lowres_workspace_bytes(B, S, S, 4)
+    lws = torch.empty(lws_bytes // 4, device=dev)
+    masks = [synthetic.ellipse_masks(B, S, S, 3 + j).to(dev) for j in range(nset)]
+    lih = (ctypes.c_int * 4)(*[S // s for s in lscs])
+    lrr = (ctypes.c_float * 4)(*[_ratio(S // s, S, False, float(s)) for s in lscs])
+    lp = [P._lib.ptr_array(t) for t in lfg + dlow]
+
+    def ll_fwd():
+        P._lib.check(lib.pv2_structure_loss_lowres_fwd(lp[0][0], lp[1][0], lih, lih, lrr, lrr, masks[rot()].data_ptr(), None, 4, B, S, S,
+                                                       loss.data_ptr(), lws.data_ptr(), lws_bytes, cur()), "lowres fwd")
+
+    def ll_bwd():
+        P._lib.check(lib.pv2_structure_loss_lowres_bwd(lp[0][0], lp[1][0], lih, lih, lrr, lrr, masks[0].data_ptr(), None, gl.data_ptr(), lp[2][0], lp[3][0],
+                                                       4, B, S, S, lws.data_ptr(), lws_bytes, cur()), "lowres bwd")
+    ll_fwd()
+    rows.append(("structure_loss_lowres fwd x4 (upsamples + boundary weight + loss, one launch)", "hbm", px * (4 + 2), timed_graph(ll_fwd)))
+    # the backward reads the weight map / plane sums of the forward that ran last: run it on the mask the backward is given
+    ll_fwd_last = lambda: P._lib.check(lib.pv2_structure_loss_lowres_fwd(lp[0][0], lp[1][0], lih, lih, lrr, lrr, masks[0].data_ptr(), None, 4, B, S, S,
+                                                                         loss.data_ptr(), lws.data_ptr(), lws_bytes, cur()), "lowres fwd")
+    ll_fwd_last()
+    rows.append(("structure_loss_lowres bwd x4 (+ fold: 2 launches)", "hbm", px * (4 + 2), timed_graph(ll_bwd)))
+    del lfg, dlow, lws, masks
     # final upsamples: x8 of a 44^2 map (two of the 8 maps are x32 / x16; x8 dominates), fp32
     for s in (8, 16, 32):
         h = S // s
@@ -314,6 +346,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--backbone", default="res2net", choices=["res2net", "pvt"])
     ap.add_argument("--kernels", action="store_true")
+    ap.add_argument("--lowres-loss", default="0", choices=["0", "1", "both"], help="loss from the low-res maps (SURVEY.md 8 f2): off / on / both, one line each")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     if not torch.cuda.is_available():
@@ -335,18 +368,19 @@ def main():
         for B in [int(b) for b in args.batches.split(",")]:
             if B * S * S > 64 * 704 * 704:
                 continue
-            r = sweep_point(P, model, B, S, args.iters, chans, dev)
-            if world > 1:
-                t = torch.tensor([r["ms_graph"]], device=dev, dtype=torch.float64)
-                allt = [torch.zeros_like(t) for _ in range(world)]
-                dist.all_gather(allt, t)
-                v = sorted(float(x) for x in allt)
-                r["ms_graph_min_over_gpus"], r["ms_graph_median_over_gpus"], r["n_gpus"] = v[0], v[len(v) // 2], world
-            r.update({"precision": args.precision, "backbone": args.backbone, "peaks": src})
-            lines.append(r)
-            if rank == 0:
-                print(json.dumps(r), flush=True)
-            torch.cuda.empty_cache()
+            for lowres in {"0": (False,), "1": (True,), "both": (False, True)}[args.lowres_loss]:
+                r = sweep_point(P, model, B, S, args.iters, chans, dev, lowres)
+                if world > 1:
+                    t = torch.tensor([r["ms_graph"]], device=dev, dtype=torch.float64)
+                    allt = [torch.zeros_like(t) for _ in range(world)]
+                    dist.all_gather(allt, t)
+                    v = sorted(float(x) for x in allt)
+                    r["ms_graph_min_over_gpus"], r["ms_graph_median_over_gpus"], r["n_gpus"] = v[0], v[len(v) // 2], world
+                r.update({"precision": args.precision, "backbone": args.backbone, "peaks": src})
+                lines.append(r)
+                if rank == 0:
+                    print(json.dumps(r), flush=True)
+                torch.cuda.empty_cache()
     if args.kernels and rank == 0:
         for r in kernel_table(P, dev, 16, 352, hbm, tfl):
             r["peaks"] = src

@@ -59,6 +59,26 @@ int pv2_structure_loss_bwd(const void* const* pred, const void* const* pred_bg, 
                            void* const* dpred_bg, int nscales, int planes, int H, int W, int logit_dtype,
                            const void* workspace, size_t workspace_bytes, void* stream);
 
+/* structure_loss computed FROM THE LOW-RESOLUTION head maps: the final
+ * F.interpolate(scale_factor=8|16|32, mode='bilinear', align_corners=False) of binary_seg/lib/pranet.py:349-350,
+ * 370-371,392-393,414-415 and the four structure_loss calls of MyTrain_med.py:78-82 as ONE forward launch and one
+ * backward launch (+ a fold): the eight full-resolution logit maps and their gradients never exist in HBM.
+ *   low_fg[k], low_bg[k] : fp32 (planes, ih[k], iw[k]) maps BEFORE their final upsample; rh[k], rw[k] = ATen's source-index
+ *                          ratios of that upsample (1/scale_factor); all HOST arrays of nscales entries.
+ *   mask_fg / mask_bg    : fp32 (planes, H, W) as for pv2_structure_loss_fwd (mask_bg NULL = 1 - mask_fg).
+ *   fwd writes loss[k]; bwd writes dlow_fg[k], dlow_bg[k] (same shapes as the maps) = grad_loss[k] * dloss_k/dmap.
+ * Results equal pv2_bilinear_fwd -> pv2_structure_loss_fwd/bwd -> pv2_bilinear_bwd up to fp32 summation order; the
+ * backward is deterministic (no atomics).  Covered: W % 4 == 0, 16-byte aligned masks, ratios <= 1/4 (up-scaling by >= 4);
+ * anything else returns an error and the caller takes the unfused pv2 kernels.  The workspace must be the one the forward used. */
+size_t pv2_structure_loss_lowres_workspace_bytes(int planes, int H, int W, int nscales);
+int pv2_structure_loss_lowres_fwd(const float* const* low_fg, const float* const* low_bg, const int* ih, const int* iw,
+                                  const float* rh, const float* rw, const float* mask_fg, const float* mask_bg,
+                                  int nscales, int planes, int H, int W, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+int pv2_structure_loss_lowres_bwd(const float* const* low_fg, const float* const* low_bg, const int* ih, const int* iw,
+                                  const float* rh, const float* rw, const float* mask_fg, const float* mask_bg,
+                                  const float* grad_loss, float* const* dlow_fg, float* const* dlow_bg,
+                                  int nscales, int planes, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * bilinear resize of NCHW planes -- F.interpolate(mode='bilinear') at binary_seg/lib/pranet.py:349-415
  * (x8/x16/x32 final maps, x0.25 / x2 crops, align_corners=False), nn.Upsample(scale_factor=2,

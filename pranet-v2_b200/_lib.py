@@ -27,6 +27,9 @@ _SIGS = {
     "pv2_structure_loss_workspace_bytes": (_sz, [_i] * 4),
     "pv2_structure_loss_fwd": (_i, [c_void_pp, c_void_pp, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pv2_structure_loss_bwd": (_i, [c_void_pp, c_void_pp, _p, _p, _p, c_void_pp, c_void_pp, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "pv2_structure_loss_lowres_workspace_bytes": (_sz, [_i] * 4),
+    "pv2_structure_loss_lowres_fwd": (_i, [c_void_pp, c_void_pp, _ip, _ip, _fp, _fp, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pv2_structure_loss_lowres_bwd": (_i, [c_void_pp, c_void_pp, _ip, _ip, _fp, _fp, _p, _p, _p, c_void_pp, c_void_pp, _i, _i, _i, _i, _p, _sz, _p]),
     "pv2_bilinear_fwd": (_i, [_p, _p] + [_i] * 5 + [_f, _f, _i, _i, _p]),
     "pv2_bilinear_bwd": (_i, [_p, _p] + [_i] * 5 + [_f, _f, _i, _i, _p]),
     "pv2_bilinear_multi_fwd": (_i, [c_void_pp, c_void_pp, _ip, _ip, C.POINTER(C.c_float), C.POINTER(C.c_float)] + [_i] * 6 + [_p]),

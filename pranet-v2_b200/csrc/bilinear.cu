@@ -220,18 +220,30 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
         rgroups = 1;
     }
     __syncthreads();
-    for (int it = threadIdx.x; it < nr * iw; it += blockDim.x) {
-        const int r = it / iw, ix = it - r * iw;
-        int xl, xh;
-        touch_window(ix, ow, rw, ac, xl, xh);
+    // pass 2: an input pixel is folded by a group of L lanes (L = the power of two that spreads the nr*iw pixels over the CTA:
+    // 32 / 8 / 2 lanes at x32 / x16 / x8), each lane taking every L-th column of the window, then a fixed shuffle tree.  One
+    // thread per pixel made this pass a 2s-long serial chain on 11..176 threads -- about half of the kernel's time.
+    const int items = nr * iw;
+    int L = 32;
+    while (L > 1 && items * L > (int)blockDim.x) L >>= 1;
+    const int sub = threadIdx.x & (L - 1), per_pass = blockDim.x / L;
+    for (int it0 = 0; it0 < items; it0 += per_pass) {       // uniform trip count: the shuffles below need every lane
+        const int it = it0 + threadIdx.x / L;
         float acc = 0.0f;
-        const float* base = colsum + r * rgroups * pitch;
-        for (int ox = xl; ox <= xh; ++ox) {
-            float cs = base[ox];
-            for (int k = 1; k < rgroups; ++k) cs += base[k * pitch + ox];
-            acc += tap_weight(ox, ix, iw, rw, ac) * cs;
+        int r = 0, ix = 0;
+        if (it < items) {
+            r = it / iw; ix = it - r * iw;
+            int xl, xh;
+            touch_window(ix, ow, rw, ac, xl, xh);
+            const float* base = colsum + r * rgroups * pitch;
+            for (int ox = xl + sub; ox <= xh; ox += L) {
+                float cs = base[ox];
+                for (int k = 1; k < rgroups; ++k) cs += base[k * pitch + ox];
+                acc = fmaf(tap_weight(ox, ix, iw, rw, ac), cs, acc);
+            }
         }
-        din[((size_t)plane * ih + iy0 + r) * iw + ix] = from_f<T>(acc);
+        for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (it < items && sub == 0) din[((size_t)plane * ih + iy0 + r) * iw + ix] = from_f<T>(acc);
     }
 }
 

@@ -304,9 +304,67 @@ constexpr int FS_W = FT_W + 2 * HALO + 1;      // 159
 constexpr int FS_PITCH = 161;                  // odd: column walks and row scans are both bank-conflict free
 constexpr int FS_PER_LANE = 5;                 // 32 lanes x 5 = 160 >= 158 staged columns
 
-template <typename T, int NS>
+// ---- loss from the low-resolution maps: geometry of the final upsamples (align_corners=False), tap tables, interpolation ----
+struct LowresGeo {
+    int ih[PV2_MAX_SCALES], iw[PV2_MAX_SCALES];
+    float rh[PV2_MAX_SCALES], rw[PV2_MAX_SCALES];     // ATen's source-index ratios (1/scale_factor)
+};
+
+// (i0, w1) of the bilinear tap of every column / row of a 32 x 128 tile, per scale; i1 = min(i0 + 1, size - 1), w0 = 1 - w1 as in
+// pv2::bilinear_tap.  Coordinates beyond the image are clamped to its last row / column (those pixels carry no weight).
+template <int NS>
+__device__ __forceinline__ void fill_tap_tables(float2 (*xt)[FT_W], float2 (*yt)[FT_H], const LowresGeo& geo, int y0, int x0, int H, int W, int tid) {
+    for (int i = tid; i < NS * FT_W; i += LS_THREADS) {
+        const int k = i / FT_W, c = i - k * FT_W;
+        const Tap t = bilinear_tap(min(x0 + c, W - 1), geo.iw[k], geo.rw[k], false);
+        xt[k][c] = make_float2(__int_as_float(t.i0), t.w1);
+    }
+    for (int i = tid; i < NS * FT_H; i += LS_THREADS) {
+        const int k = i / FT_H, r = i - k * FT_H;
+        const Tap t = bilinear_tap(min(y0 + r, H - 1), geo.ih[k], geo.rh[k], false);
+        yt[k][r] = make_float2(__int_as_float(t.i0), t.w1);
+    }
+}
+
+// the four upsampled logits of a column quad, foreground and background map at once (same taps); `xq` = the quad's 4 table entries
+__device__ __forceinline__ void interp_quad2(const float* __restrict__ fg, const float* __restrict__ bg, int ih, int iw, float2 ytap,
+                                             const float2* xq, float (&vf)[4], float (&vb)[4]) {
+    const int y0i = __float_as_int(ytap.x), y1i = min(y0i + 1, ih - 1);
+    const float wy1 = ytap.y, wy0 = 1.0f - wy1;
+    const float4 q01 = *reinterpret_cast<const float4*>(xq), q23 = *reinterpret_cast<const float4*>(xq + 2);
+    const int xi[4] = {__float_as_int(q01.x), __float_as_int(q01.z), __float_as_int(q23.x), __float_as_int(q23.z)};
+    const float xw1[4] = {q01.y, q01.w, q23.y, q23.w};
+    const float* fa = fg + (size_t)y0i * iw;
+    const float* fb = fg + (size_t)y1i * iw;
+    const float* ba = bg + (size_t)y0i * iw;
+    const float* bb = bg + (size_t)y1i * iw;
+    if (xi[0] == xi[3]) {            // integer up-scaling by a multiple of 8: the quad shares its two source columns (4 loads per map, not 16)
+        const int c0 = xi[0], c1 = min(c0 + 1, iw - 1);
+        const float f00 = __ldg(fa + c0), f01 = __ldg(fa + c1), f10 = __ldg(fb + c0), f11 = __ldg(fb + c1);
+        const float b00 = __ldg(ba + c0), b01 = __ldg(ba + c1), b10 = __ldg(bb + c0), b11 = __ldg(bb + c1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // same expression, same order as bilinear_fwd_kernel
+            const float xw0 = 1.0f - xw1[j];
+            vf[j] = wy0 * (xw0 * f00 + xw1[j] * f01) + wy1 * (xw0 * f10 + xw1[j] * f11);
+            vb[j] = wy0 * (xw0 * b00 + xw1[j] * b01) + wy1 * (xw0 * b10 + xw1[j] * b11);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c0 = xi[j], c1 = min(c0 + 1, iw - 1);
+            const float xw0 = 1.0f - xw1[j];
+            vf[j] = wy0 * (xw0 * __ldg(fa + c0) + xw1[j] * __ldg(fa + c1)) + wy1 * (xw0 * __ldg(fb + c0) + xw1[j] * __ldg(fb + c1));
+            vb[j] = wy0 * (xw0 * __ldg(ba + c0) + xw1[j] * __ldg(ba + c1)) + wy1 * (xw0 * __ldg(bb + c0) + xw1[j] * __ldg(bb + c1));
+        }
+    }
+}
+
+// LOWRES: pp.pred / pp.pred_bg are the LOW-RESOLUTION head maps (fp32 planes of geo.ih x geo.iw) and the
+// final F.interpolate(scale_factor=8|16|32, mode='bilinear') of pranet.py:349-415 happens here, per pixel, from tap tables in
+// shared memory: the eight full-resolution logit maps are never written or read (HBM bytes per pixel: 4 read + 2 written).
+template <typename T, int NS, bool LOWRES>
 __global__ void __launch_bounds__(LS_THREADS, 4)
-structure_loss_fwd_fused_kernel(PtrPack pp, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
+structure_loss_fwd_fused_kernel(PtrPack pp, const __grid_constant__ LowresGeo geo, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
                                 uint16_t* __restrict__ wmap, int H, int W, int planes, int tiles_x, int tiles,
                                 float* __restrict__ partials, float* __restrict__ wsum_part, float* __restrict__ plane_sums,
                                 float* __restrict__ plane_loss, float* __restrict__ loss, unsigned int* __restrict__ ticket) {
@@ -314,12 +372,15 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const float* __restrict__ mask_fg, c
     __shared__ float sat[FS_H * FS_PITCH];
     __shared__ float red[LS_THREADS / 32][4 * NS + 1];
     __shared__ bool is_last;
+    __shared__ __align__(16) float2 xt[LOWRES ? NS : 1][LOWRES ? FT_W : 1];   // per scale and tile column / row: (i0 as bits, w1) of the bilinear tap
+    __shared__ float2 yt[LOWRES ? NS : 1][LOWRES ? FT_H : 1];
     const int plane = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int y0 = (tile / tiles_x) * FT_H, x0 = (tile % tiles_x) * FT_W;
     const int HW = H * W;
     const size_t pbase = (size_t)plane * HW;
     const float* mp = mask_fg + pbase;
+    if constexpr (LOWRES) fill_tap_tables<NS>(xt, yt, geo, y0, x0, H, W, tid);      // visible after the first __syncthreads below
     // ---- stage + row prefix: warp = table row, lane = 5 consecutive columns ----
     if (tid < FS_PITCH) sat[tid] = 0.0f;                       // row 0
     constexpr int ROWS_PW = (FS_H - 1 + LS_THREADS / 32 - 1) / (LS_THREADS / 32);   // 8 table rows per warp
@@ -392,8 +453,14 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const float* __restrict__ mask_fg, c
         m.load(mask_fg + p);
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            x[k].load(reinterpret_cast<const T*>(pp.pred[k]) + p);
-            xb[k].load(reinterpret_cast<const T*>(pp.pred_bg[k]) + p);
+            if constexpr (LOWRES) {
+                const size_t lp = (size_t)plane * geo.ih[k] * geo.iw[k];
+                interp_quad2(reinterpret_cast<const float*>(pp.pred[k]) + lp, reinterpret_cast<const float*>(pp.pred_bg[k]) + lp,
+                             geo.ih[k], geo.iw[k], yt[k][ty], &xt[k][tx], x[k].v, xb[k].v);
+            } else {
+                x[k].load(reinterpret_cast<const T*>(pp.pred[k]) + p);
+                xb[k].load(reinterpret_cast<const T*>(pp.pred_bg[k]) + p);
+            }
         }
         if (mask_bg != nullptr) mb.load(mask_bg + p);
         else {
@@ -554,6 +621,213 @@ structure_loss_bwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// 3b. backward of the loss from the low-resolution maps: d loss / d (low-res fg_k, bg_k) directly.
+//
+// CTA = 32 x 128 pixel tile of one plane, warp = tile row, lane = quad of 4 columns.  Per scale: the per-pixel gradients of the
+// (recomputed) upsampled logits are multiplied by their x tap weights and pre-reduced in registers over the quad (a quad touches at
+// most 3 source columns when the ratio is <= 1/4), folded along x over the lanes, then along y over the 32 rows -- all in shared
+// memory, fixed order.  The tile's contribution to the few low-res pixels it touches goes to a private slot; lowres_grad_fold_kernel
+// sums the <= 6 slots of every low-res pixel in tile order: no atomics, bit-reproducible.  The full-resolution gradients (8 x 8 MB at
+// B = 16 x 352^2) and the bilinear backward that would read them back do not exist on this path.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LR_RMAX = 10, LR_CMAX = 34;              // low-res rows / columns a 32 x 128 tile can touch at ratio <= 1/4
+constexpr int LR_SLOT = LR_RMAX * LR_CMAX;             // floats per (tile, scale, map) slot
+constexpr int LR_QPITCH = 32 * 3 + 1;                  // Q row pitch (odd: the x fold walks rows across lanes)
+constexpr int LR_HPITCH = FT_H + 1;
+
+// low-res rows (or columns) a tile edge of `n` pixels starting at o0 touches: [first, first + count)
+__device__ __forceinline__ void tile_span(int o0, int n, int out_size, int in_size, float ratio, int& first, int& count) {
+    first = bilinear_tap(min(o0, out_size - 1), in_size, ratio, false).i0;
+    count = bilinear_tap(min(o0 + n - 1, out_size - 1), in_size, ratio, false).i1 - first + 1;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(LS_THREADS, 2)
+structure_loss_lowres_bwd_kernel(const __grid_constant__ PtrPack pp, const __grid_constant__ LowresGeo geo, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
+                                 const uint16_t* __restrict__ wmap, const float* __restrict__ grad_loss, const float* __restrict__ plane_sums,
+                                 float* __restrict__ gpart, int H, int W, int planes, int tiles_x, int tiles) {
+    pv2::pdl_prologue();
+    __shared__ __align__(16) float2 xt[NS][FT_W];
+    __shared__ float2 yt[NS][FT_H];
+    __shared__ float Q[2][FT_H][LR_QPITCH];            // per map, tile row, lane: the quad's contribution to source columns cb, cb+1, cb+2
+    __shared__ float Hs[2][LR_CMAX][LR_HPITCH];        // per map, low-res column, tile row: x-folded
+    const int plane = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int y0 = (tile / tiles_x) * FT_H, x0 = (tile % tiles_x) * FT_W;
+    const size_t pbase = (size_t)plane * H * W;
+    fill_tap_tables<NS>(xt, yt, geo, y0, x0, H, W, tid);
+    const float* ps = plane_sums + (size_t)plane * NSUM;
+    const float invW = 1.0f / ps[0], invn = 1.0f / (float)planes;
+    // mask and boundary weight of this thread's 4 rows x 4 columns (loaded once, used by every scale)
+    constexpr int RPT = FT_H / (LS_THREADS / 32);      // 4 rows per thread
+    const int tx = lane * 4, gx = x0 + tx;
+    float mv[RPT][4], mbv[RPT][4], wv[RPT][4];
+    bool ok[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int gy = y0 + warp + i * (LS_THREADS / 32);
+        ok[i] = gy < H && gx < W;                      // W % 4 == 0: a quad is inside or outside as a whole
+        if (ok[i]) {
+            const size_t p = pbase + (size_t)gy * W + gx;
+            Vec<float, 4> m;
+            m.load(mask_fg + p);
+            load_wq<4>(wmap + p, wv[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mv[i][j] = m.v[j];
+            if (mask_bg != nullptr) {
+                Vec<float, 4> mb;
+                mb.load(mask_bg + p);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mbv[i][j] = mb.v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mbv[i][j] = 1.0f - m.v[j];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { mv[i][j] = 0.0f; mbv[i][j] = 0.0f; wv[i][j] = 0.0f; }
+        }
+    }
+    __syncthreads();                                   // tap tables
+#pragma unroll 1
+    for (int k = 0; k < NS; ++k) {
+        const int ih = geo.ih[k], iw = geo.iw[k];
+        const float g = grad_loss[k] * invn;
+        const float inter = ps[1 + 4 * k + 2], uni = ps[1 + 4 * k + 3];
+        const float den = uni - inter + 1.0f, ip1 = inter + 1.0f, inv_den2 = 1.0f / (den * den);
+        const float* fgp = reinterpret_cast<const float*>(pp.pred[k]) + (size_t)plane * ih * iw;
+        const float* bgp = reinterpret_cast<const float*>(pp.pred_bg[k]) + (size_t)plane * ih * iw;
+        int r_first, nrows, c_first, ncols;
+        tile_span(y0, FT_H, H, ih, geo.rh[k], r_first, nrows);
+        tile_span(x0, FT_W, W, iw, geo.rw[k], c_first, ncols);
+        nrows = min(nrows, LR_RMAX);                   // cannot bind at ratio <= 1/4 (checked by the host); keeps indices in range regardless
+        ncols = min(ncols, LR_CMAX);
+        // ---- A. per-pixel gradients, weighted by their x taps and pre-reduced over the quad ----
+        const float2* xq = &xt[k][tx];
+        const int cb = __float_as_int(xq[0].x);
+        int d0[4];
+        float xw1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d0[j] = __float_as_int(xq[j].x) - cb; xw1[j] = xq[j].y; }   // d0 in {0, 1}
+        const int last = iw - 1;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int ty = warp + i * (LS_THREADS / 32);
+            float af[3] = {0.0f, 0.0f, 0.0f}, ab[3] = {0.0f, 0.0f, 0.0f};
+            if (ok[i]) {
+                float x[4], xb[4];
+                interp_quad2(fgp, bgp, ih, iw, yt[k][ty], xq, x, xb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xv = x[j], qv = xb[j], m = mv[i][j], w = wv[i][j];
+                    const float e = fast_ex2(-fabsf(xv) * LOG2E), inv = fast_rcp(1.0f + e);
+                    const float s = xv >= 0.0f ? inv : e * inv;
+                    const float e2 = fast_ex2(-fabsf(qv) * LOG2E), inv2 = fast_rcp(1.0f + e2);
+                    const float s2 = qv >= 0.0f ? inv2 : e2 * inv2;
+                    const float mw = m * w;
+                    const float dwiou = -(mw * den - ip1 * (w - mw)) * inv_den2;       // as in structure_loss_bwd_kernel
+                    const float gp = g * (w * (s - m) * invW + dwiou * s * (1.0f - s));
+                    const float gq = g * 0.8f * w * (s2 - mbv[i][j]) * invW;
+                    const float w1 = xw1[j], w0 = 1.0f - w1;
+                    const int c0 = cb + d0[j];
+                    const int e1 = d0[j] + (c0 < last ? 1 : 0);                        // column offset of the second tap (clamped at the right edge)
+                    const float p0 = gp * w0, p1 = gp * w1, q0 = gq * w0, q1 = gq * w1;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        af[d] += (d0[j] == d ? p0 : 0.0f) + (e1 == d ? p1 : 0.0f);
+                        ab[d] += (d0[j] == d ? q0 : 0.0f) + (e1 == d ? q1 : 0.0f);
+                    }
+                }
+            }
+            float* qf = &Q[0][ty][lane * 3];
+            float* qb = &Q[1][ty][lane * 3];
+            qf[0] = af[0]; qf[1] = af[1]; qf[2] = af[2];
+            qb[0] = ab[0]; qb[1] = ab[1]; qb[2] = ab[2];
+        }
+        __syncthreads();
+        // ---- B. fold along x: task = (map, low-res column, tile row); a warp shares (map, column), its lanes are the 32 rows ----
+        for (int t = tid; t < 2 * ncols * FT_H; t += LS_THREADS) {
+            const int row = t & (FT_H - 1), mc = t >> 5;
+            const int map = mc >= ncols ? 1 : 0, cl = mc - map * ncols, c = c_first + cl;
+            // lanes whose first source column is c-2, c-1 or c (monotone in the lane): conservative range from the inverse tap map
+            const float inv_r = 1.0f / geo.rw[k];
+            int l_lo = (int)floorf((((float)(c - 2) + 0.5f) * inv_r - 0.5f - (float)x0) * 0.25f) - 1;
+            int l_hi = (int)ceilf((((float)(c + 1) + 0.5f) * inv_r - 0.5f - (float)x0) * 0.25f) + 1;
+            l_lo = max(l_lo, 0);
+            l_hi = min(l_hi, 31);
+            if (c == 0) l_lo = 0;                      // clamped sources (src < 0) all land on column 0
+            const float* qrow = &Q[map][row][0];
+            float acc = 0.0f;
+            for (int l = l_lo; l <= l_hi; ++l) {
+                const int d = c - __float_as_int(xt[k][l * 4].x);
+                if (d >= 0 && d <= 2) acc += qrow[l * 3 + d];
+            }
+            Hs[map][cl][row] = acc;
+        }
+        __syncthreads();
+        // ---- C. fold along y: task = (map, low-res row, low-res column) -> this tile's slot ----
+        float* slot = gpart + (((size_t)plane * tiles + tile) * NS + k) * 2 * LR_SLOT;
+        for (int t = tid; t < 2 * nrows * ncols; t += LS_THREADS) {
+            const int map = t >= nrows * ncols ? 1 : 0, rc = t - map * nrows * ncols;
+            const int rl = rc / ncols, cl = rc - rl * ncols, r = r_first + rl;
+            const float* col = &Hs[map][cl][0];
+            float acc = 0.0f;
+#pragma unroll 8
+            for (int row = 0; row < FT_H; ++row) {
+                const float2 yq = yt[k][row];
+                const int i0 = __float_as_int(yq.x), i1 = min(i0 + 1, ih - 1);
+                const float wy = (i0 == r ? 1.0f - yq.y : 0.0f) + (i1 == r ? yq.y : 0.0f);
+                acc = fmaf(wy, col[row], acc);
+            }
+            slot[map * LR_SLOT + rl * LR_CMAX + cl] = acc;
+        }
+        // the next scale's phase A writes Q (last read before the barrier above) and its phase B writes Hs only after its own barrier
+    }
+}
+
+// dlow[k][map][plane][r][c] = sum over the tiles whose span contains (r, c) of their slot entry, in tile order.
+template <int NS>
+__global__ void __launch_bounds__(256)
+lowres_grad_fold_kernel(const __grid_constant__ PtrPack pp, const __grid_constant__ LowresGeo geo, const float* __restrict__ gpart, int H, int W, int tiles_x, int tiles) {
+    pv2::pdl_prologue();
+    const int k = blockIdx.z >> 1, map = blockIdx.z & 1, plane = blockIdx.y;
+    const int ih = geo.ih[k], iw = geo.iw[k];
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= ih * iw) return;
+    const int r = idx / iw, c = idx - r * iw;
+    // output rows / columns whose taps can touch (r, c) -> the tile rows / columns to look at (conservative; containment is checked)
+    const float irh = 1.0f / geo.rh[k], irw = 1.0f / geo.rw[k];
+    int oy_lo = (int)floorf(((float)r - 0.5f) * irh - 0.5f) - 1, oy_hi = (int)ceilf(((float)r + 1.5f) * irh - 0.5f) + 1;
+    int ox_lo = (int)floorf(((float)c - 0.5f) * irw - 0.5f) - 1, ox_hi = (int)ceilf(((float)c + 1.5f) * irw - 0.5f) + 1;
+    if (r == 0) oy_lo = 0;
+    if (c == 0) ox_lo = 0;
+    if (r == ih - 1) oy_hi = H - 1;
+    if (c == iw - 1) ox_hi = W - 1;
+    const int tiles_y = tiles / tiles_x;
+    const int ty_lo = max(oy_lo, 0) / FT_H, ty_hi = min(min(oy_hi, H - 1) / FT_H, tiles_y - 1);
+    const int tx_lo = max(ox_lo, 0) / FT_W, tx_hi = min(min(ox_hi, W - 1) / FT_W, tiles_x - 1);
+    float acc = 0.0f;
+    for (int tyi = ty_lo; tyi <= ty_hi; ++tyi) {
+        int r_first, nrows;
+        tile_span(tyi * FT_H, FT_H, H, ih, geo.rh[k], r_first, nrows);
+        nrows = min(nrows, LR_RMAX);
+        const int rl = r - r_first;
+        if (rl < 0 || rl >= nrows) continue;
+        for (int txi = tx_lo; txi <= tx_hi; ++txi) {
+            int c_first, ncols;
+            tile_span(txi * FT_W, FT_W, W, iw, geo.rw[k], c_first, ncols);
+            ncols = min(ncols, LR_CMAX);
+            const int cl = c - c_first;
+            if (cl < 0 || cl >= ncols) continue;
+            const int tile = tyi * tiles_x + txi;
+            acc += __ldcg(gpart + ((((size_t)plane * tiles + tile) * NS + k) * 2 + map) * LR_SLOT + rl * LR_CMAX + cl);
+        }
+    }
+    float* dst = reinterpret_cast<float*>(map ? pp.dpred_bg[k] : pp.dpred[k]);
+    dst[(size_t)plane * ih * iw + idx] = acc;
+}
+
 template <typename T, int VEC>
 void launch_fwd(int ns, dim3 grid, cudaStream_t st, const PtrPack& pp, const float* mf, const float* mb, const Layout& L, int HW, int planes, float* loss) {
 #define PV2_FWD(NSV) pv2::launch(structure_loss_fwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, HW, planes, L.chunks, L.wt_tiles, \
@@ -621,7 +895,8 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
         cudaError_t ce = cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), st);
         PV2_CHECK(ce == cudaSuccess, "structure_loss_fwd: memset: %s", cudaGetErrorString(ce));
         const dim3 fgrid(L.ft_tiles, planes);
-#define PV2_FUSED(TT, NSV) pv2::launch(structure_loss_fwd_fused_kernel<TT, NSV>, fgrid, LS_THREADS, 0, st, pp, mask_fg, mask_bg, L.wmap, H, W, planes, \
+        const LowresGeo geo = {};
+#define PV2_FUSED(TT, NSV) pv2::launch(structure_loss_fwd_fused_kernel<TT, NSV, false>, fgrid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, H, W, planes, \
                                        L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
         if (logit_dtype == PV2_F32) {
             switch (nscales) { case 1: PV2_FUSED(float, 1); break; case 2: PV2_FUSED(float, 2); break; case 3: PV2_FUSED(float, 3); break; default: PV2_FUSED(float, 4); break; }
@@ -670,5 +945,94 @@ extern "C" int pv2_structure_loss_bwd(const void* const* pred, const void* const
         else launch_bwd<__nv_bfloat16, 1>(nscales, grid, st, pp, mask_fg, mask_bg, L, grad_loss, HW, planes);
     }
     PV2_LAUNCH_CHECK("structure_loss_bwd");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// loss from the low-resolution maps: pranet.py:349-415 final upsamples + MyTrain_med.py:78-82 in one pass
+// ---------------------------------------------------------------------------------------------------------
+namespace pv2 {
+namespace {
+
+size_t lowres_gpart_floats(int planes, int H, int W, int nscales) {
+    const int tiles = ((W + FT_W - 1) / FT_W) * ((H + FT_H - 1) / FT_H);
+    return (size_t)planes * tiles * nscales * 2 * LR_SLOT;
+}
+
+int check_lowres(const float* const* low_fg, const float* const* low_bg, const int* ih, const int* iw, const float* rh, const float* rw,
+                 const float* mask_fg, const float* mask_bg, int nscales, int planes, int H, int W, const void* ws, size_t ws_bytes,
+                 PtrPack& pp, LowresGeo& geo) {
+    PV2_CHECK(nscales >= 1 && nscales <= PV2_MAX_SCALES, "structure_loss_lowres: nscales=%d out of range [1,%d]", nscales, PV2_MAX_SCALES);
+    PV2_CHECK(planes > 0 && planes <= 65535 && H > 0 && W > 0, "structure_loss_lowres: bad shape (planes=%d H=%d W=%d)", planes, H, W);
+    PV2_CHECK(low_fg && low_bg && ih && iw && rh && rw && mask_fg, "structure_loss_lowres: null pointer");
+    PV2_CHECK(W % 4 == 0 && aligned16(mask_fg) && (!mask_bg || aligned16(mask_bg)),
+              "structure_loss_lowres: W must be a multiple of 4 and the masks 16-byte aligned (W=%d); upsample and call pv2_structure_loss_fwd instead", W);
+    for (int k = 0; k < nscales; ++k) {
+        PV2_CHECK(low_fg[k] && low_bg[k], "structure_loss_lowres: null map pointer at scale %d", k);
+        PV2_CHECK(ih[k] > 0 && iw[k] > 0 && rh[k] > 0.0f && rw[k] > 0.0f && rh[k] <= 0.25f && rw[k] <= 0.25f,
+                  "structure_loss_lowres: scale %d (%dx%d, ratios %g %g): the fused path covers up-scaling by >= 4; upsample and call pv2_structure_loss_fwd instead",
+                  k, ih[k], iw[k], (double)rh[k], (double)rw[k]);
+        pp.pred[k] = low_fg[k]; pp.pred_bg[k] = low_bg[k];
+        geo.ih[k] = ih[k]; geo.iw[k] = iw[k]; geo.rh[k] = rh[k]; geo.rw[k] = rw[k];
+    }
+    PV2_CHECK(ws != nullptr && ((uintptr_t)ws & 255u) == 0, "structure_loss_lowres: workspace must be non-null and 256-byte aligned");
+    PV2_CHECK(ws_bytes >= pv2_structure_loss_lowres_workspace_bytes(planes, H, W, nscales), "structure_loss_lowres: workspace too small (%zu < %zu)",
+              ws_bytes, pv2_structure_loss_lowres_workspace_bytes(planes, H, W, nscales));
+    return 0;
+}
+
+}  // namespace
+}  // namespace pv2
+
+extern "C" size_t pv2_structure_loss_lowres_workspace_bytes(int planes, int H, int W, int nscales) {
+    return make_layout(nullptr, planes, H, W).bytes + sizeof(float) * lowres_gpart_floats(planes, H, W, nscales);
+}
+
+extern "C" int pv2_structure_loss_lowres_fwd(const float* const* low_fg, const float* const* low_bg, const int* ih, const int* iw,
+                                             const float* rh, const float* rw, const float* mask_fg, const float* mask_bg,
+                                             int nscales, int planes, int H, int W, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+    PtrPack pp = {};
+    LowresGeo geo = {};
+    if (int e = check_lowres(low_fg, low_bg, ih, iw, rh, rw, mask_fg, mask_bg, nscales, planes, H, W, workspace, workspace_bytes, pp, geo)) return e;
+    PV2_CHECK(loss != nullptr, "structure_loss_lowres_fwd: null loss pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout L = make_layout(workspace, planes, H, W);
+    cudaError_t ce = cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), st);
+    PV2_CHECK(ce == cudaSuccess, "structure_loss_lowres_fwd: memset: %s", cudaGetErrorString(ce));
+    const dim3 fgrid(L.ft_tiles, planes);
+#define PV2_LOWRES(NSV) pv2::launch(structure_loss_fwd_fused_kernel<float, NSV, true>, fgrid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, H, W, planes, \
+                                    L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
+    switch (nscales) { case 1: PV2_LOWRES(1); break; case 2: PV2_LOWRES(2); break; case 3: PV2_LOWRES(3); break; default: PV2_LOWRES(4); break; }
+#undef PV2_LOWRES
+    PV2_LAUNCH_CHECK("structure_loss_lowres_fwd");
+    return 0;
+}
+
+extern "C" int pv2_structure_loss_lowres_bwd(const float* const* low_fg, const float* const* low_bg, const int* ih, const int* iw,
+                                             const float* rh, const float* rw, const float* mask_fg, const float* mask_bg,
+                                             const float* grad_loss, float* const* dlow_fg, float* const* dlow_bg,
+                                             int nscales, int planes, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+    PtrPack pp = {};
+    LowresGeo geo = {};
+    if (int e = check_lowres(low_fg, low_bg, ih, iw, rh, rw, mask_fg, mask_bg, nscales, planes, H, W, workspace, workspace_bytes, pp, geo)) return e;
+    PV2_CHECK(grad_loss && dlow_fg && dlow_bg, "structure_loss_lowres_bwd: null pointer");
+    int max_px = 0;
+    for (int k = 0; k < nscales; ++k) {
+        PV2_CHECK(dlow_fg[k] && dlow_bg[k], "structure_loss_lowres_bwd: null gradient pointer at scale %d", k);
+        pp.dpred[k] = dlow_fg[k]; pp.dpred_bg[k] = dlow_bg[k];
+        if (ih[k] * iw[k] > max_px) max_px = ih[k] * iw[k];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout L = make_layout(workspace, planes, H, W);
+    float* gpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + L.bytes);
+    const dim3 grid(L.ft_tiles, planes), fold_grid((max_px + 255) / 256, planes, 2 * nscales);
+#define PV2_LOWRES_BWD(NSV)                                                                                                              \
+    pv2::launch(structure_loss_lowres_bwd_kernel<NSV>, grid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, grad_loss, L.plane_sums, gpart, \
+                H, W, planes, L.ft_tiles_x, L.ft_tiles);                                                                                \
+    PV2_LAUNCH_CHECK("structure_loss_lowres_bwd");                                                                                      \
+    pv2::launch(lowres_grad_fold_kernel<NSV>, fold_grid, 256, 0, st, pp, geo, gpart, H, W, L.ft_tiles_x, L.ft_tiles);                   \
+    PV2_LAUNCH_CHECK("lowres_grad_fold")
+    switch (nscales) { case 1: PV2_LOWRES_BWD(1); break; case 2: PV2_LOWRES_BWD(2); break; case 3: PV2_LOWRES_BWD(3); break; default: PV2_LOWRES_BWD(4); break; }
+#undef PV2_LOWRES_BWD
     return 0;
 }

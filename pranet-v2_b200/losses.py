@@ -5,4 +5,4 @@ loss is the block at EMCAD/trainer.py:123-140 (== MERIT/train_ACDC.py:259-284 ==
 """
 from __future__ import annotations
 
-from .ops import mc_dual_loss, structure_loss, structure_loss_multi  # noqa: F401
+from .ops import mc_dual_loss, structure_loss, structure_loss_lowres, structure_loss_multi  # noqa: F401

@@ -108,6 +108,89 @@ def structure_loss(pred, pred_bg, mask_fg, mask_bg=None):
     return structure_loss_multi([(pred, pred_bg)], mask_fg, mask_bg)[0]
 
 
+class _StructureLossLowresFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mask_fg, mask_bg, geo, *maps):
+        lib = _lib.load()
+        K = len(maps) // 2
+        fgs = [t.contiguous().float() for t in maps[:K]]
+        bgs = [t.contiguous().float() for t in maps[K:]]
+        hs, ws_, rhs, rws, (H, W) = geo
+        B, Cc = fgs[0].shape[:2]
+        mask_fg = mask_fg.contiguous().float()
+        mask_bg = mask_bg.contiguous().float() if mask_bg is not None else None
+        planes = B * Cc
+        ws_bytes = lib.pv2_structure_loss_lowres_workspace_bytes(planes, H, W, K)
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=mask_fg.device)
+        loss = torch.empty(K, dtype=torch.float32, device=mask_fg.device)
+        ctx.save_for_backward(mask_fg, mask_bg, ws, *fgs, *bgs)
+        ctx.meta = (K, planes, H, W, ws_bytes, hs, ws_, rhs, rws)
+        pf, k1 = _lib.ptr_array(fgs)
+        pb, k2 = _lib.ptr_array(bgs)
+        ph, k3 = _lib.int_array(hs)
+        pw, k4 = _lib.int_array(ws_)
+        prh, k5 = _lib.float_array(rhs)
+        prw, k6 = _lib.float_array(rws)
+        _lib.check(lib.pv2_structure_loss_lowres_fwd(pf, pb, ph, pw, prh, prw, mask_fg.data_ptr(),
+                                                     mask_bg.data_ptr() if mask_bg is not None else None, K, planes, H, W,
+                                                     loss.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "pv2_structure_loss_lowres_fwd")
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        lib = _lib.load()
+        K, planes, H, W, ws_bytes, hs, ws_, rhs, rws = ctx.meta
+        mask_fg, mask_bg, ws = ctx.saved_tensors[:3]
+        fgs, bgs = list(ctx.saved_tensors[3:3 + K]), list(ctx.saved_tensors[3 + K:3 + 2 * K])
+        g = grad_loss.contiguous().float()
+        dfg = [torch.empty_like(t) for t in fgs]
+        dbg = [torch.empty_like(t) for t in bgs]
+        pf, k1 = _lib.ptr_array(fgs)
+        pb, k2 = _lib.ptr_array(bgs)
+        df, k3 = _lib.ptr_array(dfg)
+        db, k4 = _lib.ptr_array(dbg)
+        ph, k5 = _lib.int_array(hs)
+        pw, k6 = _lib.int_array(ws_)
+        prh, k7 = _lib.float_array(rhs)
+        prw, k8 = _lib.float_array(rws)
+        _lib.check(lib.pv2_structure_loss_lowres_bwd(pf, pb, ph, pw, prh, prw, mask_fg.data_ptr(),
+                                                     mask_bg.data_ptr() if mask_bg is not None else None, g.data_ptr(), df, db,
+                                                     K, planes, H, W, ws.data_ptr(), ws_bytes, _stream()), "pv2_structure_loss_lowres_bwd")
+        return (None, None, None, *dfg, *dbg)
+
+
+def lowres_loss_supported(maps, scale_factors, mask_fg) -> bool:
+    """True when pv2_structure_loss_lowres_* covers this geometry (fp32 masks with W % 4 == 0, every final upsample >= x4)."""
+    W = mask_fg.shape[-1]
+    return W % 4 == 0 and all(s >= 4 for s in scale_factors) and mask_fg.data_ptr() % 16 == 0
+
+
+def structure_loss_lowres(pairs, scale_factors, mask_fg, mask_bg=None):
+    """The final upsamples of PraNet_V2.forward (pranet.py:349-350,370-371,392-393,414-415) and the structure_loss calls of
+    MyTrain_med.py:78-82 in one pass, from the LOW-RES maps `model.forward_features_lowres` returns.
+
+    pairs: [(low_fg_k, low_bg_k), ...] (1..4), each (B, C, h_k, w_k); scale_factors: the scale_factor of each pair's final
+    F.interpolate (`model.final_scale_factors()`); mask_fg (B, C, H, W) with H = floor(h_k * s_k).  Returns the tensor of
+    len(pairs) losses; equal to structure_loss_multi on the upsampled maps up to fp32 summation order, without the eight
+    full-resolution maps or their gradients ever being written.  Geometries the fused kernels do not cover
+    (`lowres_loss_supported`) go through interpolate_bilinear + structure_loss_multi -- the same pv2 kernels the module path uses."""
+    fgs, bgs = [p for p, _ in pairs], [q for _, q in pairs]
+    _need_cuda(mask_fg, mask_bg, *fgs, *bgs)
+    if not 1 <= len(pairs) <= 4 or len(scale_factors) != len(pairs):
+        raise ValueError("structure_loss_lowres takes 1..4 (low_fg, low_bg) pairs and one scale factor per pair")
+    for a, b in pairs:
+        if a.shape != b.shape or a.shape[:2] != mask_fg.shape[:2]:
+            raise ValueError("structure_loss_lowres: foreground / background maps must pair up and share (B, C) with the mask")
+    hs, ws, rhs, rws, size = _tail_geometry(fgs, scale_factors)
+    if tuple(mask_fg.shape[-2:]) != size:
+        raise ValueError(f"structure_loss_lowres: maps upsample to {size}, mask is {tuple(mask_fg.shape[-2:])}")
+    if not lowres_loss_supported(fgs, scale_factors, mask_fg):
+        up = [(interpolate_bilinear(a.float(), scale_factor=s), interpolate_bilinear(b.float(), scale_factor=s))
+              for (a, b), s in zip(pairs, scale_factors)]
+        return structure_loss_multi(up, mask_fg, mask_bg)
+    return _StructureLossLowresFn.apply(mask_fg, mask_bg, (hs, ws, rhs, rws, size), *fgs, *bgs)
+
+
 # ------------------------------------------------------------------------------------------------
 # bilinear resize
 # ------------------------------------------------------------------------------------------------

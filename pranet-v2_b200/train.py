@@ -13,12 +13,15 @@ Execution model (B200-first, no tracing compiler):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib, ops
 
+LOSS_FROM_LOWRES_DEFAULT = "0"    # TrainStep(loss_from_lowres=None): "1" = final upsamples fused into the loss kernels (§8 f2)
 _UNUSED_PREFIXES = ("conv.", "backbone.fc.", "resnet.fc.")   # defined by the reference nets but never used in forward
 
 
@@ -121,9 +124,15 @@ class FlatParams:
 class TrainStep:
     def __init__(self, model: nn.Module, lr: float = 1e-4, clip: float = 0.5, autocast_backbone: bool = True,
                  device=None, channels_last: bool = True, use_graph: bool = True, optimizer: str = "pv2",
-                 weight_decay: float = 0.0, decoupled: bool = False):
+                 weight_decay: float = 0.0, decoupled: bool = False, loss_from_lowres: bool = None):
+        """loss_from_lowres: stop the head at the low-res maps and let ops.structure_loss_lowres do the final
+        upsamples inside the loss kernels (same losses and gradients up to fp32 summation order; the eight full-resolution maps
+        and their gradients are never written).  False = the reference's data flow: model(images) -> 8 maps -> structure_loss."""
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.model = model.to(self.device).train()
+        if loss_from_lowres is None:                                  # PV2_LOSS_LOWRES=0|1 overrides the default (A/B measurements)
+            loss_from_lowres = os.environ.get("PV2_LOSS_LOWRES", LOSS_FROM_LOWRES_DEFAULT) == "1"
+        self.loss_from_lowres = bool(loss_from_lowres) and hasattr(self.model, "forward_features_lowres")
         if channels_last:
             # the stock backbone only: the head's conv weights stay dense OIHW, which is what pv2_weight_pack reads
             bb = getattr(self.model, "backbone", None) or getattr(self.model, "resnet", None)
@@ -158,9 +167,12 @@ class TrainStep:
         for p in self.params:
             p.grad = None
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
-            outs = self.model(images)
+            outs = self.model.forward_features_lowres(images) if self.loss_from_lowres else self.model(images)
         pairs = [(outs[i].float(), outs[i + 4].float()) for i in range(4)]
-        loss = ops.structure_loss_multi(pairs, gts).sum()            # MyTrain_med.py:78-82
+        if self.loss_from_lowres:
+            loss = ops.structure_loss_lowres(pairs, self.model.final_scale_factors(), gts).sum()
+        else:
+            loss = ops.structure_loss_multi(pairs, gts).sum()        # MyTrain_med.py:78-82
         loss.backward()
         self.bucket.gather([p.grad for p in self.params])
         return loss.detach()

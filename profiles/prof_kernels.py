@@ -40,6 +40,14 @@ elif what == "tail":   # fused inference tails from the low-res maps
     fg = [torch.randn(B, 9, 224 // s, 224 // s, device=dev) for s in (32, 16, 8, 4)]
     bg = [torch.randn(B, 9, 224 // s, 224 // s, device=dev) for s in (32, 16, 8, 4)]
     P.ops.infer_tail_argmax(fg, bg, [32, 16, 8, 4])
+elif what == "lowres":  # loss from the low-res maps: fused fwd, fused bwd, fold -- and the 8-map bilinear bwd it replaces
+    m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
+    for it in range(2):
+        pairs = [(torch.randn(B, 1, S // s, S // s, device=dev).requires_grad_(True), torch.randn(B, 1, S // s, S // s, device=dev).requires_grad_(True))
+                 for s in (8, 16, 32, 8)]
+        P.structure_loss_lowres(pairs, [8, 16, 32, 8], m).sum().backward()
+        ups = [(P.interpolate_bilinear(a, scale_factor=s), P.interpolate_bilinear(b, scale_factor=s)) for (a, b), s in zip(pairs, (8, 16, 32, 8))]
+        P.structure_loss_multi(ups, m).sum().backward()
 elif what == "loss":
     m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
     for it in range(2):

@@ -250,3 +250,102 @@ def test_structure_loss_fused_equals_two_pass(shape, monkeypatch):
     assert abs(res[0][0] - rl.item()) <= 1e-4 * abs(rl.item())
     assert (res[0][1] - ref_p.grad).abs().max() <= 1e-3 * ref_p.grad.abs().max()
     assert (res[0][2] - ref_q.grad).abs().max() <= 1e-3 * ref_q.grad.abs().max()
+
+
+# ------------------------------------------------------------------------------------------------
+# loss from the low-resolution maps
+# ------------------------------------------------------------------------------------------------
+def _lowres_case(B, Cc, H, W, scales, seed, soft=False):
+    maps = []
+    for k, s in enumerate(scales):
+        shape = (B, Cc, H // s, W // s)
+        maps.append((synth.logits(shape, seed, f"lf{k}"), synth.logits(shape, seed, f"lb{k}")))
+    m = (synth.soft_masks(B * Cc, H, W, seed) if soft else synth.ellipse_masks(B * Cc, H, W, seed)).view(B, Cc, H, W)
+    return maps, m
+
+
+def _oracle_lowres(maps, scales, m, mb, wts):
+    """pranet.py:349-415 final upsamples + MyTrain_med.py:78-82 losses on CPU: F.interpolate -> oracle structure_loss."""
+    leaves = [(a.clone().requires_grad_(True), b.clone().requires_grad_(True)) for a, b in maps]
+    losses = torch.stack([O.structure_loss(O.interp(a, scale=s), O.interp(b, scale=s), m, mb) for (a, b), s in zip(leaves, scales)])
+    (losses * wts).sum().backward()
+    return losses.detach(), leaves
+
+
+@pytest.mark.parametrize("B,Cc,H,W,scales,soft,pass_bg", [
+    (2, 1, 352, 352, (8, 16, 32, 8), False, False),       # PraNet-V2 geometry (pranet.py:349-350,370-371,392-393,414-415)
+    (2, 1, 256, 256, (8, 16, 32, 8), True, False),        # multi-scale rate 0.75: soft masks (MyTrain_med.py:70-73)
+    (1, 3, 224, 224, (4, 8, 16, 32), False, True),        # EMCAD scales (networks.py:116-123), explicit mask_bg
+    (2, 2, 96, 132, (4, 12), True, True),                 # ragged: W % 128 != 0, partial tiles, 2 scales
+    (1, 1, 64, 64, (16,), False, False),                  # one scale, one tile row pair
+])
+def test_structure_loss_lowres_vs_oracle(B, Cc, H, W, scales, soft, pass_bg):
+    maps, m = _lowres_case(B, Cc, H, W, scales, 21, soft)
+    mb = 1 - m
+    wts = torch.tensor([1.0, 0.5, 2.0, 1.5][:len(scales)])
+    ref_losses, leaves = _oracle_lowres(maps, scales, m, mb, wts)
+    dev = [(a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)) for a, b in maps]
+    n0 = P._lib.launch_count()
+    losses = P.structure_loss_lowres(dev, list(scales), m.to(DEV), mb.to(DEV) if pass_bg else None)
+    (losses * wts.to(DEV)).sum().backward()
+    assert P._lib.launch_count() - n0 == 3                 # fused forward, fused backward, fold: no bilinear / full-res launches
+    assert (losses.cpu() - ref_losses).abs().max().item() <= 1e-4 * ref_losses.abs().max().item()
+    for (a, b), (ra, rb) in zip(dev, leaves):
+        for got, want in ((a.grad, ra.grad), (b.grad, rb.grad)):
+            assert torch.isfinite(got).all()
+            assert (got.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item() + 1e-12
+
+
+def test_structure_loss_lowres_equals_unfused_full_size():
+    """B = 16 x 352^2, four scales: the fused path against the module path's own kernels (bilinear x8 -> structure_loss x4 ->
+    bilinear backward) -- same taps, same weight map, so agreement is at fp32 summation-order level; and it is deterministic."""
+    scales = (8, 16, 32, 8)
+    maps, m = _lowres_case(16, 1, 352, 352, scales, 4)
+    md = m.to(DEV)
+    wts = torch.tensor([1.0, 1.0, 1.0, 1.0], device=DEV)
+    res = []
+    for fused in (True, False, True):
+        dev = [(a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)) for a, b in maps]
+        if fused:
+            losses = P.structure_loss_lowres(dev, list(scales), md)
+        else:
+            up = [(P.interpolate_bilinear(a, scale_factor=s), P.interpolate_bilinear(b, scale_factor=s)) for (a, b), s in zip(dev, scales)]
+            losses = P.structure_loss_multi(up, md)
+        (losses * wts).sum().backward()
+        res.append((losses.detach().cpu(), [t.grad.cpu() for pair in dev for t in pair]))
+    (lf, gf), (lu, gu), (lf2, gf2) = res
+    assert (lf - lu).abs().max().item() <= 2e-6 * lu.abs().max().item()
+    for a, b in zip(gf, gu):
+        assert (a - b).abs().max().item() <= 2e-5 * b.abs().max().item()
+    assert torch.equal(lf, lf2) and all(torch.equal(a, b) for a, b in zip(gf, gf2))      # no atomics: bit-reproducible
+
+
+def test_structure_loss_lowres_unsupported_geometry_takes_unfused_kernels():
+    """x2 upsampling is outside the fused kernels' coverage: the op routes through interpolate_bilinear + structure_loss_multi
+    (still pv2 kernels, more launches) and matches the oracle; CPU tensors raise like every other op."""
+    maps, m = _lowres_case(2, 1, 64, 64, (2,), 8)
+    ref_losses, leaves = _oracle_lowres(maps, (2,), m, 1 - m, torch.ones(1))
+    dev = [(a.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)) for a, b in maps]
+    n0 = P._lib.launch_count()
+    losses = P.structure_loss_lowres(dev, [2], m.to(DEV))
+    losses.sum().backward()
+    assert P._lib.launch_count() - n0 > 3
+    assert (losses.cpu() - ref_losses).abs().max().item() <= 1e-4 * ref_losses.abs().max().item()
+    assert (dev[0][0].grad.cpu() - leaves[0][0].grad).abs().max().item() <= 1e-3 * leaves[0][0].grad.abs().max().item()
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        P.structure_loss_lowres(maps, [2], m)
+    with pytest.raises(ValueError):
+        P.structure_loss_lowres(dev, [4], m.to(DEV))       # 32 * 4 != 64
+    # the C ABI itself refuses what it does not cover, loudly
+    lib = P._lib.load()
+    a, b = dev[0][0].detach(), dev[0][1].detach()
+    md = m.to(DEV)
+    ws_bytes = lib.pv2_structure_loss_lowres_workspace_bytes(2, 64, 64, 1)
+    ws = torch.empty(ws_bytes // 4, device=DEV)
+    loss = torch.empty(1, device=DEV)
+    pf, k1 = P._lib.ptr_array([a]); pb, k2 = P._lib.ptr_array([b])
+    ph, k3 = P._lib.int_array([32]); pw, k4 = P._lib.int_array([32])
+    pr, k5 = P._lib.float_array([0.5])
+    st = lib.pv2_structure_loss_lowres_fwd(pf, pb, ph, pw, pr, pr, md.data_ptr(), None, 1, 2, 64, 64, loss.data_ptr(), ws.data_ptr(), ws_bytes,
+                                           torch.cuda.current_stream().cuda_stream)
+    assert st != 0 and b"up-scaling by >= 4" in lib.pv2_last_error()
