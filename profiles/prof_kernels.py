@@ -40,14 +40,31 @@ elif what == "tail":   # fused inference tails from the low-res maps
     fg = [torch.randn(B, 9, 224 // s, 224 // s, device=dev) for s in (32, 16, 8, 4)]
     bg = [torch.randn(B, 9, 224 // s, 224 // s, device=dev) for s in (32, 16, 8, 4)]
     P.ops.infer_tail_argmax(fg, bg, [32, 16, 8, 4])
-elif what == "lowres":  # loss from the low-res maps: fused fwd, fused bwd, fold -- and the 8-map bilinear bwd it replaces
+elif what == "lowres":  # loss from the low-res maps next to the four launches it replaces; 7 pv2 launches per iteration:
+    # lowres fwd, lowres bwd, fold | bilinear x8 fwd, loss fwd, loss bwd, bilinear x8 bwd
+    import ctypes
+    from pranet_v2_b200.ops import PV2_F32, _ratio
+    lib = P._lib.load()
+    scs = (8, 16, 32, 8)
     m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
+    ihs = (ctypes.c_int * 8)(*[S // s for s in scs * 2])
+    rr = (ctypes.c_float * 8)(*[_ratio(S // s, S, False, float(s)) for s in scs * 2])
+    st = lambda: torch.cuda.current_stream().cuda_stream
     for it in range(2):
         pairs = [(torch.randn(B, 1, S // s, S // s, device=dev).requires_grad_(True), torch.randn(B, 1, S // s, S // s, device=dev).requires_grad_(True))
-                 for s in (8, 16, 32, 8)]
-        P.structure_loss_lowres(pairs, [8, 16, 32, 8], m).sum().backward()
-        ups = [(P.interpolate_bilinear(a, scale_factor=s), P.interpolate_bilinear(b, scale_factor=s)) for (a, b), s in zip(pairs, (8, 16, 32, 8))]
-        P.structure_loss_multi(ups, m).sum().backward()
+                 for s in scs]
+        P.structure_loss_lowres(pairs, list(scs), m).sum().backward()
+        lows = [a.detach() for a, _ in pairs] + [b.detach() for _, b in pairs]
+        his = [torch.empty(B, 1, S, S, device=dev) for _ in range(8)]
+        (pl, k1), (ph, k2) = P._lib.ptr_array(lows), P._lib.ptr_array(his)
+        P._lib.check(lib.pv2_bilinear_multi_fwd(pl, ph, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, st()), "bilinear_multi_fwd")
+        ups = [t.requires_grad_(True) for t in his]
+        P.structure_loss_multi([(ups[i], ups[i + 4]) for i in range(4)], m).sum().backward()
+        gs, dl = [t.grad for t in ups], [torch.empty_like(t) for t in lows]
+        (pg, k3), (pd, k4) = P._lib.ptr_array(gs), P._lib.ptr_array(dl)
+        P._lib.check(lib.pv2_bilinear_multi_bwd(pg, pd, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, st()), "bilinear_multi_bwd")
+        err = max((d - t.grad).abs().max().item() / t.grad.abs().max().item() for d, t in zip(dl, [a for a, _ in pairs] + [b for _, b in pairs]))
+        print("fused vs unfused low-res gradient, max rel err", err)
 elif what == "loss":
     m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
     for it in range(2):
