@@ -20,6 +20,10 @@ bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("PV2_PDL"); return !(e && e[0] == '0'); }();
     return on;
 }
+int tune_int(const char* name, int def) {
+    const char* e = getenv(name);
+    return (e && e[0]) ? atoi(e) : def;
+}
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace pv2
 

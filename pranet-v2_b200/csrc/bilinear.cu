@@ -17,7 +17,8 @@ namespace pv2 {
 namespace {
 
 constexpr int FWD_THREADS = 256;
-constexpr int BAND = 16;  // output rows per CTA (fwd)
+constexpr int BAND = 16;      // output rows per CTA (fwd), default; PV2_BIL_BAND overrides (tuning knob)
+constexpr int MAX_BAND = 64;
 
 // up to PV2_MAX_MAPS maps of the same output size in ONE launch (grid.z = map): the 8 final logit maps of a step are
 // 8 x 8 MB at B=16 -- far too little per launch to fill HBM, so they share a launch.
@@ -30,7 +31,7 @@ struct MultiMaps {
 
 template <typename T>
 __global__ void __launch_bounds__(FWD_THREADS)
-bilinear_fwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac) {
+bilinear_fwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int band) {
     pv2::pdl_prologue();
     extern __shared__ float srows[];  // [nrows][iw]
     const int map = blockIdx.z;
@@ -39,7 +40,7 @@ bilinear_fwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
     const int ih = mm.ih[map], iw = mm.iw[map], max_src_rows = mm.max_rows[map];
     const float rh = mm.rh[map], rw = mm.rw[map];
     const int plane = blockIdx.y;
-    const int oy0 = blockIdx.x * BAND, oy1 = min(oy0 + BAND, oh);
+    const int oy0 = blockIdx.x * band, oy1 = min(oy0 + band, oh);
     const int r0 = bilinear_tap(oy0, ih, rh, ac).i0;
     const int r1 = bilinear_tap(oy1 - 1, ih, rh, ac).i1;
     const int nrows = r1 - r0 + 1;
@@ -123,14 +124,15 @@ __device__ __forceinline__ void touch_window(int i, int out_size, float ratio, b
 
 constexpr int BWD_THREADS = 384;   // upper bound; the launch uses ow4 * rgroups threads so that every thread owns a column quad
 constexpr int BWD_R = 4;             // input rows per CTA: neighbouring input rows share output rows, so (R+1)*s rows are read for R rows
-constexpr int BWD_BATCH = 8;         // output rows a thread fetches per round trip
+// output rows a thread fetches per round trip (BWD_BATCH) and CTAs per SM are template parameters of the kernel: variant 0 = (8, 2),
+// 1 = (4, 3), 2 = (2, 4); PV2_BIL_BWD_VARIANT selects (tuning knob)
 constexpr int BWD_MAX_WIN = 192;     // output rows a block of R input rows can touch: (R+1)*scale + a few (scale <= 32)
 
 // CTA = (block of BWD_R input rows, plane, map).  Pass 1: every output row the block touches is read ONCE (16-byte loads, a
 // thread owns 4 consecutive columns, the row window is split over `rgroups` thread groups) and folded into the R rows of column
 // sums with its tap weights; pass 2 folds the columns.  No atomics, deterministic.
-template <typename T>
-__global__ void __launch_bounds__(BWD_THREADS, 2)
+template <typename T, int BWD_BATCH, int MIN_CTAS>
+__global__ void __launch_bounds__(BWD_THREADS, MIN_CTAS)
 bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int rgroups) {
     pv2::pdl_prologue();
     extern __shared__ float colsum[];  // [BWD_R][rgroups][pitch]
@@ -260,10 +262,15 @@ int check(const void* a, const void* b, int planes, int ih, int iw, int oh, int 
 
 using namespace pv2;
 
-static int launch_fwd(const MultiMaps& mm, int nmaps, int planes, int oh, int ow, int align_corners, int dtype, size_t smem, cudaStream_t st) {
-    dim3 grid((oh + BAND - 1) / BAND, planes, nmaps);
-    if (dtype == PV2_F32) pv2::launch(bilinear_fwd_kernel<float>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners);
-    else pv2::launch(bilinear_fwd_kernel<__nv_bfloat16>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners);
+static int fwd_band() {
+    const int b = pv2::tune_int("PV2_BIL_BAND", BAND);
+    return b < 1 ? 1 : (b > MAX_BAND ? MAX_BAND : b);
+}
+
+static int launch_fwd(const MultiMaps& mm, int nmaps, int planes, int oh, int ow, int align_corners, int dtype, size_t smem, int band, cudaStream_t st) {
+    dim3 grid((oh + band - 1) / band, planes, nmaps);
+    if (dtype == PV2_F32) pv2::launch(bilinear_fwd_kernel<float>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners, band);
+    else pv2::launch(bilinear_fwd_kernel<__nv_bfloat16>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners, band);
     PV2_LAUNCH_CHECK("bilinear_fwd");
     return 0;
 }
@@ -285,15 +292,22 @@ static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int row_blocks
     const size_t smem = (size_t)BWD_R * rgroups * ow4 * 4 * sizeof(float);
     PV2_CHECK(smem <= 48 * 1024, "bilinear_bwd: output width %d too large", ow);
     dim3 grid(row_blocks, planes, nmaps);
-    if (dtype == PV2_F32) pv2::launch(bilinear_bwd_kernel<float>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups);
-    else pv2::launch(bilinear_bwd_kernel<__nv_bfloat16>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups);
+#define PV2_BWD(TT)                                                                                                                    \
+    switch (variant) {                                                                                                                 \
+        case 1: pv2::launch(bilinear_bwd_kernel<TT, 4, 3>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;        \
+        case 2: pv2::launch(bilinear_bwd_kernel<TT, 2, 4>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;        \
+        default: pv2::launch(bilinear_bwd_kernel<TT, 8, 2>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;       \
+    }
+    const int variant = pv2::tune_int("PV2_BIL_BWD_VARIANT", 0);
+    if (dtype == PV2_F32) { PV2_BWD(float) } else { PV2_BWD(__nv_bfloat16) }
+#undef PV2_BWD
     PV2_LAUNCH_CHECK("bilinear_bwd");
     return 0;
 }
 
 // rows of the source a BAND of output rows can touch, if they fit in 48 KB of shared memory (else 0: read through L1/L2)
-static int staged_rows(int ih, int iw, float rh) {
-    int want = (int)(BAND * (double)rh) + 4;
+static int staged_rows(int ih, int iw, float rh, int band) {
+    int want = (int)(band * (double)rh) + 4;
     if (want > ih) want = ih;
     const int cap = (48 * 1024) / (iw * 4);
     return want <= cap ? want : 0;
@@ -304,8 +318,9 @@ extern "C" int pv2_bilinear_fwd(const void* in, void* out, int planes, int ih, i
     if (int e = check(in, out, planes, ih, iw, oh, ow, dtype, "bilinear_fwd")) return e;
     MultiMaps mm = {};
     mm.in[0] = in; mm.out[0] = out; mm.ih[0] = ih; mm.iw[0] = iw; mm.rh[0] = rh; mm.rw[0] = rw;
-    mm.max_rows[0] = staged_rows(ih, iw, rh);
-    return launch_fwd(mm, 1, planes, oh, ow, align_corners, dtype, (size_t)mm.max_rows[0] * iw * 4, (cudaStream_t)stream);
+    const int band = fwd_band();
+    mm.max_rows[0] = staged_rows(ih, iw, rh, band);
+    return launch_fwd(mm, 1, planes, oh, ow, align_corners, dtype, (size_t)mm.max_rows[0] * iw * 4, band, (cudaStream_t)stream);
 }
 
 extern "C" int pv2_bilinear_bwd(const void* dout, void* din, int planes, int ih, int iw, int oh, int ow,
@@ -322,14 +337,15 @@ extern "C" int pv2_bilinear_multi_fwd(const void* const* in, void* const* out, c
     PV2_CHECK(in && out && ih && iw && rh && rw && nmaps >= 1 && nmaps <= PV2_MAX_MAPS, "bilinear_multi_fwd: 1..%d maps expected", PV2_MAX_MAPS);
     MultiMaps mm = {};
     size_t smem = 0;
+    const int band = fwd_band();
     for (int i = 0; i < nmaps; ++i) {
         if (int e = check(in[i], out[i], planes, ih[i], iw[i], oh, ow, dtype, "bilinear_multi_fwd")) return e;
         mm.in[i] = in[i]; mm.out[i] = out[i]; mm.ih[i] = ih[i]; mm.iw[i] = iw[i]; mm.rh[i] = rh[i]; mm.rw[i] = rw[i];
-        mm.max_rows[i] = staged_rows(ih[i], iw[i], rh[i]);
+        mm.max_rows[i] = staged_rows(ih[i], iw[i], rh[i], band);
         const size_t b = (size_t)mm.max_rows[i] * iw[i] * 4;
         if (b > smem) smem = b;
     }
-    return launch_fwd(mm, nmaps, planes, oh, ow, align_corners, dtype, smem, (cudaStream_t)stream);
+    return launch_fwd(mm, nmaps, planes, oh, ow, align_corners, dtype, smem, band, (cudaStream_t)stream);
 }
 
 extern "C" int pv2_bilinear_multi_bwd(const void* const* dout, void* const* din, const int* ih, const int* iw, const float* rh, const float* rw,

@@ -45,6 +45,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
 
 bool pdl_enabled();
+// integer tuning knob from the environment, read at every call (A/B measurements inside one process); `def` when unset
+int tune_int(const char* name, int def);
 
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
