@@ -135,8 +135,8 @@ template <typename T, int BWD_BATCH, int MIN_CTAS>
 __global__ void __launch_bounds__(BWD_THREADS, MIN_CTAS)
 bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int rgroups) {
     pv2::pdl_prologue();
-    extern __shared__ float colsum[];  // [BWD_R][rgroups][pitch]
-    __shared__ float wts[BWD_R][BWD_MAX_WIN];
+    extern __shared__ float colsum[];  // [BWD_R][rgroups][pitch] column sums, then [pitch] float2 x taps (i0 as bits, w1)
+    __shared__ float4 wts[BWD_MAX_WIN];   // y tap weights of a window row towards the CTA's (up to) 4 input rows: one 16-byte load per row
     const int map = blockIdx.z;
     // for the backward, `in` is the low-resolution gradient being produced and `out` the upstream gradient
     const T* __restrict__ dout = reinterpret_cast<const T*>(mm.out[map]);
@@ -156,10 +156,19 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
     const int nwin = hi - lo + 1;
     const int ow4 = (ow + 3) >> 2, pitch = ow4 * 4;
     const bool vec_ok = (ow & 3) == 0;
+    // x taps of every output column, computed once (pass 2 used to re-derive them for every (pixel, column) pair: as many
+    // instructions as pass 1)
+    float2* xtab = reinterpret_cast<float2*>(colsum + BWD_R * rgroups * pitch);
+    for (int ox = threadIdx.x; ox < pitch; ox += blockDim.x) {
+        const Tap t = bilinear_tap(min(ox, ow - 1), iw, rw, ac);
+        xtab[ox] = make_float2(__int_as_float(t.i0), t.w1);
+    }
     if (nwin <= BWD_MAX_WIN) {
-        for (int j = threadIdx.x; j < nwin * BWD_R; j += blockDim.x) {
-            const int r = j / nwin, jj = j - r * nwin;
-            wts[r][jj] = r < nr ? tap_weight(lo + jj, iy0 + r, ih, rh, ac) : 0.0f;
+        for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
+            float w[BWD_R];
+#pragma unroll
+            for (int r = 0; r < BWD_R; ++r) w[r] = r < nr ? tap_weight(lo + j, iy0 + r, ih, rh, ac) : 0.0f;
+            wts[j] = make_float4(w[0], w[1], w[2], w[3]);
         }
         __syncthreads();
         const int q = threadIdx.x % ow4, rg = threadIdx.x / ow4;
@@ -190,11 +199,12 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
                 for (int u = 0; u < BWD_BATCH; ++u) {
                     const int j = j0 + u * rgroups;
                     if (j < nwin) {
+                        const float4 w4 = wts[j];
+                        const float wy[BWD_R] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int r = 0; r < BWD_R; ++r) {
-                            const float wy = wts[r][j];
-                            acc[r][0] = fmaf(wy, v[u].x, acc[r][0]); acc[r][1] = fmaf(wy, v[u].y, acc[r][1]);
-                            acc[r][2] = fmaf(wy, v[u].z, acc[r][2]); acc[r][3] = fmaf(wy, v[u].w, acc[r][3]);
+                            acc[r][0] = fmaf(wy[r], v[u].x, acc[r][0]); acc[r][1] = fmaf(wy[r], v[u].y, acc[r][1]);
+                            acc[r][2] = fmaf(wy[r], v[u].z, acc[r][2]); acc[r][3] = fmaf(wy[r], v[u].w, acc[r][3]);
                         }
                     }
                 }
@@ -222,6 +232,16 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
         rgroups = 1;
     }
     __syncthreads();
+    if (rgroups > 1) {      // the row groups' partial column sums, folded once (same order as before: group 0, 1, ...)
+        for (int idx = threadIdx.x; idx < nr * pitch; idx += blockDim.x) {
+            const int r = idx / pitch, ox = idx - r * pitch;
+            float* b = colsum + r * rgroups * pitch + ox;
+            float cs = b[0];
+            for (int k = 1; k < rgroups; ++k) cs += b[k * pitch];
+            b[0] = cs;
+        }
+        __syncthreads();
+    }
     // pass 2: an input pixel is folded by a group of L lanes (L = the power of two that spreads the nr*iw pixels over the CTA:
     // 32 / 8 / 2 lanes at x32 / x16 / x8), each lane taking every L-th column of the window, then a fixed shuffle tree.  One
     // thread per pixel made this pass a 2s-long serial chain on 11..176 threads -- about half of the kernel's time.
@@ -239,9 +259,10 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
             touch_window(ix, ow, rw, ac, xl, xh);
             const float* base = colsum + r * rgroups * pitch;
             for (int ox = xl + sub; ox <= xh; ox += L) {
-                float cs = base[ox];
-                for (int k = 1; k < rgroups; ++k) cs += base[k * pitch + ox];
-                acc = fmaf(tap_weight(ox, ix, iw, rw, ac), cs, acc);
+                const float2 t = xtab[ox];
+                const int i0 = __float_as_int(t.x), i1 = min(i0 + 1, iw - 1);
+                const float w = (i0 == ix ? 1.0f - t.y : 0.0f) + (i1 == ix ? t.y : 0.0f);      // tap_weight(ox, ix) from the table
+                acc = fmaf(w, base[ox], acc);
             }
         }
         for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -262,9 +283,15 @@ int check(const void* a, const void* b, int planes, int ih, int iw, int oh, int 
 
 using namespace pv2;
 
-static int fwd_band() {
-    const int b = pv2::tune_int("PV2_BIL_BAND", BAND);
-    return b < 1 ? 1 : (b > MAX_BAND ? MAX_BAND : b);
+// Output rows per CTA: as tall as possible (a CTA's fixed cost -- staging, taps -- is amortised over its rows) while the launch still
+// has ~1000 CTAs (7 per SM).  Measured on 8 maps x 16 planes x 352^2: 22.7 / 17.9 / 16.1 / 15.1 / 18.2 us for bands of 8 / 16 / 32 / 44 / 64.
+static int fwd_band(int planes, int nmaps, int oh) {
+    const int env = pv2::tune_int("PV2_BIL_BAND", 0);
+    if (env > 0) return env > MAX_BAND ? MAX_BAND : env;
+    const long long pm = (long long)planes * nmaps;
+    const int bands = (int)((1024 + pm - 1) / pm);
+    int b = (oh + bands - 1) / bands;
+    return b < BAND ? BAND : (b > MAX_BAND ? MAX_BAND : b);
 }
 
 static int launch_fwd(const MultiMaps& mm, int nmaps, int planes, int oh, int ow, int align_corners, int dtype, size_t smem, int band, cudaStream_t st) {
@@ -289,16 +316,16 @@ static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int row_blocks
     if (rgroups > 8) rgroups = 8;
     int threads = (ow4 * rgroups + 31) / 32 * 32;       // every thread owns a (column quad, row group): no idle lanes beyond the last warp
     if (threads < 64) threads = 64;
-    const size_t smem = (size_t)BWD_R * rgroups * ow4 * 4 * sizeof(float);
+    const size_t smem = (size_t)BWD_R * rgroups * ow4 * 4 * sizeof(float) + (size_t)ow4 * 4 * sizeof(float2);
     PV2_CHECK(smem <= 48 * 1024, "bilinear_bwd: output width %d too large", ow);
     dim3 grid(row_blocks, planes, nmaps);
 #define PV2_BWD(TT)                                                                                                                    \
     switch (variant) {                                                                                                                 \
-        case 1: pv2::launch(bilinear_bwd_kernel<TT, 4, 3>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;        \
+        case 0: pv2::launch(bilinear_bwd_kernel<TT, 8, 2>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;        \
         case 2: pv2::launch(bilinear_bwd_kernel<TT, 2, 4>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;        \
-        default: pv2::launch(bilinear_bwd_kernel<TT, 8, 2>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;       \
+        default: pv2::launch(bilinear_bwd_kernel<TT, 4, 3>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;       \
     }
-    const int variant = pv2::tune_int("PV2_BIL_BWD_VARIANT", 0);
+    const int variant = pv2::tune_int("PV2_BIL_BWD_VARIANT", 1);      // measured at 8 maps x 16 x 352^2: 36.6 / 32.0 / 33.2 us
     if (dtype == PV2_F32) { PV2_BWD(float) } else { PV2_BWD(__nv_bfloat16) }
 #undef PV2_BWD
     PV2_LAUNCH_CHECK("bilinear_bwd");
@@ -318,7 +345,7 @@ extern "C" int pv2_bilinear_fwd(const void* in, void* out, int planes, int ih, i
     if (int e = check(in, out, planes, ih, iw, oh, ow, dtype, "bilinear_fwd")) return e;
     MultiMaps mm = {};
     mm.in[0] = in; mm.out[0] = out; mm.ih[0] = ih; mm.iw[0] = iw; mm.rh[0] = rh; mm.rw[0] = rw;
-    const int band = fwd_band();
+    const int band = fwd_band(planes, 1, oh);
     mm.max_rows[0] = staged_rows(ih, iw, rh, band);
     return launch_fwd(mm, 1, planes, oh, ow, align_corners, dtype, (size_t)mm.max_rows[0] * iw * 4, band, (cudaStream_t)stream);
 }
@@ -337,7 +364,7 @@ extern "C" int pv2_bilinear_multi_fwd(const void* const* in, void* const* out, c
     PV2_CHECK(in && out && ih && iw && rh && rw && nmaps >= 1 && nmaps <= PV2_MAX_MAPS, "bilinear_multi_fwd: 1..%d maps expected", PV2_MAX_MAPS);
     MultiMaps mm = {};
     size_t smem = 0;
-    const int band = fwd_band();
+    const int band = fwd_band(planes, nmaps, oh);
     for (int i = 0; i < nmaps; ++i) {
         if (int e = check(in[i], out[i], planes, ih[i], iw[i], oh, ow, dtype, "bilinear_multi_fwd")) return e;
         mm.in[i] = in[i]; mm.out[i] = out[i]; mm.ih[i] = ih[i]; mm.iw[i] = iw[i]; mm.rh[i] = rh[i]; mm.rw[i] = rw[i];

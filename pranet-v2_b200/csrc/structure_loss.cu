@@ -380,11 +380,13 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const __grid_constant__ LowresGeo ge
     const int HW = H * W;
     const size_t pbase = (size_t)plane * HW;
     const float* mp = mask_fg + pbase;
-    if constexpr (!LOWRES) {
-        // The grid is a single wave whose CTAs march through the same phases together: without this, HBM idles while every CTA
-        // builds its table and the SMs idle while every CTA waits for its logits.  Ask L2 for the tile's logit rows now (one
-        // prefetch per 128-byte line), so they arrive while the summed-area table is being built.
-        if (prefetch) {
+    // Experiment kept behind PV2_LOSS_PREFETCH=1|2: ask L2 for the tile's logit rows up front (one prefetch per 128-byte line) so
+    // they arrive while the summed-area table is built.  The grid is a single wave whose CTAs march through the same phases
+    // together, so this looked like free overlap; measured, mode 1 (first thing in the kernel) costs 3 us (38.5 -> 41.6 us at
+    // 16 x 352^2 x 4 scales): the mask halo loads the table build waits for queue behind 64 MB of prefetches.  Mode 2 issues them
+    // after the mask loads.
+    auto prefetch_logits = [&]() {
+        if constexpr (!LOWRES) {
             constexpr int LPR = FT_W * (int)sizeof(T) / 128;            // 128-byte lines per tile row
 #pragma unroll
             for (int k = 0; k < NS; ++k) {
@@ -400,7 +402,8 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const __grid_constant__ LowresGeo ge
                 }
             }
         }
-    }
+    };
+    if (prefetch == 1) prefetch_logits();
     if constexpr (LOWRES) fill_tap_tables<NS>(xt, yt, geo, y0, x0, H, W, tid);      // visible after the first __syncthreads below
     // ---- stage + row prefix: warp = table row, lane = 5 consecutive columns ----
     if (tid < FS_PITCH) sat[tid] = 0.0f;                       // row 0
@@ -420,6 +423,7 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const __grid_constant__ LowresGeo ge
             v[i][j] = (row_ok && c < FS_W && gx >= 0 && gx < W) ? __ldg(src + gx) : 0.0f;
         }
     }
+    if (prefetch == 2) prefetch_logits();
 #pragma unroll
     for (int i = 0; i < ROWS_PW; ++i) {
         const int r = 1 + warp + i * (LS_THREADS / 32);
@@ -917,7 +921,7 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
         PV2_CHECK(ce == cudaSuccess, "structure_loss_fwd: memset: %s", cudaGetErrorString(ce));
         const dim3 fgrid(L.ft_tiles, planes);
         const LowresGeo geo = {};
-        const int prefetch = pv2::tune_int("PV2_LOSS_PREFETCH", 1);
+        const int prefetch = pv2::tune_int("PV2_LOSS_PREFETCH", 0);      // 0 off (default), 1 / 2: see the kernel
 #define PV2_FUSED(TT, NSV) pv2::launch(structure_loss_fwd_fused_kernel<TT, NSV, false>, fgrid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, H, W, planes, \
                                        L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket, prefetch)
         if (logit_dtype == PV2_F32) {

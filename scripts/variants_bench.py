@@ -57,7 +57,7 @@ def sl_fwd():
 
 
 ref = None
-for v in ("0", "1", "0", "1"):
+for v in ("0", "1", "2", "0", "2"):
     os.environ["PV2_LOSS_PREFETCH"] = v
     report("structure_loss fwd x4 (fused)", "PV2_LOSS_PREFETCH", v, px * (4 + 32), BH.timed_graph(sl_fwd))
     cnt[0] = 0
@@ -92,7 +92,7 @@ def mb():
 
 
 ref = None
-for band in (16, 8, 22, 32, 44, 64, 16):
+for band in (16, 0, 32, 44, 0):        # 0 = the library's own choice
     os.environ["PV2_BIL_BAND"] = str(band)
     report("bilinear fwd, 8 final maps", "PV2_BIL_BAND", band, (8 * px + lowpx) * 4, BH.timed_graph(mf))
     cnt[0] = 0
@@ -101,7 +101,7 @@ for band in (16, 8, 22, 32, 44, 64, 16):
     got = torch.stack([t.sum() for t in his[1]])
     ref = got if ref is None else ref
     assert torch.equal(ref, got), "band changed the result"
-os.environ.pop("PV2_BIL_BAND")
+os.environ.pop("PV2_BIL_BAND", None)
 his = [[torch.randn(B, 1, S, S, device=dev) for _ in scs] for _ in range(nset)]
 pk = [(P._lib.ptr_array(lows[j]), P._lib.ptr_array(his[j])) for j in range(nset)]
 ref = None
