@@ -27,6 +27,7 @@ struct MultiMaps {
     void* out[PV2_MAX_MAPS];
     int ih[PV2_MAX_MAPS], iw[PV2_MAX_MAPS], max_rows[PV2_MAX_MAPS];
     float rh[PV2_MAX_MAPS], rw[PV2_MAX_MAPS];
+    float irh[PV2_MAX_MAPS], irw[PV2_MAX_MAPS];     // 1 / ratio (backward only; 0 when the ratio is 0)
 };
 
 template <typename T>
@@ -122,98 +123,109 @@ __device__ __forceinline__ void touch_window(int i, int out_size, float ratio, b
     if (i == 0) lo = 0;  // clamped sources (src < 0) all land on index 0
 }
 
+// input rows per CTA by scale: x8 and below -> 4, x16 -> 2, x32 and beyond -> 1 (same rule on the host for the grid)
+__host__ __device__ inline int bwd_rows_per_cta(int ih, int oh) {
+    const int scale = (oh + ih - 1) / ih;
+    return scale <= 8 ? 4 : (scale <= 16 ? 2 : 1);
+}
+
 constexpr int BWD_THREADS = 384;   // upper bound; the launch uses ow4 * rgroups threads so that every thread owns a column quad
 constexpr int BWD_R = 4;             // input rows per CTA: neighbouring input rows share output rows, so (R+1)*s rows are read for R rows
 // output rows a thread fetches per round trip (BWD_BATCH) and CTAs per SM are template parameters of the kernel: variant 0 = (8, 2),
 // 1 = (4, 3), 2 = (2, 4); PV2_BIL_BWD_VARIANT selects (tuning knob)
 constexpr int BWD_MAX_WIN = 192;     // output rows a block of R input rows can touch: (R+1)*scale + a few (scale <= 32)
 
-// CTA = (block of BWD_R input rows, plane, map).  Pass 1: every output row the block touches is read ONCE (16-byte loads, a
-// thread owns 4 consecutive columns, the row window is split over `rgroups` thread groups) and folded into the R rows of column
-// sums with its tap weights; pass 2 folds the columns.  No atomics, deterministic.
-template <typename T, int BWD_BATCH, int MIN_CTAS>
-__global__ void __launch_bounds__(BWD_THREADS, MIN_CTAS)
-bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int rgroups) {
-    pv2::pdl_prologue();
-    extern __shared__ float colsum[];  // [BWD_R][rgroups][pitch] column sums, then [pitch] float2 x taps (i0 as bits, w1)
-    __shared__ float4 wts[BWD_MAX_WIN];   // y tap weights of a window row towards the CTA's (up to) 4 input rows: one 16-byte load per row
-    const int map = blockIdx.z;
-    // for the backward, `in` is the low-resolution gradient being produced and `out` the upstream gradient
-    const T* __restrict__ dout = reinterpret_cast<const T*>(mm.out[map]);
-    T* __restrict__ din = reinterpret_cast<T*>(const_cast<void*>(mm.in[map]));
+// touch_window with the reciprocal ratio precomputed on the host (a float division costs ~10 instructions; the +-1 margins absorb
+// the last-bit difference)
+__device__ __forceinline__ void touch_window_r(int i, int out_size, float ratio, float inv, bool ac, int& lo, int& hi) {
+    if (!(ratio > 0.0f)) { lo = 0; hi = out_size - 1; return; }
+    float a, b;
+    if (ac) { a = ((float)i - 1.0f) * inv; b = ((float)i + 1.0f) * inv; }
+    else { a = ((float)i - 0.5f) * inv - 0.5f; b = ((float)i + 1.5f) * inv - 0.5f; }
+    lo = max(0, (int)floorf(a) - 1);
+    hi = min(out_size - 1, (int)ceilf(b) + 1);
+    if (i == 0) lo = 0;
+}
+
+// CTA = (block of R input rows, plane, map); R = 4 / 2 / 1 at x8 / x16 / x32 so that every CTA reads a similar number of rows.
+// Pass 1: every output row the block touches is read ONCE (16-byte loads, a thread owns 4 consecutive columns, the row window is
+// split over `rgroups` thread groups) and folded into the R rows of column sums with its y tap weights (one 16-byte shared-memory
+// load per row); the row groups are then folded; pass 2 folds the columns with x taps from a table.  No atomics, deterministic.
+// The kernel was issue bound (22 M warp instructions for 63 MB, 67 % issue slots busy): R is a template parameter (no multiplies by
+// zero weights), the row loops carry no per-element predicates, taps and windows are computed once.
+template <typename T, int R, int BATCH>
+__device__ __forceinline__ void bilinear_bwd_body(const MultiMaps& mm, int map, int oh, int ow, bool ac, int rgroups, float* colsum, float4* wts) {
+    const T* __restrict__ dout = reinterpret_cast<const T*>(mm.out[map]);      // for the backward, `out` is the upstream gradient
+    T* __restrict__ din = reinterpret_cast<T*>(const_cast<void*>(mm.in[map]));  // and `in` the low-resolution gradient being produced
     const int ih = mm.ih[map], iw = mm.iw[map];
     const float rh = mm.rh[map], rw = mm.rw[map];
-    // rows per CTA by scale, so that every CTA reads a similar number of output rows: x8 -> 4, x16 -> 2, x32 and beyond -> 1
-    const int scale = (oh + ih - 1) / ih;
-    const int R = scale <= 8 ? BWD_R : (scale <= 16 ? 2 : 1);
     const int plane = blockIdx.y, iy0 = blockIdx.x * R;
     if (iy0 >= ih) return;
     const int nr = min(R, ih - iy0);
     const T* g = dout + (size_t)plane * oh * ow;
     int lo, hi, lo2, hi2;
-    touch_window(iy0, oh, rh, ac, lo, hi2);
-    touch_window(iy0 + nr - 1, oh, rh, ac, lo2, hi);
+    touch_window_r(iy0, oh, rh, mm.irh[map], ac, lo, hi2);
+    touch_window_r(iy0 + nr - 1, oh, rh, mm.irh[map], ac, lo2, hi);
     const int nwin = hi - lo + 1;
     const int ow4 = (ow + 3) >> 2, pitch = ow4 * 4;
     const bool vec_ok = (ow & 3) == 0;
-    // x taps of every output column, computed once (pass 2 used to re-derive them for every (pixel, column) pair: as many
-    // instructions as pass 1)
-    float2* xtab = reinterpret_cast<float2*>(colsum + BWD_R * rgroups * pitch);
+    float2* xtab = reinterpret_cast<float2*>(colsum + BWD_R * rgroups * pitch);    // x taps of every output column: (i0 as bits, w1)
     for (int ox = threadIdx.x; ox < pitch; ox += blockDim.x) {
         const Tap t = bilinear_tap(min(ox, ow - 1), iw, rw, ac);
         xtab[ox] = make_float2(__int_as_float(t.i0), t.w1);
     }
     if (nwin <= BWD_MAX_WIN) {
-        for (int j = threadIdx.x; j < nwin; j += blockDim.x) {
-            float w[BWD_R];
+        for (int j = threadIdx.x; j < nwin; j += blockDim.x) {                    // y tap weights of window row j towards the R input rows
+            const Tap t = bilinear_tap(lo + j, ih, rh, ac);
+            float w[4];
 #pragma unroll
-            for (int r = 0; r < BWD_R; ++r) w[r] = r < nr ? tap_weight(lo + j, iy0 + r, ih, rh, ac) : 0.0f;
+            for (int r = 0; r < 4; ++r) {
+                const int i = iy0 + r;
+                w[r] = r < nr ? (t.i0 == i ? t.w0 : 0.0f) + (t.i1 == i ? t.w1 : 0.0f) : 0.0f;
+            }
             wts[j] = make_float4(w[0], w[1], w[2], w[3]);
         }
         __syncthreads();
         const int q = threadIdx.x % ow4, rg = threadIdx.x / ow4;
         if (rg < rgroups) {
-            float acc[BWD_R][4];
+            float acc[R][4];
 #pragma unroll
-            for (int r = 0; r < BWD_R; ++r) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; acc[r][3] = 0.0f; }
+            for (int r = 0; r < R; ++r) { acc[r][0] = 0.0f; acc[r][1] = 0.0f; acc[r][2] = 0.0f; acc[r][3] = 0.0f; }
             const int ox = q * 4;
-            // batches of BWD_BATCH rows: every load of a batch is issued before the first FMA (the kernel was latency bound:
-            // 6.8 long-scoreboard stalls per issue, 37 % issue slots)
-            for (int j0 = rg; j0 < nwin; j0 += BWD_BATCH * rgroups) {
-                float4 v[BWD_BATCH];
+            auto ldrow = [&](const T* p) -> float4 {
+                if (vec_ok) return load4<T>(p);
+                float4 v;
+                v.x = ox < ow ? to_f(p[0]) : 0.0f;     v.y = ox + 1 < ow ? to_f(p[1]) : 0.0f;
+                v.z = ox + 2 < ow ? to_f(p[2]) : 0.0f; v.w = ox + 3 < ow ? to_f(p[3]) : 0.0f;
+                return v;
+            };
+            auto fold = [&](const float4& v, const float4& w4) {
+                const float wy[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                for (int u = 0; u < BWD_BATCH; ++u) {
-                    const int j = j0 + u * rgroups;
-                    v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (j < nwin) {
-                        if (vec_ok) {
-                            v[u] = load4<T>(g + (size_t)(lo + j) * ow + ox);
-                        } else {
-                            const T* row = g + (size_t)(lo + j) * ow;
-                            v[u].x = ox < ow ? to_f(row[ox]) : 0.0f;         v[u].y = ox + 1 < ow ? to_f(row[ox + 1]) : 0.0f;
-                            v[u].z = ox + 2 < ow ? to_f(row[ox + 2]) : 0.0f; v[u].w = ox + 3 < ow ? to_f(row[ox + 3]) : 0.0f;
-                        }
-                    }
+                for (int r = 0; r < R; ++r) {
+                    acc[r][0] = fmaf(wy[r], v.x, acc[r][0]); acc[r][1] = fmaf(wy[r], v.y, acc[r][1]);
+                    acc[r][2] = fmaf(wy[r], v.z, acc[r][2]); acc[r][3] = fmaf(wy[r], v.w, acc[r][3]);
                 }
+            };
+            const T* gp = g + (size_t)(lo + rg) * ow + ox;       // this thread's rows: window rows rg, rg + rgroups, ...
+            const size_t gstride = (size_t)rgroups * ow;
+            int j = rg;
+            for (; j + (BATCH - 1) * rgroups < nwin; j += BATCH * rgroups) {     // full batches: every load issued before the first FMA
+                float4 v[BATCH];
 #pragma unroll
-                for (int u = 0; u < BWD_BATCH; ++u) {
-                    const int j = j0 + u * rgroups;
-                    if (j < nwin) {
-                        const float4 w4 = wts[j];
-                        const float wy[BWD_R] = {w4.x, w4.y, w4.z, w4.w};
+                for (int u = 0; u < BATCH; ++u) v[u] = ldrow(gp + u * gstride);
+                gp += BATCH * gstride;
 #pragma unroll
-                        for (int r = 0; r < BWD_R; ++r) {
-                            acc[r][0] = fmaf(wy[r], v[u].x, acc[r][0]); acc[r][1] = fmaf(wy[r], v[u].y, acc[r][1]);
-                            acc[r][2] = fmaf(wy[r], v[u].z, acc[r][2]); acc[r][3] = fmaf(wy[r], v[u].w, acc[r][3]);
-                        }
-                    }
-                }
+                for (int u = 0; u < BATCH; ++u) fold(v[u], wts[j + u * rgroups]);
+            }
+            for (; j < nwin; j += rgroups) {
+                const float4 v = ldrow(gp);
+                gp += gstride;
+                fold(v, wts[j]);
             }
 #pragma unroll
-            for (int r = 0; r < BWD_R; ++r) {
-                float* cs = colsum + (r * rgroups + rg) * pitch + ox;
-                cs[0] = acc[r][0]; cs[1] = acc[r][1]; cs[2] = acc[r][2]; cs[3] = acc[r][3];
-            }
+            for (int r = 0; r < R; ++r)
+                *reinterpret_cast<float4*>(colsum + (r * rgroups + rg) * pitch + ox) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
         }
     } else {   // very large scale factors: one column per thread, weights on the fly
         for (int r = 0; r < nr; ++r) {
@@ -232,23 +244,26 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
         rgroups = 1;
     }
     __syncthreads();
-    if (rgroups > 1) {      // the row groups' partial column sums, folded once (same order as before: group 0, 1, ...)
-        for (int idx = threadIdx.x; idx < nr * pitch; idx += blockDim.x) {
-            const int r = idx / pitch, ox = idx - r * pitch;
-            float* b = colsum + r * rgroups * pitch + ox;
-            float cs = b[0];
-            for (int k = 1; k < rgroups; ++k) cs += b[k * pitch];
-            b[0] = cs;
-        }
+    if (rgroups > 1) {      // the row groups' partial column sums, folded once (group 0, 1, ... in order)
+        for (int r = 0; r < nr; ++r)
+            for (int q4 = threadIdx.x; q4 < ow4; q4 += blockDim.x) {
+                float4* b4 = reinterpret_cast<float4*>(colsum + r * rgroups * pitch) + q4;
+                float4 cs = b4[0];
+                for (int k = 1; k < rgroups; ++k) {
+                    const float4 t = b4[k * ow4];
+                    cs.x += t.x; cs.y += t.y; cs.z += t.z; cs.w += t.w;
+                }
+                b4[0] = cs;
+            }
         __syncthreads();
     }
     // pass 2: an input pixel is folded by a group of L lanes (L = the power of two that spreads the nr*iw pixels over the CTA:
-    // 32 / 8 / 2 lanes at x32 / x16 / x8), each lane taking every L-th column of the window, then a fixed shuffle tree.  One
-    // thread per pixel made this pass a 2s-long serial chain on 11..176 threads -- about half of the kernel's time.
+    // 32 / 8 / 2 lanes at x32 / x16 / x8), each lane taking every L-th column of the window, then a fixed shuffle tree.
     const int items = nr * iw;
     int L = 32;
     while (L > 1 && items * L > (int)blockDim.x) L >>= 1;
     const int sub = threadIdx.x & (L - 1), per_pass = blockDim.x / L;
+    const float irw = mm.irw[map];
     for (int it0 = 0; it0 < items; it0 += per_pass) {       // uniform trip count: the shuffles below need every lane
         const int it = it0 + threadIdx.x / L;
         float acc = 0.0f;
@@ -256,7 +271,7 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
         if (it < items) {
             r = it / iw; ix = it - r * iw;
             int xl, xh;
-            touch_window(ix, ow, rw, ac, xl, xh);
+            touch_window_r(ix, ow, rw, irw, ac, xl, xh);
             const float* base = colsum + r * rgroups * pitch;
             for (int ox = xl + sub; ox <= xh; ox += L) {
                 const float2 t = xtab[ox];
@@ -268,6 +283,19 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
         for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (it < items && sub == 0) din[((size_t)plane * ih + iy0 + r) * iw + ix] = from_f<T>(acc);
     }
+}
+
+template <typename T, int BWD_BATCH, int MIN_CTAS>
+__global__ void __launch_bounds__(BWD_THREADS, MIN_CTAS)
+bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac, int rgroups) {
+    pv2::pdl_prologue();
+    extern __shared__ __align__(16) float colsum[];  // [BWD_R][rgroups][pitch] column sums, then [pitch] float2 x taps
+    __shared__ float4 wts[BWD_MAX_WIN];
+    const int map = blockIdx.z;
+    const int R = bwd_rows_per_cta(mm.ih[map], oh);
+    if (R == 4) bilinear_bwd_body<T, 4, BWD_BATCH>(mm, map, oh, ow, ac != 0, rgroups, colsum, wts);
+    else if (R == 2) bilinear_bwd_body<T, 2, BWD_BATCH>(mm, map, oh, ow, ac != 0, rgroups, colsum, wts);
+    else bilinear_bwd_body<T, 1, BWD_BATCH>(mm, map, oh, ow, ac != 0, rgroups, colsum, wts);
 }
 
 int check(const void* a, const void* b, int planes, int ih, int iw, int oh, int ow, int dtype, const char* who) {
@@ -304,8 +332,7 @@ static int launch_fwd(const MultiMaps& mm, int nmaps, int planes, int oh, int ow
 
 // grid.x of the backward for one map: input rows / rows per CTA (same rule as in the kernel)
 static int bwd_row_blocks(int ih, int oh) {
-    const int scale = (oh + ih - 1) / ih;
-    const int R = scale <= 8 ? BWD_R : (scale <= 16 ? 2 : 1);
+    const int R = bwd_rows_per_cta(ih, oh);
     return (ih + R - 1) / R;
 }
 
@@ -356,6 +383,7 @@ extern "C" int pv2_bilinear_bwd(const void* dout, void* din, int planes, int ih,
     PV2_CHECK(ih <= 65535 * 32, "bilinear_bwd: input height %d too large", ih);
     MultiMaps mm = {};
     mm.in[0] = din; mm.out[0] = const_cast<void*>(dout); mm.ih[0] = ih; mm.iw[0] = iw; mm.rh[0] = rh; mm.rw[0] = rw;
+    mm.irh[0] = rh > 0.0f ? 1.0f / rh : 0.0f; mm.irw[0] = rw > 0.0f ? 1.0f / rw : 0.0f;
     return launch_bwd(mm, 1, planes, bwd_row_blocks(ih, oh), oh, ow, align_corners, dtype, (cudaStream_t)stream);
 }
 
@@ -383,6 +411,7 @@ extern "C" int pv2_bilinear_multi_bwd(const void* const* dout, void* const* din,
     for (int i = 0; i < nmaps; ++i) {
         if (int e = check(dout[i], din[i], planes, ih[i], iw[i], oh, ow, dtype, "bilinear_multi_bwd")) return e;
         mm.in[i] = din[i]; mm.out[i] = const_cast<void*>(dout[i]); mm.ih[i] = ih[i]; mm.iw[i] = iw[i]; mm.rh[i] = rh[i]; mm.rw[i] = rw[i];
+        mm.irh[i] = rh[i] > 0.0f ? 1.0f / rh[i] : 0.0f; mm.irw[i] = rw[i] > 0.0f ? 1.0f / rw[i] : 0.0f;
         const int nb = bwd_row_blocks(ih[i], oh);
         if (nb > max_blocks) max_blocks = nb;
     }

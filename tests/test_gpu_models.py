@@ -241,8 +241,10 @@ def test_step_host_prefetch_equals_plain():
     # The first prefetched step (index 1) must reproduce the plain run; later steps of two independent trainings drift apart
     # chaotically (batch-2 BatchNorm, cuDNN gradients that are not bit-reproducible, Adam's sign-like steps), so from there on the
     # bit-exact check of the consumed batch above is the test.
+    # (step 0 is bit-identical; step 1 already differs by the cuDNN backward's run-to-run rounding amplified by one Adam step:
+    # 1.2e-5 relative was observed between two PLAIN runs, so the bound is 1e-4)
     for a, b in list(zip(*losses))[:2]:
-        assert abs(a - b) <= 1e-5 * abs(a), (losses[0], losses[1])
+        assert abs(a - b) <= 1e-4 * abs(a), (losses[0], losses[1])
     assert losses[0][0] != losses[0][1]          # different batches really were consumed
 
 
