@@ -281,6 +281,15 @@ def structure_loss(pred, pred_bg, mask_fg, mask_bg):
     return (wbce + wiou + 0.8 * wbce2).mean()
 
 
+def structure_loss_lowres(pairs, scale_factors, mask_fg, mask_bg=None):
+    """The final upsamples of PraNet_V2.forward (binary_seg/lib/pranet.py:349-350,370-371,392-393,414-415) followed by the loss calls
+    of the training loop (MyTrain_med.py:74,78-81), starting from the low-res (fg, bg) pairs: tensor of len(pairs) losses, in pair order
+    (SURVEY.md 8 f2 -- what pv2_structure_loss_lowres_fwd computes in one pass)."""
+    if mask_bg is None:
+        mask_bg = 1 - mask_fg                                                    # MyTrain_med.py:74
+    return torch.stack([structure_loss(interp(a, scale=s), interp(b, scale=s), mask_fg, mask_bg) for (a, b), s in zip(pairs, scale_factors)])
+
+
 def powerset_subsets(n=4):
     """Non-empty subsets in the order the reference's powerset() generator yields them
     (EMCAD/utils/utils.py:20-30; the empty set is skipped at trainer.py:132-133)."""

@@ -27,6 +27,31 @@ STRUCTURE_LOSS_CASES = {
 }
 
 
+# loss from the LOW-RES head maps: (B, S, sem_downsample, mask kind); the maps are the eight tensors PraNet_V2.forward
+# holds just before its final F.interpolate calls (pranet.py:349-350,370-371,392-393,414-415): S/8, S/16, S/32, S/8 (over sem_downsample)
+LOWRES_LOSS_CASES = {
+    "ll_352": (2, 352, 1, "hard"),
+    "ll_soft_256": (2, 256, 1, "soft"),          # multi-scale rate 0.75: resized (soft) masks, MyTrain_med.py:70-73
+    "ll_sd2_128": (1, 128, 2, "hard"),           # sem_downsample=2: final factors 4, 8, 16, 4
+    "ll_160": (3, 160, 1, "hard"),               # W % 128 != 0: partial tiles
+}
+
+
+def lowres_loss_scales(name):
+    sd = LOWRES_LOSS_CASES[name][2]
+    return [8 / sd, 16 / sd, 32 / sd, 8 / sd]
+
+
+def lowres_loss_inputs(name):
+    """-> (maps: [fg2, fg3, fg4, ra5_fg, bg2, bg3, bg4, ra5_bg] in the model's output order, mask (B,1,S/sd,S/sd))."""
+    B, S, sd, kind = LOWRES_LOSS_CASES[name]
+    seed = abs(hash_name(name))
+    maps = [synth.logits((B, 1, S // d, S // d), seed, f"low{i}") for i, d in enumerate((8, 16, 32, 8, 8, 16, 32, 8))]
+    H = S // sd
+    m = (synth.ellipse_masks(B, H, H, seed) if kind == "hard" else synth.soft_masks(B, H, H, seed)).view(B, 1, H, H)
+    return maps, m.contiguous()
+
+
 def structure_loss_inputs(name):
     B, C, H, W, kind, _ = STRUCTURE_LOSS_CASES[name]
     seed = abs(hash_name(name))

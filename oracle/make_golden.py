@@ -1,6 +1,6 @@
 """Freeze golden vectors from the UNMODIFIED reference (builder container only).
 
-    python -m oracle.make_golden [group ...]      # groups: sl head mc mcl full  (default: all)
+    python -m oracle.make_golden [group ...]      # groups: tail sl ll head mc mcl full  (default: all)
 
 Imports the reference's own modules from /root/reference through `oracle/ref_import.py`,
 feeds them the seeded inputs / weights of `oracle/synth.py` + `oracle/golden_cases.py`, and
@@ -15,6 +15,7 @@ import sys
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import golden_cases as G
 from . import ref_import as R
@@ -48,6 +49,21 @@ def gen_structure_loss():
         loss.backward()
         _save(name, loss=np.float64(loss.item()), dpred=_np(pred.grad, stride), dpred_bg=_np(pred_bg.grad, stride),
               mask_sum=np.float64(m.double().sum().item()))
+
+
+def gen_lowres_loss():
+    """Final upsamples as PraNet_V2.forward issues them (pranet.py:349-350,370-371,392-393,414-415: F.interpolate(scale_factor=,
+    mode='bilinear')) followed by the reference's own loss statements (MyTrain_med.py:74,78-82), differentiated back to the low-res maps."""
+    block = R.binary_train_loss_block()
+    for name in G.LOWRES_LOSS_CASES:
+        maps, m = G.lowres_loss_inputs(name)
+        maps = [t.requires_grad_(True) for t in maps]
+        ups = [F.interpolate(t, scale_factor=s, mode="bilinear") for t, s in zip(maps, G.lowres_loss_scales(name) * 2)]
+        loss, (l2, l3, l4, l5) = block(tuple(ups), m)
+        loss.backward()
+        # MyTrain_med.py:78-81 pairs loss5 with lateral_map_2, loss4 with _3, loss3 with _4, loss2 with _5: store in MAP order
+        _save(name, loss=np.float64(loss.item()), losses=np.array([l5.item(), l4.item(), l3.item(), l2.item()], np.float64),
+              **{f"d{i}": _np(t.grad) for i, t in enumerate(maps)})
 
 
 # --------------------------------------------------------------------------------------
@@ -239,7 +255,7 @@ def gen_tail():
         _save(name, labels=np.stack(labels))
 
 
-GROUPS = {"tail": gen_tail, "sl": gen_structure_loss, "head": gen_heads, "mc": gen_multiclass, "mcl": gen_mc_loss, "full": gen_full}
+GROUPS = {"tail": gen_tail, "sl": gen_structure_loss, "ll": gen_lowres_loss, "head": gen_heads, "mc": gen_multiclass, "mcl": gen_mc_loss, "full": gen_full}
 
 if __name__ == "__main__":
     assert R.available(), "reference not mounted; golden vectors can only be generated in the builder container"

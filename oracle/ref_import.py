@@ -257,6 +257,24 @@ def binary_test_tail():
     return run
 
 
+def binary_train_loss_block():
+    """The loss block of the reference's training loop, run from its own source: binary_seg/MyTrain_med.py:74 (bg_mask = 1-gts)
+    and :78-82 (the four structure_loss calls and their sum), compiled as they stand with the reference's structure_loss (:19-38).
+    Returns f(outs, gts) -> (loss, (loss2, loss3, loss4, loss5)) where `outs` is the 8-tuple the model returns (:76)."""
+    path = os.path.join(REF, "binary_seg", "MyTrain_med.py")
+    stmts = _stmts_between(path, 74, 74) + _stmts_between(path, 78, 82)
+    code = compile(ast.Module(body=stmts, type_ignores=[]), "MyTrain_med.py", "exec")
+    sl = structure_loss()
+
+    def run(outs, gts):
+        ns = {"torch": torch, "F": F, "structure_loss": sl, "gts": gts}
+        (ns["lateral_map_2_fg"], ns["lateral_map_3_fg"], ns["lateral_map_4_fg"], ns["lateral_map_5_fg"],
+         ns["lateral_map_2_bg"], ns["lateral_map_3_bg"], ns["lateral_map_4_bg"], ns["lateral_map_5_bg"]) = outs
+        exec(code, ns)
+        return ns["loss"], (ns["loss2"], ns["loss3"], ns["loss4"], ns["loss5"])
+    return run
+
+
 def multiclass_val_tail():
     """The dual-branch prediction rule of EMCAD/utils/utils.py:285-296 (val_single_volume, 2-D branch: P = net(input)[:4],
     P_bg = net(input)[-4:], outputs = sum (P - P_bg), argmax softmax), compiled from the reference source as it stands.

@@ -296,6 +296,24 @@ def test_structure_loss_lowres_vs_oracle(B, Cc, H, W, scales, soft, pass_bg):
             assert (got.cpu() - want).abs().max().item() <= 1e-3 * want.abs().max().item() + 1e-12
 
 
+@pytest.mark.parametrize("name", list(G.LOWRES_LOSS_CASES))
+def test_structure_loss_lowres_golden(name):
+    """Fused kernels == the UNMODIFIED reference's statements (final F.interpolate calls of pranet.py + MyTrain_med.py:74,78-82,
+    frozen by oracle/make_golden.py gen_lowres_loss): the four losses, their sum, and the gradients of the eight low-res maps."""
+    g = G.load(name)
+    maps, m = G.lowres_loss_inputs(name)
+    dev = [t.to(DEV).requires_grad_(True) for t in maps]
+    n0 = P._lib.launch_count()
+    losses = P.structure_loss_lowres([(dev[i], dev[i + 4]) for i in range(4)], G.lowres_loss_scales(name), m.to(DEV))
+    losses.sum().backward()
+    assert P._lib.launch_count() - n0 == 3                  # every golden geometry is inside the fused kernels' coverage
+    np.testing.assert_allclose(losses.detach().cpu().numpy(), g["losses"], rtol=1e-4)
+    assert abs(losses.sum().item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    for i, t in enumerate(dev):
+        ref = g[f"d{i}"]
+        np.testing.assert_allclose(t.grad.cpu().numpy(), ref, rtol=0, atol=1e-3 * np.abs(ref).max())
+
+
 def test_structure_loss_lowres_equals_unfused_full_size():
     """B = 16 x 352^2, four scales: the fused path against the module path's own kernels (bilinear x8 -> structure_loss x4 ->
     bilinear backward) -- same taps, same weight map, so agreement is at fp32 summation-order level; and it is deterministic."""

@@ -17,6 +17,21 @@ def _sub(t, stride):
     return (t[:, :, ::stride, ::stride] if stride > 1 else t).numpy()
 
 
+@pytest.mark.parametrize("name", list(G.LOWRES_LOSS_CASES))
+def test_structure_loss_lowres_oracle(name):
+    """Oracle of the loss from the low-res maps == the reference's own statements (pranet.py final F.interpolate calls +
+    MyTrain_med.py:74,78-82 compiled from source), losses and gradients w.r.t. the eight low-res maps."""
+    g = G.load(name)
+    maps, m = G.lowres_loss_inputs(name)
+    maps = [t.requires_grad_(True) for t in maps]
+    losses = O.structure_loss_lowres([(maps[i], maps[i + 4]) for i in range(4)], G.lowres_loss_scales(name), m)
+    losses.sum().backward()
+    np.testing.assert_allclose(losses.detach().numpy(), g["losses"], rtol=1e-6)
+    assert abs(losses.sum().item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    for i, t in enumerate(maps):
+        np.testing.assert_allclose(t.grad.numpy(), g[f"d{i}"], rtol=1e-5, atol=1e-7 * np.abs(g[f"d{i}"]).max())
+
+
 @pytest.mark.parametrize("name", list(G.STRUCTURE_LOSS_CASES))
 def test_structure_loss_oracle(name):
     g = G.load(name)
