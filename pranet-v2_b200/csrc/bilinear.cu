@@ -5,12 +5,15 @@
 // form at EMCAD/lib/decoders.py:460-461.  Index math is ATen's (area_pixel_compute_source_index +
 // guard_index_and_lambda), see pv2::bilinear_tap.
 //
-// fwd: CTA = (plane, band of output rows).  The few source rows the band touches are staged in shared
-//      memory once; every thread then produces 4 consecutive outputs and writes them with one 16-byte
-//      streaming store.  HBM bytes = (P_in + P_out) * elt: write-bound.
-// bwd: CTA = (plane, input row).  Pass 1 folds the <= 2s+2 output rows that touch this input row into
-//      one row of column sums in shared memory (coalesced reads of dout), pass 2 folds the columns.
-//      Every dout element is read by at most 2 input rows; no atomics, deterministic.
+// fwd: CTA = (plane, band of output rows); the band is sized on the host so that a launch has ~1000 CTAs.  The few source rows the
+//      band touches and the band's y taps are staged in shared memory once; every thread then produces 4 consecutive outputs per row
+//      (x taps computed once per thread, quads that share their two source columns are interpolated vertically first) and writes
+//      them with one 16-byte streaming store.  HBM bytes = (P_in + P_out) * elt: write-bound; 78.6 % of the measured HBM peak on the
+//      8 final maps of a B = 16 x 352^2 step (12.4 us).
+// bwd: CTA = (R input rows, plane, map), R = 4 / 2 / 1 at x8 / x16 / x32.  Pass 1 folds the output rows that touch these input rows
+//      into R rows of column sums in shared memory (coalesced 16-byte reads of dout, y weights from a table), pass 2 folds the
+//      columns (x taps from a table, lane groups + shuffle tree).  Every dout element is read by at most 2 CTAs; no atomics,
+//      deterministic.  26.5 us on the same 8 maps (36.8 %): issue / latency bound, see DESIGN.md.
 #include "pv2_common.cuh"
 
 namespace pv2 {

@@ -3,7 +3,8 @@
 //   weit = 1 + 5*|avg_pool31x31(mask) - mask|      (zero padding counted in the /961 divisor)
 //   loss = mean_{n,c}[ wbce(pred, mask) + wiou(pred, mask) + 0.8*wbce(pred_bg, mask_bg) ]
 //
-// Three kernels, all on the caller's stream:
+// Kernels, all on the caller's stream (the default forward is 2b; 1 + 2 run when rows are not 16-byte vectorisable or with
+// PV2_LOSS_TWO_PASS=1):
 //   1. boundary_weight_kernel  -- per 32x64 tile: mask + 15-px halo staged in shared memory, separable running-sum
 //      box filter out of shared memory, |avg - m| written ONCE as a 16-bit fixed-point map (2 B/px; weit is in
 //      [1,6], quantisation 7.6e-5) plus the per-tile sum of weit.  The reference recomputes the 961-tap pool in each
@@ -13,8 +14,13 @@
 //      16-byte loads of logits / mask / weight map, MUFU-only transcendental math, the 4 weighted sums per scale
 //      reduced warp-shuffle -> shared -> one partial per CTA (no atomics on data).  The last CTA to finish (ticket
 //      counter) folds the partials in a fixed order into per-plane sums and the scalar losses: bit-reproducible.
-//   3. structure_loss_bwd_kernel<T, NS, VEC> -- same streaming shape, reads the finished plane sums, writes both
+//   2b. structure_loss_fwd_fused_kernel<T, NS, LOWRES> -- boundary weight (summed-area table in shared memory) + loss sums in one
+//      pass over 32 x 128 tiles.  LOWRES = true reads the LOW-RESOLUTION head maps and does the model's final bilinear upsamples
+//      (pranet.py:349-415) per pixel, so the full-resolution logits never exist.
+//   3. structure_loss_bwd_kernel<T, NS, VEC> -- same streaming shape as 2, reads the finished plane sums, writes both
 //      gradients with 16-byte stores.
+//   3b. structure_loss_lowres_bwd_kernel<NS> + lowres_grad_fold_kernel<NS> -- backward of 2b/LOWRES: gradients scattered straight
+//      into the low-resolution maps (register pre-reduction, shared-memory folds, per-tile slots, deterministic fold).
 //
 // Algorithmic HBM bytes per pixel (fp32 logits, NS scales): fwd 4 + 8*NS, bwd 4 + 16*NS; the weight map adds
 // 2 B written once and 2 B read per pass.
