@@ -253,6 +253,10 @@ def main():
     if rank == 0:
         roof = roofline_adam(P, dev, ts.bucket.n if hasattr(ts.bucket, "n") else ts.flat.numel())
         roof["other_kernels"] = [roofline_structure_loss(P, dev, B, S)]
+        try:
+            roof["other_kernels"].append(roofline_bilinear(P, dev, B, S))
+        except Exception as exc:      # noqa: BLE001 -- an auxiliary measurement must not take the bench line down with it
+            roof["other_kernels"].append({"kernel": "bilinear_fwd/bwd_kernel (8 final maps)", "error": str(exc)[:200]})
 
     if rank == 0:
         peaks = {}
@@ -272,8 +276,9 @@ def main():
         except Exception:
             pass
         for o in roof["other_kernels"]:
-            o["frac"] = o["achieved"] / hbm
-            o["fwd"]["frac"] = o["fwd"]["achieved"] / hbm
+            if "achieved" in o:
+                o["frac"] = o["achieved"] / hbm
+                o["fwd"]["frac"] = o["fwd"]["achieved"] / hbm
         out = {
             "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -435,6 +440,56 @@ def roofline_structure_loss(P, dev, B, S, iters=24):
             "fwd": {"kernel": "structure_loss_fwd_kernel<float> (x4 scales) + finalize", "achieved": bytes_fwd / t_f / 1e9,
                     "bytes_per_launch": bytes_fwd, "avg_ms": t_f * 1e3},
             "note": f"{iters} back-to-back C-ABI launches between two CUDA events; inputs rotate over {nset} sets (> L2)"}
+
+
+def roofline_bilinear(P, dev, B, S, n=24, reps=5):
+    """The eight final upsamples of a step (pranet.py:349-350,370-371,392-393,414-415: x8, x16, x32, x8 for fg and bg) as the head
+    issues them -- one pv2_bilinear_multi_fwd launch, one pv2_bilinear_multi_bwd launch.  These launches take 12-27 us, less than a
+    ctypes call costs on the host, so `n` of them are captured in a CUDA graph (maps rotate over 4 sets, 4 x 63 MB > L2) and the
+    replay is timed with CUDA events.  Algorithmic bytes / launch = (8 full-resolution maps + their low-res sources) * 4."""
+    import ctypes
+    from pranet_v2_b200.ops import PV2_F32, _ratio
+    lib = P._lib.load()
+    scs = (8, 16, 32, 8, 8, 16, 32, 8)
+    nset = 4
+    lows = [[torch.randn(B, 1, S // s, S // s, device=dev) for s in scs] for _ in range(nset)]
+    his = [[torch.randn(B, 1, S, S, device=dev) for _ in scs] for _ in range(nset)]
+    ihs = (ctypes.c_int * 8)(*[S // s for s in scs])
+    rr = (ctypes.c_float * 8)(*[_ratio(S // s, S, False, float(s)) for s in scs])
+    pk = [(P._lib.ptr_array(lows[j]), P._lib.ptr_array(his[j])) for j in range(nset)]
+
+    def fwd(j):
+        (pl, _), (ph, _) = pk[j]
+        P._lib.check(lib.pv2_bilinear_multi_fwd(pl, ph, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, torch.cuda.current_stream().cuda_stream), "bilinear_multi_fwd")
+
+    def bwd(j):
+        (pl, _), (ph, _) = pk[j]
+        P._lib.check(lib.pv2_bilinear_multi_bwd(ph, pl, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, torch.cuda.current_stream().cuda_stream), "bilinear_multi_bwd")
+
+    def timed(fn):
+        fn(0)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for it in range(n):
+                fn(it % nset)
+        g.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / (reps * n)
+
+    t_f, t_b = timed(fwd), timed(bwd)
+    nbytes = (8 * B * S * S + sum(B * (S // s) ** 2 for s in scs)) * 4
+    return {"kernel": "bilinear_bwd_kernel<float> (8 final maps, one launch)", "bound": "hbm", "achieved": nbytes / t_b / 1e9, "unit": "GB/s",
+            "bytes_per_launch": nbytes, "avg_ms": t_b * 1e3, "traffic": None,
+            "fwd": {"kernel": "bilinear_fwd_kernel<float> (8 final maps, one launch)", "achieved": nbytes / t_f / 1e9,
+                    "bytes_per_launch": nbytes, "avg_ms": t_f * 1e3},
+            "note": f"{n} launches captured in a CUDA graph, {reps} replays between two CUDA events; maps rotate over {nset} sets (> L2)"}
 
 
 if __name__ == "__main__":
