@@ -288,7 +288,7 @@ def main():
                     "h2d_bytes_per_step": imgs_h[0].numel() * 4 + gts_h[0].numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             ips, per = time_cpu(args.cpu_batch, S, 3, 1)
             out["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                    "sample": f"3 timed steps (1 warm-up) of batch {args.cpu_batch} @ {S}^2: stock Res2Net-50 on torch-CPU + oracle head/loss, fp32"}
