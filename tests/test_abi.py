@@ -75,3 +75,17 @@ def test_reference_import_surface():
     assert [p.default for p in list(sig.parameters.values())[1:]] == [32, 3, 1, True]
     assert list(inspect.signature(PraNet_V2.forward).parameters)[1:] == ["x", "segSize"]
     assert list(inspect.signature(P.structure_loss).parameters)[:4] == ["pred", "pred_bg", "mask_fg", "mask_bg"]
+
+
+def test_ctypes_table_matches_header_arity():
+    """Every prototype of include/pv2.h has as many parameters as its ctypes signature in _lib._SIGS (a drifted binding would
+    otherwise only show up as garbage arguments on the GPU)."""
+    src = open(os.path.join(ROOT, "include", "pv2.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    protos = dict(re.findall(r"\b(pv2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(protos) == set(P._lib._SIGS)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(P._lib._SIGS[name][1]), f"{name}: header has {n} parameters, ctypes table {len(P._lib._SIGS[name][1])}"
