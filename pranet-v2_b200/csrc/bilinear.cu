@@ -143,8 +143,7 @@ __host__ __device__ inline int bwd_rows_per_cta(int ih, int oh) {
 
 constexpr int BWD_THREADS = 384;   // upper bound; the launch uses ow4 * rgroups threads so that every thread owns a column quad
 constexpr int BWD_R = 4;             // input rows per CTA: neighbouring input rows share output rows, so (R+1)*s rows are read for R rows
-// output rows a thread fetches per round trip (BWD_BATCH) and CTAs per SM are template parameters of the kernel: variant 0 = (8, 2),
-// 1 = (4, 3), 2 = (2, 4); PV2_BIL_BWD_VARIANT selects (tuning knob)
+// output rows a thread fetches per round trip (BWD_BATCH) and CTAs per SM are template parameters of the kernel; the launch uses (4, 3)
 constexpr int BWD_MAX_WIN = 192;     // output rows a block of R input rows can touch: (R+1)*scale + a few (scale <= 32)
 
 // touch_window with the reciprocal ratio precomputed on the host (a float division costs ~10 instructions; the +-1 margins absorb
@@ -358,15 +357,9 @@ static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int row_blocks
     const size_t smem = (size_t)BWD_R * rgroups * ow4 * 4 * sizeof(float) + (size_t)ow4 * 4 * sizeof(float2);
     PV2_CHECK(smem <= 48 * 1024, "bilinear_bwd: output width %d too large", ow);
     dim3 grid(row_blocks, planes, nmaps);
-#define PV2_BWD(TT)                                                                                                                    \
-    switch (variant) {                                                                                                                 \
-        case 0: pv2::launch(bilinear_bwd_kernel<TT, 8, 2>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;        \
-        case 2: pv2::launch(bilinear_bwd_kernel<TT, 2, 4>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;        \
-        default: pv2::launch(bilinear_bwd_kernel<TT, 4, 3>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups); break;       \
-    }
-    const int variant = pv2::tune_int("PV2_BIL_BWD_VARIANT", 1);      // measured at 8 maps x 16 x 352^2: 36.6 / 32.0 / 33.2 us
-    if (dtype == PV2_F32) { PV2_BWD(float) } else { PV2_BWD(__nv_bfloat16) }
-#undef PV2_BWD
+    // 4 rows in flight per thread at 3 CTAs per SM: measured 30.3 / 27.1 / 28.5 us for (8 rows, 2 CTAs) / (4, 3) / (2, 4) on 8 maps x 16 x 352^2
+    if (dtype == PV2_F32) pv2::launch(bilinear_bwd_kernel<float, 4, 3>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups);
+    else pv2::launch(bilinear_bwd_kernel<__nv_bfloat16, 4, 3>, grid, threads, smem, st, mm, oh, ow, align_corners, rgroups);
     PV2_LAUNCH_CHECK("bilinear_bwd");
     return 0;
 }

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(LS_THREADS, 4)
 structure_loss_fwd_fused_kernel(PtrPack pp, const __grid_constant__ LowresGeo geo, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
                                 uint16_t* __restrict__ wmap, int H, int W, int planes, int tiles_x, int tiles,
                                 float* __restrict__ partials, float* __restrict__ wsum_part, float* __restrict__ plane_sums,
-                                float* __restrict__ plane_loss, float* __restrict__ loss, unsigned int* __restrict__ ticket, int prefetch) {
+                                float* __restrict__ plane_loss, float* __restrict__ loss, unsigned int* __restrict__ ticket) {
     pv2::pdl_prologue();
     __shared__ float sat[FS_H * FS_PITCH];
     __shared__ float red[LS_THREADS / 32][4 * NS + 1];
@@ -386,30 +386,6 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const __grid_constant__ LowresGeo ge
     const int HW = H * W;
     const size_t pbase = (size_t)plane * HW;
     const float* mp = mask_fg + pbase;
-    // Experiment kept behind PV2_LOSS_PREFETCH=1|2: ask L2 for the tile's logit rows up front (one prefetch per 128-byte line) so
-    // they arrive while the summed-area table is built.  The grid is a single wave whose CTAs march through the same phases
-    // together, so this looked like free overlap; measured, mode 1 (first thing in the kernel) costs 3 us (38.5 -> 41.6 us at
-    // 16 x 352^2 x 4 scales): the mask halo loads the table build waits for queue behind 64 MB of prefetches.  Mode 2 issues them
-    // after the mask loads.
-    auto prefetch_logits = [&]() {
-        if constexpr (!LOWRES) {
-            constexpr int LPR = FT_W * (int)sizeof(T) / 128;            // 128-byte lines per tile row
-#pragma unroll
-            for (int k = 0; k < NS; ++k) {
-                const T* pf = reinterpret_cast<const T*>(pp.pred[k]) + pbase;
-                const T* pb = reinterpret_cast<const T*>(pp.pred_bg[k]) + pbase;
-                for (int i = tid; i < FT_H * LPR; i += LS_THREADS) {
-                    const int gy = y0 + i / LPR, gxl = x0 + (i % LPR) * (128 / (int)sizeof(T));
-                    if (gy < H && gxl < W) {
-                        const size_t off = (size_t)gy * W + gxl;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + off));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
-                    }
-                }
-            }
-        }
-    };
-    if (prefetch == 1) prefetch_logits();
     if constexpr (LOWRES) fill_tap_tables<NS>(xt, yt, geo, y0, x0, H, W, tid);      // visible after the first __syncthreads below
     // ---- stage + row prefix: warp = table row, lane = 5 consecutive columns ----
     if (tid < FS_PITCH) sat[tid] = 0.0f;                       // row 0
@@ -429,7 +405,6 @@ structure_loss_fwd_fused_kernel(PtrPack pp, const __grid_constant__ LowresGeo ge
             v[i][j] = (row_ok && c < FS_W && gx >= 0 && gx < W) ? __ldg(src + gx) : 0.0f;
         }
     }
-    if (prefetch == 2) prefetch_logits();
 #pragma unroll
     for (int i = 0; i < ROWS_PW; ++i) {
         const int r = 1 + warp + i * (LS_THREADS / 32);
@@ -673,8 +648,8 @@ __device__ __forceinline__ void tile_span(int o0, int n, int out_size, int in_si
     count = bilinear_tap(min(o0 + n - 1, out_size - 1), in_size, ratio, false).i1 - first + 1;
 }
 
-template <int NS, int MIN_CTAS>
-__global__ void __launch_bounds__(LS_THREADS, MIN_CTAS)
+template <int NS>
+__global__ void __launch_bounds__(LS_THREADS, 2)      // 128 registers: measured 61.3 / 68.7 / 70.2 us at 2 / 3 / 4 CTAs per SM (the tighter budgets spill)
 structure_loss_lowres_bwd_kernel(const __grid_constant__ PtrPack pp, const __grid_constant__ LowresGeo geo, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
                                  const uint16_t* __restrict__ wmap, const float* __restrict__ grad_loss, const float* __restrict__ plane_sums,
                                  float* __restrict__ gpart, int H, int W, int planes, int tiles_x, int tiles) {
@@ -927,9 +902,8 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
         PV2_CHECK(ce == cudaSuccess, "structure_loss_fwd: memset: %s", cudaGetErrorString(ce));
         const dim3 fgrid(L.ft_tiles, planes);
         const LowresGeo geo = {};
-        const int prefetch = pv2::tune_int("PV2_LOSS_PREFETCH", 0);      // 0 off (default), 1 / 2: see the kernel
 #define PV2_FUSED(TT, NSV) pv2::launch(structure_loss_fwd_fused_kernel<TT, NSV, false>, fgrid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, H, W, planes, \
-                                       L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket, prefetch)
+                                       L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
         if (logit_dtype == PV2_F32) {
             switch (nscales) { case 1: PV2_FUSED(float, 1); break; case 2: PV2_FUSED(float, 2); break; case 3: PV2_FUSED(float, 3); break; default: PV2_FUSED(float, 4); break; }
         } else {
@@ -1033,7 +1007,7 @@ extern "C" int pv2_structure_loss_lowres_fwd(const float* const* low_fg, const f
     PV2_CHECK(ce == cudaSuccess, "structure_loss_lowres_fwd: memset: %s", cudaGetErrorString(ce));
     const dim3 fgrid(L.ft_tiles, planes);
 #define PV2_LOWRES(NSV) pv2::launch(structure_loss_fwd_fused_kernel<float, NSV, true>, fgrid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, H, W, planes, \
-                                    L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket, 0)
+                                    L.ft_tiles_x, L.ft_tiles, L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
     switch (nscales) { case 1: PV2_LOWRES(1); break; case 2: PV2_LOWRES(2); break; case 3: PV2_LOWRES(3); break; default: PV2_LOWRES(4); break; }
 #undef PV2_LOWRES
     PV2_LAUNCH_CHECK("structure_loss_lowres_fwd");
@@ -1058,17 +1032,13 @@ extern "C" int pv2_structure_loss_lowres_bwd(const float* const* low_fg, const f
     const Layout L = make_layout(workspace, planes, H, W);
     float* gpart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + L.bytes);
     const dim3 grid(L.ft_tiles, planes), fold_grid((max_px + 255) / 256, planes, 2 * nscales);
-    const int ctas = pv2::tune_int("PV2_LOWRES_BWD_CTAS", 2);      // register budget of the backward: 2 / 3 / 4 CTAs per SM (tuning knob)
-#define PV2_LOWRES_BWD_K(NSV, MC)                                                                                                        \
-    pv2::launch(structure_loss_lowres_bwd_kernel<NSV, MC>, grid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, grad_loss, L.plane_sums, gpart, \
-                H, W, planes, L.ft_tiles_x, L.ft_tiles)
 #define PV2_LOWRES_BWD(NSV)                                                                                                              \
-    if (ctas >= 4) PV2_LOWRES_BWD_K(NSV, 4); else if (ctas == 3) PV2_LOWRES_BWD_K(NSV, 3); else PV2_LOWRES_BWD_K(NSV, 2);                \
+    pv2::launch(structure_loss_lowres_bwd_kernel<NSV>, grid, LS_THREADS, 0, st, pp, geo, mask_fg, mask_bg, L.wmap, grad_loss, L.plane_sums, gpart, \
+                H, W, planes, L.ft_tiles_x, L.ft_tiles);                                                                                \
     PV2_LAUNCH_CHECK("structure_loss_lowres_bwd");                                                                                      \
     pv2::launch(lowres_grad_fold_kernel<NSV>, fold_grid, 256, 0, st, pp, geo, gpart, H, W, L.ft_tiles_x, L.ft_tiles);                   \
     PV2_LAUNCH_CHECK("lowres_grad_fold")
     switch (nscales) { case 1: PV2_LOWRES_BWD(1); break; case 2: PV2_LOWRES_BWD(2); break; case 3: PV2_LOWRES_BWD(3); break; default: PV2_LOWRES_BWD(4); break; }
 #undef PV2_LOWRES_BWD
-#undef PV2_LOWRES_BWD_K
     return 0;
 }

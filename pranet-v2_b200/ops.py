@@ -159,7 +159,7 @@ class _StructureLossLowresFn(torch.autograd.Function):
         return (None, None, None, *dfg, *dbg)
 
 
-def lowres_loss_supported(maps, scale_factors, mask_fg) -> bool:
+def lowres_loss_supported(scale_factors, mask_fg) -> bool:
     """True when pv2_structure_loss_lowres_* covers this geometry (fp32 masks with W % 4 == 0, every final upsample >= x4)."""
     W = mask_fg.shape[-1]
     return W % 4 == 0 and all(s >= 4 for s in scale_factors) and mask_fg.data_ptr() % 16 == 0
@@ -184,7 +184,7 @@ def structure_loss_lowres(pairs, scale_factors, mask_fg, mask_bg=None):
     hs, ws, rhs, rws, size = _tail_geometry(fgs, scale_factors)
     if tuple(mask_fg.shape[-2:]) != size:
         raise ValueError(f"structure_loss_lowres: maps upsample to {size}, mask is {tuple(mask_fg.shape[-2:])}")
-    if not lowres_loss_supported(fgs, scale_factors, mask_fg):
+    if not lowres_loss_supported(scale_factors, mask_fg):
         up = [(interpolate_bilinear(a.float(), scale_factor=s), interpolate_bilinear(b.float(), scale_factor=s))
               for (a, b), s in zip(pairs, scale_factors)]
         return structure_loss_multi(up, mask_fg, mask_bg)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A/B of the tuning knobs of the memory-bound kernels at B = 16 x 352^2 (one process, knobs read per call):
-PV2_LOSS_PREFETCH (fused loss forward), PV2_BIL_BAND (final upsamples forward), PV2_BIL_BWD_VARIANT (their backward).
+PV2_LOSS_TWO_PASS (loss forward as boundary-weight kernel + streaming kernel) and PV2_BIL_BAND (rows per CTA of the final upsamples' forward).  (The knobs whose A/B is recorded in profiles/r1_kernel_knobs_v3.jsonl -- loss-forward L2 prefetch, bilinear-backward
+batch x occupancy, low-res-backward register budget -- were settled by that measurement and removed from the kernels.)
 Each variant: 24 launches captured in a CUDA graph over rotating > L2 buffers, CUDA events around the replays."""
 import ctypes
 import json
@@ -56,16 +57,7 @@ def sl_fwd():
     P._lib.check(lib.pv2_structure_loss_fwd(pp, pb, m.data_ptr(), None, 4, B, S, S, 0, loss.data_ptr(), ws.data_ptr(), ws_bytes, cur()), "fwd")
 
 
-ref = None
-for v in ("0", "1", "2", "0", "2"):
-    os.environ["PV2_LOSS_PREFETCH"] = v
-    report("structure_loss fwd x4 (fused)", "PV2_LOSS_PREFETCH", v, px * (4 + 32), BH.timed_graph(sl_fwd))
-    cnt[0] = 0
-    sl_fwd()
-    torch.cuda.synchronize()
-    ref = loss.clone() if ref is None else ref
-    assert torch.equal(ref, loss), "prefetch changed the loss"
-os.environ.pop("PV2_LOSS_PREFETCH")
+report("structure_loss fwd x4 (fused)", "PV2_LOSS_TWO_PASS", 0, px * (4 + 32), BH.timed_graph(sl_fwd))
 os.environ["PV2_LOSS_TWO_PASS"] = "1"
 report("structure_loss fwd x4 (boundary-weight kernel + streaming forward: 2 launches)", "PV2_LOSS_TWO_PASS", 1, px * (4 + 32), BH.timed_graph(sl_fwd))
 os.environ.pop("PV2_LOSS_TWO_PASS")
@@ -102,48 +94,7 @@ for band in (16, 0, 32, 44, 0):        # 0 = the library's own choice
     ref = got if ref is None else ref
     assert torch.equal(ref, got), "band changed the result"
 os.environ.pop("PV2_BIL_BAND", None)
-his = [[torch.randn(B, 1, S, S, device=dev) for _ in scs] for _ in range(nset)]
-pk = [(P._lib.ptr_array(lows[j]), P._lib.ptr_array(his[j])) for j in range(nset)]
-ref = None
-for var in (0, 1, 2, 0, 1, 2):
-    os.environ["PV2_BIL_BWD_VARIANT"] = str(var)
-    report("bilinear bwd, 8 final maps", "PV2_BIL_BWD_VARIANT", var, (8 * px + lowpx) * 4, BH.timed_graph(mb))
-    cnt[0] = 0
-    mb()
-    torch.cuda.synchronize()
-    got = torch.cat([t.flatten() for t in lows[1]]).clone()
-    ref = got if ref is None else ref
-    assert (ref - got).abs().max().item() <= 1e-5 * ref.abs().max().item(), "variant changed the gradient"
-os.environ.pop("PV2_BIL_BWD_VARIANT")
-
-# ---- loss from the low-res maps: register budget of the backward
-lscs = (8, 16, 32, 8)
-lfg = [[torch.randn(B, 1, S // s, S // s, device=dev) * 3 for s in lscs] for _ in range(2)]
-dlow = [[torch.empty(B, 1, S // s, S // s, device=dev) for s in lscs] for _ in range(2)]
-lws_bytes = lib.pv2_structure_loss_lowres_workspace_bytes(B, S, S, 4)
-lws = torch.empty(lws_bytes // 4, device=dev)
-lih = (ctypes.c_int * 4)(*[S // s for s in lscs])
-lrr = (ctypes.c_float * 4)(*[_ratio(S // s, S, False, float(s)) for s in lscs])
-lp = [P._lib.ptr_array(t) for t in lfg + dlow]
-gl = torch.ones(4, device=dev)
-P._lib.check(lib.pv2_structure_loss_lowres_fwd(lp[0][0], lp[1][0], lih, lih, lrr, lrr, m.data_ptr(), None, 4, B, S, S, loss.data_ptr(), lws.data_ptr(), lws_bytes, cur()), "lowres fwd")
-
-
-def ll_bwd():
-    P._lib.check(lib.pv2_structure_loss_lowres_bwd(lp[0][0], lp[1][0], lih, lih, lrr, lrr, m.data_ptr(), None, gl.data_ptr(), lp[2][0], lp[3][0],
-                                                   4, B, S, S, lws.data_ptr(), lws_bytes, cur()), "lowres bwd")
-
-
-ref = None
-for c in (2, 3, 4, 2, 3, 4):
-    os.environ["PV2_LOWRES_BWD_CTAS"] = str(c)
-    report("structure_loss_lowres bwd x4 + fold", "PV2_LOWRES_BWD_CTAS", c, px * 6, BH.timed_graph(ll_bwd))
-    ll_bwd()
-    torch.cuda.synchronize()
-    got = torch.cat([t.flatten() for t in dlow[0] + dlow[1]]).clone()
-    ref = got if ref is None else ref
-    assert torch.equal(ref, got), "register budget changed the gradient"
-os.environ.pop("PV2_LOWRES_BWD_CTAS")
+report("bilinear bwd, 8 final maps", "-", 0, (8 * px + lowpx) * 4, BH.timed_graph(mb))
 with open(os.path.join(ROOT, "gpurun_out", "variants.jsonl"), "w") as f:
     for r in out:
         f.write(json.dumps(r) + "\n")
