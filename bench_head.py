@@ -2,7 +2,7 @@
 """bench_head.py -- BASELINE.json config 5: DSRA head + structure_loss microbenchmark sweep with a roofline report.
 
     python bench_head.py [--batches 1,4,16,64] [--sizes 256,352,704] [--iters 50] [--precision bf16|fp32]
-                         [--backbone res2net|pvt] [--out gpurun_out/head_sweep.jsonl] [--kernels]
+                         [--backbone res2net|pvt] [--out gpurun_out/head_sweep.jsonl] [--kernels [--kernels-at 64x704]]
 
 For every (batch B, input size S) the head is fed synthetic backbone features relu(randn) of shapes
 (B,512,S/8,S/8), (B,1024,S/16,S/16), (B,2048,S/32,S/32) [PVT: 128/320/512] and timed as ONE
@@ -346,6 +346,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--backbone", default="res2net", choices=["res2net", "pvt"])
     ap.add_argument("--kernels", action="store_true")
+    ap.add_argument("--kernels-at", default="16x352", help="BxS of the per-kernel table, e.g. 64x704 (GEMM-sized conv problems)")
     ap.add_argument("--lowres-loss", default="0", choices=["0", "1", "both"], help="loss from the low-res maps (SURVEY.md 8 f2): off / on / both, one line each")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -382,7 +383,9 @@ def main():
                     print(json.dumps(r), flush=True)
                 torch.cuda.empty_cache()
     if args.kernels and rank == 0:
-        for r in kernel_table(P, dev, 16, 352, hbm, tfl):
+        kb, ks = (int(v) for v in args.kernels_at.lower().split("x"))
+        for r in kernel_table(P, dev, kb, ks, hbm, tfl):
+            r["B"], r["S"] = kb, ks
             r["peaks"] = src
             lines.append(r)
             print(json.dumps(r), flush=True)
