@@ -327,13 +327,20 @@ def kernel_table(P, dev, B, S, hbm, tflops):
         for a in acts:
             a.t.normal_()
 
+        bnm = nn.BatchNorm2d(cout).to(dev).train()
+
         def cv():
             eng.conv(acts[rot() % n], [conv])
-        cv()
-        ms = timed_graph(cv)
+
+        def cv_bn():        # as the head runs it in training: BatchNorm batch statistics produced by the same launch
+            eng.conv(acts[rot() % n], [conv], [bnm])
         fl = 2.0 * B * hw * hw * cout * cin * k * k
-        out.append({"kernel": f"conv_fwd {label} M={B * hw * hw} N={cout} K={cin * k * k}", "bound": "tensor", "flops": fl, "us": ms * 1e3,
-                    "achieved_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tflops})
+        for fn, tag in ((cv, "conv_fwd"), (cv_bn, "conv_fwd+bn_stats")):
+            fn()
+            ms = timed_graph(fn)
+            eng._keep.clear()
+            out.append({"kernel": f"{tag} {label} M={B * hw * hw} N={cout} K={cin * k * k}", "bound": "tensor", "flops": fl, "us": ms * 1e3,
+                        "achieved_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tflops})
         del acts
     return out
 

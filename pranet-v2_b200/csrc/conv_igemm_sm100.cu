@@ -299,6 +299,330 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------------
+// v2 forward / dgrad kernel: PERSISTENT CTAs, deep TMA ring, two TMEM accumulators, staged epilogue.
+//
+//   * grid = min(work items, SMs x CTAs/SM); a CTA walks work items w = blockIdx.x, + gridDim.x, ... where
+//     w = (split, n tile, m tile).  The producer streams the K slabs of consecutive work items through ONE ring, so the
+//     loads of the next tile are in flight while the current one is still being multiplied / drained;
+//   * the ring is as deep as shared memory allows (up to 12 slabs, ~160 KB): at the head's sizes a tile has 8..100 K slabs of
+//     20..48 KB and the L2 -> SM latency is ~1 us, so "all slabs of the tile in flight at once" is what turns the K loop from
+//     a chain of round trips into one;
+//   * the accumulator is double buffered in TMEM (2 x BN columns): warp 1 starts the MMAs of tile i+1 as soon as its slabs
+//     land while warps 2-5 drain tile i;
+//   * a K slab whose channel chunk is partly padding (Cin = 32 in a 64-channel box) issues only the MMAs that see data;
+//   * epilogue: tcgen05.ld (lane = pixel row) -> 128-byte-swizzled staging tile in shared memory -> (a) BatchNorm column
+//     statistics read column-wise (conflict free, all 32 rows in registers, two passes: mean, then centred squares) and
+//     (b) row-contiguous 16-byte global stores, 4 complete 128-byte rows per warp instruction.
+// ------------------------------------------------------------------------------------------------------
+constexpr int V2_MAX_STAGES = 12;
+constexpr int EPI_BUF_BYTES = 32 * 128;         // one warp's staging tile: 32 rows x 128 bytes
+constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES; // 4 epilogue warps x 2 buffers
+
+struct ConvArgs2 {
+    ConvArgs c;
+    int n_tiles, splits, work_total;
+    int ksteps_last;        // MMAs (of 32 K-bytes each) that see data in the LAST channel chunk of a tap (1..4)
+    int BNr;                // TMEM column stride between the two accumulators (BN rounded up to 32)
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+    return r;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS, 2)
+conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs2 a2,
+                 const __grid_constant__ BnFuseDev bn) {
+    constexpr int KC = (KIND == 0) ? 64 : 32;   // channels per 128-byte row
+    const ConvArgs& a = a2.c;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.BN * ROW_BYTES;
+    const int STAGES = a.stages;
+    const int stage_bytes = A_BYTES + b_bytes;
+    uint8_t* epi = smem + (size_t)STAGES * stage_bytes;                          // [4 warps][2][32 rows][128 B]
+    float* wstat = reinterpret_cast<float*>(epi + EPI_BYTES);                    // [4 row quarters][BN][mean, M2]
+    __shared__ __align__(8) uint64_t full_bar[V2_MAX_STAGES], empty_bar[V2_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_flag;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hw = a.H * a.W;
+    const int m_tiles = a.m_tiles;
+    const int per_term = a.taps * a.kc_per_tap;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA0); prefetch_tmap(&tmB0);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, a.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+    pdl_trigger();   // only now that this CTA owns its TMEM columns (see conv_fwd_kernel)
+    pdl_wait();
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        int s = 0; uint32_t ph = 0;
+        for (int w = blockIdx.x; w < a2.work_total; w += gridDim.x) {
+            const int m_tile = w % m_tiles, rest = w / m_tiles;
+            const int n_tile = rest % a2.n_tiles, split = rest / a2.n_tiles;
+            const long long m0 = (long long)m_tile * BM;
+            const int n_img = (int)(m0 / hw);
+            const int rem = (int)(m0 - (long long)n_img * hw);
+            const int y0 = rem / a.W, x0 = rem - y0 * a.W;
+            const int n0 = n_tile * a.BN;
+            const int it0 = split * a.iters_per_split, it1 = min(a.iters_total, it0 + a.iters_per_split);
+            for (int it = it0; it < it1; ++it) {
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int term = it / per_term, r2 = it - term * per_term;
+                const int tap = r2 / a.kc_per_tap, kc = r2 - tap * a.kc_per_tap;
+                const int kh = tap / a.KW, kw = tap - kh * a.KW;
+                uint8_t* sa = smem + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                tma_load_im2col_4d(sa, term == 1 ? &tmA1 : &tmA0, &full_bar[s], kc * KC, x0 - a.pad_w, y0 - a.pad_h, n_img,
+                                   (uint16_t)(kw * a.dil_w), (uint16_t)(kh * a.dil_h));
+                tma_load_3d(sa + A_BYTES, term == 2 ? &tmB1 : &tmB0, &full_bar[s], kc * KC, tap, n0);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc = instr_desc(KIND == 0 ? 1 : 2, 0, 0, BM, a.BN);
+        int s = 0; uint32_t ph = 0;
+        int lt = 0;
+        for (int w = blockIdx.x; w < a2.work_total; w += gridDim.x, ++lt) {
+            const int split = (w / m_tiles) / a2.n_tiles;
+            const int it0 = split * a.iters_per_split, it1 = min(a.iters_total, it0 + a.iters_per_split);
+            const int buf = lt & 1;
+            mbar_wait(&tempty_bar[buf], (((uint32_t)lt >> 1) & 1u) ^ 1u);      // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * a2.BNr);
+            for (int it = it0; it < it1; ++it) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + A_BYTES;
+                const int kc = it % a.kc_per_tap;
+                const int ksteps = (kc == a.kc_per_tap - 1) ? a2.ksteps_last : 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < ksteps)
+                        umma<KIND>(d_tmem, smem_desc_sw128(a_addr + k * 32, 16, 1024), smem_desc_sw128(b_addr + k * 32, 16, 1024),
+                                   idesc, (it > it0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            umma_commit(&tfull_bar[buf]);
+        }
+    } else if (warp >= 2) {
+        // ---------------- epilogue ----------------
+        const int q = warp & 3;                          // TMEM lane quarter of this warp
+        const uint32_t stg0 = smem_u32(epi + (size_t)(warp - 2) * 2 * EPI_BUF_BYTES);
+        const uint32_t my_row_off = (uint32_t)lane * 128u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        const int et = threadIdx.x - 64;
+        int lt = 0;
+        int chunk_ctr = 0;
+        for (int w = blockIdx.x; w < a2.work_total; w += gridDim.x, ++lt) {
+            const int m_tile = w % m_tiles, rest = w / m_tiles;
+            const int n_tile = rest % a2.n_tiles, split = rest / a2.n_tiles;
+            const long long m0 = (long long)m_tile * BM;
+            const int n0 = n_tile * a.BN;
+            const int buf = lt & 1;
+            mbar_wait(&tfull_bar[buf], ((uint32_t)lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a2.BNr);
+            int nvalid_w = 0;
+            {
+                const long long remr = a.M - m0 - q * 32;
+                nvalid_w = remr < 0 ? 0 : (remr > 32 ? 32 : (int)remr);
+            }
+            if (a.out_mode == 1) {
+                // biased NCHW head maps (Cout <= a few): direct stores, one pixel row per lane
+                const long long pix = m0 + q * 32 + lane;
+                const bool valid = pix < a.M;
+                const int n_pix = (int)(pix / hw);
+                const int rem = (int)(pix - (long long)n_pix * hw);
+                const int y = rem / a.W, x = rem - y * a.W;
+                for (int c0 = 0; c0 < a.BN; c0 += 16) {
+                    uint32_t t[16];
+                    tmem_ld_32x16(t_addr + (uint32_t)c0, t);
+                    tmem_ld_wait();
+                    if (c0 + 16 >= a.BN) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tempty_bar[buf]); }
+                    if (!valid) continue;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int co = n0 + c0 + j;
+                        if (co < a.Cout)
+                            a.out[(((long long)n_pix * a.Cout + co) * a.H + y) * a.W + x] = __uint_as_float(t[j]) + (a.bias ? a.bias[co] : 0.0f);
+                    }
+                }
+                continue;
+            }
+            const int CW = a.out_mode == 2 ? 64 : 32;       // accumulator columns per 128-byte staging row
+            for (int c0 = 0; c0 < a.BN; c0 += CW, ++chunk_ctr) {
+                const uint32_t stg = stg0 + (uint32_t)(chunk_ctr & 1) * EPI_BUF_BYTES;
+                uint32_t v[32];
+                // ---- TMEM -> registers -> swizzled staging rows (this lane's pixel row) ----
+                if (a.out_mode == 0) {
+                    if (a.BN - c0 >= 32) {
+                        tmem_ld_32x32(t_addr + (uint32_t)c0, v);
+                    } else {
+                        uint32_t t[16];
+                        tmem_ld_32x16(t_addr + (uint32_t)c0, t);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { v[j] = t[j]; v[16 + j] = 0u; }
+                    }
+                    tmem_ld_wait();
+                } else {
+                    uint32_t u[32];
+                    const int ncols = min(64, a.BN - c0);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int ch = ncols - 32 * h;          // columns of this half that exist
+                        if (ch >= 32) {
+                            tmem_ld_32x32(t_addr + (uint32_t)(c0 + 32 * h), u);
+                        } else if (ch >= 16) {
+                            uint32_t t[16];
+                            tmem_ld_32x16(t_addr + (uint32_t)(c0 + 32 * h), t);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) { u[j] = t[j]; u[16 + j] = 0u; }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) u[j] = 0u;
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[16 * h + j] = pack_bf16x2(__uint_as_float(u[2 * j]), __uint_as_float(u[2 * j + 1]));
+                    }
+                }
+                if (c0 + CW >= a.BN) {      // last read of this accumulator: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    st_shared_v4(stg + my_row_off + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                // ---- BatchNorm statistics of this warp's 32 rows: lane = column ----
+                if (a.stats) {
+                    float x[32];
+                    const uint32_t cb = stg + (uint32_t)((lane & 3) << 2);
+                    const uint32_t cc = (uint32_t)(lane >> 2);
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) x[r] = ld_shared_f32(cb + (uint32_t)r * 128u + ((cc ^ (uint32_t)(r & 7)) << 4));
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; r += 4) {
+                        s0 += (r < nvalid_w) ? x[r] : 0.f; s1 += (r + 1 < nvalid_w) ? x[r + 1] : 0.f;
+                        s2 += (r + 2 < nvalid_w) ? x[r + 2] : 0.f; s3 += (r + 3 < nvalid_w) ? x[r + 3] : 0.f;
+                    }
+                    const float mean = nvalid_w > 0 ? ((s0 + s1) + (s2 + s3)) / (float)nvalid_w : 0.0f;
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; r += 4) {
+                        const float d0 = x[r] - mean, d1 = x[r + 1] - mean, d2 = x[r + 2] - mean, d3 = x[r + 3] - mean;
+                        q0 = (r < nvalid_w) ? fmaf(d0, d0, q0) : q0; q1 = (r + 1 < nvalid_w) ? fmaf(d1, d1, q1) : q1;
+                        q2 = (r + 2 < nvalid_w) ? fmaf(d2, d2, q2) : q2; q3 = (r + 3 < nvalid_w) ? fmaf(d3, d3, q3) : q3;
+                    }
+                    if (c0 + lane < a.BN) {
+                        wstat[(q * a.BN + c0 + lane) * 2] = mean;
+                        wstat[(q * a.BN + c0 + lane) * 2 + 1] = (q0 + q1) + (q2 + q3);
+                    }
+                }
+                // ---- staging -> global: 4 complete 128-byte rows per warp instruction ----
+                const int colu = lane & 7;                                   // 16-byte unit of the row this lane moves
+                const int col = n0 + c0 + colu * (a.out_mode == 2 ? 8 : 4);  // first output column of that unit
+                const bool col_ok = (col < n0 + a.BN) && (col + (a.out_mode == 2 ? 7 : 3) < a.ldo);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + (lane >> 3);
+                    const uint4 val = ld_shared_v4(stg + (uint32_t)rr * 128u + ((((uint32_t)colu) ^ (uint32_t)(rr & 7)) << 4));
+                    const long long pix = m0 + q * 32 + rr;
+                    if (col_ok && pix < a.M) {
+                        if (a.out_mode == 0)
+                            *reinterpret_cast<uint4*>(a.out + (long long)split * a.split_stride + pix * a.ldo + col) = val;
+                        else
+                            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ldo + col) = val;
+                    }
+                }
+            }
+            if (a.stats) {
+                bar_sync(1, 128);
+                // tile statistics: the four row quarters combined in row order
+                for (int c = et; c < a.BN; c += 128) {
+                    const int cg = n0 + c;
+                    if (cg >= a.Cout) continue;
+                    float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const long long remr = a.M - m0 - qq * 32;
+                        const float nv = remr < 0 ? 0.0f : (remr > 32 ? 32.0f : (float)remr);
+                        chan_combine(n, mu, M2, nv, wstat[(qq * a.BN + c) * 2], wstat[(qq * a.BN + c) * 2 + 1]);
+                    }
+                    float* p = bn.f.part + ((size_t)m_tile * a.Cout + cg) * 2;
+                    p[0] = mu; p[1] = M2;
+                }
+                unsigned int* cnt = bn.f.counters + (size_t)n_tile * (a.ngroups + 1);
+                const int g = m_tile / a.G;
+                const int t0 = g * a.G, t1 = min(t0 + a.G, m_tiles);
+                if (ticket_last(cnt + g, (unsigned)(t1 - t0), et == 0, &s_flag, 1, 128)) {
+                    float* gpart = bn.f.part + (size_t)m_tiles * a.Cout * 2;
+                    for (int c = et; c < a.BN; c += 128) {
+                        const int cg = n0 + c;
+                        if (cg >= a.Cout) continue;
+                        float n, mu, M2;
+                        pooled_stats(t0, t1, [&](int t, float& pn, float& pmu, float& pm2) {
+                            const long long remr = a.M - (long long)t * BM;
+                            const float* p = bn.f.part + ((size_t)t * a.Cout + cg) * 2;
+                            pn = remr > BM ? (float)BM : (float)remr; pmu = __ldcg(p); pm2 = __ldcg(p + 1);
+                        }, n, mu, M2);
+                        if (a.ngroups == 1) {
+                            bn_write_channel(bn.f, cg, n, mu, M2);
+                        } else {
+                            float* gp = gpart + ((size_t)g * a.Cout + cg) * 3;
+                            gp[0] = n; gp[1] = mu; gp[2] = M2;
+                        }
+                    }
+                    if (a.ngroups > 1 && ticket_last(cnt + a.ngroups, (unsigned)a.ngroups, et == 0, &s_flag, 1, 128)) {
+                        for (int c = et; c < a.BN; c += 128) {
+                            const int cg = n0 + c;
+                            if (cg >= a.Cout) continue;
+                            float n, mu, M2;
+                            pooled_stats(0, a.ngroups, [&](int gg, float& pn, float& pmu, float& pm2) {
+                                const float* gp = gpart + ((size_t)gg * a.Cout + cg) * 3;
+                                pn = __ldcg(gp); pmu = __ldcg(gp + 1); pm2 = __ldcg(gp + 2);
+                            }, n, mu, M2);
+                            bn_write_channel(bn.f, cg, n, mu, M2);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // wgrad: per filter tap, dW[co][ci] = sum over pixels dY[p][co] * X[p + shift(tap)][ci].
 // CTA = (tap, (co tile, ci tile), pixel split).  A = dY patch, B = shifted X patch, both [128 pixels][128 B of
 // channels] boxes -> MN-major UMMA operands (K = pixels).  M = 128 output channels (rows beyond Cout are TMA
@@ -592,6 +916,47 @@ int plan_stages(long long ctas, int iters, size_t stage_bytes, uint32_t tmem_col
     return stages;
 }
 
+// N tiling shared by the kernels, the split-K hint and the statistics workspace: the fewest tiles of at most 256 columns,
+// evenly sized (Cout = 416 -> 2 x 208 instead of 256 + 160)
+bool use_v1();
+inline void n_tiling(int Cout, int* BN, int* n_tiles) {
+    if (use_v1()) {     // the one-tile-per-CTA kernel stores whole 32-column chunks: its tiles are 256 wide or the last one
+        *BN = Cout >= 256 ? 256 : ((Cout + 15) / 16) * 16;
+        *n_tiles = (Cout + *BN - 1) / *BN;
+        return;
+    }
+    const int nt = (Cout + 255) / 256;
+    const int per = (Cout + nt - 1) / nt;
+    *BN = ((per + 15) / 16) * 16;
+    *n_tiles = (Cout + *BN - 1) / *BN;
+}
+
+bool use_v1() {
+    static const bool on = [] { const char* e = getenv("PV2_CONV_V1"); return (e && e[0] == '1') || !use_im2col(); }();
+    return on;
+}
+
+// Persistent launch plan of conv_fwd2_kernel: CTAs per SM (1, or 2 when a work item's K slabs are few and small), ring depth.
+struct Plan2 { int grid, stages; size_t smem; };
+Plan2 plan_v2(int work_total, int slabs_per_item, size_t stage_bytes, uint32_t tmem_cols, size_t tail_bytes) {
+    const int force_stages = tune_int("PV2_CONV_STAGES", 0), force_cps = tune_int("PV2_CONV_CPS", 0);
+    int cps = ((size_t)slabs_per_item * stage_bytes <= (size_t)64 * 1024 && 2u * tmem_cols <= 512u) ? 2 : 1;
+    if (force_cps == 1 || force_cps == 2) cps = (force_cps == 2 && 2u * tmem_cols > 512u) ? 1 : force_cps;
+    Plan2 p;
+    p.grid = work_total < kNumSMs * cps ? work_total : kNumSMs * cps;
+    const int items_per_cta = (work_total + p.grid - 1) / p.grid;
+    const size_t budget = (cps == 1 ? (size_t)222 * 1024 : (size_t)110 * 1024) - 1024 - tail_bytes;   // 1 KB alignment slack
+    int st = (int)(budget / stage_bytes);
+    if (st > V2_MAX_STAGES) st = V2_MAX_STAGES;
+    const long long need = (long long)slabs_per_item * items_per_cta;
+    if (st > need) st = (int)need;
+    if (force_stages > 0 && force_stages < st) st = force_stages;
+    if (st < 1) st = 1;
+    p.stages = st;
+    p.smem = (size_t)st * stage_bytes + tail_bytes + 1024;
+    return p;
+}
+
 int common_checks(const char* who, int kind, int nterms, int N, int H, int W, int Cin_p, int Cout, int KH, int KW) {
     PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "%s: operand kind must be PV2_BF16 or PV2_TF32 (got %d)", who, kind);
     PV2_CHECK(nterms == 1 || (kind == PV2_TF32 && nterms == 3), "%s: nterms must be 1, or 3 with tf32 operands", who);
@@ -614,8 +979,8 @@ extern "C" int pv2_conv_fuses_bn_stats(int splits, int out_mode) {
 extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
     const int KC = kind == PV2_BF16 ? 64 : 32;
     const int m_tiles = m_tiles_of(N, H, W, KH, KW, true);
-    const int BN = Cout >= 256 ? 256 : ((Cout + 15) / 16) * 16;
-    const int n_tiles = (Cout + BN - 1) / BN;
+    int BN, n_tiles;
+    n_tiling(Cout, &BN, &n_tiles);
     const int iters = nterms * KH * KW * ((Cin_p + KC - 1) / KC);
     int splits = 1;
     // fill the 148 SMs when the output tiling alone cannot, keeping >= 8 K iterations per split
@@ -650,7 +1015,8 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     PV2_CHECK(splits >= 1 && splits <= a.iters_total, "conv_fwd: splits=%d out of range (K iterations %d)", splits, a.iters_total);
     a.iters_per_split = (a.iters_total + splits - 1) / splits;
     PV2_CHECK((long long)a.iters_per_split * (splits - 1) < a.iters_total, "conv_fwd: splits=%d leaves an empty split", splits);
-    a.BN = Cout >= 256 ? 256 : ((Cout + 15) / 16) * 16;
+    int n_tiles;
+    n_tiling(Cout, &a.BN, &n_tiles);
     a.tmem_cols = pow2_cols(a.BN);
     a.out_mode = out_mode; a.out = out; a.ldo = ldo; a.bias = bias;
     a.split_stride = (long long)N * H * W * ldo;
@@ -673,14 +1039,39 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
         if (int e = im2col ? make_im2col_map(&mA1, x1, k, Cin_p, W, H, N, a.pad_w, a.pad_h) : make_act_map(&mA1, x1, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
         if (int e = make_w_map(&mB1, (const uint8_t*)w_op + w_plane_stride * es, k, Cin_p, a.taps, Cout, a.BN)) return e;
     }
-    dim3 grid(im2col ? (unsigned)((a.M + BM - 1) / BM) : (unsigned)(N * a.tiles_x * a.tiles_y), (Cout + a.BN - 1) / a.BN, splits);
     const size_t stage_bytes = A_BYTES + (size_t)a.BN * ROW_BYTES;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce;
+    if (!use_v1()) {
+        ConvArgs2 a2 = {};
+        a2.n_tiles = n_tiles; a2.splits = splits;
+        a2.work_total = a.m_tiles * n_tiles * splits;
+        const int last_ch = Cin_p - (a.kc_per_tap - 1) * KC;              // channels in the last chunk of a tap
+        a2.ksteps_last = (last_ch + KC / 4 - 1) / (KC / 4);
+        a2.BNr = ((a.BN + 31) / 32) * 32;
+        a.tmem_cols = pow2_cols(2 * a2.BNr);
+        const size_t tail = (size_t)EPI_BYTES + (a.stats ? (size_t)4 * a.BN * 2 * sizeof(float) : 0);
+        const Plan2 pl = plan_v2(a2.work_total, a.iters_per_split, stage_bytes, a.tmem_cols, tail);
+        a.stages = pl.stages;
+        a2.c = a;
+        PV2_CHECK(pl.smem <= 227 * 1024, "conv_fwd: bad v2 stage plan (%d stages of %zu B)", pl.stages, stage_bytes);
+        if (k == 0) {
+            ce = cudaFuncSetAttribute(conv_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+            PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
+            pv2::launch(conv_fwd2_kernel<0>, dim3(pl.grid), THREADS, pl.smem, st, mA0, mA1, mB0, mB1, a2, bnd);
+        } else {
+            ce = cudaFuncSetAttribute(conv_fwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+            PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));
+            pv2::launch(conv_fwd2_kernel<1>, dim3(pl.grid), THREADS, pl.smem, st, mA0, mA1, mB0, mB1, a2, bnd);
+        }
+        PV2_LAUNCH_CHECK("conv_fwd");
+        return 0;
+    }
+    dim3 grid(im2col ? (unsigned)((a.M + BM - 1) / BM) : (unsigned)(N * a.tiles_x * a.tiles_y), (Cout + a.BN - 1) / a.BN, splits);
     const size_t stats_scratch = a.stats ? (size_t)(4 * 32 * 33 + 4 * a.BN * 2) * sizeof(float) : 0;   // epilogue reuses the ring
     a.stages = plan_stages((long long)grid.x * grid.y * grid.z, a.iters_per_split, stage_bytes, a.tmem_cols, stats_scratch, MAX_STAGES);
     const size_t smem = (size_t)a.stages * stage_bytes + 1024;
     PV2_CHECK(smem <= 227 * 1024 && smem - 1024 >= stats_scratch, "conv_fwd: bad stage plan (%d stages of %zu B)", a.stages, stage_bytes);
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t ce;
     if (k == 0) {
         ce = cudaFuncSetAttribute(conv_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         PV2_CHECK(ce == cudaSuccess, "conv_fwd: smem attribute: %s", cudaGetErrorString(ce));

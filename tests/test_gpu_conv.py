@@ -41,6 +41,11 @@ GEOMS = [  # cin, cout, kernel, padding, dilation, H, W, B
     (256, 3, 1, 0, 1, 3, 3, 2),
     (320, 9, 3, 1, 1, 14, 14, 2),
     (64, 64, 3, 1, 1, 7, 5, 2),
+    # persistent-kernel cases: more 128-pixel tiles than SMs (a CTA walks several work items through one ring and both TMEM
+    # accumulators), and an N of two 208-column tiles
+    (32, 32, 3, 1, 1, 88, 88, 4),
+    (64, 64, 3, 1, 1, 88, 88, 4),
+    (256, 416, 1, 0, 1, 11, 11, 16),
 ]
 
 
