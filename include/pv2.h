@@ -180,8 +180,24 @@ typedef struct pv2_bn_fuse {
     int nsegs, pad_;
 } pv2_bn_fuse;
 size_t pv2_bn_fuse_workspace_floats(long long M, int Cout);
-/* 1 when pv2_conv_fwd with these arguments computes the statistics in its epilogue (else call pv2_bn_stats_group) */
+/* How pv2_conv_fwd with these arguments produces the statistics:
+ *   0  not at all: call pv2_bn_stats_group afterwards (split-K);
+ *   2  (the persistent kernel) every CTA reduces the 128-pixel tiles it computed to ONE (count, mean, M2, -) row per channel,
+ *      bn->part[cta][Cout][4], and nothing else: no ticket, no fence, no serial tail in the GEMM.  The kernel that consumes a
+ *      channel slice (pv2_act_apply) is given a pv2_bn_defer descriptor and folds the pv2_conv_stats_parts() rows in its
+ *      prologue (fixed order: bit-reproducible), publishes mean / invstd / scale / shift and updates the running statistics;
+ *   1  (PV2_CONV_V1=1, the one-tile-per-CTA kernel kept for A/B) final statistics written by the launch (two-level ticket). */
 int pv2_conv_fuses_bn_stats(int splits, int out_mode);
+/* number of partial rows (= CTAs of the persistent launch) pv2_conv_fwd writes for this problem in mode 2 */
+int pv2_conv_stats_parts(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms, int splits);
+/* one BatchNorm module's channel slice [c_off, c_off + C) of a conv group whose statistics are still per-CTA partial rows */
+typedef struct pv2_bn_defer {
+    const float* part;                  /* [nparts][ldc][4]; NULL = this source is not deferred */
+    int nparts, ldc, c_off, pad_;       /* rows, channels per row (Cout of the group), first channel of the slice */
+    const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches_tracked;
+    float eps, momentum;
+    float* mean; float* invstd;         /* [C] outputs, saved for the backward pass (scale / shift go to the s / b arrays) */
+} pv2_bn_defer;
 /* statistics of raw[slab][M][ld] (slabs summed into slab 0 first) for every segment of `bn`: two launches per GROUP */
 int pv2_bn_stats_group(float* y, long long slab_stride, int nslabs, long long M, int Cout, int ld, const pv2_bn_fuse* bn, void* stream);
 
@@ -193,7 +209,14 @@ int pv2_bn_stats_group(float* y, long long slab_stride, int nslabs, long long M,
 int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms);
 int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,
                  int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int dil_h, int dil_w,
-                 int out_mode, float* out, int ldo, int splits, const float* bias, const pv2_bn_fuse* bn /* or NULL */, void* stream);
+                 int out_mode, float* out, int ldo, int splits, const float* bias, const pv2_bn_fuse* bn /* or NULL */,
+                 unsigned int* tile_counters /* >= (pixel tiles x N tiles) zero-initialised uints when splits > 1, left zeroed; else may be NULL */,
+                 void* stream);
+/* 1 when pv2_conv_fwd itself sums the split-K partials: with splits > 1 every split CTA ADDS its partial tile to out[0][.][.] with
+ * 16-byte fp32 reductions in L2 (red.global.add.v4.f32), so `out` must be ZERO-INITIALISED by the caller, only one slab is needed and
+ * consumers read one slab (fp32 summation order of the <= 8 partials is not fixed: results agree to rounding, not bit for bit);
+ * 0 when [split] slabs are written and left for the consumers to sum (PV2_CONV_V1=1). */
+int pv2_conv_sums_splits(void);
 /* dW partials out[split][Cout][KH*KW][Cin_p] = sum over the split's pixels of dY[p][co] * X[p + tap shift][ci] */
 int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind);
 int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const void* x, long long x_plane_stride, int kind, int nterms,
@@ -238,12 +261,16 @@ int pv2_bn_eval_affine(int C, const float* gamma, const float* beta, const float
 /* a1 = y1*s1+b1; [a2 = y2*s2+b2; v = a1 (+|*) a2 (combine 1|2)]; [v *= mult (operand format)]; [relu]
  * y_i may still be ns_i split-K slabs ss_i elements apart (summed on load).
  * -> operand NHWC slice (out_nchw = 0) or fp32 NCHW (out_nchw = 1).  Covers BN(+ReLU) (pranet.py:41-42,358),
- * relu(x_cat + conv_res) (pranet.py:82), the partial decoder's products (pranet.py:111-113) and biased heads. */
+ * relu(x_cat + conv_res) (pranet.py:82), the partial decoder's products (pranet.py:111-113) and biased heads.
+ * With a pv2_bn_defer descriptor for source i the launch first folds that source's per-CTA statistics (see
+ * pv2_conv_fuses_bn_stats) and WRITES s_i / b_i (and mean / invstd / running statistics) instead of reading them. */
 int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long long ss1, const float* s1, const float* b1,
                   const float* y2, int ld2, int off2, int ns2, long long ss2,
                   const float* s2, const float* b2, int combine, const void* mult, long long mult_plane, int mult_planes,
                   int mult_ld, int mult_off, int relu, long long M, int C, int HW, void* out, long long out_plane,
-                  int out_planes, int out_ld, int out_off, int out_nchw, int kind, void* stream);
+                  int out_planes, int out_ld, int out_off, int out_nchw,
+                  const pv2_bn_defer* defer1 /* or NULL: s1 / b1 are inputs */, const pv2_bn_defer* defer2 /* or NULL */,
+                  int kind, void* stream);
 /* backward of pv2_act_apply (+ training-mode BN when bn_train = 1): dz comes as <= 8 summed raw slabs or one NCHW
  * tensor; writes dy1 (dy2) in operand format for the dgrad/wgrad GEMMs, d(mult) raw, dgamma/dbeta. */
 int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long long ss1, const float* s1, const float* b1,

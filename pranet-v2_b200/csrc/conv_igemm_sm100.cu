@@ -323,6 +323,7 @@ struct ConvArgs2 {
     int n_tiles, splits, work_total;
     int ksteps_last;        // MMAs (of 32 K-bytes each) that see data in the LAST channel chunk of a tap (1..4)
     int BNr;                // TMEM column stride between the two accumulators (BN rounded up to 32)
+    unsigned int* tile_counters;   // split-K: one zero-initialised ticket per (n tile, m tile); left zeroed by the launch
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -332,6 +333,11 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
     return r;
+}
+// 16-byte fp32 reduction into global memory (L2 atomic unit): split-K partial tiles are ADDED to the one output slab
+__device__ __forceinline__ void red_add_v4(float* p, uint4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                 "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
 }
 __device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
     float r;
@@ -353,6 +359,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int stage_bytes = A_BYTES + b_bytes;
     uint8_t* epi = smem + (size_t)STAGES * stage_bytes;                          // [4 warps][2][32 rows][128 B]
     float* wstat = reinterpret_cast<float*>(epi + EPI_BYTES);                    // [4 row quarters][BN][mean, M2]
+    float* cacc = wstat + 4 * a.BN * 2;                                          // [Cout][count, mean, M2] of this CTA's tiles
     __shared__ __align__(8) uint64_t full_bar[V2_MAX_STAGES], empty_bar[V2_MAX_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_flag;
@@ -369,6 +376,8 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, a.tmem_cols);
+    if (a.stats)
+        for (int i = threadIdx.x; i < 3 * a.Cout; i += THREADS) cacc[i] = 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -439,6 +448,54 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int et = threadIdx.x - 64;
         int lt = 0;
         int chunk_ctr = 0;
+        // BatchNorm statistics of this warp's 32 staged rows x 32 columns (lane = column): all rows into registers, two passes
+        auto stats_chunk = [&](uint32_t stg, int nvalid_w, int c0) {
+            float x[32];
+            const uint32_t cb = stg + (uint32_t)((lane & 3) << 2);
+            const uint32_t cc = (uint32_t)(lane >> 2);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) x[r] = ld_shared_f32(cb + (uint32_t)r * 128u + ((cc ^ (uint32_t)(r & 7)) << 4));
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; r += 4) {
+                s0 += (r < nvalid_w) ? x[r] : 0.f; s1 += (r + 1 < nvalid_w) ? x[r + 1] : 0.f;
+                s2 += (r + 2 < nvalid_w) ? x[r + 2] : 0.f; s3 += (r + 3 < nvalid_w) ? x[r + 3] : 0.f;
+            }
+            const float mean = nvalid_w > 0 ? ((s0 + s1) + (s2 + s3)) / (float)nvalid_w : 0.0f;
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; r += 4) {
+                const float d0 = x[r] - mean, d1 = x[r + 1] - mean, d2 = x[r + 2] - mean, d3 = x[r + 3] - mean;
+                q0 = (r < nvalid_w) ? fmaf(d0, d0, q0) : q0; q1 = (r + 1 < nvalid_w) ? fmaf(d1, d1, q1) : q1;
+                q2 = (r + 2 < nvalid_w) ? fmaf(d2, d2, q2) : q2; q3 = (r + 3 < nvalid_w) ? fmaf(d3, d3, q3) : q3;
+            }
+            if (c0 + lane < a.BN) {
+                wstat[(q * a.BN + c0 + lane) * 2] = mean;
+                wstat[(q * a.BN + c0 + lane) * 2 + 1] = (q0 + q1) + (q2 + q3);
+            }
+        };
+        // tile statistics: the four row quarters combined in row order, then folded (Chan) into this CTA's running statistics
+        // of the channel -- always by the same thread, so no further synchronisation is needed
+        auto tile_stats = [&](long long m0, int n0) {
+            bar_sync(1, 128);
+            for (int c = et; c < a.BN; c += 128) {
+                const int cg = n0 + c;
+                if (cg >= a.Cout) continue;
+                float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const long long remr = a.M - m0 - qq * 32;
+                    const float nv = remr < 0 ? 0.0f : (remr > 32 ? 32.0f : (float)remr);
+                    chan_combine(n, mu, M2, nv, wstat[(qq * a.BN + c) * 2], wstat[(qq * a.BN + c) * 2 + 1]);
+                }
+                float* acc = cacc + 3 * cg;
+                float an = acc[0], amu = acc[1], aM2 = acc[2];
+                chan_combine(an, amu, aM2, n, mu, M2);
+                acc[0] = an; acc[1] = amu; acc[2] = aM2;
+            }
+            bar_sync(1, 128);     // wstat is rewritten by the next tile
+        };
+        const bool fix = a2.splits > 1;      // split-K: partial tiles are ADDED to the (zero-initialised) output with 16-byte reductions
         for (int w = blockIdx.x; w < a2.work_total; w += gridDim.x, ++lt) {
             const int m_tile = w % m_tiles, rest = w / m_tiles;
             const int n_tile = rest % a2.n_tiles, split = rest / a2.n_tiles;
@@ -521,32 +578,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int j = 0; j < 8; ++j)
                     st_shared_v4(stg + my_row_off + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
-                // ---- BatchNorm statistics of this warp's 32 rows: lane = column ----
-                if (a.stats) {
-                    float x[32];
-                    const uint32_t cb = stg + (uint32_t)((lane & 3) << 2);
-                    const uint32_t cc = (uint32_t)(lane >> 2);
-#pragma unroll
-                    for (int r = 0; r < 32; ++r) x[r] = ld_shared_f32(cb + (uint32_t)r * 128u + ((cc ^ (uint32_t)(r & 7)) << 4));
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                    for (int r = 0; r < 32; r += 4) {
-                        s0 += (r < nvalid_w) ? x[r] : 0.f; s1 += (r + 1 < nvalid_w) ? x[r + 1] : 0.f;
-                        s2 += (r + 2 < nvalid_w) ? x[r + 2] : 0.f; s3 += (r + 3 < nvalid_w) ? x[r + 3] : 0.f;
-                    }
-                    const float mean = nvalid_w > 0 ? ((s0 + s1) + (s2 + s3)) / (float)nvalid_w : 0.0f;
-                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll
-                    for (int r = 0; r < 32; r += 4) {
-                        const float d0 = x[r] - mean, d1 = x[r + 1] - mean, d2 = x[r + 2] - mean, d3 = x[r + 3] - mean;
-                        q0 = (r < nvalid_w) ? fmaf(d0, d0, q0) : q0; q1 = (r + 1 < nvalid_w) ? fmaf(d1, d1, q1) : q1;
-                        q2 = (r + 2 < nvalid_w) ? fmaf(d2, d2, q2) : q2; q3 = (r + 3 < nvalid_w) ? fmaf(d3, d3, q3) : q3;
-                    }
-                    if (c0 + lane < a.BN) {
-                        wstat[(q * a.BN + c0 + lane) * 2] = mean;
-                        wstat[(q * a.BN + c0 + lane) * 2 + 1] = (q0 + q1) + (q2 + q3);
-                    }
-                }
+                if (a.stats && !fix) stats_chunk(stg, nvalid_w, c0);
                 // ---- staging -> global: 4 complete 128-byte rows per warp instruction ----
                 const int colu = lane & 7;                                   // 16-byte unit of the row this lane moves
                 const int col = n0 + c0 + colu * (a.out_mode == 2 ? 8 : 4);  // first output column of that unit
@@ -557,64 +589,50 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     const uint4 val = ld_shared_v4(stg + (uint32_t)rr * 128u + ((((uint32_t)colu) ^ (uint32_t)(rr & 7)) << 4));
                     const long long pix = m0 + q * 32 + rr;
                     if (col_ok && pix < a.M) {
-                        if (a.out_mode == 0)
-                            *reinterpret_cast<uint4*>(a.out + (long long)split * a.split_stride + pix * a.ldo + col) = val;
-                        else
+                        if (a.out_mode == 0) {
+                            if (fix) red_add_v4(a.out + pix * a.ldo + col, val);
+                            else *reinterpret_cast<uint4*>(a.out + pix * a.ldo + col) = val;
+                        } else
                             *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ldo + col) = val;
                     }
                 }
             }
-            if (a.stats) {
-                bar_sync(1, 128);
-                // tile statistics: the four row quarters combined in row order
-                for (int c = et; c < a.BN; c += 128) {
-                    const int cg = n0 + c;
-                    if (cg >= a.Cout) continue;
-                    float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+            if (fix && a.stats) {
+                // split-K + BatchNorm: every split CTA has ADDED its partial tile to the output; the one that draws the tile's last
+                // ticket reads the finished tile back (L2) and reduces it to the tile statistics exactly like the unsplit path
+                unsigned int* cnt = a2.tile_counters + (size_t)n_tile * m_tiles + m_tile;
+                if (ticket_last(cnt, (unsigned)a2.splits, et == 0, &s_flag, 1, 128)) {
+                    const int colu = lane & 7;
+                    for (int c0 = 0; c0 < a.BN; c0 += 32, ++chunk_ctr) {
+                        const uint32_t stg = stg0 + (uint32_t)(chunk_ctr & 1) * EPI_BUF_BYTES;
+                        const int col = n0 + c0 + colu * 4;
+                        const bool col_ok = (col < n0 + a.BN) && (col + 3 < a.ldo);
+                        float4 t[8];
 #pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const long long remr = a.M - m0 - qq * 32;
-                        const float nv = remr < 0 ? 0.0f : (remr > 32 ? 32.0f : (float)remr);
-                        chan_combine(n, mu, M2, nv, wstat[(qq * a.BN + c) * 2], wstat[(qq * a.BN + c) * 2 + 1]);
-                    }
-                    float* p = bn.f.part + ((size_t)m_tile * a.Cout + cg) * 2;
-                    p[0] = mu; p[1] = M2;
-                }
-                unsigned int* cnt = bn.f.counters + (size_t)n_tile * (a.ngroups + 1);
-                const int g = m_tile / a.G;
-                const int t0 = g * a.G, t1 = min(t0 + a.G, m_tiles);
-                if (ticket_last(cnt + g, (unsigned)(t1 - t0), et == 0, &s_flag, 1, 128)) {
-                    float* gpart = bn.f.part + (size_t)m_tiles * a.Cout * 2;
-                    for (int c = et; c < a.BN; c += 128) {
-                        const int cg = n0 + c;
-                        if (cg >= a.Cout) continue;
-                        float n, mu, M2;
-                        pooled_stats(t0, t1, [&](int t, float& pn, float& pmu, float& pm2) {
-                            const long long remr = a.M - (long long)t * BM;
-                            const float* p = bn.f.part + ((size_t)t * a.Cout + cg) * 2;
-                            pn = remr > BM ? (float)BM : (float)remr; pmu = __ldcg(p); pm2 = __ldcg(p + 1);
-                        }, n, mu, M2);
-                        if (a.ngroups == 1) {
-                            bn_write_channel(bn.f, cg, n, mu, M2);
-                        } else {
-                            float* gp = gpart + ((size_t)g * a.Cout + cg) * 3;
-                            gp[0] = n; gp[1] = mu; gp[2] = M2;
+                        for (int i = 0; i < 8; ++i) {
+                            const long long pix = m0 + q * 32 + i * 4 + (lane >> 3);
+                            t[i] = (col_ok && pix < a.M) ? __ldcg(reinterpret_cast<const float4*>(a.out + pix * a.ldo + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
-                    }
-                    if (a.ngroups > 1 && ticket_last(cnt + a.ngroups, (unsigned)a.ngroups, et == 0, &s_flag, 1, 128)) {
-                        for (int c = et; c < a.BN; c += 128) {
-                            const int cg = n0 + c;
-                            if (cg >= a.Cout) continue;
-                            float n, mu, M2;
-                            pooled_stats(0, a.ngroups, [&](int gg, float& pn, float& pmu, float& pm2) {
-                                const float* gp = gpart + ((size_t)gg * a.Cout + cg) * 3;
-                                pn = __ldcg(gp); pmu = __ldcg(gp + 1); pm2 = __ldcg(gp + 2);
-                            }, n, mu, M2);
-                            bn_write_channel(bn.f, cg, n, mu, M2);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + (lane >> 3);
+                            st_shared_v4(stg + (uint32_t)rr * 128u + ((((uint32_t)colu) ^ (uint32_t)(rr & 7)) << 4),
+                                         __float_as_uint(t[i].x), __float_as_uint(t[i].y), __float_as_uint(t[i].z), __float_as_uint(t[i].w));
                         }
+                        __syncwarp();
+                        stats_chunk(stg, nvalid_w, c0);
                     }
+                    tile_stats(m0, n0);
                 }
+            } else if (a.stats) {
+                tile_stats(m0, n0);
             }
+        }
+        if (a.stats) {
+            // one partial row per CTA: (count, mean, M2) of the pixels this CTA saw, per channel; the CONSUMER of a channel slice
+            // (pv2_act_apply with a pv2_bn_defer descriptor) folds the <= 296 rows in its prologue.  No ticket, no fence, no tail.
+            float4* row = reinterpret_cast<float4*>(bn.f.part) + (size_t)blockIdx.x * a.Cout;
+            for (int cg = et; cg < a.Cout; cg += 128) row[cg] = make_float4(cacc[3 * cg], cacc[3 * cg + 1], cacc[3 * cg + 2], 0.0f);
         }
     }
     tc_fence_before();
@@ -936,6 +954,10 @@ bool use_v1() {
     return on;
 }
 
+inline size_t v2_tail_bytes(bool stats, int BN, int Cout) {     // staging tiles + (statistics) per-quarter scratch + CTA accumulators
+    return (size_t)EPI_BYTES + (stats ? ((size_t)4 * BN * 2 + (size_t)3 * Cout) * sizeof(float) : 0);
+}
+
 // Persistent launch plan of conv_fwd2_kernel: CTAs per SM (1, or 2 when a work item's K slabs are few and small), ring depth.
 struct Plan2 { int grid, stages; size_t smem; };
 Plan2 plan_v2(int work_total, int slabs_per_item, size_t stage_bytes, uint32_t tmem_cols, size_t tail_bytes) {
@@ -973,7 +995,24 @@ using namespace pv2;
 
 extern "C" int pv2_conv_fuses_bn_stats(int splits, int out_mode) {
     static const bool off = [] { const char* e = getenv("PV2_NO_FUSED_STATS"); return e && e[0] == '1'; }();   // A/B switch for profiling
-    return (!off && use_im2col() && splits == 1 && out_mode == 0) ? 1 : 0;
+    if (off || !use_im2col() || out_mode != 0) return 0;
+    if (use_v1()) return splits == 1 ? 1 : 0;      // 1: final statistics written by the launch
+    return 2;                                      // 2: per-CTA partials (also under split-K: the fix-up CTA of a tile produces them)
+}
+
+extern "C" int pv2_conv_sums_splits(void) { return use_v1() ? 0 : 1; }
+
+extern "C" int pv2_conv_stats_parts(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms, int splits) {
+    const int KC = kind == PV2_BF16 ? 64 : 32;
+    int BN, n_tiles;
+    n_tiling(Cout, &BN, &n_tiles);
+    const int m_tiles = (int)(((long long)N * H * W + BM - 1) / BM);
+    const int iters = nterms * KH * KW * ((Cin_p + KC - 1) / KC);
+    if (splits < 1) splits = 1;
+    const int BNr = ((BN + 31) / 32) * 32;
+    const Plan2 pl = plan_v2(m_tiles * n_tiles * splits, (iters + splits - 1) / splits, (size_t)A_BYTES + (size_t)BN * ROW_BYTES, pow2_cols(2 * BNr),
+                             v2_tail_bytes(true, BN, Cout));
+    return pl.grid;
 }
 
 extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
@@ -991,7 +1030,8 @@ extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, in
 
 extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long long w_plane_stride, int kind, int nterms,
                             int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int dil_h, int dil_w,
-                            int out_mode, float* out, int ldo, int splits, const float* bias, const pv2_bn_fuse* bn, void* stream) {
+                            int out_mode, float* out, int ldo, int splits, const float* bias, const pv2_bn_fuse* bn,
+                            unsigned int* tile_counters, void* stream) {
     if (int e = common_checks("conv_fwd", kind, nterms, N, H, W, Cin_p, Cout, KH, KW)) return e;
     PV2_CHECK(x && w_op && out, "conv_fwd: null pointer");
     PV2_CHECK(out_mode >= 0 && out_mode <= 2, "conv_fwd: bad out_mode %d", out_mode);
@@ -1049,9 +1089,14 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
         const int last_ch = Cin_p - (a.kc_per_tap - 1) * KC;              // channels in the last chunk of a tap
         a2.ksteps_last = (last_ch + KC / 4 - 1) / (KC / 4);
         a2.BNr = ((a.BN + 31) / 32) * 32;
+        a2.tile_counters = tile_counters;
+        PV2_CHECK(splits <= 8, "conv_fwd: at most 8 K splits (got %d)", splits);
+        PV2_CHECK(splits == 1 || !a.stats || (tile_counters != nullptr && (long long)a.m_tiles * n_tiles <= PV2_BN_COUNTERS),
+                  "conv_fwd: split-K with fused statistics needs %lld zero-initialised tile counters (<= %d)", (long long)a.m_tiles * n_tiles, PV2_BN_COUNTERS);
         a.tmem_cols = pow2_cols(2 * a2.BNr);
-        const size_t tail = (size_t)EPI_BYTES + (a.stats ? (size_t)4 * a.BN * 2 * sizeof(float) : 0);
+        const size_t tail = v2_tail_bytes(a.stats != 0, a.BN, Cout);
         const Plan2 pl = plan_v2(a2.work_total, a.iters_per_split, stage_bytes, a.tmem_cols, tail);
+        PV2_CHECK(!a.stats || (size_t)pl.grid * Cout * 4 <= pv2_bn_fuse_workspace_floats(a.M, Cout), "conv_fwd: statistics workspace too small");
         a.stages = pl.stages;
         a2.c = a;
         PV2_CHECK(pl.smem <= 227 * 1024, "conv_fwd: bad v2 stage plan (%d stages of %zu B)", pl.stages, stage_bytes);

@@ -446,10 +446,103 @@ __device__ __forceinline__ float apply_value(const ApplyArgs& a, long long r, in
     return v;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Deferred BatchNorm fold.  The persistent conv kernel leaves one (count, mean, M2) row per CTA; the kernel that consumes a
+// channel slice folds the rows here, in its prologue: thread (c, j) Chan-combines rows j, j+J, ... of channel c (loads issued
+// eight at a time), the J sub-results are combined in j order -- a fixed order, so the statistics are bit-reproducible.
+// Every CTA computes the slice's scale / shift into its own shared memory; CTA 0 also publishes mean / invstd / scale / shift
+// (saved for the backward pass) and updates the running statistics exactly like nn.BatchNorm2d.
+// ------------------------------------------------------------------------------------------------------
+constexpr int DEFER_MAX_C = 512;
+struct Defer2 { pv2_bn_defer d[2]; };
+
+// pooled statistics of up to NB rows held in registers: no divisions inside the loops, every M2 term non-negative
+template <int NB>
+__device__ __forceinline__ void pooled_rows(const float4 (&v)[NB], float& N, float& mean, float& M2) {
+    float Sn = 0.0f, Snm = 0.0f;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) { Sn += v[u].x; Snm = fmaf(v[u].x, v[u].y, Snm); }
+    const float m = Sn > 0.0f ? Snm / Sn : 0.0f;
+    float q = 0.0f;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) { const float dd = v[u].y - m; q += v[u].z + v[u].x * dd * dd; }
+    N = Sn; mean = m; M2 = q;
+}
+
+constexpr int DEFER_NB = 20;     // rows a thread folds from registers in one batch of independent 16-byte loads
+
+__device__ __forceinline__ void bn_fold_deferred(const pv2_bn_defer& d, int C, float* s_scale, float* s_shift, float* s_red,
+                                                 bool writer, float* g_scale, float* g_shift) {
+    const int T = blockDim.x, t = threadIdx.x;
+    for (int cb = 0; cb < C; cb += T) {
+        const int Cb = min(T, C - cb);
+        int J = T / Cb;                  // row lanes per channel: thread (c, j) folds rows j, j+J, ...
+        if (J > 32) J = 32;
+        const int c = t % Cb, j = t / Cb;
+        float n = 0.0f, mu = 0.0f, M2 = 0.0f;
+        if (j < J) {
+            const float4* base = reinterpret_cast<const float4*>(d.part) + d.c_off + cb + c;
+            for (int p0 = j; p0 < d.nparts; p0 += DEFER_NB * J) {      // one iteration unless nparts > 20 * J
+                float4 v[DEFER_NB];
+#pragma unroll
+                for (int u = 0; u < DEFER_NB; ++u) {
+                    const int p = p0 + u * J;
+                    v[u] = p < d.nparts ? __ldg(base + (size_t)p * d.ldc) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+                float bn_, bm, bq;
+                pooled_rows<DEFER_NB>(v, bn_, bm, bq);
+                chan_combine(n, mu, M2, bn_, bm, bq);
+            }
+        }
+        s_red[t * 3] = n; s_red[t * 3 + 1] = mu; s_red[t * 3 + 2] = M2;
+        __syncthreads();
+        if (t < Cb) {
+            // the J row lanes of this channel, pooled in lane order
+            float Sn = 0.0f, Snm = 0.0f;
+            for (int jj = 0; jj < J; ++jj) { const float* q = s_red + (jj * Cb + t) * 3; Sn += q[0]; Snm = fmaf(q[0], q[1], Snm); }
+            mu = Sn > 0.0f ? Snm / Sn : 0.0f;
+            M2 = 0.0f;
+            for (int jj = 0; jj < J; ++jj) { const float* q = s_red + (jj * Cb + t) * 3; const float dd = q[1] - mu; M2 += q[2] + q[0] * dd * dd; }
+            n = Sn;
+            const int cl = cb + t;
+            const float var = M2 / n;
+            const float inv = rsqrtf(var + d.eps);
+            const float g = d.gamma ? d.gamma[cl] : 1.0f, b = d.beta ? d.beta[cl] : 0.0f;
+            const float sc = g * inv, sh = b - mu * g * inv;
+            s_scale[cl] = sc; s_shift[cl] = sh;
+            if (writer) {
+                g_scale[cl] = sc; g_shift[cl] = sh;
+                d.mean[cl] = mu; d.invstd[cl] = inv;
+                if (d.running_mean) {
+                    d.running_mean[cl] = (1.0f - d.momentum) * d.running_mean[cl] + d.momentum * mu;
+                    d.running_var[cl] = (1.0f - d.momentum) * d.running_var[cl] + d.momentum * (n > 1.0f ? M2 / (n - 1.0f) : var);
+                }
+                if (cl == 0 && d.num_batches_tracked) *d.num_batches_tracked += 1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// shared prologue of the apply kernels: returns the ApplyArgs to use (scale / shift redirected to shared memory when deferred)
+#define PV2_APPLY_DEFER_PROLOGUE(a, df, la)                                                                             \
+    __shared__ __align__(16) float s_aff[2][2][DEFER_MAX_C];                                                            \
+    __shared__ float s_red[256 * 3];                                                                                    \
+    ApplyArgs la = a;                                                                                                   \
+    if (df.d[0].part) {                                                                                                 \
+        bn_fold_deferred(df.d[0], a.C, s_aff[0][0], s_aff[0][1], s_red, blockIdx.x == 0, const_cast<float*>(a.s1), const_cast<float*>(a.b1)); \
+        la.s1 = s_aff[0][0]; la.b1 = s_aff[0][1];                                                                       \
+    }                                                                                                                   \
+    if (df.d[1].part) {                                                                                                 \
+        bn_fold_deferred(df.d[1], a.C, s_aff[1][0], s_aff[1][1], s_red, blockIdx.x == 0, const_cast<float*>(a.s2), const_cast<float*>(a.b2)); \
+        la.s2 = s_aff[1][0]; la.b2 = s_aff[1][1];                                                                       \
+    }
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
-act_apply_kernel(const ApplyArgs a) {
+act_apply_kernel(const ApplyArgs a0, const Defer2 df) {
     pv2::pdl_prologue();
+    PV2_APPLY_DEFER_PROLOGUE(a0, df, a)
     const long long total = a.M * a.C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long r = e / a.C;
@@ -640,12 +733,15 @@ __device__ __forceinline__ float4 slab_sum4(const Slabs& s, long long row, int c
     return v;
 }
 
+// scale / shift vectors may live in shared memory (deferred BatchNorm fold): generic loads, not ld.global.nc
+__device__ __forceinline__ float4 f4_ldp(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
 template <int KIND>
 __device__ __forceinline__ float4 apply_value4(const ApplyArgs& a, long long r, int c, float4* a1o, float4* a2o, float4* mo) {
-    const float4 a1 = f4_fma(raw_load4(a.y1, a.ld1, a.off1, a.ns1, a.ss1, r, c), f4_ld(a.s1 + c), f4_ld(a.b1 + c));
+    const float4 a1 = f4_fma(raw_load4(a.y1, a.ld1, a.off1, a.ns1, a.ss1, r, c), f4_ldp(a.s1 + c), f4_ldp(a.b1 + c));
     float4 a2 = f4_set(0.0f), v = a1;
     if (a.combine) {
-        a2 = f4_fma(raw_load4(a.y2, a.ld2, a.off2, a.ns2, a.ss2, r, c), f4_ld(a.s2 + c), f4_ld(a.b2 + c));
+        a2 = f4_fma(raw_load4(a.y2, a.ld2, a.off2, a.ns2, a.ss2, r, c), f4_ldp(a.s2 + c), f4_ldp(a.b2 + c));
         v = a.combine == 1 ? f4_add(a1, a2) : f4_mul(a1, a2);
     }
     float4 m = f4_set(1.0f);
@@ -656,8 +752,9 @@ __device__ __forceinline__ float4 apply_value4(const ApplyArgs& a, long long r, 
 
 template <int KIND>
 __global__ void __launch_bounds__(256)
-act_apply4_kernel(const ApplyArgs a) {
+act_apply4_kernel(const ApplyArgs a0, const Defer2 df) {
     pv2::pdl_prologue();
+    PV2_APPLY_DEFER_PROLOGUE(a0, df, a)
     const unsigned C4 = (unsigned)a.C >> 2;
     const unsigned total = (unsigned)a.M * C4;
     for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += gridDim.x * 256u) {
@@ -1038,7 +1135,9 @@ extern "C" size_t pv2_bn_fuse_workspace_floats(long long M, int Cout) {
     const long long fused = m_tiles * Cout * 2 + (long long)fp.ngroups * Cout * 3;       // conv epilogue: tile + group partials
     const int rows = pick_rows(M, Cout);
     const long long standalone = ((M + rows - 1) / rows) * Cout * 3;                       // pv2_bn_stats_group row-block partials
-    return (size_t)(fused > standalone ? fused : standalone);
+    const long long deferred = 2LL * kNumSMs * Cout * 4;                                   // persistent conv: one (count, mean, M2, -) row per CTA
+    const long long need = fused > standalone ? fused : standalone;
+    return (size_t)(need > deferred ? need : deferred);
 }
 
 extern "C" int pv2_bn_stats_group(float* y, long long slab_stride, int nslabs, long long M, int Cout, int ld, const pv2_bn_fuse* bn, void* stream) {
@@ -1095,21 +1194,36 @@ extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long l
                              const float* y2, int ld2, int off2, int ns2, long long ss2,
                              const float* s2, const float* b2, int combine, const void* mult, long long mult_plane, int mult_planes,
                              int mult_ld, int mult_off, int relu, long long M, int C, int HW, void* out, long long out_plane,
-                             int out_planes, int out_ld, int out_off, int out_nchw, int kind, void* stream) {
+                             int out_planes, int out_ld, int out_off, int out_nchw, const pv2_bn_defer* d1, const pv2_bn_defer* d2,
+                             int kind, void* stream) {
     PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "act_apply: bad operand kind %d", kind);
+    Defer2 df = {};
+    if (d1) df.d[0] = *d1;
+    if (d2) df.d[1] = *d2;
+    const bool deferred = df.d[0].part != nullptr || df.d[1].part != nullptr;
+    for (int i = 0; i < 2; ++i) {
+        const pv2_bn_defer& d = df.d[i];
+        if (!d.part) continue;
+        PV2_CHECK(C <= DEFER_MAX_C, "act_apply: a deferred BatchNorm fold handles at most %d channels per slice (got %d)", DEFER_MAX_C, C);
+        PV2_CHECK(d.nparts >= 1 && d.ldc >= d.c_off + C && d.mean && d.invstd && (((uintptr_t)d.part) & 15) == 0,
+                  "act_apply: incomplete pv2_bn_defer descriptor");
+        PV2_CHECK(i == 0 ? (s1 && b1) : (combine && s2 && b2), "act_apply: deferred fold needs the scale / shift output arrays");
+    }
     ApplyArgs a;
     if (int e = fill_apply(&a, y1, ld1, off1, ns1, ss1, s1, b1, y2, ld2, off2, ns2, ss2, s2, b2, combine, mult, mult_plane, mult_planes, mult_ld, mult_off, relu, M, C, HW)) return e;
     PV2_CHECK(out != nullptr, "act_apply: null output");
     a.out = out; a.out_plane = out_plane; a.out_planes = out_planes; a.out_ld = out_ld; a.out_off = out_off; a.out_nchw = out_nchw;
     const long long total = M * C;
+    // every CTA repeats the deferred fold (nparts x C rows from L2): keep the grid at two CTAs per SM then
+    auto grid_of = [&](long long work) { const int g = grid_for(work); return (deferred && g > 2 * kNumSMs) ? 2 * kNumSMs : g; };
     if (!out_nchw && apply_vec_ok(a) && out_ld % 4 == 0 && out_off % 4 == 0 && al16(out)) {
-        if (kind == PV2_BF16) pv2::launch(act_apply4_kernel<0>, grid_for(total / 4), 256, 0, (cudaStream_t)stream, a);
-        else pv2::launch(act_apply4_kernel<1>, grid_for(total / 4), 256, 0, (cudaStream_t)stream, a);
+        if (kind == PV2_BF16) pv2::launch(act_apply4_kernel<0>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
+        else pv2::launch(act_apply4_kernel<1>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
         PV2_LAUNCH_CHECK("act_apply4");
         return 0;
     }
-    if (kind == PV2_BF16) pv2::launch(act_apply_kernel<0>, grid_for(total), 256, 0, (cudaStream_t)stream, a);
-    else pv2::launch(act_apply_kernel<1>, grid_for(total), 256, 0, (cudaStream_t)stream, a);
+    if (kind == PV2_BF16) pv2::launch(act_apply_kernel<0>, grid_of(total), 256, 0, (cudaStream_t)stream, a, df);
+    else pv2::launch(act_apply_kernel<1>, grid_of(total), 256, 0, (cudaStream_t)stream, a, df);
     PV2_LAUNCH_CHECK("act_apply");
     return 0;
 }

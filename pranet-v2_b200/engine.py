@@ -35,7 +35,11 @@ _BNSEG_DT = np.dtype([("gamma", "u8"), ("beta", "u8"), ("rm", "u8"), ("rv", "u8"
                       ("c_begin", "i4"), ("c_end", "i4")], align=True)                                  # == pv2_bn_seg (56 B)
 _BNFUSE_DT = np.dtype([("seg", _BNSEG_DT, (8,)), ("mean", "u8"), ("invstd", "u8"), ("scale", "u8"), ("shift", "u8"), ("part", "u8"),
                        ("counters", "u8"), ("nsegs", "i4"), ("pad_", "i4")], align=True)                 # == pv2_bn_fuse (504 B)
+_BNDEFER_DT = np.dtype([("part", "u8"), ("nparts", "i4"), ("ldc", "i4"), ("c_off", "i4"), ("pad_", "i4"), ("gamma", "u8"), ("beta", "u8"),
+                        ("rm", "u8"), ("rv", "u8"), ("nbt", "u8"), ("eps", "f4"), ("momentum", "f4"), ("mean", "u8"), ("invstd", "u8")],
+                       align=True)                                                                      # == pv2_bn_defer (88 B)
 assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.itemsize == 56 and _BNFUSE_DT.itemsize == 504
+assert _BNDEFER_DT.itemsize == 88
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
 
 
@@ -66,6 +70,17 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def _feat_dt(t: torch.Tensor, who: str) -> int:
+    """PV2 dtype code of a feature / gradient tensor handed to the kernels: fp32 or bf16 only.  Anything else (fp16 from
+    torch.autocast's default dtype, fp64 ...) must never be reinterpreted as bf16 bits."""
+    if t.dtype == torch.float32:
+        return PV2_F32
+    if t.dtype == torch.bfloat16:
+        return PV2_BF16
+    raise TypeError(f"pranet_v2_b200 {who}: tensor dtype {t.dtype} is not supported by the pv2 kernels (fp32 or bf16 only); "
+                    "use torch.autocast('cuda', dtype=torch.bfloat16) or cast the features")
+
+
 class Act:
     """Operand-format activation: NHWC, `ld` stored channels (padded), bf16 [N,H,W,ld] or fp32 [planes,N,H,W,ld].
     May be a channel slice [off, off+C) of a wider (concat) buffer."""
@@ -85,7 +100,7 @@ class Act:
 
 class Raw:
     """Raw conv output: fp32 [splits, M, ld]; after bn_stats slab 0 holds the split sum."""
-    __slots__ = ("t", "splits", "M", "ld", "C", "dy", "N", "H", "W", "stats", "stat_bns")
+    __slots__ = ("t", "splits", "M", "ld", "C", "dy", "N", "H", "W", "stats", "stat_bns", "defer")
 
     def __init__(self, t, splits, N, H, W, ld, C):
         self.t, self.splits, self.N, self.H, self.W, self.ld, self.C = t, splits, N, H, W, ld, C
@@ -93,6 +108,7 @@ class Raw:
         self.dy = None            # operand-format gradient w.r.t. this raw output (set by the apply backward)
         self.stats = None         # fp32 [4][C]: batch mean, invstd, scale, shift of every channel (training BN, produced with the conv)
         self.stat_bns = {}        # channel offset -> BatchNorm module whose statistics `stats` holds there
+        self.defer = None         # persistent conv kernel: {"part", "nparts", "pending": offsets whose per-CTA partial rows are not folded yet}
 
 
 class Map:
@@ -284,7 +300,7 @@ class Engine:
         else:
             xc = x.contiguous()
             a = self.new_act(N, H, W, Cc)
-            _lib.check(self.lib.pv2_pack_nchw(xc.data_ptr(), PV2_F32 if xc.dtype == torch.float32 else PV2_BF16, a.t.data_ptr(),
+            _lib.check(self.lib.pv2_pack_nchw(xc.data_ptr(), _feat_dt(xc, "from_nchw"), a.t.data_ptr(),
                                               self.plane_stride(a), self.planes, self.kind, N, Cc, H * W, a.ld, 0, _stream()), "pv2_pack_nchw")
         if self.need_grad and grad_sink is not None:
             cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
@@ -312,7 +328,7 @@ class Engine:
 
     def _unpack_slabs(self, slabs, dx, N, Cc, HW, channels_last=False):
         pp, lds, offs, keep = self._slab_arrays(slabs)
-        _lib.check(self.lib.pv2_unpack_to_nchw(pp, lds, offs, len(slabs), dx.data_ptr(), PV2_F32 if dx.dtype == torch.float32 else PV2_BF16,
+        _lib.check(self.lib.pv2_unpack_to_nchw(pp, lds, offs, len(slabs), dx.data_ptr(), _feat_dt(dx, "_unpack_slabs"),
                                                N, Cc, HW, int(channels_last), _stream()), "pv2_unpack_to_nchw")
 
     # ---- weights: every conv group of the head packed by ONE multi-tensor launch ------------------------------------------
@@ -455,27 +471,34 @@ class Engine:
             assert len(convs) == 1
             out = self.f32(N, Cout, H, W)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(x), self.plane_stride(x), w_op.data_ptr(), Cout * taps * Cin_p, self.kind, self.nterms,
-                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 1, out.data_ptr(), 0, 1, _ptr(c0.bias), None, st), "pv2_conv_fwd")
+                                        N, H, W, Cin_p, Cout, KH, KW, dh, dw, 1, out.data_ptr(), 0, 1, _ptr(c0.bias), None, None, st), "pv2_conv_fwd")
             res = Map(out)
         else:
             ld = (Cout + 3) // 4 * 4
             splits = lib.pv2_conv_splits_hint(N, H, W, Cin_p, Cout, KH, KW, self.kind, self.nterms)
-            raw_t = self.f32(splits, N * H * W, ld)
+            sums = bool(lib.pv2_conv_sums_splits())       # split-K partials are added into ONE zero-initialised slab by the kernel
+            raw_t = self.f32(1, N * H * W, ld, zero=True) if (sums and splits > 1) else self.f32(splits, N * H * W, ld)
             fuse = None
             if self.training and bns is not None and any(b is not None for b in bns):
                 fuse, stats, seg_of, hold = self._bn_fuse(convs, list(bns), N * H * W, Cout)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(x), self.plane_stride(x), w_op.data_ptr(), Cout * taps * Cin_p, self.kind, self.nterms,
                                         N, H, W, Cin_p, Cout, KH, KW, dh, dw, 0, raw_t.data_ptr(), ld, splits, None,
-                                        fuse.ctypes.data if fuse is not None else None, st), "pv2_conv_fwd")
-            res = Raw(raw_t, splits, N, H, W, ld, Cout)
+                                        fuse.ctypes.data if fuse is not None else None, _ticket_counters(self.dev, self.cur).data_ptr(), st),
+                       "pv2_conv_fwd")
+            # the persistent kernel sums the split-K slabs itself (total in slab 0; the other slabs are scratch)
+            res = Raw(raw_t, 1 if sums else splits, N, H, W, ld, Cout)
             if self.need_grad and len(convs) > 1:
                 # the gradient buffer of a horizontally fused group is filled slice by slice, possibly from several branches:
                 # allocate (and zero its padding) here, on the forward stream, not lazily inside one of them
                 res.dy = self.new_act(N, H, W, Cout)
             if fuse is not None:
-                if not lib.pv2_conv_fuses_bn_stats(splits, 0):      # split-K (or patch tiles): one grouped pass, sums the slabs into slab 0
+                how = lib.pv2_conv_fuses_bn_stats(splits, 0)
+                if not how:      # split-K (or patch tiles): one grouped pass, sums the slabs into slab 0
                     _lib.check(lib.pv2_bn_stats_group(raw_t.data_ptr(), N * H * W * ld, splits, N * H * W, Cout, ld, fuse.ctypes.data, st),
                                "pv2_bn_stats_group")
+                elif how == 2:   # per-CTA partial rows: folded by the first kernel that consumes each BatchNorm's channel slice
+                    res.defer = {"part": hold[0], "nparts": lib.pv2_conv_stats_parts(N, H, W, Cin_p, Cout, KH, KW, self.kind, self.nterms, splits),
+                                 "pending": set(seg_of.keys())}
                 res.stats, res.stat_bns = stats, seg_of
         if self.need_grad:
             self.tape.append(lambda: self._conv_bwd(x, convs, res, KH, KW, dh, dw, Cin, Cin_p, Cout))
@@ -542,13 +565,15 @@ class Engine:
                 dxf = torch.empty((N, Cin, H, W), dtype=torch.bfloat16, device=self.dev, memory_format=torch.channels_last)
                 self._keep.append(dxf)
                 _lib.check(lib.pv2_conv_fwd(self._act_ptr(dy), self.plane_stride(dy), wt.data_ptr(), Cin * taps * Cout_p, self.kind, self.nterms,
-                                            N, H, W, Cout_p, Cin, KH, KW, dh, dw, 2, dxf.data_ptr(), Cin, 1, None, None, st), "pv2_conv_fwd(dgrad, bf16)")
+                                            N, H, W, Cout_p, Cin, KH, KW, dh, dw, 2, dxf.data_ptr(), Cin, 1, None, None, None, st), "pv2_conv_fwd(dgrad, bf16)")
                 x.direct["dx"] = dxf
                 return
-            dx = self.f32(splits, N * H * W, ld)
+            sums = bool(lib.pv2_conv_sums_splits())
+            dx = self.f32(1, N * H * W, ld, zero=True) if (sums and splits > 1) else self.f32(splits, N * H * W, ld)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(dy), self.plane_stride(dy), wt.data_ptr(), Cin * taps * Cout_p, self.kind, self.nterms,
-                                        N, H, W, Cout_p, Cin, KH, KW, dh, dw, 0, dx.data_ptr(), ld, splits, None, None, st), "pv2_conv_fwd(dgrad)")
-            for s in range(splits):
+                                        N, H, W, Cout_p, Cin, KH, KW, dh, dw, 0, dx.data_ptr(), ld, splits, None, None,
+                                        _ticket_counters(self.dev, self.cur).data_ptr(), st), "pv2_conv_fwd(dgrad)")
+            for s in range(1 if sums else splits):
                 x.gslabs.append((dx[s], ld, 0))
 
     # ---- BN (+ combine, multiplier, relu) -> operand slice or NCHW map -------------------------------------------
@@ -562,17 +587,27 @@ class Engine:
                 shift.copy_(bias.detach())
             else:
                 shift.zero_()
-            return scale, shift, None, None
+            return scale, shift, None, None, None
         if self.training:
             raise RuntimeError("internal: training-mode BN statistics are computed per Raw, see bn_apply")
         _lib.check(lib.pv2_bn_eval_affine(C, _ptr(bn.weight), _ptr(bn.bias), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
                                           float(bn.eps), scale.data_ptr(), shift.data_ptr(), st), "pv2_bn_eval_affine")
-        return scale, shift, None, None
+        return scale, shift, None, None, None
 
     def _bn_train_stats(self, raw: Raw, off, C, bn):
         if raw.stats is not None and raw.stat_bns.get(off) is bn:      # produced together with the conv
             st4 = raw.stats
-            return st4[2, off:off + C], st4[3, off:off + C], st4[0, off:off + C], st4[1, off:off + C]
+            d = None
+            if raw.defer is not None and off in raw.defer["pending"]:
+                # still per-CTA partial rows: this consumer folds them (pv2_bn_defer) and publishes the four vectors
+                raw.defer["pending"].discard(off)
+                track = bn.track_running_stats and bn.running_mean is not None
+                d = np.zeros(1, dtype=_BNDEFER_DT)
+                d[0] = (raw.defer["part"].data_ptr(), raw.defer["nparts"], raw.C, off, 0, _ptr(bn.weight) or 0, _ptr(bn.bias) or 0,
+                        bn.running_mean.data_ptr() if track else 0, bn.running_var.data_ptr() if track else 0,
+                        bn.num_batches_tracked.data_ptr() if track else 0, float(bn.eps), 0.1 if bn.momentum is None else float(bn.momentum),
+                        st4[0, off:off + C].data_ptr(), st4[1, off:off + C].data_ptr())
+            return st4[2, off:off + C], st4[3, off:off + C], st4[0, off:off + C], st4[1, off:off + C], d
         lib, st = self.lib, _stream()
         scale, shift, mean, inv = self.f32(C), self.f32(C), self.f32(C), self.f32(C)
         ws = self.f32(lib.pv2_bn_workspace_floats(raw.M, C))
@@ -582,7 +617,7 @@ class Engine:
                                     float(bn.eps), mom, _ptr(bn.running_mean) if track else None, _ptr(bn.running_var) if track else None,
                                     _ptr(bn.num_batches_tracked) if track else None, mean.data_ptr(), inv.data_ptr(), scale.data_ptr(),
                                     shift.data_ptr(), ws.data_ptr(), st), "pv2_bn_stats")
-        return scale, shift, mean, inv
+        return scale, shift, mean, inv, None
 
     def bn_apply(self, src1, src2=None, combine=0, mult: Act = None, relu=False, out: Act = None, out_map=False):
         """src = (raw, channel offset, C, bn module or None, bias or None).  Writes into `out` (an Act or Act slice) or
@@ -596,8 +631,8 @@ class Engine:
                 stats.append(self._bn_train_stats(raw, off, c, bn))      # also folds the split-K slabs into slab 0
             else:
                 stats.append(self._affine(raw, off, c, bn, bias))
-        (s1, b1, m1, i1) = stats[0]
-        (s2, b2, m2, i2) = stats[1] if src2 else (None, None, None, None)
+        (s1, b1, m1, i1, df1) = stats[0]
+        (s2, b2, m2, i2, df2) = stats[1] if src2 else (None, None, None, None, None)
         raw2, off2 = (src2[0], src2[1]) if src2 else (None, 0)
         M, HW = raw1.M, raw1.H * raw1.W
         if out_map:
@@ -617,7 +652,9 @@ class Engine:
                     _ptr(s2), _ptr(b2), combine,
                     (mult.t.data_ptr() if mult is not None else None), self.plane_stride(mult) if mult is not None else 0,
                     self.planes, mult.ld if mult is not None else 0, mult.off if mult is not None else 0, int(relu), M, Cc, HW)
-        _lib.check(lib.pv2_act_apply(*fwd_args, o_ptr, o_plane, o_planes, o_ld, o_off, o_nchw, self.kind, st), "pv2_act_apply")
+        _lib.check(lib.pv2_act_apply(*fwd_args, o_ptr, o_plane, o_planes, o_ld, o_off, o_nchw,
+                                     df1.ctypes.data if df1 is not None else None, df2.ctypes.data if df2 is not None else None,
+                                     self.kind, st), "pv2_act_apply")
         if self.need_grad:
             keep = (s1, b1, s2, b2, m1, i1, m2, i2)
 
@@ -821,7 +858,7 @@ class Engine:
         xc = x.contiguous()
         B, Cc, h, w = xc.shape
         y = torch.empty_like(xc)
-        dt = PV2_F32 if xc.dtype == torch.float32 else PV2_BF16
+        dt = _feat_dt(xc, "ra_v1")
         _lib.check(lib.pv2_ra_v1_scale_fwd(xc.data_ptr(), crop.t.data_ptr(), y.data_ptr(), B, Cc, h * w, dt, _stream()), "pv2_ra_v1_scale_fwd")
 
         def sink(dy):
@@ -892,13 +929,27 @@ class _HeadFn(torch.autograd.Function):
         outs = runner(eng, inputs, in_grads)
         if cache is not None and "groups" not in cache:
             cache["groups"] = eng.groups_seen
-        ctx.eng, ctx.in_grads, ctx.params, ctx.outs = eng, in_grads, params, outs
+        res = tuple(o.t for o in outs)
+        if need_grad:
+            # The returned tensor OBJECTS must not be reachable from ctx (output -> grad_fn -> ctx -> output is a cycle that would
+            # pin every activation of a forward that is never backpropagated until the cycle collector runs): the tape's Maps keep
+            # detached aliases of the same storage (backward closures of the fusion kernels still read them).
+            for o in outs:
+                o.t = o.t.detach()
+            ctx.eng, ctx.in_grads, ctx.params, ctx.outs = eng, in_grads, params, outs
+        else:
+            eng._keep = []
+            ctx.eng = ctx.outs = None
+            ctx.in_grads, ctx.params = in_grads, params
         ctx.n_inputs = n_inputs
-        return tuple(o.t for o in outs)
+        return res
 
     @staticmethod
     def backward(ctx, *gouts):
         eng = ctx.eng
+        if eng is None:
+            raise RuntimeError("pranet_v2_b200 head: backward called twice (or on a forward that recorded no tape); the engine's tape "
+                               "is consumed by the first backward -- retain_graph=True is not supported, run the forward again")
         for o, g in zip(ctx.outs, gouts):
             if g is not None:
                 o.grads.append(g)
@@ -922,8 +973,15 @@ def run_head(runner, inputs, params, training, cache=None):
     for t in inputs:
         if not t.is_cuda:
             raise RuntimeError("pranet_v2_b200 head is CUDA-only (sm_100a); got a CPU tensor and there is no CPU fallback")
+    # fp16 features (torch.autocast's default CUDA dtype, and what the reference's EMCAD / MIST trainers get from
+    # torch.cuda.amp.autocast) are converted to bf16 by a differentiable cast -- autograd casts the gradient back; any other
+    # dtype is rejected by _feat_dt.  Never reinterpret.
+    inputs = [t.to(torch.bfloat16) if t.dtype == torch.float16 else t for t in inputs]
+    for t in inputs:
+        _feat_dt(t, "run_head")
     prec = _PRECISION
     if prec == "auto":
-        prec = "bf16" if (inputs[0].dtype == torch.bfloat16 or torch.is_autocast_enabled()) else "fp32"
+        autocast_bf16 = torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16
+        prec = "bf16" if (inputs[0].dtype == torch.bfloat16 or autocast_bf16) else "fp32"
     with torch.autocast("cuda", enabled=False):
         return _HeadFn.apply(runner, len(inputs), prec, training, cache, *inputs, *params)

@@ -22,7 +22,16 @@ import torch.nn as nn
 from . import _lib, ops
 
 LOSS_FROM_LOWRES_DEFAULT = "0"    # TrainStep(loss_from_lowres=None): "1" = final upsamples fused into the loss kernels (§8 f2)
-_UNUSED_PREFIXES = ("conv.", "backbone.fc.", "resnet.fc.")   # defined by the reference nets but never used in forward
+_UNUSED_PREFIXES = ("backbone.fc.", "resnet.fc.")   # defined by the reference nets but never used in forward
+
+
+def _unused_prefixes(model) -> tuple:
+    """Parameters the model's forward never touches (frozen: they would only carry zero gradients through Adam).  The 1 -> 3
+    channel stem `conv.*` is dead in PraNet_V2 (pranet.py:328-417 never calls it) but LIVE in PVT_PraNet_V2, which applies it
+    to grayscale input (pranet.py:190-191): there it trains like every other parameter, as in the reference's Adam over
+    model.parameters()."""
+    from .models import PraNet_V2
+    return _UNUSED_PREFIXES + (("conv.",) if isinstance(model, PraNet_V2) else ())
 
 
 class FlatGradBucket:
@@ -138,8 +147,9 @@ class TrainStep:
             bb = getattr(self.model, "backbone", None) or getattr(self.model, "resnet", None)
             if bb is not None:
                 bb.to(memory_format=torch.channels_last)
+        unused = _unused_prefixes(self.model)
         for n, p in self.model.named_parameters():
-            if n.startswith(_UNUSED_PREFIXES):
+            if n.startswith(unused):
                 p.requires_grad_(False)
         self.params = [p for p in self.model.parameters() if p.requires_grad]
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
