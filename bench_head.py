@@ -136,6 +136,7 @@ def sweep_point(P, model, B, S, iters, chans, dev, lowres=False):
         feats = [f.detach().float().contiguous().requires_grad_(True) for f in feats]
     gt = synthetic.ellipse_masks(B, S, S, 3).to(dev)
     params = model.head_parameters()
+    prep_stream = torch.cuda.Stream()
 
     def step():
         for p in params:
@@ -146,8 +147,9 @@ def sweep_point(P, model, B, S, iters, chans, dev, lowres=False):
             outs = model.forward_head(*feats, lowres=True)
             loss = P.structure_loss_lowres([(outs[i], outs[i + 4]) for i in range(4)], model.final_scale_factors(), gt).sum()
         else:
+            prepared = P.ops.structure_loss_prepare(gt, prep_stream)      # mask-only boundary weight: a side branch, as in TrainStep
             outs = model.forward_head(*feats)
-            loss = P.structure_loss_multi([(outs[i], outs[i + 4]) for i in range(4)], gt).sum()
+            loss = P.structure_loss_multi([(outs[i], outs[i + 4]) for i in range(4)], gt, prepared=prepared).sum()
         loss.backward()
         return loss
 

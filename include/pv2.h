@@ -54,6 +54,14 @@ size_t pv2_structure_loss_workspace_bytes(int planes, int H, int W, int nscales)
 int pv2_structure_loss_fwd(const void* const* pred, const void* const* pred_bg, const float* mask_fg,
                            const float* mask_bg, int nscales, int planes, int H, int W, int logit_dtype,
                            float* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* The 31x31 boundary weight depends on the mask only (MyTrain_med.py:21): pv2_structure_loss_prepare computes the 16-bit weight map
+ * into `workspace` ahead of time (a training step runs it on a side branch under the backbone), and pv2_structure_loss_fwd_prepared
+ * -- same arguments as pv2_structure_loss_fwd, same workspace -- is then a pure stream over logits, mask and weight map.
+ * pv2_structure_loss_bwd works after either forward. */
+int pv2_structure_loss_prepare(const float* mask_fg, int planes, int H, int W, void* workspace, size_t workspace_bytes, void* stream);
+int pv2_structure_loss_fwd_prepared(const void* const* pred, const void* const* pred_bg, const float* mask_fg, const float* mask_bg,
+                                    int nscales, int planes, int H, int W, int logit_dtype, float* loss, void* workspace,
+                                    size_t workspace_bytes, void* stream);
 int pv2_structure_loss_bwd(const void* const* pred, const void* const* pred_bg, const float* mask_fg,
                            const float* mask_bg, const float* grad_loss, void* const* dpred,
                            void* const* dpred_bg, int nscales, int planes, int H, int W, int logit_dtype,
@@ -282,7 +290,9 @@ int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long long ss1, c
                    float* dmult, int dmult_ld, void* dy1, long long dy1_plane, int dy1_planes, int dy1_ld,
                    void* dy2, long long dy2_plane, int dy2_planes, int dy2_ld,
                    float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace,
-                   unsigned int* counters /* PV2_BN_COUNTERS zero-initialised uints (or NULL: three-launch scalar path) */, int kind, void* stream);
+                   float* sums_zeroed /* 4*C ZERO-INITIALISED floats, 16-byte aligned: the reduce pass adds its block sums there (fp32
+                                         reductions in L2, no ticket / fold) and the dx pass reads them; NULL: three-launch scalar path */,
+                   int kind, void* stream);
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (pranet.py:93) on operand tensors; backward raw -> raw */
 int pv2_up2_nhwc_fwd(const void* in, long long in_plane, int in_planes, int in_ld, int in_off, void* out, long long out_plane,
                      int out_planes, int out_ld, int out_off, int N, int H, int W, int C, int kind, void* stream);

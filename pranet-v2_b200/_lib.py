@@ -26,6 +26,8 @@ _SIGS = {
     "pv2_launch_count": (C.c_ulonglong, []),
     "pv2_structure_loss_workspace_bytes": (_sz, [_i] * 4),
     "pv2_structure_loss_fwd": (_i, [c_void_pp, c_void_pp, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pv2_structure_loss_prepare": (_i, [_p, _i, _i, _i, _p, _sz, _p]),
+    "pv2_structure_loss_fwd_prepared": (_i, [c_void_pp, c_void_pp, _p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pv2_structure_loss_bwd": (_i, [c_void_pp, c_void_pp, _p, _p, _p, c_void_pp, c_void_pp, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "pv2_structure_loss_lowres_workspace_bytes": (_sz, [_i] * 4),
     "pv2_structure_loss_lowres_fwd": (_i, [c_void_pp, c_void_pp, _ip, _ip, _fp, _fp, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),

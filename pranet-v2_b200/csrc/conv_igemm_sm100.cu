@@ -112,7 +112,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // Dependents may be scheduled only now that this CTA owns its TMEM columns: CTAs of a dependent grid co-reside with ours
     // (shallow rings leave shared memory free) and would otherwise be able to take the columns we still need while they
     // sit in griddepcontrol.wait for us -- a circular wait.
-    pdl_trigger();
+    if (PV2_PDL_EARLY) pdl_trigger();
     pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
 
     if (warp == 0 && lane == 0) {
@@ -152,6 +152,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             umma_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
         }
         umma_commit(&acc_bar);            // accumulator complete
+        pdl_done();
     } else if (warp >= 2) {
         // ---------------- epilogue: TMEM -> registers -> global ----------------
         mbar_wait(&acc_bar, 0);
@@ -316,7 +317,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 // ------------------------------------------------------------------------------------------------------
 constexpr int V2_MAX_STAGES = 12;
 constexpr int EPI_BUF_BYTES = 32 * 128;         // one warp's staging tile: 32 rows x 128 bytes
-constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES; // 4 epilogue warps x 2 buffers
+constexpr int EPI_BYTES = 4 * EPI_BUF_BYTES;     // one staging tile per epilogue warp
 
 struct ConvArgs2 {
     ConvArgs c;
@@ -357,7 +358,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     const int b_bytes = a.BN * ROW_BYTES;
     const int STAGES = a.stages;
     const int stage_bytes = A_BYTES + b_bytes;
-    uint8_t* epi = smem + (size_t)STAGES * stage_bytes;                          // [4 warps][2][32 rows][128 B]
+    uint8_t* epi = smem + (size_t)STAGES * stage_bytes;                          // [4 warps][32 rows][128 B]
     float* wstat = reinterpret_cast<float*>(epi + EPI_BYTES);                    // [4 row quarters][BN][mean, M2]
     float* cacc = wstat + 4 * a.BN * 2;                                          // [Cout][count, mean, M2] of this CTA's tiles
     __shared__ __align__(8) uint64_t full_bar[V2_MAX_STAGES], empty_bar[V2_MAX_STAGES], tfull_bar[2], tempty_bar[2];
@@ -382,7 +383,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    pdl_trigger();   // only now that this CTA owns its TMEM columns (see conv_fwd_kernel)
+    if (PV2_PDL_EARLY) pdl_trigger();   // (early mode: only now that this CTA owns its TMEM columns, see conv_fwd_kernel)
     pdl_wait();
 
     if (warp == 0 && lane == 0) {
@@ -439,15 +440,15 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
             umma_commit(&tfull_bar[buf]);
         }
+        pdl_done();      // every MMA of this CTA is issued: what is left is the last tile's epilogue, the dependent's prologue may overlap it
     } else if (warp >= 2) {
         // ---------------- epilogue ----------------
         const int q = warp & 3;                          // TMEM lane quarter of this warp
-        const uint32_t stg0 = smem_u32(epi + (size_t)(warp - 2) * 2 * EPI_BUF_BYTES);
+        const uint32_t stg = smem_u32(epi + (size_t)(warp - 2) * EPI_BUF_BYTES);
         const uint32_t my_row_off = (uint32_t)lane * 128u;
         const uint32_t sw = (uint32_t)(lane & 7);
         const int et = threadIdx.x - 64;
         int lt = 0;
-        int chunk_ctr = 0;
         // BatchNorm statistics of this warp's 32 staged rows x 32 columns (lane = column): all rows into registers, two passes
         auto stats_chunk = [&](uint32_t stg, int nvalid_w, int c0) {
             float x[32];
@@ -533,8 +534,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 continue;
             }
             const int CW = a.out_mode == 2 ? 64 : 32;       // accumulator columns per 128-byte staging row
-            for (int c0 = 0; c0 < a.BN; c0 += CW, ++chunk_ctr) {
-                const uint32_t stg = stg0 + (uint32_t)(chunk_ctr & 1) * EPI_BUF_BYTES;
+            for (int c0 = 0; c0 < a.BN; c0 += CW) {
                 uint32_t v[32];
                 // ---- TMEM -> registers -> swizzled staging rows (this lane's pixel row) ----
                 if (a.out_mode == 0) {
@@ -596,6 +596,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                             *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ldo + col) = val;
                     }
                 }
+                __syncwarp();      // the staging tile is rewritten by the next chunk
             }
             if (fix && a.stats) {
                 // split-K + BatchNorm: every split CTA has ADDED its partial tile to the output; the one that draws the tile's last
@@ -603,8 +604,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 unsigned int* cnt = a2.tile_counters + (size_t)n_tile * m_tiles + m_tile;
                 if (ticket_last(cnt, (unsigned)a2.splits, et == 0, &s_flag, 1, 128)) {
                     const int colu = lane & 7;
-                    for (int c0 = 0; c0 < a.BN; c0 += 32, ++chunk_ctr) {
-                        const uint32_t stg = stg0 + (uint32_t)(chunk_ctr & 1) * EPI_BUF_BYTES;
+                    for (int c0 = 0; c0 < a.BN; c0 += 32) {
                         const int col = n0 + c0 + colu * 4;
                         const bool col_ok = (col < n0 + a.BN) && (col + 3 < a.ldo);
                         float4 t[8];
@@ -621,6 +621,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                         }
                         __syncwarp();
                         stats_chunk(stg, nvalid_w, c0);
+                        __syncwarp();
                     }
                     tile_stats(m0, n0);
                 }
@@ -699,7 +700,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constan
     // Dependents may be scheduled only now that this CTA owns its TMEM columns: CTAs of a dependent grid co-reside with ours
     // (shallow rings leave shared memory free) and would otherwise be able to take the columns we still need while they
     // sit in griddepcontrol.wait for us -- a circular wait.
-    pdl_trigger();
+    if (PV2_PDL_EARLY) pdl_trigger();
     pdl_wait();   // everything above (barriers, TMEM, descriptor prefetch) overlapped the predecessor's tail
 
     if (warp == 0 && lane == 0) {
@@ -751,6 +752,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG0, const __grid_constan
             umma_commit(&empty_bar[s]);
         }
         umma_commit(&acc_bar);
+        pdl_done();
     } else if (warp >= 2) {
         mbar_wait(&acc_bar, 0);
         tc_fence_after();
@@ -960,14 +962,19 @@ inline size_t v2_tail_bytes(bool stats, int BN, int Cout) {     // staging tiles
 
 // Persistent launch plan of conv_fwd2_kernel: CTAs per SM (1, or 2 when a work item's K slabs are few and small), ring depth.
 struct Plan2 { int grid, stages; size_t smem; };
+// Policy.  A work item whose K slabs add up to more than ~256 KB (the level GEMMs, the 5x5 and 96-channel stacks) gets an SM to
+// itself and the deepest ring that fits (latency: as many slabs in flight as possible).  Smaller items -- the 32/64-channel
+// chains, twelve of which run concurrently in the head -- take at most half an SM, so that CTAs of two launches (or two tiles
+// of one) share it and one's epilogue / TMA round trips overlap the other's MMAs; 242-tile grids are then one resident wave.
 Plan2 plan_v2(int work_total, int slabs_per_item, size_t stage_bytes, uint32_t tmem_cols, size_t tail_bytes) {
     const int force_stages = tune_int("PV2_CONV_STAGES", 0), force_cps = tune_int("PV2_CONV_CPS", 0);
-    int cps = ((size_t)slabs_per_item * stage_bytes <= (size_t)64 * 1024 && 2u * tmem_cols <= 512u) ? 2 : 1;
+    int cps = ((size_t)slabs_per_item * stage_bytes <= (size_t)256 * 1024 && 2u * tmem_cols <= 512u) ? 2 : 1;
     if (force_cps == 1 || force_cps == 2) cps = (force_cps == 2 && 2u * tmem_cols > 512u) ? 1 : force_cps;
+    if (cps == 2 && (size_t)112 * 1024 < 1024 + tail_bytes + stage_bytes) cps = 1;
     Plan2 p;
     p.grid = work_total < kNumSMs * cps ? work_total : kNumSMs * cps;
     const int items_per_cta = (work_total + p.grid - 1) / p.grid;
-    const size_t budget = (cps == 1 ? (size_t)222 * 1024 : (size_t)110 * 1024) - 1024 - tail_bytes;   // 1 KB alignment slack
+    const size_t budget = (cps == 1 ? (size_t)226 * 1024 : (size_t)112 * 1024) - 1024 - tail_bytes;   // 1 KB alignment slack
     int st = (int)(budget / stage_bytes);
     if (st > V2_MAX_STAGES) st = V2_MAX_STAGES;
     const long long need = (long long)slabs_per_item * items_per_cta;

@@ -765,6 +765,50 @@ act_apply4_kernel(const ApplyArgs a0, const Defer2 df) {
         if (a.relu) v = make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
         store_op4<KIND>(a.out, a.out_plane, a.out_planes, (long long)r * a.out_ld + a.out_off + c, v);
     }
+    pv2::pdl_done();
+}
+
+// Deferred-fold form of the vector apply: CTA = (row chunk, group of 16 channels).  A CTA folds the per-CTA partial rows of ITS
+// 16 channels only (<= 296 x 16 rows of 16 bytes: one batch of independent loads per thread whatever the slice width -- with the
+// flat layout above every CTA would fold all C channels, ~4 batches at C = 96) and then streams its rows: 64 B of fp32 raw in,
+// 32 B of bf16 operand out per row, whole sectors both ways.  The CTAs of row chunk 0 publish the statistics.
+constexpr int APPLY_CG = 16;
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+act_apply4_cg_kernel(const ApplyArgs a0, const Defer2 df) {
+    pv2::pdl_prologue();
+    __shared__ __align__(16) float s_aff[2][2][APPLY_CG];
+    __shared__ float s_red[256 * 3];
+    const int c0 = blockIdx.y * APPLY_CG;
+    const int Cg = min(APPLY_CG, a0.C - c0);
+    ApplyArgs a = a0;       // channel-indexed fields shifted to this group: local channel 0 .. Cg-1
+    a.off1 += c0; a.off2 += c0; a.mult_off += c0; a.out_off += c0;
+    a.s1 += c0; a.b1 += c0;
+    if (a.combine) { a.s2 += c0; a.b2 += c0; }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (!df.d[i].part) continue;
+        pv2_bn_defer d = df.d[i];
+        d.c_off += c0;
+        if (d.gamma) d.gamma += c0;
+        if (d.beta) d.beta += c0;
+        if (d.running_mean) { d.running_mean += c0; d.running_var += c0; }
+        if (blockIdx.y != 0) d.num_batches_tracked = nullptr;
+        d.mean += c0; d.invstd += c0;
+        bn_fold_deferred(d, Cg, s_aff[i][0], s_aff[i][1], s_red, blockIdx.x == 0,
+                         const_cast<float*>(i == 0 ? a.s1 : a.s2), const_cast<float*>(i == 0 ? a.b1 : a.b2));
+        if (i == 0) { a.s1 = s_aff[0][0]; a.b1 = s_aff[0][1]; } else { a.s2 = s_aff[1][0]; a.b2 = s_aff[1][1]; }
+    }
+    const int c = (threadIdx.x & 3) << 2;
+    if (c >= Cg) return;
+    for (long long r = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); r < a.M; r += (long long)gridDim.x * 64) {
+        float4 a1, a2, m;
+        float4 v = apply_value4<KIND>(a, r, c, &a1, &a2, &m);
+        if (a.relu) v = make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
+        store_op4<KIND>(a.out, a.out_plane, a.out_planes, r * a.out_ld + a.out_off + c, v);
+    }
+    pv2::pdl_done();
 }
 
 struct Da4 { float4 da1, da2, yh1, yh2, dm; };
@@ -795,17 +839,17 @@ __device__ __forceinline__ Da4 bwd_da4(const BwdArgs& b, long long r, int c) {
     return o;
 }
 
-// reduce pass, vector form.  block = RP rows x C4 channel quads; the row-block partials are folded by the CTA that draws the
-// last ticket (two levels, fixed order) into sums[4][C] = (sum da1, sum da1*yhat1, sum da2, sum da2*yhat2) -- which are also
-// dbeta / dgamma -- so no finalize launch follows.
-struct Reduce4Plan { int nblk, rows_pb, RP, G, ngroups; unsigned int* counters; float* gpart; float* dg1; float* db1; float* dg2; float* db2; float* sums_out; };
+// reduce pass, vector form.  block = RP rows x C4 channel quads; each block folds its rows in shared memory and ADDS its
+// 4 x C block sums to sums[4][C] = (sum da1, sum da1*yhat1, sum da2, sum da2*yhat2) -- which are also dbeta / dgamma -- with fp32
+// reductions in L2 (sums must be zero on entry).  No ticket, no fence, no serial fold: the dx pass reads the finished sums.
+// (The <= 296 block sums per value are added in arrival order: results agree to fp32 rounding, not bit for bit.)
+struct Reduce4Plan { int nblk, rows_pb, RP; float* dg1; float* db1; float* dg2; float* db2; float* sums_out; };
 
 template <int KIND>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce4_kernel(const BwdArgs b, const Reduce4Plan pl) {
     pv2::pdl_prologue();
     __shared__ float sh[256 * 17];     // pitch 17: conflict-free writes (thread-major) and reads (value-major)
-    __shared__ int s_flag;
     const int C = b.f.C, C4 = C >> 2;
     const int tid = threadIdx.x;
     const int quad = tid % C4, rp = tid / C4;
@@ -813,55 +857,58 @@ bn_bwd_reduce4_kernel(const BwdArgs b, const Reduce4Plan pl) {
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+    auto add = [&](const Da4& d) {
+        acc[0] += d.da1.x; acc[1] += d.da1.y; acc[2] += d.da1.z; acc[3] += d.da1.w;
+        acc[4] = fmaf(d.da1.x, d.yh1.x, acc[4]); acc[5] = fmaf(d.da1.y, d.yh1.y, acc[5]);
+        acc[6] = fmaf(d.da1.z, d.yh1.z, acc[6]); acc[7] = fmaf(d.da1.w, d.yh1.w, acc[7]);
+        acc[8] += d.da2.x; acc[9] += d.da2.y; acc[10] += d.da2.z; acc[11] += d.da2.w;
+        acc[12] = fmaf(d.da2.x, d.yh2.x, acc[12]); acc[13] = fmaf(d.da2.y, d.yh2.y, acc[13]);
+        acc[14] = fmaf(d.da2.z, d.yh2.z, acc[14]); acc[15] = fmaf(d.da2.w, d.yh2.w, acc[15]);
+    };
     if (rp < pl.RP) {
         const int c = quad << 2;
-        for (long long r = r0 + rp; r < r1; r += pl.RP) {
-            const Da4 d = bwd_da4<KIND>(b, r, c);
-            acc[0] += d.da1.x; acc[1] += d.da1.y; acc[2] += d.da1.z; acc[3] += d.da1.w;
-            acc[4] = fmaf(d.da1.x, d.yh1.x, acc[4]); acc[5] = fmaf(d.da1.y, d.yh1.y, acc[5]);
-            acc[6] = fmaf(d.da1.z, d.yh1.z, acc[6]); acc[7] = fmaf(d.da1.w, d.yh1.w, acc[7]);
-            acc[8] += d.da2.x; acc[9] += d.da2.y; acc[10] += d.da2.z; acc[11] += d.da2.w;
-            acc[12] = fmaf(d.da2.x, d.yh2.x, acc[12]); acc[13] = fmaf(d.da2.y, d.yh2.y, acc[13]);
-            acc[14] = fmaf(d.da2.z, d.yh2.z, acc[14]); acc[15] = fmaf(d.da2.w, d.yh2.w, acc[15]);
-            if (b.dmult) *reinterpret_cast<float4*>(b.dmult + r * b.dmult_ld + c) = d.dm;
+        // two rows per trip: their loads are independent, and the d(mult) stores no longer sit between one row's loads and the next's
+        for (long long r = r0 + rp; r < r1; r += 2 * pl.RP) {
+            const long long rb = r + pl.RP;
+            const bool two = rb < r1;
+            const Da4 d0 = bwd_da4<KIND>(b, r, c);
+            const Da4 d1 = bwd_da4<KIND>(b, two ? rb : r, c);
+            add(d0);
+            if (b.dmult) *reinterpret_cast<float4*>(b.dmult + r * b.dmult_ld + c) = d0.dm;
+            if (two) {
+                add(d1);
+                if (b.dmult) *reinterpret_cast<float4*>(b.dmult + rb * b.dmult_ld + c) = d1.dm;
+            }
         }
     }
+    pv2::pdl_done();
 #pragma unroll
     for (int i = 0; i < 16; ++i) sh[tid * 17 + i] = acc[i];
     __syncthreads();
+    const int nk = b.f.combine ? 16 : 8;          // sums 2, 3 belong to the second source
     // (quad, k) -> sum over the RP row lanes in order; k = 4*which_sum + channel
     for (int idx = tid; idx < C4 * 16; idx += 256) {
         const int qd = idx >> 4, k = idx & 15;
+        if (k >= nk) continue;
         float t = 0.0f;
         for (int j = 0; j < pl.RP; ++j) t += sh[(j * C4 + qd) * 17 + k];
-        b.part[((long long)blockIdx.x * 4 + (k >> 2)) * C + (qd << 2) + (k & 3)] = t;
-    }
-    const int g = blockIdx.x / pl.G;
-    const int b0 = g * pl.G, b1 = min(b0 + pl.G, pl.nblk);
-    if (!ticket_last(pl.counters + g, (unsigned)(b1 - b0), tid == 0, &s_flag, 1, 256)) return;
-    const int nv = b.f.combine ? 4 * C : 2 * C;       // sums 2, 3 belong to the second source
-    const bool single = pl.ngroups == 1;              // few row blocks: the group fold is already the final one
-    if (!single) {
-        for (int i = tid; i < nv; i += 256)           // one thread per value, the group's row-block partials loaded as one batch
-            pl.gpart[(long long)g * 4 * C + i] = fold_sum(b.part + i, 4LL * C, b0, b1);
-        if (!ticket_last(pl.counters + pl.ngroups, (unsigned)pl.ngroups, tid == 0, &s_flag, 1, 256)) return;
-    }
-    for (int i = tid; i < nv; i += 256) {
-        const float t = single ? fold_sum(b.part + i, 4LL * C, b0, b1) : fold_sum(pl.gpart + i, 4LL * C, 0, pl.ngroups);
-        pl.sums_out[i] = t;
-        const int k = i / C, c = i - k * C;
-        if (k == 0 && pl.db1) pl.db1[c] = t;
-        if (k == 1 && pl.dg1) pl.dg1[c] = t;
-        if (k == 2 && pl.db2) pl.db2[c] = t;
-        if (k == 3 && pl.dg2) pl.dg2[c] = t;
+        atomicAdd(pl.sums_out + (k >> 2) * C + (qd << 2) + (k & 3), t);
     }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(256)
-bn_bwd_dx4_kernel(const BwdArgs b) {
+bn_bwd_dx4_kernel(const BwdArgs b, const Reduce4Plan pl) {
     pv2::pdl_prologue();
     const ApplyArgs& a = b.f;
+    if (blockIdx.x == 0) {      // the finished sums ARE the parameter gradients: dbeta_i = S1_i, dgamma_i = S2_i
+        for (int i = threadIdx.x; i < a.C; i += 256) {
+            if (pl.db1) pl.db1[i] = b.sums[i];
+            if (pl.dg1) pl.dg1[i] = b.sums[a.C + i];
+            if (a.combine && pl.db2) pl.db2[i] = b.sums[2 * a.C + i];
+            if (a.combine && pl.dg2) pl.dg2[i] = b.sums[3 * a.C + i];
+        }
+    }
     const unsigned C4 = (unsigned)a.C >> 2;
     const unsigned total = (unsigned)a.M * C4;
     const float invn = 1.0f / (float)a.M;
@@ -887,6 +934,7 @@ bn_bwd_dx4_kernel(const BwdArgs b) {
         store_op4<KIND>(b.dy1, b.dy1_plane, b.dy1_planes, (long long)r * b.dy1_ld + c, d1);
         if (a.combine) store_op4<KIND>(b.dy2, b.dy2_plane, b.dy2_planes, (long long)r * b.dy2_ld + c, d2);
     }
+    pv2::pdl_done();
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -914,6 +962,7 @@ up2_nhwc_fwd_kernel(const void* in, long long in_plane, int in_planes, int in_ld
         const float v = ty.w0 * (tx.w0 * v00 + tx.w1 * v01) + ty.w1 * (tx.w0 * v10 + tx.w1 * v11);
         store_op<KIND>(out, out_plane, out_planes, ((n * OH + oy) * OW + ox) * out_ld + out_off + c, v);
     }
+    pv2::pdl_done();
 }
 
 __device__ __forceinline__ float ac_weight(int o, int i, int in_size, float ratio) {
@@ -946,6 +995,48 @@ up2_nhwc_bwd_kernel(const Slabs g, float* __restrict__ din, int din_ld, int N, i
         }
         din[((n * H + iy) * W + ix) * din_ld + c] = acc;
     }
+}
+
+// 4-channel vector form: one thread = one INPUT pixel x 4 channels.  The contributing output rows / columns and their tap
+// weights are computed once per thread (<= 7 candidates per axis, the same bilinear_tap arithmetic as the forward), then the
+// non-zero (wy * wx) taps are gathered with 16-byte loads -- ~16 independent loads per thread instead of a nested scalar
+// walk with the weights recomputed per element.  Accumulation order = (oy, ox) ascending, as in the scalar kernel.
+__global__ void __launch_bounds__(256)
+up2_nhwc_bwd4_kernel(const Slabs g, float* __restrict__ din, int din_ld, int N, int H, int W, int C, float rh, float rw) {
+    pv2::pdl_prologue();
+    constexpr int NC = 7;
+    const int OH = 2 * H, OW = 2 * W, C4 = C >> 2;
+    const long long total = (long long)N * H * W * C4;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C4) << 2;
+        long long t = e / C4;
+        const int ix = (int)(t % W); t /= W;
+        const int iy = (int)(t % H);
+        const long long n = t / H;
+        const int ylo = max(0, rh > 0.f ? (int)floorf((iy - 1) / rh) : 0), yhi = min(OH - 1, rh > 0.f ? (int)ceilf((iy + 1) / rh) : OH - 1);
+        const int xlo = max(0, rw > 0.f ? (int)floorf((ix - 1) / rw) : 0), xhi = min(OW - 1, rw > 0.f ? (int)ceilf((ix + 1) / rw) : OW - 1);
+        float wy[NC], wx[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            wy[k] = (ylo + k <= yhi) ? ac_weight(ylo + k, iy, H, rh) : 0.0f;
+            wx[k] = (xlo + k <= xhi) ? ac_weight(xlo + k, ix, W, rw) : 0.0f;
+        }
+        float4 acc = f4_set(0.0f);
+        // candidates beyond NC (ratio < 2/7: never for a x2 upsample of >= 2 pixels) fall to the tail loops below
+#pragma unroll
+        for (int a = 0; a < NC; ++a) {
+            if (wy[a] == 0.0f) continue;
+#pragma unroll
+            for (int b = 0; b < NC; ++b) {
+                if (wx[b] == 0.0f) continue;
+                const float w = wy[a] * wx[b];
+                const float4 v = slab_sum4(g, (n * OH + ylo + a) * OW + xlo + b, c);
+                acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+            }
+        }
+        *reinterpret_cast<float4*>(din + ((n * H + iy) * W + ix) * din_ld + c) = acc;
+    }
+    pv2::pdl_done();
 }
 
 inline int grid_for(long long total, int threads = 256) {
@@ -1217,6 +1308,18 @@ extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long l
     // every CTA repeats the deferred fold (nparts x C rows from L2): keep the grid at two CTAs per SM then
     auto grid_of = [&](long long work) { const int g = grid_for(work); return (deferred && g > 2 * kNumSMs) ? 2 * kNumSMs : g; };
     if (!out_nchw && apply_vec_ok(a) && out_ld % 4 == 0 && out_off % 4 == 0 && al16(out)) {
+        if (deferred) {
+            const int ncg = (C + APPLY_CG - 1) / APPLY_CG;
+            long long R = (2LL * kNumSMs + ncg - 1) / ncg;
+            const long long rmax = (M + 63) / 64;
+            if (R > rmax) R = rmax;
+            if (R < 1) R = 1;
+            const dim3 grid((unsigned)R, (unsigned)ncg);
+            if (kind == PV2_BF16) pv2::launch(act_apply4_cg_kernel<0>, grid, 256, 0, (cudaStream_t)stream, a, df);
+            else pv2::launch(act_apply4_cg_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a, df);
+            PV2_LAUNCH_CHECK("act_apply4_cg");
+            return 0;
+        }
         if (kind == PV2_BF16) pv2::launch(act_apply4_kernel<0>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
         else pv2::launch(act_apply4_kernel<1>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
         PV2_LAUNCH_CHECK("act_apply4");
@@ -1236,7 +1339,7 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
                               const float* mean1, const float* inv1, const float* mean2, const float* inv2, int bn_train,
                               float* dmult, int dmult_ld, void* dy1, long long dy1_plane, int dy1_planes, int dy1_ld,
                               void* dy2, long long dy2_plane, int dy2_planes, int dy2_ld,
-                              float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace, unsigned int* counters,
+                              float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace, float* sums_zeroed,
                               int kind, void* stream) {
     PV2_CHECK(kind == PV2_BF16 || kind == PV2_TF32, "bn_act_bwd: bad operand kind %d", kind);
     BwdArgs b = {};
@@ -1256,7 +1359,7 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
     b.dy1 = dy1; b.dy1_plane = dy1_plane; b.dy1_planes = dy1_planes; b.dy1_ld = dy1_ld;
     b.dy2 = dy2; b.dy2_plane = dy2_plane; b.dy2_planes = dy2_planes; b.dy2_ld = dy2_ld;
     {   // vector path: reduce (+ ticket fold) and dx, two launches
-        bool ok = dz_nchw == nullptr && apply_vec_ok(b.f) && dy1_ld % 4 == 0 && al16(dy1) && dy1_plane % 4 == 0 && counters != nullptr;
+        bool ok = dz_nchw == nullptr && apply_vec_ok(b.f) && dy1_ld % 4 == 0 && al16(dy1) && dy1_plane % 4 == 0 && sums_zeroed != nullptr && al16(sums_zeroed);
         if (ok && combine) ok = dy2_ld % 4 == 0 && al16(dy2) && dy2_plane % 4 == 0;
         if (ok && bn_train) ok = al16(mean1) && al16(inv1) && (!combine || (al16(mean2) && al16(inv2)));
         if (ok && b.dmult) ok = dmult_ld % 4 == 0 && al16(dmult);
@@ -1274,22 +1377,14 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
                 rows = (rows + pl.RP - 1) / pl.RP * pl.RP;
                 nblk = (M + rows - 1) / rows;
                 pl.nblk = (int)nblk; pl.rows_pb = (int)rows;
-                const FoldPlan fp = make_fold_plan(pl.nblk);
-                pl.G = fp.G; pl.ngroups = fp.ngroups;
-                PV2_CHECK(fp.ngroups + 1 <= PV2_BN_COUNTERS, "bn_act_bwd: ticket counters too small");
-                pl.counters = counters;
-                // workspace: part [nblk][4][C] | gpart [ngroups][4][C] | sums [4][C]   (pv2_bn_workspace_floats covers it)
-                b.part = workspace;
-                pl.gpart = workspace + (size_t)pl.nblk * 4 * C;
-                float* sums4 = pl.gpart + (size_t)pl.ngroups * 4 * C;
-                pl.sums_out = sums4; b.sums = sums4;
+                pl.sums_out = sums_zeroed; b.sums = sums_zeroed;
                 pl.dg1 = dgamma1; pl.db1 = dbeta1; pl.dg2 = dgamma2; pl.db2 = dbeta2;
                 b.rows_pb = pl.rows_pb;
                 cudaStream_t st4 = (cudaStream_t)stream;
                 if (kind == PV2_BF16) pv2::launch(bn_bwd_reduce4_kernel<0>, pl.nblk, 256, 0, st4, b, pl); else pv2::launch(bn_bwd_reduce4_kernel<1>, pl.nblk, 256, 0, st4, b, pl);
                 PV2_LAUNCH_CHECK("bn_bwd_reduce4");
                 const long long total4 = M * C4;
-                if (kind == PV2_BF16) pv2::launch(bn_bwd_dx4_kernel<0>, grid_for(total4), 256, 0, st4, b); else pv2::launch(bn_bwd_dx4_kernel<1>, grid_for(total4), 256, 0, st4, b);
+                if (kind == PV2_BF16) pv2::launch(bn_bwd_dx4_kernel<0>, grid_for(total4), 256, 0, st4, b, pl); else pv2::launch(bn_bwd_dx4_kernel<1>, grid_for(total4), 256, 0, st4, b, pl);
                 PV2_LAUNCH_CHECK("bn_bwd_dx4");
                 return 0;
             }
@@ -1331,6 +1426,13 @@ extern "C" int pv2_up2_nhwc_bwd(const float* const* slabs, const int* lds, const
     if (int e = fill_slabs(&s, slabs, lds, offs, nslabs, "up2_nhwc_bwd")) return e;
     PV2_CHECK(din && N > 0 && H > 0 && W > 0 && C > 0, "up2_nhwc_bwd: bad arguments");
     const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
+    bool vec = C % 4 == 0 && din_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(din) & 15u) == 0 && H >= 2 && W >= 2;
+    for (int i = 0; vec && i < s.n; ++i) vec = s.ld[i] % 4 == 0 && s.off[i] % 4 == 0 && (reinterpret_cast<uintptr_t>(s.p[i]) & 15u) == 0;
+    if (vec) {
+        pv2::launch(up2_nhwc_bwd4_kernel, grid_for((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream, s, din, din_ld, N, H, W, C, rh, rw);
+        PV2_LAUNCH_CHECK("up2_nhwc_bwd4");
+        return 0;
+    }
     pv2::launch(up2_nhwc_bwd_kernel, grid_for((long long)N * H * W * C), 256, 0, (cudaStream_t)stream, s, din, din_ld, N, H, W, C, rh, rw);
     PV2_LAUNCH_CHECK("up2_nhwc_bwd");
     return 0;

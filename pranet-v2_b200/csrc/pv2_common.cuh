@@ -40,9 +40,18 @@ void count_launch(int n = 1);
 // successor start launching immediately (launch_dependents) and waits for its predecessor's memory (wait) before it
 // touches global memory.  Inside a CUDA graph this removes most of the inter-kernel gap of the ~600 small launches a
 // head step consists of.  PV2_PDL=0 in the environment falls back to plain stream-ordered launches.
+// WHEN a kernel lets its dependents launch matters: a dependent that is launched early sits in griddepcontrol.wait holding its
+// registers / shared memory / TMEM for as long as the primary runs.  With twelve chains of the head running concurrently those
+// idle CTAs crowd out the CTAs that have work (a waiting 296-CTA apply kernel pins every SM's register file), so the default is
+// LATE: a kernel signals when its own main work is done (pdl_done) and only the dependent's launch latency and prologue overlap
+// the primary's tail.  -DPV2_PDL_EARLY=1 restores "signal first thing" (best for a single serial chain).
+#ifndef PV2_PDL_EARLY
+#define PV2_PDL_EARLY 0
+#endif
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+__device__ __forceinline__ void pdl_prologue() { if (PV2_PDL_EARLY) pdl_trigger(); pdl_wait(); }
+__device__ __forceinline__ void pdl_done() { if (!PV2_PDL_EARLY) pdl_trigger(); }
 
 bool pdl_enabled();
 // integer tuning knob from the environment, read at every call (A/B measurements inside one process); `def` when unset

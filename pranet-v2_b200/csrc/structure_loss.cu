@@ -885,9 +885,38 @@ static int check_common(const void* const* pred, const void* const* pred_bg, con
     return 0;
 }
 
+// The boundary weight weit = 1 + 5*|avgpool31(mask) - mask| (MyTrain_med.py:21) depends on the mask only, and the mask is on the device
+// before the backbone starts: a training step computes it on a side branch that forks at step start (it hides under the ~18 ms
+// backbone) and the loss forward that follows the head is then a pure stream over logits + mask + 2-byte weight map.
+extern "C" int pv2_structure_loss_prepare(const float* mask_fg, int planes, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+    PV2_CHECK(mask_fg != nullptr && planes > 0 && planes <= 65535 && H > 0 && W > 0, "structure_loss_prepare: bad arguments");
+    PV2_CHECK(workspace != nullptr && ((uintptr_t)workspace & 255u) == 0 && workspace_bytes >= pv2_structure_loss_workspace_bytes(planes, H, W, 1),
+              "structure_loss_prepare: workspace must be 256-byte aligned and pv2_structure_loss_workspace_bytes() large");
+    const Layout L = make_layout(workspace, planes, H, W);
+    pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, (cudaStream_t)stream, mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
+    PV2_LAUNCH_CHECK("boundary_weight");
+    return 0;
+}
+
+static int structure_loss_fwd_impl(const void* const* pred, const void* const* pred_bg, const float* mask_fg,
+                                   const float* mask_bg, int nscales, int planes, int H, int W, int logit_dtype,
+                                   float* loss, void* workspace, size_t workspace_bytes, void* stream, bool prepared);
+
 extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const* pred_bg, const float* mask_fg,
                                       const float* mask_bg, int nscales, int planes, int H, int W, int logit_dtype,
                                       float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+    return structure_loss_fwd_impl(pred, pred_bg, mask_fg, mask_bg, nscales, planes, H, W, logit_dtype, loss, workspace, workspace_bytes, stream, false);
+}
+
+extern "C" int pv2_structure_loss_fwd_prepared(const void* const* pred, const void* const* pred_bg, const float* mask_fg,
+                                               const float* mask_bg, int nscales, int planes, int H, int W, int logit_dtype,
+                                               float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+    return structure_loss_fwd_impl(pred, pred_bg, mask_fg, mask_bg, nscales, planes, H, W, logit_dtype, loss, workspace, workspace_bytes, stream, true);
+}
+
+static int structure_loss_fwd_impl(const void* const* pred, const void* const* pred_bg, const float* mask_fg,
+                                   const float* mask_bg, int nscales, int planes, int H, int W, int logit_dtype,
+                                   float* loss, void* workspace, size_t workspace_bytes, void* stream, bool prepared) {
     if (int e = check_common(pred, pred_bg, mask_fg, nscales, planes, H, W, logit_dtype, workspace, workspace_bytes)) return e;
     PV2_CHECK(loss != nullptr, "structure_loss_fwd: null loss pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -896,7 +925,7 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
     for (int k = 0; k < nscales; ++k) { pp.pred[k] = pred[k]; pp.pred_bg[k] = pred_bg[k]; }
     const int HW = H * W;
     const bool vec = can_vec(pp, nscales, mask_fg, mask_bg, HW, false);
-    const bool no_fused = pv2::tune_int("PV2_LOSS_TWO_PASS", 0) == 1;      // A/B switch: boundary-weight kernel + streaming forward
+    const bool no_fused = prepared || pv2::tune_int("PV2_LOSS_TWO_PASS", 0) == 1;      // boundary-weight kernel + streaming forward
     if (vec && W % 4 == 0 && !no_fused) {      // one pass: boundary weight + loss sums
         cudaError_t ce = cudaMemsetAsync(L.ticket, 0, sizeof(unsigned int), st);
         PV2_CHECK(ce == cudaSuccess, "structure_loss_fwd: memset: %s", cudaGetErrorString(ce));
@@ -913,8 +942,10 @@ extern "C" int pv2_structure_loss_fwd(const void* const* pred, const void* const
         PV2_LAUNCH_CHECK("structure_loss_fwd_fused");
         return 0;
     }
-    pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, st, mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
-    PV2_LAUNCH_CHECK("boundary_weight");
+    if (!prepared) {
+        pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, st, mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
+        PV2_LAUNCH_CHECK("boundary_weight");
+    }
     const dim3 grid(L.chunks, planes);
     if (logit_dtype == PV2_F32) {
         if (vec) launch_fwd<float, 4>(nscales, grid, st, pp, mask_fg, mask_bg, L, HW, planes, loss);

@@ -40,6 +40,7 @@ _BNDEFER_DT = np.dtype([("part", "u8"), ("nparts", "i4"), ("ldc", "i4"), ("c_off
                        align=True)                                                                      # == pv2_bn_defer (88 B)
 assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.itemsize == 56 and _BNFUSE_DT.itemsize == 504
 assert _BNDEFER_DT.itemsize == 88
+_ZARENA_FLOATS = 1 << 18   # 1 MB: ~60 BatchNorm layers x 4 sums x <= 256 channels is 61 K floats
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
 
 
@@ -219,6 +220,10 @@ class Engine:
         self.need_grad = need_grad
         self.tape = _Tape(self)
         self.param_grads = {}     # id(param) -> grad tensor
+        # One zero-filled arena per pass (ONE memset at the start of the forward, off every chain): the BatchNorm-backward
+        # kernels add their block sums into 4*C-float slices of it (pv2_bn_act_bwd `sums_zeroed`).
+        self._zarena = torch.zeros(_ZARENA_FLOATS, dtype=torch.float32, device=device) if need_grad else None
+        self._zoff = 0
 
     # ---- parallel sections -----------------------------------------------------------------------------
     def _fan_out(self, n):
@@ -281,6 +286,15 @@ class Engine:
     def f32(self, *shape, zero=False):
         t = (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=self.dev)
         self._keep.append(t)
+        return t
+
+    def zeros_small(self, n):
+        """n zero-initialised floats (16-byte aligned) from the per-pass arena; a fresh torch.zeros when the arena is exhausted."""
+        n4 = (n + 3) // 4 * 4
+        if self._zarena is None or self._zoff + n4 > self._zarena.numel():
+            return self.f32(n4, zero=True)
+        t = self._zarena[self._zoff:self._zoff + n4]
+        self._zoff += n4
         return t
 
     def add_param_grad(self, p, g):
@@ -657,6 +671,7 @@ class Engine:
                                      self.kind, st), "pv2_act_apply")
         if self.need_grad:
             keep = (s1, b1, s2, b2, m1, i1, m2, i2)
+            sums0 = self.zeros_small(4 * Cc)          # zero until this op's backward adds its block sums there
 
             def bwd():
                 _alive = keep     # fwd_args holds raw device pointers into these tensors: keep them referenced
@@ -683,7 +698,7 @@ class Engine:
                 _lib.check(lib.pv2_bn_act_bwd(*fwd_args, *dz, _ptr(m1), _ptr(i1), _ptr(m2), _ptr(i2), bn_train,
                                               _ptr(dmult), Cc, dy1_ptr, self.plane_stride(dy1), self.planes, dy1.ld,
                                               dy2_ptr, self.plane_stride(dy2) if dy2 else 0, self.planes, dy2.ld if dy2 else 0,
-                                              dg1.data_ptr(), db1.data_ptr(), _ptr(dg2), _ptr(db2), ws.data_ptr(), _ticket_counters(self.dev, self.cur).data_ptr(),
+                                              dg1.data_ptr(), db1.data_ptr(), _ptr(dg2), _ptr(db2), ws.data_ptr(), sums0.data_ptr(),
                                               self.kind, _stream()),
                            "pv2_bn_act_bwd")
                 self._route_bn_grads(src1, dg1, db1, bn_train)

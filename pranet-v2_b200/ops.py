@@ -36,9 +36,41 @@ def _stream() -> int:
 # ------------------------------------------------------------------------------------------------
 # structure loss
 # ------------------------------------------------------------------------------------------------
+class PreparedMask:
+    """The mask-only part of structure_loss (the 31x31 boundary weight map, MyTrain_med.py:21), computed ahead of the logits by
+    `structure_loss_prepare`: holds the contiguous fp32 mask and the loss workspace the weight map lives in."""
+    __slots__ = ("mask_fg", "ws", "ws_bytes", "shape", "event")
+
+    def __init__(self, mask_fg, ws, ws_bytes, event):
+        self.mask_fg, self.ws, self.ws_bytes, self.shape, self.event = mask_fg, ws, ws_bytes, tuple(mask_fg.shape), event
+
+
+def structure_loss_prepare(mask_fg: torch.Tensor, stream: "torch.cuda.Stream" = None) -> PreparedMask:
+    """Launch the boundary-weight kernel for `mask_fg` (B, C, H, W) now -- on `stream` if given (a side stream that was made to
+    wait for the mask), else on the current stream -- and return the handle `structure_loss_multi(..., prepared=handle)` takes.
+    A training step calls this before the backbone so that the weight map is off the critical path (train.TrainStep)."""
+    _need_cuda(mask_fg)
+    lib = _lib.load()
+    B, Cc, H, W = mask_fg.shape
+    cur = torch.cuda.current_stream()
+    m = mask_fg.contiguous().float()
+    ws_bytes = lib.pv2_structure_loss_workspace_bytes(B * Cc, H, W, 4)
+    ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=m.device)      # allocated on the CURRENT stream: the loss runs there
+    ev = None
+    if stream is not None and stream != cur:
+        stream.wait_stream(cur)
+        with torch.cuda.stream(stream):
+            _lib.check(lib.pv2_structure_loss_prepare(m.data_ptr(), B * Cc, H, W, ws.data_ptr(), ws_bytes, stream.cuda_stream), "pv2_structure_loss_prepare")
+            ev = torch.cuda.Event()
+            ev.record(stream)
+    else:
+        _lib.check(lib.pv2_structure_loss_prepare(m.data_ptr(), B * Cc, H, W, ws.data_ptr(), ws_bytes, _stream()), "pv2_structure_loss_prepare")
+    return PreparedMask(m, ws, ws_bytes, ev)
+
+
 class _StructureLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mask_fg, mask_bg, *logits):
+    def forward(ctx, mask_fg, mask_bg, prepared, *logits):
         lib = _lib.load()
         K = len(logits) // 2
         preds = [t.contiguous() for t in logits[0::2]]
@@ -53,14 +85,24 @@ class _StructureLossFn(torch.autograd.Function):
         mask_fg = mask_fg.contiguous().float()
         mask_bg = mask_bg.contiguous().float() if mask_bg is not None else None
         planes = B * Cc
-        ws_bytes = lib.pv2_structure_loss_workspace_bytes(planes, H, W, K)
-        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=mask_fg.device)
         loss = torch.empty(K, dtype=torch.float32, device=mask_fg.device)
         pp, keep1 = _lib.ptr_array(preds)
         pb, keep2 = _lib.ptr_array(pred_bgs)
-        _lib.check(lib.pv2_structure_loss_fwd(pp, pb, mask_fg.data_ptr(), mask_bg.data_ptr() if mask_bg is not None else None,
-                                              K, planes, H, W, dt, loss.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
-                   "pv2_structure_loss_fwd")
+        if prepared is not None:
+            if prepared.shape != (B, Cc, H, W):
+                raise ValueError(f"structure_loss: prepared mask shape {prepared.shape} != logits shape {(B, Cc, H, W)}")
+            mask_fg, ws, ws_bytes = prepared.mask_fg, prepared.ws, prepared.ws_bytes
+            if prepared.event is not None:
+                torch.cuda.current_stream().wait_event(prepared.event)
+            _lib.check(lib.pv2_structure_loss_fwd_prepared(pp, pb, mask_fg.data_ptr(), mask_bg.data_ptr() if mask_bg is not None else None,
+                                                           K, planes, H, W, dt, loss.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+                       "pv2_structure_loss_fwd_prepared")
+        else:
+            ws_bytes = lib.pv2_structure_loss_workspace_bytes(planes, H, W, K)
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=mask_fg.device)
+            _lib.check(lib.pv2_structure_loss_fwd(pp, pb, mask_fg.data_ptr(), mask_bg.data_ptr() if mask_bg is not None else None,
+                                                  K, planes, H, W, dt, loss.data_ptr(), ws.data_ptr(), ws_bytes, _stream()),
+                       "pv2_structure_loss_fwd")
         ctx.save_for_backward(mask_fg, mask_bg, ws, *preds, *pred_bgs)
         ctx.meta = (K, planes, H, W, dt, ws_bytes)
         return loss
@@ -85,20 +127,21 @@ class _StructureLossFn(torch.autograd.Function):
         grads = []
         for a, b in zip(dps, dqs):
             grads += [a, b]
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
-def structure_loss_multi(pairs, mask_fg, mask_bg=None):
+def structure_loss_multi(pairs, mask_fg, mask_bg=None, prepared: PreparedMask = None):
     """`pairs` = [(pred, pred_bg), ...] (1..4 of them) supervised by ONE mask -> tensor of len(pairs) losses.
     One forward launch (+finalize) and one backward launch for all scales; the 31x31 boundary weight is
-    computed once per tile instead of once per call (the reference recomputes it 4x, MyTrain_med.py:78-81)."""
+    computed once per tile instead of once per call (the reference recomputes it 4x, MyTrain_med.py:78-81).
+    `prepared` = structure_loss_prepare(mask_fg): the weight map was computed ahead of time and the forward is a pure stream."""
     flat = []
     for p, q in pairs:
         flat += [p, q]
     _need_cuda(mask_fg, mask_bg, *flat)
     if not 1 <= len(pairs) <= 4:
         raise ValueError("structure_loss_multi takes 1..4 (pred, pred_bg) pairs")
-    return _StructureLossFn.apply(mask_fg, mask_bg, *flat)
+    return _StructureLossFn.apply(mask_fg, mask_bg, prepared, *flat)
 
 
 def structure_loss(pred, pred_bg, mask_fg, mask_bg=None):

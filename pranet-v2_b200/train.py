@@ -170,19 +170,27 @@ class TrainStep:
         self._graphs = {}      # (image shape, mask shape) -> (graph_a, graph_b, static image, static mask, loss)
         self._pool = None
         self._staged, self._copy_stream, self._stage_bufs, self._stage_slot = None, None, {}, 0
+        self._prep_stream = None
         self.pv2_launches_per_step = 0
 
     # -- the two halves of a step ------------------------------------------------------------------------
     def _fwd_bwd(self, images, gts):
         for p in self.params:
             p.grad = None
+        prepared = None
+        if not self.loss_from_lowres and gts.dim() == 4 and gts.shape[1] == getattr(self.model, "num_class", gts.shape[1]):
+            # the loss's boundary weight depends on the mask only: a branch that forks here and joins before the loss (it hides
+            # under the backbone), so that the loss forward after the head is a pure stream
+            if self._prep_stream is None:
+                self._prep_stream = torch.cuda.Stream(device=self.device)
+            prepared = ops.structure_loss_prepare(gts, self._prep_stream)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
             outs = self.model.forward_features_lowres(images) if self.loss_from_lowres else self.model(images)
         pairs = [(outs[i].float(), outs[i + 4].float()) for i in range(4)]
         if self.loss_from_lowres:
             loss = ops.structure_loss_lowres(pairs, self.model.final_scale_factors(), gts).sum()
         else:
-            loss = ops.structure_loss_multi(pairs, gts).sum()        # MyTrain_med.py:78-82
+            loss = ops.structure_loss_multi(pairs, gts, prepared=prepared).sum()        # MyTrain_med.py:78-82
         loss.backward()
         self.bucket.gather([p.grad for p in self.params])
         return loss.detach()
