@@ -216,9 +216,20 @@ def kernel_table(P, dev, B, S, hbm, tflops):
         (pp, _), (pb, _), (dp, _), (dq, _) = packs[rot()]
         P._lib.check(lib.pv2_structure_loss_bwd(pp, pb, m.data_ptr(), None, gl.data_ptr(), dp, dq, 4, B, S, S, 0, ws.data_ptr(), ws_bytes, cur()), "bwd")
 
+    def sl_prep():
+        P._lib.check(lib.pv2_structure_loss_prepare(m.data_ptr(), B, S, S, ws.data_ptr(), ws_bytes, cur()), "prep")
+
+    def sl_fwd_prepared():
+        (pp, _), (pb, _), _, _ = packs[rot()]
+        P._lib.check(lib.pv2_structure_loss_fwd_prepared(pp, pb, m.data_ptr(), None, 4, B, S, S, 0, loss.data_ptr(), ws.data_ptr(), ws_bytes, cur()), "fwdp")
+
     sl_fwd()
     t = timed_graph(sl_fwd)
     rows.append(("structure_loss fwd x4 (+ boundary weight + finalize)", "hbm", px * (4 + 4 * 8), t))
+    sl_prep()
+    rows.append(("structure_loss prepare (31x31 boundary weight map of the mask; side branch under the backbone)", "hbm", px * (4 + 2), timed_graph(sl_prep)))
+    sl_prep()
+    rows.append(("structure_loss fwd x4, prepared (streaming: logits + mask + 2-byte weight map)", "hbm", px * (4 + 2 + 4 * 8), timed_graph(sl_fwd_prepared)))
     t = timed_graph(sl_bwd)
     rows.append(("structure_loss bwd x4", "hbm", px * (4 + 4 * 16), t))
     # the same four losses from the LOW-RES maps (8 f2): final upsamples inside the loss kernels, no full-resolution maps / gradients.

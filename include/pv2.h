@@ -190,18 +190,17 @@ typedef struct pv2_bn_fuse {
 size_t pv2_bn_fuse_workspace_floats(long long M, int Cout);
 /* How pv2_conv_fwd with these arguments produces the statistics:
  *   0  not at all: call pv2_bn_stats_group afterwards (split-K);
- *   2  (the persistent kernel) every CTA reduces the 128-pixel tiles it computed to ONE (count, mean, M2, -) row per channel,
- *      bn->part[cta][Cout][4], and nothing else: no ticket, no fence, no serial tail in the GEMM.  The kernel that consumes a
- *      channel slice (pv2_act_apply) is given a pv2_bn_defer descriptor and folds the pv2_conv_stats_parts() rows in its
- *      prologue (fixed order: bit-reproducible), publishes mean / invstd / scale / shift and updates the running statistics;
+ *   2  (the persistent kernel) every CTA reduces the 128-pixel tiles it computed to per-channel (count, mean, M2) in shared memory
+ *      (Chan) and, when it is done, ADDS sum x = n*mean and sum x^2 = M2 + n*mean^2 -- in DOUBLE precision -- to the two accumulators
+ *      per channel at bn->part (2*Cout doubles = 4*Cout floats, ZERO on entry): no partial rows, no ticket, no fence, no serial tail in
+ *      the GEMM.  The kernel that consumes a channel slice (pv2_act_apply) is given a pv2_bn_defer descriptor, turns the two doubles of
+ *      each of its channels into mean / invstd / scale / shift in its prologue and updates the running statistics;
  *   1  (PV2_CONV_V1=1, the one-tile-per-CTA kernel kept for A/B) final statistics written by the launch (two-level ticket). */
 int pv2_conv_fuses_bn_stats(int splits, int out_mode);
-/* number of partial rows (= CTAs of the persistent launch) pv2_conv_fwd writes for this problem in mode 2 */
-int pv2_conv_stats_parts(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms, int splits);
 /* one BatchNorm module's channel slice [c_off, c_off + C) of a conv group whose statistics are still per-CTA partial rows */
 typedef struct pv2_bn_defer {
-    const float* part;                  /* [nparts][ldc][4]; NULL = this source is not deferred */
-    int nparts, ldc, c_off, pad_;       /* rows, channels per row (Cout of the group), first channel of the slice */
+    const float* part;                  /* the conv group's accumulators: [ldc][2] DOUBLES (sum x, sum x^2); NULL = this source is not deferred */
+    float count; int ldc, c_off, pad_;  /* pixels summed (N*H*W), channels of the whole group (Cout), first channel of the slice */
     const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches_tracked;
     float eps, momentum;
     float* mean; float* invstd;         /* [C] outputs, saved for the backward pass (scale / shift go to the s / b arrays) */
@@ -225,6 +224,12 @@ int pv2_conv_fwd(const void* x, long long x_plane_stride, const void* w_op, long
  * consumers read one slab (fp32 summation order of the <= 8 partials is not fixed: results agree to rounding, not bit for bit);
  * 0 when [split] slabs are written and left for the consumers to sum (PV2_CONV_V1=1). */
 int pv2_conv_sums_splits(void);
+/* Upper bound on the CTAs of the following pv2_conv_fwd launches of this process (0 = none: one CTA per tile up to two per SM).
+ * A caller that runs several convolutions CONCURRENTLY (the head's twelve chains on side streams) gives each a share of the
+ * machine: a persistent CTA then walks several tiles through one ring -- barrier setup, TMEM allocation and the first TMA round
+ * trip are paid once per CTA instead of once per tile -- and CTAs of different launches are resident side by side instead of
+ * queueing for the same slots.  Returns the previous value. */
+int pv2_conv_set_cta_budget(int max_ctas);
 /* dW partials out[split][Cout][KH*KW][Cin_p] = sum over the split's pixels of dY[p][co] * X[p + tap shift][ci] */
 int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind);
 int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const void* x, long long x_plane_stride, int kind, int nterms,

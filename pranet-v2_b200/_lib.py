@@ -47,6 +47,7 @@ _SIGS = {
     "pv2_conv_splits_hint": (_i, [_i] * 9),
     "pv2_conv_fwd": (_i, [_p, _ll, _p, _ll, _i, _i] + [_i] * 9 + [_i, _p, _i, _i, _p, _p, _p, _p]),
     "pv2_conv_sums_splits": (_i, []),
+    "pv2_conv_set_cta_budget": (_i, [_i]),
     "pv2_bn_fuse_workspace_floats": (_sz, [_ll, _i]),
     "pv2_conv_fuses_bn_stats": (_i, [_i, _i]),
     "pv2_bn_stats_group": (_i, [_p, _ll, _i, _ll, _i, _i, _p, _p]),
@@ -62,7 +63,6 @@ _SIGS = {
     "pv2_bn_stats": (_i, [_p, _ll, _i, _ll, _i, _i, _p, _p, _f, _f] + [_p] * 8 + [_p]),
     "pv2_bn_eval_affine": (_i, [_i, _p, _p, _p, _p, _f, _p, _p, _p]),
     "pv2_act_apply": (_i, _APPLY + [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _p]),
-    "pv2_conv_stats_parts": (_i, [_i] * 10),
     "pv2_bn_act_bwd": (_i, _APPLY + [c_void_pp, _ip, _ip, _i, _p] + [_p] * 4 + [_i, _p, _i] + [_p, _ll, _i, _i] * 2 + [_p] * 6 + [_i, _p]),
     "pv2_up2_nhwc_fwd": (_i, [_p, _ll, _i, _i, _i, _p, _ll, _i, _i, _i] + [_i] * 5 + [_p]),
     "pv2_up2_nhwc_bwd": (_i, [c_void_pp, _ip, _ip, _i, _p, _i] + [_i] * 4 + [_p]),

@@ -1,4 +1,6 @@
 // Library-wide pieces of the C ABI: version, thread-local error string, launch counter.
+#include <mutex>
+#include <unordered_set>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -23,6 +25,18 @@ bool pdl_enabled() {
 int tune_int(const char* name, int def) {
     const char* e = getenv(name);
     return (e && e[0]) ? atoi(e) : def;
+}
+// Every pv2 kernel asks for the SAME L1 / shared-memory split (maximum shared memory).  An SM has to drain before its carve-out
+// can change, and the head alternates 100-220 KB tensor-core kernels with small element-wise ones on up to twelve concurrent
+// chains: with per-kernel default carve-outs the SMs kept reconfiguring and the chains serialised (~40 us between two dependent
+// 10 us kernels of a chain).  The element-wise kernels stream and do not miss the L1.  PV2_CARVEOUT=-1 leaves the driver default.
+void prefer_max_shared(const void* kernel) {
+    static const int pct = [] { const char* e = getenv("PV2_CARVEOUT"); return (e && e[0]) ? atoi(e) : 100; }();
+    if (pct < 0) return;
+    static std::mutex mu;
+    static std::unordered_set<const void*> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done.insert(kernel).second) (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace pv2

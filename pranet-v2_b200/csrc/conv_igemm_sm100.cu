@@ -630,10 +630,20 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             }
         }
         if (a.stats) {
-            // one partial row per CTA: (count, mean, M2) of the pixels this CTA saw, per channel; the CONSUMER of a channel slice
-            // (pv2_act_apply with a pv2_bn_defer descriptor) folds the <= 296 rows in its prologue.  No ticket, no fence, no tail.
-            float4* row = reinterpret_cast<float4*>(bn.f.part) + (size_t)blockIdx.x * a.Cout;
-            for (int cg = et; cg < a.Cout; cg += 128) row[cg] = make_float4(cacc[3 * cg], cacc[3 * cg + 1], cacc[3 * cg + 2], 0.0f);
+            // This CTA's (count, mean, M2) of every channel it saw become raw moments sum x = n*mean and sum x^2 = M2 + n*mean^2 and
+            // are ADDED, in double precision, to the layer's two accumulators per channel (zero on entry).  No partial rows, no
+            // ticket, no fold: the kernel that consumes a channel slice reads 2 doubles per channel (pv2_bn_defer).  In double the
+            // cancellation of E[x^2] - E[x]^2 costs ~1e-16 * (1 + mean^2 / var): nothing at fp32 output precision, and the order in
+            // which the <= 296 CTAs arrive changes the result below the rounding of the final float.
+            double* acc2 = reinterpret_cast<double*>(bn.f.part);
+            for (int cg = et; cg < a.Cout; cg += 128) {
+                const float n = cacc[3 * cg], mu = cacc[3 * cg + 1], M2 = cacc[3 * cg + 2];
+                if (n > 0.0f) {
+                    const double dn = (double)n, dm = (double)mu;
+                    atomicAdd(acc2 + 2 * cg, dn * dm);
+                    atomicAdd(acc2 + 2 * cg + 1, (double)M2 + dn * dm * dm);
+                }
+            }
         }
     }
     tc_fence_before();
@@ -962,6 +972,11 @@ inline size_t v2_tail_bytes(bool stats, int BN, int Cout) {     // staging tiles
 
 // Persistent launch plan of conv_fwd2_kernel: CTAs per SM (1, or 2 when a work item's K slabs are few and small), ring depth.
 struct Plan2 { int grid, stages; size_t smem; };
+int g_cta_budget = 0;
+int cta_budget() {
+    const int e = tune_int("PV2_CONV_MAXGRID", 0);
+    return e > 0 ? e : g_cta_budget;
+}
 // Policy.  A work item whose K slabs add up to more than ~256 KB (the level GEMMs, the 5x5 and 96-channel stacks) gets an SM to
 // itself and the deepest ring that fits (latency: as many slabs in flight as possible).  Smaller items -- the 32/64-channel
 // chains, twelve of which run concurrently in the head -- take at most half an SM, so that CTAs of two launches (or two tiles
@@ -973,6 +988,8 @@ Plan2 plan_v2(int work_total, int slabs_per_item, size_t stage_bytes, uint32_t t
     if (cps == 2 && (size_t)112 * 1024 < 1024 + tail_bytes + stage_bytes) cps = 1;
     Plan2 p;
     p.grid = work_total < kNumSMs * cps ? work_total : kNumSMs * cps;
+    const int cap = cta_budget();      // concurrent chains: fewer CTAs, each walking more tiles through its ring (see pv2_conv_set_cta_budget)
+    if (cap > 0 && p.grid > cap) p.grid = cap;
     const int items_per_cta = (work_total + p.grid - 1) / p.grid;
     const size_t budget = (cps == 1 ? (size_t)226 * 1024 : (size_t)112 * 1024) - 1024 - tail_bytes;   // 1 KB alignment slack
     int st = (int)(budget / stage_bytes);
@@ -1009,17 +1026,10 @@ extern "C" int pv2_conv_fuses_bn_stats(int splits, int out_mode) {
 
 extern "C" int pv2_conv_sums_splits(void) { return use_v1() ? 0 : 1; }
 
-extern "C" int pv2_conv_stats_parts(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms, int splits) {
-    const int KC = kind == PV2_BF16 ? 64 : 32;
-    int BN, n_tiles;
-    n_tiling(Cout, &BN, &n_tiles);
-    const int m_tiles = (int)(((long long)N * H * W + BM - 1) / BM);
-    const int iters = nterms * KH * KW * ((Cin_p + KC - 1) / KC);
-    if (splits < 1) splits = 1;
-    const int BNr = ((BN + 31) / 32) * 32;
-    const Plan2 pl = plan_v2(m_tiles * n_tiles * splits, (iters + splits - 1) / splits, (size_t)A_BYTES + (size_t)BN * ROW_BYTES, pow2_cols(2 * BNr),
-                             v2_tail_bytes(true, BN, Cout));
-    return pl.grid;
+extern "C" int pv2_conv_set_cta_budget(int max_ctas) {
+    const int old = g_cta_budget;
+    g_cta_budget = max_ctas > 0 ? max_ctas : 0;
+    return old;
 }
 
 extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
@@ -1103,7 +1113,6 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
         a.tmem_cols = pow2_cols(2 * a2.BNr);
         const size_t tail = v2_tail_bytes(a.stats != 0, a.BN, Cout);
         const Plan2 pl = plan_v2(a2.work_total, a.iters_per_split, stage_bytes, a.tmem_cols, tail);
-        PV2_CHECK(!a.stats || (size_t)pl.grid * Cout * 4 <= pv2_bn_fuse_workspace_floats(a.M, Cout), "conv_fwd: statistics workspace too small");
         a.stages = pl.stages;
         a2.c = a;
         PV2_CHECK(pl.smem <= 227 * 1024, "conv_fwd: bad v2 stage plan (%d stages of %zu B)", pl.stages, stage_bytes);

@@ -447,94 +447,52 @@ __device__ __forceinline__ float apply_value(const ApplyArgs& a, long long r, in
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Deferred BatchNorm fold.  The persistent conv kernel leaves one (count, mean, M2) row per CTA; the kernel that consumes a
-// channel slice folds the rows here, in its prologue: thread (c, j) Chan-combines rows j, j+J, ... of channel c (loads issued
-// eight at a time), the J sub-results are combined in j order -- a fixed order, so the statistics are bit-reproducible.
-// Every CTA computes the slice's scale / shift into its own shared memory; CTA 0 also publishes mean / invstd / scale / shift
-// (saved for the backward pass) and updates the running statistics exactly like nn.BatchNorm2d.
+// Deferred BatchNorm statistics.  The persistent conv kernel leaves, per channel, sum x and sum x^2 over all pixels as two
+// doubles (added by its CTAs, see conv_fwd2_kernel); the kernel that consumes a channel slice turns them into scale / shift here,
+// in its prologue: two loads per channel.  Every CTA keeps the slice's scale / shift in its own shared memory; CTA 0 also
+// publishes mean / invstd / scale / shift (saved for the backward pass) and updates the running statistics exactly like
+// nn.BatchNorm2d (momentum, unbiased running variance).
 // ------------------------------------------------------------------------------------------------------
 constexpr int DEFER_MAX_C = 512;
 struct Defer2 { pv2_bn_defer d[2]; };
 
-// pooled statistics of up to NB rows held in registers: no divisions inside the loops, every M2 term non-negative
-template <int NB>
-__device__ __forceinline__ void pooled_rows(const float4 (&v)[NB], float& N, float& mean, float& M2) {
-    float Sn = 0.0f, Snm = 0.0f;
-#pragma unroll
-    for (int u = 0; u < NB; ++u) { Sn += v[u].x; Snm = fmaf(v[u].x, v[u].y, Snm); }
-    const float m = Sn > 0.0f ? Snm / Sn : 0.0f;
-    float q = 0.0f;
-#pragma unroll
-    for (int u = 0; u < NB; ++u) { const float dd = v[u].y - m; q += v[u].z + v[u].x * dd * dd; }
-    N = Sn; mean = m; M2 = q;
-}
-
-constexpr int DEFER_NB = 20;     // rows a thread folds from registers in one batch of independent 16-byte loads
-
-__device__ __forceinline__ void bn_fold_deferred(const pv2_bn_defer& d, int C, float* s_scale, float* s_shift, float* s_red,
+__device__ __forceinline__ void bn_fold_deferred(const pv2_bn_defer& d, int C, float* s_scale, float* s_shift,
                                                  bool writer, float* g_scale, float* g_shift) {
-    const int T = blockDim.x, t = threadIdx.x;
-    for (int cb = 0; cb < C; cb += T) {
-        const int Cb = min(T, C - cb);
-        int J = T / Cb;                  // row lanes per channel: thread (c, j) folds rows j, j+J, ...
-        if (J > 32) J = 32;
-        const int c = t % Cb, j = t / Cb;
-        float n = 0.0f, mu = 0.0f, M2 = 0.0f;
-        if (j < J) {
-            const float4* base = reinterpret_cast<const float4*>(d.part) + d.c_off + cb + c;
-            for (int p0 = j; p0 < d.nparts; p0 += DEFER_NB * J) {      // one iteration unless nparts > 20 * J
-                float4 v[DEFER_NB];
-#pragma unroll
-                for (int u = 0; u < DEFER_NB; ++u) {
-                    const int p = p0 + u * J;
-                    v[u] = p < d.nparts ? __ldg(base + (size_t)p * d.ldc) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                }
-                float bn_, bm, bq;
-                pooled_rows<DEFER_NB>(v, bn_, bm, bq);
-                chan_combine(n, mu, M2, bn_, bm, bq);
+    const double* sums = reinterpret_cast<const double*>(d.part) + 2 * (size_t)d.c_off;
+    const double N = (double)d.count;
+    for (int cl = threadIdx.x; cl < C; cl += blockDim.x) {
+        const double S1 = __ldcg(sums + 2 * cl), S2 = __ldcg(sums + 2 * cl + 1);
+        const double dmean = S1 / N;
+        double dvar = S2 / N - dmean * dmean;
+        if (dvar < 0.0) dvar = 0.0;
+        const float mu = (float)dmean, var = (float)dvar, n = (float)d.count;
+        const float inv = rsqrtf(var + d.eps);
+        const float g = d.gamma ? d.gamma[cl] : 1.0f, b = d.beta ? d.beta[cl] : 0.0f;
+        const float sc = g * inv, sh = b - mu * g * inv;
+        s_scale[cl] = sc; s_shift[cl] = sh;
+        if (writer) {
+            g_scale[cl] = sc; g_shift[cl] = sh;
+            d.mean[cl] = mu; d.invstd[cl] = inv;
+            if (d.running_mean) {
+                d.running_mean[cl] = (1.0f - d.momentum) * d.running_mean[cl] + d.momentum * mu;
+                d.running_var[cl] = (1.0f - d.momentum) * d.running_var[cl] + d.momentum * (n > 1.0f ? var * n / (n - 1.0f) : var);
             }
+            if (cl == 0 && d.num_batches_tracked) *d.num_batches_tracked += 1;
         }
-        s_red[t * 3] = n; s_red[t * 3 + 1] = mu; s_red[t * 3 + 2] = M2;
-        __syncthreads();
-        if (t < Cb) {
-            // the J row lanes of this channel, pooled in lane order
-            float Sn = 0.0f, Snm = 0.0f;
-            for (int jj = 0; jj < J; ++jj) { const float* q = s_red + (jj * Cb + t) * 3; Sn += q[0]; Snm = fmaf(q[0], q[1], Snm); }
-            mu = Sn > 0.0f ? Snm / Sn : 0.0f;
-            M2 = 0.0f;
-            for (int jj = 0; jj < J; ++jj) { const float* q = s_red + (jj * Cb + t) * 3; const float dd = q[1] - mu; M2 += q[2] + q[0] * dd * dd; }
-            n = Sn;
-            const int cl = cb + t;
-            const float var = M2 / n;
-            const float inv = rsqrtf(var + d.eps);
-            const float g = d.gamma ? d.gamma[cl] : 1.0f, b = d.beta ? d.beta[cl] : 0.0f;
-            const float sc = g * inv, sh = b - mu * g * inv;
-            s_scale[cl] = sc; s_shift[cl] = sh;
-            if (writer) {
-                g_scale[cl] = sc; g_shift[cl] = sh;
-                d.mean[cl] = mu; d.invstd[cl] = inv;
-                if (d.running_mean) {
-                    d.running_mean[cl] = (1.0f - d.momentum) * d.running_mean[cl] + d.momentum * mu;
-                    d.running_var[cl] = (1.0f - d.momentum) * d.running_var[cl] + d.momentum * (n > 1.0f ? M2 / (n - 1.0f) : var);
-                }
-                if (cl == 0 && d.num_batches_tracked) *d.num_batches_tracked += 1;
-            }
-        }
-        __syncthreads();
     }
+    __syncthreads();
 }
 
 // shared prologue of the apply kernels: returns the ApplyArgs to use (scale / shift redirected to shared memory when deferred)
 #define PV2_APPLY_DEFER_PROLOGUE(a, df, la)                                                                             \
     __shared__ __align__(16) float s_aff[2][2][DEFER_MAX_C];                                                            \
-    __shared__ float s_red[256 * 3];                                                                                    \
     ApplyArgs la = a;                                                                                                   \
     if (df.d[0].part) {                                                                                                 \
-        bn_fold_deferred(df.d[0], a.C, s_aff[0][0], s_aff[0][1], s_red, blockIdx.x == 0, const_cast<float*>(a.s1), const_cast<float*>(a.b1)); \
+        bn_fold_deferred(df.d[0], a.C, s_aff[0][0], s_aff[0][1], blockIdx.x == 0, const_cast<float*>(a.s1), const_cast<float*>(a.b1)); \
         la.s1 = s_aff[0][0]; la.b1 = s_aff[0][1];                                                                       \
     }                                                                                                                   \
     if (df.d[1].part) {                                                                                                 \
-        bn_fold_deferred(df.d[1], a.C, s_aff[1][0], s_aff[1][1], s_red, blockIdx.x == 0, const_cast<float*>(a.s2), const_cast<float*>(a.b2)); \
+        bn_fold_deferred(df.d[1], a.C, s_aff[1][0], s_aff[1][1], blockIdx.x == 0, const_cast<float*>(a.s2), const_cast<float*>(a.b2)); \
         la.s2 = s_aff[1][0]; la.b2 = s_aff[1][1];                                                                       \
     }
 
@@ -764,49 +722,6 @@ act_apply4_kernel(const ApplyArgs a0, const Defer2 df) {
         float4 v = apply_value4<KIND>(a, r, c, &a1, &a2, &m);
         if (a.relu) v = make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
         store_op4<KIND>(a.out, a.out_plane, a.out_planes, (long long)r * a.out_ld + a.out_off + c, v);
-    }
-    pv2::pdl_done();
-}
-
-// Deferred-fold form of the vector apply: CTA = (row chunk, group of 16 channels).  A CTA folds the per-CTA partial rows of ITS
-// 16 channels only (<= 296 x 16 rows of 16 bytes: one batch of independent loads per thread whatever the slice width -- with the
-// flat layout above every CTA would fold all C channels, ~4 batches at C = 96) and then streams its rows: 64 B of fp32 raw in,
-// 32 B of bf16 operand out per row, whole sectors both ways.  The CTAs of row chunk 0 publish the statistics.
-constexpr int APPLY_CG = 16;
-
-template <int KIND>
-__global__ void __launch_bounds__(256)
-act_apply4_cg_kernel(const ApplyArgs a0, const Defer2 df) {
-    pv2::pdl_prologue();
-    __shared__ __align__(16) float s_aff[2][2][APPLY_CG];
-    __shared__ float s_red[256 * 3];
-    const int c0 = blockIdx.y * APPLY_CG;
-    const int Cg = min(APPLY_CG, a0.C - c0);
-    ApplyArgs a = a0;       // channel-indexed fields shifted to this group: local channel 0 .. Cg-1
-    a.off1 += c0; a.off2 += c0; a.mult_off += c0; a.out_off += c0;
-    a.s1 += c0; a.b1 += c0;
-    if (a.combine) { a.s2 += c0; a.b2 += c0; }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        if (!df.d[i].part) continue;
-        pv2_bn_defer d = df.d[i];
-        d.c_off += c0;
-        if (d.gamma) d.gamma += c0;
-        if (d.beta) d.beta += c0;
-        if (d.running_mean) { d.running_mean += c0; d.running_var += c0; }
-        if (blockIdx.y != 0) d.num_batches_tracked = nullptr;
-        d.mean += c0; d.invstd += c0;
-        bn_fold_deferred(d, Cg, s_aff[i][0], s_aff[i][1], s_red, blockIdx.x == 0,
-                         const_cast<float*>(i == 0 ? a.s1 : a.s2), const_cast<float*>(i == 0 ? a.b1 : a.b2));
-        if (i == 0) { a.s1 = s_aff[0][0]; a.b1 = s_aff[0][1]; } else { a.s2 = s_aff[1][0]; a.b2 = s_aff[1][1]; }
-    }
-    const int c = (threadIdx.x & 3) << 2;
-    if (c >= Cg) return;
-    for (long long r = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); r < a.M; r += (long long)gridDim.x * 64) {
-        float4 a1, a2, m;
-        float4 v = apply_value4<KIND>(a, r, c, &a1, &a2, &m);
-        if (a.relu) v = make_float4(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f), fmaxf(v.z, 0.0f), fmaxf(v.w, 0.0f));
-        store_op4<KIND>(a.out, a.out_plane, a.out_planes, r * a.out_ld + a.out_off + c, v);
     }
     pv2::pdl_done();
 }
@@ -1226,9 +1141,7 @@ extern "C" size_t pv2_bn_fuse_workspace_floats(long long M, int Cout) {
     const long long fused = m_tiles * Cout * 2 + (long long)fp.ngroups * Cout * 3;       // conv epilogue: tile + group partials
     const int rows = pick_rows(M, Cout);
     const long long standalone = ((M + rows - 1) / rows) * Cout * 3;                       // pv2_bn_stats_group row-block partials
-    const long long deferred = 2LL * kNumSMs * Cout * 4;                                   // persistent conv: one (count, mean, M2, -) row per CTA
-    const long long need = fused > standalone ? fused : standalone;
-    return (size_t)(need > deferred ? need : deferred);
+    return (size_t)(fused > standalone ? fused : standalone);
 }
 
 extern "C" int pv2_bn_stats_group(float* y, long long slab_stride, int nslabs, long long M, int Cout, int ld, const pv2_bn_fuse* bn, void* stream) {
@@ -1296,7 +1209,7 @@ extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long l
         const pv2_bn_defer& d = df.d[i];
         if (!d.part) continue;
         PV2_CHECK(C <= DEFER_MAX_C, "act_apply: a deferred BatchNorm fold handles at most %d channels per slice (got %d)", DEFER_MAX_C, C);
-        PV2_CHECK(d.nparts >= 1 && d.ldc >= d.c_off + C && d.mean && d.invstd && (((uintptr_t)d.part) & 15) == 0,
+        PV2_CHECK(d.count >= 1.0f && d.ldc >= d.c_off + C && d.mean && d.invstd && (((uintptr_t)d.part) & 15) == 0,
                   "act_apply: incomplete pv2_bn_defer descriptor");
         PV2_CHECK(i == 0 ? (s1 && b1) : (combine && s2 && b2), "act_apply: deferred fold needs the scale / shift output arrays");
     }
@@ -1305,21 +1218,9 @@ extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long l
     PV2_CHECK(out != nullptr, "act_apply: null output");
     a.out = out; a.out_plane = out_plane; a.out_planes = out_planes; a.out_ld = out_ld; a.out_off = out_off; a.out_nchw = out_nchw;
     const long long total = M * C;
-    // every CTA repeats the deferred fold (nparts x C rows from L2): keep the grid at two CTAs per SM then
-    auto grid_of = [&](long long work) { const int g = grid_for(work); return (deferred && g > 2 * kNumSMs) ? 2 * kNumSMs : g; };
+    auto grid_of = [&](long long work) { return grid_for(work); };
+    (void)deferred;
     if (!out_nchw && apply_vec_ok(a) && out_ld % 4 == 0 && out_off % 4 == 0 && al16(out)) {
-        if (deferred) {
-            const int ncg = (C + APPLY_CG - 1) / APPLY_CG;
-            long long R = (2LL * kNumSMs + ncg - 1) / ncg;
-            const long long rmax = (M + 63) / 64;
-            if (R > rmax) R = rmax;
-            if (R < 1) R = 1;
-            const dim3 grid((unsigned)R, (unsigned)ncg);
-            if (kind == PV2_BF16) pv2::launch(act_apply4_cg_kernel<0>, grid, 256, 0, (cudaStream_t)stream, a, df);
-            else pv2::launch(act_apply4_cg_kernel<1>, grid, 256, 0, (cudaStream_t)stream, a, df);
-            PV2_LAUNCH_CHECK("act_apply4_cg");
-            return 0;
-        }
         if (kind == PV2_BF16) pv2::launch(act_apply4_kernel<0>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
         else pv2::launch(act_apply4_kernel<1>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
         PV2_LAUNCH_CHECK("act_apply4");

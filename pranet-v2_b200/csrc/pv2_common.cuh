@@ -57,8 +57,11 @@ bool pdl_enabled();
 // integer tuning knob from the environment, read at every call (A/B measurements inside one process); `def` when unset
 int tune_int(const char* name, int def);
 
+void prefer_max_shared(const void* kernel);
+
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    prefer_max_shared(reinterpret_cast<const void*>(kernel));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

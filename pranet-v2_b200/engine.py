@@ -35,11 +35,12 @@ _BNSEG_DT = np.dtype([("gamma", "u8"), ("beta", "u8"), ("rm", "u8"), ("rv", "u8"
                       ("c_begin", "i4"), ("c_end", "i4")], align=True)                                  # == pv2_bn_seg (56 B)
 _BNFUSE_DT = np.dtype([("seg", _BNSEG_DT, (8,)), ("mean", "u8"), ("invstd", "u8"), ("scale", "u8"), ("shift", "u8"), ("part", "u8"),
                        ("counters", "u8"), ("nsegs", "i4"), ("pad_", "i4")], align=True)                 # == pv2_bn_fuse (504 B)
-_BNDEFER_DT = np.dtype([("part", "u8"), ("nparts", "i4"), ("ldc", "i4"), ("c_off", "i4"), ("pad_", "i4"), ("gamma", "u8"), ("beta", "u8"),
+_BNDEFER_DT = np.dtype([("part", "u8"), ("count", "f4"), ("ldc", "i4"), ("c_off", "i4"), ("pad_", "i4"), ("gamma", "u8"), ("beta", "u8"),
                         ("rm", "u8"), ("rv", "u8"), ("nbt", "u8"), ("eps", "f4"), ("momentum", "f4"), ("mean", "u8"), ("invstd", "u8")],
                        align=True)                                                                      # == pv2_bn_defer (88 B)
 assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.itemsize == 56 and _BNFUSE_DT.itemsize == 504
 assert _BNDEFER_DT.itemsize == 88
+_PAR_CTA_BUDGET = int(os.environ.get("PV2_PAR_CTA_BUDGET", "96"))
 _ZARENA_FLOATS = 1 << 18   # 1 MB: ~60 BatchNorm layers x 4 sums x <= 256 channels is 61 K floats
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
 
@@ -222,11 +223,18 @@ class Engine:
         self.param_grads = {}     # id(param) -> grad tensor
         # One zero-filled arena per pass (ONE memset at the start of the forward, off every chain): the BatchNorm-backward
         # kernels add their block sums into 4*C-float slices of it (pv2_bn_act_bwd `sums_zeroed`).
-        self._zarena = torch.zeros(_ZARENA_FLOATS, dtype=torch.float32, device=device) if need_grad else None
+        self._zarena = torch.zeros(_ZARENA_FLOATS, dtype=torch.float32, device=device) if (need_grad or training) else None
         self._zoff = 0
 
     # ---- parallel sections -----------------------------------------------------------------------------
+    def _set_width(self, n):
+        """Tell the conv launcher how many chains run side by side: with four or more, every persistent conv launch is capped at
+        96 CTAs (each then walks several tiles through its ring) so that CTAs of the sibling chains are resident next to it
+        instead of queueing for the same slots; a lone chain keeps the whole machine (pv2_conv_set_cta_budget)."""
+        self.lib.pv2_conv_set_cta_budget(_PAR_CTA_BUDGET if n >= 4 else 0)
+
     def _fan_out(self, n):
+        self._set_width(n)
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)
@@ -234,6 +242,7 @@ class Engine:
             self.side[i].wait_event(ev)
 
     def _fan_in(self, n):
+        self._set_width(0)
         main = torch.cuda.current_stream()
         for i in range(n):
             ev = torch.cuda.Event()
@@ -433,7 +442,10 @@ class Engine:
     def _bn_fuse(self, convs, bns, M, Cout):
         """pv2_bn_fuse descriptor (host struct, passed by value into the kernels) for the BatchNorms that follow `convs`."""
         stats = self.f32(4, Cout)
-        ws = self.f32(self.lib.pv2_bn_fuse_workspace_floats(M, Cout))
+        if self.lib.pv2_conv_fuses_bn_stats(1, 0) == 2:
+            ws = self.zeros_small(4 * Cout)     # persistent kernel: two DOUBLE accumulators per channel, zero on entry (the per-pass arena)
+        else:
+            ws = self.f32(self.lib.pv2_bn_fuse_workspace_floats(M, Cout))
         cnt = _ticket_counters(self.dev, self.cur)
         d = np.zeros(1, dtype=_BNFUSE_DT)
         o, n, seg_of = 0, 0, {}
@@ -511,8 +523,7 @@ class Engine:
                     _lib.check(lib.pv2_bn_stats_group(raw_t.data_ptr(), N * H * W * ld, splits, N * H * W, Cout, ld, fuse.ctypes.data, st),
                                "pv2_bn_stats_group")
                 elif how == 2:   # per-CTA partial rows: folded by the first kernel that consumes each BatchNorm's channel slice
-                    res.defer = {"part": hold[0], "nparts": lib.pv2_conv_stats_parts(N, H, W, Cin_p, Cout, KH, KW, self.kind, self.nterms, splits),
-                                 "pending": set(seg_of.keys())}
+                    res.defer = {"part": hold[0], "count": float(N * H * W), "pending": set(seg_of.keys())}
                 res.stats, res.stat_bns = stats, seg_of
         if self.need_grad:
             self.tape.append(lambda: self._conv_bwd(x, convs, res, KH, KW, dh, dw, Cin, Cin_p, Cout))
@@ -617,7 +628,7 @@ class Engine:
                 raw.defer["pending"].discard(off)
                 track = bn.track_running_stats and bn.running_mean is not None
                 d = np.zeros(1, dtype=_BNDEFER_DT)
-                d[0] = (raw.defer["part"].data_ptr(), raw.defer["nparts"], raw.C, off, 0, _ptr(bn.weight) or 0, _ptr(bn.bias) or 0,
+                d[0] = (raw.defer["part"].data_ptr(), raw.defer["count"], raw.C, off, 0, _ptr(bn.weight) or 0, _ptr(bn.bias) or 0,
                         bn.running_mean.data_ptr() if track else 0, bn.running_var.data_ptr() if track else 0,
                         bn.num_batches_tracked.data_ptr() if track else 0, float(bn.eps), 0.1 if bn.momentum is None else float(bn.momentum),
                         st4[0, off:off + C].data_ptr(), st4[1, off:off + C].data_ptr())

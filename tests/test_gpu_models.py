@@ -269,7 +269,7 @@ def test_train_step_loss_from_lowres_equals_module_path():
     assert abs(l1 - l0) <= 1e-5 * abs(l0), (l0, l1)
     # cuDNN backward of the stock backbone is not bit-reproducible run to run: compare at the level two unfused runs agree
     assert (g1 - g0).abs().max().item() <= 2e-3 * g0.abs().max().item()
-    assert n_fused == n_unfused - 1        # (bilinear x8 fwd, loss fwd, loss bwd, bilinear x8 bwd) -> (loss fwd, loss bwd, fold)
+    assert n_fused == n_unfused - 2        # (boundary weight, bilinear x8 fwd, loss fwd, loss bwd, bilinear x8 bwd) -> (loss fwd, loss bwd, fold)
     # and the captured step trains with it
     ts = TrainStep(m, lr=1e-4, clip=0.5, autocast_backbone=False, device="cuda:0", use_graph=True, loss_from_lowres=True)
     a = float(ts.step_device(x, gt)); b = float(ts.step_device(x, gt))
