@@ -25,6 +25,13 @@ import torch  # noqa: E402
 
 METRIC = "train images/sec @352^2 (PraNet-V2 Res2Net-50, DSRA head + structure loss, fwd+bwd+Adam)"
 UNIT = "images/s"
+# BASELINE.json configs: [1] Res2Net-50 training (the headline), [2] PVTv2-b2 training / inference, [3] EMCAD + DSRA multiclass
+CONFIGS = {
+    "res2net": dict(model="PraNet_V2", kw=dict(num_class=1), size=352, task="binary", label="PraNet-V2 Res2Net-50"),
+    "pvt": dict(model="PVT_PraNet_V2", kw=dict(num_class=1), size=352, task="binary", label="PVT-PraNet-V2 (PVTv2-b2)"),
+    "emcad": dict(model="EMCADNet", kw=dict(num_classes=9, encoder="pvt_v2_b2", pretrain=False, dual=True), size=224, task="multiclass",
+                  label="EMCAD (PVTv2-b2) + DSRA, 9 classes"),
+}
 
 
 def parse():
@@ -33,17 +40,23 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="res2net", choices=list(CONFIGS), help="res2net (headline, BASELINE config 2) | pvt (config 3) | emcad (config 4)")
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
-    ap.add_argument("--size", type=int, default=352)
-    ap.add_argument("--cpu-batch", type=int, default=4, help="batch of one CPU-baseline step (bounded sample)")
+    ap.add_argument("--size", type=int, default=None, help="input size (default: 352, emcad: 224)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (inference, PVT, EMCAD) embedded in the N=1 line")
+    ap.add_argument("--no-eager-reference", action="store_true", help="skip the reference-in-eager-PyTorch-on-this-GPU leg")
+    ap.add_argument("--ref-seconds", type=float, default=150.0, help="wall-clock budget of the reference arm's timed steps (a bounded sample)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train (default, the headline metric) or infer: batched test-time path, images/s of uint8 saliency maps")
     ap.add_argument("--profile-only", action="store_true",
                     help="run the warm-up + timed steps only (no e2e / roofline / CPU legs) and exit: the command ncu wraps for the launch list")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.size is None:
+        a.size = CONFIGS[a.config]["size"]
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,21 +108,111 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference's path on the host cores
+# Reference arm / CPU baseline: the reference's OWN modules (oracle/_ref, staged byte for byte by build()) on the host cores;
+# the oracle port when they are not there.  fp32, all host threads, the benchmarked batch.
 # ------------------------------------------------------------------------------------------------
-def cpu_train_step_factory(batch: int, size: int):
-    """One training step of the reference's path on CPU: stock Res2Net-50 backbone (torch CPU) + the
-    oracle's functional DSRA head + 4x oracle structure_loss + backward + clamp + Adam, fp32, all host threads."""
-    from oracle import dsra_oracle as O
-    from oracle import synth, templates
-    from pranet_v2_b200.backbones import Res2Net50
+def _labels(B, S, C, seed):
+    """9-class blob maps: background 0 ~ 70 %, the other classes as random ellipses."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:S, 0:S]
+    out = np.zeros((B, S, S), dtype=np.int64)
+    for b in range(B):
+        for c in range(1, C):
+            cy, cx = rng.uniform(0.15, 0.85, 2) * S
+            ry, rx = rng.uniform(0.04, 0.14, 2) * S
+            out[b][((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0] = c
+    return torch.from_numpy(out)
 
-    torch.set_num_threads(os.cpu_count() or 1)
+
+def reference_step_factory(config: str, batch: int, size: int, device="cpu", mode="train", variant="fp32"):
+    """One step of the reference's path with the reference's own modules when they are staged (kind 'reference'), else the oracle
+    port (kind 'port').  train: model forward, the loss block (MyTrain_med.py:76-82 / EMCAD trainer.py:105-140), backward,
+    clip_gradient (binary), Adam / AdamW.  infer: eval forward + the test-time rule.  Returns (step, kind, description)."""
+    from oracle import ref_import as R
+    from oracle import synth
+    cfg = CONFIGS[config]
+    dev = torch.device(device)
+    if dev.type == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(1000)
+    if R.available():
+        kind = "reference"
+        if config == "emcad":
+            model = R.emcad_networks().EMCADNet(**cfg["kw"])
+            x = torch.randn(batch, 1, size, size, generator=g)
+            y = _labels(batch, size, 9, 1000)
+        else:
+            model = R.build_binary(cfg["model"], **cfg["kw"])
+            x = torch.randn(batch, 3, size, size, generator=g)
+            y = synth.ellipse_masks(batch, size, size, 1000)
+        model = model.to(dev)
+        x, y = x.to(dev), y.to(dev)
+        if variant == "bf16_cl":
+            model = model.to(memory_format=torch.channels_last)
+            x = x.contiguous(memory_format=torch.channels_last)
+        autocast = variant == "bf16_cl"
+        if mode == "infer":
+            model.eval()
+
+            def step():
+                with torch.no_grad(), torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
+                    o = model(x)
+                    res = (o[0] + o[1] + o[2] + o[3]).float().sigmoid()          # MyTest_med.py:35-39
+                    res = (res - res.amin((1, 2, 3), keepdim=True)) / (res.amax((1, 2, 3), keepdim=True) - res.amin((1, 2, 3), keepdim=True) + 1e-8)
+                    return (res * 255).to(torch.uint8)
+            return step, kind, f"{cfg['label']} eval forward + test-time rule, the reference's own modules"
+        model.train()
+        if config == "emcad":
+            powerset, DiceLoss, one_hot = R.emcad_loss_pieces()
+            ce, dice, bce = torch.nn.CrossEntropyLoss(), DiceLoss(9), torch.nn.BCEWithLogitsLoss()
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4)     # EMCAD/trainer.py:86
+            subsets = [s for s in powerset(list(range(4))) if s]
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
+                    P = model(x, mode="train")
+                P = [p.float() for p in P]
+                bg_mask = one_hot(y.cpu(), 9).to(dev).float()                           # trainer.py:22-29,99-103 (built on the CPU there)
+                loss = 0.0
+                for sub in subsets:                                                     # trainer.py:123-140
+                    iout = sum(P[i] for i in sub)
+                    ibg = sum(P[i + 4] for i in sub)
+                    loss = loss + 0.5 * ce(iout, y) + 0.7 * dice(iout, y, softmax=True) + 0.3 * bce(ibg, bg_mask)
+                loss.backward()
+                opt.step()
+                return float(loss)
+            return step, kind, "EMCADNet(dual) train step: forward, 15-subset dual loss, backward, AdamW -- the reference's own modules"
+        sl = R.structure_loss()
+        opt = torch.optim.Adam(model.parameters(), 1e-4)                                # MyTrain_med.py:148-149
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast(dev.type, dtype=torch.bfloat16, enabled=autocast):
+                o = model(x)
+            o = [t.float() for t in o]
+            loss = sum(sl(o[i], o[i + 4], y, 1 - y) for i in range(4))                  # MyTrain_med.py:74,78-82
+            loss.backward()
+            for grp in opt.param_groups:                                                # utils/utils.py:7-17 clip_gradient(optimizer, 0.5)
+                for p in grp["params"]:
+                    if p.grad is not None:
+                        p.grad.data.clamp_(-0.5, 0.5)
+            opt.step()
+            return float(loss)
+        return step, kind, f"{cfg['label']} train step (forward, 4x structure_loss, backward, clip_gradient, Adam), the reference's own modules"
+    # ---- oracle port (the staged reference is missing) ----
+    if config != "res2net" or mode != "train" or dev.type != "cpu":
+        raise RuntimeError("oracle/_ref is not staged (run __graft_entry__.build() in the builder container): only the Res2Net training "
+                           "port is available")
+    from oracle import dsra_oracle as O
+    from oracle import templates
+    from pranet_v2_b200.backbones import Res2Net50
     bb = Res2Net50().train()
     sd = synth.synth_state_dict(templates.pranet_head(num_class=1), seed=0)
     params = [v.requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k]
     opt = torch.optim.Adam(list(bb.parameters()) + params, 1e-4)
-    x = torch.randn(batch, 3, size, size, generator=torch.Generator().manual_seed(1000))
+    x = torch.randn(batch, 3, size, size, generator=g)
     gt = synth.ellipse_masks(batch, size, size, 1000)
 
     def step():
@@ -123,45 +226,236 @@ def cpu_train_step_factory(batch: int, size: int):
                 p.grad.clamp_(-0.5, 0.5)
         opt.step()
         return float(loss)
-    return step
+    return step, "port", "oracle port: stock Res2Net-50 on torch-CPU + oracle head / loss (the staged reference modules are missing)"
 
 
-def time_cpu(batch, size, steps, warmup):
-    step = cpu_train_step_factory(batch, size)
-    for _ in range(warmup):
+def time_cpu(config, batch, size, steps, warmup, budget_s, mode="train"):
+    """(images/s, s/step, steps timed, kind, description): a bounded sample -- at most `steps` steps, at least one, stopping once
+    `budget_s` seconds of timed work are spent (a batch-16 Res2Net training step is seconds of CPU time)."""
+    step, kind, desc = reference_step_factory(config, batch, size, "cpu", mode)
+    t_w = time.perf_counter()
+    for _ in range(max(0, warmup)):
         step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
+        if time.perf_counter() - t_w > budget_s / 3:
+            break
+    done, t0 = 0, time.perf_counter()
+    while done < steps:
         step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps
+    return batch * done / dt, dt / done, done, kind, desc
 
 
-def train_config(args, world):
-    """The workload both arms are quoted on (BASELINE.json configs[1])."""
-    return {"workload": f"PraNet-V2 Res2Net-50 train step (fwd + 4x structure_loss + bwd + clamp + Adam), per-GPU batch {args.batch} @ {args.size}^2, random init",
-            "global_batch": world * args.batch, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
-            "l2": "inputs rotate over 4 batches; per-step working set (activations+grads) >> 126 MB L2"}
+def workload(args, world):
+    """The workload both arms are quoted on."""
+    cfg = CONFIGS[args.config]
+    if args.mode == "infer":
+        what = f"{cfg['label']} batched inference (eval forward + test-time rule -> uint8 maps)"
+    elif cfg["task"] == "multiclass":
+        what = f"{cfg['label']} train step (fwd + 15-subset dual loss + bwd + AdamW)"
+    else:
+        what = f"{cfg['label']} train step (fwd + 4x structure_loss + bwd + clamp + Adam)"
+    return {"workload": f"{what}, per-GPU batch {args.batch} @ {args.size}^2, random init, synthetic data",
+            "global_batch": world * args.batch, "parallelism": f"dp{world}" if args.mode == "train" else f"replicas x{world}"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ips, per = time_cpu(args.cpu_batch, args.size, args.steps, args.warmup)
+    ips, per, done, kind, desc = time_cpu(args.config, args.batch, args.size, args.steps, min(args.warmup, 1), args.ref_seconds, args.mode)
     cores = torch.get_num_threads()
-    sample = f"{args.steps} timed steps of batch {args.cpu_batch} @ {args.size}^2 (oracle port: stock Res2Net-50 on torch-CPU + oracle head/loss, fp32)"
+    sample = f"{done} timed step(s) of batch {args.batch} @ {args.size}^2 (<= {args.ref_seconds:.0f} s budget; {desc}; fp32, {cores} host threads)"
+    cfg = dict(workload(args, int(os.environ.get("WORLD_SIZE", "1"))), device="host CPU", cuda_graph=False)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": train_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC if (args.config == "res2net" and args.mode == "train") else cfg["workload"], "value": ips, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": done, "warmup": min(args.warmup, 1), "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def gpu_eager_reference(args, dev):
+    """The like-for-like "before" number: the reference's own modules in eager PyTorch on THIS GPU, same batch --
+    fp32 with cuDNN off (as the reference ships: MyTrain_med.py:16) and bf16 autocast + channels_last with cuDNN on, the latter
+    also replayed from a CUDA graph.  Full-step images/s, and the head + loss share as (full fwd+bwd) - (backbone-only fwd+bwd)."""
+    from oracle import ref_import as R
+    if not R.available():
+        return {"unavailable": "oracle/_ref not staged (run __graft_entry__.build() where /root/reference is mounted)"}
+    out = {"batch": args.batch, "size": args.size, "note": "reference modules (oracle/_ref), eager PyTorch on this GPU; CUDA events, 3 warm-up + 8 timed"}
+
+    def timed(fn, n=8, warm=3):
+        for _ in range(warm):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    saved = torch.backends.cudnn.enabled
+    try:
+        for variant, cudnn_on in (("fp32_cudnn_off", False), ("bf16_cl", True)):
+            torch.backends.cudnn.enabled = cudnn_on
+            try:
+                step, _, _ = reference_step_factory(args.config, args.batch, args.size, dev, "train", "bf16_cl" if variant == "bf16_cl" else "fp32")
+                ms = timed(step)
+                name = "fp32_cudnn_off" if variant == "fp32_cudnn_off" else "bf16_autocast_channels_last_cudnn_on"
+                out[name] = {"ms_per_step": ms, "images_per_s": args.batch / ms * 1e3}
+            except Exception as exc:      # noqa: BLE001
+                out[variant] = {"error": str(exc)[:200]}
+            torch.cuda.empty_cache()
+        # head + loss share on the bf16 / cuDNN-on variant: full fwd+bwd minus backbone-only fwd+bwd (the reference has no separable head)
+        torch.backends.cudnn.enabled = True
+        if args.config in ("res2net", "pvt"):
+            try:
+                from oracle import synth
+                model = R.build_binary(CONFIGS[args.config]["model"], num_class=1).to(dev).to(memory_format=torch.channels_last).train()
+                sl = R.structure_loss()
+                x = torch.randn(args.batch, 3, args.size, args.size, device=dev).contiguous(memory_format=torch.channels_last)
+                y = synth.ellipse_masks(args.batch, args.size, args.size, 1).to(dev)
+                bb = model.backbone
+
+                def full():
+                    model.zero_grad(set_to_none=True)
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        o = model(x)
+                    o = [t.float() for t in o]
+                    sum(sl(o[i], o[i + 4], y, 1 - y) for i in range(4)).backward()
+
+                def backbone_only():
+                    model.zero_grad(set_to_none=True)
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        if args.config == "res2net":
+                            t = bb.maxpool(bb.relu(bb.bn1(bb.conv1(x))))
+                            x1 = bb.layer1(t); x2 = bb.layer2(x1); x3 = bb.layer3(x2); x4 = bb.layer4(x3)
+                        else:
+                            _, x2, x3, x4 = bb(x)
+                    (x2.float().mean() + x3.float().mean() + x4.float().mean()).backward()
+                t_full, t_bb = timed(full), timed(backbone_only)
+                out["head_plus_loss_fwd_bwd_ms"] = {"full_fwd_bwd_ms": t_full, "backbone_only_fwd_bwd_ms": t_bb, "difference_ms": t_full - t_bb,
+                                                    "variant": "bf16 autocast, channels_last, cuDNN on, eager"}
+                # the same step replayed from a CUDA graph (launch overhead removed): what eager PyTorch can reach at best
+                try:
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        for _ in range(3):
+                            full()
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr):
+                        full()
+                    t_g = timed(gr.replay)
+                    with torch.cuda.graph(gr2 := torch.cuda.CUDAGraph()):
+                        backbone_only()
+                    t_gb = timed(gr2.replay)
+                    out["head_plus_loss_fwd_bwd_ms"]["cuda_graph"] = {"full_fwd_bwd_ms": t_g, "backbone_only_fwd_bwd_ms": t_gb, "difference_ms": t_g - t_gb}
+                except Exception as exc:      # noqa: BLE001
+                    out["head_plus_loss_fwd_bwd_ms"]["cuda_graph"] = {"error": str(exc)[:200]}
+                del model
+            except Exception as exc:      # noqa: BLE001
+                out["head_plus_loss_fwd_bwd_ms"] = {"error": str(exc)[:300]}
+    finally:
+        torch.backends.cudnn.enabled = saved
+        torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
+def build_model(P, config):
+    cfg = CONFIGS[config]
+    return getattr(P, cfg["model"])(**cfg["kw"])
+
+
+def make_batches(config, B, S, rank, nbuf=4):
+    """Pinned host batches (inputs change step to step; together with the activations far beyond the 126 MB L2)."""
+    from pranet_v2_b200 import synthetic as synth
+    g = torch.Generator().manual_seed(1000 + rank)
+    if CONFIGS[config]["task"] == "multiclass":
+        imgs = [torch.randn(B, 1, S, S, generator=g).pin_memory() for _ in range(nbuf)]
+        gts = [_labels(B, S, 9, 1000 + rank * 17 + i).pin_memory() for i in range(nbuf)]
+    else:
+        imgs = [torch.randn(B, 3, S, S, generator=g).pin_memory() for _ in range(nbuf)]
+        gts = [synth.ellipse_masks(B, S, S, 1000 + rank * 17 + i).pin_memory() for i in range(nbuf)]
+    return imgs, gts
+
+
+def make_train_step(P, config, dev, precision, use_graph):
+    from pranet_v2_b200.train import TrainStep
+    cfg = CONFIGS[config]
+    model = build_model(P, config)
+    if cfg["task"] == "multiclass":     # EMCAD/trainer.py:86: AdamW(lr, weight_decay=1e-4), no gradient clipping
+        return TrainStep(model, lr=1e-4, clip=0.0, autocast_backbone=(precision == "bf16"), device=dev, use_graph=use_graph,
+                         weight_decay=1e-4, decoupled=True, task="multiclass", num_classes=9)
+    return TrainStep(model, lr=1e-4, clip=0.5, autocast_backbone=(precision == "bf16"), device=dev, use_graph=use_graph)
+
+
+def time_train(ts, imgs_d, gts_d, steps, warmup, barrier):
+    nbuf = len(imgs_d)
+    for i in range(warmup):
+        ts.step_device(imgs_d[i % nbuf], gts_d[i % nbuf])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        ts.step_device(imgs_d[i % nbuf], gts_d[i % nbuf])
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def secondary_records(P, dev, args):
+    """BASELINE.json's other configurations, measured in the same run and embedded in the N = 1 line (device-resident, CUDA events,
+    3 warm-up + 10 timed steps each): Res2Net inference, PVT training + inference (config 3), EMCAD + DSRA training (config 4)."""
+    from pranet_v2_b200.train import InferStep
+    out = {}
+
+    def sync():
+        torch.cuda.synchronize()
+
+    def infer(config):
+        B, S = args.batch, CONFIGS[config]["size"]
+        inf = InferStep(build_model(P, config), device=dev, autocast=(args.precision == "bf16"), use_graph=not args.no_graph)
+        g = torch.Generator().manual_seed(7)
+        xs = [torch.randn(B, 3, S, S, generator=g).to(dev) for _ in range(4)]
+        for i in range(3):
+            inf.predict_device(xs[i % 4])
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(10):
+            inf.predict_device(xs[i % 4])
+        b.record()
+        sync()
+        ms = a.elapsed_time(b) / 10
+        return {"metric": f"infer images/sec @{S}^2 ({CONFIGS[config]['label']} eval forward + fused uint8 tail)", "value": B / ms * 1e3, "unit": UNIT,
+                "ms_per_step": ms, "batch": B, "gpu_launches_per_step": int(inf.pv2_launches_per_step), "dtype": args.precision}
+
+    def train(config):
+        B, S = args.batch, CONFIGS[config]["size"]
+        ts = make_train_step(P, config, dev, args.precision, not args.no_graph)
+        imgs, gts = make_batches(config, B, S, 0)
+        ms = time_train(ts, [t.to(dev) for t in imgs], [t.to(dev) for t in gts], 10, 3, sync) / 10
+        return {"metric": f"train images/sec @{S}^2 ({workload(argparse.Namespace(config=config, mode='train', batch=B, size=S), 1)['workload']})",
+                "value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "batch": B, "gpu_launches_per_step": int(ts.pv2_launches_per_step), "dtype": args.precision}
+
+    for name, fn, cfg in (("infer_res2net", infer, "res2net"), ("train_pvt", train, "pvt"), ("infer_pvt", infer, "pvt"), ("train_emcad", train, "emcad")):
+        try:
+            out[name] = fn(cfg)
+        except Exception as exc:      # noqa: BLE001 -- a secondary record must not take the headline down with it
+            out[name] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -169,8 +463,6 @@ def main():
 
     import torch.distributed as dist
     import pranet_v2_b200 as P
-    from pranet_v2_b200.train import TrainStep
-    from pranet_v2_b200 import synthetic as synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -185,15 +477,11 @@ def main():
 
     B, S = args.batch, args.size
     torch.manual_seed(0)
-    model = P.PraNet_V2(num_class=1)
     if args.mode == "infer":
-        return run_infer(args, P, model, dev, world, rank, local)
-    ts = TrainStep(model, lr=1e-4, clip=0.5, autocast_backbone=(args.precision == "bf16"), device=dev, use_graph=not args.no_graph)
-    g = torch.Generator().manual_seed(1000 + rank)
-    # a few distinct batches (> L2 together with the activations; inputs change step to step)
+        return run_infer(args, P, build_model(P, args.config), dev, world, rank, local)
+    ts = make_train_step(P, args.config, dev, args.precision, not args.no_graph)
     nbuf = 4
-    imgs_h = [torch.randn(B, 3, S, S, generator=g).pin_memory() for _ in range(nbuf)]
-    gts_h = [synth.ellipse_masks(B, S, S, 1000 + rank * 17 + i).pin_memory() for i in range(nbuf)]
+    imgs_h, gts_h = make_batches(args.config, B, S, rank, nbuf)
     imgs_d = [t.to(dev) for t in imgs_h]
     gts_d = [t.to(dev) for t in gts_h]
 
@@ -248,50 +536,37 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
-    # ---- roofline of the dominant pv2 kernel, timed live with CUDA events on the launching stream ----
-    roof = None
     if rank == 0:
-        roof = roofline_adam(P, dev, ts.bucket.n if hasattr(ts.bucket, "n") else ts.flat.numel())
-        roof["other_kernels"] = [roofline_structure_loss(P, dev, B, S)]
-        try:
-            roof["other_kernels"].append(roofline_bilinear(P, dev, B, S))
-        except Exception as exc:      # noqa: BLE001 -- an auxiliary measurement must not take the bench line down with it
-            roof["other_kernels"].append({"kernel": "bilinear_fwd/bwd_kernel (8 final maps)", "error": str(exc)[:200]})
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        roof["peak"] = hbm
-        roof["peak_source"] = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        roof["frac"] = roof["achieved"] / hbm
-        try:     # measured DRAM bytes per launch of the same kernel at the same size, from the committed ncu --set full capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["adam_clamp_flat_kernel"]
-            if tr["elements"] == roof["elements"]:
-                roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                roof["traffic_source"] = tr["source"]
-        except Exception:
-            pass
-        for o in roof["other_kernels"]:
-            if "achieved" in o:
-                o["frac"] = o["achieved"] / hbm
-                o["fwd"]["frac"] = o["fwd"]["achieved"] / hbm
+        n_params = ts.bucket.n if hasattr(ts.bucket, "n") else ts.flat.numel()
+        h2d = imgs_h[0].numel() * imgs_h[0].element_size() + gts_h[0].numel() * gts_h[0].element_size()
+        cfg = dict(workload(args, world), cuda_graph=not args.no_graph, loss_from_lowres=bool(ts.loss_from_lowres),
+                   l2="inputs rotate over 4 batches; per-step working set (activations + gradients) >> 126 MB L2")
         out = {
-            "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": dict(train_config(args, world), loss_from_lowres=bool(ts.loss_from_lowres)),
-            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": imgs_h[0].numel() * 4 + gts_h[0].numel() * 4, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "metric": METRIC if args.config == "res2net" else cfg["workload"], "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
-            ips, per = time_cpu(args.cpu_batch, S, 3, 1)
-            out["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                   "sample": f"3 timed steps (1 warm-up) of batch {args.cpu_batch} @ {S}^2: stock Res2Net-50 on torch-CPU + oracle head/loss, fp32"}
+        del ts
+        torch.cuda.empty_cache()
+        # ---- roofline of the dominant hot-path kernel (the tcgen05 conv) and of the other pv2 kernels, timed live ----
+        try:
+            out["roofline"] = roofline_report(P, dev, B if args.config != "emcad" else 16, 352, n_params)
+        except Exception as exc:      # noqa: BLE001
+            out["roofline"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+        if world == 1:
+            if not args.no_cpu_baseline:      # the CPU baseline is reported at N = 1 only: a bounded sample of the same workload
+                try:
+                    ips, per, done, kind, desc = time_cpu(args.config, B, S, 2, 1, 25.0)
+                    out["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                           "sample": f"{done} timed step(s) (1 warm-up, <= 25 s) of batch {B} @ {S}^2: {desc}; fp32"}
+                except Exception as exc:      # noqa: BLE001
+                    out["cpu_baseline"] = {"error": str(exc)[:300]}
+            if not args.no_eager_reference:
+                out["gpu_eager_reference"] = gpu_eager_reference(args, dev)
+            if not args.no_secondary and args.config == "res2net":
+                out["secondary"] = secondary_records(P, dev, args)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -347,16 +622,114 @@ def run_infer(args, P, model, dev, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
     if rank == 0:
+        cfg = dict(workload(args, world), cuda_graph=not args.no_graph, l2="inputs rotate over 4 batches")
         print(json.dumps({
-            "metric": "infer images/sec @352^2 (PraNet-V2 Res2Net-50 forward + fused uint8 tail)", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
+            "metric": f"infer images/sec @{S}^2 ({CONFIGS[args.config]['label']} forward + fused uint8 tail)", "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"PraNet-V2 Res2Net-50 batched inference (eval forward + p2+p3+p4+p5 / resize / sigmoid / min-max / uint8 tail), per-GPU batch {B} @ {S}^2",
-                       "global_batch": world * B, "parallelism": f"replicas x{world}", "cuda_graph": not args.no_graph, "l2": "inputs rotate over 4 batches"},
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": imgs_h[0].numel() * 4, "d2h_bytes_per_step": out_h.numel()},
             "gpu_launches": int(inf.pv2_launches_per_step * args.steps), "clocks": clocks}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def roofline_report(P, dev, B, S, n_params):
+    """`roofline` of the bench line: the dominant hot-path kernel -- the persistent tcgen05 implicit-GEMM conv (102 of the ~440 pv2
+    launches of a head step, the largest share of its kernel time) -- as the FLOP-weighted aggregate over the head's seven distinct
+    forward shapes with the BatchNorm statistics fused, against the measured bf16 peak; `shapes` lists each; `other_kernels` carries
+    the memory-bound kernels (structure loss fwd / bwd, final upsamples fwd / bwd, V1 reverse-attention scale, multiclass dual loss,
+    optimizer tail) against the measured HBM copy peak.  Every number: CUDA events, launches captured in a CUDA graph (the launches
+    take 5-40 us, less than a ctypes call costs on the host), inputs rotating over sets larger than the L2.  `traffic` = DRAM bytes
+    per launch from the committed ncu --set full capture (profiles/ncu_traffic.json) where one exists."""
+    import bench_head
+    hbm, tfl, src = bench_head.peaks()
+    rows = bench_head.kernel_table(P, dev, B, S, hbm, tfl)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        traffic = {}
+    convs = [r for r in rows if r["bound"] == "tensor" and r["kernel"].startswith("conv_fwd+bn_stats")]
+    plain = {r["kernel"].replace("conv_fwd ", ""): r for r in rows if r["bound"] == "tensor" and r["kernel"].startswith("conv_fwd ")}
+    fl, us = sum(r["flops"] for r in convs), sum(r["us"] for r in convs)
+    roof = {"kernel": "conv_fwd2_kernel<bf16> (tcgen05 / TMEM / TMA implicit GEMM, BatchNorm statistics fused): FLOP-weighted over the head's 7 forward shapes",
+            "bound": "tensor", "achieved": fl / (us * 1e-6) / 1e12, "peak": tfl, "unit": "TFLOP/s", "frac": fl / (us * 1e-6) / 1e12 / tfl,
+            "peak_source": f"{src}: bf16_tflops (burst; each kernel is timed alone)", "flops_per_launch_set": fl, "us_per_launch_set": us,
+            "traffic": traffic.get("conv_fwd2_kernel", {}).get("dram_bytes_per_launch_set"),
+            "shapes": [{"shape": r["kernel"].replace("conv_fwd+bn_stats ", ""), "flops": r["flops"], "us": r["us"], "tflops": r["achieved_tflops"],
+                        "frac": r["frac_of_bf16_peak"], "us_without_bn_stats": plain.get(r["kernel"].replace("conv_fwd+bn_stats ", ""), {}).get("us")} for r in convs],
+            "note": "2*M*N*K un-padded; 24 launches per shape captured in a CUDA graph, inputs rotate over > 300 MB"}
+    others = []
+    for r in rows:
+        if r["bound"] != "hbm" or r["kernel"].startswith("yardstick"):
+            continue
+        key = r["kernel"].split(" (")[0]
+        tr = traffic.get(key)
+        others.append({"kernel": r["kernel"], "bound": "hbm", "achieved": r["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": r["frac_of_hbm_peak"],
+                       "bytes_per_launch": r["bytes"], "avg_ms": r["us"] * 1e-3,
+                       "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr and "dram_bytes_read" in tr else None})
+    for fn in (lambda: roofline_mc_loss(P, dev), lambda: roofline_adam(P, dev, n_params)):
+        try:
+            o = fn()
+            o["peak"], o["frac"] = hbm, o["achieved"] / hbm
+            tr = traffic.get(o.pop("traffic_key", ""), None)
+            if tr and tr.get("elements", o.get("elements")) == o.get("elements"):
+                o["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            others.append(o)
+        except Exception as exc:      # noqa: BLE001
+            others.append({"error": str(exc)[:200]})
+    roof["other_kernels"] = others
+    roof["hbm_peak_source"] = f"{src}: hbm_gbs (measured copy)"
+    return roof
+
+
+def roofline_mc_loss(P, dev, B=16, C=9, S=224, n=12, reps=5):
+    """Multiclass dual loss (EMCAD/trainer.py:123-140) at config 4's shape: forward and backward launches, algorithmic bytes
+    fwd = P*8*4 (eight logit maps) + 8 B/px labels, bwd = the same reads + P*8*4 gradient bytes written."""
+    g = torch.Generator().manual_seed(3)
+    sets = [[torch.randn(B, C, S, S, generator=g).to(dev).requires_grad_(True) for _ in range(8)] for _ in range(3)]
+    labels = _labels(B, S, C, 5).to(dev)
+
+    def fwd(j):
+        return P.mc_dual_loss(sets[j][:4], sets[j][4:], labels, C)
+
+    def fb(j):
+        for t in sets[j]:
+            t.grad = None
+        fwd(j).backward()
+
+    def timed(fn):
+        fn(0)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn(0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for it in range(n):
+                fn(it % len(sets))
+        gr.replay()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            gr.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3 / (reps * n)
+
+    with torch.no_grad():
+        t_f = timed(lambda j: fwd(j))
+    t_fb = timed(fb)
+    px = B * C * S * S
+    bytes_f = px * 8 * 4 + B * S * S * 8
+    bytes_b = bytes_f + px * 8 * 4
+    return {"kernel": f"mc_dual_loss fwd+bwd (15 subsets, {B}x{C}x{S}^2)", "bound": "hbm", "achieved": (bytes_f + bytes_b) / t_fb / 1e9, "unit": "GB/s",
+            "bytes_per_launch": bytes_f + bytes_b, "avg_ms": t_fb * 1e3, "traffic": None,
+            "fwd": {"kernel": "mc_dual_loss fwd", "achieved": bytes_f / t_f / 1e9, "bytes_per_launch": bytes_f, "avg_ms": t_f * 1e3},
+            "note": f"{n} fwd(+bwd) calls captured in a CUDA graph, {reps} replays; logits rotate over 3 sets"}
 
 
 def roofline_adam(P, dev, n, iters=20):
@@ -387,109 +760,8 @@ def roofline_adam(P, dev, n, iters=20):
     torch.cuda.synchronize()
     t = a.elapsed_time(b) * 1e-3 / iters
     return {"kernel": "adam_clamp_flat_kernel (clip_gradient + Adam, flat parameters)", "bound": "hbm", "achieved": 28.0 * n / t / 1e9, "unit": "GB/s",
-            "bytes_per_launch": 28 * n, "elements": n, "avg_ms": t * 1e3, "traffic": None,
+            "bytes_per_launch": 28 * n, "elements": n, "avg_ms": t * 1e3, "traffic": None, "traffic_key": "adam_clamp_flat_kernel",
             "note": f"{iters} back-to-back C-ABI launches between two CUDA events; 4 x {4 * n / 1e6:.0f} MB buffers (> L2)"}
-
-
-def roofline_structure_loss(P, dev, B, S, iters=24):
-    """structure_loss x4 backward: the largest-traffic pv2 launch of the step, timed live with CUDA events
-    around back-to-back C-ABI launches on torch's current stream (inputs rotate over sets larger than L2).
-    Algorithmic bytes / launch = P * (4 [mask] + 4 scales * (8 read + 8 written)) fp32, P = B*S*S."""
-    from pranet_v2_b200 import synthetic as synth
-    lib = P._lib.load()
-    st = torch.cuda.current_stream().cuda_stream
-    shape = (B, 1, S, S)
-    m = synth.ellipse_masks(B, S, S, 3).to(dev)
-    nset = 6    # 6 sets x (8 logits + 8 grads) x 7.9 MB  ~ 760 MB at B=16: far beyond the 126 MB L2
-    logits = [[torch.randn(shape, device=dev) for _ in range(8)] for _ in range(nset)]
-    grads = [[torch.empty(shape, device=dev) for _ in range(8)] for _ in range(nset)]
-    ws_bytes = lib.pv2_structure_loss_workspace_bytes(B, S, S, 4)
-    ws = torch.empty(ws_bytes // 4, device=dev)
-    loss = torch.empty(4, device=dev)
-    gl = torch.ones(4, device=dev)
-    packs = []
-    for j in range(nset):
-        packs.append((P._lib.ptr_array(logits[j][:4]), P._lib.ptr_array(logits[j][4:]), P._lib.ptr_array(grads[j][:4]), P._lib.ptr_array(grads[j][4:])))
-
-    def fwd(j):
-        (pp, _), (pb, _), _, _ = packs[j]
-        P._lib.check(lib.pv2_structure_loss_fwd(pp, pb, m.data_ptr(), None, 4, B, S, S, 0, loss.data_ptr(), ws.data_ptr(), ws_bytes, st), "fwd")
-
-    def bwd(j):
-        (pp, _), (pb, _), (dp, _), (dq, _) = packs[j]
-        P._lib.check(lib.pv2_structure_loss_bwd(pp, pb, m.data_ptr(), None, gl.data_ptr(), dp, dq, 4, B, S, S, 0, ws.data_ptr(), ws_bytes, st), "bwd")
-
-    def timed(fn):
-        for j in range(nset):
-            fn(j)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        for it in range(iters):
-            fn(it % nset)
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) * 1e-3 / iters
-
-    fwd(0)
-    t_f, t_b = timed(fwd), timed(bwd)
-    px = B * S * S
-    bytes_bwd, bytes_fwd = px * (4 + 4 * 16), px * (4 + 4 * 8)
-    return {"kernel": "structure_loss_bwd_kernel<float> (x4 scales)", "bound": "hbm", "achieved": bytes_bwd / t_b / 1e9, "unit": "GB/s",
-            "bytes_per_launch": bytes_bwd, "avg_ms": t_b * 1e3, "traffic": None,
-            "fwd": {"kernel": "structure_loss_fwd_kernel<float> (x4 scales) + finalize", "achieved": bytes_fwd / t_f / 1e9,
-                    "bytes_per_launch": bytes_fwd, "avg_ms": t_f * 1e3},
-            "note": f"{iters} back-to-back C-ABI launches between two CUDA events; inputs rotate over {nset} sets (> L2)"}
-
-
-def roofline_bilinear(P, dev, B, S, n=24, reps=5):
-    """The eight final upsamples of a step (pranet.py:349-350,370-371,392-393,414-415: x8, x16, x32, x8 for fg and bg) as the head
-    issues them -- one pv2_bilinear_multi_fwd launch, one pv2_bilinear_multi_bwd launch.  These launches take 12-27 us, less than a
-    ctypes call costs on the host, so `n` of them are captured in a CUDA graph (maps rotate over 4 sets, 4 x 63 MB > L2) and the
-    replay is timed with CUDA events.  Algorithmic bytes / launch = (8 full-resolution maps + their low-res sources) * 4."""
-    import ctypes
-    from pranet_v2_b200.ops import PV2_F32, _ratio
-    lib = P._lib.load()
-    scs = (8, 16, 32, 8, 8, 16, 32, 8)
-    nset = 4
-    lows = [[torch.randn(B, 1, S // s, S // s, device=dev) for s in scs] for _ in range(nset)]
-    his = [[torch.randn(B, 1, S, S, device=dev) for _ in scs] for _ in range(nset)]
-    ihs = (ctypes.c_int * 8)(*[S // s for s in scs])
-    rr = (ctypes.c_float * 8)(*[_ratio(S // s, S, False, float(s)) for s in scs])
-    pk = [(P._lib.ptr_array(lows[j]), P._lib.ptr_array(his[j])) for j in range(nset)]
-
-    def fwd(j):
-        (pl, _), (ph, _) = pk[j]
-        P._lib.check(lib.pv2_bilinear_multi_fwd(pl, ph, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, torch.cuda.current_stream().cuda_stream), "bilinear_multi_fwd")
-
-    def bwd(j):
-        (pl, _), (ph, _) = pk[j]
-        P._lib.check(lib.pv2_bilinear_multi_bwd(ph, pl, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, torch.cuda.current_stream().cuda_stream), "bilinear_multi_bwd")
-
-    def timed(fn):
-        fn(0)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for it in range(n):
-                fn(it % nset)
-        g.replay()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(reps):
-            g.replay()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) * 1e-3 / (reps * n)
-
-    t_f, t_b = timed(fwd), timed(bwd)
-    nbytes = (8 * B * S * S + sum(B * (S // s) ** 2 for s in scs)) * 4
-    return {"kernel": "bilinear_bwd_kernel<float> (8 final maps, one launch)", "bound": "hbm", "achieved": nbytes / t_b / 1e9, "unit": "GB/s",
-            "bytes_per_launch": nbytes, "avg_ms": t_b * 1e3, "traffic": None,
-            "fwd": {"kernel": "bilinear_fwd_kernel<float> (8 final maps, one launch)", "achieved": nbytes / t_f / 1e9,
-                    "bytes_per_launch": nbytes, "avg_ms": t_f * 1e3},
-            "note": f"{n} launches captured in a CUDA graph, {reps} replays between two CUDA events; maps rotate over {nset} sets (> L2)"}
 
 
 if __name__ == "__main__":

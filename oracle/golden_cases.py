@@ -112,6 +112,26 @@ MC_CASES = {
     "mist_c9": dict(kind="mist", channels=[768, 384, 192, 96], num_class=9, B=1, size=64, training=False),
 }
 
+# ---- the drop-in decoder classes (pranet_v2_b200.multiclass) against the reference decoders, every weight synthetic ----
+MC_DEC_CASES = {
+    "mcdec_emcad_c9": dict(kind="emcad", channels=[512, 320, 128, 64], num_class=9, B=2, size=64, kw=dict(expansion_factor=2, activation="relu")),
+    "mcdec_merit_c4": dict(kind="merit", channels=[768, 384, 192, 96], num_class=4, B=2, size=64, kw=dict(use_softmax=True)),
+}
+
+
+def mc_dec_pyramid(name):
+    c = MC_DEC_CASES[name]
+    seed = hash_name(name)
+    return [torch.randn(c["B"], ch, c["size"] // s, c["size"] // s, generator=synth._gen(seed, f"pyr{i}"))
+            for i, (ch, s) in enumerate(zip(c["channels"], (32, 16, 8, 4)))]
+
+
+def mc_dec_out_weights(name, shapes):
+    """Fixed random cotangents: the scalar that is backpropagated is sum_i <w_i, out_i>."""
+    seed = hash_name(name)
+    return [torch.randn(tuple(sh), generator=synth._gen(seed, f"cot{i}")) for i, sh in enumerate(shapes)]
+
+
 # ---- multiclass dual loss -------------------------------------------------------------
 MC_LOSS_CASES = {
     "mcl_c9_32": dict(num_class=9, B=2, H=32, W=32),

@@ -189,6 +189,50 @@ def gen_multiclass():
         _save(name, **arrays)
 
 
+def gen_mc_decoders():
+    """The reference's dual decoders (EMCAD_dual, CASCADE_Add_dual) with EVERY weight synthetic (keyed by parameter name), train mode,
+    forward + backward of a fixed linear functional of the outputs: what pranet_v2_b200.multiclass must reproduce from the same
+    state_dict.  Also freezes the state_dict key / shape lists of the three decoder classes and of EMCADNet(dual=True)."""
+    import json
+    keys = {}
+    for name, case in G.MC_DEC_CASES.items():
+        ch, nc = case["channels"], case["num_class"]
+        if case["kind"] == "emcad":
+            dec = R.emcad_decoders().EMCAD_dual(channels=ch, num_class=nc, **case["kw"])
+        else:
+            dec = R.merit_decoders().CASCADE_Add_dual(channels=ch, num_class=nc, **case["kw"])
+        dec.load_state_dict(synth.synth_state_dict(dec.state_dict(), seed=4))
+        dec.train()
+        pyr = [p.clone().requires_grad_(True) for p in G.mc_dec_pyramid(name)]
+        outs = list(dec(pyr[0], pyr[1:]))[:8]
+        cots = G.mc_dec_out_weights(name, [o.shape for o in outs])
+        sum((o * w).sum() for o, w in zip(outs, cots)).backward()
+        arrays = {f"out{i}": _np(o) for i, o in enumerate(outs)}
+        arrays.update({f"dpyr{i}": _np(p.grad) for i, p in enumerate(pyr)})
+        for k, p in dec.named_parameters():
+            g = p.grad.double() if p.grad is not None else torch.zeros(1, dtype=torch.double)
+            arrays["dw:" + k] = np.array([g.sum().item(), g.norm().item()])
+        post = dec.state_dict()
+        for k in post:
+            if k.endswith(("running_mean", "running_var")) and ("_fg." in k or "_bg." in k):
+                arrays["stat:" + k] = _np(post[k])
+        _save(name, **arrays)
+    # key / shape fixtures
+    mk = lambda m: {k: list(v.shape) for k, v in m.state_dict().items()}
+    keys["EMCAD_dual"] = mk(R.emcad_decoders().EMCAD_dual(channels=[512, 320, 128, 64], num_class=9))
+    keys["CASCADE_Add_dual"] = mk(R.merit_decoders().CASCADE_Add_dual(channels=[768, 384, 192, 96], num_class=4))
+    keys["CAM"] = mk(R.mist_cam().CAM("SSS", channels=[768, 384, 192, 96], n_class=9))
+    try:
+        net = R.emcad_networks().EMCADNet(num_classes=9, encoder="pvt_v2_b2", pretrain=False, dual=True)
+        keys["EMCADNet"] = mk(net)
+    except Exception as exc:      # noqa: BLE001
+        print("  EMCADNet keys not frozen:", exc)
+    path = os.path.join(G.GOLDEN_DIR, "mc_state_dict_keys.json")
+    with open(path, "w") as f:
+        json.dump(keys, f, sort_keys=True)
+    print(f"  wrote mc_state_dict_keys.json ({os.path.getsize(path) / 1024:.0f} KiB, {sum(len(v) for v in keys.values())} keys)")
+
+
 def gen_mc_loss():
     powerset, DiceLoss, to_inv = R.emcad_loss_pieces()
     for name, case in G.MC_LOSS_CASES.items():
@@ -255,7 +299,8 @@ def gen_tail():
         _save(name, labels=np.stack(labels))
 
 
-GROUPS = {"tail": gen_tail, "sl": gen_structure_loss, "ll": gen_lowres_loss, "head": gen_heads, "mc": gen_multiclass, "mcl": gen_mc_loss, "full": gen_full}
+GROUPS = {"tail": gen_tail, "sl": gen_structure_loss, "ll": gen_lowres_loss, "head": gen_heads, "mc": gen_multiclass, "mcdec": gen_mc_decoders,
+          "mcl": gen_mc_loss, "full": gen_full}
 
 if __name__ == "__main__":
     assert R.available(), "reference not mounted; golden vectors can only be generated in the builder container"

@@ -32,7 +32,17 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REF = os.environ.get("PV2_REFERENCE_ROOT", "/root/reference")
+def _root() -> str:
+    """The mounted reference (builder container) or the byte-for-byte staged copy oracle/_ref (oracle/build_ref.py; GPU box)."""
+    env = os.environ.get("PV2_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/binary_seg/lib"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REF = _root()
 
 
 def available() -> bool:

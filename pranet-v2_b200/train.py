@@ -31,6 +31,9 @@ def _unused_prefixes(model) -> tuple:
     to grayscale input (pranet.py:190-191): there it trains like every other parameter, as in the reference's Adam over
     model.parameters()."""
     from .models import PraNet_V2
+    from .multiclass import EMCADNet
+    if isinstance(model, EMCADNet):          # the single-supervision heads are never applied in dual mode (EMCAD/lib/networks.py:114-125)
+        return _UNUSED_PREFIXES + ("out_head",)
     return _UNUSED_PREFIXES + (("conv.",) if isinstance(model, PraNet_V2) else ())
 
 
@@ -133,12 +136,22 @@ class FlatParams:
 class TrainStep:
     def __init__(self, model: nn.Module, lr: float = 1e-4, clip: float = 0.5, autocast_backbone: bool = True,
                  device=None, channels_last: bool = True, use_graph: bool = True, optimizer: str = "pv2",
-                 weight_decay: float = 0.0, decoupled: bool = False, loss_from_lowres: bool = None):
+                 weight_decay: float = 0.0, decoupled: bool = False, loss_from_lowres: bool = None,
+                 task: str = "binary", num_classes: int = None, supervision: str = "mutation"):
         """loss_from_lowres: stop the head at the low-res maps and let ops.structure_loss_lowres do the final
         upsamples inside the loss kernels (same losses and gradients up to fp32 summation order; the eight full-resolution maps
         and their gradients are never written).  False = the reference's data flow: model(images) -> 8 maps -> structure_loss."""
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.model = model.to(self.device).train()
+        # task = "multiclass": one step of multiclass_seg/EMCAD/trainer.py:97-157 -- model(images, mode='train') -> 4 fg + 4 bg maps,
+        # the dual loss over all non-empty subsets of the four scales (ops.mc_dual_loss, labels (B, H, W) int64), AdamW
+        if task not in ("binary", "multiclass"):
+            raise ValueError(f"task must be 'binary' or 'multiclass', got {task!r}")
+        self.task, self.num_classes, self.supervision = task, num_classes, supervision
+        if task == "multiclass":
+            if num_classes is None:
+                raise ValueError("task='multiclass' needs num_classes")
+            loss_from_lowres = False
         if loss_from_lowres is None:                                  # PV2_LOSS_LOWRES=0|1 overrides the default (A/B measurements)
             loss_from_lowres = os.environ.get("PV2_LOSS_LOWRES", LOSS_FROM_LOWRES_DEFAULT) == "1"
         self.loss_from_lowres = bool(loss_from_lowres) and hasattr(self.model, "forward_features_lowres")
@@ -177,6 +190,14 @@ class TrainStep:
     def _fwd_bwd(self, images, gts):
         for p in self.params:
             p.grad = None
+        if self.task == "multiclass":
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+                outs = self.model(images, mode="train")
+            loss = ops.mc_dual_loss([o.float() for o in outs[:4]], [o.float() for o in outs[4:]], gts, self.num_classes,
+                                    supervision=self.supervision)      # EMCAD/trainer.py:123-140
+            loss.backward()
+            self.bucket.gather([p.grad for p in self.params])
+            return loss.detach()
         prepared = None
         if not self.loss_from_lowres and gts.dim() == 4 and gts.shape[1] == getattr(self.model, "num_class", gts.shape[1]):
             # the loss's boundary weight depends on the mask only: a branch that forks here and joins before the loss (it hides

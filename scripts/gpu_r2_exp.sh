@@ -1,10 +1,16 @@
 #!/bin/bash
-mkdir -p gpurun_out /tmp/ncu
-run() { echo "== $1"; shift; env "$@" timeout 200 python bench_head.py --batches 16 --sizes 352 --iters 40 2>&1 | grep ms_graph | cut -c1-110; }
-run base A=1
-run maxgrid96 PV2_CONV_MAXGRID=96
-run v1 PV2_CONV_V1=1
-timeout 900 python -m pytest tests/ -x -q -m gpu 2>&1 | tail -4
-PV2_TRACE=gpurun_out/r2_timeline_v2.txt timeout 300 python bench_head.py --batches 16 --sizes 352 --iters 20 --kernels --out gpurun_out/r2_head_kernels_v2.jsonl > gpurun_out/r2_trace.log 2>&1; echo "trace rc=$?"
-grep -E '"kernel": "(conv_fwd\+|struct)' gpurun_out/r2_trace.log | cut -c1-170
-head -14 gpurun_out/r2_timeline_v2.txt
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/ -x -q -m gpu -k "multiclass or bench_config" 2>&1 | tail -6
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; echo "bench rc=$?"; tail -3 gpurun_out/r2_bench_default.err | cut -c1-300
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench_default.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e'])
+r=d.get('roofline',{})
+print('roofline', {k:r.get(k) for k in ('achieved','frac','error')})
+for sh in r.get('shapes',[]): print('   ', sh['shape'][:60], round(sh['us'],1), round(sh['frac'],3), sh.get('us_without_bn_stats'))
+for o in r.get('other_kernels',[]): print('   ', str(o.get('kernel'))[:70], round(o.get('avg_ms',0)*1e3,1), round(o.get('frac',0),3), o.get('error'))
+print('cpu_baseline', d.get('cpu_baseline'))
+print('eager', json.dumps(d.get('gpu_eager_reference'))[:900])
+print('secondary', json.dumps(d.get('secondary'))[:1200])
+PY

@@ -1,0 +1,108 @@
+"""GPU parity of the multiclass DSRA integrations.
+
+1. The drop-in decoder classes (pranet_v2_b200.multiclass.EMCAD_dual / CASCADE_Add_dual), given the state_dict of the
+   reference class (every weight synthetic, keyed by parameter name), reproduce the reference decoder's outputs, its input
+   gradients, its parameter-gradient norms and its BatchNorm running statistics -- forward AND backward, train mode
+   (goldens `mcdec_*`, frozen from the unmodified reference by `python -m oracle.make_golden mcdec`).
+2. `DSRAStages` backward on the decoder features captured from the reference decoders (goldens `emcad_c9`, `merit_c4`,
+   `mist_c9`) against the CPU oracle's autograd (oracle.dsra_oracle.dual_heads_cascade).
+Reference: EMCAD/lib/decoders.py:454-526, MERIT/lib/decoders.py:342-431, MIST/lib/MIST.py:418-451."""
+import numpy as np
+import pytest
+import torch
+
+import pranet_v2_b200 as P
+from pranet_v2_b200 import engine as E
+from oracle import dsra_oracle as O
+from oracle import golden_cases as G
+from oracle import synth, templates
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.fixture(autouse=True)
+def _fp32():
+    E.set_precision("fp32")
+    yield
+    E.set_precision("auto")
+
+
+@pytest.mark.parametrize("name", list(G.MC_DEC_CASES))
+def test_decoder_class_matches_reference(name):
+    case = G.MC_DEC_CASES[name]
+    g = G.load(name)
+    ch, nc = case["channels"], case["num_class"]
+    dec = (P.EMCAD_dual if case["kind"] == "emcad" else P.CASCADE_Add_dual)(channels=ch, num_class=nc, **case["kw"])
+    dec.load_state_dict(synth.synth_state_dict(dec.state_dict(), seed=4))      # same names -> same weights as the reference run
+    dec = dec.to(DEV).train()
+    pyr = [p.to(DEV).requires_grad_(True) for p in G.mc_dec_pyramid(name)]
+    outs = list(dec(pyr[0], pyr[1:]))
+    if case["kind"] == "merit":
+        assert len(outs) == 9 and outs[8].shape[1] == ch[3]                      # the 9-tuple ends with d1
+    outs = outs[:8]
+    for i, o in enumerate(outs):
+        ref = g[f"out{i}"]
+        err = np.abs(o.detach().cpu().numpy() - ref).max()
+        assert err <= 1e-3 * max(1.0, np.abs(ref).max()), f"{name} out{i}: {err:.3e}"
+    cots = G.mc_dec_out_weights(name, [o.shape for o in outs])
+    sum((o * w.to(DEV)).sum() for o, w in zip(outs, cots)).backward()
+    for i, p in enumerate(pyr):
+        ref = g[f"dpyr{i}"]
+        err = np.abs(p.grad.cpu().numpy() - ref).max()
+        assert err <= 3e-3 * np.abs(ref).max(), f"{name} dpyr{i}: {err:.3e} of {np.abs(ref).max():.3e}"
+    checked = 0
+    for k, p in dec.named_parameters():
+        ref = g["dw:" + k]
+        if p.grad is None:
+            assert ref[1] == 0.0, k
+            continue
+        gn = p.grad.double().norm().item()
+        assert abs(gn - ref[1]) <= 3e-3 * ref[1] + 1e-6, f"{name} grad norm of {k}: {gn:.6e} vs {ref[1]:.6e}"
+        checked += 1
+    assert checked > 50
+    post = dec.state_dict()
+    for k in [k for k in g if k.startswith("stat:")]:
+        np.testing.assert_allclose(post[k[5:]].float().cpu().numpy(), g[k], rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["emcad_c9", "merit_c4", "merit_c9_linear", "mist_c9"])
+def test_dsra_stages_backward_vs_oracle(name):
+    case = G.MC_CASES[name]
+    g = G.load(name)
+    bn = case["kind"] != "mist"
+    names = ("ConvBlock4", "ConvBlock3", "ConvBlock2", "ConvBlock1") if bn else ("out_head1", "out_head2", "out_head3", "out_head4")
+    ks = (1, 3, 3, 3) if bn else (1, 1, 1, 1)
+    host = torch.nn.Module()
+    stages = P.DSRAStages(host, case["channels"], case["num_class"], names, ks, bn, case.get("use_softmax", True))
+    sd = synth.synth_state_dict(templates.dual_heads(case["channels"], case["num_class"], names, ks, bn), seed=2)
+    host.load_state_dict(sd)
+    host.to(DEV).train(case["training"])
+    feats = [torch.from_numpy(g[f"d{i}"]).to(DEV).requires_grad_(True) for i in range(4)]
+    outs = stages(feats)
+    for i, o in enumerate(outs):
+        assert np.abs(o.detach().cpu().numpy() - g[f"out{i}"]).max() <= 1e-3, f"{name} out{i}"
+    gen = torch.Generator().manual_seed(17)
+    cots = [torch.randn(o.shape, generator=gen) for o in outs]
+    sum((o * w.to(DEV)).sum() for o, w in zip(outs, cots)).backward()
+    # oracle: same features, same weights, autograd on the CPU
+    rfeats = [torch.from_numpy(g[f"d{i}"]).clone().requires_grad_(True) for i in range(4)]
+    rsd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+    routs = O.dual_heads_cascade(rfeats, rsd, kernel_sizes=ks, use_softmax=case.get("use_softmax", True), training=case["training"],
+                                 names=names, bn=bn)
+    sum((o * w).sum() for o, w in zip(routs, cots)).backward()
+    for i, (f, rf) in enumerate(zip(feats, rfeats)):
+        err = (f.grad.cpu() - rf.grad).abs().max().item()
+        assert err <= 2e-3 * rf.grad.abs().max().item(), f"{name} dfeat{i}: {err:.3e}"
+    n = 0
+    for k, p in host.named_parameters():
+        r = rsd[k].grad
+        if r is None:
+            continue
+        err = (p.grad.cpu() - r).abs().max().item()
+        assert err <= 2e-3 * max(r.abs().max().item(), 1e-6), f"{name} grad of {k}: {err:.3e}"
+        n += 1
+    assert n >= 8
+
