@@ -40,13 +40,14 @@ template <int C> struct Row { static constexpr int N = 2 + 2 * C; };
 template <int C>
 __global__ void __launch_bounds__(MC_THREADS)
 mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mode, long long npix, int HW,
-                   float* __restrict__ partials /* [grid][nsub*Row + C] */) {
+                   float* __restrict__ partials /* [grid][nsub*Row + C] */, unsigned int* __restrict__ ticket) {
     pv2::pdl_prologue();
     constexpr int R = Row<C>::N;
     const int nsub = mode == 0 ? (1 << n) - 1 : n;
     extern __shared__ float sacc[];                     // [warps][nsub*R + C]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = MC_THREADS / 32;
     const int width = nsub * R + C;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *ticket = 0u;      // the fold kernel that follows counts on it
     for (int i = threadIdx.x; i < nw * width; i += MC_THREADS) sacc[i] = 0.0f;
     __syncthreads();
     float* my = sacc + warp * width;
@@ -115,31 +116,64 @@ mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mo
     }
 }
 
-// one CTA: totals[i] = sum over CTA rows (fixed order); loss from the totals
+// totals[i] = sum over the forward kernel's CTA rows, loss from the totals.  CTA = 8 columns x 32 row lanes: a lane adds rows
+// lane, lane+32, ... with four independent accumulators (one CTA walking all 1184 rows one dependent load at a time took 217 us),
+// the lanes are folded in lane order: a fixed order, bit-reproducible.  The CTA that draws the last ticket computes the scalar.
 template <int C>
-__global__ void mc_loss_fold_kernel(const float* __restrict__ partials, int nrows, int nsub, long long npix,
-                                    float lc_ce, float lc_dice, float lc_bce, float* __restrict__ totals, float* __restrict__ loss) {
+__global__ void __launch_bounds__(256)
+mc_loss_fold_kernel(const float* __restrict__ partials, int nrows, int nsub, long long npix,
+                    float lc_ce, float lc_dice, float lc_bce, float* __restrict__ totals, float* __restrict__ loss, unsigned int* __restrict__ ticket) {
     pv2::pdl_prologue();
     constexpr int R = Row<C>::N;
     const int width = nsub * R + C;
-    for (int i = threadIdx.x; i < width; i += blockDim.x) {
-        float v = 0.0f;
-        for (int r = 0; r < nrows; ++r) v += partials[(size_t)r * width + i];
-        totals[i] = v;
+    __shared__ float sh[32][9];
+    __shared__ float sterm[32];
+    __shared__ bool is_last;
+    const int cl = threadIdx.x & 7, lane = threadIdx.x >> 3;
+    const int col = blockIdx.x * 8 + cl;
+    float v = 0.0f;
+    if (col < width) {
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        const float* src = partials + col;
+        int r = lane;
+        for (; r + 96 < nrows; r += 128) {
+            a0 += src[(size_t)r * width]; a1 += src[(size_t)(r + 32) * width];
+            a2 += src[(size_t)(r + 64) * width]; a3 += src[(size_t)(r + 96) * width];
+        }
+        for (; r < nrows; r += 32) a0 += src[(size_t)r * width];
+        v = (a0 + a1) + (a2 + a3);
     }
+    sh[lane][cl] = v;
+    __syncthreads();
+    if (threadIdx.x < 8 && col < width) {
+        float t = 0.0f;
+#pragma unroll
+        for (int l = 0; l < 32; ++l) t += sh[l][threadIdx.x];
+        totals[col] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    float term = 0.0f;
+    if ((int)threadIdx.x < nsub) {       // one thread per subset (<= 15)
+        const float* row = totals + threadIdx.x * R;
+        float dice = 0.0f;
+        for (int c = 0; c < C; ++c) {
+            const float Y = __ldcg(totals + nsub * R + c);
+            dice += 1.0f - (2.0f * __ldcg(row + 2 + c) + DICE_EPS) / (__ldcg(row + 2 + C + c) + Y + DICE_EPS);
+        }
+        term = lc_ce * __ldcg(row) / (float)npix + lc_dice * dice / (float)C + lc_bce * __ldcg(row + 1) / ((float)npix * (float)C);
+    }
+    if (threadIdx.x < 32) sterm[threadIdx.x] = term;
     __syncthreads();
     if (threadIdx.x == 0) {
         float L = 0.0f;
-        for (int j = 0; j < nsub; ++j) {
-            const float* row = totals + j * R;
-            float dice = 0.0f;
-            for (int c = 0; c < C; ++c) {
-                const float Y = totals[nsub * R + c];
-                dice += 1.0f - (2.0f * row[2 + c] + DICE_EPS) / (row[2 + C + c] + Y + DICE_EPS);
-            }
-            L += lc_ce * row[0] / (float)npix + lc_dice * dice / (float)C + lc_bce * row[1] / ((float)npix * (float)C);
-        }
+        for (int j = 0; j < nsub; ++j) L += sterm[j];      // subset order, as before
         *loss = L;
+        *ticket = 0u;
     }
 }
 
@@ -265,9 +299,12 @@ int launch_all(bool backward, const McPtrs& p, const long long* labels, const fl
     float* partials = ws + ((width + 63) / 64) * 64;
     if (!backward) {
         const size_t smem = sizeof(float) * (MC_THREADS / 32) * width;
-        pv2::launch(mc_loss_fwd_kernel<C>, grid, MC_THREADS, smem, st, p, labels, n, mode, npix, H * W, partials);
+        pv2::launch(mc_loss_fwd_kernel<C>, grid, MC_THREADS, smem, st, p, labels, n, mode, npix, H * W, partials,
+                    reinterpret_cast<unsigned int*>(totals + width));
         PV2_LAUNCH_CHECK("mc_loss_fwd");
-        pv2::launch(mc_loss_fold_kernel<C>, 1, 256, 0, st, partials, grid, nsub, npix, lc_ce, lc_dice, lc_bce, totals, loss);
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(totals + width);      // inside the 64-float-aligned totals block; zeroed by the forward kernel
+        if (width % 64 == 0) { set_error("mc_dual_loss: no room for the fold ticket (width %d)", width); return 1; }   // 30 + 31*C is never a multiple of 64 for C <= 12
+        pv2::launch(mc_loss_fold_kernel<C>, (width + 7) / 8, 256, 0, st, partials, grid, nsub, npix, lc_ce, lc_dice, lc_bce, totals, loss, ticket);
         PV2_LAUNCH_CHECK("mc_loss_fold");
     } else {
         pv2::launch(mc_loss_bwd_kernel<C>, (unsigned)((npix + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st, p, labels, grad_loss, totals, n, mode, npix, H * W,

@@ -45,13 +45,14 @@ __device__ __forceinline__ float weit_from_q(uint32_t q) { return fmaf((float)q,
 
 __global__ void __launch_bounds__(WT_THREADS)
 boundary_weight_kernel(const float* __restrict__ mask, uint16_t* __restrict__ wmap, float* __restrict__ wsum_part,
-                       unsigned int* __restrict__ ticket, int H, int W, int tiles_x, int tiles_per_plane) {
+                       unsigned int* __restrict__ ticket, double* __restrict__ plane_acc, int H, int W, int tiles_x, int tiles_per_plane) {
     pv2::pdl_prologue();
     __shared__ float sm[SH * SPITCH];
     __shared__ float hs[SH * TW];
     __shared__ float red[WT_THREADS / 32];
     const int plane = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     if (plane == 0 && tile == 0 && tid == 0) *ticket = 0u;   // the forward kernel that follows counts on this
+    if (tile == 0 && tid < 4 * PV2_MAX_SCALES) plane_acc[(size_t)plane * (4 * PV2_MAX_SCALES) + tid] = 0.0;   // ... and on zeroed plane accumulators
     const int y0 = (tile / tiles_x) * TH, x0 = (tile % tiles_x) * TW;
     const float* mp = mask + (size_t)plane * H * W;
     // stage tile + halo: warp = staged row (stride 8), lane = staged column (stride 32): coalesced, no integer division
@@ -242,13 +243,17 @@ structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
         if (lane == 0) red[warp][i] = v;
     }
     __syncthreads();
+    // The CTA's sums are ADDED, in double precision, to the plane's accumulators (zeroed by boundary_weight_kernel, re-zeroed by the
+    // finalizing CTA below): no per-CTA partial rows and no fold over the ~61 chunks of a plane.  In double the order in which the
+    // chunks arrive moves the sums by ~1e-16 relative -- below the rounding of the float the loss is reported in.
+    double* pacc = reinterpret_cast<double*>(partials);
     if (tid < 4 * NS) {
         float v = 0.0f;
 #pragma unroll
         for (int wi = 0; wi < LS_THREADS / 32; ++wi) v += red[wi][tid];
-        partials[((size_t)plane * chunks + chunk) * (4 * PV2_MAX_SCALES) + tid] = v;
+        atomicAdd(pacc + (size_t)plane * (4 * PV2_MAX_SCALES) + tid, (double)v);
     }
-    // ---- the last CTA to finish folds everything in a fixed order ----
+    // ---- the last CTA to finish turns the plane sums into the losses ----
     __threadfence();
     __syncthreads();
     if (tid == 0) is_last = (atomicAdd(ticket, 1u) == (unsigned)(planes * chunks) - 1u);
@@ -259,16 +264,12 @@ structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
         float Wp = 0.0f;
         for (int t = lane; t < wt_tiles; t += 32) Wp += __ldcg(wsum_part + (size_t)pl * wt_tiles + t);
         Wp = warp_sum(Wp);
+        double* pa = pacc + (size_t)pl * (4 * PV2_MAX_SCALES);
+        float mine = 0.0f;
+        if (lane < 4 * NS) { mine = (float)__ldcg(pa + lane); pa[lane] = 0.0; }     // leave the accumulators zeroed for the next forward
         float s[4 * NS];
 #pragma unroll
-        for (int i = 0; i < 4 * NS; ++i) s[i] = 0.0f;
-        for (int c = lane; c < chunks; c += 32) {
-            const float* src = partials + ((size_t)pl * chunks + c) * (4 * PV2_MAX_SCALES);
-#pragma unroll
-            for (int i = 0; i < 4 * NS; ++i) s[i] += __ldcg(src + i);
-        }
-#pragma unroll
-        for (int i = 0; i < 4 * NS; ++i) s[i] = warp_sum(s[i]);
+        for (int i = 0; i < 4 * NS; ++i) s[i] = __shfl_sync(0xffffffffu, mine, i);
         if (lane == 0) {
             float* ps = plane_sums + (size_t)pl * NSUM;
             ps[0] = Wp;
@@ -893,7 +894,7 @@ extern "C" int pv2_structure_loss_prepare(const float* mask_fg, int planes, int 
     PV2_CHECK(workspace != nullptr && ((uintptr_t)workspace & 255u) == 0 && workspace_bytes >= pv2_structure_loss_workspace_bytes(planes, H, W, 1),
               "structure_loss_prepare: workspace must be 256-byte aligned and pv2_structure_loss_workspace_bytes() large");
     const Layout L = make_layout(workspace, planes, H, W);
-    pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, (cudaStream_t)stream, mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
+    pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, (cudaStream_t)stream, mask_fg, L.wmap, L.wsum_part, L.ticket, reinterpret_cast<double*>(L.partials), H, W, L.wt_tiles_x, L.wt_tiles);
     PV2_LAUNCH_CHECK("boundary_weight");
     return 0;
 }
@@ -943,7 +944,7 @@ static int structure_loss_fwd_impl(const void* const* pred, const void* const* p
         return 0;
     }
     if (!prepared) {
-        pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, st, mask_fg, L.wmap, L.wsum_part, L.ticket, H, W, L.wt_tiles_x, L.wt_tiles);
+        pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, st, mask_fg, L.wmap, L.wsum_part, L.ticket, reinterpret_cast<double*>(L.partials), H, W, L.wt_tiles_x, L.wt_tiles);
         PV2_LAUNCH_CHECK("boundary_weight");
     }
     const dim3 grid(L.chunks, planes);

@@ -65,6 +65,35 @@ elif what == "lowres":  # loss from the low-res maps next to th
         P._lib.check(lib.pv2_bilinear_multi_bwd(pg, pd, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, st()), "bilinear_multi_bwd")
         err = max((d - t.grad).abs().max().item() / t.grad.abs().max().item() for d, t in zip(dl, [a for a, _ in pairs] + [b for _, b in pairs]))
         print("fused vs unfused low-res gradient, max rel err", err)
+elif what == "r2":     # round 2: the kernels the bench line's roofline / other_kernels name, at the benchmarked sizes
+    import ctypes
+    import torch.nn as nn
+    from pranet_v2_b200.ops import PV2_F32, _ratio
+    lib = P._lib.load()
+    m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
+    for it in range(2):
+        pairs = [(torch.randn(B, 1, S, S, device=dev).requires_grad_(True), torch.randn(B, 1, S, S, device=dev).requires_grad_(True)) for _ in range(4)]
+        P.structure_loss_multi(pairs, m, prepared=P.ops.structure_loss_prepare(m)).sum().backward()      # boundary_weight, loss fwd (streaming), loss bwd
+        P.structure_loss_multi([(a.detach(), b.detach()) for a, b in pairs], m)                            # fused forward
+        scs = (8, 16, 32, 8) * 2
+        lows = [torch.randn(B, 1, S // s, S // s, device=dev) for s in scs]
+        his = [torch.randn(B, 1, S, S, device=dev) for _ in scs]
+        ihs = (ctypes.c_int * 8)(*[S // s for s in scs])
+        rr = (ctypes.c_float * 8)(*[_ratio(S // s, S, False, float(s)) for s in scs])
+        (pl, k1), (ph, k2) = P._lib.ptr_array(lows), P._lib.ptr_array(his)
+        st = torch.cuda.current_stream().cuda_stream
+        P._lib.check(lib.pv2_bilinear_multi_fwd(pl, ph, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, st), "bilinear_multi_fwd")
+        P._lib.check(lib.pv2_bilinear_multi_bwd(ph, pl, ihs, ihs, rr, rr, 8, B, S, S, 0, PV2_F32, st), "bilinear_multi_bwd")
+        fg = [torch.randn(B, 9, 224, 224, device=dev).requires_grad_(True) for _ in range(8)]
+        lab = torch.randint(0, 9, (B, 224, 224), device=dev)
+        P.mc_dual_loss(fg[:4], fg[4:], lab, 9).backward()
+        eng = P.engine.Engine(torch.device(dev), "bf16", True, False)
+        for (cin, cout, k, hw) in ((512, 224, 1, S // 8), (2048, 416, 1, S // 32), (256, 256, 5, S // 32), (96, 96, 3, S // 8), (64, 64, 3, S // 8), (32, 32, 3, S // 8)):
+            conv = nn.Conv2d(cin, cout, k, padding=k // 2, bias=False).to(dev)
+            bnm = nn.BatchNorm2d(cout).to(dev).train()
+            a = eng.new_act(B, hw, hw, cin)
+            a.t.normal_()
+            eng.conv(a, [conv], [bnm])
 elif what == "loss":
     m = synthetic.ellipse_masks(B, S, S, 3).to(dev)
     for it in range(2):
