@@ -173,6 +173,8 @@ int pv2_mc_dual_loss_bwd(const float* const* P_fg, const float* const* P_bg, con
  * / shift = beta - mean*scale for all Cout channels and updates running_mean / running_var / num_batches_tracked exactly
  * like nn.BatchNorm2d (momentum, unbiased running variance).  With split-K the same descriptor is given to
  * pv2_bn_stats_group after the conv.  `counters` must be zero-initialised once; every launch leaves it zeroed. */
+#define PV2_BN_ACC_STRIDE 16   /* doubles between the accumulator pairs of consecutive channels (128 bytes) */
+#define PV2_SUM_STRIDE 32      /* floats between consecutive entries of pv2_bn_act_bwd's `sums_zeroed` (128 bytes) */
 #define PV2_MAX_BN_SEGS 8
 #define PV2_BN_COUNTERS 4096
 typedef struct pv2_bn_seg {
@@ -192,14 +194,15 @@ size_t pv2_bn_fuse_workspace_floats(long long M, int Cout);
  *   0  not at all: call pv2_bn_stats_group afterwards (split-K);
  *   2  (the persistent kernel) every CTA reduces the 128-pixel tiles it computed to per-channel (count, mean, M2) in shared memory
  *      (Chan) and, when it is done, ADDS sum x = n*mean and sum x^2 = M2 + n*mean^2 -- in DOUBLE precision -- to the two accumulators
- *      per channel at bn->part (2*Cout doubles = 4*Cout floats, ZERO on entry): no partial rows, no ticket, no fence, no serial tail in
- *      the GEMM.  The kernel that consumes a channel slice (pv2_act_apply) is given a pv2_bn_defer descriptor, turns the two doubles of
+ *      per channel at bn->part (channel c at double index PV2_BN_ACC_STRIDE*c: one 128-byte line per channel, so that the CTAs'
+ *      atomics spread over the L2 slices; PV2_BN_ACC_STRIDE*Cout doubles, ZERO on entry): no partial rows, no ticket, no fence, no
+ *      serial tail in the GEMM.  The kernel that consumes a channel slice (pv2_act_apply) is given a pv2_bn_defer descriptor, turns the two doubles of
  *      each of its channels into mean / invstd / scale / shift in its prologue and updates the running statistics;
  *   1  (PV2_CONV_V1=1, the one-tile-per-CTA kernel kept for A/B) final statistics written by the launch (two-level ticket). */
 int pv2_conv_fuses_bn_stats(int splits, int out_mode);
 /* one BatchNorm module's channel slice [c_off, c_off + C) of a conv group whose statistics are still per-CTA partial rows */
 typedef struct pv2_bn_defer {
-    const float* part;                  /* the conv group's accumulators: [ldc][2] DOUBLES (sum x, sum x^2); NULL = this source is not deferred */
+    const float* part;                  /* the conv group's accumulators (sum x, sum x^2 as DOUBLES at PV2_BN_ACC_STRIDE*channel); NULL = not deferred */
     float count; int ldc, c_off, pad_;  /* pixels summed (N*H*W), channels of the whole group (Cout), first channel of the slice */
     const float* gamma; const float* beta; float* running_mean; float* running_var; long long* num_batches_tracked;
     float eps, momentum;
@@ -295,8 +298,10 @@ int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long long ss1, c
                    float* dmult, int dmult_ld, void* dy1, long long dy1_plane, int dy1_planes, int dy1_ld,
                    void* dy2, long long dy2_plane, int dy2_planes, int dy2_ld,
                    float* dgamma1, float* dbeta1, float* dgamma2, float* dbeta2, float* workspace,
-                   float* sums_zeroed /* 4*C ZERO-INITIALISED floats, 16-byte aligned: the reduce pass adds its block sums there (fp32
-                                         reductions in L2, no ticket / fold) and the dx pass reads them; NULL: three-launch scalar path */,
+                   float* sums_zeroed /* 4*C*PV2_SUM_STRIDE ZERO-INITIALISED floats, 128-byte aligned: entry i = which_sum*C + channel lives at
+                                         float index PV2_SUM_STRIDE*i (its own 128-byte line, so the blocks' L2 reductions do not queue in
+                                         one slice); the reduce pass adds its block sums there (no ticket / fold) and the dx pass reads
+                                         them; NULL: three-launch scalar path */,
                    int kind, void* stream);
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (pranet.py:93) on operand tensors; backward raw -> raw */
 int pv2_up2_nhwc_fwd(const void* in, long long in_plane, int in_planes, int in_ld, int in_off, void* out, long long out_plane,

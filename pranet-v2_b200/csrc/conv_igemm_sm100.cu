@@ -324,6 +324,8 @@ struct ConvArgs2 {
     int n_tiles, splits, work_total;
     int ksteps_last;        // MMAs (of 32 K-bytes each) that see data in the LAST channel chunk of a tap (1..4)
     int BNr;                // TMEM column stride between the two accumulators (BN rounded up to 32)
+    int row_bytes;          // bytes of K per shared-memory row: 128 (128-byte swizzle), or 64 when the channel count is 32 mod 64 (bf16:
+                            // 32-channel TMA boxes, 64-byte swizzle -- a 64-channel box would be half zero fill for the 32-channel chains)
     unsigned int* tile_counters;   // split-K: one zero-initialised ticket per (n tile, m tile); left zeroed by the launch
 };
 
@@ -351,13 +353,15 @@ __global__ void __launch_bounds__(THREADS, 2)
 conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1, const ConvArgs2 a2,
                  const __grid_constant__ BnFuseDev bn) {
-    constexpr int KC = (KIND == 0) ? 64 : 32;   // channels per 128-byte row
     const ConvArgs& a = a2.c;
+    const int RB = a2.row_bytes;
+    const int KC = RB / (KIND == 0 ? 2 : 4);    // channels per shared-memory row
+    const int a_bytes = BM * RB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = a.BN * ROW_BYTES;
+    const int b_bytes = a.BN * RB;
     const int STAGES = a.stages;
-    const int stage_bytes = A_BYTES + b_bytes;
+    const int stage_bytes = a_bytes + b_bytes;
     uint8_t* epi = smem + (size_t)STAGES * stage_bytes;                          // [4 warps][32 rows][128 B]
     float* wstat = reinterpret_cast<float*>(epi + EPI_BYTES);                    // [4 row quarters][BN][mean, M2]
     float* cacc = wstat + 4 * a.BN * 2;                                          // [Cout][count, mean, M2] of this CTA's tiles
@@ -407,7 +411,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
                 tma_load_im2col_4d(sa, term == 1 ? &tmA1 : &tmA0, &full_bar[s], kc * KC, x0 - a.pad_w, y0 - a.pad_h, n_img,
                                    (uint16_t)(kw * a.dil_w), (uint16_t)(kh * a.dil_h));
-                tma_load_3d(sa + A_BYTES, term == 2 ? &tmB1 : &tmB0, &full_bar[s], kc * KC, tap, n0);
+                tma_load_3d(sa + a_bytes, term == 2 ? &tmB1 : &tmB0, &full_bar[s], kc * KC, tap, n0);
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         }
@@ -426,13 +430,15 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             for (int it = it0; it < it1; ++it) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + A_BYTES;
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes), b_addr = a_addr + (uint32_t)a_bytes;
                 const int kc = it % a.kc_per_tap;
-                const int ksteps = (kc == a.kc_per_tap - 1) ? a2.ksteps_last : 4;
+                const int ksteps = (kc == a.kc_per_tap - 1) ? a2.ksteps_last : (RB >> 5);
+                // K-major canonical layouts: 8-row core groups of 8 * row bytes; layout type 2 = 128-byte swizzle, 4 = 64-byte swizzle
+                const uint32_t sbo = 8u * (uint32_t)RB, lt = RB == 128 ? 2u : 4u;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (k < ksteps)
-                        umma<KIND>(d_tmem, smem_desc_sw128(a_addr + k * 32, 16, 1024), smem_desc_sw128(b_addr + k * 32, 16, 1024),
+                        umma<KIND>(d_tmem, smem_desc(a_addr + k * 32, 16, sbo, lt), smem_desc(b_addr + k * 32, 16, sbo, lt),
                                    idesc, (it > it0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[s]);
@@ -635,13 +641,15 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             // ticket, no fold: the kernel that consumes a channel slice reads 2 doubles per channel (pv2_bn_defer).  In double the
             // cancellation of E[x^2] - E[x]^2 costs ~1e-16 * (1 + mean^2 / var): nothing at fp32 output precision, and the order in
             // which the <= 296 CTAs arrive changes the result below the rounding of the final float.
+            // Each channel's two accumulators sit in their OWN 128-byte line (PV2_BN_ACC_STRIDE doubles apart): same-line atomics
+            // serialise in one L2 slice -- with 16 doubles per line 242 CTAs x 16 addresses queued behind each other (~5-9 us).
             double* acc2 = reinterpret_cast<double*>(bn.f.part);
             for (int cg = et; cg < a.Cout; cg += 128) {
                 const float n = cacc[3 * cg], mu = cacc[3 * cg + 1], M2 = cacc[3 * cg + 2];
                 if (n > 0.0f) {
                     const double dn = (double)n, dm = (double)mu;
-                    atomicAdd(acc2 + 2 * cg, dn * dm);
-                    atomicAdd(acc2 + 2 * cg + 1, (double)M2 + dn * dm * dm);
+                    atomicAdd(acc2 + (size_t)PV2_BN_ACC_STRIDE * cg, dn * dm);
+                    atomicAdd(acc2 + (size_t)PV2_BN_ACC_STRIDE * cg + 1, (double)M2 + dn * dm * dm);
                 }
             }
         }
@@ -836,7 +844,7 @@ bool use_im2col() {
 // NHWC activation map in im2col mode: dims (C, W, H, N); the base pixel walks the W x H bounding box whose lower corner is
 // (-pad_w, -pad_h) and whose upper corner is pulled in by (K-1)*dil - pad = pad ("same" convolution), KC channels per pixel,
 // 128 pixels per load; the per-tap displacement (kw*dil_w, kh*dil_h) is given to each load instruction.
-int make_im2col_map(CUtensorMap* m, const void* base, int kind, int Cp, int W, int H, int N, int pad_w, int pad_h, bool atom32 = false) {
+int make_im2col_map(CUtensorMap* m, const void* base, int kind, int Cp, int W, int H, int N, int pad_w, int pad_h, bool atom32 = false, bool narrow = false) {
     auto enc = get_encode_im2col();
     PV2_CHECK(enc != nullptr, "cuTensorMapEncodeIm2col not available from the driver");
     PV2_CHECK(pad_w <= 127 && pad_h <= 127, "im2col map: padding %dx%d exceeds the 8-bit corner range", pad_h, pad_w);
@@ -846,8 +854,8 @@ int make_im2col_map(CUtensorMap* m, const void* base, int kind, int Cp, int W, i
     int lower[2] = {-pad_w, -pad_h}, upper[2] = {-pad_w, -pad_h};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims,
-                     strides, lower, upper, (cuuint32_t)(kind == 0 ? 64 : 32), (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     strides, lower, upper, (cuuint32_t)(narrow ? 32 : (kind == 0 ? 64 : 32)), (cuuint32_t)BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     narrow ? CU_TENSOR_MAP_SWIZZLE_64B : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PV2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col(C=%d W=%d H=%d N=%d pad %dx%d) failed: %d", Cp, W, H, N, pad_h, pad_w, (int)r);
     return 0;
@@ -870,16 +878,16 @@ int make_flat_map(CUtensorMap* m, const void* base, int kind, int Cp, long long 
 }
 
 // weight map: dims (Cin_p, taps, Cout), box (KC, 1, BN)
-int make_w_map(CUtensorMap* m, const void* base, int kind, int Cin_p, int taps, int Cout, int BN) {
+int make_w_map(CUtensorMap* m, const void* base, int kind, int Cin_p, int taps, int Cout, int BN, bool narrow = false) {
     auto enc = get_encode();
     PV2_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     const size_t es = kind == 0 ? 2 : 4;
     cuuint64_t dims[3] = {(cuuint64_t)Cin_p, (cuuint64_t)taps, (cuuint64_t)Cout};
     cuuint64_t strides[2] = {(cuuint64_t)Cin_p * es, (cuuint64_t)taps * Cin_p * es};
-    cuuint32_t box[3] = {(cuuint32_t)(kind == 0 ? 64 : 32), 1, (cuuint32_t)BN};
+    cuuint32_t box[3] = {(cuuint32_t)(narrow ? 32 : (kind == 0 ? 64 : 32)), 1, (cuuint32_t)BN};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PV2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights Cin=%d taps=%d Cout=%d BN=%d) failed: %d", Cin_p, taps, Cout, BN, (int)r);
     return 0;
@@ -949,6 +957,7 @@ int plan_stages(long long ctas, int iters, size_t stage_bytes, uint32_t tmem_col
 // N tiling shared by the kernels, the split-K hint and the statistics workspace: the fewest tiles of at most 256 columns,
 // evenly sized (Cout = 416 -> 2 x 208 instead of 256 + 160)
 bool use_v1();
+bool use_narrow(int kind, int Cin_p);
 inline void n_tiling(int Cout, int* BN, int* n_tiles) {
     if (use_v1()) {     // the one-tile-per-CTA kernel stores whole 32-column chunks: its tiles are 256 wide or the last one
         *BN = Cout >= 256 ? 256 : ((Cout + 15) / 16) * 16;
@@ -959,6 +968,13 @@ inline void n_tiling(int Cout, int* BN, int* n_tiles) {
     const int per = (Cout + nt - 1) / nt;
     *BN = ((per + 15) / 16) * 16;
     *n_tiles = (Cout + *BN - 1) / *BN;
+}
+
+// bf16 convs with 32 input channels (the RFB / aggregation chains: 30 of the head's 51 convs, and their dgrads) load 32-channel boxes
+// into 64-byte-swizzled rows: a 64-channel box would be half zero fill -- TMA and shared-memory traffic for nothing
+bool use_narrow(int kind, int Cin_p) {
+    static const bool off = [] { const char* e = getenv("PV2_CONV_NARROW"); return e && e[0] == '0'; }();
+    return !off && !use_v1() && kind == PV2_BF16 && Cin_p == 32;      // (at 96 channels three 32-channel slabs per tap cost more barrier round trips than the zero fill saves)
 }
 
 bool use_v1() {
@@ -1033,7 +1049,7 @@ extern "C" int pv2_conv_set_cta_budget(int max_ctas) {
 }
 
 extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind, int nterms) {
-    const int KC = kind == PV2_BF16 ? 64 : 32;
+    const int KC = use_narrow(kind, Cin_p) ? 32 : (kind == PV2_BF16 ? 64 : 32);
     const int m_tiles = m_tiles_of(N, H, W, KH, KW, true);
     int BN, n_tiles;
     n_tiling(Cout, &BN, &n_tiles);
@@ -1057,8 +1073,10 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
     PV2_CHECK(out_mode == 0 || splits == 1, "conv_fwd: split-K needs the raw output mode");
     const bool im2col = use_im2col();
     if (out_mode == 0 && !im2col) flatten_1x1(KH, KW, &N, &H, &W);
-    const int k = kind == PV2_BF16 ? 0 : 1, KC = k == 0 ? 64 : 32;
+    const bool narrow = use_narrow(kind, Cin_p);
+    const int k = kind == PV2_BF16 ? 0 : 1, KC = narrow ? 32 : (k == 0 ? 64 : 32);
     const size_t es = k == 0 ? 2 : 4;
+    const int row_bytes = narrow ? 64 : ROW_BYTES;
     ConvArgs a = {};
     a.H = H; a.W = W; a.Cout = Cout;
     a.KW = KW; a.taps = KH * KW; a.dil_h = dil_h; a.dil_w = dil_w;
@@ -1088,23 +1106,25 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
         bnd.f = *bn;
     }
     CUtensorMap mA0, mA1, mB0, mB1;
-    if (int e = im2col ? make_im2col_map(&mA0, x, k, Cin_p, W, H, N, a.pad_w, a.pad_h) : make_act_map(&mA0, x, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
-    if (int e = make_w_map(&mB0, w_op, k, Cin_p, a.taps, Cout, a.BN)) return e;
+    if (int e = im2col ? make_im2col_map(&mA0, x, k, Cin_p, W, H, N, a.pad_w, a.pad_h, false, narrow) : make_act_map(&mA0, x, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
+    if (int e = make_w_map(&mB0, w_op, k, Cin_p, a.taps, Cout, a.BN, narrow)) return e;
     mA1 = mA0; mB1 = mB0;
     if (nterms == 3) {
         const void* x1 = (const uint8_t*)x + x_plane_stride * es;
         if (int e = im2col ? make_im2col_map(&mA1, x1, k, Cin_p, W, H, N, a.pad_w, a.pad_h) : make_act_map(&mA1, x1, k, Cin_p, W, H, N, a.TWb, a.THb)) return e;
         if (int e = make_w_map(&mB1, (const uint8_t*)w_op + w_plane_stride * es, k, Cin_p, a.taps, Cout, a.BN)) return e;
     }
-    const size_t stage_bytes = A_BYTES + (size_t)a.BN * ROW_BYTES;
+    const size_t stage_bytes = (size_t)BM * row_bytes + (size_t)a.BN * row_bytes;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce;
     if (!use_v1()) {
         ConvArgs2 a2 = {};
+        a2.row_bytes = row_bytes;
         a2.n_tiles = n_tiles; a2.splits = splits;
         a2.work_total = a.m_tiles * n_tiles * splits;
         const int last_ch = Cin_p - (a.kc_per_tap - 1) * KC;              // channels in the last chunk of a tap
-        a2.ksteps_last = (last_ch + KC / 4 - 1) / (KC / 4);
+        const int step_ch = k == 0 ? 16 : 8;                              // channels one MMA consumes (32 bytes of K)
+        a2.ksteps_last = (last_ch + step_ch - 1) / step_ch;
         a2.BNr = ((a.BN + 31) / 32) * 32;
         a2.tile_counters = tile_counters;
         PV2_CHECK(splits <= 8, "conv_fwd: at most 8 K splits (got %d)", splits);

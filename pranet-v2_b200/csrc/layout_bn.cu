@@ -458,10 +458,10 @@ struct Defer2 { pv2_bn_defer d[2]; };
 
 __device__ __forceinline__ void bn_fold_deferred(const pv2_bn_defer& d, int C, float* s_scale, float* s_shift,
                                                  bool writer, float* g_scale, float* g_shift) {
-    const double* sums = reinterpret_cast<const double*>(d.part) + 2 * (size_t)d.c_off;
+    const double* sums = reinterpret_cast<const double*>(d.part) + (size_t)PV2_BN_ACC_STRIDE * d.c_off;
     const double N = (double)d.count;
     for (int cl = threadIdx.x; cl < C; cl += blockDim.x) {
-        const double S1 = __ldcg(sums + 2 * cl), S2 = __ldcg(sums + 2 * cl + 1);
+        const double S1 = __ldcg(sums + (size_t)PV2_BN_ACC_STRIDE * cl), S2 = __ldcg(sums + (size_t)PV2_BN_ACC_STRIDE * cl + 1);
         const double dmean = S1 / N;
         double dvar = S2 / N - dmean * dmean;
         if (dvar < 0.0) dvar = 0.0;
@@ -807,7 +807,7 @@ bn_bwd_reduce4_kernel(const BwdArgs b, const Reduce4Plan pl) {
         if (k >= nk) continue;
         float t = 0.0f;
         for (int j = 0; j < pl.RP; ++j) t += sh[(j * C4 + qd) * 17 + k];
-        atomicAdd(pl.sums_out + (k >> 2) * C + (qd << 2) + (k & 3), t);
+        atomicAdd(pl.sums_out + (size_t)PV2_SUM_STRIDE * ((k >> 2) * C + (qd << 2) + (k & 3)), t);     // one 128-byte line per entry
     }
 }
 
@@ -816,12 +816,17 @@ __global__ void __launch_bounds__(256)
 bn_bwd_dx4_kernel(const BwdArgs b, const Reduce4Plan pl) {
     pv2::pdl_prologue();
     const ApplyArgs& a = b.f;
-    if (blockIdx.x == 0) {      // the finished sums ARE the parameter gradients: dbeta_i = S1_i, dgamma_i = S2_i
+    // the finished sums (one 128-byte line each in global memory) gathered into shared memory once per CTA
+    __shared__ __align__(16) float s_sums[4 * 256];
+    const int nv = (a.combine ? 4 : 2) * a.C;
+    for (int i = threadIdx.x; i < nv; i += 256) s_sums[i] = __ldcg(b.sums + (size_t)PV2_SUM_STRIDE * i);
+    __syncthreads();
+    if (blockIdx.x == 0) {      // ... they ARE the parameter gradients: dbeta_i = S1_i, dgamma_i = S2_i
         for (int i = threadIdx.x; i < a.C; i += 256) {
-            if (pl.db1) pl.db1[i] = b.sums[i];
-            if (pl.dg1) pl.dg1[i] = b.sums[a.C + i];
-            if (a.combine && pl.db2) pl.db2[i] = b.sums[2 * a.C + i];
-            if (a.combine && pl.dg2) pl.dg2[i] = b.sums[3 * a.C + i];
+            if (pl.db1) pl.db1[i] = s_sums[i];
+            if (pl.dg1) pl.dg1[i] = s_sums[a.C + i];
+            if (a.combine && pl.db2) pl.db2[i] = s_sums[2 * a.C + i];
+            if (a.combine && pl.dg2) pl.dg2[i] = s_sums[3 * a.C + i];
         }
     }
     const unsigned C4 = (unsigned)a.C >> 2;
@@ -834,11 +839,11 @@ bn_bwd_dx4_kernel(const BwdArgs b, const Reduce4Plan pl) {
         float4 d1, d2 = f4_set(0.0f);
         const float4 s1 = f4_ld(a.s1 + c);
         if (b.bn_train) {
-            const float4 S1 = f4_ld(b.sums + c), S2 = f4_ld(b.sums + a.C + c);
+            const float4 S1 = f4_ldp(s_sums + c), S2 = f4_ldp(s_sums + a.C + c);
             d1 = make_float4(s1.x * (d.da1.x - S1.x * invn - d.yh1.x * S2.x * invn), s1.y * (d.da1.y - S1.y * invn - d.yh1.y * S2.y * invn),
                              s1.z * (d.da1.z - S1.z * invn - d.yh1.z * S2.z * invn), s1.w * (d.da1.w - S1.w * invn - d.yh1.w * S2.w * invn));
             if (a.combine) {
-                const float4 s2 = f4_ld(a.s2 + c), T1 = f4_ld(b.sums + 2 * a.C + c), T2 = f4_ld(b.sums + 3 * a.C + c);
+                const float4 s2 = f4_ld(a.s2 + c), T1 = f4_ldp(s_sums + 2 * a.C + c), T2 = f4_ldp(s_sums + 3 * a.C + c);
                 d2 = make_float4(s2.x * (d.da2.x - T1.x * invn - d.yh2.x * T2.x * invn), s2.y * (d.da2.y - T1.y * invn - d.yh2.y * T2.y * invn),
                                  s2.z * (d.da2.z - T1.z * invn - d.yh2.z * T2.z * invn), s2.w * (d.da2.w - T1.w * invn - d.yh2.w * T2.w * invn));
             }
@@ -1260,14 +1265,15 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
     b.dy1 = dy1; b.dy1_plane = dy1_plane; b.dy1_planes = dy1_planes; b.dy1_ld = dy1_ld;
     b.dy2 = dy2; b.dy2_plane = dy2_plane; b.dy2_planes = dy2_planes; b.dy2_ld = dy2_ld;
     {   // vector path: reduce (+ ticket fold) and dx, two launches
-        bool ok = dz_nchw == nullptr && apply_vec_ok(b.f) && dy1_ld % 4 == 0 && al16(dy1) && dy1_plane % 4 == 0 && sums_zeroed != nullptr && al16(sums_zeroed);
+        bool ok = dz_nchw == nullptr && apply_vec_ok(b.f) && dy1_ld % 4 == 0 && al16(dy1) && dy1_plane % 4 == 0 && sums_zeroed != nullptr &&
+                  (reinterpret_cast<uintptr_t>(sums_zeroed) & 127u) == 0;
         if (ok && combine) ok = dy2_ld % 4 == 0 && al16(dy2) && dy2_plane % 4 == 0;
         if (ok && bn_train) ok = al16(mean1) && al16(inv1) && (!combine || (al16(mean2) && al16(inv2)));
         if (ok && b.dmult) ok = dmult_ld % 4 == 0 && al16(dmult);
         for (int i = 0; ok && i < b.dz.n; ++i) ok = b.dz.ld[i] % 4 == 0 && b.dz.off[i] % 4 == 0 && al16(b.dz.p[i]);
         if (ok) {
             const int C4 = C / 4;
-            ok = C4 <= 256;
+            ok = C4 <= 64;        // the dx pass keeps the 4*C finished sums in 4 KB of shared memory
             if (ok) {
                 Reduce4Plan pl;
                 pl.RP = 256 / C4;

@@ -41,7 +41,8 @@ _BNDEFER_DT = np.dtype([("part", "u8"), ("count", "f4"), ("ldc", "i4"), ("c_off"
 assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.itemsize == 56 and _BNFUSE_DT.itemsize == 504
 assert _BNDEFER_DT.itemsize == 88
 _PAR_CTA_BUDGET = int(os.environ.get("PV2_PAR_CTA_BUDGET", "96"))
-_ZARENA_FLOATS = 1 << 18   # 1 MB: ~60 BatchNorm layers x 4 sums x <= 256 channels is 61 K floats
+_BN_ACC_STRIDE, _SUM_STRIDE = 16, 32   # == PV2_BN_ACC_STRIDE (doubles), PV2_SUM_STRIDE (floats) of include/pv2.h
+_ZARENA_FLOATS = 1 << 20   # 4 MB: ~3.5 K conv channels x 32 floats (forward moments) + ~3.5 K x 4 sums x 32 floats (backward) = 0.56 M floats
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
 
 
@@ -297,9 +298,16 @@ class Engine:
         self._keep.append(t)
         return t
 
+    def _tile_counters(self, N, H, W, splits):
+        """Zero-initialised ticket counters for one split-K conv launch (one per 128-pixel tile x N tile), taken from this pass's zero
+        arena: no state survives a pass, nothing is shared between launches.  None when the launch is not split."""
+        if splits <= 1:
+            return None
+        return self.zeros_small(2 * ((N * H * W + 127) // 128)).data_ptr()
+
     def zeros_small(self, n):
-        """n zero-initialised floats (16-byte aligned) from the per-pass arena; a fresh torch.zeros when the arena is exhausted."""
-        n4 = (n + 3) // 4 * 4
+        """n zero-initialised floats (128-byte aligned) from the per-pass arena; a fresh torch.zeros when the arena is exhausted."""
+        n4 = (n + 31) // 32 * 32
         if self._zarena is None or self._zoff + n4 > self._zarena.numel():
             return self.f32(n4, zero=True)
         t = self._zarena[self._zoff:self._zoff + n4]
@@ -443,7 +451,7 @@ class Engine:
         """pv2_bn_fuse descriptor (host struct, passed by value into the kernels) for the BatchNorms that follow `convs`."""
         stats = self.f32(4, Cout)
         if self.lib.pv2_conv_fuses_bn_stats(1, 0) == 2:
-            ws = self.zeros_small(4 * Cout)     # persistent kernel: two DOUBLE accumulators per channel, zero on entry (the per-pass arena)
+            ws = self.zeros_small(2 * _BN_ACC_STRIDE * Cout)   # persistent kernel: two DOUBLE accumulators per channel, one 128-byte line each, zero on entry
         else:
             ws = self.f32(self.lib.pv2_bn_fuse_workspace_floats(M, Cout))
         cnt = _ticket_counters(self.dev, self.cur)
@@ -509,7 +517,7 @@ class Engine:
                 fuse, stats, seg_of, hold = self._bn_fuse(convs, list(bns), N * H * W, Cout)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(x), self.plane_stride(x), w_op.data_ptr(), Cout * taps * Cin_p, self.kind, self.nterms,
                                         N, H, W, Cin_p, Cout, KH, KW, dh, dw, 0, raw_t.data_ptr(), ld, splits, None,
-                                        fuse.ctypes.data if fuse is not None else None, _ticket_counters(self.dev, self.cur).data_ptr(), st),
+                                        fuse.ctypes.data if fuse is not None else None, self._tile_counters(N, H, W, splits), st),
                        "pv2_conv_fwd")
             # the persistent kernel sums the split-K slabs itself (total in slab 0; the other slabs are scratch)
             res = Raw(raw_t, 1 if sums else splits, N, H, W, ld, Cout)
@@ -597,7 +605,7 @@ class Engine:
             dx = self.f32(1, N * H * W, ld, zero=True) if (sums and splits > 1) else self.f32(splits, N * H * W, ld)
             _lib.check(lib.pv2_conv_fwd(self._act_ptr(dy), self.plane_stride(dy), wt.data_ptr(), Cin * taps * Cout_p, self.kind, self.nterms,
                                         N, H, W, Cout_p, Cin, KH, KW, dh, dw, 0, dx.data_ptr(), ld, splits, None, None,
-                                        _ticket_counters(self.dev, self.cur).data_ptr(), st), "pv2_conv_fwd(dgrad)")
+                                        self._tile_counters(N, H, W, splits), st), "pv2_conv_fwd(dgrad)")
             for s in range(1 if sums else splits):
                 x.gslabs.append((dx[s], ld, 0))
 
@@ -682,7 +690,7 @@ class Engine:
                                      self.kind, st), "pv2_act_apply")
         if self.need_grad:
             keep = (s1, b1, s2, b2, m1, i1, m2, i2)
-            sums0 = self.zeros_small(4 * Cc)          # zero until this op's backward adds its block sums there
+            sums0 = self.zeros_small(4 * Cc * _SUM_STRIDE)   # zero until this op's backward adds its block sums there (one 128-byte line per sum)
 
             def bwd():
                 _alive = keep     # fwd_args holds raw device pointers into these tensors: keep them referenced

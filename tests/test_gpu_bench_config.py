@@ -74,7 +74,8 @@ def test_head_b16_352_graph_fwd_bwd(precision):
         feats = [f.to(DEV).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats_cpu]
     else:
         feats = [f.to(DEV).requires_grad_(True) for f in feats_cpu]
-    outs, loss, dfeats, dparams, graph = _graph_step(m, feats, gt.to(DEV))
+    gt_dev = gt.to(DEV)          # must outlive the graph: a replay reads the mask from this very buffer
+    outs, loss, dfeats, dparams, graph = _graph_step(m, feats, gt_dev)
 
     rfeats = [f.clone().requires_grad_(True) for f in feats_cpu]
     rsd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
