@@ -328,13 +328,13 @@ def kernel_table(P, dev, B, S, hbm, tflops):
         ach = work / (ms * 1e-3) / 1e9
         out.append({"kernel": name, "bound": bound, "bytes": work, "us": ms * 1e3, "achieved_gbs": ach, "frac_of_hbm_peak": ach / hbm})
     # conv GEMMs (fprop) of the head's distinct big shapes, bf16
-    eng = P.engine.Engine(torch.device(dev), "bf16", True, False)
     import torch.nn as nn
     for (cin, cout, k, hw, label) in ((512, 224, 1, S // 8, "x2: 6 fused 1x1 (RFB x5 + ra2_conv1)"), (1024, 224, 1, S // 16, "x3: 6 fused 1x1"),
                                       (2048, 416, 1, S // 32, "x4: 6 fused 1x1 (RFB x5 + ra4_conv1)"), (256, 256, 5, S // 32, "ra4_conv2-4 5x5 256->256"),
                                       (96, 96, 3, S // 8, "agg1.conv_concat3 / conv4 3x3 96->96"), (64, 64, 3, S // 8, "ra2_conv2-3 3x3 64->64"),
                                       (32, 32, 3, S // 8, "RFB branch 3x3 32->32 (dil 3)")):
         conv = nn.Conv2d(cin, cout, k, padding=k // 2, bias=False).to(dev)
+        eng = P.engine.Engine(torch.device(dev), "bf16", True, False)      # one engine (one zero arena for the statistics accumulators) per shape
         n = max(2, int(300e6 // (B * cin * hw * hw * 2)) + 1)
         acts = [eng.new_act(B, hw, hw, cin) for _ in range(n)]
         for a in acts:

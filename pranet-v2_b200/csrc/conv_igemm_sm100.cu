@@ -327,6 +327,7 @@ struct ConvArgs2 {
     int row_bytes;          // bytes of K per shared-memory row: 128 (128-byte swizzle), or 64 when the channel count is 32 mod 64 (bf16:
                             // 32-channel TMA boxes, 64-byte swizzle -- a 64-channel box would be half zero fill for the 32-channel chains)
     unsigned int* tile_counters;   // split-K: one zero-initialised ticket per (n tile, m tile); left zeroed by the launch
+    int dbg;                       // profiling switches (PV2_CONV_DBG): 1 = skip the final statistics atomics, 2 = skip the per-chunk column pass
 };
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -584,7 +585,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 for (int j = 0; j < 8; ++j)
                     st_shared_v4(stg + my_row_off + ((((uint32_t)j) ^ sw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
-                if (a.stats && !fix) stats_chunk(stg, nvalid_w, c0);
+                if (a.stats && !fix && !(a2.dbg & 2)) stats_chunk(stg, nvalid_w, c0);
                 // ---- staging -> global: 4 complete 128-byte rows per warp instruction ----
                 const int colu = lane & 7;                                   // 16-byte unit of the row this lane moves
                 const int col = n0 + c0 + colu * (a.out_mode == 2 ? 8 : 4);  // first output column of that unit
@@ -646,7 +647,7 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
             double* acc2 = reinterpret_cast<double*>(bn.f.part);
             for (int cg = et; cg < a.Cout; cg += 128) {
                 const float n = cacc[3 * cg], mu = cacc[3 * cg + 1], M2 = cacc[3 * cg + 2];
-                if (n > 0.0f) {
+                if (n > 0.0f && !(a2.dbg & 1)) {
                     const double dn = (double)n, dm = (double)mu;
                     atomicAdd(acc2 + (size_t)PV2_BN_ACC_STRIDE * cg, dn * dm);
                     atomicAdd(acc2 + (size_t)PV2_BN_ACC_STRIDE * cg + 1, (double)M2 + dn * dm * dm);
@@ -1055,8 +1056,17 @@ extern "C" int pv2_conv_splits_hint(int N, int H, int W, int Cin_p, int Cout, in
     n_tiling(Cout, &BN, &n_tiles);
     const int iters = nterms * KH * KW * ((Cin_p + KC - 1) / KC);
     int splits = 1;
-    // fill the 148 SMs when the output tiling alone cannot, keeping >= 8 K iterations per split
-    while (splits < 8 && m_tiles * n_tiles * splits * 2 <= kNumSMs && iters / (splits * 2) >= 8) splits *= 2;   // <= 8: consumers sum at most 8 slabs
+    if (use_v1()) {
+        // fill the 148 SMs when the output tiling alone cannot, keeping >= 8 K iterations per split
+        while (splits < 8 && m_tiles * n_tiles * splits * 2 <= kNumSMs && iters / (splits * 2) >= 8) splits *= 2;   // <= 8: consumers sum at most 8 slabs
+    } else {
+        // Persistent kernel: splitting K costs the partial-tile reductions in L2 plus -- for a BatchNorm'd conv -- a ticket and a re-read
+        // of the finished tile (~10 us), so a problem with 48+ output tiles runs unsplit even though it leaves SMs idle (measured at
+        // B = 16: the 61-tile level-3 GEMM 26 us split in two, 20 us unsplit); fewer tiles than that (the 16-tile 5x5 stack, the
+        // 32-tile level-4 GEMM: 1.3 - 4.8 MB of K slabs per tile) are split until the SMs are filled, keeping >= 8 K slabs per split.
+        if (m_tiles * n_tiles < 48)
+            while (splits < 8 && m_tiles * n_tiles * splits * 2 <= kNumSMs && iters / (splits * 2) >= 8) splits *= 2;
+    }
     const int per = (iters + splits - 1) / splits;
     return (iters + per - 1) / per;   // no empty split
 }
@@ -1127,6 +1137,7 @@ extern "C" int pv2_conv_fwd(const void* x, long long x_plane_stride, const void*
         a2.ksteps_last = (last_ch + step_ch - 1) / step_ch;
         a2.BNr = ((a.BN + 31) / 32) * 32;
         a2.tile_counters = tile_counters;
+        a2.dbg = tune_int("PV2_CONV_DBG", 0);
         PV2_CHECK(splits <= 8, "conv_fwd: at most 8 K splits (got %d)", splits);
         PV2_CHECK(splits == 1 || !a.stats || (tile_counters != nullptr && (long long)a.m_tiles * n_tiles <= PV2_BN_COUNTERS),
                   "conv_fwd: split-K with fused statistics needs %lld zero-initialised tile counters (<= %d)", (long long)a.m_tiles * n_tiles, PV2_BN_COUNTERS);

@@ -127,24 +127,29 @@ weight_pack_multi_kernel(const __grid_constant__ PackBatch b, int n, int nplanes
     const int co0 = (lt / ci_tiles) * TCO, ci0 = (lt % ci_tiles) * PK_TCI;
     const int nco = min(TCO, t.Cout - co0), nci = min(PK_TCI, t.Cin - ci0);
     const int run = nci * taps, pitch = PK_TCI * taps + 1;
+    // Warp-per-row loops, lanes along the contiguous axis of whichever side is being touched: no integer division per element
+    // (three passes of i / run, i % nci, r % taps with run-time divisors made this kernel ~60 us for the head's 27 MB of weights).
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // OIHW side: for every co of the tile the (ci, tap) run is contiguous
-    for (int i = threadIdx.x; i < nco * run; i += 256) {
-        const int col = i / run, j = i - col * run;
-        pk_tile[col * pitch + j] = __ldg(t.w + ((size_t)(co0 + col) * t.Cin + ci0) * taps + j);
+    for (int col = warp; col < nco; col += 8) {
+        const float* src = t.w + ((size_t)(co0 + col) * t.Cin + ci0) * taps;
+        for (int j = lane; j < run; j += 32) pk_tile[col * pitch + j] = __ldg(src + j);
     }
     __syncthreads();
-    // fprop layout [co][tap][ci]: ci fastest
-    for (int i = threadIdx.x; i < nco * run; i += 256) {
-        const int cil = i % nci, r = i / nci, tap = r % taps, col = r / taps;
-        store_op<KIND>(t.out_f, t.f_plane, nplanes, ((long long)(co0 + col + t.f_ooff) * taps + tap) * t.f_ild + t.f_ioff + ci0 + cil,
-                       pk_tile[col * pitch + cil * taps + tap]);
+    // fprop layout [co][tap][ci]: ci fastest (lane = ci; shared-memory stride `taps` is odd or 1: conflict free)
+    for (int col = warp; col < nco; col += 8) {
+        const long long row = (long long)(co0 + col + t.f_ooff) * taps;
+        for (int tap = 0; tap < taps; ++tap)
+            if (lane < nci)
+                store_op<KIND>(t.out_f, t.f_plane, nplanes, (row + tap) * t.f_ild + t.f_ioff + ci0 + lane, pk_tile[col * pitch + lane * taps + tap]);
     }
-    // dgrad layout [ci][flipped tap][co]: co fastest
+    // dgrad layout [ci][flipped tap][co]: co fastest (lane = co; stride `pitch` is odd)
     if (t.out_d) {
-        for (int i = threadIdx.x; i < nco * run; i += 256) {
-            const int col = i % nco, r = i / nco, tap = r % taps, cil = r / taps;
-            store_op<KIND>(t.out_d, t.d_plane, nplanes, ((long long)(ci0 + cil + t.d_ooff) * taps + (taps - 1 - tap)) * t.d_ild + t.d_ioff + co0 + col,
-                           pk_tile[col * pitch + cil * taps + tap]);
+        for (int cil = warp; cil < nci; cil += 8) {
+            const long long row = (long long)(ci0 + cil + t.d_ooff) * taps;
+            for (int tap = 0; tap < taps; ++tap)
+                for (int col = lane; col < nco; col += 32)
+                    store_op<KIND>(t.out_d, t.d_plane, nplanes, (row + (taps - 1 - tap)) * t.d_ild + t.d_ioff + co0 + col, pk_tile[col * pitch + cil * taps + tap]);
         }
     }
 }
@@ -811,6 +816,198 @@ bn_bwd_reduce4_kernel(const BwdArgs b, const Reduce4Plan pl) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Lean forms of the two passes for the common layer of the head -- one BatchNorm'd source, optional ReLU, no product / second
+// source, the incoming gradient in ONE slab (the persistent conv sums its split-K partials itself): ~40 registers instead of
+// 128, so 6+ CTAs per SM, and four rows of independent 16-byte loads in flight per thread.  Same arithmetic as the general
+// kernels above (which stay for the combined / multiplied / multi-slab cases).
+// ------------------------------------------------------------------------------------------------------
+struct LeanBwd {
+    const float* y; int ldy, offy;            // raw conv output rows
+    const float* dz; int ldz, offz;           // gradient w.r.t. the activation, raw rows
+    const float* scale; const float* shift; const float* mean; const float* inv;
+    int relu; long long M; int C;
+    float* sums;                              // [2*C] entries PV2_SUM_STRIDE floats apart: sum da, sum da*yhat
+    void* dy; long long dy_plane; int dy_planes, dy_ld;
+    float* dgamma; float* dbeta;
+    int rows_pb, RP;
+};
+
+__device__ __forceinline__ void lean_da(const LeanBwd& a, long long r, int c, const float4& sc, const float4& sh, const float4& mu, const float4& iv,
+                                        float4* da, float4* yh) {
+    const float4 y = f4_ld(a.y + r * a.ldy + a.offy + c);
+    float4 g = f4_ld(a.dz + r * a.ldz + a.offz + c);
+    if (a.relu) {
+        if (!(fmaf(y.x, sc.x, sh.x) > 0.0f)) g.x = 0.0f;
+        if (!(fmaf(y.y, sc.y, sh.y) > 0.0f)) g.y = 0.0f;
+        if (!(fmaf(y.z, sc.z, sh.z) > 0.0f)) g.z = 0.0f;
+        if (!(fmaf(y.w, sc.w, sh.w) > 0.0f)) g.w = 0.0f;
+    }
+    *da = g;
+    *yh = f4_mul(f4_sub(y, mu), iv);
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce4_lean_kernel(const LeanBwd a) {
+    pv2::pdl_prologue();
+    __shared__ float sh[256 * 9];
+    const int C4 = a.C >> 2, tid = threadIdx.x;
+    const int quad = tid % C4, rp = tid / C4;
+    const long long r0 = (long long)blockIdx.x * a.rows_pb, r1 = min(a.M, r0 + a.rows_pb);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    if (rp < a.RP) {
+        const int c = quad << 2;
+        const float4 sc = f4_ld(a.scale + c), shf = f4_ld(a.shift + c), mu = f4_ld(a.mean + c), iv = f4_ld(a.inv + c);
+        for (long long r = r0 + rp; r < r1; r += 4LL * a.RP) {
+            float4 da[4], yh[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long ru = r + (long long)u * a.RP;
+                lean_da(a, ru < r1 ? ru : r, c, sc, shf, mu, iv, &da[u], &yh[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (r + (long long)u * a.RP >= r1) break;
+                acc[0] += da[u].x; acc[1] += da[u].y; acc[2] += da[u].z; acc[3] += da[u].w;
+                acc[4] = fmaf(da[u].x, yh[u].x, acc[4]); acc[5] = fmaf(da[u].y, yh[u].y, acc[5]);
+                acc[6] = fmaf(da[u].z, yh[u].z, acc[6]); acc[7] = fmaf(da[u].w, yh[u].w, acc[7]);
+            }
+        }
+    }
+    pv2::pdl_done();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sh[tid * 9 + i] = acc[i];
+    __syncthreads();
+    for (int idx = tid; idx < C4 * 8; idx += 256) {
+        const int qd = idx >> 3, k = idx & 7;
+        float t = 0.0f;
+        for (int j = 0; j < a.RP; ++j) t += sh[(j * C4 + qd) * 9 + k];
+        atomicAdd(a.sums + (size_t)PV2_SUM_STRIDE * ((k >> 2) * a.C + (qd << 2) + (k & 3)), t);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+bn_bwd_dx4_lean_kernel(const LeanBwd a) {
+    pv2::pdl_prologue();
+    __shared__ __align__(16) float s_sums[2 * 256];
+    for (int i = threadIdx.x; i < 2 * a.C; i += 256) s_sums[i] = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * i);
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < a.C; i += 256) {
+            if (a.dbeta) a.dbeta[i] = s_sums[i];
+            if (a.dgamma) a.dgamma[i] = s_sums[a.C + i];
+        }
+    }
+    const unsigned C4 = (unsigned)a.C >> 2;
+    const unsigned total = (unsigned)a.M * C4;
+    const float invn = 1.0f / (float)a.M;
+    const unsigned stride = gridDim.x * 256u;
+    for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += 2u * stride) {
+        float4 da[2], yh[2];
+        unsigned rr[2];
+        int cc[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const unsigned eu = e + (unsigned)u * stride;
+            const unsigned ev = eu < total ? eu : e;
+            rr[u] = ev / C4; cc[u] = (int)(ev - rr[u] * C4) << 2;
+            lean_da(a, rr[u], cc[u], f4_ld(a.scale + cc[u]), f4_ld(a.shift + cc[u]), f4_ld(a.mean + cc[u]), f4_ld(a.inv + cc[u]), &da[u], &yh[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (e + (unsigned)u * stride >= total) break;
+            const int c = cc[u];
+            const float4 s1 = f4_ld(a.scale + c), S1 = f4_ldp(s_sums + c), S2 = f4_ldp(s_sums + a.C + c);
+            const float4 d1 = make_float4(s1.x * (da[u].x - S1.x * invn - yh[u].x * S2.x * invn), s1.y * (da[u].y - S1.y * invn - yh[u].y * S2.y * invn),
+                                          s1.z * (da[u].z - S1.z * invn - yh[u].z * S2.z * invn), s1.w * (da[u].w - S1.w * invn - yh[u].w * S2.w * invn));
+            store_op4<KIND>(a.dy, a.dy_plane, a.dy_planes, (long long)rr[u] * a.dy_ld + c, d1);
+        }
+    }
+    pv2::pdl_done();
+}
+
+// Small-C forms (the fg / bg logit heads: C = 1 .. 8 maps, gradient arriving as an fp32 NCHW tensor): thread = pixel row, all C
+// channels in registers; the block's 2*C sums go to the strided accumulators with one reduction each.  The channel-major
+// general kernel gives such a layer 8 of its 256 threads per block something to do.
+constexpr int SMALL_C = 8;
+struct SmallBwd {
+    const float* y; int ldy, offy;
+    const float* dz_nchw; int HW;
+    const float* scale; const float* shift; const float* mean; const float* inv;
+    int relu; long long M; int C;
+    float* sums;
+    void* dy; long long dy_plane; int dy_planes, dy_ld;
+    float* dgamma; float* dbeta;
+};
+
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_small_kernel(const SmallBwd a) {
+    pv2::pdl_prologue();
+    __shared__ float red[8][2 * SMALL_C];
+    float acc[2 * SMALL_C];
+#pragma unroll
+    for (int i = 0; i < 2 * SMALL_C; ++i) acc[i] = 0.0f;
+    for (long long r = (long long)blockIdx.x * 256 + threadIdx.x; r < a.M; r += (long long)gridDim.x * 256) {
+        const long long n = r / a.HW, p = r - n * a.HW;
+#pragma unroll
+        for (int c = 0; c < SMALL_C; ++c) {
+            if (c >= a.C) break;
+            const float y = __ldg(a.y + r * a.ldy + a.offy + c);
+            float g = __ldg(a.dz_nchw + (n * a.C + c) * a.HW + p);
+            if (a.relu && !(fmaf(y, a.scale[c], a.shift[c]) > 0.0f)) g = 0.0f;
+            acc[c] += g;
+            acc[SMALL_C + c] = fmaf(g, (y - a.mean[c]) * a.inv[c], acc[SMALL_C + c]);
+        }
+    }
+    pv2::pdl_done();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 2 * SMALL_C; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * SMALL_C) {
+        const int k = threadIdx.x / SMALL_C, c = threadIdx.x % SMALL_C;
+        if (c < a.C) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+            atomicAdd(a.sums + (size_t)PV2_SUM_STRIDE * (k * a.C + c), t);
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_small_kernel(const SmallBwd a) {
+    pv2::pdl_prologue();
+    __shared__ float s_sums[2 * SMALL_C];
+    if (threadIdx.x < 2 * a.C) s_sums[threadIdx.x] = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * threadIdx.x);
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < a.C) {
+        if (a.dbeta) a.dbeta[threadIdx.x] = s_sums[threadIdx.x];
+        if (a.dgamma) a.dgamma[threadIdx.x] = s_sums[a.C + threadIdx.x];
+    }
+    const float invn = 1.0f / (float)a.M;
+    for (long long r = (long long)blockIdx.x * 256 + threadIdx.x; r < a.M; r += (long long)gridDim.x * 256) {
+        const long long n = r / a.HW, p = r - n * a.HW;
+#pragma unroll
+        for (int c = 0; c < SMALL_C; ++c) {
+            if (c >= a.C) break;
+            const float y = __ldg(a.y + r * a.ldy + a.offy + c);
+            float g = __ldg(a.dz_nchw + (n * a.C + c) * a.HW + p);
+            if (a.relu && !(fmaf(y, a.scale[c], a.shift[c]) > 0.0f)) g = 0.0f;
+            const float yh = (y - a.mean[c]) * a.inv[c];
+            store_op<KIND>(a.dy, a.dy_plane, a.dy_planes, r * a.dy_ld + c, a.scale[c] * (g - s_sums[c] * invn - yh * s_sums[a.C + c] * invn));
+        }
+    }
+    pv2::pdl_done();
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx4_kernel(const BwdArgs b, const Reduce4Plan pl) {
@@ -1288,6 +1485,30 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
                 pl.dg1 = dgamma1; pl.db1 = dbeta1; pl.dg2 = dgamma2; pl.db2 = dbeta2;
                 b.rows_pb = pl.rows_pb;
                 cudaStream_t st4 = (cudaStream_t)stream;
+                static const bool lean_off = [] { const char* e = getenv("PV2_BN_BWD_LEAN"); return e && e[0] == '0'; }();
+                if (!lean_off && bn_train && combine == 0 && mult == nullptr && b.dz.n == 1 && b.f.ns1 == 1 && M * C4 < (1LL << 31)) {
+                    LeanBwd a = {};
+                    a.y = y1; a.ldy = ld1; a.offy = off1;
+                    a.dz = b.dz.p[0]; a.ldz = b.dz.ld[0]; a.offz = b.dz.off[0];
+                    a.scale = s1; a.shift = b1; a.mean = mean1; a.inv = inv1;
+                    a.relu = relu; a.M = M; a.C = C; a.sums = sums_zeroed;
+                    a.dy = dy1; a.dy_plane = dy1_plane; a.dy_planes = dy1_planes; a.dy_ld = dy1_ld;
+                    a.dgamma = dgamma1; a.dbeta = dbeta1;
+                    a.RP = pl.RP;
+                    // more, smaller row blocks than the general kernel: the lean kernel keeps 6+ CTAs per SM resident
+                    long long nb = (M + a.RP - 1) / a.RP;
+                    if (nb > 4 * kNumSMs) nb = 4 * kNumSMs;
+                    long long rws = (M + nb - 1) / nb;
+                    rws = (rws + a.RP - 1) / a.RP * a.RP;
+                    nb = (M + rws - 1) / rws;
+                    a.rows_pb = (int)rws;
+                    pv2::launch(bn_bwd_reduce4_lean_kernel, (int)nb, 256, 0, st4, a);
+                    PV2_LAUNCH_CHECK("bn_bwd_reduce4_lean");
+                    const long long total4l = M * C4;
+                    if (kind == PV2_BF16) pv2::launch(bn_bwd_dx4_lean_kernel<0>, grid_for(total4l), 256, 0, st4, a); else pv2::launch(bn_bwd_dx4_lean_kernel<1>, grid_for(total4l), 256, 0, st4, a);
+                    PV2_LAUNCH_CHECK("bn_bwd_dx4_lean");
+                    return 0;
+                }
                 if (kind == PV2_BF16) pv2::launch(bn_bwd_reduce4_kernel<0>, pl.nblk, 256, 0, st4, b, pl); else pv2::launch(bn_bwd_reduce4_kernel<1>, pl.nblk, 256, 0, st4, b, pl);
                 PV2_LAUNCH_CHECK("bn_bwd_reduce4");
                 const long long total4 = M * C4;
@@ -1296,6 +1517,21 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
                 return 0;
             }
         }
+    }
+    if (dz_nchw != nullptr && C <= SMALL_C && bn_train && combine == 0 && mult == nullptr && b.f.ns1 == 1 && sums_zeroed != nullptr) {
+        SmallBwd a = {};
+        a.y = y1; a.ldy = ld1; a.offy = off1; a.dz_nchw = dz_nchw; a.HW = HW;
+        a.scale = s1; a.shift = b1; a.mean = mean1; a.inv = inv1; a.relu = relu; a.M = M; a.C = C;
+        a.sums = sums_zeroed; a.dy = dy1; a.dy_plane = dy1_plane; a.dy_planes = dy1_planes; a.dy_ld = dy1_ld;
+        a.dgamma = dgamma1; a.dbeta = dbeta1;
+        cudaStream_t sts = (cudaStream_t)stream;
+        long long nb = (M + 255) / 256;
+        if (nb > 2 * kNumSMs) nb = 2 * kNumSMs;
+        pv2::launch(bn_bwd_reduce_small_kernel, (int)nb, 256, 0, sts, a);
+        PV2_LAUNCH_CHECK("bn_bwd_reduce_small");
+        if (kind == PV2_BF16) pv2::launch(bn_bwd_dx_small_kernel<0>, grid_for(M), 256, 0, sts, a); else pv2::launch(bn_bwd_dx_small_kernel<1>, grid_for(M), 256, 0, sts, a);
+        PV2_LAUNCH_CHECK("bn_bwd_dx_small");
+        return 0;
     }
     const int rows = pick_rows(M, C);
     const int rb = (int)((M + rows - 1) / rows);
