@@ -611,24 +611,32 @@ conv_fwd2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 unsigned int* cnt = a2.tile_counters + (size_t)n_tile * m_tiles + m_tile;
                 if (ticket_last(cnt, (unsigned)a2.splits, et == 0, &s_flag, 1, 128)) {
                     const int colu = lane & 7;
-                    for (int c0 = 0; c0 < a.BN; c0 += 32) {
+                    // software pipeline over the 32-column chunks: the loads of chunk c+1 are in flight while chunk c is staged and
+                    // reduced (a chunk-by-chunk walk is a chain of L2 round trips: 7-8 of them for a 224..256-column tile)
+                    auto load_chunk = [&](int c0, float4 (&t)[8]) {
                         const int col = n0 + c0 + colu * 4;
-                        const bool col_ok = (col < n0 + a.BN) && (col + 3 < a.ldo);
-                        float4 t[8];
+                        const bool col_ok = (c0 < a.BN) && (col < n0 + a.BN) && (col + 3 < a.ldo);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const long long pix = m0 + q * 32 + i * 4 + (lane >> 3);
                             t[i] = (col_ok && pix < a.M) ? __ldcg(reinterpret_cast<const float4*>(a.out + pix * a.ldo + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
+                    };
+                    float4 cur[8], nxt[8];
+                    load_chunk(0, cur);
+                    for (int c0 = 0; c0 < a.BN; c0 += 32) {
+                        load_chunk(c0 + 32, nxt);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = i * 4 + (lane >> 3);
                             st_shared_v4(stg + (uint32_t)rr * 128u + ((((uint32_t)colu) ^ (uint32_t)(rr & 7)) << 4),
-                                         __float_as_uint(t[i].x), __float_as_uint(t[i].y), __float_as_uint(t[i].z), __float_as_uint(t[i].w));
+                                         __float_as_uint(cur[i].x), __float_as_uint(cur[i].y), __float_as_uint(cur[i].z), __float_as_uint(cur[i].w));
                         }
                         __syncwarp();
                         stats_chunk(stg, nvalid_w, c0);
                         __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
                     }
                     tile_stats(m0, n0);
                 }
