@@ -309,6 +309,161 @@ bilinear_bwd_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int ac
     else bilinear_bwd_body<T, 1, BWD_BATCH>(mm, map, oh, ow, ac != 0, rgroups, colsum, wts);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Backward, integer up-scaling by s = 8, 16, 32, 64 with half-pixel centres (the final x8 / x16 / x32 maps of a step): separable
+// in registers.  With s % 8 == 0 every aligned run of 4 output rows and every aligned quad of 4 output columns has ONE pair of
+// source rows / columns (the cell boundaries sit at s/2 + k*s, multiples of 4).  A thread owns a column quad and a subset of the
+// CTA's 4-row chunks; per chunk it issues 4 independent 16-byte loads, folds each row's quad into (a, b) = (sum w0x*v, sum w1x*v)
+// and the four rows into (a, b) x (lo, hi) with the rows' y taps: 13 FMA per 16-byte load, 4.4 instructions per element (the
+// gather kernel above spends ~30).  Pass 2 adds, for every input pixel, the chunk x quad partials of its own cell (lo / a) and of
+// the cell before it (hi / b) in a fixed order.  CTA = (band of R input rows, plane, map); the band also reads the cell above it
+// (its hi part): (R + 1) / R of the bytes.  No atomics, deterministic.  Taps come from pv2::bilinear_tap (ATen's formula).
+// ------------------------------------------------------------------------------------------------------------------------------
+constexpr int BWD2_THREADS = 384;
+constexpr int BWD2_MAX_CHUNKS = 52;      // 4-row chunks a CTA may own: (R + 1) * s / 4 + s / 8 (cell 0 also holds the s/2 clamped rows)
+constexpr int BWD2_MAX_IW = 96;
+
+constexpr int BWD2_SMEM = 100 * 1024;    // partial sums of a CTA: 4 components x chunks x ow / 4 floats = 4 * chunks * ow bytes
+
+// `bands` = bands per plane the host asks for: 2 when the launch already has ~2 CTAs per SM (the 8 final maps x 16 planes of a step
+// are 288 CTAs, one wave at 2 CTAs per SM), more for launches with few planes
+__host__ __device__ inline int bwd2_rows_per_cta(int ih, int s, int ow, int bands) {
+    int r = (ih + bands - 1) / bands;
+    int maxc = BWD2_SMEM / (4 * ow);
+    if (maxc > BWD2_MAX_CHUNKS) maxc = BWD2_MAX_CHUNKS;
+    const int cap = (maxc - s / 8) * 4 / s - 1;
+    if (r > cap) r = cap;
+    return r < 1 ? 1 : r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BWD2_THREADS, 2)
+bilinear_bwd2_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int G, int bands_hint) {
+    pv2::pdl_prologue();
+    extern __shared__ __align__(16) float part[];     // [4 components: a_lo, a_hi, b_lo, b_hi][chunk][ow4]
+    __shared__ float2 ytab[BWD2_MAX_CHUNKS * 4];      // (w0, w1) of every window row
+    __shared__ int chunk_i0[BWD2_MAX_CHUNKS];         // source row i0 of a chunk
+    __shared__ int cell_k0[BWD2_MAX_CHUNKS + 2];      // first chunk of cell (c0 + i); sentinel at the end
+    __shared__ int quad_i0[BWD2_THREADS];
+    __shared__ int run_q0[BWD2_MAX_IW + 2];           // first quad whose source column is >= ix; sentinel at iw
+    const int map = blockIdx.z, plane = blockIdx.y;
+    const int ih = mm.ih[map], iw = mm.iw[map];
+    const int s = oh / ih;
+    const int R = bwd2_rows_per_cta(ih, s, ow, bands_hint);
+    const int ya = blockIdx.x * R;
+    if (ya >= ih) return;
+    const int yb = min(ya + R, ih), nr = yb - ya;
+    const float rh = mm.rh[map], rw = mm.rw[map];
+    const T* __restrict__ g = reinterpret_cast<const T*>(mm.out[map]) + (size_t)plane * oh * ow;
+    T* __restrict__ din = reinterpret_cast<T*>(const_cast<void*>(mm.in[map]));
+    // cells (= source row of the upper tap) c0 .. yb - 1; cell c covers output rows [c*s + s/2, (c+1)*s + s/2), cell 0 also the
+    // clamped rows above it, cell ih - 1 ends at oh
+    const int c0 = max(ya - 1, 0), ncell = yb - c0;
+    const int row0 = c0 == 0 ? 0 : c0 * s + (s >> 1);
+    const int row1 = yb == ih ? oh : yb * s + (s >> 1);
+    const int nchunk = (row1 - row0) >> 2;
+    const int ow4 = ow >> 2;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < nchunk * 4; j += blockDim.x) {
+        const Tap t = bilinear_tap(row0 + j, ih, rh, false);
+        ytab[j] = make_float2(t.w0, t.w1);
+        if ((j & 3) == 0) chunk_i0[j >> 2] = t.i0;
+    }
+    const int q = tid % ow4, grp = tid / ow4;
+    float wx0[4], wx1[4];
+    {
+        int i0 = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const Tap t = bilinear_tap(q * 4 + e, iw, rw, false);
+            wx0[e] = t.w0; wx1[e] = t.w1;
+            if (e == 0) i0 = t.i0;
+        }
+        if (grp == 0) quad_i0[q] = i0;
+    }
+    __syncthreads();
+    // first chunk of every cell / first quad of every source column (chunks and quads are sorted by their source index)
+    for (int k = tid; k <= nchunk; k += blockDim.x) {
+        const int prev = k == 0 ? c0 - 1 : chunk_i0[k - 1];
+        const int cur = k == nchunk ? c0 + ncell : chunk_i0[k];
+        for (int c = prev + 1; c <= cur; ++c) cell_k0[c - c0] = k;
+    }
+    for (int k = tid; k <= ow4; k += blockDim.x) {
+        const int prev = k == 0 ? -1 : quad_i0[k - 1];
+        const int cur = k == ow4 ? iw : quad_i0[k];
+        for (int c = prev + 1; c <= cur; ++c) run_q0[c] = k;
+    }
+    const int cstride = nchunk * ow4;                  // component stride of part[]
+    if (grp < G) {
+        const T* gp = g + (size_t)row0 * ow + q * 4;
+        // two chunks per trip, folded in ONE interleaved loop so that all 8 independent 16-byte loads are issued before the first
+        // FMA (with two separate folds ptxas sinks the second chunk's loads below the first fold: 4 in flight again)
+        for (int k = grp; k < nchunk; k += 2 * G) {
+            const bool two = k + G < nchunk;
+            const int k2 = two ? k + G : k;
+            const T* p = gp + (size_t)(k * 4) * ow;
+            const T* p2 = gp + (size_t)(k2 * 4) * ow;
+            float4 v[4], v2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = load4<T>(p + (size_t)u * ow);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v2[u] = load4<T>(p2 + (size_t)u * ow);
+            float alo = 0.0f, ahi = 0.0f, blo = 0.0f, bhi = 0.0f, alo2 = 0.0f, ahi2 = 0.0f, blo2 = 0.0f, bhi2 = 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float a = fmaf(wx0[3], v[u].w, fmaf(wx0[2], v[u].z, fmaf(wx0[1], v[u].y, wx0[0] * v[u].x)));
+                const float a2 = fmaf(wx0[3], v2[u].w, fmaf(wx0[2], v2[u].z, fmaf(wx0[1], v2[u].y, wx0[0] * v2[u].x)));
+                const float b = fmaf(wx1[3], v[u].w, fmaf(wx1[2], v[u].z, fmaf(wx1[1], v[u].y, wx1[0] * v[u].x)));
+                const float b2 = fmaf(wx1[3], v2[u].w, fmaf(wx1[2], v2[u].z, fmaf(wx1[1], v2[u].y, wx1[0] * v2[u].x)));
+                const float2 wy = ytab[k * 4 + u], wy2 = ytab[k2 * 4 + u];
+                alo = fmaf(wy.x, a, alo); ahi = fmaf(wy.y, a, ahi);
+                blo = fmaf(wy.x, b, blo); bhi = fmaf(wy.y, b, bhi);
+                alo2 = fmaf(wy2.x, a2, alo2); ahi2 = fmaf(wy2.y, a2, ahi2);
+                blo2 = fmaf(wy2.x, b2, blo2); bhi2 = fmaf(wy2.y, b2, bhi2);
+            }
+            float* o = part + k * ow4 + q;
+            o[0] = alo; o[cstride] = ahi; o[2 * cstride] = blo; o[3 * cstride] = bhi;
+            if (two) {
+                float* o2 = part + k2 * ow4 + q;
+                o2[0] = alo2; o2[cstride] = ahi2; o2[2 * cstride] = blo2; o2[3 * cstride] = bhi2;
+            }
+        }
+    }
+    pv2::pdl_done();
+    __syncthreads();
+    // pass 2a: the chunks of a cell folded into the cell's first chunk slot, per (component, cell, quad): s/4 terms each, in chunk
+    // order (at x32 a cell has 8 chunks and a column 8 quads: folding both inside the per-pixel loop is a 256-term serial chain)
+    for (int it = tid; it < 4 * ncell * ow4; it += blockDim.x) {
+        const int qq = it % ow4, r = it / ow4, cell = r % ncell, comp = r / ncell;
+        const int k0 = cell_k0[cell], k1 = cell_k0[cell + 1];
+        float* base = part + comp * cstride + qq;
+        float t = base[k0 * ow4];
+        for (int k = k0 + 1; k < k1; ++k) t += base[k * ow4];
+        base[k0 * ow4] = t;
+    }
+    __syncthreads();
+    // pass 2b: input pixel (y, ix) = lo parts of cell y + hi parts of cell y - 1 (and of cell y itself on the clamped last row),
+    // 'a' parts of the quads of column ix + 'b' parts of the quads of column ix - 1 (and of ix itself on the clamped last column)
+    for (int o = tid; o < nr * iw; o += blockDim.x) {
+        const int r = o / iw, ix = o - r * iw, y = ya + r;
+        float acc = 0.0f;
+        auto fold = [&](int cell, int ysel) {          // ysel 0: lo, 1: hi
+            const int k0 = cell_k0[cell - c0];
+            const float* pa = part + ysel * cstride + k0 * ow4;
+            const float* pb = part + (2 + ysel) * cstride + k0 * ow4;
+            for (int qq = run_q0[ix]; qq < run_q0[ix + 1]; ++qq) acc += pa[qq];
+            if (ix > 0)
+                for (int qq = run_q0[ix - 1]; qq < run_q0[ix]; ++qq) acc += pb[qq];
+            if (ix == iw - 1)
+                for (int qq = run_q0[ix]; qq < run_q0[ix + 1]; ++qq) acc += pb[qq];
+        };
+        fold(y, 0);
+        if (y > 0) fold(y - 1, 1);
+        if (y == ih - 1) fold(y, 1);
+        din[((size_t)plane * ih + y) * iw + ix] = from_f<T>(acc);
+    }
+}
+
 int check(const void* a, const void* b, int planes, int ih, int iw, int oh, int ow, int dtype, const char* who) {
     PV2_CHECK(a && b, "%s: null pointer", who);
     PV2_CHECK(planes > 0 && ih > 0 && iw > 0 && oh > 0 && ow > 0, "%s: empty shape", who);
@@ -347,7 +502,55 @@ static int bwd_row_blocks(int ih, int oh) {
     return (ih + R - 1) / R;
 }
 
+// the separable integer-scale backward applies when every map is an exact x8 / x16 / x32 / x64 half-pixel up-scaling
+static bool bwd2_ok(const MultiMaps& mm, int nmaps, int oh, int ow, int align_corners) {
+    static const bool off = [] { const char* e = getenv("PV2_BIL_BWD2"); return e && e[0] == '0'; }();
+    if (off || align_corners || (ow & 3) || ow / 4 > BWD2_THREADS) return false;
+    for (int i = 0; i < nmaps; ++i) {
+        const int ih = mm.ih[i], iw = mm.iw[i];
+        if (oh % ih || ow % iw) return false;
+        const int s = oh / ih;
+        if (s != ow / iw || (s & 7) || s > 64 || iw > BWD2_MAX_IW) return false;
+        if (mm.rh[i] != 1.0f / (float)s || mm.rw[i] != 1.0f / (float)s) return false;
+        const int chunks = (bwd2_rows_per_cta(ih, s, ow, 1) + 1) * s / 4 + s / 8;      // bands = 1: the tallest band the caps allow
+        if (chunks > BWD2_MAX_CHUNKS || 4 * chunks * ow > BWD2_SMEM) return false;
+    }
+    return true;
+}
+
+static int launch_bwd2(const MultiMaps& mm, int nmaps, int planes, int oh, int ow, int dtype, cudaStream_t st) {
+    const int ow4 = ow / 4;
+    int G = BWD2_THREADS / ow4;
+    if (G > 8) G = 8;
+    int threads = (ow4 * G + 31) / 32 * 32;
+    if (threads < 128) threads = 128;          // pass 2 and the tables still want a few warps
+    int hint = 2 * kNumSMs / (planes * nmaps);       // rounded down: one wave
+    if (hint < 2) hint = 2;
+    int bands = 1, maxchunk = 0;
+    for (int i = 0; i < nmaps; ++i) {
+        const int s = oh / mm.ih[i], R = bwd2_rows_per_cta(mm.ih[i], s, ow, hint);
+        const int nb = (mm.ih[i] + R - 1) / R;
+        if (nb > bands) bands = nb;
+        const int ch = (R + 1) * s / 4 + s / 8;       // the band that starts at input row 1 also reads all of cell 0 (1.5 s rows)
+        if (ch > maxchunk) maxchunk = ch;
+    }
+    const size_t smem = (size_t)4 * maxchunk * ow4 * sizeof(float);
+    dim3 grid(bands, planes, nmaps);
+    if (dtype == PV2_F32) {
+        static bool once = [] { return cudaFuncSetAttribute(bilinear_bwd2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM) == cudaSuccess; }();
+        (void)once;
+        pv2::launch(bilinear_bwd2_kernel<float>, grid, threads, smem, st, mm, oh, ow, G, hint);
+    } else {
+        static bool once = [] { return cudaFuncSetAttribute(bilinear_bwd2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM) == cudaSuccess; }();
+        (void)once;
+        pv2::launch(bilinear_bwd2_kernel<__nv_bfloat16>, grid, threads, smem, st, mm, oh, ow, G, hint);
+    }
+    PV2_LAUNCH_CHECK("bilinear_bwd2");
+    return 0;
+}
+
 static int launch_bwd(const MultiMaps& mm, int nmaps, int planes, int row_blocks, int oh, int ow, int align_corners, int dtype, cudaStream_t st) {
+    if (bwd2_ok(mm, nmaps, oh, ow, align_corners)) return launch_bwd2(mm, nmaps, planes, oh, ow, dtype, st);
     const int ow4 = (ow + 3) / 4;
     PV2_CHECK(ow4 <= BWD_THREADS, "bilinear_bwd: output width %d too large", ow);
     int rgroups = BWD_THREADS / ow4;

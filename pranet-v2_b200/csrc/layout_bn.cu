@@ -1139,20 +1139,18 @@ up2_nhwc_bwd4_kernel(const Slabs g, float* __restrict__ din, int din_ld, int N, 
             wx[k] = (xlo + k <= xhi) ? ac_weight(xlo + k, ix, W, rw) : 0.0f;
         }
         float4 acc = f4_set(0.0f);
-        // per contributing output row: ALL NC column candidates are loaded at once (clamped address, the weight decides) -- NC
-        // independent 16-byte loads in flight instead of a chain of conditional ones; zero-weight taps add exactly 0
+        // candidates beyond NC (ratio < 2/7: never for a x2 upsample of >= 2 pixels) cannot occur.  (Loading all NC column candidates
+        // of a contributing row unconditionally -- 7 independent loads per row instead of ~4 conditional ones -- was measured
+        // SLOWER, 34 us against 27: the kernel is bound by its L2 -> SM traffic, ~4.5x the gradient's bytes, not by load latency.)
 #pragma unroll
         for (int a = 0; a < NC; ++a) {
             if (wy[a] == 0.0f) continue;
-            const long long rowbase = (n * OH + min(ylo + a, OH - 1)) * OW;
-            float4 v[NC];
-#pragma unroll
-            for (int b = 0; b < NC; ++b) v[b] = slab_sum4(g, rowbase + min(xlo + b, OW - 1), c);
 #pragma unroll
             for (int b = 0; b < NC; ++b) {
                 if (wx[b] == 0.0f) continue;
                 const float w = wy[a] * wx[b];
-                acc.x += w * v[b].x; acc.y += w * v[b].y; acc.z += w * v[b].z; acc.w += w * v[b].w;
+                const float4 v = slab_sum4(g, (n * OH + ylo + a) * OW + xlo + b, c);
+                acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
             }
         }
         *reinterpret_cast<float4*>(din + ((n * H + iy) * W + ix) * din_ld + c) = acc;

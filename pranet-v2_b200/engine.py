@@ -42,6 +42,7 @@ assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.items
 assert _BNDEFER_DT.itemsize == 88
 _PAR_CTA_BUDGET = int(os.environ.get("PV2_PAR_CTA_BUDGET", "96"))
 _BN_ACC_STRIDE, _SUM_STRIDE = 16, 32   # == PV2_BN_ACC_STRIDE (doubles), PV2_SUM_STRIDE (floats) of include/pv2.h
+_UNPACK_BATCH = int(os.environ.get("PV2_UNPACK_BATCH", "4"))     # weight-gradient tensors per unpack launch on a companion stream
 _ZARENA_FLOATS = 1 << 20   # 4 MB: ~3.5 K conv channels x 32 floats (forward moments) + ~3.5 K x 4 sums x 32 floats (backward) = 0.56 M floats
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
 
@@ -212,6 +213,7 @@ class Engine:
         self.groups_seen = []      # conv groups in call order (recorded on the first run, prepacked in one launch afterwards)
         self.packed = {}           # group key -> (w_op fprop layout, w_op dgrad layout or None)
         self.unpack_jobs = []
+        self._wjobs = {}               # branch -> unpack jobs of wgrad GEMMs already launched on its companion stream
         self.dev = device
         self.kind = PV2_BF16 if precision == "bf16" else PV2_TF32
         self.nterms = 1 if precision == "bf16" else 3
@@ -580,9 +582,14 @@ class Engine:
                 _lib.check(lib.pv2_conv_wgrad(self._act_ptr(dy), self.plane_stride(dy), self._act_ptr(x), self.plane_stride(x), self.kind, self.nterms,
                                               N, H, W, Cin_p, Cout_p, Cout, KH, KW, dh, dw, part.data_ptr(), splits, wst), "pv2_conv_wgrad")
                 if wctx is not None:
-                    # on the companion stream the split sum + OIHW transpose follows its GEMM at once: it is off the critical path
-                    # there, and the end of the backward pass is not a 200 us serial tail of one big unpack over cold partials
-                    self._unpack(jobs, wst)
+                    # on the companion stream the split sum + OIHW transpose follows its GEMMs in batches of _UNPACK_BATCH layers (one
+                    # multi-tensor launch each): off the critical path there, a quarter of the launches of one unpack per layer, and
+                    # the end of the backward pass is not a 200 us serial tail of one big unpack over cold partials
+                    pend = self._wjobs.setdefault(self.cur, [])
+                    pend += jobs
+                    if len(pend) >= _UNPACK_BATCH:
+                        self._unpack(pend, wst)
+                        self._wjobs[self.cur] = []
                 else:
                     self.unpack_jobs += jobs                 # single-stream mode: one multi-tensor launch in flush_unpack()
             finally:
@@ -916,10 +923,13 @@ class Engine:
         if self._wused:            # join the weight-gradient streams
             main = torch.cuda.current_stream()
             for i in sorted(self._wused):
+                if self._wjobs.get(i):           # the stream's last (partial) batch of unpacks
+                    self._unpack(self._wjobs[i], self.wside[i].cuda_stream)
                 ev = torch.cuda.Event()
                 ev.record(self.wside[i])
                 main.wait_event(ev)
             self._wused = set()
+            self._wjobs = {}
         self.flush_unpack()
         self.tape = _Tape(self)
         self._keep = []

@@ -15,7 +15,7 @@ import pranet_v2_b200 as P
 from pranet_v2_b200 import synthetic
 
 what = sys.argv[1] if len(sys.argv) > 1 else "loss"
-B, S = 16, 352
+B, S = (int(v) for v in os.environ.get("PV2_PROF_BS", "16x352").lower().split("x"))
 dev = "cuda"
 torch.manual_seed(0)
 if what == "step":     # two eager training steps of the bench workload (launch list of the pv2 kernels)
@@ -93,6 +93,16 @@ elif what == "r2":     # round 2: the kernels the bench line's roofline / other_
             bnm = nn.BatchNorm2d(cout).to(dev).train()
             a = eng.new_act(B, hw, hw, cin)
             a.t.normal_()
+            eng.conv(a, [conv], [bnm])
+elif what == "r2conv":  # the seven distinct forward conv shapes of the head with the BatchNorm statistics fused, at PV2_PROF_BS
+    import torch.nn as nn
+    eng = P.engine.Engine(torch.device(dev), "bf16", True, False)
+    for (cin, cout, k, hw) in ((512, 224, 1, S // 8), (1024, 224, 1, S // 16), (2048, 416, 1, S // 32), (256, 256, 5, S // 32), (96, 96, 3, S // 8), (64, 64, 3, S // 8)):
+        conv = nn.Conv2d(cin, cout, k, padding=k // 2, bias=False).to(dev)
+        bnm = nn.BatchNorm2d(cout).to(dev).train()
+        a = eng.new_act(B, hw, hw, cin)
+        a.t.normal_()
+        for it in range(2):
             eng.conv(a, [conv], [bnm])
 elif what == "loss":
     m = synthetic.ellipse_masks(B, S, S, 3).to(dev)

@@ -96,6 +96,9 @@ def test_structure_loss_errors():
     ((2, 1, 44, 44), dict(scale_factor=0.25)), ((2, 1, 11, 11), dict(scale_factor=2)), ((3, 32, 11, 11), dict(scale_factor=2, align_corners=True)),
     ((2, 9, 7, 7), dict(size=(14, 14))), ((1, 4, 13, 9), dict(size=(31, 20))), ((2, 9, 56, 56), dict(scale_factor=4)),
     ((1, 2, 5, 7), dict(scale_factor=3)), ((1, 1, 1, 1), dict(scale_factor=4)), ((1, 1, 64, 64), dict(scale_factor=4.0)),
+    # the separable integer-scale backward (s % 8 == 0): ragged last band, non-square planes, 6 bands of 15 rows, x64, one row
+    ((1, 2, 13, 9), dict(scale_factor=16)), ((2, 2, 10, 14), dict(scale_factor=8)), ((1, 1, 88, 88), dict(scale_factor=8)),
+    ((1, 1, 3, 5), dict(scale_factor=64)), ((2, 1, 1, 4), dict(scale_factor=8)), ((1, 3, 22, 22), dict(scale_factor=32)),
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_bilinear_fwd_bwd(shape, kw, dtype):
