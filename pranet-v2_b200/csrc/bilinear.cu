@@ -10,10 +10,12 @@
 //      (x taps computed once per thread, quads that share their two source columns are interpolated vertically first) and writes
 //      them with one 16-byte streaming store.  HBM bytes = (P_in + P_out) * elt: write-bound; 78.6 % of the measured HBM peak on the
 //      8 final maps of a B = 16 x 352^2 step (12.4 us).
-// bwd: CTA = (R input rows, plane, map), R = 4 / 2 / 1 at x8 / x16 / x32.  Pass 1 folds the output rows that touch these input rows
-//      into R rows of column sums in shared memory (coalesced 16-byte reads of dout, y weights from a table), pass 2 folds the
-//      columns (x taps from a table, lane groups + shuffle tree).  Every dout element is read by at most 2 CTAs; no atomics,
-//      deterministic.  26.5 us on the same 8 maps (36.8 %): issue / latency bound, see DESIGN.md.
+// bwd: two kernels.  Exact x8 / x16 / x32 / x64 half-pixel up-scalings (the final maps of a step) take bilinear_bwd2_kernel: separable
+//      in registers -- a thread folds the 4 x 4 elements of a chunk into 4 partial sums with 13 FMA per 16-byte load, 8 loads in
+//      flight, CTA = (band of input rows, plane, map), 288 CTAs in one wave -- 19.1 us on the 8 maps (51 % of the measured HBM peak;
+//      the gather kernel: 28.5 us, 34 %).  Everything else (x2, x4, fractional ratios, align_corners) takes the gather kernel: CTA =
+//      (R input rows, plane, map), pass 1 folds the output rows that touch these input rows into R rows of column sums in shared
+//      memory, pass 2 folds the columns (x taps from a table, lane groups + shuffle tree).  No atomics in either, deterministic.
 #include "pv2_common.cuh"
 
 namespace pv2 {
@@ -323,16 +325,19 @@ constexpr int BWD2_THREADS = 384;
 constexpr int BWD2_MAX_CHUNKS = 52;      // 4-row chunks a CTA may own: (R + 1) * s / 4 + s / 8 (cell 0 also holds the s/2 clamped rows)
 constexpr int BWD2_MAX_IW = 96;
 
-constexpr int BWD2_SMEM = 100 * 1024;    // partial sums of a CTA: 4 components x chunks x ow / 4 floats = 4 * chunks * ow bytes
+constexpr int BWD2_SMEM = 64 * 1024;     // partial sums of a CTA: 4 components x cells x ow / 4 floats = 4 * (R + 1) * ow bytes
 
 // `bands` = bands per plane the host asks for: 2 when the launch already has ~2 CTAs per SM (the 8 final maps x 16 planes of a step
 // are 288 CTAs, one wave at 2 CTAs per SM), more for launches with few planes
 __host__ __device__ inline int bwd2_rows_per_cta(int ih, int s, int ow, int bands) {
+    // (a cell is s/8 trips and cells are dealt whole to the 4 row groups: at x32 a band of 5 rows is 6 cells = 8 trips for two
+    // groups and 4 for the others.  Twice the bands for x32 maps balances that, but the 8-map launch then has 320 CTAs, more than
+    // the 296 resident slots: measured 24.5 us against 19.1.)
     int r = (ih + bands - 1) / bands;
-    int maxc = BWD2_SMEM / (4 * ow);
-    if (maxc > BWD2_MAX_CHUNKS) maxc = BWD2_MAX_CHUNKS;
-    const int cap = (maxc - s / 8) * 4 / s - 1;
+    const int cap = (BWD2_MAX_CHUNKS - s / 8) * 4 / s - 1;         // window rows: (R + 1) * s + s / 2 <= 4 * BWD2_MAX_CHUNKS
+    const int cap2 = BWD2_SMEM / (4 * ow) - 1;
     if (r > cap) r = cap;
+    if (r > cap2) r = cap2;
     return r < 1 ? 1 : r;
 }
 
@@ -340,7 +345,7 @@ template <typename T>
 __global__ void __launch_bounds__(BWD2_THREADS, 2)
 bilinear_bwd2_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int G, int bands_hint) {
     pv2::pdl_prologue();
-    extern __shared__ __align__(16) float part[];     // [4 components: a_lo, a_hi, b_lo, b_hi][chunk][ow4]
+    extern __shared__ __align__(16) float part[];     // [4 components: a_lo, a_hi, b_lo, b_hi][cell][ow4]
     __shared__ float2 ytab[BWD2_MAX_CHUNKS * 4];      // (w0, w1) of every window row
     __shared__ int chunk_i0[BWD2_MAX_CHUNKS];         // source row i0 of a chunk
     __shared__ int cell_k0[BWD2_MAX_CHUNKS + 2];      // first chunk of cell (c0 + i); sentinel at the end
@@ -393,54 +398,48 @@ bilinear_bwd2_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int G
         const int cur = k == ow4 ? iw : quad_i0[k];
         for (int c = prev + 1; c <= cur; ++c) run_q0[c] = k;
     }
-    const int cstride = nchunk * ow4;                  // component stride of part[]
+    __syncthreads();
+    const int cstride = ncell * ow4;                   // component stride of part[]
     if (grp < G) {
         const T* gp = g + (size_t)row0 * ow + q * 4;
-        // two chunks per trip, folded in ONE interleaved loop so that all 8 independent 16-byte loads are issued before the first
-        // FMA (with two separate folds ptxas sinks the second chunk's loads below the first fold: 4 in flight again)
-        for (int k = grp; k < nchunk; k += 2 * G) {
-            const bool two = k + G < nchunk;
-            const int k2 = two ? k + G : k;
-            const T* p = gp + (size_t)(k * 4) * ow;
-            const T* p2 = gp + (size_t)(k2 * 4) * ow;
-            float4 v[4], v2[4];
+        // a thread folds whole cells (cell grp, grp + G, ...): the chunks of a cell accumulate in registers, two chunks per trip in ONE
+        // interleaved loop so that all 8 independent 16-byte loads are issued before the first FMA (with two separate folds ptxas
+        // sinks the second chunk's loads below the first fold: 4 in flight again).  (Dealing two-chunk work items instead of cells to
+        // the groups balances a x32 band better on paper and measured slower, 22.8 us against 19.1: one more table, longer pass 2.)
+        for (int cell = grp; cell < ncell; cell += G) {
+            const int k0 = cell_k0[cell], k1 = cell_k0[cell + 1];
+            float alo = 0.0f, ahi = 0.0f, blo = 0.0f, bhi = 0.0f;
+            for (int k = k0; k < k1; k += 2) {
+                const bool two = k + 1 < k1;
+                const int k2 = two ? k + 1 : k;
+                const float m2 = two ? 1.0f : 0.0f;
+                const T* p = gp + (size_t)(k * 4) * ow;
+                const T* p2 = gp + (size_t)(k2 * 4) * ow;
+                float4 v[4], v2[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = load4<T>(p + (size_t)u * ow);
+                for (int u = 0; u < 4; ++u) v[u] = load4<T>(p + (size_t)u * ow);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v2[u] = load4<T>(p2 + (size_t)u * ow);
-            float alo = 0.0f, ahi = 0.0f, blo = 0.0f, bhi = 0.0f, alo2 = 0.0f, ahi2 = 0.0f, blo2 = 0.0f, bhi2 = 0.0f;
+                for (int u = 0; u < 4; ++u) v2[u] = load4<T>(p2 + (size_t)u * ow);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float a = fmaf(wx0[3], v[u].w, fmaf(wx0[2], v[u].z, fmaf(wx0[1], v[u].y, wx0[0] * v[u].x)));
-                const float a2 = fmaf(wx0[3], v2[u].w, fmaf(wx0[2], v2[u].z, fmaf(wx0[1], v2[u].y, wx0[0] * v2[u].x)));
-                const float b = fmaf(wx1[3], v[u].w, fmaf(wx1[2], v[u].z, fmaf(wx1[1], v[u].y, wx1[0] * v[u].x)));
-                const float b2 = fmaf(wx1[3], v2[u].w, fmaf(wx1[2], v2[u].z, fmaf(wx1[1], v2[u].y, wx1[0] * v2[u].x)));
-                const float2 wy = ytab[k * 4 + u], wy2 = ytab[k2 * 4 + u];
-                alo = fmaf(wy.x, a, alo); ahi = fmaf(wy.y, a, ahi);
-                blo = fmaf(wy.x, b, blo); bhi = fmaf(wy.y, b, bhi);
-                alo2 = fmaf(wy2.x, a2, alo2); ahi2 = fmaf(wy2.y, a2, ahi2);
-                blo2 = fmaf(wy2.x, b2, blo2); bhi2 = fmaf(wy2.y, b2, bhi2);
+                for (int u = 0; u < 4; ++u) {
+                    const float a = fmaf(wx0[3], v[u].w, fmaf(wx0[2], v[u].z, fmaf(wx0[1], v[u].y, wx0[0] * v[u].x)));
+                    const float a2 = fmaf(wx0[3], v2[u].w, fmaf(wx0[2], v2[u].z, fmaf(wx0[1], v2[u].y, wx0[0] * v2[u].x)));
+                    const float b = fmaf(wx1[3], v[u].w, fmaf(wx1[2], v[u].z, fmaf(wx1[1], v[u].y, wx1[0] * v[u].x)));
+                    const float b2 = fmaf(wx1[3], v2[u].w, fmaf(wx1[2], v2[u].z, fmaf(wx1[1], v2[u].y, wx1[0] * v2[u].x)));
+                    const float2 wy = ytab[k * 4 + u];
+                    float2 wy2 = ytab[k2 * 4 + u];
+                    wy2.x *= m2; wy2.y *= m2;
+                    alo = fmaf(wy.x, a, alo); ahi = fmaf(wy.y, a, ahi);
+                    blo = fmaf(wy.x, b, blo); bhi = fmaf(wy.y, b, bhi);
+                    alo = fmaf(wy2.x, a2, alo); ahi = fmaf(wy2.y, a2, ahi);
+                    blo = fmaf(wy2.x, b2, blo); bhi = fmaf(wy2.y, b2, bhi);
+                }
             }
-            float* o = part + k * ow4 + q;
+            float* o = part + cell * ow4 + q;
             o[0] = alo; o[cstride] = ahi; o[2 * cstride] = blo; o[3 * cstride] = bhi;
-            if (two) {
-                float* o2 = part + k2 * ow4 + q;
-                o2[0] = alo2; o2[cstride] = ahi2; o2[2 * cstride] = blo2; o2[3 * cstride] = bhi2;
-            }
         }
     }
     pv2::pdl_done();
-    __syncthreads();
-    // pass 2a: the chunks of a cell folded into the cell's first chunk slot, per (component, cell, quad): s/4 terms each, in chunk
-    // order (at x32 a cell has 8 chunks and a column 8 quads: folding both inside the per-pixel loop is a 256-term serial chain)
-    for (int it = tid; it < 4 * ncell * ow4; it += blockDim.x) {
-        const int qq = it % ow4, r = it / ow4, cell = r % ncell, comp = r / ncell;
-        const int k0 = cell_k0[cell], k1 = cell_k0[cell + 1];
-        float* base = part + comp * cstride + qq;
-        float t = base[k0 * ow4];
-        for (int k = k0 + 1; k < k1; ++k) t += base[k * ow4];
-        base[k0 * ow4] = t;
-    }
     __syncthreads();
     // pass 2b: input pixel (y, ix) = lo parts of cell y + hi parts of cell y - 1 (and of cell y itself on the clamped last row),
     // 'a' parts of the quads of column ix + 'b' parts of the quads of column ix - 1 (and of ix itself on the clamped last column)
@@ -448,9 +447,8 @@ bilinear_bwd2_kernel(const __grid_constant__ MultiMaps mm, int oh, int ow, int G
         const int r = o / iw, ix = o - r * iw, y = ya + r;
         float acc = 0.0f;
         auto fold = [&](int cell, int ysel) {          // ysel 0: lo, 1: hi
-            const int k0 = cell_k0[cell - c0];
-            const float* pa = part + ysel * cstride + k0 * ow4;
-            const float* pb = part + (2 + ysel) * cstride + k0 * ow4;
+            const float* pa = part + ysel * cstride + (cell - c0) * ow4;
+            const float* pb = part + (2 + ysel) * cstride + (cell - c0) * ow4;
             for (int qq = run_q0[ix]; qq < run_q0[ix + 1]; ++qq) acc += pa[qq];
             if (ix > 0)
                 for (int qq = run_q0[ix - 1]; qq < run_q0[ix]; ++qq) acc += pb[qq];
@@ -513,7 +511,7 @@ static bool bwd2_ok(const MultiMaps& mm, int nmaps, int oh, int ow, int align_co
         if (s != ow / iw || (s & 7) || s > 64 || iw > BWD2_MAX_IW) return false;
         if (mm.rh[i] != 1.0f / (float)s || mm.rw[i] != 1.0f / (float)s) return false;
         const int chunks = (bwd2_rows_per_cta(ih, s, ow, 1) + 1) * s / 4 + s / 8;      // bands = 1: the tallest band the caps allow
-        if (chunks > BWD2_MAX_CHUNKS || 4 * chunks * ow > BWD2_SMEM) return false;
+        if (chunks > BWD2_MAX_CHUNKS || 4 * (bwd2_rows_per_cta(ih, s, ow, 1) + 1) * ow > BWD2_SMEM) return false;
     }
     return true;
 }
@@ -526,15 +524,14 @@ static int launch_bwd2(const MultiMaps& mm, int nmaps, int planes, int oh, int o
     if (threads < 128) threads = 128;          // pass 2 and the tables still want a few warps
     int hint = 2 * kNumSMs / (planes * nmaps);       // rounded down: one wave
     if (hint < 2) hint = 2;
-    int bands = 1, maxchunk = 0;
+    int bands = 1, maxcell = 0;
     for (int i = 0; i < nmaps; ++i) {
         const int s = oh / mm.ih[i], R = bwd2_rows_per_cta(mm.ih[i], s, ow, hint);
         const int nb = (mm.ih[i] + R - 1) / R;
         if (nb > bands) bands = nb;
-        const int ch = (R + 1) * s / 4 + s / 8;       // the band that starts at input row 1 also reads all of cell 0 (1.5 s rows)
-        if (ch > maxchunk) maxchunk = ch;
+        if (R + 1 > maxcell) maxcell = R + 1;
     }
-    const size_t smem = (size_t)4 * maxchunk * ow4 * sizeof(float);
+    const size_t smem = (size_t)4 * maxcell * ow4 * sizeof(float);
     dim3 grid(bands, planes, nmaps);
     if (dtype == PV2_F32) {
         static bool once = [] { return cudaFuncSetAttribute(bilinear_bwd2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM) == cudaSuccess; }();
