@@ -162,7 +162,7 @@ def sweep_point(P, model, B, S, iters, chans, dev, lowres=False):
     torch.cuda.synchronize()
     n0 = P._lib.launch_count()
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    with torch.cuda.graph(graph, stream=P.engine.capture_stream()):
         loss = step()
     launches = P._lib.launch_count() - n0
     ms = timed(graph.replay, iters)

@@ -189,7 +189,7 @@ inline Layout make_layout(void* ws, int planes, int H, int W) {
 template <typename T, int NS, int VEC>
 __global__ void __launch_bounds__(LS_THREADS)
 structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const float* __restrict__ mask_bg,
-                          const uint16_t* __restrict__ wmap, int HW, int planes, int chunks, int wt_tiles,
+                          const uint16_t* __restrict__ wmap, int HW, int planes, int chunks, int chunk_px, int wt_tiles,
                           float* __restrict__ partials, const float* __restrict__ wsum_part, float* __restrict__ plane_sums,
                           float* __restrict__ plane_loss, float* __restrict__ loss, unsigned int* __restrict__ ticket) {
     pv2::pdl_prologue();
@@ -197,7 +197,7 @@ structure_loss_fwd_kernel(PtrPack pp, const float* __restrict__ mask_fg, const f
     __shared__ bool is_last;
     const int plane = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const size_t pbase = (size_t)plane * HW;
-    const int p0 = chunk * CHUNK, p1 = min(HW, p0 + CHUNK);
+    const int p0 = chunk * chunk_px, p1 = min(HW, p0 + chunk_px);
     float acc[4 * NS];
 #pragma unroll
     for (int i = 0; i < 4 * NS; ++i) acc[i] = 0.0f;
@@ -836,8 +836,8 @@ lowres_grad_fold_kernel(const __grid_constant__ PtrPack pp, const __grid_constan
 }
 
 template <typename T, int VEC>
-void launch_fwd(int ns, dim3 grid, cudaStream_t st, const PtrPack& pp, const float* mf, const float* mb, const Layout& L, int HW, int planes, float* loss) {
-#define PV2_FWD(NSV) pv2::launch(structure_loss_fwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, HW, planes, L.chunks, L.wt_tiles, \
+void launch_fwd(int ns, dim3 grid, int chunk_px, cudaStream_t st, const PtrPack& pp, const float* mf, const float* mb, const Layout& L, int HW, int planes, float* loss) {
+#define PV2_FWD(NSV) pv2::launch(structure_loss_fwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, HW, planes, (int)grid.x, chunk_px, L.wt_tiles, \
                          L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
     switch (ns) { case 1: PV2_FWD(1); break; case 2: PV2_FWD(2); break; case 3: PV2_FWD(3); break; default: PV2_FWD(4); break; }
 #undef PV2_FWD
@@ -947,13 +947,19 @@ static int structure_loss_fwd_impl(const void* const* pred, const void* const* p
         pv2::launch(boundary_weight_kernel, dim3(L.wt_tiles, planes), WT_THREADS, 0, st, mask_fg, L.wmap, L.wsum_part, L.ticket, reinterpret_cast<double*>(L.partials), H, W, L.wt_tiles_x, L.wt_tiles);
         PV2_LAUNCH_CHECK("boundary_weight");
     }
-    const dim3 grid(L.chunks, planes);
+    // pixels per CTA: 2048 like the backward.  Measured at B = 16 x 352^2 (PV2_LOSS_FWD_CHUNK): 1024 / 2048 / 3072 / 4096 / 6144 / 8192 px
+    // -> 24.0 / 23.1 / 24.4 / 24.2 / 26.3 / 26.1 us: neither the reduction tail of a CTA nor the 1.65 waves of 976 CTAs is what bounds it
+    int chunk_px = pv2::tune_int("PV2_LOSS_FWD_CHUNK", 0);
+    if (chunk_px <= 0) chunk_px = CHUNK;
+    if (chunk_px < 1024) chunk_px = 1024;
+    chunk_px = (chunk_px + 1023) / 1024 * 1024;
+    const dim3 grid((HW + chunk_px - 1) / chunk_px, planes);
     if (logit_dtype == PV2_F32) {
-        if (vec) launch_fwd<float, 4>(nscales, grid, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
-        else launch_fwd<float, 1>(nscales, grid, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
+        if (vec) launch_fwd<float, 4>(nscales, grid, chunk_px, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
+        else launch_fwd<float, 1>(nscales, grid, chunk_px, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
     } else {
-        if (vec) launch_fwd<__nv_bfloat16, 4>(nscales, grid, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
-        else launch_fwd<__nv_bfloat16, 1>(nscales, grid, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
+        if (vec) launch_fwd<__nv_bfloat16, 4>(nscales, grid, chunk_px, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
+        else launch_fwd<__nv_bfloat16, 1>(nscales, grid, chunk_px, st, pp, mask_fg, mask_bg, L, HW, planes, loss);
     }
     PV2_LAUNCH_CHECK("structure_loss_fwd");
     return 0;

@@ -42,6 +42,10 @@ assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.items
 assert _BNDEFER_DT.itemsize == 88
 _PAR_CTA_BUDGET = int(os.environ.get("PV2_PAR_CTA_BUDGET", "96"))
 _BN_ACC_STRIDE, _SUM_STRIDE = 16, 32   # == PV2_BN_ACC_STRIDE (doubles), PV2_SUM_STRIDE (floats) of include/pv2.h
+# stream priority of the dependent chains (branch streams; -1 = above the default 0 the weight-gradient companions run at, so a chain's
+# next kernel is placed before queued wgrad / unpack CTAs; captured graphs keep it as the kernel nodes' priority).  Head step at
+# B = 16 x 352^2: 1.775 ms at priority 0, 1.749 ms at -1 (two runs each, same box).  capture_stream() is what TrainStep / bench_head capture on.
+_CHAIN_PRIORITY = int(os.environ.get("PV2_CHAIN_PRIORITY", "-1"))
 _UNPACK_BATCH = int(os.environ.get("PV2_UNPACK_BATCH", "4"))     # weight-gradient tensors per unpack launch on a companion stream
 _ZARENA_FLOATS = 1 << 20   # 4 MB: ~3.5 K conv channels x 32 floats (forward moments) + ~3.5 K x 4 sums x 32 floats (backward) = 0.56 M floats
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
@@ -138,7 +142,7 @@ MAX_BRANCHES = 12
 def _side_streams(device):
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx not in _SIDE_STREAMS:
-        _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=device) for _ in range(MAX_BRANCHES)]
+        _SIDE_STREAMS[idx] = [torch.cuda.Stream(device=device, priority=_CHAIN_PRIORITY) for _ in range(MAX_BRANCHES)]
     return _SIDE_STREAMS[idx]
 
 
@@ -150,6 +154,12 @@ def _wgrad_streams(device):
     if idx not in _WGRAD_STREAMS:
         _WGRAD_STREAMS[idx] = [torch.cuda.Stream(device=device) for _ in range(MAX_BRANCHES + 1)]
     return _WGRAD_STREAMS[idx]
+
+
+def capture_stream(device=None):
+    """A stream of the chains' priority to capture a step on (torch.cuda.graph(g, stream=...)): the main chain then outranks the
+    weight-gradient companions like the branch streams do."""
+    return torch.cuda.Stream(device=device, priority=_CHAIN_PRIORITY)
 
 
 def streams_enabled() -> bool:

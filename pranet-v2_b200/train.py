@@ -20,6 +20,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import _lib, ops
+from . import engine as _engine
 
 LOSS_FROM_LOWRES_DEFAULT = "0"    # TrainStep(loss_from_lowres=None): "1" = final upsamples fused into the loss kernels (§8 f2)
 _UNUSED_PREFIXES = ("backbone.fc.", "resnet.fc.")   # defined by the reference nets but never used in forward
@@ -260,11 +261,12 @@ class TrainStep:
         graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         pool = self._pool
         n0 = _lib.launch_count()
-        with torch.cuda.graph(graph_a, pool=pool):
+        cap = _engine.capture_stream(self.device)
+        with torch.cuda.graph(graph_a, pool=pool, stream=cap):
             loss = self._fwd_bwd(img, gt)
         if pool is None:
             pool = self._pool = graph_a.pool()
-        with torch.cuda.graph(graph_b, pool=pool):
+        with torch.cuda.graph(graph_b, pool=pool, stream=cap):
             self._update()
         self.pv2_launches_per_step = _lib.launch_count() - n0     # pv2 kernel nodes inside the two graphs
         return graph_a, graph_b, img, gt, loss
@@ -404,7 +406,7 @@ class InferStep:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=_engine.capture_stream(self.device)):
                 out = self._run(img, size)
             self.pv2_launches_per_step = _lib.launch_count() - n0
             self._graphs[key] = (graph, img, out)

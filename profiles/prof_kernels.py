@@ -88,7 +88,7 @@ elif what == "r2":     # round 2: the kernels the bench line's roofline / other_
         lab = torch.randint(0, 9, (B, 224, 224), device=dev)
         P.mc_dual_loss(fg[:4], fg[4:], lab, 9).backward()
         eng = P.engine.Engine(torch.device(dev), "bf16", True, False)
-        for (cin, cout, k, hw) in ((512, 224, 1, S // 8), (2048, 416, 1, S // 32), (256, 256, 5, S // 32), (96, 96, 3, S // 8), (64, 64, 3, S // 8), (32, 32, 3, S // 8)):
+        for (cin, cout, k, hw) in ((512, 224, 1, S // 8), (1024, 224, 1, S // 16), (2048, 416, 1, S // 32), (256, 256, 5, S // 32), (96, 96, 3, S // 8), (64, 64, 3, S // 8), (32, 32, 3, S // 8)):
             conv = nn.Conv2d(cin, cout, k, padding=k // 2, bias=False).to(dev)
             bnm = nn.BatchNorm2d(cout).to(dev).train()
             a = eng.new_act(B, hw, hw, cin)
