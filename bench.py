@@ -656,8 +656,13 @@ def roofline_report(P, dev, B, S, n_params):
             "peak_source": f"{src}: bf16_tflops (burst; each kernel is timed alone)", "flops_per_launch_set": fl, "us_per_launch_set": us,
             "traffic": traffic.get("conv_fwd2_kernel", {}).get("dram_bytes_per_launch_set"),
             "shapes": [{"shape": r["kernel"].replace("conv_fwd+bn_stats ", ""), "flops": r["flops"], "us": r["us"], "tflops": r["achieved_tflops"],
-                        "frac": r["frac_of_bf16_peak"], "us_without_bn_stats": plain.get(r["kernel"].replace("conv_fwd+bn_stats ", ""), {}).get("us")} for r in convs],
-            "note": "2*M*N*K un-padded; 24 launches per shape captured in a CUDA graph, inputs rotate over > 300 MB"}
+                        "frac": r["frac_of_bf16_peak"], "hbm_bytes": r.get("hbm_bytes"), "hbm_frac": r.get("frac_of_hbm_peak"), "roof": r.get("roof"),
+                        "frac_of_own_roof": r.get("frac_of_own_roof"),
+                        "us_without_bn_stats": plain.get(r["kernel"].replace("conv_fwd+bn_stats ", ""), {}).get("us")} for r in convs],
+            "frac_of_own_roofs": sum(r.get("frac_of_own_roof", 0.0) * r["us"] for r in convs) / us,
+            "note": "2*M*N*K un-padded; 24 launches per shape captured in a CUDA graph, inputs rotate over > 300 MB.  `frac` is against the bf16 tensor "
+                    "peak for every shape; `roof` / `frac_of_own_roof` per shape use the lower of the tensor and the HBM roof (the 1x1 level GEMMs have "
+                    "119-156 FLOP/B against a ridge of ~254), `frac_of_own_roofs` is their time-weighted mean"}
     others = []
     for r in rows:
         if r["bound"] != "hbm" or r["kernel"].startswith("yardstick"):
@@ -727,7 +732,7 @@ def roofline_mc_loss(P, dev, B=16, C=9, S=224, n=12, reps=5):
     bytes_f = px * 8 * 4 + B * S * S * 8
     bytes_b = bytes_f + px * 8 * 4
     return {"kernel": f"mc_dual_loss fwd+bwd (15 subsets, {B}x{C}x{S}^2)", "bound": "hbm", "achieved": (bytes_f + bytes_b) / t_fb / 1e9, "unit": "GB/s",
-            "bytes_per_launch": bytes_f + bytes_b, "avg_ms": t_fb * 1e3, "traffic": None,
+            "bytes_per_launch": bytes_f + bytes_b, "avg_ms": t_fb * 1e3, "traffic": None, "traffic_key": "mc_dual_loss", "elements": px,
             "fwd": {"kernel": "mc_dual_loss fwd", "achieved": bytes_f / t_f / 1e9, "bytes_per_launch": bytes_f, "avg_ms": t_f * 1e3},
             "note": f"{n} fwd(+bwd) calls captured in a CUDA graph, {reps} replays; logits rotate over 3 sets"}
 

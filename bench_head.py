@@ -352,8 +352,13 @@ def kernel_table(P, dev, B, S, hbm, tflops):
             fn()
             ms = timed_graph(fn)
             eng._keep.clear()
+            # algorithmic HBM bytes: A once (bf16), the packed weights, the fp32 raw output; the roof of a shape is the lower of the two
+            hb = B * hw * hw * cin * 2 + cout * cin * k * k * 2 + B * hw * hw * cout * 4
+            t_roof = max(fl / (tflops * 1e12), hb / (hbm * 1e9))
             out.append({"kernel": f"{tag} {label} M={B * hw * hw} N={cout} K={cin * k * k}", "bound": "tensor", "flops": fl, "us": ms * 1e3,
-                        "achieved_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tflops})
+                        "achieved_tflops": fl / (ms * 1e-3) / 1e12, "frac_of_bf16_peak": fl / (ms * 1e-3) / 1e12 / tflops,
+                        "hbm_bytes": hb, "frac_of_hbm_peak": hb / (ms * 1e-3) / 1e9 / hbm,
+                        "roof": "hbm" if hb / (hbm * 1e9) > fl / (tflops * 1e12) else "tensor", "frac_of_own_roof": t_roof / (ms * 1e-3)})
         del acts
     return out
 
