@@ -225,6 +225,28 @@ class TrainStep:
         self.bucket.install(self.params)
         self.opt.step()
 
+    # -- hyper-parameters ---------------------------------------------------------------------------------------
+    @property
+    def lr(self) -> float:
+        return float(self.bucket.lr) if self.opt is None else float(self.opt.param_groups[0]["lr"])
+
+    def set_lr(self, lr: float) -> None:
+        """The reference's per-epoch `adjust_lr` (binary_seg/utils/utils.py:20-23, MyTrain_med.py:160).  The hyper-parameters are
+        launch arguments of pv2_adam_clamp_flat (or Python floats of the torch optimizer) and therefore frozen into the captured
+        optimizer graph: graph B of every captured shape -- one launch -- is re-captured with the new value; graph A (forward,
+        backward, gradient gather) is untouched.  Capturing launches nothing, so this does not train."""
+        lr = float(lr)
+        if self.opt is None:
+            self.bucket.lr = lr
+        else:
+            for grp in self.opt.param_groups:
+                grp["lr"] = torch.as_tensor(lr, device=grp["lr"].device) if isinstance(grp["lr"], torch.Tensor) else lr
+        for key, (graph_a, _old, img, gt, loss) in list(self._graphs.items()):
+            graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_b, pool=self._pool, stream=_engine.capture_stream(self.device)):
+                self._update()
+            self._graphs[key] = (graph_a, graph_b, img, gt, loss)
+
     # -- graph capture ------------------------------------------------------------------------------------------
     def _capture(self, images, gts):
         """Capture the step for one input shape.  Every shape (the multi-scale loop of MyTrain_med.py:59-74 uses three) gets its
@@ -237,10 +259,14 @@ class TrainStep:
         gt.copy_(gts)
         # warm-up (cuDNN autotune, allocator, lazy inits) must not train: with the flat layout the whole training state is
         # four buffers + the BatchNorm statistics, snapshotted here and put back before the capture
-        snap = None
+        snap = osnap = None
         if self.opt is None:
             b = self.bucket
             snap = ([b.p.clone(), b.m.clone(), b.v.clone(), b.step.clone()], [t.clone() for t in self.model.buffers()])
+        else:       # the torch-optimizer arm: parameters, BatchNorm statistics and the optimizer's own state
+            import copy
+            snap = ([p.detach().clone() for p in self.params], [t.clone() for t in self.model.buffers()])
+            osnap = copy.deepcopy(self.opt.state_dict())
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -251,13 +277,19 @@ class TrainStep:
                 self._update()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        if snap is not None:
-            for dst, src in zip([b.p, b.m, b.v, b.step], snap[0]):
+        with torch.no_grad():
+            for dst, src in zip([b.p, b.m, b.v, b.step] if self.opt is None else self.params, snap[0]):
                 dst.copy_(src)
             for dst, src in zip(self.model.buffers(), snap[1]):
                 dst.copy_(src)
-            del snap
-            torch.cuda.synchronize()
+            if osnap is not None:     # in place: the captured graph must keep seeing the same state tensors
+                old = osnap["state"]
+                for k, st in self.opt.state_dict()["state"].items():
+                    for name, val in st.items():
+                        if isinstance(val, torch.Tensor):     # state created by the warm-up itself (first capture) goes back to zero
+                            val.copy_(old[k][name]) if (k in old and name in old[k]) else val.zero_()
+        del snap, osnap
+        torch.cuda.synchronize()
         graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         pool = self._pool
         n0 = _lib.launch_count()

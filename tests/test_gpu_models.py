@@ -218,6 +218,59 @@ def test_train_step_multiscale_graphs():
     assert len(ts._graphs) == 3 and sum(again) < sum(losses)        # replays only, and it trains
 
 
+def test_train_step_set_lr_recaptures_optimizer_graph():
+    """binary_seg/utils/utils.py:20-23 adjust_lr: the learning rate is frozen into the captured optimizer graph, set_lr() re-captures it
+    (ADVICE r1).  With lr = 0 a replayed step must leave the parameters where they are; back at 1e-4 it trains again."""
+    from pranet_v2_b200.train import TrainStep
+    from pranet_v2_b200 import synthetic
+    torch.manual_seed(0)
+    m = P.PraNet_V2(num_class=1)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=3))
+    ts = TrainStep(m, lr=1e-4, clip=0.5, autocast_backbone=False, device="cuda:0", use_graph=True)
+    x = synthetic.images(2, 96, 0).to(DEV)
+    gt = synthetic.ellipse_masks(2, 96, 96, 0).to(DEV)
+    ts.step_device(x, gt)
+    assert ts.lr == pytest.approx(1e-4)
+    p1 = ts.bucket.p.clone()
+    ts.set_lr(0.0)
+    assert ts.lr == 0.0 and int(ts.bucket.step.item()) == 1          # re-capturing launched nothing
+    ts.step_device(x, gt)
+    assert torch.equal(ts.bucket.p, p1) and int(ts.bucket.step.item()) == 2
+    ts.set_lr(1e-4)
+    ts.step_device(x, gt)
+    assert (ts.bucket.p - p1).abs().max().item() > 0
+
+
+def test_train_step_torch_optimizer_warmup_does_not_train():
+    """The capture warm-up of the torch-optimizer arm (the A/B arm against pv2_adam_clamp_flat) is undone like the pv2 arm's
+    (ADVICE r1): after the first graph step the parameters moved by ONE Adam step (<= lr each), not four, and the optimizer's
+    step counter reads 1."""
+    from pranet_v2_b200.train import TrainStep
+    from pranet_v2_b200 import synthetic
+    torch.manual_seed(0)
+    m = P.PraNet_V2(num_class=1)
+    m.load_state_dict(synth.synth_state_dict(m.state_dict(), seed=3))
+    ts = TrainStep(m, lr=1e-4, clip=0.5, autocast_backbone=False, device="cuda:0", use_graph=True, optimizer="torch")
+    x = synthetic.images(2, 96, 0).to(DEV)
+    gt = synthetic.ellipse_masks(2, 96, 96, 0).to(DEV)
+    p0 = [p.detach().clone() for p in ts.params]
+    b0 = [t.clone() for t in m.buffers() if t.dtype.is_floating_point]
+    ts.step_device(x, gt)
+    torch.cuda.synchronize()
+    moved = max((p.detach() - q).abs().max().item() for p, q in zip(ts.params, p0))
+    assert 0 < moved <= 1.01e-4, moved
+    steps = {int(st["step"].item()) for st in ts.opt.state.values() if "step" in st}
+    assert steps == {1}, steps
+    # BatchNorm running statistics: exactly one momentum update from the initial values (a second replay moves them again)
+    b1 = [t.clone() for t in m.buffers() if t.dtype.is_floating_point]
+    ts.step_device(x, gt)
+    torch.cuda.synchronize()
+    b2 = [t.clone() for t in m.buffers() if t.dtype.is_floating_point]
+    d1 = max((a - b).abs().max().item() for a, b in zip(b1, b0))
+    d2 = max((a - b).abs().max().item() for a, b in zip(b2, b1))
+    assert d1 > 0 and d2 > 0 and d1 <= 1.6 * d2 + 1e-6, (d1, d2)      # one momentum update: d1 ~ 1.1 d2; three un-undone warm-up steps would make d1 ~ 5 d2
+
+
 def test_step_host_prefetch_equals_plain():
     """step_host with next_batch= (H2D of the next batch overlapped with this step's compute) trains exactly like step_host
     without it: same batches in the same order reach the same losses."""
