@@ -233,6 +233,12 @@ int pv2_conv_sums_splits(void);
  * trip are paid once per CTA instead of once per tile -- and CTAs of different launches are resident side by side instead of
  * queueing for the same slots.  Returns the previous value. */
 int pv2_conv_set_cta_budget(int max_ctas);
+/* BatchNorm backward (pv2_bn_act_bwd, single-source training case) as ONE launch -- reduce, grid-wide barrier, dx -- instead of two.
+ * A barrier kernel is only safe when all of its CTAs are resident at once, so the caller, who knows how many such launches can run
+ * side by side (parallel chains on side streams), grants each at most `max_ctas` CTAs (capped at one per SM): the sum over
+ * concurrent launches must stay below what the device can hold (4 CTAs of 256 threads x 64 registers per SM).  0 (the default) = two launches.
+ * Returns the previous value. */
+int pv2_bn_set_fused_grid(int max_ctas);
 /* dW partials out[split][Cout][KH*KW][Cin_p] = sum over the split's pixels of dY[p][co] * X[p + tap shift][ci] */
 int pv2_conv_wgrad_splits_hint(int N, int H, int W, int Cin_p, int Cout, int KH, int KW, int kind);
 int pv2_conv_wgrad(const void* dy, long long dy_plane_stride, const void* x, long long x_plane_stride, int kind, int nterms,

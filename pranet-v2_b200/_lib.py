@@ -48,6 +48,7 @@ _SIGS = {
     "pv2_conv_fwd": (_i, [_p, _ll, _p, _ll, _i, _i] + [_i] * 9 + [_i, _p, _i, _i, _p, _p, _p, _p]),
     "pv2_conv_sums_splits": (_i, []),
     "pv2_conv_set_cta_budget": (_i, [_i]),
+    "pv2_bn_set_fused_grid": (_i, [_i]),
     "pv2_bn_fuse_workspace_floats": (_sz, [_ll, _i]),
     "pv2_conv_fuses_bn_stats": (_i, [_i, _i]),
     "pv2_bn_stats_group": (_i, [_p, _ll, _i, _ll, _i, _i, _p, _p]),

@@ -46,6 +46,7 @@ _BN_ACC_STRIDE, _SUM_STRIDE = 16, 32   # == PV2_BN_ACC_STRIDE (doubles), PV2_SUM
 # next kernel is placed before queued wgrad / unpack CTAs; captured graphs keep it as the kernel nodes' priority).  Head step at
 # B = 16 x 352^2: 1.775 ms at priority 0, 1.749 ms at -1 (two runs each, same box).  capture_stream() is what TrainStep / bench_head capture on.
 _CHAIN_PRIORITY = int(os.environ.get("PV2_CHAIN_PRIORITY", "-1"))
+_BN_FUSED_SLOTS = int(os.environ.get("PV2_BN_FUSED_SLOTS", "296"))
 _UNPACK_BATCH = int(os.environ.get("PV2_UNPACK_BATCH", "4"))     # weight-gradient tensors per unpack launch on a companion stream
 _ZARENA_FLOATS = 1 << 20   # 4 MB: ~3.5 K conv channels x 32 floats (forward moments) + ~3.5 K x 4 sums x 32 floats (backward) = 0.56 M floats
 _COUNTERS = {}     # device -> zero-initialised ticket counters shared by every launch on that device (each launch leaves them zeroed)
@@ -245,6 +246,10 @@ class Engine:
         96 CTAs (each then walks several tiles through its ring) so that CTAs of the sibling chains are resident next to it
         instead of queueing for the same slots; a lone chain keeps the whole machine (pv2_conv_set_cta_budget)."""
         self.lib.pv2_conv_set_cta_budget(_PAR_CTA_BUDGET if n >= 4 else 0)
+        # the one-launch BatchNorm backward spins on a grid barrier: its CTAs must all be resident, so the n chains share _BN_FUSED_SLOTS
+        # CTA slots (half of the 4 x 148 the device holds at the kernel's 64 registers); below 32 CTAs per launch the two-launch form is used
+        share = _BN_FUSED_SLOTS // max(n, 1)
+        self.lib.pv2_bn_set_fused_grid(share if share >= 32 else 0)
 
     def _fan_out(self, n):
         self._set_width(n)
