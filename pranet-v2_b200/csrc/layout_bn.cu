@@ -1255,6 +1255,67 @@ up2_nhwc_bwd4_kernel(const Slabs g, float* __restrict__ din, int din_ld, int N, 
     pv2::pdl_done();
 }
 
+// Tiled form of the x2 backward: CTA = 8 x 8 input pixels x 16 channels of one image.  The window of output pixels the tile touches
+// (<= 22 x 22) is summed over the slabs ONCE while it is staged in shared memory -- every gradient element is read ~1.6x per slab
+// instead of the ~4.5x of the gather above (which is bound by exactly that L2 -> SM traffic, times the number of slabs) -- with
+// all of a thread's loads independent; the <= 5 x 5 taps of an input pixel then come from shared memory.
+constexpr int UT = 8, UC = 16, UWIN = 22;
+__global__ void __launch_bounds__(256)
+up2_nhwc_bwd4_tiled_kernel(const Slabs g, float* __restrict__ din, int din_ld, int H, int W, int C, float rh, float rw, int tiles_x, int tiles_y, int cgroups) {
+    pv2::pdl_prologue();
+    __shared__ __align__(16) float win[UWIN * UWIN * UC];
+    constexpr int NC = 7;
+    const int OH = 2 * H, OW = 2 * W;
+    int b = blockIdx.x;
+    const int cg = b % cgroups; b /= cgroups;
+    const int tx = b % tiles_x; b /= tiles_x;
+    const int ty = b % tiles_y;
+    const long long n = b / tiles_y;
+    const int iy0 = ty * UT, ix0 = tx * UT, c0 = cg * UC;
+    const int iy1 = min(iy0 + UT, H) - 1, ix1 = min(ix0 + UT, W) - 1;
+    auto lo_of = [](int i, float r) { return max(0, r > 0.f ? (int)floorf((i - 1) / r) : 0); };
+    auto hi_of = [](int i, float r, int on) { return min(on - 1, r > 0.f ? (int)ceilf((i + 1) / r) : on - 1); };
+    const int wy0 = lo_of(iy0, rh), wy1 = hi_of(iy1, rh, OH), wx0 = lo_of(ix0, rw), wx1 = hi_of(ix1, rw, OW);
+    const int wh = wy1 - wy0 + 1, ww = wx1 - wx0 + 1;
+    const bool staged = wh <= UWIN && ww <= UWIN;          // always, for a x2 up-sampling of >= 2 pixels
+    const int lanes = UC / 4;                                // float4 lanes per pixel
+    if (staged) {
+        for (int i = threadIdx.x; i < wh * ww * lanes; i += 256) {
+            const int l = i % lanes, px = i / lanes, wx = px % ww, wy = px / ww;
+            const int c = c0 + l * 4;
+            float4 v = f4_set(0.0f);
+            if (c < C) v = slab_sum4(g, (n * OH + wy0 + wy) * OW + wx0 + wx, c);
+            *reinterpret_cast<float4*>(win + (wy * UWIN + wx) * UC + l * 4) = v;
+        }
+    }
+    pv2::pdl_done();
+    __syncthreads();
+    const int l = threadIdx.x % lanes, pix = threadIdx.x / lanes;      // 64 pixels x 4 lanes
+    const int iy = iy0 + pix / UT, ix = ix0 + pix % UT, c = c0 + l * 4;
+    if (iy > iy1 || ix > ix1 || c >= C) return;
+    const int ylo = lo_of(iy, rh), yhi = hi_of(iy, rh, OH), xlo = lo_of(ix, rw), xhi = hi_of(ix, rw, OW);
+    float wyv[NC], wxv[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+        wyv[k] = (ylo + k <= yhi) ? ac_weight(ylo + k, iy, H, rh) : 0.0f;
+        wxv[k] = (xlo + k <= xhi) ? ac_weight(xlo + k, ix, W, rw) : 0.0f;
+    }
+    float4 acc = f4_set(0.0f);
+#pragma unroll
+    for (int a = 0; a < NC; ++a) {
+        if (wyv[a] == 0.0f) continue;
+#pragma unroll
+        for (int bb = 0; bb < NC; ++bb) {
+            if (wxv[bb] == 0.0f) continue;
+            const float w = wyv[a] * wxv[bb];
+            const float4 v = staged ? *reinterpret_cast<const float4*>(win + ((ylo + a - wy0) * UWIN + (xlo + bb - wx0)) * UC + l * 4)
+                                    : slab_sum4(g, (n * OH + ylo + a) * OW + xlo + bb, c);
+            acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        }
+    }
+    *reinterpret_cast<float4*>(din + ((n * H + iy) * W + ix) * din_ld + c) = acc;
+}
+
 inline int grid_for(long long total, int threads = 256) {
     long long b = (total + threads - 1) / threads;
     const long long cap = (long long)kNumSMs * 8;
@@ -1691,6 +1752,16 @@ extern "C" int pv2_up2_nhwc_bwd(const float* const* slabs, const int* lds, const
     const float rh = (float)(H - 1) / (float)(2 * H - 1), rw = (float)(W - 1) / (float)(2 * W - 1);
     bool vec = C % 4 == 0 && din_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(din) & 15u) == 0 && H >= 2 && W >= 2;
     for (int i = 0; vec && i < s.n; ++i) vec = s.ld[i] % 4 == 0 && s.off[i] % 4 == 0 && (reinterpret_cast<uintptr_t>(s.p[i]) & 15u) == 0;
+    static const bool tiled_off = [] { const char* e = getenv("PV2_UP2_TILED"); return e && e[0] == '0'; }();
+    if (vec && !tiled_off) {
+        const int tiles_x = (W + UT - 1) / UT, tiles_y = (H + UT - 1) / UT, cgroups = (C + UC - 1) / UC;
+        const long long blocks = (long long)N * tiles_y * tiles_x * cgroups;
+        if (blocks < (1LL << 31)) {
+            pv2::launch(up2_nhwc_bwd4_tiled_kernel, (int)blocks, 256, 0, (cudaStream_t)stream, s, din, din_ld, H, W, C, rh, rw, tiles_x, tiles_y, cgroups);
+            PV2_LAUNCH_CHECK("up2_nhwc_bwd4_tiled");
+            return 0;
+        }
+    }
     if (vec) {
         pv2::launch(up2_nhwc_bwd4_kernel, grid_for((long long)N * H * W * (C / 4)), 256, 0, (cudaStream_t)stream, s, din, din_ld, N, H, W, C, rh, rw);
         PV2_LAUNCH_CHECK("up2_nhwc_bwd4");

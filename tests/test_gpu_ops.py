@@ -405,3 +405,29 @@ def test_structure_loss_lowres_unsupported_geometry_takes_unfused_kernels():
     st = lib.pv2_structure_loss_lowres_fwd(pf, pb, ph, pw, pr, pr, md.data_ptr(), None, 1, 2, 64, 64, loss.data_ptr(), ws.data_ptr(), ws_bytes,
                                            torch.cuda.current_stream().cuda_stream)
     assert st != 0 and b"up-scaling by >= 4" in lib.pv2_last_error()
+
+
+@pytest.mark.parametrize("N,H,W,Cc,nslabs", [(2, 11, 11, 32, 1), (16, 22, 22, 64, 3), (2, 22, 18, 96, 2), (1, 2, 3, 4, 1), (3, 9, 17, 20, 2), (1, 44, 44, 32, 1)])
+def test_up2_nhwc_bwd_vs_aten(N, H, W, Cc, nslabs):
+    """pv2_up2_nhwc_bwd (backward of nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True), pranet.py:93, on NHWC rows with
+    the upstream gradient arriving as several slabs that are summed on load) against ATen's backward: the shared-memory tiled kernel
+    (ragged tiles, partial channel groups, slabs wider than C with a channel offset)."""
+    import ctypes
+    lib = P._lib.load()
+    g = torch.Generator().manual_seed(H * 100 + W)
+    slabs, ref_g = [], torch.zeros(N, Cc, 2 * H, 2 * W)
+    for i in range(nslabs):
+        ld, off = Cc + 8 * i, 4 * i                      # slab i holds the gradient in channels [off, off + C) of rows ld wide
+        t = torch.randn(N * 2 * H * 2 * W, ld, generator=g)
+        slabs.append((t.to(DEV), ld, off))
+        ref_g += t[:, off:off + Cc].reshape(N, 2 * H, 2 * W, Cc).permute(0, 3, 1, 2)
+    x = torch.zeros(N, Cc, H, W, requires_grad=True)
+    F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True).backward(ref_g)
+    din = torch.full((N * H * W, Cc), float("nan"), device=DEV)
+    pp, keep = P._lib.ptr_array([t for t, _, _ in slabs])
+    lds = (ctypes.c_int * nslabs)(*[ld for _, ld, _ in slabs])
+    offs = (ctypes.c_int * nslabs)(*[off for _, _, off in slabs])
+    P._lib.check(lib.pv2_up2_nhwc_bwd(pp, lds, offs, nslabs, din.data_ptr(), Cc, N, H, W, Cc, torch.cuda.current_stream().cuda_stream), "pv2_up2_nhwc_bwd")
+    got = din.cpu().reshape(N, H, W, Cc).permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    assert (got - x.grad).abs().max().item() <= 2e-5 * max(1.0, x.grad.abs().max().item())
