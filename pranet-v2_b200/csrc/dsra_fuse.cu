@@ -150,6 +150,53 @@ __global__ void ra_v1_fwd_scalar_kernel(const T* __restrict__ x, const float* __
     }
 }
 
+// Planes whose pixel count is not a multiple of 4 (11 x 11 = 121 at the deepest level): an image is ONE flat run of C * hw elements,
+// read and written as 16-byte vectors regardless of where the planes start.  The image's hw factors (1 - sigmoid(crop)) are computed
+// once per CTA into shared memory, extended by one vector's worth of wrap-around copies, so the factors of a vector that starts at
+// flat index i are a[(i mod hw) + k] -- one 32-bit remainder per VECTOR; the scalar form above pays a 64-bit division and an exp per
+// ELEMENT.  Needs C * hw to be a multiple of the vector length (16-byte aligned images) and hw + VEC floats of shared memory.
+constexpr int RA_FLAT_MAX_HW = 4096;
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+ra_v1_fwd_flat_kernel(const T* __restrict__ x, const float* __restrict__ crop, T* __restrict__ y, int C, int hw, int vec_per_image, int vec_per_cta) {
+    pv2::pdl_prologue();
+    extern __shared__ float fac[];          // [hw + VEC]
+    const int b = blockIdx.y;
+    for (int p = threadIdx.x; p < hw + VEC; p += 256) {
+        const int q = p < hw ? p : p - hw;
+        fac[p] = 1.0f - 1.0f / (1.0f + __expf(-crop[(size_t)b * hw + q]));
+    }
+    __syncthreads();
+    const size_t img = (size_t)b * C * hw;
+    const int v0 = blockIdx.x * vec_per_cta, v1 = min(vec_per_image, v0 + vec_per_cta);
+    for (int v = v0 + threadIdx.x; v < v1; v += 2 * 256) {
+        const int vb = v + 256;
+        const bool two = vb < v1;
+        const size_t e0 = img + (size_t)v * VEC, e1 = img + (size_t)(two ? vb : v) * VEC;
+        const int p0 = (int)(((unsigned)v * (unsigned)VEC) % (unsigned)hw), p1 = (int)(((unsigned)(two ? vb : v) * (unsigned)VEC) % (unsigned)hw);
+        if (VEC == 4) {
+            const float4 a = load4<T>(x + e0), c = load4<T>(x + e1);
+            store4<T>(y + e0, make_float4(a.x * fac[p0], a.y * fac[p0 + 1], a.z * fac[p0 + 2], a.w * fac[p0 + 3]));
+            if (two) store4<T>(y + e1, make_float4(c.x * fac[p1], c.y * fac[p1 + 1], c.z * fac[p1 + 2], c.w * fac[p1 + 3]));
+        } else {        // 8 bf16 per 16 bytes
+            const uint4 ua = __ldg(reinterpret_cast<const uint4*>(x + e0)), uc = __ldg(reinterpret_cast<const uint4*>(x + e1));
+            auto scale8 = [&](const uint4& u, int p) {
+                const unsigned w[4] = {u.x, u.y, u.z, u.w};
+                unsigned o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float lo = __uint_as_float(w[j] << 16) * fac[p + 2 * j], hi = __uint_as_float(w[j] & 0xffff0000u) * fac[p + 2 * j + 1];
+                    const __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+                    o[j] = *reinterpret_cast<const unsigned*>(&r);
+                }
+                return make_uint4(o[0], o[1], o[2], o[3]);
+            };
+            *reinterpret_cast<uint4*>(y + e0) = scale8(ua, p0);
+            if (two) *reinterpret_cast<uint4*>(y + e1) = scale8(uc, p1);
+        }
+    }
+}
+
 // block = 32 pixels x 8 channel groups; grid = (ceil(hw/32), B)   (scalar form: hw % 4 != 0)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -267,11 +314,29 @@ extern "C" int pv2_ra_v1_scale_fwd(const void* x, const float* crop, void* y, in
     cudaStream_t st = (cudaStream_t)stream;
     const size_t total = (size_t)B * C * hw;
     const int threads = 256;
-    if ((hw & 3) == 0 && B <= 65535 && (C + 4 * RA_CPT - 1) / (4 * RA_CPT) <= 65535) {
+    // the flat kernel serves the geometries the plane-wise vector kernel cannot (hw % 4 != 0): 15.2 -> 4.4 us at 16 x 2048 x 11^2 bf16
+    // (16 % -> 55 % of the HBM peak).  For planes that ARE 16-byte multiples it was measured slower than the plane-wise kernel
+    // (PV2_RA_FLAT=2: 23.2 us against 17.9 at 512 x 44^2, 164 against 126 us at 64 x 1024 x 44^2), so it is not used there
+    const bool flat_ok = hw <= RA_FLAT_MAX_HW && B <= 65535 && ((size_t)C * hw) % (dtype == PV2_F32 ? 4 : 8) == 0 && (size_t)C * hw < (1u << 31) &&
+                         (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0;
+    const int flat_mode = pv2::tune_int("PV2_RA_FLAT", 1);      // 0 never, 1 only when hw % 4 != 0, 2 whenever possible
+    if ((hw & 3) == 0 && B <= 65535 && (C + 4 * RA_CPT - 1) / (4 * RA_CPT) <= 65535 && !(flat_ok && flat_mode >= 2)) {
         const int vpp = hw >> 2;
         dim3 grid((vpp + 63) / 64, B, (C + 4 * RA_CPT - 1) / (4 * RA_CPT));
         if (dtype == PV2_F32) pv2::launch(ra_v1_fwd_kernel<float>, grid, threads, 0, st, (const float*)x, crop, (float*)y, C, hw, vpp);
         else pv2::launch(ra_v1_fwd_kernel<__nv_bfloat16>, grid, threads, 0, st, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, vpp);
+    } else if (flat_ok && flat_mode >= 1) {
+        const int VEC = dtype == PV2_F32 ? 4 : 8;
+        const int vpi = (int)((size_t)C * hw / VEC);
+        // ~4 CTAs per SM over the batch, at least two vectors per thread
+        int per_img = (4 * kNumSMs + B - 1) / B;
+        int vpc = (vpi + per_img - 1) / per_img;
+        if (vpc < 512) vpc = 512;
+        vpc = (vpc + 511) / 512 * 512;
+        dim3 grid((vpi + vpc - 1) / vpc, B);
+        const size_t smem = (size_t)(hw + VEC) * sizeof(float);
+        if (dtype == PV2_F32) pv2::launch(ra_v1_fwd_flat_kernel<float, 4>, grid, threads, smem, st, (const float*)x, crop, (float*)y, C, hw, vpi, vpc);
+        else pv2::launch(ra_v1_fwd_flat_kernel<__nv_bfloat16, 8>, grid, threads, smem, st, (const __nv_bfloat16*)x, crop, (__nv_bfloat16*)y, C, hw, vpi, vpc);
     } else {
         int blocks = (int)((total + threads - 1) / threads);
         if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

@@ -146,7 +146,7 @@ def test_dsra_fuse(B, C, h, scale, softmax):
         assert d[1].grad.abs().max().item() == 0.0 and d[2].grad.abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("B,C,h", [(2, 2048, 11), (2, 1024, 22), (1, 512, 44), (1, 7, 5)])
+@pytest.mark.parametrize("B,C,h", [(2, 2048, 11), (2, 1024, 22), (1, 512, 44), (1, 7, 5), (3, 12, 11), (2, 16, 7), (16, 2048, 11)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_ra_v1_scale(B, C, h, dtype):
     g = torch.Generator().manual_seed(4)
