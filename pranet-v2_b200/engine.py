@@ -41,6 +41,7 @@ _BNDEFER_DT = np.dtype([("part", "u8"), ("count", "f4"), ("ldc", "i4"), ("c_off"
 assert _PACK_DT.itemsize == 88 and _UNPACK_DT.itemsize == 64 and _BNSEG_DT.itemsize == 56 and _BNFUSE_DT.itemsize == 504
 assert _BNDEFER_DT.itemsize == 88
 _PAR_CTA_BUDGET = int(os.environ.get("PV2_PAR_CTA_BUDGET", "96"))
+_PAR_CTA_BUDGET_NARROW = int(os.environ.get("PV2_PAR_CTA_BUDGET_NARROW", "0"))    # sections of 2-3 chains
 _BN_ACC_STRIDE, _SUM_STRIDE = 16, 32   # == PV2_BN_ACC_STRIDE (doubles), PV2_SUM_STRIDE (floats) of include/pv2.h
 # stream priority of the dependent chains (branch streams; -1 = above the default 0 the weight-gradient companions run at, so a chain's
 # next kernel is placed before queued wgrad / unpack CTAs; captured graphs keep it as the kernel nodes' priority).  Head step at
@@ -245,7 +246,7 @@ class Engine:
         """Tell the conv launcher how many chains run side by side: with four or more, every persistent conv launch is capped at
         96 CTAs (each then walks several tiles through its ring) so that CTAs of the sibling chains are resident next to it
         instead of queueing for the same slots; a lone chain keeps the whole machine (pv2_conv_set_cta_budget)."""
-        self.lib.pv2_conv_set_cta_budget(_PAR_CTA_BUDGET if n >= 4 else 0)
+        self.lib.pv2_conv_set_cta_budget(_PAR_CTA_BUDGET if n >= 4 else (_PAR_CTA_BUDGET_NARROW if n >= 2 else 0))
         # the one-launch BatchNorm backward spins on a grid barrier: its CTAs must all be resident, so the n chains share _BN_FUSED_SLOTS
         # CTA slots (half of the 4 x 148 the device holds at the kernel's 64 registers); below 32 CTAs per launch the two-launch form is used
         share = _BN_FUSED_SLOTS // max(n, 1)

@@ -1,5 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_models.py -x -q -m gpu --timeout 120 -k "ra_v1 or v1" 2>&1 | grep -E "^E   |^tests/|passed|failed|^FAILED|Timeout" | head -12 | cut -c1-300
-for m in 2 1; do echo "flat mode $m"; PV2_RA_FLAT=$m timeout 300 python bench_head.py --batches 16 --sizes 352 --iters 40 --kernels --kernels-at 16x352 2>&1 | grep -E "ra_v1" | cut -c1-50,60-150; done
-echo "64x704"; timeout 300 python bench_head.py --batches 64 --sizes 704 --iters 5 --kernels --kernels-at 64x704 2>&1 | grep -E "ra_v1" | cut -c1-50,60-150
+for b in 48 24 32 40; do
+  echo "budget $b"; PV2_PAR_CTA_BUDGET=$b timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 60 2>&1 | grep -E "ms_graph" | cut -c1-100
+done
+for nb in 148 96 74; do
+  echo "budget 48 narrow $nb"; PV2_PAR_CTA_BUDGET=48 PV2_PAR_CTA_BUDGET_NARROW=$nb timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 60 2>&1 | grep -E "ms_graph" | cut -c1-100
+done
+echo "budget 48, 64x704 and 1x352, 64x352"; PV2_PAR_CTA_BUDGET=48 timeout 200 python bench_head.py --batches 1,64 --sizes 352,704 --iters 10 2>&1 | grep -E "ms_graph" | cut -c1-100
+echo "budget 96, 64x704 and 1x352, 64x352"; PV2_PAR_CTA_BUDGET=96 timeout 200 python bench_head.py --batches 1,64 --sizes 352,704 --iters 10 2>&1 | grep -E "ms_graph" | cut -c1-100
