@@ -1,10 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for b in 48 24 32 40; do
-  echo "budget $b"; PV2_PAR_CTA_BUDGET=$b timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 60 2>&1 | grep -E "ms_graph" | cut -c1-100
+for kv in PV2_STREAMS=0 PV2_PDL=0 PV2_CONV_V1=1 PV2_WGRAD_STREAMS=0 PV2_BN_BWD_LEAN=0 PV2_BN_BWD_FUSED=1 PV2_BIL_BWD2=0 PV2_UP2_TILED=0 PV2_CONV_NARROW=0 PV2_CHAIN_PRIORITY=0; do
+  echo "== $kv"; env $kv timeout 600 python -m pytest tests/test_gpu_bench_config.py tests/test_gpu_models.py -x -q -m gpu --timeout 200 2>&1 | grep -E "^E   |passed|failed|^FAILED|Timeout" | head -5 | cut -c1-250
 done
-for nb in 148 96 74; do
-  echo "budget 48 narrow $nb"; PV2_PAR_CTA_BUDGET=48 PV2_PAR_CTA_BUDGET_NARROW=$nb timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 60 2>&1 | grep -E "ms_graph" | cut -c1-100
-done
-echo "budget 48, 64x704 and 1x352, 64x352"; PV2_PAR_CTA_BUDGET=48 timeout 200 python bench_head.py --batches 1,64 --sizes 352,704 --iters 10 2>&1 | grep -E "ms_graph" | cut -c1-100
-echo "budget 96, 64x704 and 1x352, 64x352"; PV2_PAR_CTA_BUDGET=96 timeout 200 python bench_head.py --batches 1,64 --sizes 352,704 --iters 10 2>&1 | grep -E "ms_graph" | cut -c1-100
