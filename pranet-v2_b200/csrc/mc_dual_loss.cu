@@ -12,7 +12,9 @@
 //   * the inverted one-hot target is derived from the label on the fly (no mask tensor, no H2D copy);
 //   * per subset the 2 + 2C partial sums are reduced warp-shuffle -> per-warp shared slots -> one partial row per CTA;
 //     the fold kernel adds the CTA rows in a fixed order (bit-reproducible) and leaves the Dice sums for the backward.
-// Bound: MUFU (C exp + C softplus per subset and pixel), not HBM: 15*(2C) ex2 + 15*C lg2 per pixel.
+// Bound: instruction issue (15 subsets x C classes of softmax / softplus arithmetic per pixel), not HBM.  The per-subset sums -- 2 + 2C
+// values per pixel -- are reduced over the warp with ONE multi-value reduction (multi_warp_sum: 21 shuffles for 20 values instead of
+// 100); with one 5-step warp sum per value the forward spent half of its ~9 400 instructions per pixel there (0.42 -> 0.29 ms).
 #include "pv2_common.cuh"
 
 namespace pv2 {
@@ -34,6 +36,57 @@ __device__ __forceinline__ int subset_of(int k, int mode) {   // k = 1 .. nsub
     return mode == 0 ? (k ^ (k >> 1)) : (1 << (k - 1));         // Gray code over all non-empty subsets | singletons
 }
 
+// Warp reduction of NV values per lane at once: at every halving step a lane keeps one half of its values, sends the other half to
+// its partner and adds what it receives, so NV values cost NV-ish shuffles in total (10 + 5 + 3 + 2 + 1 = 21 for NV = 20) instead of
+// 5 each (100), and the totals end up spread over the lanes: lane L holds the total of value multi_slot(L) (or nothing).  Fixed
+// order, deterministic.
+template <int N>
+__device__ __forceinline__ void multi_step(float (&v)[N], int off, bool up) {
+    constexpr int H = (N + 1) / 2;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float lo = v[j], hi = (j + H < N) ? v[j + H] : 0.0f;
+        const float recv = __shfl_xor_sync(0xffffffffu, up ? lo : hi, off);
+        v[j] = (up ? hi : lo) + recv;
+    }
+}
+template <int NV>
+__device__ __forceinline__ float multi_warp_sum(float (&v)[NV], int lane) {
+    static_assert(NV <= 32, "at most one value per lane");
+    constexpr int N1 = (NV + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2;
+    multi_step<NV>(v, 16, (lane & 16) != 0);
+    float a[N1];
+#pragma unroll
+    for (int j = 0; j < N1; ++j) a[j] = v[j];
+    multi_step<N1>(a, 8, (lane & 8) != 0);
+    float b[N2];
+#pragma unroll
+    for (int j = 0; j < N2; ++j) b[j] = a[j];
+    multi_step<N2>(b, 4, (lane & 4) != 0);
+    float c[N3];
+#pragma unroll
+    for (int j = 0; j < N3; ++j) c[j] = b[j];
+    multi_step<N3>(c, 2, (lane & 2) != 0);
+    float d[N4];
+#pragma unroll
+    for (int j = 0; j < N4; ++j) d[j] = c[j];
+    multi_step<N4>(d, 1, (lane & 1) != 0);
+    return d[0];
+}
+// which value a lane ends up with (-1: a padding slot).  Every lane halves the same N per step; `real` counts how many of the values a
+// lane kept are real ones (the upper half of an odd N is one short and padded with a zero)
+template <int NV>
+__device__ __forceinline__ int multi_slot(int lane) {
+    int N = NV, real = NV, idx = 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const int H = (N + 1) / 2;
+        if (lane & off) { idx += H; real = real > H ? real - H : 0; } else { real = real < H ? real : H; }
+        N = H;
+    }
+    return real >= 1 ? idx : -1;
+}
+
 // row layout of the partial / total sums for subset index j (0-based): [ce, bce, I_0..I_{C-1}, Z_0..Z_{C-1}]
 template <int C> struct Row { static constexpr int N = 2 + 2 * C; };
 
@@ -51,6 +104,7 @@ mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mo
     for (int i = threadIdx.x; i < nw * width; i += MC_THREADS) sacc[i] = 0.0f;
     __syncthreads();
     float* my = sacc + warp * width;
+    const int slot = multi_slot<R>(lane);
     for (long long pix0 = (long long)blockIdx.x * MC_THREADS; pix0 < npix; pix0 += (long long)gridDim.x * MC_THREADS) {
         const long long pix = pix0 + threadIdx.x;
         const bool ok = pix < npix;
@@ -65,11 +119,11 @@ mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mo
                 f[i][c] = (ok && i < n) ? __ldg(p.fg[i] + off) : 0.0f;
                 g[i][c] = (ok && i < n) ? __ldg(p.bg[i] + off) : 0.0f;
             }
-        // class counts (sum t_c^2 = sum t_c), once per pixel
+        // class counts (sum t_c^2 = sum t_c), once per pixel: one ballot per class
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float v = warp_sum((ok && y == c) ? 1.0f : 0.0f);
-            if (lane == 0) my[nsub * R + c] += v;
+            const unsigned m = __ballot_sync(0xffffffffu, ok && y == c);
+            if (lane == 0) my[nsub * R + c] += (float)__popc(m);
         }
         float so[C], sb[C];
 #pragma unroll
@@ -93,7 +147,8 @@ mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mo
 #pragma unroll
             for (int c = 0; c < C; ++c) { e[c] = __expf(so[c] - mx); den += e[c]; if (c == y) sy = so[c]; }
             const float inv = 1.0f / den;
-            float ce = ok ? (__logf(den) + mx - sy) : 0.0f, bce = 0.0f;
+            float vals[R];                                   // [ce, bce, I_0.., Z_0..] of this pixel
+            float bce = 0.0f;
             float* row = my + (k - 1) * R;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -101,11 +156,12 @@ mc_loss_fwd_kernel(McPtrs p, const long long* __restrict__ labels, int n, int mo
                 const float t = (c == y) ? 1.0f : 0.0f;
                 const float x = sb[c];
                 bce += ok ? (fmaxf(x, 0.0f) - x * (1.0f - t) + __logf(1.0f + __expf(-fabsf(x)))) : 0.0f;
-                const float I = warp_sum(pc * t), Z = warp_sum(pc * pc);
-                if (lane == 0) { row[2 + c] += I; row[2 + C + c] += Z; }
+                vals[2 + c] = pc * t; vals[2 + C + c] = pc * pc;
             }
-            ce = warp_sum(ce); bce = warp_sum(bce);
-            if (lane == 0) { row[0] += ce; row[1] += bce; }
+            vals[0] = ok ? (__logf(den) + mx - sy) : 0.0f;
+            vals[1] = bce;
+            const float tot = multi_warp_sum<R>(vals, lane);      // lane `slot` holds the warp total of value `slot`
+            if (slot >= 0) row[slot] += tot;
         }
     }
     __syncthreads();
@@ -185,12 +241,22 @@ mc_loss_bwd_kernel(McPtrs p, const long long* __restrict__ labels, const float* 
     pv2::pdl_prologue();
     constexpr int R = Row<C>::N;
     const int nsub = mode == 0 ? (1 << n) - 1 : n;
+    const float gl = *grad_loss;
+    const float w_ce = gl * lc_ce / (float)npix, w_bce = gl * lc_bce / ((float)npix * (float)C), w_dice = gl * lc_dice / (float)C;
+    // Dice coefficients of every (subset, class), once per CTA: d/dp_c of -(num/D) = -(2 t D - 2 num p) / D^2 = -(cA t - cB p)
+    __shared__ float cA[MAXS * C], cB[MAXS * C];
+    for (int i = threadIdx.x; i < nsub * C; i += MC_THREADS) {
+        const int k = i / C, c = i - k * C;
+        const float* row = totals + k * R;
+        const float num = 2.0f * row[2 + c] + DICE_EPS, D = row[2 + C + c] + totals[nsub * R + c] + DICE_EPS;
+        cA[i] = w_dice * 2.0f / D;
+        cB[i] = w_dice * 2.0f * num / (D * D);
+    }
+    __syncthreads();
     const long long pix = (long long)blockIdx.x * MC_THREADS + threadIdx.x;
     if (pix >= npix) return;
     const long long b = pix / HW, hw = pix - b * HW;
     const int y = (int)labels[pix];
-    const float gl = *grad_loss;
-    const float w_ce = gl * lc_ce / (float)npix, w_bce = gl * lc_bce / ((float)npix * (float)C), w_dice = gl * lc_dice / (float)C;
     // ---- foreground: CE + Dice through the softmax ----
     {
         float f[MAXN][C], d[MAXN][C], so[C];
@@ -218,15 +284,13 @@ mc_loss_bwd_kernel(McPtrs p, const long long* __restrict__ labels, const float* 
 #pragma unroll
             for (int c = 0; c < C; ++c) { pr[c] = __expf(so[c] - mx); den += pr[c]; }
             const float inv = 1.0f / den;
-            const float* row = totals + (k - 1) * R;
+            const float* ka = cA + (k - 1) * C;
+            const float* kb = cB + (k - 1) * C;
             float dp[C], dot = 0.0f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 pr[c] *= inv;
-                const float t = (c == y) ? 1.0f : 0.0f;
-                const float num = 2.0f * row[2 + c] + DICE_EPS, D = row[2 + C + c] + totals[nsub * R + c] + DICE_EPS;
-                // d/dp_c of -(num/D): -(2 t D - num * 2 p) / D^2
-                dp[c] = -w_dice * (2.0f * t * D - num * 2.0f * pr[c]) / (D * D);
+                dp[c] = kb[c] * pr[c] - ((c == y) ? ka[c] : 0.0f);
                 dot += pr[c] * dp[c];
             }
             float gs[C];
