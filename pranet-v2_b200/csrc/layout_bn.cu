@@ -731,6 +731,41 @@ act_apply4_kernel(const ApplyArgs a0, const Defer2 df) {
     pv2::pdl_done();
 }
 
+// Lean form of the common case -- one source, one slab, no multiplier, NHWC out: thread = (channel quad, row lane) like the lean
+// BatchNorm-backward kernels, so the quad's scale / shift live in registers and the loop has no division (the general kernel above
+// divides by C/4 for every 16 bytes and re-reads the affine from shared memory); 4 rows in flight per thread.
+template <int KIND>
+__global__ void __launch_bounds__(256)
+act_apply4_lean_kernel(const ApplyArgs a0, const Defer2 df, int RP) {
+    pv2::pdl_prologue();
+    PV2_APPLY_DEFER_PROLOGUE(a0, df, a)
+    const int C4 = a.C >> 2;
+    const int quad = threadIdx.x % C4, rp = threadIdx.x / C4;
+    if (rp < RP) {
+        const int c = quad << 2;
+        const float4 sc = f4_ldp(a.s1 + c), sh = f4_ldp(a.b1 + c);
+        const float* src = a.y1 + a.off1 + c;
+        const long long step = (long long)gridDim.x * RP;
+        for (long long r = (long long)blockIdx.x * RP + rp; r < a.M; r += 4 * step) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long ru = r + u * step;
+                v[u] = f4_ld(src + (ru < a.M ? ru : r) * a.ld1);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long ru = r + u * step;
+                if (ru >= a.M) break;
+                float4 o = f4_fma(v[u], sc, sh);
+                if (a.relu) o = make_float4(fmaxf(o.x, 0.0f), fmaxf(o.y, 0.0f), fmaxf(o.z, 0.0f), fmaxf(o.w, 0.0f));
+                store_op4<KIND>(a.out, a.out_plane, a.out_planes, ru * a.out_ld + a.out_off + c, o);
+            }
+        }
+    }
+    pv2::pdl_done();
+}
+
 struct Da4 { float4 da1, da2, yh1, yh2, dm; };
 
 template <int KIND>
@@ -1589,6 +1624,18 @@ extern "C" int pv2_act_apply(const float* y1, int ld1, int off1, int ns1, long l
     auto grid_of = [&](long long work) { return grid_for(work); };
     (void)deferred;
     if (!out_nchw && apply_vec_ok(a) && out_ld % 4 == 0 && out_off % 4 == 0 && al16(out)) {
+        static const bool lean_off = [] { const char* e = getenv("PV2_ACT_LEAN"); return e && e[0] == '0'; }();
+        if (!lean_off && a.combine == 0 && a.mult == nullptr && a.ns1 == 1 && C / 4 <= 256) {
+            const int RP = 256 / (C / 4);
+            long long nb = (M + 4LL * RP - 1) / (4LL * RP);          // >= 4 rows per thread when there are that many
+            const long long cap = (long long)kNumSMs * 8;
+            if (nb > cap) nb = cap;
+            if (nb < 1) nb = 1;
+            if (kind == PV2_BF16) pv2::launch(act_apply4_lean_kernel<0>, (int)nb, 256, 0, (cudaStream_t)stream, a, df, RP);
+            else pv2::launch(act_apply4_lean_kernel<1>, (int)nb, 256, 0, (cudaStream_t)stream, a, df, RP);
+            PV2_LAUNCH_CHECK("act_apply4_lean");
+            return 0;
+        }
         if (kind == PV2_BF16) pv2::launch(act_apply4_kernel<0>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
         else pv2::launch(act_apply4_kernel<1>, grid_of(total / 4), 256, 0, (cudaStream_t)stream, a, df);
         PV2_LAUNCH_CHECK("act_apply4");

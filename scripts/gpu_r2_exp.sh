@@ -1,10 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_multiclass.py -x -q -m gpu --timeout 200 -k "mc or multiclass or emcad or merit or mist or dual" 2>&1 | grep -E "^E   |passed|failed|^FAILED|Timeout" | head -8 | cut -c1-250
-timeout 300 python - <<'PY'
-import torch, sys
-sys.path.insert(0, '.')
-import bench, pranet_v2_b200 as P
-r = bench.roofline_mc_loss(P, torch.device('cuda:0'))
-print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items() if k in ('achieved', 'avg_ms')}, {k: round(v, 3) for k, v in r['fwd'].items() if isinstance(v, float)})
-PY
+timeout 600 python -m pytest tests/ -x -q -m gpu --timeout 200 2>&1 | grep -E "^E   |passed|failed|^FAILED|Timeout" | head -8 | cut -c1-250
+for f in 1 0 1 0; do
+  echo "act lean $f"; PV2_ACT_LEAN=$f timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 60 2>&1 | grep -E "ms_graph" | cut -c1-100
+done
+PV2_TRACE=gpurun_out/r2_timeline_a.txt timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 20 > /dev/null 2>&1; grep -E "act_apply|# B" gpurun_out/r2_timeline_a.txt | cut -c1-100; rm -f gpurun_out/r2_timeline_a.txt.chrome.json
