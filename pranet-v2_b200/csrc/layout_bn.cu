@@ -927,38 +927,40 @@ template <int KIND>
 __global__ void __launch_bounds__(256)
 bn_bwd_dx4_lean_kernel(const LeanBwd a) {
     pv2::pdl_prologue();
-    __shared__ __align__(16) float s_sums[2 * 256];
-    for (int i = threadIdx.x; i < 2 * a.C; i += 256) s_sums[i] = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * i);
-    __syncthreads();
+    // thread = (channel quad, row lane), like the reduce pass: the quad's affine, statistics and finished sums live in registers and
+    // the row loop has no division (the element-indexed form divided by C/4 for every 16 bytes); 4 rows in flight per thread
+    const int C4 = a.C >> 2, tid = threadIdx.x;
+    const int quad = tid % C4, rp = tid / C4, c = quad << 2;
     if (blockIdx.x == 0) {
-        for (int i = threadIdx.x; i < a.C; i += 256) {
-            if (a.dbeta) a.dbeta[i] = s_sums[i];
-            if (a.dgamma) a.dgamma[i] = s_sums[a.C + i];
+        for (int i = tid; i < a.C; i += 256) {
+            if (a.dbeta) a.dbeta[i] = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * i);
+            if (a.dgamma) a.dgamma[i] = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (a.C + i));
         }
     }
-    const unsigned C4 = (unsigned)a.C >> 2;
-    const unsigned total = (unsigned)a.M * C4;
-    const float invn = 1.0f / (float)a.M;
-    const unsigned stride = gridDim.x * 256u;
-    for (unsigned e = blockIdx.x * 256u + threadIdx.x; e < total; e += 2u * stride) {
-        float4 da[2], yh[2];
-        unsigned rr[2];
-        int cc[2];
+    if (rp < a.RP) {
+        const float invn = 1.0f / (float)a.M;
+        const float4 sc = f4_ld(a.scale + c), shf = f4_ld(a.shift + c), mu = f4_ld(a.mean + c), iv = f4_ld(a.inv + c);
+        float4 k1, k2;
+        k1.x = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (c + 0)) * invn; k1.y = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (c + 1)) * invn;
+        k1.z = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (c + 2)) * invn; k1.w = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (c + 3)) * invn;
+        k2.x = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (a.C + c + 0)) * invn; k2.y = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (a.C + c + 1)) * invn;
+        k2.z = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (a.C + c + 2)) * invn; k2.w = __ldcg(a.sums + (size_t)PV2_SUM_STRIDE * (a.C + c + 3)) * invn;
+        const long long step = (long long)gridDim.x * a.RP;
+        for (long long r = (long long)blockIdx.x * a.RP + rp; r < a.M; r += 4 * step) {
+            float4 da[4], yh[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const unsigned eu = e + (unsigned)u * stride;
-            const unsigned ev = eu < total ? eu : e;
-            rr[u] = ev / C4; cc[u] = (int)(ev - rr[u] * C4) << 2;
-            lean_da(a, rr[u], cc[u], f4_ld(a.scale + cc[u]), f4_ld(a.shift + cc[u]), f4_ld(a.mean + cc[u]), f4_ld(a.inv + cc[u]), &da[u], &yh[u]);
-        }
+            for (int u = 0; u < 4; ++u) {
+                const long long ru = r + u * step;
+                lean_da(a, ru < a.M ? ru : r, c, sc, shf, mu, iv, &da[u], &yh[u]);
+            }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (e + (unsigned)u * stride >= total) break;
-            const int c = cc[u];
-            const float4 s1 = f4_ld(a.scale + c), S1 = f4_ldp(s_sums + c), S2 = f4_ldp(s_sums + a.C + c);
-            const float4 d1 = make_float4(s1.x * (da[u].x - S1.x * invn - yh[u].x * S2.x * invn), s1.y * (da[u].y - S1.y * invn - yh[u].y * S2.y * invn),
-                                          s1.z * (da[u].z - S1.z * invn - yh[u].z * S2.z * invn), s1.w * (da[u].w - S1.w * invn - yh[u].w * S2.w * invn));
-            store_op4<KIND>(a.dy, a.dy_plane, a.dy_planes, (long long)rr[u] * a.dy_ld + c, d1);
+            for (int u = 0; u < 4; ++u) {
+                const long long ru = r + u * step;
+                if (ru >= a.M) break;
+                const float4 d1 = make_float4(sc.x * (da[u].x - k1.x - yh[u].x * k2.x), sc.y * (da[u].y - k1.y - yh[u].y * k2.y),
+                                              sc.z * (da[u].z - k1.z - yh[u].z * k2.z), sc.w * (da[u].w - k1.w - yh[u].w * k2.w));
+                store_op4<KIND>(a.dy, a.dy_plane, a.dy_planes, ru * a.dy_ld + c, d1);
+            }
         }
     }
     pv2::pdl_done();
@@ -1733,7 +1735,10 @@ extern "C" int pv2_bn_act_bwd(const float* y1, int ld1, int off1, int ns1, long 
                     pv2::launch(bn_bwd_reduce4_lean_kernel, (int)nb, 256, 0, st4, a);
                     PV2_LAUNCH_CHECK("bn_bwd_reduce4_lean");
                     const long long total4l = M * C4;
-                    if (kind == PV2_BF16) pv2::launch(bn_bwd_dx4_lean_kernel<0>, grid_for(total4l), 256, 0, st4, a); else pv2::launch(bn_bwd_dx4_lean_kernel<1>, grid_for(total4l), 256, 0, st4, a);
+                    (void)total4l;
+                    long long nd = (M + 4LL * a.RP - 1) / (4LL * a.RP);       // >= 4 rows per thread when there are that many
+                    if (nd > 8LL * kNumSMs) nd = 8LL * kNumSMs;
+                    if (kind == PV2_BF16) pv2::launch(bn_bwd_dx4_lean_kernel<0>, (int)nd, 256, 0, st4, a); else pv2::launch(bn_bwd_dx4_lean_kernel<1>, (int)nd, 256, 0, st4, a);
                     PV2_LAUNCH_CHECK("bn_bwd_dx4_lean");
                     return 0;
                 }

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/ -x -q -m gpu --timeout 200 2>&1 | grep -E "^E   |passed|failed|^FAILED|Timeout" | head -8 | cut -c1-250
-for f in 1 0 1 0; do
-  echo "act lean $f"; PV2_ACT_LEAN=$f timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 60 2>&1 | grep -E "ms_graph" | cut -c1-100
+for f in 1 2; do
+  timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 60 2>&1 | grep -E "ms_graph" | cut -c1-100
 done
-PV2_TRACE=gpurun_out/r2_timeline_a.txt timeout 120 python bench_head.py --batches 16 --sizes 352 --iters 20 > /dev/null 2>&1; grep -E "act_apply|# B" gpurun_out/r2_timeline_a.txt | cut -c1-100; rm -f gpurun_out/r2_timeline_a.txt.chrome.json
