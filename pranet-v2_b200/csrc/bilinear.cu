@@ -488,8 +488,8 @@ static int fwd_band(int planes, int nmaps, int oh) {
 
 static int launch_fwd(const MultiMaps& mm, int nmaps, int planes, int oh, int ow, int align_corners, int dtype, size_t smem, int band, cudaStream_t st) {
     dim3 grid((oh + band - 1) / band, planes, nmaps);
-    if (dtype == PV2_F32) pv2::launch(bilinear_fwd_kernel<float>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners, band);
-    else pv2::launch(bilinear_fwd_kernel<__nv_bfloat16>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners, band);
+    if (dtype == PV2_F32) pv2::launch_streaming(bilinear_fwd_kernel<float>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners, band);
+    else pv2::launch_streaming(bilinear_fwd_kernel<__nv_bfloat16>, grid, FWD_THREADS, smem, st, mm, oh, ow, align_corners, band);
     PV2_LAUNCH_CHECK("bilinear_fwd");
     return 0;
 }
@@ -536,11 +536,11 @@ static int launch_bwd2(const MultiMaps& mm, int nmaps, int planes, int oh, int o
     if (dtype == PV2_F32) {
         static bool once = [] { return cudaFuncSetAttribute(bilinear_bwd2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM) == cudaSuccess; }();
         (void)once;
-        pv2::launch(bilinear_bwd2_kernel<float>, grid, threads, smem, st, mm, oh, ow, G, hint);
+        pv2::launch_streaming(bilinear_bwd2_kernel<float>, grid, threads, smem, st, mm, oh, ow, G, hint);
     } else {
         static bool once = [] { return cudaFuncSetAttribute(bilinear_bwd2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD2_SMEM) == cudaSuccess; }();
         (void)once;
-        pv2::launch(bilinear_bwd2_kernel<__nv_bfloat16>, grid, threads, smem, st, mm, oh, ow, G, hint);
+        pv2::launch_streaming(bilinear_bwd2_kernel<__nv_bfloat16>, grid, threads, smem, st, mm, oh, ow, G, hint);
     }
     PV2_LAUNCH_CHECK("bilinear_bwd2");
     return 0;

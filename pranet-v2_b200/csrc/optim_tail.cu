@@ -111,7 +111,7 @@ extern "C" int pv2_adam_clamp_flat(float* params, const float* grads, float* exp
     }();
     const long long cap = (long long)kNumSMs * per_sm;
     const int grid = (int)(want < cap ? want : cap);
-    pv2::launch(adam_clamp_flat_kernel, dim3(grid), dim3(OT_THREADS), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, step, ticket, a);
+    pv2::launch_streaming(adam_clamp_flat_kernel, dim3(grid), dim3(OT_THREADS), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, step, ticket, a);
     PV2_LAUNCH_CHECK("adam_clamp_flat");
     return 0;
 }

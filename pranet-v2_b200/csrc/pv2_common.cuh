@@ -57,11 +57,11 @@ bool pdl_enabled();
 // integer tuning knob from the environment, read at every call (A/B measurements inside one process); `def` when unset
 int tune_int(const char* name, int def);
 
-void prefer_max_shared(const void* kernel);
+void prefer_max_shared(const void* kernel, bool streaming = false);
 
-template <typename... KArgs, typename... Args>
+template <bool STREAMING = false, typename... KArgs, typename... Args>
 inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    prefer_max_shared(reinterpret_cast<const void*>(kernel));
+    prefer_max_shared(reinterpret_cast<const void*>(kernel), STREAMING);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -70,6 +70,11 @@ inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface through PV2_LAUNCH_CHECK
+}
+// pure HBM streams with little or no shared memory (optimizer tail, loss, final upsamples): they keep the driver's default L1 split
+template <typename... KArgs, typename... Args>
+inline void launch_streaming(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    launch<true>(kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

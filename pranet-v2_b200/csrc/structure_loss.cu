@@ -837,14 +837,14 @@ lowres_grad_fold_kernel(const __grid_constant__ PtrPack pp, const __grid_constan
 
 template <typename T, int VEC>
 void launch_fwd(int ns, dim3 grid, int chunk_px, cudaStream_t st, const PtrPack& pp, const float* mf, const float* mb, const Layout& L, int HW, int planes, float* loss) {
-#define PV2_FWD(NSV) pv2::launch(structure_loss_fwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, HW, planes, (int)grid.x, chunk_px, L.wt_tiles, \
+#define PV2_FWD(NSV) pv2::launch_streaming(structure_loss_fwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, HW, planes, (int)grid.x, chunk_px, L.wt_tiles, \
                          L.partials, L.wsum_part, L.plane_sums, L.plane_loss, loss, L.ticket)
     switch (ns) { case 1: PV2_FWD(1); break; case 2: PV2_FWD(2); break; case 3: PV2_FWD(3); break; default: PV2_FWD(4); break; }
 #undef PV2_FWD
 }
 template <typename T, int VEC>
 void launch_bwd(int ns, dim3 grid, cudaStream_t st, const PtrPack& pp, const float* mf, const float* mb, const Layout& L, const float* gl, int HW, int planes) {
-#define PV2_BWD(NSV) pv2::launch(structure_loss_bwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, gl, L.plane_sums, HW, planes)
+#define PV2_BWD(NSV) pv2::launch_streaming(structure_loss_bwd_kernel<T, NSV, VEC>, grid, LS_THREADS, 0, st, pp, mf, mb, L.wmap, gl, L.plane_sums, HW, planes)
     switch (ns) { case 1: PV2_BWD(1); break; case 2: PV2_BWD(2); break; case 3: PV2_BWD(3); break; default: PV2_BWD(4); break; }
 #undef PV2_BWD
 }
