@@ -12,7 +12,7 @@
 //      8 final maps of a B = 16 x 352^2 step (12.4 us).
 // bwd: two kernels.  Exact x8 / x16 / x32 / x64 half-pixel up-scalings (the final maps of a step) take bilinear_bwd2_kernel: separable
 //      in registers -- a thread folds the 4 x 4 elements of a chunk into 4 partial sums with 13 FMA per 16-byte load, 8 loads in
-//      flight, CTA = (band of input rows, plane, map), 288 CTAs in one wave -- 19.1 us on the 8 maps (51 % of the measured HBM peak;
+//      flight, CTA = (band of input rows, plane, map), 288 CTAs in one wave -- 16.2 us on the 8 maps (60 % of the measured HBM peak;
 //      the gather kernel: 28.5 us, 34 %).  Everything else (x2, x4, fractional ratios, align_corners) takes the gather kernel: CTA =
 //      (R input rows, plane, map), pass 1 folds the output rows that touch these input rows into R rows of column sums in shared
 //      memory, pass 2 folds the columns (x taps from a table, lane groups + shuffle tree).  No atomics in either, deterministic.
